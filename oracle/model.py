@@ -1,0 +1,270 @@
+"""Encoders -> cross-modal attention -> fusion -> MC-dropout, restated on CPU.
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Plain torch tensor arithmetic on CPU (matmul / exp / tanh / mean), written as
+functions over a flat state-dict (SURVEY.md Appendix A key names), so the same
+code runs in fp32 (like the reference) or fp64 (tight checker for the CUDA
+kernels).  No nn.Module, no nn.LSTM: the recurrence is written out.  Each
+function cites the reference lines it follows.  Validated against the
+reference's own modules by tests/golden/make_golden.py (run in the build
+container, where /root/reference exists); its outputs are the committed golden
+vectors that tests/test_oracle_model.py re-checks everywhere.
+
+Dropout: the reference draws masks from torch's global RNG; here every
+``nn.Dropout`` site takes its mask from the Philox spec (oracle/philox.py)
+through a ``DropCtx``.  ``ctx=None`` means eval mode (dropout is identity).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import philox as px
+
+
+@dataclass
+class DropCtx:
+    """Which masks a stochastic pass uses: (seed, pass index t, global clip ids)."""
+    seed: int
+    t: int
+    clip_ids: np.ndarray           # (B,) global clip indices
+    p_encoder: float = 0.1         # FrameEncoder dropout (configs/base.yaml:46)
+    p_fusion: float = 0.3          # model.dropout (configs/base.yaml:27)
+
+    def apply(self, x: torch.Tensor, site: int, p: float) -> torch.Tensor:
+        """nn.Dropout forward in train mode with a spec mask: x * keep / (1 - p)."""
+        if p <= 0.0:
+            return x
+        B = x.shape[0]
+        n = int(np.prod(x.shape[1:]))
+        keep = px.dropout_keep(n, self.clip_ids, self.t, site, p, self.seed).reshape(x.shape)
+        scale = torch.tensor(float(px.keep_scale(p)), dtype=torch.float32).to(x.dtype)
+        return x * (torch.from_numpy(keep).to(x.dtype) * scale)
+
+
+def _lin(x, sd, name):
+    return x @ sd[name + ".weight"].T + sd[name + ".bias"]
+
+
+def _layer_norm(x, w, b, eps=1e-5):
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)      # biased, like nn.LayerNorm
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def _softmax(x, dim=-1):
+    m = x.max(dim=dim, keepdim=True).values
+    e = torch.exp(x - m)
+    return e / e.sum(dim=dim, keepdim=True)
+
+
+def sequence_encoder_lstm(seq, sd, prefix="encoders.audio.", num_layers=2):
+    """SequenceEncoder(encoder_type='lstm').forward, lengths=None branch.
+
+    src/encoders.py:54-62 (nn.LSTM batch_first, unidirectional, zero initial
+    state), :148-155 (h_n[-1] -> projection).  nn.LSTM cell: gate order
+    i, f, g, o in the 4H rows; c' = f*c + i*g; h' = o*tanh(c').  Inter-layer
+    dropout is inactive in eval and under MC-dropout.
+    """
+    B, T, _ = seq.shape
+    x = seq
+    h = None
+    for l in range(num_layers):
+        w_ih = sd[f"{prefix}rnn.weight_ih_l{l}"]
+        w_hh = sd[f"{prefix}rnn.weight_hh_l{l}"]
+        bias = sd[f"{prefix}rnn.bias_ih_l{l}"] + sd[f"{prefix}rnn.bias_hh_l{l}"]
+        H = w_hh.shape[1]
+        xp = x @ w_ih.T + bias                      # (B, T, 4H): input part, all steps
+        h = torch.zeros(B, H, dtype=seq.dtype)
+        c = torch.zeros(B, H, dtype=seq.dtype)
+        outs = []
+        for t in range(T):
+            g = xp[:, t] + h @ w_hh.T
+            i_g = torch.sigmoid(g[:, 0 * H:1 * H])
+            f_g = torch.sigmoid(g[:, 1 * H:2 * H])
+            g_g = torch.tanh(g[:, 2 * H:3 * H])
+            o_g = torch.sigmoid(g[:, 3 * H:4 * H])
+            c = f_g * c + i_g * g_g
+            h = o_g * torch.tanh(c)
+            outs.append(h)
+        x = torch.stack(outs, dim=1)
+    return _lin(h, sd, prefix + "projection")
+
+
+def frame_hidden(frames, sd, prefix="encoders.video."):
+    """frame_mlp[0:2]: Linear(frame_dim -> H) + ReLU, before dropout.  src/encoders.py:225-227,272."""
+    return torch.relu(_lin(frames, sd, prefix + "frame_mlp.0"))
+
+
+def frame_encoder_tail(hid, sd, prefix="encoders.video.", ctx: Optional[DropCtx] = None):
+    """FrameEncoder after the ReLU: dropout -> attention_pool -> dropout -> LN -> Linear.
+
+    src/encoders.py:228 (Dropout inside frame_mlp), :320-326 (scores, softmax over
+    frames, einsum 'bt,bth->bh'; mask=None on the hot path, src/train.py:136),
+    :296 (_dropout), :246-249,297 (LayerNorm + Linear).
+    """
+    x = hid
+    if ctx is not None:
+        x = ctx.apply(x, px.SITE_FRAME_MLP, ctx.p_encoder)
+    scores = (x @ sd[prefix + "attention.weight"].T + sd[prefix + "attention.bias"]).squeeze(-1)
+    w = _softmax(scores, dim=1)
+    pooled = (w.unsqueeze(-1) * x).sum(dim=1)
+    if ctx is not None:
+        pooled = ctx.apply(pooled, px.SITE_FRAME_POOL, ctx.p_encoder)
+    y = _layer_norm(pooled, sd[prefix + "projection.0.weight"], sd[prefix + "projection.0.bias"])
+    return _lin(y, sd, prefix + "projection.1")
+
+
+def frame_encoder(frames, sd, prefix="encoders.video.", ctx: Optional[DropCtx] = None):
+    """FrameEncoder.forward(frames, mask=None), temporal_pooling='attention'.  src/encoders.py:253-297."""
+    return frame_encoder_tail(frame_hidden(frames, sd, prefix), sd, prefix, ctx)
+
+
+def cross_modal_attention(query, key, value, invalid, sd, prefix, num_heads=4,
+                          ctx: Optional[DropCtx] = None, site: int = px.SITE_ATTN,
+                          p: float = 0.0):
+    """CrossModalAttention.forward.  src/attention.py:80-141.
+
+    query (B,Tq,Dq), key/value (B,Tk,Dk); invalid (B,Tk) bool (True = masked key)
+    or None.  Returns (out (B,Tq,D) or (B,D) when Tq == 1, attn (B,heads,Tq,Tk)).
+    """
+    if query.dim() == 2:
+        query = query.unsqueeze(1)
+    if key.dim() == 2:
+        key = key.unsqueeze(1)
+    if value.dim() == 2:
+        value = value.unsqueeze(1)
+    B, Tq, _ = query.shape
+    Tk = key.shape[1]
+    q = _layer_norm(query, sd[prefix + "q_in_ln.weight"], sd[prefix + "q_in_ln.bias"])   # :97
+    k = _layer_norm(key, sd[prefix + "k_in_ln.weight"], sd[prefix + "k_in_ln.bias"])     # :98
+    v = _layer_norm(value, sd[prefix + "v_in_ln.weight"], sd[prefix + "v_in_ln.bias"])   # :99
+    Q = _lin(q, sd, prefix + "q_proj")
+    K = _lin(k, sd, prefix + "k_proj")
+    V = _lin(v, sd, prefix + "v_proj")
+    D = Q.shape[-1]
+    dh = D // num_heads
+    Q = Q.view(B, Tq, num_heads, dh).transpose(1, 2)
+    K = K.view(B, Tk, num_heads, dh).transpose(1, 2)
+    V = V.view(B, Tk, num_heads, dh).transpose(1, 2)
+    scores = (Q @ K.transpose(-2, -1)) * (1.0 / math.sqrt(dh))                          # :112
+    if invalid is not None:
+        scores = scores.masked_fill(invalid[:, None, None, :], -1e4)                    # :115-118
+    attn = _softmax(scores, dim=-1)                                                     # :121
+    if invalid is not None:
+        all_masked = invalid.all(dim=-1)                                                # :124-128
+        if all_masked.any():
+            attn = attn.clone()
+            attn[all_masked] = 0.0
+    if ctx is not None:
+        attn = ctx.apply(attn, site, p)                                                 # :130
+    context = (attn @ V).transpose(1, 2).contiguous().view(B, Tq, D)                    # :133-136
+    out = _lin(context, sd, prefix + "out_proj")                                        # :137
+    if Tq == 1:
+        out = out.squeeze(1)                                                            # :140
+    return out, attn
+
+
+def hybrid_fusion(feats: Dict[str, torch.Tensor], mask, sd, prefix="fusion_model.",
+                  modalities: Sequence[str] = ("audio", "video"), num_heads=4,
+                  ctx: Optional[DropCtx] = None, return_info=False):
+    """HybridFusion.forward.  src/fusion.py:455-530 (all modalities present)."""
+    ref = feats[modalities[0]]
+    B = ref.shape[0]
+    M = len(modalities)
+    if mask is None:
+        mask_f = torch.ones(B, M, dtype=torch.float32)
+    else:
+        mask_f = torch.as_tensor(mask).float()
+    invalid = mask_f <= 0                                                               # :474
+    Z = torch.stack([_lin(feats[m], sd, f"{prefix}proj_layers.{m}") for m in modalities], dim=1)
+    Z = _layer_norm(Z, sd[prefix + "pre_ln.weight"], sd[prefix + "pre_ln.bias"])        # :490-491
+    p = ctx.p_fusion if ctx is not None else 0.0
+    att, attn_w = [], []
+    for i, m in enumerate(modalities):
+        out, a = cross_modal_attention(Z[:, i:i + 1, :], Z, Z, invalid, sd,
+                                       f"{prefix}attn_layers.{m}.", num_heads, ctx,
+                                       px.SITE_ATTN + i, p)                             # :497-500
+        out = _layer_norm(out + Z[:, i, :], sd[prefix + "post_ln.weight"],
+                          sd[prefix + "post_ln.bias"])                                  # :502
+        att.append(out)
+        attn_w.append(a)
+    H_att = torch.stack(att, dim=1)                                                     # :508
+    g = torch.relu(_lin(H_att, sd, prefix + "fusion_gate.0"))                           # :445-447
+    if ctx is not None:
+        g = ctx.apply(g, px.SITE_GATE, p)                                               # :448
+    scores = _lin(g, sd, prefix + "fusion_gate.3").squeeze(-1)                          # :449,511
+    scores = scores.masked_fill(invalid, -1e4)                                          # :513
+    w = _softmax(scores, dim=-1)                                                        # :514
+    w = torch.where(torch.isfinite(w), w, torch.zeros_like(w))                          # :516
+    w = w / w.sum(dim=-1, keepdim=True).clamp_min(1e-8)                                 # :517-518
+    fused = (w.unsqueeze(-1) * H_att).sum(dim=1)                                        # :521
+    logits = _lin(fused, sd, prefix + "classifier")                                     # :522
+    if return_info:
+        return logits, {"fusion_weights": w, "per_modality_attention": attn_w, "H_att": H_att}
+    return logits
+
+
+def baseline_head(z_list, sd, prefix="fusion_head."):
+    """Live path of MultimodalFusionModule.forward: concat -> Linear -> ReLU -> Linear.
+
+    src/train.py:81-85 (ctor), :153-164 (forward; mask ignored).
+    """
+    fused = torch.cat(list(z_list), dim=-1)
+    return _lin(torch.relu(_lin(fused, sd, prefix + "0")), sd, prefix + "2")
+
+
+def av_forward(feats, frames, mask, sd, head="hybrid", ctx: Optional[DropCtx] = None,
+               z_audio=None, hid=None):
+    """encoders -> head, composed as src/train.py:133-136 + :138-147 (hybrid, the
+    commented-out composition) or :153-164 (concat baseline, the live one).
+
+    z_audio / hid let the caller pass the pass-invariant parts.
+    """
+    if z_audio is None:
+        z_audio = sequence_encoder_lstm(feats, sd)
+    if hid is None:
+        hid = frame_hidden(frames, sd)
+    z_video = frame_encoder_tail(hid, sd, ctx=ctx)
+    if head == "hybrid":
+        return hybrid_fusion({"audio": z_audio, "video": z_video}, mask, sd, ctx=ctx)
+    return baseline_head([z_audio, z_video], sd)
+
+
+def mc_statistics(logits_stack):
+    """MCDropoutUncertainty.forward after the T passes.  src/uncertainty.py:74-84:
+    mean of LOGITS over passes; POPULATION variance of softmax PROBABILITIES over
+    passes, averaged over classes."""
+    mean_logits = logits_stack.mean(dim=0)
+    probs = _softmax(logits_stack, dim=-1)
+    var = ((probs - probs.mean(dim=0, keepdim=True)) ** 2).mean(dim=0)
+    return mean_logits, var.mean(dim=-1)
+
+
+def mc_dropout_forward(feats, frames, mask, sd, T, seed, clip_ids, head="hybrid",
+                       p_encoder=0.1, p_fusion=0.3):
+    """MCDropoutUncertainty(model, T).forward(features, mask).  src/uncertainty.py:48-86.
+
+    The reference recomputes the whole model T times; the audio encoder and the
+    video Linear+ReLU contain no active nn.Dropout, so they are
+    computed once here - same values, T times less CPU work.
+    Returns (mean_logits (B,C), uncertainty (B,), logits_stack (T,B,C)).
+    """
+    z_audio = sequence_encoder_lstm(feats, sd)
+    hid = frame_hidden(frames, sd)
+    stack = []
+    for t in range(T):
+        ctx = DropCtx(seed=seed, t=t, clip_ids=np.asarray(clip_ids), p_encoder=p_encoder,
+                      p_fusion=p_fusion)
+        stack.append(av_forward(None, None, mask, sd, head, ctx, z_audio=z_audio, hid=hid))
+    stack = torch.stack(stack, dim=0)
+    mean_logits, unc = mc_statistics(stack)
+    return mean_logits, unc, stack
+
+
+def to_torch(sd_np, dtype=torch.float32):
+    return {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in sd_np.items()}

@@ -1,0 +1,216 @@
+#!/usr/bin/env python
+"""Generate the golden vectors in tests/golden/ by running the REFERENCE's own modules.
+
+Runs only in the build container, where /root/reference exists (it cannot travel
+to the GPU box).  Imports encoders / attention / fusion / uncertainty from
+/root/reference/src (flat imports, like src/train.py:28-31), composes them the
+way MultimodalFusionModule does (src/train.py:41-85 ctor, :121-164 forward, and
+the commented hybrid composition :138-147), loads the seeded synthetic weights
+with strict=True (proving the state-dict layout of SURVEY.md Appendix A), and
+records outputs on seeded synthetic inputs.
+
+Dropout: every nn.Dropout instance of the reference model is given a forward that
+multiplies by the Philox spec mask (oracle/philox.py) instead of torch's global
+mt19937 stream; the reference's MCDropoutUncertainty then runs UNMODIFIED on top.
+
+It also checks oracle/model.py (the restatement that travels) against the
+reference modules and prints the max differences.
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/src")
+sys.dont_write_bytecode = True
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+import encoders as ref_encoders          # /root/reference/src/encoders.py
+import fusion as ref_fusion              # /root/reference/src/fusion.py
+import uncertainty as ref_uncertainty    # /root/reference/src/uncertainty.py
+
+from oracle import frontend as ofe, model as om, philox as px, synth
+
+SEED = 42
+CLIP_IDS = np.array([0, 1, 2, 3, 1000003, 4294967295], dtype=np.uint64)
+T_MC = 8
+MODALITIES = ["audio", "video"]
+ENC_CFG = {   # configs/base.yaml:30-47 with the BASELINE.json input dims
+    "audio": {"type": "sequence", "input_dim": 104, "encoder_type": "lstm", "hidden_dim": 256,
+              "output_dim": 128, "num_layers": 2, "dropout": 0.1},
+    "video": {"type": "frame", "input_dim": 12544, "temporal_pooling": "attention",
+              "hidden_dim": 256, "output_dim": 128, "dropout": 0.1},
+}
+
+
+class RefAVModel(nn.Module):
+    """MultimodalFusionModule without Lightning: src/train.py:50-85 and :121-164."""
+
+    def __init__(self, head):
+        super().__init__()
+        self.head = head
+        self.encoders = nn.ModuleDict()
+        dims = {}
+        for m in MODALITIES:                                   # train.py:55-66
+            cfg = ENC_CFG[m]
+            self.encoders[m] = ref_encoders.build_encoder(
+                modality=m, input_dim=cfg.get("input_dim", 64), output_dim=128, encoder_config=cfg)
+            dims[m] = 128
+        self.fusion_model = ref_fusion.build_fusion_model(     # train.py:69-76 (commented there)
+            fusion_type="hybrid", modality_dims=dims, num_classes=8, hidden_dim=256,
+            num_heads=4, dropout=0.3)
+        self.fusion_head = nn.Sequential(                      # train.py:81-85
+            nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 8))
+
+    def forward(self, features, mask=None):
+        enc = {m: e(features[m]) for m, e in self.encoders.items() if m in features}  # :134-136
+        if self.head == "hybrid":
+            out = self.fusion_model(enc, mask)                 # :139
+            return out[0] if isinstance(out, tuple) else out   # :142-145
+        fused = torch.cat([enc[m] for m in MODALITIES if m in enc], dim=-1)           # :153-161
+        return self.fusion_head(fused)                         # :163
+
+
+class MaskInjector:
+    """Gives each nn.Dropout of the reference model its Philox spec mask."""
+
+    SITES = {
+        "encoders.video.frame_mlp.2": px.SITE_FRAME_MLP,
+        "encoders.video._dropout": px.SITE_FRAME_POOL,
+        "fusion_model.attn_layers.audio.attn_dropout": px.SITE_ATTN + 0,
+        "fusion_model.attn_layers.video.attn_dropout": px.SITE_ATTN + 1,
+        "fusion_model.fusion_gate.2": px.SITE_GATE,
+    }
+
+    def __init__(self, model, seed, clip_ids):
+        self.seed, self.clip_ids, self.t = seed, clip_ids, -1
+        model.register_forward_pre_hook(self._bump)
+        found = {n for n, m in model.named_modules() if isinstance(m, nn.Dropout)}
+        assert found == set(self.SITES), (found, set(self.SITES))
+        for name, mod in model.named_modules():
+            if isinstance(mod, nn.Dropout):
+                mod.forward = self._make_forward(mod, self.SITES[name])
+
+    def _bump(self, *_):
+        self.t += 1
+
+    def _make_forward(self, mod, site):
+        def fwd(x):
+            if not mod.training or mod.p <= 0:
+                return x
+            n = int(np.prod(x.shape[1:]))
+            keep = px.dropout_keep(n, self.clip_ids, self.t, site, mod.p, self.seed).reshape(x.shape)
+            return x * (torch.from_numpy(keep).float() * float(px.keep_scale(mod.p)))
+        return fwd
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    sd_np = synth.synth_weights(SEED)
+    sd = om.to_torch(sd_np)
+    wave = synth.synth_audio(CLIP_IDS, SEED)
+    frames_u8 = synth.synth_video_u8(CLIP_IDS, SEED)
+    frames = torch.from_numpy(frames_u8.astype(np.float32) / np.float32(255.0))
+    feats_np = ofe.logmel_mfcc(wave)                       # oracle front-end (no reference exists)
+    feats = torch.from_numpy(feats_np)
+    B = len(CLIP_IDS)
+    masks = {
+        "ones": torch.ones(B, 2),
+        "mixed": torch.tensor([[1, 1], [1, 0], [0, 1], [0, 0], [1, 1], [0, 1]], dtype=torch.float32),
+        "p05": torch.from_numpy(px.modality_mask(CLIP_IDS, 2, 0.05, SEED)),
+    }
+
+    out = {"clip_ids": CLIP_IDS, "seed": np.int64(SEED), "t_mc": np.int64(T_MC)}
+    # front-end anchors (oracle's own output, stored so drift in the oracle is caught)
+    out["feats_clip0"] = feats_np[0]
+    out["feats_last"] = feats_np[-1]
+    worst = {}
+
+    def rec(name, ref_t, ora_t):
+        ref_t = ref_t.detach()
+        out[name] = ref_t.numpy()
+        d = (ref_t.double() - ora_t.double()).abs().max().item()
+        s = ref_t.abs().max().item()
+        worst[name] = (d, s)
+
+    for head in ("hybrid", "concat"):
+        model = RefAVModel(head)
+        full = {k: v for k, v in sd.items()}
+        missing = model.load_state_dict(full, strict=True)       # layout check, Appendix A
+        model.eval()
+        inj = MaskInjector(model, SEED, CLIP_IDS)
+        with torch.inference_mode():
+            z_a = model.encoders["audio"](feats)
+            z_v = model.encoders["video"](frames)
+            if head == "hybrid":
+                rec("z_audio", z_a, om.sequence_encoder_lstm(feats, sd))
+                rec("z_video", z_v, om.frame_encoder(frames, sd))
+            for mname, mask in masks.items():
+                if head == "concat" and mname != "ones":
+                    continue                                     # mask ignored on the live path
+                logits = model({"audio": feats, "video": frames}, mask.clone())
+                rec(f"logits_{head}_{mname}", logits,
+                    om.av_forward(feats, frames, mask, sd, head))
+                if head == "hybrid":
+                    lg, info = model.fusion_model({"audio": z_a, "video": z_v}, mask.clone(),
+                                                  return_attention=True)
+                    _, oinfo = om.hybrid_fusion({"audio": z_a, "video": z_v}, mask, sd,
+                                                return_info=True)
+                    rec(f"fusion_weights_{mname}", info["fusion_weights"], oinfo["fusion_weights"])
+                    rec(f"attn_audio_{mname}", info["per_modality_attention"]["audio"],
+                        oinfo["per_modality_attention"][0])
+                    rec(f"attn_video_{mname}", info["per_modality_attention"]["video"],
+                        oinfo["per_modality_attention"][1])
+        # MC-dropout: the reference wrapper, unmodified, over the mask-injected model
+        for mname in (("ones", "p05") if head == "hybrid" else ("ones",)):
+            mask = masks[mname]
+            inj.t = -1
+            mc = ref_uncertainty.MCDropoutUncertainty(model, num_samples=T_MC)
+            mean_logits, unc = mc({"audio": feats, "video": frames}, mask.clone())
+            o_mean, o_unc, o_stack = om.mc_dropout_forward(feats, frames, mask, sd, T_MC, SEED,
+                                                           CLIP_IDS, head)
+            rec(f"mc_mean_logits_{head}_{mname}", mean_logits, o_mean)
+            rec(f"mc_uncertainty_{head}_{mname}", unc, o_unc)
+            out[f"mc_labels_{head}_{mname}"] = mean_logits.argmax(dim=1).numpy()
+            assert (mean_logits.argmax(dim=1) == o_mean.argmax(dim=1)).all()
+
+    # standalone CrossModalAttention at the reference's own smoke shapes
+    # (src/attention.py:605-651: (4,512) x (4,64) -> (4,256)) with a sequence of keys
+    torch.manual_seed(1)
+    import attention as ref_attention
+    att = ref_attention.CrossModalAttention(query_dim=512, key_dim=64, hidden_dim=256, num_heads=4,
+                                            dropout=0.1).eval()
+    asd = {"att." + k: v for k, v in att.state_dict().items()}
+    q = torch.randn(4, 3, 512)
+    kv = torch.randn(4, 5, 64)
+    inv = torch.tensor([[0, 0, 0, 0, 0], [1, 0, 0, 1, 0], [1, 1, 1, 1, 1], [0, 1, 1, 1, 1]]).bool()
+    with torch.inference_mode():
+        o, a = att(q, kv, kv, inv)
+    oo, oa = om.cross_modal_attention(q, kv, kv, inv, asd, "att.", 4)
+    for k_, v_ in asd.items():
+        out["xattn." + k_] = v_.numpy()
+    out["xattn.q"], out["xattn.kv"], out["xattn.invalid"] = q.numpy(), kv.numpy(), inv.numpy()
+    rec("xattn.out", o, oo)
+    rec("xattn.attn", a, oa)
+
+    print("reference vs oracle/model.py (max abs diff, max |ref|):")
+    bad = False
+    for k_, (d, s) in worst.items():
+        flag = "" if d <= 2e-5 * max(1.0, s) else "   <-- MISMATCH"
+        bad |= bool(flag)
+        print(f"  {k_:40s} {d:.3e}  {s:.3e}{flag}")
+    assert not bad
+    path = os.path.join(HERE, "av_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
