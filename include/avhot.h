@@ -1,0 +1,212 @@
+/* avhot.h - C ABI of libavhot.so: the B200 (sm_100a) audio-visual inference hot path.
+ *
+ * The reference (parshva-mehta/multimodal-emotion-detection) is pure Python and has
+ * no FFI of its own; its "operator interface" for this path is the set of Python
+ * callables cited beside each entry point below (paths relative to the reference
+ * root).  The Python drop-in modules in multimodal-emotion-detection_b200/ keep
+ * those signatures and bind these symbols with ctypes (see INTEGRATION.md for the
+ * stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every pointer argument is a DEVICE pointer unless its name ends in _host;
+ *    fp32, row-major, contiguous, in the reference's own tensor layouts;
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and
+ *    never synchronise the host.  Only *_create allocates (device memory owned by
+ *    the handle, released by *_destroy); the forward calls use caller workspaces;
+ *  - return value: AVHOT_OK or a negative avhot_status; avhot_last_error() gives the
+ *    message for the calling thread.  The Python layer raises ValueError for
+ *    AVHOT_ERR_INVALID / AVHOT_ERR_UNSUPPORTED (the reference raises ValueError /
+ *    assert for bad shapes: src/encoders.py:115,242,636; src/attention.py:34,74-76;
+ *    src/fusion.py:696) and RuntimeError for AVHOT_ERR_CUDA;
+ *  - one host thread per device, like the reference's callers (src/train.py:133-136).
+ */
+#ifndef AVHOT_H_
+#define AVHOT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVHOT_VERSION 100 /* 0.1.0 */
+
+typedef void* avhot_stream_t; /* cudaStream_t */
+
+typedef enum {
+  AVHOT_OK = 0,
+  AVHOT_ERR_INVALID = -1,     /* bad argument / shape                      */
+  AVHOT_ERR_UNSUPPORTED = -2, /* valid in the reference, not built here    */
+  AVHOT_ERR_CUDA = -3,        /* CUDA runtime error (see avhot_last_error) */
+  AVHOT_ERR_WORKSPACE = -4    /* caller workspace too small                */
+} avhot_status;
+
+/* arithmetic of the dense contractions (GEMM operands); accumulation is fp32 and
+ * everything outside the contractions is fp32 in every mode. */
+typedef enum {
+  AVHOT_PREC_FP32 = 0,   /* fp32 FMA on CUDA cores (bit-for-bit deterministic)        */
+  AVHOT_PREC_BF16X3 = 1, /* tcgen05, operands split hi+lo bf16, 3 MMAs: fp32-class    */
+  AVHOT_PREC_BF16 = 2    /* tcgen05, operands rounded to bf16 once: stated tolerance  */
+} avhot_precision;
+
+int avhot_version(void);
+const char* avhot_last_error(void);
+/* cudaGetDeviceProperties of the current device: fails unless it is sm_100. */
+int avhot_check_device(void);
+
+/* ---- Philox-4x32-10 spec (oracle/philox.py) ------------------------------------ */
+/* keep[b*n_elems + e] = 1 iff words(e>>2, clip0+b, t, site)[e&3] >= floor(p*2^32).
+ * Test/diagnostic entry: the masks the fused kernels apply at the nn.Dropout sites
+ * of src/encoders.py:228,230; src/attention.py:51; src/fusion.py:448. */
+int avhot_dropout_keep(uint8_t* keep, int B, int n_elems, uint64_t clip0, uint32_t t,
+                       uint32_t site, float p, uint64_t seed, avhot_stream_t stream);
+/* src/data.py:108-118  modality dropout: mask (B, M) fp32, 1 = available. */
+int avhot_modality_mask(float* mask, int B, int M, uint64_t clip0, float p, uint64_t seed,
+                        avhot_stream_t stream);
+
+/* ---- synthetic RAVDESS-shaped inputs (oracle/synth.py), bit-exact with the oracle -- */
+int avhot_synth_audio(float* wave, int B, int n_samples, uint64_t clip0, uint64_t seed,
+                      avhot_stream_t stream);
+/* exactly one of frames_f32 / frames_u8 may be NULL */
+int avhot_synth_video(float* frames_f32, uint8_t* frames_u8, int B, int n_elems_per_clip,
+                      uint64_t clip0, uint64_t seed, avhot_stream_t stream);
+
+/* ---- a1: src/dataprocessing.py:198-211  load_raw_audio post-conditions ------------ */
+/* out[b, :] = first min(len_b, n_out) samples of in[b, :], right zero padded to n_out,
+ * divided by max|.| when that is > 0.  lengths may be NULL (= in_stride). */
+int avhot_condition_audio(const float* in, const int32_t* lengths, float* out, int B,
+                          int in_stride, int n_out, avhot_stream_t stream);
+
+/* ---- a2: log-mel + MFCC front-end (no reference code; spec in oracle/frontend.py) --- */
+/* wave (B, n_samples) -> feats (B, 1 + n_samples/160, 104) = [64 log-mel | 40 MFCC]. */
+int avhot_frontend(const float* wave, float* feats, int B, int n_samples,
+                   avhot_stream_t stream);
+/* the fp32 tables the kernel uses, copied to HOST buffers (any may be NULL):
+ * mel (64, 257), dct (40, 64), window (512). */
+int avhot_frontend_tables_host(float* mel_host, float* dct_host, float* window_host);
+
+/* ---- a3: src/encoders.py:15-155  SequenceEncoder(encoder_type='lstm') -------------- */
+typedef struct avhot_lstm* avhot_lstm_t;
+typedef struct {
+  int input_dim, hidden_dim, num_layers, output_dim; /* ctor args, src/encoders.py:23-31 */
+  const float* weight_ih[4];                         /* rnn.weight_ih_l{k} (4H, in_k)    */
+  const float* weight_hh[4];                         /* rnn.weight_hh_l{k} (4H, H)       */
+  const float* bias_ih[4];                           /* rnn.bias_ih_l{k}   (4H)          */
+  const float* bias_hh[4];                           /* rnn.bias_hh_l{k}   (4H)          */
+  const float* proj_weight;                          /* projection.weight (out, H)       */
+  const float* proj_bias;                            /* projection.bias   (out)          */
+} avhot_lstm_desc;
+int avhot_lstm_create(const avhot_lstm_desc* desc, avhot_lstm_t* out, avhot_stream_t stream);
+void avhot_lstm_destroy(avhot_lstm_t h);
+size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int precision);
+/* forward(sequence (B,T,input_dim), lengths) -> (B, output_dim).  src/encoders.py:137-155.
+ * lengths: (B) int32 valid steps per clip (the packed-sequence branch, :139-147: h_n is the
+ * state after step lengths[b]), or NULL (every clip runs T steps, :148-154). */
+int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_t* lengths, float* out,
+                       int B, int T, int precision, void* workspace, size_t workspace_bytes,
+                       avhot_stream_t stream);
+
+/* ---- a4: src/encoders.py:196-327  FrameEncoder(temporal_pooling='attention') -------- */
+typedef struct avhot_frame* avhot_frame_t;
+typedef struct {
+  int frame_dim, hidden_dim, output_dim; /* ctor args, src/encoders.py:203-210 */
+  const float* mlp_weight;               /* frame_mlp.0.weight (H, frame_dim)  */
+  const float* mlp_bias;                 /* frame_mlp.0.bias   (H)             */
+  const float* attn_weight;              /* attention.weight   (1, H)          */
+  const float* attn_bias;                /* attention.bias     (1)             */
+  const float* ln_weight;                /* projection.0.weight (H)            */
+  const float* ln_bias;                  /* projection.0.bias   (H)            */
+  const float* proj_weight;              /* projection.1.weight (out, H)       */
+  const float* proj_bias;                /* projection.1.bias   (out)          */
+} avhot_frame_desc;
+int avhot_frame_create(const avhot_frame_desc* desc, avhot_frame_t* out, avhot_stream_t stream);
+void avhot_frame_destroy(avhot_frame_t h);
+size_t avhot_frame_workspace_bytes(avhot_frame_t h, int B, int F, int precision);
+/* frame_mlp[0:2] = Linear + ReLU (src/encoders.py:225-227,272): frames (B*F, frame_dim)
+ * fp32, or u8 pixels k meaning k/255 (src/dataprocessing.py:261-265) when frames_u8 is
+ * given instead -> hid (B*F, H).  Pass-invariant under MC-dropout. */
+int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, const uint8_t* frames_u8,
+                       float* hid, int B, int F, int precision, void* workspace,
+                       size_t workspace_bytes, avhot_stream_t stream);
+/* the rest of forward (src/encoders.py:228,274-297,320-326): dropout -> attention_pool ->
+ * dropout -> LayerNorm -> Linear, for T passes: z (B, T, out).  T = 1 with p = 0 is eval
+ * mode.  Pass t of clip b uses Philox masks (seed, t0 + t, clip0 + b).  frame_valid: (B, F)
+ * bytes, 1 = valid frame (forward's `mask`, src/encoders.py:321-324), or NULL (the hot path,
+ * src/train.py:136). */
+int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z,
+                     int B, int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                     avhot_stream_t stream);
+
+/* ---- a5: src/attention.py:14-141  CrossModalAttention (general shapes) ------------- */
+typedef struct avhot_xattn* avhot_xattn_t;
+typedef struct {
+  int query_dim, key_dim, hidden_dim, num_heads; /* ctor args, src/attention.py:31-32 */
+  const float *q_ln_w, *q_ln_b, *k_ln_w, *k_ln_b, *v_ln_w, *v_ln_b;
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
+} avhot_xattn_desc;
+int avhot_xattn_create(const avhot_xattn_desc* desc, avhot_xattn_t* out, avhot_stream_t stream);
+void avhot_xattn_destroy(avhot_xattn_t h);
+/* forward(query (B,Tq,Dq), key (B,Tk,Dk), value (B,Tk,Dk), mask) -> out (B,Tq,D),
+ * attn (B,heads,Tq,Tk).  invalid: (B,Tk) bytes, 1 = masked key, or NULL.  Dropout on the
+ * attention weights when p > 0 (site AVHOT_SITE_ATTN + site_index). Tk <= 64. */
+size_t avhot_xattn_workspace_bytes(avhot_xattn_t h, int B, int Tq, int Tk);
+int avhot_xattn_forward(avhot_xattn_t h, const float* query, const float* key,
+                        const float* value, const uint8_t* invalid, float* out, float* attn,
+                        int B, int Tq, int Tk, float p, uint64_t seed, uint64_t clip0,
+                        uint32_t t, uint32_t site_index, void* workspace,
+                        size_t workspace_bytes, avhot_stream_t stream);
+
+/* ---- a6 + a7: src/fusion.py:404-530 HybridFusion; src/train.py:78-85,153-164 head --- */
+typedef struct avhot_fusion* avhot_fusion_t;
+#define AVHOT_MAX_MODALITIES 4
+typedef struct {
+  int num_modalities, hidden_dim, num_heads, num_classes, gate_hidden;
+  int modality_dim[AVHOT_MAX_MODALITIES];            /* modality_dims values, in key order */
+  const float* proj_w[AVHOT_MAX_MODALITIES];         /* proj_layers.<m>.weight (D, dim_m)  */
+  const float* proj_b[AVHOT_MAX_MODALITIES];
+  avhot_xattn_desc attn[AVHOT_MAX_MODALITIES];       /* attn_layers.<m>.*                  */
+  const float *pre_ln_w, *pre_ln_b, *post_ln_w, *post_ln_b;
+  const float *gate0_w, *gate0_b, *gate3_w, *gate3_b; /* fusion_gate.0 (G,D), .3 (1,G)     */
+  const float *cls_w, *cls_b;                         /* classifier (C, D)                 */
+} avhot_fusion_desc;
+typedef struct {
+  int in_dim, hidden_dim, num_classes;               /* fusion_head: Linear-ReLU-Linear    */
+  const float *w0, *b0, *w2, *b2;
+} avhot_head_desc;
+/* exactly one of fusion / head is non-NULL: hybrid (src/train.py:138-147 composition) or
+ * the live concat baseline (src/train.py:153-164). */
+int avhot_fusion_create(const avhot_fusion_desc* fusion, const avhot_head_desc* head,
+                        avhot_fusion_t* out, avhot_stream_t stream);
+void avhot_fusion_destroy(avhot_fusion_t h);
+/* logits for R = B*T rows.  z[m] points at modality m's embeddings; row (b, t) reads
+ * z[m] + (b * z_rows_per_clip[m] + (z_rows_per_clip[m] == 1 ? 0 : t)) * dim_m, so a
+ * pass-invariant modality passes 1 row per clip and a stochastic one passes T.
+ * mask (B, M) fp32 1 = available, or NULL.  Optional outputs (may be NULL):
+ * fusion_weights (R, M), attn (M, R, heads, M), h_att (R, M, D).
+ * Dropout (p > 0): attention weights (site ATTN+i) and gate hidden (site GATE). */
+int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
+                         const int* z_rows_per_clip_host, const float* mask, float* logits,
+                         float* fusion_weights, float* attn, float* h_att, int B, int T,
+                         float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                         avhot_stream_t stream);
+
+/* ---- a8: src/uncertainty.py:17-86  MCDropoutUncertainty statistics ------------------ */
+/* logits (B, T, C) -> mean_logits (B, C), uncertainty (B) = mean_c Var_t softmax (population
+ * variance, src/uncertainty.py:77-84), labels (B) = argmax mean_logits (first max wins,
+ * like torch.argmax).  packed (B, C+1) = [mean_logits | uncertainty] for the all-gather
+ * (any output may be NULL). */
+int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
+                    int32_t* labels, float* packed, int B, int T, int C,
+                    avhot_stream_t stream);
+
+#define AVHOT_SITE_FRAME_MLP 0u
+#define AVHOT_SITE_FRAME_POOL 1u
+#define AVHOT_SITE_GATE 2u
+#define AVHOT_SITE_MODMASK 3u
+#define AVHOT_SITE_ATTN 16u
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVHOT_H_ */

@@ -1,0 +1,125 @@
+// Shared helpers for libavhot (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/avhot.h"
+
+namespace avhot {
+
+void set_error(const char* fmt, ...);
+
+#define AVHOT_REQUIRE(cond, code, ...)     \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::avhot::set_error(__VA_ARGS__);     \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+#define AVHOT_CUDA(call)                                                                \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::avhot::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
+                         cudaGetErrorString(e__));                                      \
+      return AVHOT_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+#define AVHOT_LAUNCH_CHECK()                                                            \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) {                                                           \
+      ::avhot::set_error("%s:%d launch -> %s", __FILE__, __LINE__,                     \
+                         cudaGetErrorString(e__));                                      \
+      return AVHOT_ERR_CUDA;                                                            \
+    }                                                                                   \
+  } while (0)
+
+static inline cudaStream_t as_stream(avhot_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int num_sms();
+// core.cu
+int transpose(const float* src, float* dst, int R, int C, cudaStream_t s);   // dst[c][r] = src[r][c]
+int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
+// gemm.cu: C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); fp32 FMA on CUDA cores.
+// Exactly one of a_f32 / a_u8 is non-NULL (u8 pixel k means fp32(k)/255).  K % 4 == 0.
+enum { ACT_NONE = 0, ACT_RELU = 1 };
+int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, int ldw,
+             const float* bias, float* c, int ldc, int M, int N, int K, int act, cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// Philox-4x32-10 (oracle/philox.py is the written spec; Random123 algorithm).
+// ---------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+#else
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, uint32_t i) {
+  return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
+}
+
+// floor(p * 2^32) clamped to uint32: an element is kept iff word >= threshold.
+static inline uint32_t drop_threshold(float p) {
+  double v = (double)p * 4294967296.0;
+  if (v <= 0.0) return 0u;
+  if (v >= 4294967295.0) return 0xFFFFFFFFu;
+  return (uint32_t)v;
+}
+// nn.Dropout's multiplier in fp32: 1 / (1 - p)
+static inline float keep_scale(float p) { return 1.0f / (1.0f - p); }
+
+struct DropSpec {  // what a kernel needs to draw the masks of one launch
+  uint32_t k0, k1;       // seed
+  uint32_t thr;          // drop threshold (0 => dropout off)
+  float scale;           // 1/(1-p)
+  uint64_t clip0;        // global index of clip 0 of this launch
+  uint32_t t0;           // pass index of pass 0 of this launch
+};
+static inline DropSpec make_drop(float p, uint64_t seed, uint64_t clip0, uint32_t t0) {
+  DropSpec d;
+  d.k0 = (uint32_t)seed;
+  d.k1 = (uint32_t)(seed >> 32);
+  d.thr = p > 0.f ? drop_threshold(p) : 0u;
+  d.scale = p > 0.f ? keep_scale(p) : 1.0f;
+  d.clip0 = clip0;
+  d.t0 = t0;
+  return d;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace avhot

@@ -1,0 +1,245 @@
+// a4: FrameEncoder(temporal_pooling='attention')  (src/encoders.py:203-251 ctor, :253-297 forward,
+// :300-327 attention_pool).
+//
+//   frames (B, F, frame_dim) -> Linear + ReLU -> [Dropout] -> scores = Linear(H -> 1) -> softmax over F
+//       -> weighted sum -> [Dropout] -> LayerNorm(H) -> Linear(H -> out)              = (B, out)
+//
+// Split at the only place the stochastic passes differ:
+//   avhot_frame_hidden   Linear + ReLU, pass-invariant, the 102.8 MFLOP/clip contraction (gemm.cu);
+//   avhot_frame_tail     everything after the ReLU for T passes.  One CTA = 32 rows (clip, pass);
+//                        one warp per row streams the (F, H) activations once with an online
+//                        softmax (Philox keep bits drawn in registers, lane <-> 2 x 4 consecutive
+//                        columns = 2 Philox blocks per frame), then LayerNorm by warp shuffles;
+//                        the 32 normalised rows are staged in shared memory and the H -> out
+//                        projection runs as one 32-row tile so the weights are read once per CTA.
+#include <float.h>
+
+#include "common.cuh"
+
+struct avhot_frame {
+  int frame_dim, hidden_dim, output_dim;
+  float* mlp_w;     // (H, frame_dim)
+  float* mlp_b;     // (H)
+  float* attn_w;    // (H)
+  float* attn_b;    // (1)
+  float* ln_w;      // (H)
+  float* ln_b;      // (H)
+  float* proj_wt;   // [j][o] = projection.1.weight[o][j]
+  float* proj_b;    // (out)
+  float* arena;
+};
+
+namespace avhot {
+
+constexpr int FH = 256;         // hidden size this kernel is specialised for
+constexpr int FT_ROWS = 32;     // rows (clip, pass) per CTA
+constexpr int FT_WARPS = 8;
+
+__global__ void __launch_bounds__(FT_WARPS * 32)
+frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, pre-dropout
+                  const uint8_t* __restrict__ valid,    // (B, F) 1 = valid frame, or NULL
+                  float* __restrict__ z,                // (B, T, out)
+                  const float* __restrict__ attn_w, const float* __restrict__ attn_b,
+                  const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  const float* __restrict__ proj_wt, const float* __restrict__ proj_b,
+                  int B, int F, int T, int out_dim, DropSpec ds) {
+  __shared__ __align__(16) float ys[FH][FT_ROWS];   // normalised rows, [j][r]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_rows = (long long)B * T;
+  const long long row0 = (long long)blockIdx.x * FT_ROWS;
+  const int c0 = 4 * lane, c1 = 128 + 4 * lane;   // this lane's two column groups
+
+  const float4 aw0 = __ldg(reinterpret_cast<const float4*>(attn_w + c0));
+  const float4 aw1 = __ldg(reinterpret_cast<const float4*>(attn_w + c1));
+  const float ab = __ldg(attn_b);
+  const bool drop = ds.thr != 0u;
+
+  for (int i = warp; i < FT_ROWS; i += FT_WARPS) {
+    const long long row = row0 + i;
+    float y[8];
+    if (row < n_rows) {                                    // warp-uniform
+      const int b = (int)(row / T), t = (int)(row % T);
+      const uint32_t g = (uint32_t)(ds.clip0 + (uint64_t)b), pass = ds.t0 + (uint32_t)t;
+      const float* hb = hid + (size_t)b * F * FH;
+      float m = -INFINITY, denom = 0.f;
+      float pooled[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pooled[q] = 0.f;
+      for (int f = 0; f < F; ++f) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(hb + (size_t)f * FH + c0));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(hb + (size_t)f * FH + c1));
+        float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (drop) {   // site FRAME_MLP: element e = f*H + col, block e >> 2
+          const Philox4 r0 = philox4x32_10((uint32_t)(f * 64 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds.k0, ds.k1);
+          const Philox4 r1 = philox4x32_10((uint32_t)(f * 64 + 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds.k0, ds.k1);
+          const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[q] = w[q] >= ds.thr ? x[q] * ds.scale : 0.f;
+        }
+        float s = x[0] * aw0.x + x[1] * aw0.y + x[2] * aw0.z + x[3] * aw0.w +
+                  x[4] * aw1.x + x[5] * aw1.y + x[6] * aw1.z + x[7] * aw1.w;
+        s = warp_sum(s) + ab;
+        if (valid && !valid[(size_t)b * F + f]) s = -FLT_MAX;       // masked_fill(finfo.min), :322-324
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn), e = expf(s - mn);           // exp(-inf) = 0 on the first frame
+        denom = denom * corr + e;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pooled[q] = pooled[q] * corr + e * x[q];
+        m = mn;
+      }
+      const float inv = 1.f / denom;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pooled[q] *= inv;
+      if (drop) {     // site FRAME_POOL: element e = col
+        const Philox4 r0 = philox4x32_10((uint32_t)lane, g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
+        const Philox4 r1 = philox4x32_10((uint32_t)(32 + lane), g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
+        const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pooled[q] = w[q] >= ds.thr ? pooled[q] * ds.scale : 0.f;
+      }
+      // LayerNorm(H), biased variance, eps 1e-5 (nn.LayerNorm defaults)
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sum += pooled[q];
+      const float mean = warp_sum(sum) * (1.f / FH);
+      float sq = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const float d = pooled[q] - mean; sq = fmaf(d, d, sq); }
+      const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / FH) + 1e-5f);
+      const float4 lw0 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+      const float4 lw1 = __ldg(reinterpret_cast<const float4*>(ln_w + c1));
+      const float4 lb0 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
+      const float4 lb1 = __ldg(reinterpret_cast<const float4*>(ln_b + c1));
+      const float lw[8] = {lw0.x, lw0.y, lw0.z, lw0.w, lw1.x, lw1.y, lw1.z, lw1.w};
+      const float lb[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y[q] = (pooled[q] - mean) * rstd * lw[q] + lb[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y[q] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ys[c0 + q][i] = y[q]; ys[c1 + q][i] = y[4 + q]; }
+  }
+  __syncthreads();
+  // projection H -> out for the 32 rows of this CTA: thread = (output o, half of the rows)
+  const int half = tid >> 7;
+  for (int o = tid & 127; o < out_dim; o += 128) {
+    float acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < FH; ++j) {
+      const float w = __ldg(proj_wt + (size_t)j * out_dim + o);
+#pragma unroll
+      for (int r4 = 0; r4 < 16; r4 += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&ys[j][half * 16 + r4]);
+        acc[r4] = fmaf(w, v.x, acc[r4]); acc[r4 + 1] = fmaf(w, v.y, acc[r4 + 1]);
+        acc[r4 + 2] = fmaf(w, v.z, acc[r4 + 2]); acc[r4 + 3] = fmaf(w, v.w, acc[r4 + 3]);
+      }
+    }
+    const float pb = __ldg(proj_b + o);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const long long row = row0 + half * 16 + r;
+      if (row < n_rows) z[(size_t)row * out_dim + o] = acc[r] + pb;
+    }
+  }
+}
+
+static size_t align256f(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace avhot
+
+using namespace avhot;
+
+extern "C" int avhot_frame_create(const avhot_frame_desc* d, avhot_frame_t* out, avhot_stream_t stream) {
+  AVHOT_REQUIRE(d && out, AVHOT_ERR_INVALID, "frame_create: null argument");
+  AVHOT_REQUIRE(d->frame_dim > 0 && d->output_dim > 0, AVHOT_ERR_INVALID, "frame_create: bad dims");
+  AVHOT_REQUIRE(d->hidden_dim == FH, AVHOT_ERR_UNSUPPORTED,
+                "frame_create: hidden_dim=%d; this build is specialised for hidden_dim=256 "
+                "(configs/base.yaml:44)", d->hidden_dim);
+  AVHOT_REQUIRE((d->frame_dim & 3) == 0, AVHOT_ERR_UNSUPPORTED, "frame_create: frame_dim=%d must be a multiple of 4",
+                d->frame_dim);
+  AVHOT_REQUIRE(d->mlp_weight && d->mlp_bias && d->attn_weight && d->attn_bias && d->ln_weight && d->ln_bias &&
+                    d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "frame_create: tensors missing");
+  const int H = FH, O = d->output_dim;
+  const size_t sizes[8] = {(size_t)H * d->frame_dim, (size_t)H, (size_t)H, 1, (size_t)H, (size_t)H, (size_t)O * H, (size_t)O};
+  size_t total = 0;
+  for (size_t n : sizes) total += align256f(n * sizeof(float));
+  avhot_frame* h = new avhot_frame();
+  h->frame_dim = d->frame_dim; h->hidden_dim = H; h->output_dim = O;
+  h->arena = nullptr;
+  cudaError_t e = cudaMalloc(&h->arena, total);
+  if (e != cudaSuccess) {
+    delete h;
+    set_error("frame_create: cudaMalloc(%zu) -> %s", total, cudaGetErrorString(e));
+    return AVHOT_ERR_CUDA;
+  }
+  cudaStream_t s = as_stream(stream);
+  char* p = reinterpret_cast<char*>(h->arena);
+  float* dst[8];
+  for (int i = 0; i < 8; ++i) { dst[i] = reinterpret_cast<float*>(p); p += align256f(sizes[i] * sizeof(float)); }
+  h->mlp_w = dst[0]; h->mlp_b = dst[1]; h->attn_w = dst[2]; h->attn_b = dst[3];
+  h->ln_w = dst[4]; h->ln_b = dst[5]; h->proj_wt = dst[6]; h->proj_b = dst[7];
+  const float* src[8] = {d->mlp_weight, d->mlp_bias, d->attn_weight, d->attn_bias, d->ln_weight, d->ln_bias,
+                         nullptr, d->proj_bias};
+  int rc = AVHOT_OK;
+  for (int i = 0; i < 8 && rc == AVHOT_OK; ++i) {
+    if (!src[i]) continue;
+    if (cudaMemcpyAsync(dst[i], src[i], sizes[i] * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+      set_error("frame_create: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = AVHOT_ERR_CUDA;
+    }
+  }
+  if (rc == AVHOT_OK) rc = transpose(d->proj_weight, h->proj_wt, O, H, s);
+  if (rc != AVHOT_OK) {
+    cudaFree(h->arena);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return AVHOT_OK;
+}
+
+extern "C" void avhot_frame_destroy(avhot_frame_t h) {
+  if (!h) return;
+  cudaFree(h->arena);
+  delete h;
+}
+
+extern "C" size_t avhot_frame_workspace_bytes(avhot_frame_t h, int B, int F, int precision) {
+  (void)h; (void)B; (void)F; (void)precision;
+  return 0;   // the fp32 path needs no scratch
+}
+
+extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, const uint8_t* frames_u8, float* hid,
+                                  int B, int F, int precision, void* workspace, size_t workspace_bytes,
+                                  avhot_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  AVHOT_REQUIRE(h && hid && B >= 0 && F >= 1, AVHOT_ERR_INVALID, "frame_hidden: bad arguments");
+  AVHOT_REQUIRE((frames_f32 != nullptr) != (frames_u8 != nullptr), AVHOT_ERR_INVALID,
+                "frame_hidden: exactly one of frames_f32 / frames_u8");
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32, AVHOT_ERR_UNSUPPORTED,
+                "frame_hidden: precision %d not built (only AVHOT_PREC_FP32)", precision);
+  AVHOT_REQUIRE((long long)B * F <= 0x7fffffff / 2, AVHOT_ERR_INVALID, "frame_hidden: B*F too large for one call");
+  return gemm_f32(frames_f32, frames_u8, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim,
+                  B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream));
+}
+
+extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B,
+                                int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                                avhot_stream_t stream) {
+  AVHOT_REQUIRE(h && hid && z && B >= 0 && F >= 1 && T >= 1, AVHOT_ERR_INVALID, "frame_tail: bad arguments");
+  AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "frame_tail: dropout p=%g outside [0, 1)", (double)p);
+  AVHOT_REQUIRE((long long)F * 64 + 64 <= 0xffffffffLL, AVHOT_ERR_INVALID, "frame_tail: F too large");
+  if (B == 0) return AVHOT_OK;
+  const long long rows = (long long)B * T;
+  const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
+  AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail: B*T too large for one call");
+  frame_tail_kernel<<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
+      hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
+      make_drop(p, seed, clip0, t0));
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}

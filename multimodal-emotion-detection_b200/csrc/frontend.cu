@@ -1,0 +1,350 @@
+// a2: log-mel + MFCC front-end.  Written spec: oracle/frontend.py (the reference has no
+// implementation of this stage).
+//
+//   wave (B, N) fp32 -> feats (B, 1 + N/160, 104) fp32 = [64 log-mel | 40 MFCC]
+//
+// One CTA = FPB consecutive frames of one clip.  The pre-emphasised, reflect-padded samples
+// the frames share are staged once in shared memory with coalesced loads (frames overlap
+// 3.2x, so HBM is read once).  One warp = one frame at a time:
+//   window + pack 512 reals as 256 complex -> in-place Stockham FFT-256 in shared memory,
+//   radix 8 x 8 x 4 (last pass stays in registers) -> real-FFT split + |X|^2 with the
+//   mirrored bin fetched by warp shuffle -> sparse (triangular) mel filters -> 10 log10 ->
+//   40 x 64 DCT-II -> output tile in shared memory -> coalesced 128-bit stores.
+#include <math.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace avhot {
+
+constexpr int N_FFT = 512, HOP = 160, N_BINS = 257, N_MELS = 64, N_MFCC = 40, N_FEATS = 104;
+constexpr int FPB = 16;            // frames per CTA
+constexpr int FE_WARPS = 8;        // warps per CTA
+constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
+constexpr int ZPAD = 256 + 16;     // padded complex buffer (index i -> i + (i >> 4))
+constexpr int MEL_NNZ_MAX = 640;
+
+struct FrontendTables {            // device layout, all fp32 unless noted
+  float window[N_FFT];
+  float2 tw[N_FFT];                // tw[k] = exp(-2 pi i k / 512)
+  float mel_w[MEL_NNZ_MAX];        // CSR values
+  int mel_start[N_MELS];           // first bin of filter m
+  int mel_len[N_MELS];
+  int mel_off[N_MELS];
+  float dct_t[N_MELS * N_MFCC];    // dct_t[j * 40 + c] = C[c][j]
+};
+
+static FrontendTables g_host_tables;
+static std::vector<float> g_host_mel_dense, g_host_dct;
+static std::once_flag g_tables_once;
+
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+  const double logstep = log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+  const double logstep = log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+static void build_tables() {
+  FrontendTables& t = g_host_tables;
+  const double PI = 3.14159265358979323846;
+  for (int n = 0; n < N_FFT; ++n) {
+    t.window[n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / N_FFT));
+    t.tw[n] = make_float2((float)cos(2.0 * PI * n / N_FFT), (float)(-sin(2.0 * PI * n / N_FFT)));
+  }
+  // Slaney mel filterbank, Slaney area normalisation, 0..8000 Hz (oracle/frontend.py mel_filterbank)
+  const double sr = 16000.0, f_lo = 0.0, f_hi = 8000.0;
+  std::vector<double> hz(N_MELS + 2);
+  const double m_lo = hz_to_mel(f_lo), m_hi = hz_to_mel(f_hi);
+  for (int i = 0; i < N_MELS + 2; ++i) hz[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (N_MELS + 1));
+  g_host_mel_dense.assign(N_MELS * N_BINS, 0.f);
+  int off = 0;
+  for (int m = 0; m < N_MELS; ++m) {
+    const double enorm = 2.0 / (hz[m + 2] - hz[m]);
+    int start = -1, len = 0;
+    for (int k = 0; k < N_BINS; ++k) {
+      const double f = (sr / 2.0) * k / (N_BINS - 1);
+      const double lower = (f - hz[m]) / (hz[m + 1] - hz[m]);
+      const double upper = (hz[m + 2] - f) / (hz[m + 2] - hz[m + 1]);
+      const double w = lower < upper ? lower : upper;
+      if (w > 0.0) {
+        if (start < 0) start = k;
+        len = k - start + 1;
+        g_host_mel_dense[m * N_BINS + k] = (float)(w * enorm);
+      }
+    }
+    if (start < 0) start = 0;
+    t.mel_start[m] = start;
+    t.mel_len[m] = len;
+    t.mel_off[m] = off;
+    for (int i = 0; i < len; ++i) t.mel_w[off + i] = g_host_mel_dense[m * N_BINS + start + i];
+    off += len;
+  }
+  g_host_dct.assign(N_MFCC * N_MELS, 0.f);
+  for (int c = 0; c < N_MFCC; ++c)
+    for (int j = 0; j < N_MELS; ++j) {
+      double v = cos(PI * (j + 0.5) * c / N_MELS) * sqrt(2.0 / N_MELS);
+      if (c == 0) v *= sqrt(0.5);
+      g_host_dct[c * N_MELS + j] = (float)v;
+      t.dct_t[j * N_MFCC + c] = (float)v;
+    }
+}
+
+constexpr int MAX_DEVICES = 64;
+static FrontendTables* g_dev_tables[MAX_DEVICES] = {};
+static std::mutex g_dev_mutex;
+
+static int get_tables(const FrontendTables** out) {
+  std::call_once(g_tables_once, build_tables);
+  int dev = 0;
+  AVHOT_CUDA(cudaGetDevice(&dev));
+  AVHOT_REQUIRE(dev >= 0 && dev < MAX_DEVICES, AVHOT_ERR_INVALID, "frontend: device index %d", dev);
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (!g_dev_tables[dev]) {
+    FrontendTables* d = nullptr;
+    AVHOT_CUDA(cudaMalloc(&d, sizeof(FrontendTables)));
+    AVHOT_CUDA(cudaMemcpy(d, &g_host_tables, sizeof(FrontendTables), cudaMemcpyHostToDevice));
+    g_dev_tables[dev] = d;
+  }
+  *out = g_dev_tables[dev];
+  return AVHOT_OK;
+}
+
+// ---- complex helpers -------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// DFT-4, natural order in and out (forward transform, e^{-i...})
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = mul_mi(csub(v1, v3));
+  v0 = cadd(a0, a2);
+  v1 = cadd(a1, a3);
+  v2 = csub(a0, a2);
+  v3 = csub(a1, a3);
+}
+// DFT-8, natural order in and out
+__device__ __forceinline__ void dft8(float2* v) {
+  dft4(v[0], v[2], v[4], v[6]);  // E[0..3] in v0 v2 v4 v6
+  dft4(v[1], v[3], v[5], v[7]);  // O[0..3] in v1 v3 v5 v7
+  const float r = 0.70710678118654752440f;
+  const float2 o0 = v[1];
+  const float2 o1 = make_float2(r * (v[3].x + v[3].y), r * (v[3].y - v[3].x));   // * (1-i)/sqrt2
+  const float2 o2 = mul_mi(v[5]);
+  const float2 o3 = make_float2(r * (v[7].y - v[7].x), -r * (v[7].x + v[7].y));  // * (-1-i)/sqrt2
+  const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+__device__ __forceinline__ int zpad(int i) { return i + (i >> 4); }
+
+struct FeSmem {
+  float seg[SEG];
+  float win[N_FFT];
+  float2 tw[N_FFT];
+  float melw[MEL_NNZ_MAX];
+  int mel_start[N_MELS], mel_len[N_MELS], mel_off[N_MELS];
+  float dct[N_MELS * N_MFCC];
+  float2 z[FE_WARPS][ZPAD];
+  float pow[FE_WARPS][N_BINS + 3];
+  float lm[FE_WARPS][N_MELS];
+  float out[FPB][N_FEATS];
+};
+
+__global__ void __launch_bounds__(FE_WARPS * 32)
+frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n_samples, int n_frames,
+                const FrontendTables* __restrict__ tab) {
+  extern __shared__ __align__(16) unsigned char fe_smem_raw[];
+  FeSmem& sm = *reinterpret_cast<FeSmem*>(fe_smem_raw);
+  float* s_seg = sm.seg;
+  float* s_win = sm.win;
+  float2* s_tw = sm.tw;
+  float* s_melw = sm.melw;
+  int *s_mel_start = sm.mel_start, *s_mel_len = sm.mel_len, *s_mel_off = sm.mel_off;
+  float* s_dct = sm.dct;
+  float2 (*s_z)[ZPAD] = sm.z;
+  float (*s_pow)[N_BINS + 3] = sm.pow;
+  float (*s_lm)[N_MELS] = sm.lm;
+  float (*s_out)[N_FEATS] = sm.out;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int clip = blockIdx.y;
+  const int t0 = blockIdx.x * FPB;
+  const float* y = wave + (size_t)clip * n_samples;
+
+  // tables -> smem
+  for (int i = tid; i < N_FFT; i += blockDim.x) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
+  for (int i = tid; i < MEL_NNZ_MAX; i += blockDim.x) s_melw[i] = tab->mel_w[i];
+  for (int i = tid; i < N_MELS; i += blockDim.x) {
+    s_mel_start[i] = tab->mel_start[i]; s_mel_len[i] = tab->mel_len[i]; s_mel_off[i] = tab->mel_off[i];
+  }
+  for (int i = tid; i < N_MELS * N_MFCC; i += blockDim.x) s_dct[i] = tab->dct_t[i];
+
+  // pre-emphasised, reflect-padded segment: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
+  const int q0 = t0 * HOP;
+  for (int i = tid; i < SEG; i += blockDim.x) {
+    int n = q0 + i - N_FFT / 2;
+    if (n < 0) n = -n;
+    if (n >= n_samples) n = 2 * (n_samples - 1) - n;
+    float v = 0.f;
+    if (n >= 0 && n < n_samples) {
+      const float cur = __ldg(y + n);
+      const float prev = n > 0 ? __ldg(y + n - 1) : 0.f;
+      v = fmaf(-0.97f, prev, cur);
+    }
+    s_seg[i] = v;
+  }
+  __syncthreads();
+
+  float2* z = s_z[warp];
+  for (int f = warp; f < FPB; f += FE_WARPS) {
+    const int t = t0 + f;
+    if (t >= n_frames) break;            // warp-uniform
+    const float2* x2 = reinterpret_cast<const float2*>(s_seg + f * HOP);
+    const float2* w2 = reinterpret_cast<const float2*>(s_win);
+    float2 v[8];
+    // ---- pass 1: radix 8, Ns = 1 (no twiddles); input straight from the windowed samples
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float2 s = x2[lane + 32 * r], w = w2[lane + 32 * r];
+      v[r] = make_float2(s.x * w.x, s.y * w.y);
+    }
+    dft8(v);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) z[zpad(lane * 8 + r)] = v[r];
+    __syncwarp();
+    // ---- pass 2: radix 8, Ns = 8
+    {
+      const int k = lane & 7;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float2 a = z[zpad(lane + 32 * r)];
+        v[r] = r == 0 ? a : cmul(a, s_tw[r * k * 8]);   // exp(-2 pi i r k / 64)
+      }
+      dft8(v);
+      __syncwarp();
+      const int j0 = (lane - k) * 8 + k;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) z[zpad(j0 + 8 * r)] = v[r];
+      __syncwarp();
+    }
+    // ---- pass 3: radix 4, Ns = 64, two butterflies per lane; results stay in registers:
+    //      Z[lane + 32 m] = v[m],  m = 2 r + jj
+    {
+      float2 u[2][4];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = lane + 32 * jj;    // 0..63 = k
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 a = z[zpad(j + 64 * r)];
+          u[jj][r] = r == 0 ? a : cmul(a, s_tw[r * j * 2]);   // exp(-2 pi i r j / 256)
+        }
+        dft4(u[jj][0], u[jj][1], u[jj][2], u[jj][3]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { v[2 * r] = u[0][r]; v[2 * r + 1] = u[1][r]; }
+    }
+    // ---- real-FFT split + power.  Bin k = lane + 32 m needs Z[(256 - k) & 255], which is
+    //      register v[7 - m] (m' = 7 - m) of lane (32 - lane) & 31, or v[(8 - m) & 7] of lane 0
+    //      when lane == 0.
+    float* pw = s_pow[warp];
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      // value from the mirrored lane: for lane != 0 we need its v[7-m]; for lane 0 its v[(8-m)&7]
+      const float2 a = v[7 - m], b = v[(8 - m) & 7];
+      const float mx_a = __shfl_sync(0xffffffffu, a.x, src), my_a = __shfl_sync(0xffffffffu, a.y, src);
+      const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);  // conj(Z[N-k])
+      const float2 zk = v[m];
+      const int k = lane + 32 * m;
+      const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+      const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+      const float2 xo = mul_mi(d);                       // (Zk - Zc) / (2i)
+      const float2 X = cadd(xe, cmul(s_tw[k], xo));
+      pw[k] = X.x * X.x + X.y * X.y;
+    }
+    if (lane == 0) {  // k = 256: X = Re(Z0) - Im(Z0)
+      const float X = v[0].x - v[0].y;
+      pw[256] = X * X;
+    }
+    __syncwarp();
+    // ---- sparse mel filters + log
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      const int st = s_mel_start[m], len = s_mel_len[m], off = s_mel_off[m];
+      float acc = 0.f;
+      for (int i = 0; i < len; ++i) acc = fmaf(pw[st + i], s_melw[off + i], acc);
+      const float lm = 3.01029995663981195f * log2f(fmaxf(acc, 1e-10f));   // 10 log10(.)
+      s_lm[warp][m] = lm;
+      s_out[f][m] = lm;
+    }
+    __syncwarp();
+    // ---- DCT-II (orthonormal), first 40 coefficients
+    {
+      float acc0 = 0.f, acc1 = 0.f;
+      const int c1 = lane + 32 < N_MFCC ? lane + 32 : lane;
+#pragma unroll 8
+      for (int j = 0; j < N_MELS; ++j) {
+        const float l = s_lm[warp][j];
+        acc0 = fmaf(l, s_dct[j * N_MFCC + lane], acc0);
+        acc1 = fmaf(l, s_dct[j * N_MFCC + c1], acc1);
+      }
+      s_out[f][N_MELS + lane] = acc0;
+      if (lane + 32 < N_MFCC) s_out[f][N_MELS + 32 + lane] = acc1;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // coalesced store of the CTA's output tile (rows are contiguous in feats)
+  const int rows = min(FPB, n_frames - t0);
+  float4* dst = reinterpret_cast<float4*>(feats + ((size_t)clip * n_frames + t0) * N_FEATS);
+  const float4* srcv = reinterpret_cast<const float4*>(&s_out[0][0]);
+  for (int i = tid; i < rows * N_FEATS / 4; i += blockDim.x) dst[i] = srcv[i];
+}
+
+}  // namespace avhot
+
+using namespace avhot;
+
+extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samples,
+                              avhot_stream_t stream) {
+  AVHOT_REQUIRE(wave && feats && B >= 0, AVHOT_ERR_INVALID, "frontend: null pointer or B < 0");
+  AVHOT_REQUIRE(n_samples > N_FFT / 2, AVHOT_ERR_INVALID,
+                "frontend: n_samples=%d must exceed the reflect pad (256)", n_samples);
+  AVHOT_REQUIRE(B <= 65535, AVHOT_ERR_INVALID, "frontend: B > 65535 per call");
+  if (B == 0) return AVHOT_OK;
+  const FrontendTables* tab = nullptr;
+  int rc = get_tables(&tab);
+  if (rc != AVHOT_OK) return rc;
+  const int n_frames = 1 + n_samples / HOP;
+  dim3 grid(ceil_div(n_frames, FPB), B);
+  // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
+  AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(FeSmem)));
+  frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), as_stream(stream)>>>(wave, feats, n_samples,
+                                                                              n_frames, tab);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_frontend_tables_host(float* mel_host, float* dct_host, float* window_host) {
+  std::call_once(g_tables_once, build_tables);
+  if (mel_host) memcpy(mel_host, g_host_mel_dense.data(), sizeof(float) * N_MELS * N_BINS);
+  if (dct_host) memcpy(dct_host, g_host_dct.data(), sizeof(float) * N_MFCC * N_MELS);
+  if (window_host) memcpy(window_host, g_host_tables.window, sizeof(float) * N_FFT);
+  return AVHOT_OK;
+}

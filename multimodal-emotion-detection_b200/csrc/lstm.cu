@@ -1,0 +1,231 @@
+// a3: SequenceEncoder(encoder_type='lstm')  (src/encoders.py:49-63 ctor, :137-155 forward).
+//
+//   seq (B, T, in) -> nn.LSTM(in -> H, L layers, batch_first, zero initial state) -> h_n[-1]
+//       -> Linear(H -> out)                                             = (B, out)
+//
+// AVHOT_PREC_FP32 path (this file): per layer
+//   1. xp = x @ W_ih^T + (b_ih + b_hh) for all steps at once (gemm.cu), (B*T, 4H);
+//   2. the recurrence, one CTA per tile of BT clips, thread j owns hidden unit j: the four gate
+//      pre-activations of unit j for every clip of the tile live in registers, h_{t-1} of the
+//      tile is broadcast from shared memory, W_hh is read k-major ([k][gate][j], transposed once
+//      at create time) so each warp load is one coalesced 128-byte line served from L1/L2;
+//      c_t stays in registers for the whole sequence.
+// Gate order i, f, g, o (nn.LSTM); c' = f*c + i*g; h' = o*tanh(c').  Inter-layer dropout is
+// inactive in eval mode and under MC-dropout.
+#include "common.cuh"
+
+struct avhot_lstm {
+  int input_dim, hidden_dim, num_layers, output_dim;
+  float* w_ih[4];    // (4H, in_k) row-major copies
+  float* w_hh_t[4];  // [k][gate][j]  = W_hh[gate*H + j][k]
+  float* bias[4];    // b_ih + b_hh
+  float* proj_w;     // (out, H)
+  float* proj_b;
+  float* arena;
+};
+
+namespace avhot {
+
+constexpr int LH = 256;  // hidden size this kernel is specialised for (one thread per unit)
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int BT>
+__global__ void __launch_bounds__(LH)
+lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
+                       const float* __restrict__ whh_t,   // [H][4][H]
+                       float* __restrict__ h_seq,         // (B, T, H) or NULL
+                       float* __restrict__ h_last,        // (B, H) or NULL
+                       const int32_t* __restrict__ lengths,  // (B) valid steps per clip, or NULL (= T)
+                       int B, int T) {
+  constexpr int HP = BT + 4;  // padded row: conflict-free 128-bit stores of one unit's BT values
+  extern __shared__ __align__(16) unsigned char lstm_smem_raw[];
+  float (*hs)[LH][HP] = reinterpret_cast<float (*)[LH][HP]>(lstm_smem_raw);   // [2][LH][HP]
+  const int j = threadIdx.x;
+  const int b0 = blockIdx.x * BT;
+  float c[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    c[b] = 0.f;
+    hs[0][j][b] = 0.f;
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const int cur = t & 1;
+    float acc[4][BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      const bool live = b0 + b < B;
+      const float* x = xp + ((size_t)(live ? b0 + b : b0) * T + t) * (4 * LH) + j;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[g][b] = __ldg(x + g * LH);
+    }
+    const float* w = whh_t + j;
+#pragma unroll 2
+    for (int k = 0; k < LH; ++k) {
+      float wg[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) wg[g] = __ldg(w + (size_t)(k * 4 + g) * LH);
+      float hv[BT];
+#pragma unroll
+      for (int b4 = 0; b4 < BT; b4 += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&hs[cur][k][b4]);
+        hv[b4] = v.x; hv[b4 + 1] = v.y; hv[b4 + 2] = v.z; hv[b4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[g][b] = fmaf(wg[g], hv[b], acc[g][b]);
+    }
+    float hn[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      const float ig = sigmoid_acc(acc[0][b]), fg = sigmoid_acc(acc[1][b]);
+      const float gg = tanhf(acc[2][b]), og = sigmoid_acc(acc[3][b]);
+      c[b] = fmaf(fg, c[b], ig * gg);
+      hn[b] = og * tanhf(c[b]);
+    }
+#pragma unroll
+    for (int b4 = 0; b4 < BT; b4 += 4)
+      *reinterpret_cast<float4*>(&hs[cur ^ 1][j][b4]) = make_float4(hn[b4], hn[b4 + 1], hn[b4 + 2], hn[b4 + 3]);
+    if (h_seq) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        if (b0 + b < B) h_seq[((size_t)(b0 + b) * T + t) * LH + j] = hn[b];
+    }
+    if (h_last) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        if (b0 + b < B) {   // h_n = state after the clip's last valid step (packed sequences, src/encoders.py:139-147)
+          const int last_t = (lengths ? min(max(__ldg(lengths + b0 + b), 1), T) : T) - 1;
+          if (t == last_t) h_last[(size_t)(b0 + b) * LH + j] = hn[b];
+        }
+    }
+    __syncthreads();
+  }
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace avhot
+
+using namespace avhot;
+
+extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, avhot_stream_t stream) {
+  AVHOT_REQUIRE(d && out, AVHOT_ERR_INVALID, "lstm_create: null argument");
+  AVHOT_REQUIRE(d->num_layers >= 1 && d->num_layers <= 4, AVHOT_ERR_INVALID,
+                "lstm_create: num_layers=%d (1..4)", d->num_layers);
+  AVHOT_REQUIRE(d->input_dim > 0 && d->output_dim > 0, AVHOT_ERR_INVALID, "lstm_create: bad dims");
+  AVHOT_REQUIRE(d->hidden_dim == LH, AVHOT_ERR_UNSUPPORTED,
+                "lstm_create: hidden_dim=%d; this build is specialised for hidden_dim=256 "
+                "(configs/base.yaml:35)", d->hidden_dim);
+  AVHOT_REQUIRE((d->input_dim & 3) == 0, AVHOT_ERR_UNSUPPORTED,
+                "lstm_create: input_dim=%d must be a multiple of 4", d->input_dim);
+  const int H = LH, L = d->num_layers;
+  size_t total = 0;
+  for (int l = 0; l < L; ++l) {
+    const int in = l == 0 ? d->input_dim : H;
+    AVHOT_REQUIRE(d->weight_ih[l] && d->weight_hh[l] && d->bias_ih[l] && d->bias_hh[l], AVHOT_ERR_INVALID,
+                  "lstm_create: layer %d tensors missing", l);
+    total += align256(sizeof(float) * 4 * H * in) + align256(sizeof(float) * 4 * H * H) +
+             align256(sizeof(float) * 4 * H);
+  }
+  AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
+  total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
+  avhot_lstm* h = new avhot_lstm();
+  h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
+  h->arena = nullptr;
+  cudaError_t e = cudaMalloc(&h->arena, total);
+  if (e != cudaSuccess) {
+    delete h;
+    set_error("lstm_create: cudaMalloc(%zu) -> %s", total, cudaGetErrorString(e));
+    return AVHOT_ERR_CUDA;
+  }
+  cudaStream_t s = as_stream(stream);
+  char* p = reinterpret_cast<char*>(h->arena);
+  auto take = [&](size_t bytes) { float* r = reinterpret_cast<float*>(p); p += align256(bytes); return r; };
+  int rc = AVHOT_OK;
+  for (int l = 0; l < L && rc == AVHOT_OK; ++l) {
+    const int in = l == 0 ? d->input_dim : H;
+    h->w_ih[l] = take(sizeof(float) * 4 * H * in);
+    h->w_hh_t[l] = take(sizeof(float) * 4 * H * H);
+    h->bias[l] = take(sizeof(float) * 4 * H);
+    if (cudaMemcpyAsync(h->w_ih[l], d->weight_ih[l], sizeof(float) * 4 * H * in, cudaMemcpyDeviceToDevice, s) !=
+        cudaSuccess) rc = AVHOT_ERR_CUDA;
+    if (rc == AVHOT_OK) rc = transpose(d->weight_hh[l], h->w_hh_t[l], 4 * H, H, s);  // [k][gate*H + j]
+    if (rc == AVHOT_OK) rc = add_vec(d->bias_ih[l], d->bias_hh[l], h->bias[l], 4 * H, s);
+  }
+  if (rc == AVHOT_OK) {
+    h->proj_w = take(sizeof(float) * d->output_dim * H);
+    h->proj_b = take(sizeof(float) * d->output_dim);
+    if (cudaMemcpyAsync(h->proj_w, d->proj_weight, sizeof(float) * d->output_dim * H, cudaMemcpyDeviceToDevice, s) !=
+            cudaSuccess ||
+        cudaMemcpyAsync(h->proj_b, d->proj_bias, sizeof(float) * d->output_dim, cudaMemcpyDeviceToDevice, s) !=
+            cudaSuccess)
+      rc = AVHOT_ERR_CUDA;
+  }
+  if (rc != AVHOT_OK) {
+    if (rc == AVHOT_ERR_CUDA) set_error("lstm_create: device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(h->arena);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return AVHOT_OK;
+}
+
+extern "C" void avhot_lstm_destroy(avhot_lstm_t h) {
+  if (!h) return;
+  cudaFree(h->arena);
+  delete h;
+}
+
+// workspace (fp32 path): xp (B*T*4H) + h_seq (B*T*H) + h_last (B*H)
+extern "C" size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int precision) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  (void)precision;
+  const size_t H = h->hidden_dim;
+  return align256(sizeof(float) * (size_t)B * T * 4 * H) + align256(sizeof(float) * (size_t)B * T * H) +
+         align256(sizeof(float) * (size_t)B * H);
+}
+
+extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_t* lengths, float* out, int B,
+                                  int T, int precision, void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
+  AVHOT_REQUIRE(h && seq && out && B >= 0 && T >= 1, AVHOT_ERR_INVALID, "lstm_forward: bad arguments");
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32, AVHOT_ERR_UNSUPPORTED,
+                "lstm_forward: precision %d not built (only AVHOT_PREC_FP32)", precision);
+  if (B == 0) return AVHOT_OK;
+  const size_t need = avhot_lstm_workspace_bytes(h, B, T, precision);
+  AVHOT_REQUIRE(workspace && workspace_bytes >= need, AVHOT_ERR_WORKSPACE,
+                "lstm_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+  AVHOT_REQUIRE((size_t)B * T <= 0x7fffffffu / 8, AVHOT_ERR_INVALID, "lstm_forward: B*T too large for one call");
+  const int H = h->hidden_dim;
+  cudaStream_t s = as_stream(stream);
+  char* p = reinterpret_cast<char*>(workspace);
+  float* xp = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * T * 4 * H);
+  float* h_seq = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * T * H);
+  float* h_last = reinterpret_cast<float*>(p);
+  const bool small = ceil_div(B, 32) * 2 < num_sms();   // few clips: smaller tiles, more CTAs
+  for (int l = 0; l < h->num_layers; ++l) {
+    const float* x = l == 0 ? seq : h_seq;
+    const int in = l == 0 ? h->input_dim : H;
+    int rc = gemm_f32(x, nullptr, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s);
+    if (rc != AVHOT_OK) return rc;
+    const bool last = l == h->num_layers - 1;
+    float* hs_out = last ? nullptr : h_seq;   // layer l overwrites its own input only after xp is formed
+    float* hl_out = last ? h_last : nullptr;
+    if (small) {
+      constexpr int BT = 4;
+      const size_t smem = sizeof(float) * 2 * LH * (BT + 4);
+      lstm_recurrence_kernel<BT><<<ceil_div(B, BT), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T);
+    } else {
+      constexpr int BT = 32;
+      const size_t smem = sizeof(float) * 2 * LH * (BT + 4);
+      AVHOT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+      lstm_recurrence_kernel<BT><<<ceil_div(B, BT), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T);
+    }
+    AVHOT_LAUNCH_CHECK();
+  }
+  return gemm_f32(h_last, nullptr, H, h->proj_w, H, h->proj_b, out, h->output_dim, B, h->output_dim, H, ACT_NONE, s);
+}

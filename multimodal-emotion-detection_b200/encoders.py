@@ -1,0 +1,246 @@
+"""Drop-in modules for src/encoders.py: SequenceEncoder (lstm), FrameEncoder (attention pooling),
+build_encoder.  Same constructor / forward signatures, parameter names, shapes and default init as the
+reference (the torch.nn modules below are parameter containers: their forward is never called), so a
+reference state-dict loads with strict=True.  forward runs the sm_100a kernels of libavhot.so; inference
+only (no autograd graph is recorded).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _rng
+from ._handles import Handle, Workspace
+
+_ws = Workspace()
+
+
+class SequenceEncoder(nn.Module):
+    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru', 'cnn',
+    'transformer' are valid in the reference and not built here (ValueError says so)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int = 256, output_dim: int = 128, num_layers: int = 2,
+                 encoder_type: str = 'lstm', dropout: float = 0.1):
+        super().__init__()
+        self.encoder_type = encoder_type
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+        self.input_dim = input_dim
+        self.num_layers = num_layers
+        self.precision = _lib.PREC_FP32
+        if encoder_type == 'lstm':
+            self.rnn = nn.LSTM(input_size=input_dim, hidden_size=hidden_dim, num_layers=num_layers,
+                               batch_first=True, dropout=dropout if num_layers > 1 else 0.0,
+                               bidirectional=False)                                  # src/encoders.py:54-61
+            self.projection = nn.Linear(hidden_dim, output_dim)                      # :62
+        elif encoder_type in ('gru', 'cnn', 'transformer'):
+            raise ValueError(f"encoder type '{encoder_type}' exists in the reference but is not built in this "
+                             "library (hot path = 'lstm')")
+        else:
+            raise ValueError(f"Unknown encoder type: {encoder_type}")                # :115
+        self._handle = Handle("avhot_lstm_destroy")
+
+    def _params(self):
+        ps = []
+        for l in range(self.num_layers):
+            ps += [getattr(self.rnn, f"weight_ih_l{l}"), getattr(self.rnn, f"weight_hh_l{l}"),
+                   getattr(self.rnn, f"bias_ih_l{l}"), getattr(self.rnn, f"bias_hh_l{l}")]
+        return ps + [self.projection.weight, self.projection.bias]
+
+    def _get_handle(self, dev):
+        ps = [_lib.f32c(p.detach()) for p in self._params()]
+        _lib.require_cuda(*ps)
+
+        def create():
+            d = _lib.LstmDesc()
+            d.input_dim, d.hidden_dim = self.input_dim, self.hidden_dim
+            d.num_layers, d.output_dim = self.num_layers, self.output_dim
+            for l in range(self.num_layers):
+                d.weight_ih[l], d.weight_hh[l] = ps[4 * l].data_ptr(), ps[4 * l + 1].data_ptr()
+                d.bias_ih[l], d.bias_hh[l] = ps[4 * l + 2].data_ptr(), ps[4 * l + 3].data_ptr()
+            d.proj_weight, d.proj_bias = ps[-2].data_ptr(), ps[-1].data_ptr()
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_lstm_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
+                       "SequenceEncoder")
+            return out.value
+
+        return self._handle.get(self._params(), create)
+
+    @torch.no_grad()
+    def forward(self, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev = _lib.require_cuda(sequence)
+        _lib.check_device(dev)
+        if sequence.dim() != 3 or sequence.shape[2] != self.input_dim:
+            raise ValueError(f"sequence must be (B, T, {self.input_dim}), got {tuple(sequence.shape)}")
+        x = _lib.f32c(sequence)
+        B, T, _ = x.shape
+        if T < 1:
+            raise ValueError("empty sequence")
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths).to(device=dev, dtype=torch.int32).contiguous()
+            if lengths.shape != (B,):
+                raise ValueError("lengths must be (B,)")
+        out = torch.empty(B, self.output_dim, device=dev, dtype=torch.float32)
+        if B == 0:
+            return out
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._get_handle(dev)
+            nbytes = lib.avhot_lstm_workspace_bytes(h, B, T, self.precision)
+            ws = _ws.get(nbytes, dev)
+            _lib.check(lib.avhot_lstm_forward(h, _lib.ptr(x), _lib.ptr(lengths), _lib.ptr(out), B, T,
+                                              self.precision, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                       "SequenceEncoder.forward")
+        return out
+
+
+class FrameEncoder(nn.Module):
+    """src/encoders.py:196-327.  temporal_pooling 'attention' is the hot path (configs/base.yaml:43)."""
+
+    def __init__(self, frame_dim: int, hidden_dim: int = 256, output_dim: int = 128,
+                 temporal_pooling: str = 'attention', dropout: float = 0.1):
+        super().__init__()
+        self.temporal_pooling = temporal_pooling
+        self.frame_dim, self.hidden_dim, self.output_dim = frame_dim, hidden_dim, output_dim
+        self.precision = _lib.PREC_FP32
+        self.frame_mlp = nn.Sequential(nn.Linear(frame_dim, hidden_dim), nn.ReLU(inplace=True),
+                                       nn.Dropout(dropout))                          # :225-229
+        self._dropout = nn.Dropout(dropout)                                           # :230
+        if temporal_pooling == 'attention':
+            self.attention = nn.Linear(hidden_dim, 1)                                 # :236
+        elif temporal_pooling in ('average', 'max'):
+            raise ValueError(f"temporal_pooling '{temporal_pooling}' exists in the reference but is not built in "
+                             "this library (hot path = 'attention')")
+        else:
+            raise ValueError(f"Unknown pooling: {temporal_pooling}")                  # :242
+        self.projection = nn.Sequential(nn.LayerNorm(hidden_dim), nn.Linear(hidden_dim, output_dim))  # :246-249
+        self._handle = Handle("avhot_frame_destroy")
+
+    def _params(self):
+        return [self.frame_mlp[0].weight, self.frame_mlp[0].bias, self.attention.weight, self.attention.bias,
+                self.projection[0].weight, self.projection[0].bias, self.projection[1].weight,
+                self.projection[1].bias]
+
+    def _get_handle(self, dev):
+        ps = [_lib.f32c(p.detach()) for p in self._params()]
+        _lib.require_cuda(*ps)
+
+        def create():
+            d = _lib.FrameDesc()
+            d.frame_dim, d.hidden_dim, d.output_dim = self.frame_dim, self.hidden_dim, self.output_dim
+            (d.mlp_weight, d.mlp_bias, d.attn_weight, d.attn_bias, d.ln_weight, d.ln_bias, d.proj_weight,
+             d.proj_bias) = [p.data_ptr() for p in ps]
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_frame_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
+                       "FrameEncoder")
+            return out.value
+
+        return self._handle.get(self._params(), create)
+
+    # -- the two halves of forward, exposed so the MC wrapper can hoist the pass-invariant one ------------
+    @torch.no_grad()
+    def hidden(self, frames: torch.Tensor) -> torch.Tensor:
+        """frame_mlp[0:2] = Linear + ReLU (:225-227): (B, F, frame_dim) fp32, or uint8 pixels k meaning k/255
+        (src/dataprocessing.py:261-265) -> (B, F, H), before dropout."""
+        dev = _lib.require_cuda(frames)
+        _lib.check_device(dev)
+        if frames.dim() != 3 or frames.shape[2] != self.frame_dim:
+            raise ValueError(f"frames must be (B, F, {self.frame_dim}), got {tuple(frames.shape)}")
+        u8 = frames.dtype == torch.uint8
+        x = frames.contiguous() if u8 else _lib.f32c(frames)
+        B, F, _ = x.shape
+        if F < 1:
+            raise ValueError("no frames")
+        hid = torch.empty(B, F, self.hidden_dim, device=dev, dtype=torch.float32)
+        if B == 0:
+            return hid
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._get_handle(dev)
+            nbytes = lib.avhot_frame_workspace_bytes(h, B, F, self.precision)
+            ws = _ws.get(nbytes, dev)
+            _lib.check(lib.avhot_frame_hidden(h, None if u8 else _lib.ptr(x), _lib.ptr(x) if u8 else None,
+                                              _lib.ptr(hid), B, F, self.precision, _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(dev)), "FrameEncoder.hidden")
+        return hid
+
+    @torch.no_grad()
+    def tail(self, hid: torch.Tensor, mask: Optional[torch.Tensor] = None, passes: int = 1, p: float = 0.0,
+             seed: int = 0, clip0: int = 0, t0: int = 0) -> torch.Tensor:
+        """Everything after the ReLU for `passes` stochastic passes: (B, F, H) -> (B, passes, out)."""
+        dev = _lib.require_cuda(hid, mask)
+        B, F, _ = hid.shape
+        valid = None
+        if mask is not None:
+            valid = torch.as_tensor(mask).to(device=dev).bool().to(torch.uint8).contiguous()
+            if valid.shape != (B, F):
+                raise ValueError("mask must be (B, num_frames)")
+        z = torch.empty(B, passes, self.output_dim, device=dev, dtype=torch.float32)
+        if B == 0:
+            return z
+        with torch.cuda.device(dev):
+            h = self._get_handle(dev)
+            _lib.check(_lib.load().avhot_frame_tail(h, _lib.ptr(hid), _lib.ptr(valid), _lib.ptr(z), B, F, passes,
+                                                    float(p), seed, clip0, t0, _lib.stream_ptr(dev)),
+                       "FrameEncoder.tail")
+        return z
+
+    def _drop_p(self) -> float:
+        # nn.Dropout is active only in train mode; MCDropoutUncertainty flips exactly these two modules
+        # (src/uncertainty.py:36-46).  Both sites share p (one ctor argument, src/encoders.py:228,230).
+        d0, d1 = self.frame_mlp[2], self._dropout
+        if d0.training != d1.training:
+            raise ValueError("frame_mlp dropout and _dropout must be in the same mode")
+        return float(d0.p) if d0.training else 0.0
+
+    def forward(self, frames: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        hid = self.hidden(frames)
+        seed, t, clip0 = _rng.current()
+        return self.tail(hid, mask, 1, self._drop_p(), seed, clip0, t)[:, 0, :]
+
+    def attention_pool(self, frames: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """src/encoders.py:300-327 on already-encoded frames (B, F, H) -> (B, H).  Off the hot path (forward fuses
+        it); provided for signature parity with plain torch ops on the caller's device."""
+        scores = torch.nn.functional.linear(frames, self.attention.weight, self.attention.bias).squeeze(-1)
+        if mask is not None:
+            scores = scores.masked_fill(~mask.bool(), torch.finfo(scores.dtype).min)
+        weights = torch.softmax(scores, dim=1)
+        return torch.einsum('bt,bth->bh', weights, frames)
+
+
+def build_encoder(modality: str, input_dim: int, output_dim: int, encoder_config: dict = None) -> nn.Module:
+    """src/encoders.py:532-636: same selection rules; 'mlp' and 'pretrained_cnn' are out of scope."""
+    if encoder_config is None:
+        encoder_config = {}
+    cfg = dict(encoder_config)
+    enc_type = cfg.pop("type", None)
+    in_dim = cfg.pop("input_dim", input_dim)
+    if enc_type is None:
+        mod_lower = modality.lower()
+        if mod_lower in {"video", "frames"}:
+            enc_type = "frame"
+        elif mod_lower in {"imu", "mocap", "audio", "accelerometer", "gyro", "magnetometer", "imu_hand",
+                           "imu_chest", "imu_ankle"}:
+            enc_type = "sequence"
+        else:
+            enc_type = "mlp"
+    if enc_type == "frame":
+        temporal_pooling = cfg.pop("temporal_pooling", "attention")
+        hidden_dim = cfg.pop("hidden_dim", None)
+        dropout = cfg.pop("dropout", 0.1)
+        return FrameEncoder(frame_dim=in_dim, hidden_dim=hidden_dim if hidden_dim is not None else output_dim * 2,
+                            output_dim=output_dim, temporal_pooling=temporal_pooling, dropout=dropout)
+    if enc_type == "sequence":
+        encoder_kind = cfg.pop("encoder_type", "lstm")
+        num_layers = cfg.pop("num_layers", 2)
+        hidden_dim = cfg.pop("hidden_dim", None)
+        dropout = cfg.pop("dropout", 0.1)
+        return SequenceEncoder(input_dim=in_dim, hidden_dim=hidden_dim if hidden_dim is not None else output_dim * 2,
+                               output_dim=output_dim, num_layers=num_layers, encoder_type=encoder_kind,
+                               dropout=dropout)
+    if enc_type in ("mlp", "pretrained_cnn"):
+        raise ValueError(f"encoder type '{enc_type}' exists in the reference but is not built in this library")
+    raise ValueError(f"Unknown encoder type '{enc_type}' for modality '{modality}'")

@@ -1,0 +1,107 @@
+"""The per-clip audio-visual inference hot path as one module.
+
+AVHotPath mirrors MultimodalFusionModule (src/train.py:34-164) without Lightning: ``encoders`` (ModuleDict, in
+``modalities`` order, :55-66), then either ``fusion_model`` = HybridFusion (the commented composition :69-76,
+:138-147) or ``fusion_head`` = Linear-ReLU-Linear on the concatenation (:81-85, :153-164, the live path, which
+ignores the mask) - same attribute names, so state-dict keys match SURVEY.md Appendix A.
+
+forward(features, mask)   one pass, like the reference's forward.
+mc_forward(features, mask, num_samples, ...)   MCDropoutUncertainty's result with the pass-invariant stages
+                          (front-end, LSTM, video Linear + ReLU) computed once and the T stochastic passes inside
+                          the fused tail kernels.
+
+features["audio"] may be the raw waveform (B, 48000) / (B, 48000, 1) as load_raw_audio produces it
+(src/dataprocessing.py:210-211) - the log-mel/MFCC front-end is applied - or precomputed (B, T, 104) features.
+features["video"] is (B, 16, 12544) fp32 in [0, 1] or uint8 pixels.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _rng, dataprocessing
+from .encoders import build_encoder
+from .fusion import ConcatHead, build_fusion_model
+from .uncertainty import mc_reduce
+
+DEFAULT_ENCODERS = {   # configs/base.yaml:30-47 with BASELINE.json's input dims
+    "audio": {"type": "sequence", "input_dim": dataprocessing.N_FEATS, "encoder_type": "lstm", "hidden_dim": 256,
+              "num_layers": 2, "dropout": 0.1},
+    "video": {"type": "frame", "input_dim": 112 * 112, "temporal_pooling": "attention", "hidden_dim": 256,
+              "dropout": 0.1},
+}
+
+
+class AVHotPath(nn.Module):
+    def __init__(self, head: str = "hybrid", modalities=("audio", "video"), encoders: Optional[dict] = None,
+                 output_dim: int = 128, hidden_dim: int = 256, num_heads: int = 4, num_classes: int = 8,
+                 dropout: float = 0.3):
+        super().__init__()
+        if head not in ("hybrid", "concat"):
+            raise ValueError(f"Unknown head: {head}")
+        self.head = head
+        self.modalities = list(modalities)
+        cfgs = encoders or DEFAULT_ENCODERS
+        self.encoders = nn.ModuleDict()
+        dims = {}
+        for m in self.modalities:                                                        # src/train.py:55-66
+            cfg = cfgs[m]
+            self.encoders[m] = build_encoder(modality=m, input_dim=cfg.get("input_dim", 64), output_dim=output_dim,
+                                             encoder_config=cfg)
+            dims[m] = output_dim
+        if head == "hybrid":
+            self.fusion_model = build_fusion_model("hybrid", dims, num_classes, hidden_dim=hidden_dim,
+                                                   num_heads=num_heads, dropout=dropout)  # :69-76
+        else:
+            self.fusion_head = ConcatHead(output_dim * len(self.modalities), hidden_dim, num_classes,
+                                          len(self.modalities))                          # :81-85
+        self.num_classes = num_classes
+
+    # ---- stages ----------------------------------------------------------------------------------------
+    def audio_features(self, audio: torch.Tensor) -> torch.Tensor:
+        enc = self.encoders["audio"]
+        if audio.dim() == 3 and audio.shape[-1] == enc.input_dim and enc.input_dim != 1:
+            return audio                                   # already (B, T, 104)
+        return dataprocessing.logmel_mfcc(audio)           # raw waveform (B, N) or (B, N, 1)
+
+    @torch.no_grad()
+    def _run(self, features: Dict[str, torch.Tensor], mask, passes: int, stochastic: bool, seed: int, clip0: int,
+             t0: int):
+        if set(self.modalities) != {"audio", "video"}:
+            raise ValueError("AVHotPath is the audio + video path")
+        audio, video = features["audio"], features["video"]
+        dev = _lib.require_cuda(audio, video)
+        _lib.check_device(dev)
+        B = audio.shape[0]
+        z_a = self.encoders["audio"](self.audio_features(audio))                          # (B, out), pass-invariant
+        venc = self.encoders["video"]
+        hid = venc.hidden(video)                                                          # (B, F, H), pass-invariant
+        p_enc = venc._drop_p() if stochastic else 0.0
+        z_v = venc.tail(hid, None, passes, p_enc, seed, clip0, t0)                        # (B, passes, out)
+        zs = [z_a, z_v.reshape(B * passes, -1)] if self.modalities[0] == "audio" else [z_v.reshape(B * passes, -1), z_a]
+        rpc = [1, passes] if self.modalities[0] == "audio" else [passes, 1]
+        if self.head == "hybrid":
+            fm = self.fusion_model
+            mask_f = None
+            if mask is not None:
+                mask_f = torch.as_tensor(mask).to(device=dev, dtype=torch.float32).contiguous()
+                if mask_f.shape != (B, 2):
+                    raise ValueError("mask must be (B, 2)")
+            p_f = fm._drop_p() if stochastic else 0.0
+            logits, _, _, _ = fm.run(zs, rpc, mask_f, B, passes, p_f, seed, clip0, t0)
+        else:
+            logits = self.fusion_head.run(zs, rpc, B, passes)                             # mask ignored (F2)
+        return logits                                                                     # (B, passes, C)
+
+    def forward(self, features: Dict[str, torch.Tensor], mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        seed, t, clip0 = _rng.current()
+        return self._run(features, mask, 1, True, seed, clip0, t)[:, 0, :]
+
+    def mc_forward(self, features: Dict[str, torch.Tensor], mask: Optional[torch.Tensor] = None,
+                   num_samples: int = 32, seed: int = _rng.DEFAULT_SEED, clip0: int = 0):
+        """-> (mean_logits (B, C), uncertainty (B,), labels (B,) int32, packed (B, C + 1)).  Dropout modules must
+        be in the mode the caller wants (MCDropoutUncertainty puts exactly the nn.Dropout modules in train mode)."""
+        logits = self._run(features, mask, num_samples, True, seed, clip0, 0)
+        return mc_reduce(logits)

@@ -1,0 +1,108 @@
+"""Host-side mirror of the reference interface: signatures, state-dict layout, error
+behaviour, and the no-CPU-fallback rule.  No GPU needed."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+import multimodal_emotion_detection_b200 as pkg
+from oracle import synth
+
+
+def test_signatures_match_reference():
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(pkg.SequenceEncoder.__init__)[1:] == ["input_dim", "hidden_dim", "output_dim", "num_layers",
+                                                     "encoder_type", "dropout"]          # src/encoders.py:23-31
+    assert sig(pkg.SequenceEncoder.forward)[1:] == ["sequence", "lengths"]
+    assert sig(pkg.FrameEncoder.__init__)[1:] == ["frame_dim", "hidden_dim", "output_dim", "temporal_pooling",
+                                                  "dropout"]                              # :203-210
+    assert sig(pkg.FrameEncoder.forward)[1:] == ["frames", "mask"]
+    assert sig(pkg.build_encoder) == ["modality", "input_dim", "output_dim", "encoder_config"]
+    assert sig(pkg.CrossModalAttention.__init__)[1:] == ["query_dim", "key_dim", "hidden_dim", "num_heads",
+                                                         "dropout"]                       # src/attention.py:31-32
+    assert sig(pkg.CrossModalAttention.forward)[1:] == ["query", "key", "value", "mask"]
+    assert sig(pkg.HybridFusion.__init__)[1:] == ["modality_dims", "hidden_dim", "num_classes", "num_heads",
+                                                  "dropout"]                              # src/fusion.py:409-416
+    assert sig(pkg.HybridFusion.forward)[1:] == ["modality_features", "modality_mask", "return_attention"]
+    assert sig(pkg.build_fusion_model)[:3] == ["fusion_type", "modality_dims", "num_classes"]
+    assert sig(pkg.MCDropoutUncertainty.__init__)[1:] == ["model", "num_samples"]         # src/uncertainty.py:25
+    assert inspect.signature(pkg.HybridFusion.__init__).parameters["num_classes"].default == 11
+    assert inspect.signature(pkg.MCDropoutUncertainty.__init__).parameters["num_samples"].default == 10
+    assert sig(pkg.load_raw_audio) == ["wav_path", "sr", "max_duration"]                  # src/dataprocessing.py:184-188
+
+
+def test_state_dict_layout_appendix_a():
+    want = synth.model_shapes()
+    for head, drop in (("hybrid", "fusion_head."), ("concat", "fusion_model.")):
+        sd = pkg.AVHotPath(head).state_dict()
+        exp = {k: v[0] for k, v in want.items() if not k.startswith(drop)}
+        assert set(sd) == set(exp)
+        for k, shape in exp.items():
+            assert tuple(sd[k].shape) == tuple(shape), k
+    m = pkg.AVHotPath("hybrid")
+    w = {k: torch.from_numpy(v) for k, v in synth.synth_weights(42).items() if not k.startswith("fusion_head.")}
+    m.load_state_dict(w, strict=True)
+    assert sum(p.numel() for p in m.encoders["audio"].parameters()) == 929920
+    assert sum(p.numel() for p in m.encoders["video"].parameters()) == 3245185
+    assert sum(p.numel() for p in m.fusion_model.parameters()) == 631561
+
+
+def test_error_behaviour_like_reference():
+    with pytest.raises(ValueError):
+        pkg.SequenceEncoder(8, encoder_type="bogus")                                      # src/encoders.py:115
+    with pytest.raises(ValueError):
+        pkg.FrameEncoder(8, temporal_pooling="bogus")                                     # :242
+    with pytest.raises(ValueError):
+        pkg.build_encoder("x", 8, 8, {"type": "bogus"})                                   # :636
+    with pytest.raises(ValueError):
+        pkg.build_fusion_model("bogus", {"a": 8}, 3)                                      # src/fusion.py:696
+    with pytest.raises(AssertionError):
+        pkg.CrossModalAttention(8, 8, 10, num_heads=4)                                    # src/attention.py:34
+    with pytest.raises(AssertionError):
+        pkg.MCDropoutUncertainty(torch.nn.Identity(), num_samples=0)                      # src/uncertainty.py:31
+    att = pkg.CrossModalAttention(8, 8, 8, num_heads=2)
+    with pytest.raises(ValueError):
+        att._normalize_mask(torch.zeros(2, 2, 2), 2, 2)                                   # src/attention.py:76
+    assert att._normalize_mask(torch.tensor([1.0, 0.0]), 2, 3).tolist() == [[False] * 3, [True] * 3]
+    assert isinstance(pkg.build_encoder("video", 12544, 128, {"hidden_dim": 256}), pkg.FrameEncoder)
+    assert isinstance(pkg.build_encoder("audio", 104, 128, {"hidden_dim": 256}), pkg.SequenceEncoder)
+
+
+def test_no_cpu_fallback():
+    m = pkg.AVHotPath("hybrid")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m({"audio": torch.zeros(1, 48000), "video": torch.zeros(1, 16, 12544)})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.logmel_mfcc(torch.zeros(1, 48000))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.HybridFusion({"audio": 128, "video": 128}, num_classes=8)({"audio": torch.zeros(1, 128),
+                                                                       "video": torch.zeros(1, 128)})
+
+
+def test_mc_wrapper_mode_handling():
+    m = pkg.AVHotPath("hybrid").train()
+    mc = pkg.MCDropoutUncertainty(m, num_samples=2)
+    with pytest.raises(RuntimeError):
+        mc({"audio": torch.zeros(1, 48000), "video": torch.zeros(1, 16, 12544)})
+    assert m.training                                     # restored (src/uncertainty.py:67-71)
+    m.eval()
+    pkg.MCDropoutUncertainty._set_dropout_train(m)
+    on = [n for n, x in m.named_modules() if isinstance(x, torch.nn.Dropout) and x.training]
+    assert sorted(on) == sorted(["encoders.video.frame_mlp.2", "encoders.video._dropout",
+                                 "fusion_model.attn_layers.audio.attn_dropout",
+                                 "fusion_model.attn_layers.video.attn_dropout", "fusion_model.fusion_gate.2"])
+    assert not m.encoders["audio"].rnn.training           # LSTM dropout stays off
+
+
+def test_shard_ranges():
+    from multimodal_emotion_detection_b200 import parallel as par
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 4, 8):
+            r = [par.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            c = par.shard_counts(n, w)
+            assert sum(c) == n and max(c) - min(c) <= 1
+    with pytest.raises(ValueError):
+        par.shard_range(10, 2, 2)

@@ -1,0 +1,67 @@
+"""oracle/model.py against the golden vectors produced by the REFERENCE's own modules
+(tests/golden/make_golden.py imported them from /root/reference/src in the build container)."""
+import numpy as np
+import torch
+
+from oracle import frontend as fe, model as om, philox as px, synth
+
+TOL = dict(rtol=1e-4, atol=2e-5)
+
+
+def _inputs(golden):
+    ids = golden["clip_ids"]
+    seed = int(golden["seed"])
+    sd = om.to_torch(synth.synth_weights(seed))
+    wave = synth.synth_audio(ids, seed)
+    frames = torch.from_numpy(synth.synth_video(ids, seed))
+    feats = torch.from_numpy(fe.logmel_mfcc(wave))
+    masks = {
+        "ones": torch.ones(len(ids), 2),
+        "mixed": torch.tensor([[1, 1], [1, 0], [0, 1], [0, 0], [1, 1], [0, 1]], dtype=torch.float32),
+        "p05": torch.from_numpy(px.modality_mask(ids, 2, 0.05, seed)),
+    }
+    return ids, seed, sd, feats, frames, masks
+
+
+def test_encoders_and_heads(golden):
+    torch.set_num_threads(8)
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    z_a = om.sequence_encoder_lstm(feats, sd)
+    z_v = om.frame_encoder(frames, sd)
+    np.testing.assert_allclose(z_a.numpy(), golden["z_audio"], **TOL)
+    np.testing.assert_allclose(z_v.numpy(), golden["z_video"], **TOL)
+    hid = om.frame_hidden(frames, sd)
+    for name, mask in masks.items():
+        lg, info = om.hybrid_fusion({"audio": z_a, "video": z_v}, mask, sd, return_info=True)
+        np.testing.assert_allclose(lg.numpy(), golden[f"logits_hybrid_{name}"], **TOL)
+        np.testing.assert_allclose(info["fusion_weights"].numpy(), golden[f"fusion_weights_{name}"], **TOL)
+        np.testing.assert_allclose(info["per_modality_attention"][0].numpy(), golden[f"attn_audio_{name}"], **TOL)
+        np.testing.assert_allclose(info["per_modality_attention"][1].numpy(), golden[f"attn_video_{name}"], **TOL)
+    lg = om.av_forward(None, None, None, sd, "concat", z_audio=z_a, hid=hid)
+    np.testing.assert_allclose(lg.numpy(), golden["logits_concat_ones"], **TOL)
+    # MC-dropout through the oracle's Philox masks == the reference wrapper over mask-injected reference modules
+    T = int(golden["t_mc"])
+    for head, names in (("hybrid", ("ones", "p05")), ("concat", ("ones",))):
+        for name in names:
+            mean, unc, _ = om.mc_dropout_forward(feats, frames, masks[name], sd, T, seed, ids, head)
+            np.testing.assert_allclose(mean.numpy(), golden[f"mc_mean_logits_{head}_{name}"], **TOL)
+            np.testing.assert_allclose(unc.numpy(), golden[f"mc_uncertainty_{head}_{name}"], rtol=1e-3, atol=1e-7)
+            assert (mean.argmax(dim=1).numpy() == golden[f"mc_labels_{head}_{name}"]).all()
+
+
+def test_cross_modal_attention_general_shapes(golden):
+    sd = {k[len("xattn."):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("xattn.att.")}
+    q, kv = torch.from_numpy(golden["xattn.q"]), torch.from_numpy(golden["xattn.kv"])
+    inv = torch.from_numpy(golden["xattn.invalid"])
+    out, attn = om.cross_modal_attention(q, kv, kv, inv, sd, "att.", 4)
+    np.testing.assert_allclose(out.numpy(), golden["xattn.out"], **TOL)
+    np.testing.assert_allclose(attn.numpy(), golden["xattn.attn"], **TOL)
+    assert (attn[2] == 0).all()                              # all keys masked -> zeros (src/attention.py:124-128)
+
+
+def test_fp64_oracle_close_to_fp32(golden):
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    z32 = om.frame_encoder(frames[:2], sd)
+    z64 = om.frame_encoder(frames[:2].double(), sd64)
+    assert (z32.double() - z64).abs().max() < 1e-5
