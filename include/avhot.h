@@ -55,6 +55,17 @@ const char* avhot_last_error(void);
 /* cudaGetDeviceProperties of the current device: fails unless it is sm_100. */
 int avhot_check_device(void);
 
+/* ---- measurement hooks (bench.py): kernels launched so far by this library in this process, and
+ * optional CUDA-event timing of each named kernel on its launching stream. ---------------------- */
+long long avhot_launch_count(void);
+int avhot_prof_enable(int on);
+int avhot_prof_reset(void);
+/* total device time (ms) and number of timed launches of kernel `name` since the last reset;
+ * synchronises on the recorded events. */
+int avhot_prof_read(const char* name, double* total_ms, int* launches);
+/* newline-separated names seen since the last reset */
+int avhot_prof_names(char* buf, int buf_bytes);
+
 /* ---- Philox-4x32-10 spec (oracle/philox.py) ------------------------------------ */
 /* keep[b*n_elems + e] = 1 iff words(e>>2, clip0+b, t, site)[e&3] >= floor(p*2^32).
  * Test/diagnostic entry: the masks the fused kernels apply at the nn.Dropout sites

@@ -64,6 +64,11 @@ PROTOTYPES = {
     "avhot_version": (_I, []),
     "avhot_last_error": (C.c_char_p, []),
     "avhot_check_device": (_I, []),
+    "avhot_launch_count": (C.c_longlong, []),
+    "avhot_prof_enable": (_I, [_I]),
+    "avhot_prof_reset": (_I, []),
+    "avhot_prof_read": (_I, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_I)]),
+    "avhot_prof_names": (_I, [C.c_char_p, _I]),
     "avhot_dropout_keep": (_I, [_P, _I, _I, _U64, _U32, _U32, _F, _U64, _P]),
     "avhot_modality_mask": (_I, [_P, _I, _I, _U64, _F, _U64, _P]),
     "avhot_synth_audio": (_I, [_P, _I, _I, _U64, _U64, _P]),
@@ -170,3 +175,28 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t if t.is_contiguous() else t.contiguous()
+
+
+def prof_enable(on: bool = True) -> None:
+    load().avhot_prof_enable(1 if on else 0)
+
+
+def prof_reset() -> None:
+    load().avhot_prof_reset()
+
+
+def prof_report() -> dict:
+    """{kernel name: (total ms, launches)} since the last reset (synchronises)."""
+    lib = load()
+    buf = C.create_string_buffer(4096)
+    check(lib.avhot_prof_names(buf, 4096))
+    out = {}
+    for name in [n for n in buf.value.decode().split("\n") if n]:
+        ms, n = C.c_double(), C.c_int()
+        check(lib.avhot_prof_read(name.encode(), C.byref(ms), C.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out
+
+
+def launch_count() -> int:
+    return int(load().avhot_launch_count())

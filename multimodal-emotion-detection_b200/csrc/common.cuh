@@ -10,6 +10,16 @@
 namespace avhot {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library is counted (avhot_launch_count)
+
+// Optional per-kernel timing (avhot_prof_*): CUDA events recorded on the launching stream around the
+// launches of one named kernel.  A no-op unless enabled, so the product path pays one branch.
+struct ProfScope {
+  cudaStream_t s;
+  int slot;
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+};
 
 #define AVHOT_REQUIRE(cond, code, ...)     \
   do {                                     \
@@ -31,6 +41,7 @@ void set_error(const char* fmt, ...);
 
 #define AVHOT_LAUNCH_CHECK()                                                            \
   do {                                                                                  \
+    ::avhot::count_launch();                                                            \
     cudaError_t e__ = cudaGetLastError();                                               \
     if (e__ != cudaSuccess) {                                                           \
       ::avhot::set_error("%s:%d launch -> %s", __FILE__, __LINE__,                     \
@@ -49,7 +60,8 @@ int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
 // Exactly one of a_f32 / a_u8 is non-NULL (u8 pixel k means fp32(k)/255).  K % 4 == 0.
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, int ldw,
-             const float* bias, float* c, int ldc, int M, int N, int K, int act, cudaStream_t s);
+             const float* bias, float* c, int ldc, int M, int N, int K, int act, cudaStream_t s,
+             const char* prof_name = "gemm_f32");
 
 // ---------------------------------------------------------------------------
 // Philox-4x32-10 (oracle/philox.py is the written spec; Random123 algorithm).

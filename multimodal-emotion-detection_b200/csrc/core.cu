@@ -1,5 +1,11 @@
 // Library plumbing: error strings, version, device check, small layout kernels.
 #include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -12,6 +18,41 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfEntry {
+  std::string name;
+  std::vector<cudaEvent_t> ev;   // start, stop, start, stop, ...
+};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mutex;
+static std::vector<ProfEntry> g_prof;
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : s(stream), slot(-1) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (size_t i = 0; i < g_prof.size(); ++i)
+    if (g_prof[i].name == name) slot = (int)i;
+  if (slot < 0) {
+    g_prof.push_back(ProfEntry{name, {}});
+    slot = (int)g_prof.size() - 1;
+  }
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { slot = -1; return; }
+  cudaEventRecord(e, s);
+  g_prof[slot].ev.push_back(e);
+}
+
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { g_prof[slot].ev.pop_back(); return; }
+  cudaEventRecord(e, s);
+  g_prof[slot].ev.push_back(e);
 }
 
 int num_sms() {
@@ -74,5 +115,48 @@ extern "C" int avhot_check_device(void) {
   AVHOT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   AVHOT_REQUIRE(major == 10 && minor == 0, AVHOT_ERR_UNSUPPORTED,
                 "libavhot is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+  return AVHOT_OK;
+}
+
+extern "C" long long avhot_launch_count(void) { return avhot::g_launches.load(); }
+
+extern "C" int avhot_prof_enable(int on) {
+  avhot::g_prof_on.store(on ? 1 : 0);
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_prof_reset(void) {
+  std::lock_guard<std::mutex> lock(avhot::g_prof_mutex);
+  for (auto& p : avhot::g_prof)
+    for (cudaEvent_t e : p.ev) cudaEventDestroy(e);
+  avhot::g_prof.clear();
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_prof_read(const char* name, double* total_ms, int* launches) {
+  AVHOT_REQUIRE(name && total_ms && launches, AVHOT_ERR_INVALID, "prof_read: null argument");
+  std::lock_guard<std::mutex> lock(avhot::g_prof_mutex);
+  *total_ms = 0.0;
+  *launches = 0;
+  for (auto& p : avhot::g_prof) {
+    if (p.name != name) continue;
+    for (size_t i = 0; i + 1 < p.ev.size(); i += 2) {
+      AVHOT_CUDA(cudaEventSynchronize(p.ev[i + 1]));
+      float ms = 0.f;
+      AVHOT_CUDA(cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]));
+      *total_ms += ms;
+      *launches += 1;
+    }
+  }
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_prof_names(char* buf, int buf_bytes) {
+  AVHOT_REQUIRE(buf && buf_bytes > 0, AVHOT_ERR_INVALID, "prof_names: bad buffer");
+  std::lock_guard<std::mutex> lock(avhot::g_prof_mutex);
+  std::string all;
+  for (auto& p : avhot::g_prof) all += p.name + "\n";
+  strncpy(buf, all.c_str(), (size_t)buf_bytes - 1);
+  buf[buf_bytes - 1] = 0;
   return AVHOT_OK;
 }

@@ -224,7 +224,7 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
                 "frame_hidden: precision %d not built (only AVHOT_PREC_FP32)", precision);
   AVHOT_REQUIRE((long long)B * F <= 0x7fffffff / 2, AVHOT_ERR_INVALID, "frame_hidden: B*F too large for one call");
   return gemm_f32(frames_f32, frames_u8, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim,
-                  B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream));
+                  B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
 }
 
 extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B,
@@ -237,6 +237,7 @@ extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t
   const long long rows = (long long)B * T;
   const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
   AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail: B*T too large for one call");
+  ProfScope prof("frame_tail", as_stream(stream));
   frame_tail_kernel<<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
       hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
       make_drop(p, seed, clip0, t0));

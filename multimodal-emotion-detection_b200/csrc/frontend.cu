@@ -335,6 +335,7 @@ extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samp
   // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
   AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FeSmem)));
+  ProfScope prof("frontend", as_stream(stream));
   frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), as_stream(stream)>>>(wave, feats, n_samples,
                                                                               n_frames, tab);
   AVHOT_LAUNCH_CHECK();

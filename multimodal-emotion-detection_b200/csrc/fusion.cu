@@ -584,6 +584,7 @@ extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host
     P.ds = make_drop(p, seed, clip0, t0);
     AVHOT_CUDA(cudaFuncSetAttribute(hybrid_fusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(FusionSmem)));
+    ProfScope prof("hybrid_fusion", s);
     hybrid_fusion_kernel<<<(unsigned)grid, FTHREADS, sizeof(FusionSmem), s>>>(P);
     AVHOT_LAUNCH_CHECK();
   } else {
@@ -601,6 +602,7 @@ extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host
     P.w0t = h->h0_wt; P.b0 = h->h0_b; P.w2 = h->cls_w; P.b2 = h->cls_b;
     const size_t smem = sizeof(float) * FRT * (size_t)(h->head_in + FD);
     AVHOT_CUDA(cudaFuncSetAttribute(concat_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof("concat_head", s);
     concat_head_kernel<<<(unsigned)grid, FTHREADS, smem, s>>>(P);
     AVHOT_LAUNCH_CHECK();
   }

@@ -119,7 +119,8 @@ gemm_f32_kernel(const float* __restrict__ A, const uint8_t* __restrict__ A8, int
 }
 
 int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, int ldw,
-             const float* bias, float* c, int ldc, int M, int N, int K, int act, cudaStream_t s) {
+             const float* bias, float* c, int ldc, int M, int N, int K, int act, cudaStream_t s,
+             const char* prof_name) {
   AVHOT_REQUIRE((a_f32 != nullptr) != (a_u8 != nullptr), AVHOT_ERR_INVALID, "gemm: exactly one A operand");
   AVHOT_REQUIRE(w && c && M >= 0 && N > 0 && K > 0, AVHOT_ERR_INVALID, "gemm: bad arguments");
   AVHOT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0, AVHOT_ERR_INVALID,
@@ -131,6 +132,7 @@ int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, i
   if (M == 0) return AVHOT_OK;
   dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM));
   AVHOT_REQUIRE(grid.y <= 65535, AVHOT_ERR_INVALID, "gemm: M too large for one launch");
+  ProfScope prof(prof_name, s);
   if (a_u8)
     gemm_f32_kernel<true><<<grid, GTHREADS, 0, s>>>(nullptr, a_u8, lda, w, ldw, bias, c, ldc, M, N, K, act);
   else

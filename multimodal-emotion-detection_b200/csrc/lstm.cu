@@ -209,11 +209,13 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
   for (int l = 0; l < h->num_layers; ++l) {
     const float* x = l == 0 ? seq : h_seq;
     const int in = l == 0 ? h->input_dim : H;
-    int rc = gemm_f32(x, nullptr, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s);
+    int rc = gemm_f32(x, nullptr, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s,
+                      "lstm_input_gemm");
     if (rc != AVHOT_OK) return rc;
     const bool last = l == h->num_layers - 1;
     float* hs_out = last ? nullptr : h_seq;   // layer l overwrites its own input only after xp is formed
     float* hl_out = last ? h_last : nullptr;
+    ProfScope prof("lstm_recurrence", s);
     if (small) {
       constexpr int BT = 4;
       const size_t smem = sizeof(float) * 2 * LH * (BT + 4);
@@ -227,5 +229,6 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
     }
     AVHOT_LAUNCH_CHECK();
   }
-  return gemm_f32(h_last, nullptr, H, h->proj_w, H, h->proj_b, out, h->output_dim, B, h->output_dim, H, ACT_NONE, s);
+  return gemm_f32(h_last, nullptr, H, h->proj_w, H, h->proj_b, out, h->output_dim, B, h->output_dim, H, ACT_NONE, s,
+                  "lstm_projection");
 }

@@ -250,6 +250,7 @@ extern "C" int avhot_mc_reduce(const float* logits, float* mean_logits, float* u
   AVHOT_REQUIRE(logits && B >= 0 && T >= 1 && C >= 1 && C <= 32, AVHOT_ERR_INVALID,
                 "mc_reduce: bad arguments (1 <= C <= 32)");
   if (B == 0) return AVHOT_OK;
+  ProfScope prof("mc_reduce", as_stream(stream));
   mc_reduce_kernel<<<ceil_div(B, 4), 128, 0, as_stream(stream)>>>(logits, mean_logits, uncertainty, labels, packed,
                                                                  B, T, C);
   AVHOT_LAUNCH_CHECK();

@@ -95,6 +95,30 @@ def sequence_encoder_lstm(seq, sd, prefix="encoders.audio.", num_layers=2):
     return _lin(h, sd, prefix + "projection")
 
 
+_LSTM_CACHE = {}
+
+
+def sequence_encoder_lstm_torch(seq, sd, prefix="encoders.audio.", num_layers=2):
+    """Same function as sequence_encoder_lstm, computed by torch.nn.LSTM on CPU - the op the reference itself
+    calls (src/encoders.py:54-61, :148-154).  Used for the CPU-baseline timing so the baseline pays what the
+    reference pays (ATen's fused LSTM cell), not the cost of a Python time loop; checked against the written-out
+    recurrence in tests/test_oracle_model.py."""
+    key = (id(sd), prefix, num_layers, seq.dtype)
+    rnn = _LSTM_CACHE.get(key)
+    if rnn is None:
+        H = sd[f"{prefix}rnn.weight_hh_l0"].shape[1]
+        rnn = torch.nn.LSTM(input_size=sd[f"{prefix}rnn.weight_ih_l0"].shape[1], hidden_size=H,
+                            num_layers=num_layers, batch_first=True, bidirectional=False).to(seq.dtype)
+        rnn.load_state_dict({k[len(prefix) + 4:]: v.to(seq.dtype) for k, v in sd.items()
+                             if k.startswith(prefix + "rnn.")}, strict=True)
+        rnn.eval()
+        _LSTM_CACHE.clear()
+        _LSTM_CACHE[key] = rnn
+    with torch.inference_mode():
+        _, (h_n, _) = rnn(seq)
+    return _lin(h_n[-1], sd, prefix + "projection")
+
+
 def frame_hidden(frames, sd, prefix="encoders.video."):
     """frame_mlp[0:2]: Linear(frame_dim -> H) + ReLU, before dropout.  src/encoders.py:225-227,272."""
     return torch.relu(_lin(frames, sd, prefix + "frame_mlp.0"))
@@ -243,6 +267,22 @@ def mc_statistics(logits_stack):
     probs = _softmax(logits_stack, dim=-1)
     var = ((probs - probs.mean(dim=0, keepdim=True)) ** 2).mean(dim=0)
     return mean_logits, var.mean(dim=-1)
+
+
+def mc_dropout_forward_as_reference(feats, frames, mask, sd, T, seed, clip_ids, head="hybrid",
+                                    p_encoder=0.1, p_fusion=0.3):
+    """MCDropoutUncertainty exactly as the reference executes it (src/uncertainty.py:62-65): T FULL forwards of
+    the model - audio encoder (torch.nn.LSTM) and video Linear + ReLU recomputed every pass.  Same values as
+    mc_dropout_forward; this is the one the CPU baseline times."""
+    stack = []
+    with torch.inference_mode():
+        for t in range(T):
+            ctx = DropCtx(seed=seed, t=t, clip_ids=np.asarray(clip_ids), p_encoder=p_encoder, p_fusion=p_fusion)
+            z_audio = sequence_encoder_lstm_torch(feats, sd)
+            stack.append(av_forward(None, frames, mask, sd, head, ctx, z_audio=z_audio))
+        stack = torch.stack(stack, dim=0)
+        mean_logits, unc = mc_statistics(stack)
+    return mean_logits, unc, stack
 
 
 def mc_dropout_forward(feats, frames, mask, sd, T, seed, clip_ids, head="hybrid",

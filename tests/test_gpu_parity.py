@@ -1,0 +1,389 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the reference-generated golden
+vectors, on the same seeded inputs.  Tolerances (BASELINE.json north_star): features and logits within 1e-4
+relative in fp32; dropout masks, synthetic inputs and predicted labels bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import frontend as ofe, model as om, philox as px, synth as osynth
+
+SEED = 42
+REL = 1e-4
+
+
+def rel_err(got, want):
+    """norm-wise relative error max|got - want| / max|want| (the '1e-4 relative' of the north star)."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import multimodal_emotion_detection_b200 as p
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    p._lib.check_device(torch.device("cuda:0"))
+    return p
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def world(golden):
+    """Seeded inputs / weights shared by the tests (oracle side, CPU)."""
+    ids = golden["clip_ids"]
+    sd_np = osynth.synth_weights(SEED)
+    wave = osynth.synth_audio(ids, SEED)
+    frames_u8 = osynth.synth_video_u8(ids, SEED)
+    frames = frames_u8.astype(np.float32) / np.float32(255.0)
+    feats = ofe.logmel_mfcc(wave)
+    return dict(ids=ids, sd_np=sd_np, sd=om.to_torch(sd_np), sd64=om.to_torch(sd_np, torch.float64), wave=wave,
+                frames=frames, frames_u8=frames_u8, feats=feats)
+
+
+def make_model(pkg, dev, world, head="hybrid"):
+    m = pkg.AVHotPath(head)
+    drop = "fusion_head." if head == "hybrid" else "fusion_model."
+    m.load_state_dict({k: v for k, v in world["sd"].items() if not k.startswith(drop)}, strict=True)
+    return m.to(dev).eval()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bit-exact pieces: synthetic inputs, masks
+# ---------------------------------------------------------------------------------------------------------
+def test_synth_inputs_bit_exact(pkg, dev):
+    for clip0, B in ((0, 5), (1000003, 3), (4294967294, 2)):
+        ids = (np.arange(B, dtype=np.uint64) + np.uint64(clip0))
+        a = pkg.synth.synth_audio(B, clip0, SEED, dev).cpu().numpy()
+        assert (a == osynth.synth_audio(ids, SEED)).all()
+        v8 = pkg.synth.synth_video(B, clip0, SEED, dev, dtype=torch.uint8).cpu().numpy()
+        assert (v8 == osynth.synth_video_u8(ids, SEED)).all()
+        v = pkg.synth.synth_video(B, clip0, SEED, dev).cpu().numpy()
+        assert (v == osynth.synth_video(ids, SEED)).all()
+    a = pkg.synth.synth_audio(4, 7, SEED, dev)
+    assert float(a.abs().max(dim=1).values.min()) == 1.0          # peak-normalised (src/dataprocessing.py:207-208)
+
+
+def test_dropout_masks_bit_exact(pkg, dev):
+    ids = np.array([0, 1, 2, 77], dtype=np.uint64)
+    for site, n, p in ((px.SITE_FRAME_MLP, 16 * 256, 0.1), (px.SITE_FRAME_POOL, 256, 0.1), (px.SITE_GATE, 256, 0.3),
+                       (px.SITE_ATTN, 8, 0.3), (px.SITE_ATTN + 1, 8, 0.3), (px.SITE_GATE, 7, 0.5)):
+        for t in (0, 5, 31):
+            got = pkg.synth.dropout_keep(3, n, 0, t, site, p, SEED, dev).cpu().numpy().astype(bool)
+            assert (got == px.dropout_keep(n, ids[:3], t, site, p, SEED)).all()
+    got = pkg.synth.dropout_keep(1, 256, 77, 2, px.SITE_GATE, 0.3, 123456789012345, dev).cpu().numpy().astype(bool)
+    assert (got == px.dropout_keep(256, ids[3:], 2, px.SITE_GATE, 0.3, 123456789012345)).all()
+
+
+def test_modality_mask_bit_exact(pkg, dev):
+    ids = np.arange(5000, dtype=np.uint64) + np.uint64(123)
+    for p in (0.0, 0.05, 0.9):
+        got = pkg.synth.modality_mask(5000, 123, p, SEED, dev).cpu().numpy()
+        assert (got == px.modality_mask(ids, 2, p, SEED)).all()
+
+
+def test_condition_audio(pkg, dev):
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(4, 5000)).astype(np.float32)
+    x[2] = 0.0                                                     # silent clip: no division (:207)
+    lengths = np.array([5000, 1234, 5000, 1], dtype=np.int32)
+    for n_out in (3000, 5000, 8000):
+        got = pkg.condition_audio(torch.from_numpy(x).to(dev), torch.from_numpy(lengths).to(dev), n_out).cpu().numpy()
+        for b in range(4):
+            L = min(int(lengths[b]), n_out)
+            y = np.zeros(n_out, dtype=np.float32)
+            y[:L] = x[b, :L]
+            peak = np.abs(y).max()
+            if peak > 0:
+                y = y / peak
+            assert (got[b] == y).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a2 front-end
+# ---------------------------------------------------------------------------------------------------------
+def test_frontend_vs_oracle(pkg, dev, world, golden):
+    got = pkg.logmel_mfcc(torch.from_numpy(world["wave"]).to(dev)).cpu().numpy()
+    want = world["feats"]
+    assert got.shape == want.shape == (6, 301, 104)
+    assert rel_err(got, want) <= REL
+    assert rel_err(got[..., :64], want[..., :64]) <= REL and rel_err(got[..., 64:], want[..., 64:]) <= REL
+    assert np.abs(got - want).max() <= 5e-3                        # dB / DCT-of-dB units
+    assert rel_err(got[0], golden["feats_clip0"]) <= REL and rel_err(got[-1], golden["feats_last"]) <= REL
+    mel, dct, win = pkg.dataprocessing.frontend_tables()
+    np.testing.assert_allclose(mel, ofe.mel_filterbank(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(dct, ofe.dct_matrix(), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(win, ofe.hann_periodic(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("n", [257, 1000, 1600, 16000, 48000, 48160])
+def test_frontend_ragged_lengths_and_silence(pkg, dev, n):
+    rng = np.random.default_rng(n)
+    w = rng.uniform(-1, 1, size=(3, n)).astype(np.float32)
+    w[1] = 0.0                                                     # silence -> log floor
+    w[2, n // 2:] = 0.0                                            # zero tail (right padding)
+    got = pkg.logmel_mfcc(torch.from_numpy(w).to(dev)).cpu().numpy()
+    want = ofe.logmel_mfcc(w)
+    assert got.shape == want.shape == (3, 1 + n // 160, 104)
+    assert rel_err(got, want) <= REL
+    assert np.allclose(got[1, :, :64], -100.0, atol=1e-4)
+
+
+def test_frontend_rejects_bad_input(pkg, dev):
+    with pytest.raises(ValueError):
+        pkg.logmel_mfcc(torch.zeros(2, 100, device=dev))           # shorter than the reflect pad
+    with pytest.raises(ValueError):
+        pkg.logmel_mfcc(torch.zeros(2, 3, 4, 5, device=dev))
+    assert pkg.logmel_mfcc(torch.zeros(0, 48000, device=dev)).shape == (0, 301, 104)
+    assert pkg.logmel_mfcc(torch.zeros(2, 48000, 1, device=dev)).shape == (2, 301, 104)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a3 LSTM encoder
+# ---------------------------------------------------------------------------------------------------------
+def test_sequence_encoder_vs_oracle_and_golden(pkg, dev, world, golden):
+    m = make_model(pkg, dev, world)
+    feats = torch.from_numpy(world["feats"])
+    got = m.encoders["audio"](feats.to(dev)).cpu().numpy()
+    want64 = om.sequence_encoder_lstm(feats.double(), world["sd64"]).numpy()
+    assert rel_err(got, want64) <= REL
+    assert rel_err(got, golden["z_audio"]) <= REL                  # the reference's own nn.LSTM output
+
+
+def test_sequence_encoder_lengths_and_small_shapes(pkg, dev, world):
+    m = make_model(pkg, dev, world)
+    enc = m.encoders["audio"]
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(5, 12, 104)).astype(np.float32)
+    lengths = np.array([12, 1, 7, 12, 3])
+    got = enc(torch.from_numpy(x).to(dev), torch.from_numpy(lengths)).cpu().numpy()
+    for b in range(5):                                             # packed-sequence semantics (:139-147)
+        want = om.sequence_encoder_lstm(torch.from_numpy(x[b:b + 1, :lengths[b]]).double(), world["sd64"]).numpy()
+        assert rel_err(got[b:b + 1], want) <= REL
+    full = enc(torch.from_numpy(x).to(dev)).cpu().numpy()
+    want = om.sequence_encoder_lstm(torch.from_numpy(x).double(), world["sd64"]).numpy()
+    assert rel_err(full, want) <= REL
+    big = enc(torch.from_numpy(np.tile(x, (80, 1, 1))).to(dev)).cpu().numpy()   # B = 400: the 32-clip tile kernel
+    assert rel_err(big[:5], want) <= REL and (big[5:10] == big[:5]).all()
+    assert enc(torch.zeros(0, 12, 104, device=dev)).shape == (0, 128)
+    with pytest.raises(ValueError):
+        enc(torch.zeros(2, 12, 100, device=dev))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a4 frame encoder
+# ---------------------------------------------------------------------------------------------------------
+def test_frame_encoder_eval(pkg, dev, world, golden):
+    m = make_model(pkg, dev, world)
+    enc = m.encoders["video"]
+    frames = torch.from_numpy(world["frames"])
+    hid = enc.hidden(frames.to(dev))
+    want_hid = om.frame_hidden(frames.double(), world["sd64"]).numpy()
+    assert rel_err(hid.cpu().numpy(), want_hid) <= REL
+    hid8 = enc.hidden(torch.from_numpy(world["frames_u8"]).to(dev))                 # u8 ingest == fp32 k/255
+    assert (hid8 == hid).all()
+    got = enc(frames.to(dev)).cpu().numpy()
+    assert rel_err(got, golden["z_video"]) <= REL
+    assert rel_err(got, om.frame_encoder(frames.double(), world["sd64"]).numpy()) <= REL
+
+
+def test_frame_encoder_dropout_passes_and_mask(pkg, dev, world):
+    m = make_model(pkg, dev, world)
+    enc = m.encoders["video"]
+    frames = torch.from_numpy(world["frames"])
+    hid = enc.hidden(frames.to(dev))
+    hid64 = om.frame_hidden(frames.double(), world["sd64"])
+    T = 5
+    z = enc.tail(hid, None, T, 0.1, SEED, 0, 0).cpu().numpy()      # clips 0..5 are ids 0..5 only for the first 4
+    ids = np.arange(6, dtype=np.uint64)
+    for t in range(T):
+        ctx = om.DropCtx(seed=SEED, t=t, clip_ids=ids, p_encoder=0.1)
+        want = om.frame_encoder_tail(hid64, world["sd64"], ctx=ctx).numpy()
+        assert rel_err(z[:, t], want) <= REL
+    z2 = enc.tail(hid[2:4], None, 2, 0.1, SEED, 2, 3).cpu().numpy()   # clip0 / t0 offsets select the same masks
+    assert (z2 == z[2:4, 3:5]).all()
+    # forward(frames, mask): invalid frames get no weight (src/encoders.py:321-324)
+    valid = torch.ones(6, 16, dtype=torch.bool)
+    valid[1, 5:] = False
+    valid[2, :15] = False
+    got = enc(frames.to(dev), valid.to(dev)).cpu().numpy()
+    x = hid64
+    scores = (x @ world["sd64"]["encoders.video.attention.weight"].T + world["sd64"]["encoders.video.attention.bias"]).squeeze(-1)
+    scores = scores.masked_fill(~valid, torch.finfo(torch.float32).min)
+    pooled = (torch.softmax(scores, dim=1).unsqueeze(-1) * x).sum(dim=1)
+    y = om._layer_norm(pooled, world["sd64"]["encoders.video.projection.0.weight"], world["sd64"]["encoders.video.projection.0.bias"])
+    want = om._lin(y, world["sd64"], "encoders.video.projection.1").numpy()
+    assert rel_err(got, want) <= REL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a5 / a6 / a7 fusion
+# ---------------------------------------------------------------------------------------------------------
+def _masks(world):
+    ids = world["ids"]
+    return {"ones": np.ones((6, 2), np.float32),
+            "mixed": np.array([[1, 1], [1, 0], [0, 1], [0, 0], [1, 1], [0, 1]], np.float32),
+            "p05": px.modality_mask(ids, 2, 0.05, SEED)}
+
+
+def test_hybrid_fusion_vs_reference_golden(pkg, dev, world, golden):
+    m = make_model(pkg, dev, world)
+    fm = m.fusion_model
+    feats = {"audio": torch.from_numpy(golden["z_audio"]).to(dev), "video": torch.from_numpy(golden["z_video"]).to(dev)}
+    for name, mask in _masks(world).items():
+        logits, info = fm(feats, torch.from_numpy(mask).to(dev), return_attention=True)
+        assert rel_err(logits.cpu().numpy(), golden[f"logits_hybrid_{name}"]) <= REL
+        assert rel_err(info["fusion_weights"].cpu().numpy(), golden[f"fusion_weights_{name}"]) <= REL
+        assert rel_err(info["per_modality_attention"]["audio"].cpu().numpy(), golden[f"attn_audio_{name}"]) <= REL
+        assert rel_err(info["per_modality_attention"]["video"].cpu().numpy(), golden[f"attn_video_{name}"]) <= REL
+        assert info["H_att"].shape == (6, 2, 256)
+        assert info["per_modality_attention"]["audio"].shape == (6, 4, 1, 2)
+        only = fm(feats, torch.from_numpy(mask).to(dev))
+        assert isinstance(only, torch.Tensor) and (only == logits).all()
+    none_mask = fm(feats).cpu().numpy()                            # modality_mask=None == ones (:468-469)
+    assert rel_err(none_mask, golden["logits_hybrid_ones"]) <= REL
+    # absent modality: zero features + masked (:480-485)
+    got = fm({"audio": feats["audio"], "video": None}).cpu().numpy()
+    z = {"audio": torch.from_numpy(golden["z_audio"]).double(), "video": torch.zeros(6, 128, dtype=torch.float64)}
+    want = om.hybrid_fusion(z, torch.tensor([[1.0, 0.0]] * 6), world["sd64"]).numpy()
+    assert rel_err(got, want) <= REL
+
+
+def test_hybrid_fusion_dropout_vs_oracle(pkg, dev, world, golden):
+    m = make_model(pkg, dev, world)
+    fm = m.fusion_model
+    pkg.MCDropoutUncertainty._set_dropout_train(fm)
+    z = {"audio": torch.from_numpy(golden["z_audio"]), "video": torch.from_numpy(golden["z_video"])}
+    zd = {k: v.to(dev) for k, v in z.items()}
+    z64 = {k: v.double() for k, v in z.items()}
+    ids = np.arange(6, dtype=np.uint64) + np.uint64(100)
+    mask = _masks(world)["mixed"]
+    for t in (0, 3):
+        with pkg.philox_context(SEED, t, 100):
+            got, info = fm(zd, torch.from_numpy(mask).to(dev), return_attention=True)
+        ctx = om.DropCtx(seed=SEED, t=t, clip_ids=ids, p_fusion=0.3)
+        want, winfo = om.hybrid_fusion(z64, torch.from_numpy(mask), world["sd64"], ctx=ctx, return_info=True)
+        assert rel_err(got.cpu().numpy(), want.numpy()) <= REL
+        assert rel_err(info["per_modality_attention"]["video"].cpu().numpy(), winfo["per_modality_attention"][1].numpy()) <= REL
+        assert rel_err(info["fusion_weights"].cpu().numpy(), winfo["fusion_weights"].numpy()) <= REL
+
+
+def test_cross_modal_attention_general_shapes(pkg, dev, golden):
+    att = pkg.CrossModalAttention(query_dim=512, key_dim=64, hidden_dim=256, num_heads=4, dropout=0.1)
+    att.load_state_dict({k[len("xattn.att."):]: torch.from_numpy(golden[k]) for k in golden.files
+                         if k.startswith("xattn.att.")}, strict=True)
+    att = att.to(dev).eval()
+    q, kv = torch.from_numpy(golden["xattn.q"]).to(dev), torch.from_numpy(golden["xattn.kv"]).to(dev)
+    inv = torch.from_numpy(golden["xattn.invalid"]).to(dev)
+    out, attn = att(q, kv, kv, inv)
+    assert out.shape == (4, 3, 256) and attn.shape == (4, 4, 3, 5)
+    assert rel_err(out.cpu().numpy(), golden["xattn.out"]) <= REL
+    assert rel_err(attn.cpu().numpy(), golden["xattn.attn"]) <= REL
+    out1, attn1 = att(q[:, 0], kv, kv, (~inv).float())             # (B, D) query, numeric 1 = valid mask
+    assert out1.shape == (4, 256) and rel_err(out1.cpu().numpy(), golden["xattn.out"][:, 0]) <= REL
+    # dropout on the attention weights draws the spec masks
+    att.attn_dropout.train()
+    with pkg.philox_context(SEED, 2, 9):
+        _, attn_d = att(q, kv, kv, inv)
+    keep = px.dropout_keep(4 * 3 * 5, np.arange(4, dtype=np.uint64) + np.uint64(9), 2, px.SITE_ATTN, 0.1, SEED)
+    want = golden["xattn.attn"].reshape(4, -1) * keep / (1 - 0.1)
+    assert rel_err(attn_d.cpu().numpy().reshape(4, -1), want) <= REL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole path + a8 MC-dropout
+# ---------------------------------------------------------------------------------------------------------
+def _features(world, dev, u8=False):
+    v = torch.from_numpy(world["frames_u8"] if u8 else world["frames"]).to(dev)
+    return {"audio": torch.from_numpy(world["wave"]).to(dev), "video": v}
+
+
+@pytest.mark.parametrize("head", ["hybrid", "concat"])
+def test_full_path_vs_reference_golden(pkg, dev, world, golden, head):
+    m = make_model(pkg, dev, world, head)
+    feats = _features(world, dev)
+    for name, mask in _masks(world).items():
+        if head == "concat" and name != "ones":
+            continue
+        got = m(feats, torch.from_numpy(mask).to(dev)).cpu().numpy()
+        want = golden[f"logits_{head}_{name}"]
+        assert rel_err(got, want) <= REL
+        assert (got.argmax(1) == want.argmax(1)).all()
+    got8 = m(_features(world, dev, u8=True)).cpu().numpy()
+    assert rel_err(got8, golden[f"logits_{head}_ones"]) <= REL
+    pre = m({"audio": torch.from_numpy(world["feats"]).to(dev), "video": feats["video"]}).cpu().numpy()
+    assert rel_err(pre, golden[f"logits_{head}_ones"]) <= REL      # precomputed (B, 301, 104) features accepted
+
+
+@pytest.mark.parametrize("head,names", [("hybrid", ("ones", "p05")), ("concat", ("ones",))])
+def test_mc_dropout_vs_reference_golden(pkg, dev, world, golden, head, names):
+    """The reference's MCDropoutUncertainty ran unmodified over mask-injected reference modules (make_golden.py);
+    clip ids there are NOT contiguous, so each clip runs with its own clip0."""
+    m = make_model(pkg, dev, world, head)
+    T = int(golden["t_mc"])
+    ids = world["ids"]
+    feats = _features(world, dev)
+    for name in names:
+        mask = torch.from_numpy(_masks(world)[name]).to(dev)
+        means, uncs = [], []
+        for b, g in enumerate(ids):
+            mc = pkg.MCDropoutUncertainty(m, num_samples=T)
+            mc.seed, mc.clip0 = SEED, int(g)
+            mean, unc = mc({k: v[b:b + 1] for k, v in feats.items()}, mask[b:b + 1])
+            means.append(mean)
+            uncs.append(unc)
+        mean = torch.cat(means).cpu().numpy()
+        unc = torch.cat(uncs).cpu().numpy()
+        assert rel_err(mean, golden[f"mc_mean_logits_{head}_{name}"]) <= REL
+        assert rel_err(unc, golden[f"mc_uncertainty_{head}_{name}"]) <= 1e-3
+        assert (mean.argmax(1) == golden[f"mc_labels_{head}_{name}"]).all()
+        assert not m.training and not m.encoders["video"]._dropout.training   # modes restored
+
+
+def test_mc_fused_equals_pass_by_pass(pkg, dev, world):
+    """Hoisting the pass-invariant stages changes nothing: the fused T-pass path equals T separate forwards."""
+    m = make_model(pkg, dev, world)
+    feats = _features(world, dev)
+    mask = torch.from_numpy(_masks(world)["p05"]).to(dev)
+    T = 6
+    pkg.MCDropoutUncertainty._set_dropout_train(m)
+    mean, unc, labels, packed = m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=500)
+    stack = []
+    for t in range(T):
+        with pkg.philox_context(SEED, t, 500):
+            stack.append(m(feats, mask))
+    stack = torch.stack(stack, dim=1)
+    mean2, unc2, labels2, packed2 = pkg.mc_reduce(stack)
+    assert (mean == mean2).all() and (unc == unc2).all() and (labels == labels2).all() and (packed == packed2).all()
+    want_mean, want_unc = om.mc_statistics(stack.transpose(0, 1).cpu().double())
+    assert rel_err(mean.cpu().numpy(), want_mean.numpy()) <= 1e-6
+    assert rel_err(unc.cpu().numpy(), want_unc.numpy()) <= 1e-4
+    assert (labels.cpu().numpy() == want_mean.argmax(1).numpy()).all()
+    assert (packed[:, :8] == mean).all() and (packed[:, 8] == unc).all()
+    m.eval()
+    assert (m.mc_forward(feats, mask, num_samples=3)[1] == 0).all()   # eval mode: no dropout, zero variance
+
+
+def test_shard_invariance_and_determinism(pkg, dev, world):
+    """Size-independent properties at a benchmark-like batch: results do not depend on how clips are batched or
+    sharded (masks and inputs are keyed by global clip index), and repeat bit-exactly."""
+    m = make_model(pkg, dev, world)
+    pkg.MCDropoutUncertainty._set_dropout_train(m)
+    B, T, clip0 = 96, 8, 10_000
+    def run(lo, hi):
+        n = hi - lo
+        f = {"audio": pkg.synth.synth_audio(n, clip0 + lo, SEED, dev), "video": pkg.synth.synth_video(n, clip0 + lo, SEED, dev)}
+        mask = pkg.synth.modality_mask(n, clip0 + lo, 0.05, SEED, dev)
+        return m.mc_forward(f, mask, num_samples=T, seed=SEED, clip0=clip0 + lo)[3]
+    whole = run(0, B)
+    again = run(0, B)
+    assert (whole == again).all()
+    parts = torch.cat([run(0, 40), run(40, 41), run(41, B)])
+    # the LSTM / fusion tile kernels reduce in a fixed order per clip, so batching does not change a single bit
+    assert (parts == whole).all()
+    assert torch.isfinite(whole).all() and (whole[:, 8] >= 0).all()

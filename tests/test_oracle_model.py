@@ -65,3 +65,16 @@ def test_fp64_oracle_close_to_fp32(golden):
     z32 = om.frame_encoder(frames[:2], sd)
     z64 = om.frame_encoder(frames[:2].double(), sd64)
     assert (z32.double() - z64).abs().max() < 1e-5
+
+
+def test_reference_style_execution_matches_hoisted(golden):
+    """The CPU-baseline path (torch.nn.LSTM, T full forwards like src/uncertainty.py:62-65) computes the same
+    numbers as the hoisted, written-out oracle."""
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    z1 = om.sequence_encoder_lstm(feats[:3], sd)
+    z2 = om.sequence_encoder_lstm_torch(feats[:3], sd)
+    np.testing.assert_allclose(z2.numpy(), z1.numpy(), rtol=1e-4, atol=2e-6)
+    a = om.mc_dropout_forward(feats[:3], frames[:3], masks["p05"][:3], sd, 3, seed, ids[:3])
+    b = om.mc_dropout_forward_as_reference(feats[:3], frames[:3], masks["p05"][:3], sd, 3, seed, ids[:3])
+    np.testing.assert_allclose(b[0].numpy(), a[0].numpy(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(b[1].numpy(), a[1].numpy(), rtol=1e-3, atol=1e-8)
