@@ -366,7 +366,7 @@ def test_mc_fused_equals_pass_by_pass(pkg, dev, world):
     assert (labels.cpu().numpy() == want_mean.argmax(1).numpy()).all()
     assert (packed[:, :8] == mean).all() and (packed[:, 8] == unc).all()
     m.eval()
-    assert (m.mc_forward(feats, mask, num_samples=3)[1] == 0).all()   # eval mode: no dropout, zero variance
+    assert float(m.mc_forward(feats, mask, num_samples=3)[1].abs().max()) < 1e-12   # eval: identical passes
 
 
 def test_shard_invariance_and_determinism(pkg, dev, world):
