@@ -42,12 +42,14 @@ typedef enum {
   AVHOT_ERR_WORKSPACE = -4    /* caller workspace too small                */
 } avhot_status;
 
-/* arithmetic of the dense contractions (GEMM operands); accumulation is fp32 and
- * everything outside the contractions is fp32 in every mode. */
+/* arithmetic of the dense contractions (GEMM operands); accumulation is fp32 and everything
+ * outside the contractions is fp32 in every mode. */
 typedef enum {
-  AVHOT_PREC_FP32 = 0,   /* fp32 FMA on CUDA cores (bit-for-bit deterministic)        */
-  AVHOT_PREC_BF16X3 = 1, /* tcgen05, operands split hi+lo bf16, 3 MMAs: fp32-class    */
-  AVHOT_PREC_BF16 = 2    /* tcgen05, operands rounded to bf16 once: stated tolerance  */
+  AVHOT_PREC_FP32 = 0,   /* fp32 FMA on CUDA cores: the parity path (1e-4 relative)            */
+  AVHOT_PREC_BF16X3 = 1, /* reserved: split operands, 3 tensor-core passes (not built)         */
+  AVHOT_PREC_TC = 2      /* tcgen05 tensor cores, operands rounded once: TF32 for the
+                            time-batched GEMMs, fp16 for the recurrent GEMM; stated tolerance
+                            in DESIGN.md                                                       */
 } avhot_precision;
 
 int avhot_version(void);
@@ -65,6 +67,11 @@ int avhot_prof_reset(void);
 int avhot_prof_read(const char* name, double* total_ms, int* launches);
 /* newline-separated names seen since the last reset */
 int avhot_prof_names(char* buf, int buf_bytes);
+
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]) with the library's GEMM in `precision` (test entry for the
+ * contraction every nn.Linear on the path lowers to); A, W, C dense row-major, K % 4 == 0. */
+int avhot_gemm(const float* a, const float* w, const float* bias, float* c, int M, int N, int K,
+               int relu, int precision, avhot_stream_t stream);
 
 /* ---- Philox-4x32-10 spec (oracle/philox.py) ------------------------------------ */
 /* keep[b*n_elems + e] = 1 iff words(e>>2, clip0+b, t, site)[e&3] >= floor(p*2^32).

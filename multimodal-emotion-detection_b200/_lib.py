@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libavhot.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_TC = 0, 1, 2
 SITE_FRAME_MLP, SITE_FRAME_POOL, SITE_GATE, SITE_MODMASK, SITE_ATTN = 0, 1, 2, 3, 16
 MAX_MODALITIES = 4
 
@@ -69,6 +69,7 @@ PROTOTYPES = {
     "avhot_prof_reset": (_I, []),
     "avhot_prof_read": (_I, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_I)]),
     "avhot_prof_names": (_I, [C.c_char_p, _I]),
+    "avhot_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "avhot_dropout_keep": (_I, [_P, _I, _I, _U64, _U32, _U32, _F, _U64, _P]),
     "avhot_modality_mask": (_I, [_P, _I, _I, _U64, _F, _U64, _P]),
     "avhot_synth_audio": (_I, [_P, _I, _I, _U64, _U64, _P]),

@@ -63,6 +63,10 @@ int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, i
              const float* bias, float* c, int ldc, int M, int N, int K, int act, cudaStream_t s,
              const char* prof_name = "gemm_f32");
 
+// gemm_tc.cu: same contract on the tcgen05 tensor cores (fp32 operands multiplied as TF32, fp32 accumulate).
+int gemm_tf32_tc(const float* a, int lda, const float* w, int ldw, const float* bias, float* c, int ldc, int M,
+                 int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_tf32_tc");
+
 // ---------------------------------------------------------------------------
 // Philox-4x32-10 (oracle/philox.py is the written spec; Random123 algorithm).
 // ---------------------------------------------------------------------------

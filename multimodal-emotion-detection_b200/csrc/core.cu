@@ -160,3 +160,14 @@ extern "C" int avhot_prof_names(char* buf, int buf_bytes) {
   buf[buf_bytes - 1] = 0;
   return AVHOT_OK;
 }
+
+// Diagnostic / test entry: the library's GEMM  C[M,N] = act(A[M,K] W[N,K]^T + bias)  in a given precision.
+extern "C" int avhot_gemm(const float* a, const float* w, const float* bias, float* c, int M, int N, int K,
+                          int relu, int precision, avhot_stream_t stream) {
+  using namespace avhot;
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
+                "gemm: precision %d not built", precision);
+  if (precision == AVHOT_PREC_FP32)
+    return gemm_f32(a, nullptr, K, w, K, bias, c, N, M, N, K, relu ? ACT_RELU : ACT_NONE, as_stream(stream));
+  return gemm_tf32_tc(a, K, w, K, bias, c, N, M, N, K, relu ? ACT_RELU : ACT_NONE, as_stream(stream));
+}

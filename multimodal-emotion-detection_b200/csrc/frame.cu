@@ -220,9 +220,12 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
   AVHOT_REQUIRE(h && hid && B >= 0 && F >= 1, AVHOT_ERR_INVALID, "frame_hidden: bad arguments");
   AVHOT_REQUIRE((frames_f32 != nullptr) != (frames_u8 != nullptr), AVHOT_ERR_INVALID,
                 "frame_hidden: exactly one of frames_f32 / frames_u8");
-  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32, AVHOT_ERR_UNSUPPORTED,
-                "frame_hidden: precision %d not built (only AVHOT_PREC_FP32)", precision);
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
+                "frame_hidden: precision %d not built", precision);
   AVHOT_REQUIRE((long long)B * F <= 0x7fffffff / 2, AVHOT_ERR_INVALID, "frame_hidden: B*F too large for one call");
+  if (precision == AVHOT_PREC_TC && frames_f32)
+    return gemm_tf32_tc(frames_f32, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim, B * F,
+                        h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
   return gemm_f32(frames_f32, frames_u8, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim,
                   B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
 }

@@ -36,8 +36,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// Bounded wait: a barrier that does not complete within ~2 s of SM clocks means a broken pipeline (bad
+// descriptor, wrong byte count); trap so the launch fails loudly instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05 operand reads)
