@@ -67,6 +67,11 @@ int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, i
 int gemm_tf32_tc(const float* a, int lda, const float* w, int ldw, const float* bias, float* c, int ldc, int M,
                  int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_tf32_tc");
 
+// lstm_tc.cu: W_hh (4H, H) fp32 -> fp16, rows regrouped per 32-unit chunk; and the tcgen05 recurrence of one layer.
+int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s);
+int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, float* h_seq, float* h_last,
+                       const int32_t* lengths, int B, int T, cudaStream_t s);
+
 // ---------------------------------------------------------------------------
 // Philox-4x32-10 (oracle/philox.py is the written spec; Random123 algorithm).
 // ---------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct avhot_lstm {
   float* w_ih[4];    // (4H, in_k) row-major copies
   float* w_hh_t[4];  // [k][gate][j]  = W_hh[gate*H + j][k]
   float* bias[4];    // b_ih + b_hh
+  void* w_hh_r16[4]; // fp16, rows regrouped per 32-unit chunk (lstm_tc.cu)
   float* proj_w;     // (out, H)
   float* proj_b;
   float* arena;
@@ -128,7 +129,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     AVHOT_REQUIRE(d->weight_ih[l] && d->weight_hh[l] && d->bias_ih[l] && d->bias_hh[l], AVHOT_ERR_INVALID,
                   "lstm_create: layer %d tensors missing", l);
     total += align256(sizeof(float) * 4 * H * in) + align256(sizeof(float) * 4 * H * H) +
-             align256(sizeof(float) * 4 * H);
+             align256(sizeof(float) * 4 * H) + align256(2 * 4 * H * H);
   }
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
@@ -150,10 +151,12 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     h->w_ih[l] = take(sizeof(float) * 4 * H * in);
     h->w_hh_t[l] = take(sizeof(float) * 4 * H * H);
     h->bias[l] = take(sizeof(float) * 4 * H);
+    h->w_hh_r16[l] = take(2 * 4 * H * H);
     if (cudaMemcpyAsync(h->w_ih[l], d->weight_ih[l], sizeof(float) * 4 * H * in, cudaMemcpyDeviceToDevice, s) !=
         cudaSuccess) rc = AVHOT_ERR_CUDA;
     if (rc == AVHOT_OK) rc = transpose(d->weight_hh[l], h->w_hh_t[l], 4 * H, H, s);  // [k][gate*H + j]
     if (rc == AVHOT_OK) rc = add_vec(d->bias_ih[l], d->bias_hh[l], h->bias[l], 4 * H, s);
+    if (rc == AVHOT_OK) rc = lstm_pack_whh_fp16(d->weight_hh[l], h->w_hh_r16[l], s);
   }
   if (rc == AVHOT_OK) {
     h->proj_w = take(sizeof(float) * d->output_dim * H);
@@ -192,8 +195,8 @@ extern "C" size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int p
 extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_t* lengths, float* out, int B,
                                   int T, int precision, void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
   AVHOT_REQUIRE(h && seq && out && B >= 0 && T >= 1, AVHOT_ERR_INVALID, "lstm_forward: bad arguments");
-  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32, AVHOT_ERR_UNSUPPORTED,
-                "lstm_forward: precision %d not built (only AVHOT_PREC_FP32)", precision);
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
+                "lstm_forward: precision %d not built", precision);
   if (B == 0) return AVHOT_OK;
   const size_t need = avhot_lstm_workspace_bytes(h, B, T, precision);
   AVHOT_REQUIRE(workspace && workspace_bytes >= need, AVHOT_ERR_WORKSPACE,
@@ -209,12 +212,19 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
   for (int l = 0; l < h->num_layers; ++l) {
     const float* x = l == 0 ? seq : h_seq;
     const int in = l == 0 ? h->input_dim : H;
-    int rc = gemm_f32(x, nullptr, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s,
-                      "lstm_input_gemm");
-    if (rc != AVHOT_OK) return rc;
     const bool last = l == h->num_layers - 1;
     float* hs_out = last ? nullptr : h_seq;   // layer l overwrites its own input only after xp is formed
     float* hl_out = last ? h_last : nullptr;
+    if (precision == AVHOT_PREC_TC) {
+      int rc = gemm_tf32_tc(x, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s,
+                            "lstm_input_gemm_tc");
+      if (rc == AVHOT_OK) rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, hs_out, hl_out, lengths, B, T, s);
+      if (rc != AVHOT_OK) return rc;
+      continue;
+    }
+    int rc = gemm_f32(x, nullptr, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s,
+                      "lstm_input_gemm");
+    if (rc != AVHOT_OK) return rc;
     ProfScope prof("lstm_recurrence", s);
     if (small) {
       constexpr int BT = 4;

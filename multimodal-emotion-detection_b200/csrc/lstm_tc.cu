@@ -1,0 +1,259 @@
+// LSTM recurrence on the tcgen05 tensor cores (AVHOT_PREC_TC path of a3, src/encoders.py:54-61, :148-154).
+//
+// Per layer, after the time-batched input projection xp = x W_ih^T + b (gemm_tc.cu), one persistent CTA owns
+// 128 clips for the whole sequence and every step computes
+//     gates[128 clips, 1024] = h_{t-1}[128, 256] (fp16, shared memory) x W_hh^T (fp16, streamed by TMA) + xp_t
+// in 8 chunks of 32 hidden units (N = 4 gates x 32 = 128 accumulator columns, double-buffered in TMEM):
+//   warp 0     TMA producer: W_hh tiles (128 gate rows x 64 k, 128-byte swizzle) through a 6-stage ring; the
+//              1024 x 256 weight matrix is re-read from L2 every step (it never fits next to the state);
+//   warp 1     one lane issues tcgen05.mma (M 128 clips, N 128, K 16) x 16 per chunk; A is the fp16 hidden
+//              state the epilogue wrote, ping-ponged between steps;
+//   warps 2-5  epilogue, thread = clip = TMEM lane: tcgen05.ld the four gate pre-activations of 16 units,
+//              add xp_t (256-bit loads), sigmoid / tanh, update the fp32 cell state that lives in 256 further
+//              TMEM columns of the same lane (tcgen05.ld / .st), write h_t as fp16 straight into the
+//              swizzled A-operand layout of the next step and (layer 0) as fp32 to h_seq.
+// mbarriers: full/empty per weight stage, acc_full/acc_empty per TMEM buffer, h_ready per 64-unit k-block of
+// the hidden state (so step t+1 starts on k-block 0 while the epilogue of step t finishes k-block 3).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace avhot {
+namespace tc {
+
+constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 192;
+
+struct RecSmem {
+  __half hA[2][RKB][RB * 64];   // hidden state, A operand: [step parity][k-block][128 rows x 128 B, swizzled]
+  __half wB[RST][RN * 64];      // W_hh tile ring, B operand
+  uint64_t full[RST], empty[RST], acc_full[2], acc_empty[2], h_ready[RKB];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+// 1 / (1 + 2^(-x log2 e)): ex2.approx + rcp.approx, ~2 ulp each
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, sigmoid_fast(2.f * x), -1.f); }
+
+__global__ void __launch_bounds__(RTHREADS, 1)
+lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp, float* __restrict__ h_seq,
+                   float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T) {
+  extern __shared__ unsigned char rec_smem_raw[];
+  RecSmem& sm = *reinterpret_cast<RecSmem*>((reinterpret_cast<uintptr_t>(rec_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // h_{-1} = 0
+  {
+    uint4* z = reinterpret_cast<uint4*>(&sm.hA[0][0][0]);
+    for (int i = threadIdx.x; i < (int)(sizeof(sm.hA[0]) / 16); i += RTHREADS) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < RST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 128); }
+    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = 0; t < T; ++t)
+        for (int c = 0; c < RNC; ++c)
+          for (int kb = 0; kb < RKB; ++kb, ++it) {
+            const int s = it % RST;
+            mbar_wait(&sm.empty[s], ((it / RST) & 1) ^ 1);
+            mbar_expect_tx(&sm.full[s], (uint32_t)sizeof(sm.wB[0]));
+            tma_load_2d(sm.wB[s], &tmW, &sm.full[s], kb * 64, c * RN);
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(FMT_F16, RB, RN);
+      uint32_t it = 0, use[2] = {0, 0};
+      for (int t = 0; t < T; ++t) {
+        for (int c = 0; c < RNC; ++c) {
+          const int b = c & 1;
+          mbar_wait(&sm.acc_empty[b], (use[b] & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < RKB; ++kb, ++it) {
+            if (c == 0 && t > 0) mbar_wait(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+            const int s = it % RST;
+            mbar_wait(&sm.full[s], (it / RST) & 1);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(sm.hA[t & 1][kb]));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem + (uint32_t)(b * RN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&sm.empty[s]);
+          }
+          umma_commit(&sm.acc_full[b]);
+          ++use[b];
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // clip row = TMEM lane
+    const int clip = blockIdx.x * RB + r;
+    const bool live = clip < B;
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int last_t = (live && lengths ? min(max(__ldg(lengths + clip), 1), T) : T) - 1;
+    {                                                         // c_{-1} = 0
+      uint32_t z[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll 1
+      for (int u = 0; u < RH; u += 16) tmem_st16(tlane + 256u + (uint32_t)u, z);
+      tmem_st_wait();
+    }
+    const float* xrow = xp + (size_t)(live ? clip : 0) * T * (4 * RH);
+    float* hrow = h_seq ? h_seq + (size_t)(live ? clip : 0) * T * RH : nullptr;
+    uint32_t use[2] = {0, 0};
+    unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      const float* xt = xrow + (size_t)t * (4 * RH);
+      unsigned char* hnext = hbase + (size_t)((t + 1) & 1) * sizeof(sm.hA[0]);
+#pragma unroll 1
+      for (int c = 0; c < RNC; ++c) {
+        const int b = c & 1;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int u0 = c * RCH + half * 16;
+          float xg[4][16];
+          if (live) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              ldg256(xt + g * RH + u0, *reinterpret_cast<float(*)[8]>(&xg[g][0]));
+              ldg256(xt + g * RH + u0 + 8, *reinterpret_cast<float(*)[8]>(&xg[g][8]));
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xg[g][j] = 0.f;
+          }
+          if (half == 0) {
+            mbar_wait(&sm.acc_full[b], use[b] & 1);
+            tc_fence_after();
+          }
+          uint32_t acc[4][16], cs[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld16(tlane + (uint32_t)(b * RN + g * RCH + half * 16), acc[g]);
+          tmem_ld16(tlane + 256u + (uint32_t)u0, cs);
+          tmem_ld_wait();
+          float hn[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float ig = sigmoid_fast(__uint_as_float(acc[0][j]) + xg[0][j]);
+            const float fg = sigmoid_fast(__uint_as_float(acc[1][j]) + xg[1][j]);
+            const float gg = tanh_fast(__uint_as_float(acc[2][j]) + xg[2][j]);
+            const float og = sigmoid_fast(__uint_as_float(acc[3][j]) + xg[3][j]);
+            const float cn = fmaf(fg, __uint_as_float(cs[j]), ig * gg);
+            cs[j] = __float_as_uint(cn);
+            hn[j] = og * tanh_fast(cn);
+          }
+          tmem_st16(tlane + 256u + (uint32_t)u0, cs);
+          // h_t (fp16) -> A operand of step t+1: k-block u0 / 64, 16-byte chunks (u0 % 64) / 8 and + 1, XOR-swizzled
+          {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            unsigned char* tile = hnext + (size_t)(u0 >> 6) * (RB * 128) + (size_t)r * 128;
+            const int j0 = (u0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(tile + (((j0) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(tile + (((j0 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (live) {
+            if (hrow) {
+              stg256(hrow + (size_t)t * RH + u0, &hn[0]);
+              stg256(hrow + (size_t)t * RH + u0 + 8, &hn[8]);
+            }
+            if (h_last && t == last_t) {
+              stg256(h_last + (size_t)clip * RH + u0, &hn[0]);
+              stg256(h_last + (size_t)clip * RH + u0 + 8, &hn[8]);
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&sm.acc_empty[b]);
+        ++use[b];
+        if (c & 1) {                      // both chunks of k-block c/2 of h_t are written by this thread
+          fence_proxy_async_smem();
+          mbar_arrive(&sm.h_ready[c >> 1]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// out[(c*128 + g*32 + u) * 256 + k] = half(W_hh[(g*256 + c*32 + u) * 256 + k])
+__global__ void pack_whh_fp16_kernel(const float* __restrict__ w, __half* __restrict__ out) {
+  const int row = blockIdx.x;                 // packed row
+  const int c = row >> 7, g = (row >> 5) & 3, u = row & 31;
+  const float* src = w + (size_t)(g * RH + c * RCH + u) * RH;
+  for (int k = threadIdx.x; k < RH; k += blockDim.x) out[(size_t)row * RH + k] = __float2half_rn(src[k]);
+}
+
+}  // namespace tc
+
+int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s) {
+  tc::pack_whh_fp16_kernel<<<4 * tc::RH, 128, 0, s>>>(w_hh, reinterpret_cast<__half*>(out));
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, float* h_seq, float* h_last,
+                       const int32_t* lengths, int B, int T, cudaStream_t s) {
+  using namespace tc;
+  CUtensorMap tmW;
+  int rc = make_tensor_map_2d(&tmW, whh_packed_fp16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * RH, RH, RH, RN, 64);
+  if (rc != AVHOT_OK) return rc;
+  const int smem = (int)sizeof(RecSmem) + 1024;
+  AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ProfScope prof("lstm_recurrence_tc", s);
+  lstm_rec_tc_kernel<<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_last, lengths, B, T);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+}  // namespace avhot

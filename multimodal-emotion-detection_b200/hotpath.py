@@ -37,7 +37,7 @@ DEFAULT_ENCODERS = {   # configs/base.yaml:30-47 with BASELINE.json's input dims
 class AVHotPath(nn.Module):
     def __init__(self, head: str = "hybrid", modalities=("audio", "video"), encoders: Optional[dict] = None,
                  output_dim: int = 128, hidden_dim: int = 256, num_heads: int = 4, num_classes: int = 8,
-                 dropout: float = 0.3):
+                 dropout: float = 0.3, precision: str = "fp32"):
         super().__init__()
         if head not in ("hybrid", "concat"):
             raise ValueError(f"Unknown head: {head}")
@@ -58,6 +58,19 @@ class AVHotPath(nn.Module):
             self.fusion_head = ConcatHead(output_dim * len(self.modalities), hidden_dim, num_classes,
                                           len(self.modalities))                          # :81-85
         self.num_classes = num_classes
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str) -> "AVHotPath":
+        """'fp32': every contraction in fp32 FMA (the 1e-4 parity path).  'tc': the large contractions (video
+        Linear, LSTM input projections and recurrence) on the tcgen05 tensor cores (TF32 / fp16 operands, fp32
+        accumulate; tolerance stated in DESIGN.md); the fusion tail stays fp32."""
+        if precision not in ("fp32", "tc"):
+            raise ValueError(f"Unknown precision: {precision}")
+        self.precision = precision
+        code = _lib.PREC_FP32 if precision == "fp32" else _lib.PREC_TC
+        for enc in self.encoders.values():
+            enc.precision = code
+        return self
 
     # ---- stages ----------------------------------------------------------------------------------------
     def audio_features(self, audio: torch.Tensor) -> torch.Tensor:

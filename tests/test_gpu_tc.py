@@ -1,0 +1,65 @@
+"""AVHOT_PREC_TC: the tcgen05 tensor-core path (TF32 time-batched GEMMs, fp16 recurrent GEMM, fp32 accumulate and
+fp32 everything else) against the fp64 oracle at its STATED tolerance, and against the fp32 CUDA path for labels."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import frontend as ofe, model as om, philox as px, synth as osynth
+from test_gpu_parity import SEED, make_model, rel_err, world, pkg, dev  # noqa: F401  (fixtures)
+
+TC_REL_HID = 2e-3      # video Linear + ReLU output, TF32 operands over K = 12544
+TC_REL_LSTM = 5e-3     # audio embedding after 2 x 301 recurrent steps with fp16 state / weights
+TC_REL_LOGITS = 1e-2   # logits after LayerNorms and the fusion head
+
+
+def test_frame_hidden_tc(pkg, dev, world):
+    m = make_model(pkg, dev, world).set_precision("tc")
+    frames = torch.from_numpy(world["frames"])
+    hid = m.encoders["video"].hidden(frames.to(dev)).cpu().numpy()
+    want = om.frame_hidden(frames.double(), world["sd64"]).numpy()
+    err = rel_err(hid, want)
+    print("frame hidden tc rel err", err)
+    assert err <= TC_REL_HID
+
+
+def test_lstm_tc_vs_oracle(pkg, dev, world, golden):
+    m = make_model(pkg, dev, world).set_precision("tc")
+    enc = m.encoders["audio"]
+    feats = torch.from_numpy(world["feats"])
+    got = enc(feats.to(dev)).cpu().numpy()
+    want = om.sequence_encoder_lstm(feats.double(), world["sd64"]).numpy()
+    err = rel_err(got, want)
+    print("lstm tc rel err", err)
+    assert err <= TC_REL_LSTM
+    # several CTAs with a partial last tile, ragged lengths, and agreement with the fp32 CUDA path
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.normal(size=(300, 20, 104)).astype(np.float32)).to(dev)
+    lengths = torch.from_numpy(rng.integers(1, 21, size=300))
+    tc_out = enc(x, lengths)
+    enc.precision = pkg._lib.PREC_FP32
+    ref_out = enc(x, lengths)
+    err2 = rel_err(tc_out.cpu().numpy(), ref_out.cpu().numpy())
+    print("lstm tc vs fp32 cuda (B=300, ragged) rel err", err2)
+    assert err2 <= TC_REL_LSTM
+    again = enc(x, lengths)
+    assert (again == ref_out).all()
+
+
+def test_full_path_tc(pkg, dev, world, golden):
+    m = make_model(pkg, dev, world).set_precision("tc")
+    feats = {"audio": torch.from_numpy(world["wave"]).to(dev), "video": torch.from_numpy(world["frames"]).to(dev)}
+    got = m(feats).cpu().numpy()
+    want = golden["logits_hybrid_ones"]
+    err = rel_err(got, want)
+    print("full path tc logits rel err", err, "labels", got.argmax(1), want.argmax(1))
+    assert err <= TC_REL_LOGITS
+    # MC statistics: same masks (bit-exact Philox), tensor-core contractions
+    pkg.MCDropoutUncertainty._set_dropout_train(m)
+    mask = torch.from_numpy(px.modality_mask(np.arange(6, dtype=np.uint64) + np.uint64(50), 2, 0.05, SEED)).to(dev)
+    mean_tc, unc_tc, lab_tc, _ = m.mc_forward(feats, mask, num_samples=8, seed=SEED, clip0=50)
+    m.set_precision("fp32")
+    mean, unc, lab, _ = m.mc_forward(feats, mask, num_samples=8, seed=SEED, clip0=50)
+    assert rel_err(mean_tc.cpu().numpy(), mean.cpu().numpy()) <= TC_REL_LOGITS
+    assert rel_err(unc_tc.cpu().numpy(), unc.cpu().numpy()) <= 5e-2
