@@ -150,7 +150,7 @@ def workload_config(args, batch):
                         "112x112 fp32) -> log-mel/MFCC front-end (n_fft 512, hop 160, 64 mel + 40 MFCC) -> LSTM 2x256 "
                         "+ frame encoder -> hybrid cross-modal attention fusion -> MC-dropout uncertainty",
             "clips_per_gpu_per_step": batch, "mc_passes": args.passes, "modality_dropout_p": P_MODALITY,
-            "classes": N_CLASSES, "parallelism": f"clip-sharded x{args.gpus}, all-gather of (B,9) fp32",
+            "classes": N_CLASSES, "precision": args.precision, "parallelism": f"clip-sharded x{args.gpus}, all-gather of (B,9) fp32",
             "l2_policy": "inputs larger than L2 (4 GB per step per GPU), two batches alternate"}
 
 
@@ -186,7 +186,7 @@ def run_b200_arm(args):
     model = pkg.AVHotPath("hybrid")
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items() if not k.startswith("fusion_head.")},
                           strict=True)
-    model = model.to(dev).eval()
+    model = model.to(dev).eval().set_precision(args.precision)
     pkg.MCDropoutUncertainty._set_dropout_train(model)            # what MCDropoutUncertainty.forward does (:58-59)
 
     def clip0_of(step):                                            # global clip index of this rank's batch
@@ -250,12 +250,15 @@ def run_b200_arm(args):
     stages = {}
     for name, (tot, n) in sorted(prof.items()):
         stages[name] = {"ms_per_step": tot / args.steps, "launches_per_step": n / args.steps}
-    rec_ms, rec_n = prof.get("lstm_recurrence", (0.0, 0))
+    rec_name = "lstm_recurrence_tc" if args.precision == "tc" else "lstm_recurrence"
+    rec_ms, rec_n = prof.get(rec_name, (0.0, 0))
     roofline = None
     if rec_n:
         per_launch_s = rec_ms / rec_n / 1e3
         achieved = B * FLOPS_LSTM_RECURRENT_PER_LAYER / per_launch_s / 1e12
-        roofline = {"kernel": "lstm_recurrence_kernel (fp32 FMA, one launch per LSTM layer)", "bound": "tensor",
+        kname = ("lstm_rec_tc_kernel (tcgen05 fp16 x fp16 -> fp32, one launch per LSTM layer)" if args.precision == "tc"
+                 else "lstm_recurrence_kernel (fp32 FMA, one launch per LSTM layer)")
+        roofline = {"kernel": kname, "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tf_sustained"], "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
@@ -273,6 +276,20 @@ def run_b200_arm(args):
         extra["frame_gemm"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": gbs / peaks["hbm_gbs"],
                                "tflops": B * FLOPS_FRAME_GEMM / (fg_ms / fg_n / 1e3) / 1e12}
+
+    # labels of the timed precision against the fp32 CUDA path (itself checked against the oracle) on one batch
+    parity = None
+    if args.precision != "fp32":
+        feats, mask, c0 = pool[0]
+        nchk = min(B, 1024)
+        sub = {k: v[:nchk] for k, v in feats.items()}
+        a = model.mc_forward(sub, mask[:nchk], num_samples=T, seed=SEED, clip0=c0)
+        model.set_precision("fp32")
+        b = model.mc_forward(sub, mask[:nchk], num_samples=T, seed=SEED, clip0=c0)
+        model.set_precision(args.precision)
+        parity = {"clips": nchk, "label_mismatches_vs_fp32_path": int((a[2] != b[2]).sum().item()),
+                  "mean_logits_rel_err_vs_fp32_path": float((a[0] - b[0]).abs().max() / b[0].abs().max()),
+                  "uncertainty_rel_err_vs_fp32_path": float((a[1] - b[1]).abs().max() / b[1].abs().max())}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -295,9 +312,10 @@ def run_b200_arm(args):
 
     line = {"metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/f16 tensor-core operands, f32 accumulate",
+            "data": "synthetic", "config": workload_config(args, B),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "stages": stages, "stage_rooflines": extra}
+            "cpu_baseline": cpu_baseline, "parity": parity, "stages": stages, "stage_rooflines": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +394,8 @@ def main():
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=32, help="clips in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
+                    help="tc: large contractions on tcgen05 (TF32 / fp16 operands); fp32: CUDA-core fp32 everywhere")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                                         # timing rule: W >= 3
