@@ -151,7 +151,8 @@ def workload_config(args, batch):
                         "+ frame encoder -> hybrid cross-modal attention fusion -> MC-dropout uncertainty",
             "clips_per_gpu_per_step": batch, "mc_passes": args.passes, "modality_dropout_p": P_MODALITY,
             "classes": N_CLASSES, "precision": args.precision, "parallelism": f"clip-sharded x{args.gpus}, all-gather of (B,9) fp32",
-            "l2_policy": "inputs larger than L2 (4 GB per step per GPU), two batches alternate"}
+            "l2_policy": f"inputs larger than L2 ({batch * BYTES_IN_PER_CLIP / 1e9:.1f} GB per step per GPU), two "
+                         "batches alternate"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -324,54 +325,65 @@ def run_b200_arm(args):
 
 def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier):
     """Same step through the public API (AVHotPath.mc_forward = MCDropoutUncertainty's fast path) with inputs in
-    pinned HOST memory: every step copies its inputs host->device and reads the packed result back; uploads of step
-    i+1 overlap the kernels of step i on a second stream (two device staging slots)."""
+    pinned HOST memory: every step uploads its B clips host->device in sub-batches of --e2e-chunk clips and reads the
+    packed results back; the upload of sub-batch i+1 overlaps the kernels of sub-batch i on a second stream (two
+    device staging slots).  The pinned source ring holds two sub-batches (real copies every time; clip indices for
+    the Philox masks advance normally)."""
     import torch
     import torch.distributed as dist
+    C = min(args.e2e_chunk, B)
+    n_sub = (B + C - 1) // C
     host = []
     for j in range(2):
         c0 = clip0_of(j)
-        a = pkg.synth.synth_audio(B, c0, SEED, dev)
-        v = pkg.synth.synth_video(B, c0, SEED, dev)
-        m = pkg.synth.modality_mask(B, c0, P_MODALITY, SEED, dev)
+        a = pkg.synth.synth_audio(C, c0, SEED, dev)
+        v = pkg.synth.synth_video(C, c0, SEED, dev)
+        m = pkg.synth.modality_mask(C, c0, P_MODALITY, SEED, dev)
         ha = torch.empty(a.shape, dtype=a.dtype, pin_memory=True).copy_(a)
         hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v)
         hm = torch.empty(m.shape, dtype=m.dtype, pin_memory=True).copy_(m)
-        host.append((ha, hv, hm, c0))
+        host.append((ha, hv, hm))
         del a, v, m
-    slots = [(torch.empty(B, N_SAMPLES, device=dev), torch.empty(B, N_FRAMES, FRAME_DIM, device=dev),
-              torch.empty(B, 2, device=dev)) for _ in range(2)]
-    result_host = [torch.empty(B * world, N_CLASSES + 1, pin_memory=True) for _ in range(2)]
+    slots = [(torch.empty(C, N_SAMPLES, device=dev), torch.empty(C, N_FRAMES, FRAME_DIM, device=dev),
+              torch.empty(C, 2, device=dev)) for _ in range(2)]
+    packed_dev = torch.empty(B, N_CLASSES + 1, device=dev)
+    result_host = torch.empty(B * world, N_CLASSES + 1, pin_memory=True)
     copy_stream = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    counter = [0]
 
-    def run(n_steps):
+    def run(n_steps, step0):
         for j in range(n_steps):
-            s = j % 2
-            ha, hv, hm, c0 = host[s]
-            with torch.cuda.stream(copy_stream):
-                if j >= 2:
-                    copy_stream.wait_event(consumed[s])
-                slots[s][0].copy_(ha, non_blocking=True)
-                slots[s][1].copy_(hv, non_blocking=True)
-                slots[s][2].copy_(hm, non_blocking=True)
-                uploaded[s].record(copy_stream)
-            main.wait_event(uploaded[s])
-            packed = model.mc_forward({"audio": slots[s][0], "video": slots[s][1]}, slots[s][2], num_samples=T,
-                                      seed=SEED, clip0=c0)[3]
-            consumed[s].record(main)
-            if world > 1:
-                packed = par.all_gather_packed(packed, B * world)
-            result_host[s].copy_(packed, non_blocking=True)
+            base = clip0_of(step0 + j)
+            for i in range(n_sub):
+                n = min(C, B - i * C)
+                k = counter[0]
+                counter[0] += 1
+                s = k % 2
+                ha, hv, hm = host[s]
+                with torch.cuda.stream(copy_stream):
+                    if k >= 2:
+                        copy_stream.wait_event(consumed[s])
+                    slots[s][0][:n].copy_(ha[:n], non_blocking=True)
+                    slots[s][1][:n].copy_(hv[:n], non_blocking=True)
+                    slots[s][2][:n].copy_(hm[:n], non_blocking=True)
+                    uploaded[s].record(copy_stream)
+                main.wait_event(uploaded[s])
+                packed = model.mc_forward({"audio": slots[s][0][:n], "video": slots[s][1][:n]}, slots[s][2][:n],
+                                          num_samples=T, seed=SEED, clip0=base + i * C)[3]
+                consumed[s].record(main)
+                packed_dev[i * C:i * C + n].copy_(packed)
+            out = par.all_gather_packed(packed_dev, B * world) if world > 1 else packed_dev
+            result_host.copy_(out, non_blocking=True)
 
-    run(min(2, args.warmup))
+    run(1, 0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
     copy_stream.wait_event(e0)
-    run(args.steps)
+    run(args.steps, 1)
     e1.record(main)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -380,8 +392,8 @@ def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier):
     ms = float(ms.item())
     return {"value": world * B * args.steps / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms / args.steps,
             "h2d_bytes_per_step": B * BYTES_IN_PER_CLIP, "d2h_bytes_per_step": B * world * BYTES_OUT_PER_CLIP,
-            "api": "AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), fp32 host buffers, "
-                   "uploads double-buffered on a copy stream"}
+            "api": f"AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), fp32 pinned host buffers, "
+                   f"{n_sub} sub-batches of <= {C} clips per step, uploads double-buffered on a copy stream"}
 
 
 def main():
@@ -390,7 +402,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=148 * 128,
+                    help="clips per GPU per step (default: one 128-clip CTA of the recurrent kernel per SM)")
+    ap.add_argument("--e2e-chunk", type=int, default=4096, help="clips per host->device sub-batch in the e2e leg")
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=32, help="clips in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
