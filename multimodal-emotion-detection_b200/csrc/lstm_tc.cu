@@ -8,10 +8,11 @@
 //              1024 x 256 weight matrix is re-read from L2 every step (it never fits next to the state);
 //   warp 1     one lane issues tcgen05.mma (M 128 clips, N 128, K 16) x 16 per chunk; A is the fp16 hidden
 //              state the epilogue wrote, ping-ponged between steps;
-//   warps 2-5  epilogue, thread = clip = TMEM lane: tcgen05.ld the four gate pre-activations of 16 units,
-//              add xp_t (256-bit loads), sigmoid / tanh, update the fp32 cell state that lives in 256 further
-//              TMEM columns of the same lane (tcgen05.ld / .st), write h_t as fp16 straight into the
-//              swizzled A-operand layout of the next step and (layer 0) as fp32 to h_seq.
+//   warps 2-9  two epilogue warpgroups (even / odd chunks), thread = clip = TMEM lane: tcgen05.ld the four gate
+//              pre-activations of 8 units, add xp_t (256-bit loads, prefetched two items ahead in registers),
+//              sigmoid / tanh, update the fp32 cell state that lives in 256 further TMEM columns of the same
+//              lane (tcgen05.ld / .st), write h_t as fp16 straight into the swizzled A-operand layout of the
+//              next step and (layer 0) as fp32 to h_seq.
 // mbarriers: full/empty per weight stage, acc_full/acc_empty per TMEM buffer, h_ready per 64-unit k-block of
 // the hidden state (so step t+1 starts on k-block 0 while the epilogue of step t finishes k-block 3).
 #include <cuda_fp16.h>
@@ -22,7 +23,7 @@
 namespace avhot {
 namespace tc {
 
-constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 192;
+constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 320;
 
 struct RecSmem {
   __half hA[2][RKB][RB * 64];   // hidden state, A operand: [step parity][k-block][128 rows x 128 B, swizzled]
@@ -40,6 +41,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
@@ -47,7 +59,7 @@ __device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
-__device__ __forceinline__ void stg256(float* p, const float* v) {
+__device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
@@ -73,7 +85,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < RST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 128); }
-    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 128);
+    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 256);   // both warpgroups write half of a k-block
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -124,100 +136,107 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       }
     }
   } else {
+    // Two epilogue warpgroups: warpgroup g owns the chunks c = g (mod 2), i.e. TMEM buffer g, so each has two
+    // chunk-times of MMA to finish one chunk.  Work item = 8 hidden units of one chunk; xp for the item two ahead
+    // is already in flight in registers (two named buffers) while the current one is computed.
+    const int wg = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // clip row = TMEM lane
     const int clip = blockIdx.x * RB + r;
     const bool live = clip < B;
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
     const int last_t = (live && lengths ? min(max(__ldg(lengths + clip), 1), T) : T) - 1;
-    {                                                         // c_{-1} = 0
+    {                                                         // c_{-1} = 0 for the units this warpgroup owns
       uint32_t z[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) z[i] = 0u;
 #pragma unroll 1
-      for (int u = 0; u < RH; u += 16) tmem_st16(tlane + 256u + (uint32_t)u, z);
+      for (int c = wg; c < RNC; c += 2) {
+        tmem_st16(tlane + 256u + (uint32_t)(c * RCH), z);
+        tmem_st16(tlane + 256u + (uint32_t)(c * RCH + 16), z);
+      }
       tmem_st_wait();
     }
     const float* xrow = xp + (size_t)(live ? clip : 0) * T * (4 * RH);
     float* hrow = h_seq ? h_seq + (size_t)(live ? clip : 0) * T * RH : nullptr;
-    uint32_t use[2] = {0, 0};
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
+    uint32_t use = 0;
+
+    // xp of item (t, c, q): 4 gates x 8 units, one 256-bit load per gate
+    auto load_x = [&](int t, int c, int q, float (&xg)[4][8]) {
+      if (live && t < T) {
+        const float* src = xrow + (size_t)t * (4 * RH) + c * RCH + q * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ldg256(src + g * RH, xg[g]);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xg[g][j] = 0.f;
+      }
+    };
+    auto item = [&](int t, int c, int q, const float (&xg)[4][8]) {
+      const int u0 = c * RCH + q * 8;
+      uint32_t acc[4][8], cs[8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld8(tlane + (uint32_t)(wg * RN + g * RCH + q * 8), acc[g]);
+      tmem_ld8(tlane + 256u + (uint32_t)u0, cs);
+      tmem_ld_wait();
+      float hn[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float ig = sigmoid_fast(__uint_as_float(acc[0][j]) + xg[0][j]);
+        const float fg = sigmoid_fast(__uint_as_float(acc[1][j]) + xg[1][j]);
+        const float gg = tanh_fast(__uint_as_float(acc[2][j]) + xg[2][j]);
+        const float og = sigmoid_fast(__uint_as_float(acc[3][j]) + xg[3][j]);
+        const float cn = fmaf(fg, __uint_as_float(cs[j]), ig * gg);
+        cs[j] = __float_as_uint(cn);
+        hn[j] = og * tanh_fast(cn);
+      }
+      tmem_st8(tlane + 256u + (uint32_t)u0, cs);
+      // h_t (fp16) -> A operand of step t+1: k-block u0 / 64, 16-byte chunk (u0 % 64) / 8, XOR-swizzled by the row
+      {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&v);
+        }
+        unsigned char* tile = hbase + (size_t)((t + 1) & 1) * sizeof(sm.hA[0]) + (size_t)(u0 >> 6) * (RB * 128) +
+                              (size_t)r * 128;
+        *reinterpret_cast<uint4*>(tile + ((((u0 & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      if (live) {
+        if (hrow) stg256(hrow + (size_t)t * RH + u0, hn);
+        if (h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
+      }
+    };
+
+    float xa[4][8], xb[4][8];
+    load_x(0, wg, 0, xa);
+    load_x(0, wg, 1, xb);
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-      const float* xt = xrow + (size_t)t * (4 * RH);
-      unsigned char* hnext = hbase + (size_t)((t + 1) & 1) * sizeof(sm.hA[0]);
 #pragma unroll 1
-      for (int c = 0; c < RNC; ++c) {
-        const int b = c & 1;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const int u0 = c * RCH + half * 16;
-          float xg[4][16];
-          if (live) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              ldg256(xt + g * RH + u0, *reinterpret_cast<float(*)[8]>(&xg[g][0]));
-              ldg256(xt + g * RH + u0 + 8, *reinterpret_cast<float(*)[8]>(&xg[g][8]));
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-              for (int j = 0; j < 16; ++j) xg[g][j] = 0.f;
-          }
-          if (half == 0) {
-            mbar_wait(&sm.acc_full[b], use[b] & 1);
-            tc_fence_after();
-          }
-          uint32_t acc[4][16], cs[16];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld16(tlane + (uint32_t)(b * RN + g * RCH + half * 16), acc[g]);
-          tmem_ld16(tlane + 256u + (uint32_t)u0, cs);
-          tmem_ld_wait();
-          float hn[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float ig = sigmoid_fast(__uint_as_float(acc[0][j]) + xg[0][j]);
-            const float fg = sigmoid_fast(__uint_as_float(acc[1][j]) + xg[1][j]);
-            const float gg = tanh_fast(__uint_as_float(acc[2][j]) + xg[2][j]);
-            const float og = sigmoid_fast(__uint_as_float(acc[3][j]) + xg[3][j]);
-            const float cn = fmaf(fg, __uint_as_float(cs[j]), ig * gg);
-            cs[j] = __float_as_uint(cn);
-            hn[j] = og * tanh_fast(cn);
-          }
-          tmem_st16(tlane + 256u + (uint32_t)u0, cs);
-          // h_t (fp16) -> A operand of step t+1: k-block u0 / 64, 16-byte chunks (u0 % 64) / 8 and + 1, XOR-swizzled
-          {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
-              pk[j] = *reinterpret_cast<const uint32_t*>(&v);
-            }
-            unsigned char* tile = hnext + (size_t)(u0 >> 6) * (RB * 128) + (size_t)r * 128;
-            const int j0 = (u0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(tile + (((j0) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(tile + (((j0 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-          if (live) {
-            if (hrow) {
-              stg256(hrow + (size_t)t * RH + u0, &hn[0]);
-              stg256(hrow + (size_t)t * RH + u0 + 8, &hn[8]);
-            }
-            if (h_last && t == last_t) {
-              stg256(h_last + (size_t)clip * RH + u0, &hn[0]);
-              stg256(h_last + (size_t)clip * RH + u0 + 8, &hn[8]);
-            }
-          }
-        }
+      for (int c = wg; c < RNC; c += 2) {
+        // the item two ahead of (c, q): same chunk for q < 2, else the next chunk of this warpgroup
+        const int cn = c + 2 < RNC ? c + 2 : wg, tn = c + 2 < RNC ? t : t + 1;
+        mbar_wait(&sm.acc_full[wg], use & 1);
+        tc_fence_after();
+        item(t, c, 0, xa);
+        load_x(t, c, 2, xa);
+        item(t, c, 1, xb);
+        load_x(t, c, 3, xb);
+        item(t, c, 2, xa);
+        load_x(tn, cn, 0, xa);
+        item(t, c, 3, xb);
+        load_x(tn, cn, 1, xb);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&sm.acc_empty[b]);
-        ++use[b];
-        if (c & 1) {                      // both chunks of k-block c/2 of h_t are written by this thread
-          fence_proxy_async_smem();
-          mbar_arrive(&sm.h_ready[c >> 1]);
-        }
+        mbar_arrive(&sm.acc_empty[wg]);
+        ++use;
+        fence_proxy_async_smem();              // this thread's part of k-block c/2 of h_t is written
+        mbar_arrive(&sm.h_ready[c >> 1]);
       }
     }
   }
