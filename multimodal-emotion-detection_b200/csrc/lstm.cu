@@ -12,6 +12,8 @@
 //      c_t stays in registers for the whole sequence.
 // Gate order i, f, g, o (nn.LSTM); c' = f*c + i*g; h' = o*tanh(c').  Inter-layer dropout is
 // inactive in eval mode and under MC-dropout.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 struct avhot_lstm {
@@ -20,7 +22,8 @@ struct avhot_lstm {
   float* w_hh_t[4];  // [k][gate][j]  = W_hh[gate*H + j][k]
   float* bias[4];    // b_ih + b_hh
   void* w_hh_r16[4]; // fp16, rows regrouped per 32-unit chunk (lstm_tc.cu)
-  float* w_ih0_split; // (4H, 3*in): [W_hi | W_hi | W_lo], TF32 split of layer 0's input weights
+  void* w_ih_f16[4];  // fp16 input weights for the tensor-core path: layer 0 (4H, 3*in) = [W_hi | W_hi | W_lo],
+                      // layers > 0 (4H, H)
   float* proj_w;     // (out, H)
   float* proj_b;
   float* arena;
@@ -109,22 +112,26 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// TF32 operand split.  hi = x with the 13 low mantissa bits cleared (what kind::tf32 keeps), lo = x - hi (exact).
-// A' = [hi | lo | hi] and W' = [hi | hi | lo] turn one TF32 GEMM over K' = 3K into
-// A W^T - lo(A) lo(W)^T, i.e. an fp32-class product (dropped term ~2^-20): used for layer 0's input projection,
-// whose inputs (log-mel features in dB, |x| ~ 100) are too large for a single TF32 pass.
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__global__ void split3_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int K,
-                              int weight_order) {
+// fp16 operand split.  hi = fp16(x), lo = fp16(x - hi).  A' = [hi | lo | hi] against W' = [hi | hi | lo] turns one
+// fp16 tensor-core GEMM over K' = 3K into A W^T - lo(A) lo(W)^T - O(2^-22), i.e. an fp32-class product: used for
+// layer 0's input projection, whose inputs (log-mel features in dB, |x| ~ 100) are far too large for a single
+// half-precision pass (measured 5.7e-3 error with one TF32 pass).  Requires |x| < 65504.
+__global__ void split3_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long rows, int K,
+                                  int weight_order) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
   const long long r = i / K;
   const int k = (int)(i % K);
-  const float v = x[i], hi = tf32_hi(v), lo = v - hi;
-  float* o = out + r * 3 * K;
+  const float v = x[i];
+  const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+  __half* o = out + r * 3 * K;
   o[k] = hi;
   o[K + k] = weight_order ? hi : lo;
   o[2 * K + k] = weight_order ? lo : hi;
+}
+__global__ void to_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(x[i]);
 }
 
 }  // namespace avhot
@@ -152,7 +159,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   }
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
-  total += align256(sizeof(float) * 4 * H * 3 * d->input_dim);
+  total += align256(2 * 4 * H * 3 * d->input_dim) + (L - 1) * align256(2 * 4 * H * H);
   avhot_lstm* h = new avhot_lstm();
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
@@ -178,10 +185,17 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     if (rc == AVHOT_OK) rc = add_vec(d->bias_ih[l], d->bias_hh[l], h->bias[l], 4 * H, s);
     if (rc == AVHOT_OK) rc = lstm_pack_whh_fp16(d->weight_hh[l], h->w_hh_r16[l], s);
   }
-  if (rc == AVHOT_OK) {
-    h->w_ih0_split = take(sizeof(float) * 4 * H * 3 * d->input_dim);
-    const long long n = (long long)4 * H * d->input_dim;
-    split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->weight_ih[0], h->w_ih0_split, 4 * H, d->input_dim, 1);
+  for (int l = 0; l < L && rc == AVHOT_OK; ++l) {
+    if (l == 0) {
+      h->w_ih_f16[0] = take(2 * 4 * H * 3 * d->input_dim);
+      const long long n = (long long)4 * H * d->input_dim;
+      split3_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->weight_ih[0], reinterpret_cast<__half*>(h->w_ih_f16[0]),
+                                                                   4 * H, d->input_dim, 1);
+    } else {
+      h->w_ih_f16[l] = take(2 * 4 * H * H);
+      const long long n = (long long)4 * H * H;
+      to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->weight_ih[l], reinterpret_cast<__half*>(h->w_ih_f16[l]), n);
+    }
     if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
   }
   if (rc == AVHOT_OK) {
@@ -215,7 +229,7 @@ extern "C" size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int p
   const size_t H = h->hidden_dim;
   size_t n = align256(sizeof(float) * (size_t)B * T * 4 * H) + align256(sizeof(float) * (size_t)B * T * H) +
              align256(sizeof(float) * (size_t)B * H);
-  if (precision == AVHOT_PREC_TC) n += align256(sizeof(float) * (size_t)B * T * 3 * h->input_dim);
+  if (precision == AVHOT_PREC_TC) n += align256(2 * (size_t)B * T * 3 * h->input_dim);   // fp16 split of the input
   return n;
 }
 
@@ -235,7 +249,7 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
   float* xp = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * T * 4 * H);
   float* h_seq = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * T * H);
   float* h_last = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * H);
-  float* x_split = reinterpret_cast<float*>(p);   // TC path only
+  __half* x_split = reinterpret_cast<__half*>(p);   // TC path only
   const bool small = ceil_div(B, 32) * 2 < num_sms();   // few clips: smaller tiles, more CTAs
   for (int l = 0; l < h->num_layers; ++l) {
     const float* x = l == 0 ? seq : h_seq;
@@ -244,21 +258,23 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
     float* hs_out = last ? nullptr : h_seq;   // layer l overwrites its own input only after xp is formed
     float* hl_out = last ? h_last : nullptr;
     if (precision == AVHOT_PREC_TC) {
+      // TC path: h_seq holds the fp16 hidden sequence (it is only ever the next layer's GEMM operand)
       int rc;
+      AVHOT_REQUIRE(3 * in <= 320 || l > 0, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d > 106", in);
       if (l == 0) {
         const long long n = (long long)B * T * in;
         {
           ProfScope prof("lstm_split3", s);
-          split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x_split, (long long)B * T, in, 0);
+          split3_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x_split, (long long)B * T, in, 0);
           AVHOT_LAUNCH_CHECK();
         }
-        rc = gemm_tf32_tc(x_split, 3 * in, h->w_ih0_split, 3 * in, h->bias[l], xp, 4 * H, B * T, 4 * H, 3 * in,
-                          ACT_NONE, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(x_split, 3 * in, h->w_ih_f16[0], 3 * in, h->bias[l], xp, 4 * H, B * T, 4 * H, 3 * in, s,
+                         "lstm_input_gemm_tc");
       } else {
-        rc = gemm_tf32_tc(x, in, h->w_ih[l], in, h->bias[l], xp, 4 * H, B * T, 4 * H, in, ACT_NONE, s,
-                          "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(h_seq, H, h->w_ih_f16[l], H, h->bias[l], xp, 4 * H, B * T, 4 * H, H, s, "lstm_input_gemm_tc");
       }
-      if (rc == AVHOT_OK) rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, hs_out, hl_out, lengths, B, T, s);
+      if (rc == AVHOT_OK)
+        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, last ? nullptr : (void*)h_seq, hl_out, lengths, B, T, s);
       if (rc != AVHOT_OK) return rc;
       continue;
     }
