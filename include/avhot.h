@@ -203,11 +203,14 @@ void avhot_fusion_destroy(avhot_fusion_t h);
  * mask (B, M) fp32 1 = available, or NULL.  Optional outputs (may be NULL):
  * fusion_weights (R, M), attn (M, R, heads, M), h_att (R, M, D).
  * Dropout (p > 0): attention weights (site ATTN+i) and gate hidden (site GATE). */
+size_t avhot_fusion_workspace_bytes(avhot_fusion_t h, int B, int T);
 int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
                          const int* z_rows_per_clip_host, const float* mask, float* logits,
                          float* fusion_weights, float* attn, float* h_att, int B, int T,
-                         float p, uint64_t seed, uint64_t clip0, uint32_t t0,
-                         avhot_stream_t stream);
+                         float p, uint64_t seed, uint64_t clip0, uint32_t t0, void* workspace,
+                         size_t workspace_bytes, avhot_stream_t stream);
+/* workspace (optional, avhot_fusion_workspace_bytes): lets the hybrid path compute the pass-invariant
+ * half of modality 0 once per clip when z_rows_per_clip[0] == 1 (same results, fewer FLOPs). */
 
 /* ---- a8: src/uncertainty.py:17-86  MCDropoutUncertainty statistics ------------------ */
 /* logits (B, T, C) -> mean_logits (B, C), uncertainty (B) = mean_c Var_t softmax (population

@@ -9,8 +9,11 @@ import torch
 import torch.nn as nn
 
 from . import _lib, _rng
-from ._handles import Handle
+from ._handles import Handle, Workspace
 from .attention import CrossModalAttention
+
+
+_ws = Workspace()
 
 
 def _z_args(zs, rows_per_clip):
@@ -108,9 +111,11 @@ class HybridFusion(nn.Module):
             arr, rpc = _z_args(zs, rows_per_clip)
             with torch.cuda.device(dev):
                 h = self._get_handle(dev)
-                _lib.check(_lib.load().avhot_fusion_forward(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits),
-                                                            _lib.ptr(fw), _lib.ptr(attn), _lib.ptr(hatt), B, passes,
-                                                            float(p), seed, clip0, t0, _lib.stream_ptr(dev)),
+                lib = _lib.load()
+                ws = _ws.get(lib.avhot_fusion_workspace_bytes(h, B, passes), dev)
+                _lib.check(lib.avhot_fusion_forward(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits), _lib.ptr(fw),
+                                                    _lib.ptr(attn), _lib.ptr(hatt), B, passes, float(p), seed, clip0,
+                                                    t0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
                            "HybridFusion.forward")
         return logits, fw, attn, hatt
 
@@ -186,7 +191,7 @@ class ConcatHead(nn.Sequential):
             with torch.cuda.device(dev):
                 h = self._get_handle(dev)
                 _lib.check(_lib.load().avhot_fusion_forward(h, arr, rpc, None, _lib.ptr(logits), None, None, None,
-                                                            B, passes, 0.0, 0, 0, 0, _lib.stream_ptr(dev)),
+                                                            B, passes, 0.0, 0, 0, 0, None, 0, _lib.stream_ptr(dev)),
                            "ConcatHead.forward")
         return logits
 
