@@ -463,60 +463,67 @@ __global__ void __launch_bounds__(FTHREADS, 2) fusion_clip_kernel(const FusionPa
       for (int j = 0; j < 5; ++j) clipbuf[((size_t)(b0 + r) * FCB + 1 + j) * FD + n] = acc[j][r];
 }
 
-constexpr int HRT = 32, HTHREADS = 512, HR = 16;   // rows per CTA, threads, rows per thread
+constexpr int HRT = 32, HTHREADS = 512, HR = 8;   // rows per CTA, threads, rows per thread
 
 struct FusionPassSmem {
   float xh[HRT][FD];           // x^_v
   float hatt[HRT][FM][FD];     // H_att
   float buf[HRT][FD];          // context, then fused
-  float part[16][HRT][FM];     // per-warp partial reductions
-  float attn[HRT][FHEADS][FM];
+  float part[16][HRT];         // per-warp partial reductions (gate scores)
   float zmean[HRT], zstd[HRT], fw[HRT][FM];
 };
 
+// Thread = 2 adjacent output columns x 8 rows: every 128-bit broadcast load of x^ feeds 8 FMAs per weight matrix and
+// the weights arrive as 64-bit coalesced loads.  Warp w = (row group w >> 2, head w & 3): the 32 lanes of a warp hold
+// exactly the 64 columns of one head, so a head's QK^T dot product is a single warp reduction and the whole attention
+// (softmax over the two modality tokens, masks, Philox dropout, PV) stays in registers.
 __global__ void __launch_bounds__(HTHREADS, 1)
 fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
   extern __shared__ __align__(16) unsigned char fusion_pass_smem_raw[];
   FusionPassSmem& sm = *reinterpret_cast<FusionPassSmem*>(fusion_pass_smem_raw);
-  const int tid = threadIdx.x, n = tid & (FD - 1), half = tid >> 8, lane = tid & 31, warp = tid >> 5;
-  const int h = n >> 6;                    // head of column n
-  const int rbase = half * HR;             // this thread's 16 rows of the tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cp = tid & 127, n0 = 2 * cp, rg = tid >> 7, rbase = rg * HR;
+  const int head = warp & 3;
   const long long n_rows = (long long)P.B * P.T;
   const long long row0 = (long long)blockIdx.x * HRT;
-  int bclip[HR];                           // clip of each of this thread's rows
+  int bclip[HR], tpass[HR];
 #pragma unroll
   for (int j = 0; j < HR; ++j) {
     long long row = row0 + rbase + j;
     if (row >= n_rows) row = n_rows - 1;
     bclip[j] = (int)(row / P.T);
+    tpass[j] = (int)(row % P.T);
   }
+  auto cb = [&](int j, int slot) {      // this thread's two columns of a per-clip vector
+    return __ldg(reinterpret_cast<const float2*>(clipbuf + ((size_t)bclip[j] * FCB + slot) * FD + n0));
+  };
 
   // ---- phase 1: Z_v = pre_ln(proj_v(z_v)), x^_v ---------------------------------------------------------------
   {
-    float acc[HR];
+    float a0[HR], a1[HR];
     const float* src[HR];
 #pragma unroll
     for (int j = 0; j < HR; ++j) {
-      long long row = row0 + rbase + j;
-      if (row >= n_rows) row = n_rows - 1;
-      const long long t = row % P.T;
-      src[j] = P.z[1] + (size_t)((long long)bclip[j] * P.rpc[1] + (P.rpc[1] == 1 ? 0 : t)) * P.dim[1];
-      acc[j] = 0.f;
+      src[j] = P.z[1] + (size_t)((long long)bclip[j] * P.rpc[1] + (P.rpc[1] == 1 ? 0 : tpass[j])) * P.dim[1];
+      a0[j] = 0.f; a1[j] = 0.f;
     }
-    const float* wt = P.proj_wt[1] + n;
+    const float* wt = P.proj_wt[1] + n0;
     for (int k = 0; k < P.dim[1]; k += 4) {
-      const float w0 = __ldg(wt + (size_t)k * FD), w1 = __ldg(wt + (size_t)(k + 1) * FD);
-      const float w2 = __ldg(wt + (size_t)(k + 2) * FD), w3 = __ldg(wt + (size_t)(k + 3) * FD);
+      float2 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const float2*>(wt + (size_t)(k + u) * FD));
 #pragma unroll
       for (int j = 0; j < HR; ++j) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(src[j] + k));
-        acc[j] = fmaf(w0, x.x, acc[j]); acc[j] = fmaf(w1, x.y, acc[j]);
-        acc[j] = fmaf(w2, x.z, acc[j]); acc[j] = fmaf(w3, x.w, acc[j]);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a0[j] = fmaf(w[u].x, xs[u], a0[j]); a1[j] = fmaf(w[u].y, xs[u], a1[j]); }
       }
     }
-    const float pb = __ldg(P.proj_b[1] + n);
+    const float2 pb = __ldg(reinterpret_cast<const float2*>(P.proj_b[1] + n0));
 #pragma unroll
-    for (int j = 0; j < HR; ++j) sm.xh[rbase + j][n] = acc[j] + pb;
+    for (int j = 0; j < HR; ++j)
+      *reinterpret_cast<float2*>(&sm.xh[rbase + j][n0]) = make_float2(a0[j] + pb.x, a1[j] + pb.y);
   }
   __syncthreads();
   for (int r = warp; r < HRT; r += 16) {
@@ -542,39 +549,23 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
   // ---- phase 2: the two attention layers; layer i's query is token i ----------------------------------------------
 #pragma unroll 1
   for (int i = 0; i < FM; ++i) {
-    float q[HR], kk[HR], vv[HR];
+    float q0[HR], q1[HR], k0[HR], k1[HR], v0[HR], v1[HR];
     {
-      const float bq = __ldg(P.qkv_b[i][0] + n), bk = __ldg(P.qkv_b[i][1] + n), bv = __ldg(P.qkv_b[i][2] + n);
+      const float2 bq = __ldg(reinterpret_cast<const float2*>(P.qkv_b[i][0] + n0));
+      const float2 bk = __ldg(reinterpret_cast<const float2*>(P.qkv_b[i][1] + n0));
+      const float2 bv = __ldg(reinterpret_cast<const float2*>(P.qkv_b[i][2] + n0));
 #pragma unroll
-      for (int j = 0; j < HR; ++j) { q[j] = bq; kk[j] = bk; vv[j] = bv; }
+      for (int j = 0; j < HR; ++j) { q0[j] = bq.x; q1[j] = bq.y; k0[j] = bk.x; k1[j] = bk.y; v0[j] = bv.x; v1[j] = bv.y; }
     }
-    const float *wq = P.qkv_wt[i][0] + n, *wk = P.qkv_wt[i][1] + n, *wv = P.qkv_wt[i][2] + n;
+    const float *wq = P.qkv_wt[i][0] + n0, *wk = P.qkv_wt[i][1] + n0, *wv = P.qkv_wt[i][2] + n0;
     if (i == 0) {
-      // Q_0 comes from the audio token: precomputed per clip
 #pragma unroll 2
       for (int k = 0; k < FD; k += 4) {
-        float ck[4], cv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { ck[u] = __ldg(wk + (size_t)(k + u) * FD); cv[u] = __ldg(wv + (size_t)(k + u) * FD); }
-#pragma unroll
-        for (int j = 0; j < HR; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(&sm.xh[rbase + j][k]);
-          const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { kk[j] = fmaf(ck[u], xs[u], kk[j]); vv[j] = fmaf(cv[u], xs[u], vv[j]); }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < HR; ++j) q[j] = __ldg(clipbuf + ((size_t)bclip[j] * FCB + 1) * FD + n);
-    } else {
-#pragma unroll 1
-      for (int k = 0; k < FD; k += 4) {
-        float cq[4], ck[4], cv[4];
+        float2 ck[4], cv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          cq[u] = __ldg(wq + (size_t)(k + u) * FD);
-          ck[u] = __ldg(wk + (size_t)(k + u) * FD);
-          cv[u] = __ldg(wv + (size_t)(k + u) * FD);
+          ck[u] = __ldg(reinterpret_cast<const float2*>(wk + (size_t)(k + u) * FD));
+          cv[u] = __ldg(reinterpret_cast<const float2*>(wv + (size_t)(k + u) * FD));
         }
 #pragma unroll
         for (int j = 0; j < HR; ++j) {
@@ -582,83 +573,93 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
           const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            q[j] = fmaf(cq[u], xs[u], q[j]); kk[j] = fmaf(ck[u], xs[u], kk[j]); vv[j] = fmaf(cv[u], xs[u], vv[j]);
+            k0[j] = fmaf(ck[u].x, xs[u], k0[j]); k1[j] = fmaf(ck[u].y, xs[u], k1[j]);
+            v0[j] = fmaf(cv[u].x, xs[u], v0[j]); v1[j] = fmaf(cv[u].y, xs[u], v1[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < HR; ++j) { const float2 t2 = cb(j, 1); q0[j] = t2.x; q1[j] = t2.y; }   // Q_0: per clip
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < FD; k += 4) {
+        float2 cq[4], ck[4], cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          cq[u] = __ldg(reinterpret_cast<const float2*>(wq + (size_t)(k + u) * FD));
+          ck[u] = __ldg(reinterpret_cast<const float2*>(wk + (size_t)(k + u) * FD));
+          cv[u] = __ldg(reinterpret_cast<const float2*>(wv + (size_t)(k + u) * FD));
+        }
+#pragma unroll
+        for (int j = 0; j < HR; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(&sm.xh[rbase + j][k]);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            q0[j] = fmaf(cq[u].x, xs[u], q0[j]); q1[j] = fmaf(cq[u].y, xs[u], q1[j]);
+            k0[j] = fmaf(ck[u].x, xs[u], k0[j]); k1[j] = fmaf(ck[u].y, xs[u], k1[j]);
+            v0[j] = fmaf(cv[u].x, xs[u], v0[j]); v1[j] = fmaf(cv[u].y, xs[u], v1[j]);
           }
         }
       }
     }
-    // scores against the audio key (per clip) and the video key (this row)
+    // attention of this warp's head for its 8 rows, entirely in registers
     const int ka = i == 0 ? 2 : 4, va = i == 0 ? 3 : 5;        // clipbuf slots of K_ia, V_ia
 #pragma unroll
     for (int j = 0; j < HR; ++j) {
-      const float kaud = __ldg(clipbuf + ((size_t)bclip[j] * FCB + ka) * FD + n);
-      const float s0 = warp_sum(q[j] * kaud), s1 = warp_sum(q[j] * kk[j]);
-      if (lane == 0) { sm.part[warp][rbase + j][0] = s0; sm.part[warp][rbase + j][1] = s1; }
-    }
-    __syncthreads();
-    if (tid < HRT * FHEADS) {
-      const int r = tid >> 2, hh = tid & 3;
-      long long row = row0 + r;
-      if (row >= n_rows) row = n_rows - 1;
-      const int b = (int)(row / P.T), t = (int)(row % P.T);
-      const int w0 = (r >= HR ? 8 : 0) + 2 * hh;                 // the two warps of (row half, head hh)
-      float s[FM];
-      bool inv[FM], all_inv = true;
-#pragma unroll
-      for (int m = 0; m < FM; ++m) {
-        inv[m] = P.mask ? (__ldg(P.mask + (size_t)b * FM + m) <= 0.f) : false;
-        all_inv = all_inv && inv[m];
-        s[m] = (sm.part[w0][r][m] + sm.part[w0 + 1][r][m]) * 0.125f;
-        if (inv[m]) s[m] = -1e4f;
-      }
-      const float mx = fmaxf(s[0], s[1]);
-      const float e0 = expf(s[0] - mx), e1 = expf(s[1] - mx);
+      const float2 kaud = cb(j, ka);
+      float s0 = warp_sum(q0[j] * kaud.x + q1[j] * kaud.y) * 0.125f;      // key = audio token
+      float s1 = warp_sum(q0[j] * k0[j] + q1[j] * k1[j]) * 0.125f;        // key = video token
+      const int b = bclip[j];
+      const bool inv0 = P.mask ? (__ldg(P.mask + (size_t)b * FM) <= 0.f) : false;
+      const bool inv1 = P.mask ? (__ldg(P.mask + (size_t)b * FM + 1) <= 0.f) : false;
+      if (inv0) s0 = -1e4f;
+      if (inv1) s1 = -1e4f;
+      const float mx = fmaxf(s0, s1);
+      const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
       const float den = e0 + e1;
-      float a[FM] = {e0 / den, e1 / den};
-      if (all_inv) { a[0] = 0.f; a[1] = 0.f; }
+      float a0 = e0 / den, a1 = e1 / den;
+      if (inv0 && inv1) { a0 = 0.f; a1 = 0.f; }
       if (P.ds.thr != 0u) {
-        const Philox4 w = philox4x32_10((uint32_t)(hh >> 1), (uint32_t)(P.ds.clip0 + (uint64_t)b),
-                                        P.ds.t0 + (uint32_t)t, AVHOT_SITE_ATTN + i, P.ds.k0, P.ds.k1);
-#pragma unroll
-        for (int m = 0; m < FM; ++m) {
-          const uint32_t word = philox_word(w, (uint32_t)((hh & 1) * 2 + m));
-          a[m] = word >= P.ds.thr ? a[m] * P.ds.scale : 0.f;
-        }
+        const Philox4 w = philox4x32_10((uint32_t)(head >> 1), (uint32_t)(P.ds.clip0 + (uint64_t)b),
+                                        P.ds.t0 + (uint32_t)tpass[j], AVHOT_SITE_ATTN + i, P.ds.k0, P.ds.k1);
+        a0 = philox_word(w, (uint32_t)((head & 1) * 2)) >= P.ds.thr ? a0 * P.ds.scale : 0.f;
+        a1 = philox_word(w, (uint32_t)((head & 1) * 2 + 1)) >= P.ds.thr ? a1 * P.ds.scale : 0.f;
       }
-      sm.attn[r][hh][0] = a[0];
-      sm.attn[r][hh][1] = a[1];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < HR; ++j) {
-      const float vaud = __ldg(clipbuf + ((size_t)bclip[j] * FCB + va) * FD + n);
-      sm.buf[rbase + j][n] = sm.attn[rbase + j][h][0] * vaud + sm.attn[rbase + j][h][1] * vv[j];
+      const float2 vaud = cb(j, va);
+      *reinterpret_cast<float2*>(&sm.buf[rbase + j][n0]) = make_float2(a0 * vaud.x + a1 * v0[j], a0 * vaud.y + a1 * v1[j]);
     }
     __syncthreads();
     {
-      float acc[HR];
-      const float bo = __ldg(P.o_b[i] + n);
+      float a0[HR], a1[HR];
+      const float2 bo = __ldg(reinterpret_cast<const float2*>(P.o_b[i] + n0));
 #pragma unroll
-      for (int j = 0; j < HR; ++j) acc[j] = bo;
-      const float* wo = P.o_wt[i] + n;
+      for (int j = 0; j < HR; ++j) { a0[j] = bo.x; a1[j] = bo.y; }
+      const float* wo = P.o_wt[i] + n0;
 #pragma unroll 2
       for (int k = 0; k < FD; k += 4) {
-        float co[4];
+        float2 co[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) co[u] = __ldg(wo + (size_t)(k + u) * FD);
+        for (int u = 0; u < 4; ++u) co[u] = __ldg(reinterpret_cast<const float2*>(wo + (size_t)(k + u) * FD));
 #pragma unroll
         for (int j = 0; j < HR; ++j) {
           const float4 x = *reinterpret_cast<const float4*>(&sm.buf[rbase + j][k]);
-          acc[j] = fmaf(co[0], x.x, acc[j]); acc[j] = fmaf(co[1], x.y, acc[j]);
-          acc[j] = fmaf(co[2], x.z, acc[j]); acc[j] = fmaf(co[3], x.w, acc[j]);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { a0[j] = fmaf(co[u].x, xs[u], a0[j]); a1[j] = fmaf(co[u].y, xs[u], a1[j]); }
         }
       }
 #pragma unroll
       for (int j = 0; j < HR; ++j) {
         const int r = rbase + j;
-        const float res = i == 0 ? __ldg(clipbuf + ((size_t)bclip[j] * FCB + 0) * FD + n)
-                                 : fmaf(sm.xh[r][n], sm.zstd[r], sm.zmean[r]);
-        sm.hatt[r][i][n] = acc[j] + res;
+        float2 res;
+        if (i == 0) {
+          res = cb(j, 0);                                                         // Z_a, per clip
+        } else {
+          const float2 xv = *reinterpret_cast<const float2*>(&sm.xh[r][n0]);
+          res = make_float2(fmaf(xv.x, sm.zstd[r], sm.zmean[r]), fmaf(xv.y, sm.zstd[r], sm.zmean[r]));
+        }
+        *reinterpret_cast<float2*>(&sm.hatt[r][i][n0]) = make_float2(a0[j] + res.x, a1[j] + res.y);
       }
     }
     __syncthreads();
@@ -680,39 +681,38 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
 
   // ---- phase 3: gate, modality softmax, classifier ------------------------------------------------------------------
   {
-    const int g = tid & (FG - 1), m = (tid >> 7) & 1;
-    float acc[HR];
-    const float gb = __ldg(P.g0_b + g);
+    const int g0 = 2 * (tid & 63), m = (tid >> 6) & 1;      // warps 4rg + 2m, 4rg + 2m + 1 cover the 128 gate units
+    float a0[HR], a1[HR];
+    const float2 gb = __ldg(reinterpret_cast<const float2*>(P.g0_b + g0));
 #pragma unroll
-    for (int j = 0; j < HR; ++j) acc[j] = gb;
-    const float* w0 = P.g0_wt + g;
+    for (int j = 0; j < HR; ++j) { a0[j] = gb.x; a1[j] = gb.y; }
+    const float* w0 = P.g0_wt + g0;
 #pragma unroll 2
     for (int k = 0; k < FD; k += 4) {
-      float c0[4];
+      float2 c0[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) c0[u] = __ldg(w0 + (size_t)(k + u) * FG);
+      for (int u = 0; u < 4; ++u) c0[u] = __ldg(reinterpret_cast<const float2*>(w0 + (size_t)(k + u) * FG));
 #pragma unroll
       for (int j = 0; j < HR; ++j) {
         const float4 x = *reinterpret_cast<const float4*>(&sm.hatt[rbase + j][m][k]);
-        acc[j] = fmaf(c0[0], x.x, acc[j]); acc[j] = fmaf(c0[1], x.y, acc[j]);
-        acc[j] = fmaf(c0[2], x.z, acc[j]); acc[j] = fmaf(c0[3], x.w, acc[j]);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a0[j] = fmaf(c0[u].x, xs[u], a0[j]); a1[j] = fmaf(c0[u].y, xs[u], a1[j]); }
       }
     }
-    const float w3 = __ldg(P.g3_w + g);
+    const float2 w3 = __ldg(reinterpret_cast<const float2*>(P.g3_w + g0));
 #pragma unroll
     for (int j = 0; j < HR; ++j) {
-      float v = fmaxf(acc[j], 0.f);
+      float va = fmaxf(a0[j], 0.f), vb = fmaxf(a1[j], 0.f);
       if (P.ds.thr != 0u) {
-        long long row = row0 + rbase + j;
-        if (row >= n_rows) row = n_rows - 1;
-        const int t = (int)(row % P.T);
-        const uint32_t e = (uint32_t)(m * FG + g);
-        const Philox4 w = philox4x32_10(e >> 2, (uint32_t)(P.ds.clip0 + (uint64_t)bclip[j]), P.ds.t0 + (uint32_t)t,
-                                        AVHOT_SITE_GATE, P.ds.k0, P.ds.k1);
-        v = philox_word(w, e & 3) >= P.ds.thr ? v * P.ds.scale : 0.f;
+        const uint32_t e = (uint32_t)(m * FG + g0);           // even: both elements are in one Philox block
+        const Philox4 w = philox4x32_10(e >> 2, (uint32_t)(P.ds.clip0 + (uint64_t)bclip[j]),
+                                        P.ds.t0 + (uint32_t)tpass[j], AVHOT_SITE_GATE, P.ds.k0, P.ds.k1);
+        va = philox_word(w, e & 3) >= P.ds.thr ? va * P.ds.scale : 0.f;
+        vb = philox_word(w, (e & 3) + 1) >= P.ds.thr ? vb * P.ds.scale : 0.f;
       }
-      const float sres = warp_sum(v * w3);
-      if (lane == 0) sm.part[warp][rbase + j][0] = sres;
+      const float sres = warp_sum(va * w3.x + vb * w3.y);
+      if (lane == 0) sm.part[warp][rbase + j] = sres;
     }
   }
   __syncthreads();
@@ -722,12 +722,11 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
     if (row >= n_rows) row = n_rows - 1;
     const int b = (int)(row / P.T);
     const float gb3 = __ldg(P.g3_b);
-    const int wbase = r >= HR ? 8 : 0;       // warps of this row half: modality m uses warps wbase + 4m .. + 3
+    const int wbase = 4 * (r / HR);            // warps of this row's group: modality m uses warps wbase + 2m, + 2m + 1
     float s[FM];
 #pragma unroll
     for (int m = 0; m < FM; ++m) {
-      s[m] = sm.part[wbase + 4 * m][r][0] + sm.part[wbase + 4 * m + 1][r][0] + sm.part[wbase + 4 * m + 2][r][0] +
-             sm.part[wbase + 4 * m + 3][r][0] + gb3;
+      s[m] = sm.part[wbase + 2 * m][r] + sm.part[wbase + 2 * m + 1][r] + gb3;
       const bool inv = P.mask ? (__ldg(P.mask + (size_t)b * FM + m) <= 0.f) : false;
       if (inv) s[m] = -1e4f;
     }
@@ -744,7 +743,10 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
 #pragma unroll
   for (int j = 0; j < HR; ++j) {
     const int r = rbase + j;
-    sm.buf[r][n] = sm.fw[r][0] * sm.hatt[r][0][n] + sm.fw[r][1] * sm.hatt[r][1][n];
+    const float2 h0 = *reinterpret_cast<const float2*>(&sm.hatt[r][0][n0]);
+    const float2 h1 = *reinterpret_cast<const float2*>(&sm.hatt[r][1][n0]);
+    *reinterpret_cast<float2*>(&sm.buf[r][n0]) =
+        make_float2(sm.fw[r][0] * h0.x + sm.fw[r][1] * h1.x, sm.fw[r][0] * h0.y + sm.fw[r][1] * h1.y);
   }
   __syncthreads();
   {

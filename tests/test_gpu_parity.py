@@ -243,8 +243,10 @@ def test_hybrid_fusion_vs_reference_golden(pkg, dev, world, golden):
         assert rel_err(info["per_modality_attention"]["video"].cpu().numpy(), golden[f"attn_video_{name}"]) <= REL
         assert info["H_att"].shape == (6, 2, 256)
         assert info["per_modality_attention"]["audio"].shape == (6, 4, 1, 2)
-        only = fm(feats, torch.from_numpy(mask).to(dev))
-        assert isinstance(only, torch.Tensor) and (only == logits).all()
+        only = fm(feats, torch.from_numpy(mask).to(dev))          # no diagnostics: the hoisted kernels
+        assert isinstance(only, torch.Tensor)
+        assert rel_err(only.cpu().numpy(), golden[f"logits_hybrid_{name}"]) <= REL
+        assert rel_err(only.cpu().numpy(), logits.cpu().numpy()) <= 1e-5
     none_mask = fm(feats).cpu().numpy()                            # modality_mask=None == ones (:468-469)
     assert rel_err(none_mask, golden["logits_hybrid_ones"]) <= REL
     # absent modality: zero features + masked (:480-485)
