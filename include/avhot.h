@@ -207,8 +207,8 @@ size_t avhot_fusion_workspace_bytes(avhot_fusion_t h, int B, int T);
 int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
                          const int* z_rows_per_clip_host, const float* mask, float* logits,
                          float* fusion_weights, float* attn, float* h_att, int B, int T,
-                         float p, uint64_t seed, uint64_t clip0, uint32_t t0, void* workspace,
-                         size_t workspace_bytes, avhot_stream_t stream);
+                         float p, uint64_t seed, uint64_t clip0, uint32_t t0, int precision,
+                         void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 /* workspace (optional, avhot_fusion_workspace_bytes): lets the hybrid path compute the pass-invariant
  * half of modality 0 once per clip when z_rows_per_clip[0] == 1 (same results, fewer FLOPs). */
 

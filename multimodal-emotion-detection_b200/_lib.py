@@ -95,7 +95,7 @@ PROTOTYPES = {
     "avhot_fusion_destroy": (None, [_P]),
     "avhot_fusion_workspace_bytes": (_SZ, [_P, _I, _I]),
     "avhot_fusion_forward": (_I, [_P, C.POINTER(_P), C.POINTER(_I), _P, _P, _P, _P, _P, _I, _I, _F,
-                                  _U64, _U64, _U32, _P, _SZ, _P]),
+                                  _U64, _U64, _U32, _I, _P, _SZ, _P]),
     "avhot_mc_reduce": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
 }
 

@@ -12,6 +12,7 @@
 //   -> out_proj -> + residual -> post_ln] -> gate MLP (Philox dropout) -> masked softmax over modalities
 //   -> finite guard + renormalise -> weighted sum -> classifier.
 #include "common.cuh"
+#include "fusion_tc.cuh"
 
 struct avhot_fusion {
   int kind;             // 0 hybrid, 1 concat head
@@ -30,6 +31,8 @@ struct avhot_fusion {
   // concat head
   int head_in, head_hidden;
   float *h0_wt, *h0_b;                     // [k][n]
+  void* tc_w;                              // packed fp16 weights of the tensor-core per-pass kernel (fusion_tc.cu)
+  float* tc_vec;                           // its small fp32 vectors
   float* arena;
 };
 
@@ -860,6 +863,7 @@ extern "C" int avhot_fusion_create(const avhot_fusion_desc* f, const avhot_head_
     }
     total += 4 * al(FD) + al((size_t)FD * FG) + al(FG) + al(FG) + al(1) + al((size_t)f->num_classes * FD) +
              al(f->num_classes);
+    total += al(fusion_tc_packed_bytes() / sizeof(float)) + al(FUS_VEC_FLOATS);
   } else {
     if (!(hd->hidden_dim == FD && hd->num_classes >= 1 && hd->num_classes <= FCMAX && hd->in_dim > 0 &&
           (hd->in_dim & 3) == 0 && hd->in_dim <= 2048)) {
@@ -921,6 +925,33 @@ extern "C" int avhot_fusion_create(const avhot_fusion_desc* f, const avhot_head_
     copy(h->g3_w, f->gate3_w, FG); copy(h->g3_b, f->gate3_b, 1);
     h->cls_w = take((size_t)h->C * FD); h->cls_b = take(h->C);
     copy(h->cls_w, f->cls_w, (size_t)h->C * FD); copy(h->cls_b, f->cls_b, h->C);
+    // tensor-core per-pass kernel: packed fp16 weights (from the folded k-major fp32 copies above) + small vectors
+    h->tc_w = take(fusion_tc_packed_bytes() / sizeof(float));
+    h->tc_vec = take(FUS_VEC_FLOATS);
+    if (ok && h->dim[1] % 64 == 0 && h->dim[1] <= 256 && h->C <= 8) {
+      auto pack = [&](const float* src_t, int row0, int N, int K) {
+        if (fusion_tc_pack_rows(src_t, h->tc_w, row0, N, K, s) != AVHOT_OK) ok = false;
+      };
+      pack(h->proj_wt[1], 0, FD, h->dim[1]);
+      pack(h->qkv_wt[0][1], 256, FD, FD);  pack(h->qkv_wt[0][2], 512, FD, FD);
+      pack(h->qkv_wt[1][0], 768, FD, FD);  pack(h->qkv_wt[1][1], 1024, FD, FD);  pack(h->qkv_wt[1][2], 1280, FD, FD);
+      pack(h->o_wt[0], 1536, FD, FD);      pack(h->o_wt[1], 1792, FD, FD);
+      pack(h->g0_wt, 2048, FG, FD);
+      if (cudaMemsetAsync(h->tc_vec, 0, sizeof(float) * FUS_VEC_FLOATS, s) != cudaSuccess) ok = false;
+      copy(h->tc_vec + VEC_PROJ_B, h->proj_b[1], FD);
+      copy(h->tc_vec + VEC_PRE_W, h->pre_w, FD);   copy(h->tc_vec + VEC_PRE_B, h->pre_b, FD);
+      copy(h->tc_vec + VEC_POST_W, h->post_w, FD); copy(h->tc_vec + VEC_POST_B, h->post_b, FD);
+      copy(h->tc_vec + VEC_BK0, h->qkv_b[0][1], FD); copy(h->tc_vec + VEC_BV0, h->qkv_b[0][2], FD);
+      copy(h->tc_vec + VEC_BQ1, h->qkv_b[1][0], FD); copy(h->tc_vec + VEC_BK1, h->qkv_b[1][1], FD);
+      copy(h->tc_vec + VEC_BV1, h->qkv_b[1][2], FD);
+      copy(h->tc_vec + VEC_BO0, h->o_b[0], FD);    copy(h->tc_vec + VEC_BO1, h->o_b[1], FD);
+      copy(h->tc_vec + VEC_G0_B, h->g0_b, FG);     copy(h->tc_vec + VEC_G3_W, h->g3_w, FG);
+      copy(h->tc_vec + VEC_G3_B, h->g3_b, 1);
+      copy(h->tc_vec + VEC_CLS_W, h->cls_w, (size_t)h->C * FD);
+      copy(h->tc_vec + VEC_CLS_B, h->cls_b, h->C);
+    } else {
+      h->tc_w = nullptr;
+    }
   } else {
     h->kind = 1; h->M = FM; h->D = FD; h->C = hd->num_classes; h->head_in = hd->in_dim; h->head_hidden = FD;
     h->h0_wt = take((size_t)hd->in_dim * FD); h->h0_b = take(FD);
@@ -954,11 +985,13 @@ extern "C" size_t avhot_fusion_workspace_bytes(avhot_fusion_t h, int B, int T) {
 extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
                                     const int* z_rows_per_clip_host, const float* mask, float* logits,
                                     float* fusion_weights, float* attn, float* h_att, int B, int T, float p,
-                                    uint64_t seed, uint64_t clip0, uint32_t t0, void* workspace,
+                                    uint64_t seed, uint64_t clip0, uint32_t t0, int precision, void* workspace,
                                     size_t workspace_bytes, avhot_stream_t stream) {
   AVHOT_REQUIRE(h && z_host_array && z_rows_per_clip_host && logits && B >= 0 && T >= 1, AVHOT_ERR_INVALID,
                 "fusion_forward: bad arguments");
   AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "fusion_forward: dropout p=%g outside [0, 1)", (double)p);
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
+                "fusion_forward: precision %d not built", precision);
   if (B == 0) return AVHOT_OK;
   const long long rows = (long long)B * T;
   const long long grid = (rows + FRT - 1) / FRT;
@@ -993,6 +1026,13 @@ extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host
         ProfScope prof("fusion_clip", s);
         fusion_clip_kernel<<<ceil_div(B, FRT), FTHREADS, 0, s>>>(P, clipbuf);
         AVHOT_LAUNCH_CHECK();
+      }
+      if (precision == AVHOT_PREC_TC && h->tc_w) {
+        FusTcParams Q;
+        Q.z_v = P.z[1]; Q.rpc_v = P.rpc[1]; Q.dim_v = P.dim[1];
+        Q.clipbuf = clipbuf; Q.mask = mask; Q.logits = logits;
+        Q.B = B; Q.T = T; Q.C = h->C; Q.vec = h->tc_vec; Q.ds = P.ds;
+        return fusion_tc_forward(h->tc_w, Q, s);
       }
       const long long grid2 = (rows + HRT - 1) / HRT;
       AVHOT_CUDA(cudaFuncSetAttribute(fusion_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,0 +1,472 @@
+// HybridFusion per-pass work on the tcgen05 tensor cores (AVHOT_PREC_TC path of a5 + a6, src/fusion.py:455-530,
+// src/attention.py:80-141), for rows (clip, pass) whose audio token is pass-invariant (fusion_clip_kernel has
+// already produced Z_a, Q_0, K_0a, V_0a, K_1a, V_1a per clip).
+//
+// One CTA = 128 rows.  Thread r of the four epilogue warps owns row r = TMEM lane r, so every non-GEMM step of the
+// module - both LayerNorms, the 4-head / 2-key softmax, masks, Philox dropout, residuals, the gate's ReLU + dropout
+// + 128-wide dot, the 8-class classifier - is thread-local arithmetic over the 256 accumulator columns of its
+// lane: no shuffles, no shared-memory reductions.  The eight GEMM groups of a tile
+//   G1 proj_v              x = z_v        -> Z_v raw            G5 Q_1 | K_1v          x^ -> D_a | D_b
+//   G2 K_0v | V_0v         x^             -> D_a | D_b          G6 V_1v                x^ -> D_a
+//   G3 out_proj_0          ctx_0          -> D_a                G7 out_proj_1          ctx_1 -> D_b
+//   G4 gate(H_0)           H_0            -> D_a[0:128]         G8 gate(H_1)           H_1 -> D_a[0:128]
+// run as tcgen05.mma kind::f16 (M 128, N 128, K 16) with fp16 A operands that the epilogue writes straight into
+// the 128-byte-swizzled K-major layout (two 64 KB buffers X and C), fp16 weights streamed by TMA through a
+// 4-stage ring, and two 256-column fp32 accumulators in TMEM.  The classifier is linear, so
+// logits = w_0 cls(H_0) + w_1 cls(H_1) + b and H_m never has to outlive its own epilogue.
+//   warp 0  TMA producer      warp 1  TMEM alloc + MMA issue      warps 2-5  epilogue (thread = row)
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+#include "fusion_tc.cuh"
+
+namespace avhot {
+namespace tc {
+
+constexpr int UB = 128, UD = 256, UST = 4, UTHREADS = 192;
+// rows of the packed fp16 weight tensor (K = 256 columns each)
+constexpr int ROW_PROJ = 0, ROW_K0 = 256, ROW_V0 = 512, ROW_Q1 = 768, ROW_K1 = 1024, ROW_V1 = 1280, ROW_O0 = 1536,
+              ROW_O1 = 1792, ROW_G0 = 2048, ROWS_ALL = 2176;
+
+struct FusTcSmem {
+  __half X[4][UB * 64];      // A operand: z_v, then x^_v
+  __half C[4][UB * 64];      // A operand: ctx_0 -> H_0 -> ctx_1 -> H_1
+  __half wB[UST][128 * 64];  // weight ring, 128 output rows x 64 k per stage
+  float vec[FUS_VEC_FLOATS];
+  uint64_t full[UST], empty[UST], m2e, e2m;
+  uint32_t tmem_base;
+};
+
+struct SubGemm { int row0, n, from_c, dcol; };
+struct Group { int n_sub; SubGemm sub[2]; };
+__device__ __constant__ Group kGroups[8] = {
+    {1, {{ROW_PROJ, 256, 0, 0}, {0, 0, 0, 0}}},
+    {2, {{ROW_K0, 256, 0, 0}, {ROW_V0, 256, 0, 256}}},
+    {1, {{ROW_O0, 256, 1, 0}, {0, 0, 0, 0}}},
+    {1, {{ROW_G0, 128, 1, 0}, {0, 0, 0, 0}}},
+    {2, {{ROW_Q1, 256, 0, 0}, {ROW_K1, 256, 0, 256}}},
+    {1, {{ROW_V1, 256, 0, 0}, {0, 0, 0, 0}}},
+    {1, {{ROW_O1, 256, 1, 256}, {0, 0, 0, 0}}},
+    {1, {{ROW_G0, 128, 1, 0}, {0, 0, 0, 0}}},
+};
+
+// 8 consecutive fp16 of row r starting at column c (c % 8 == 0) in a [4][128 x 64] swizzled K-major operand
+__device__ __forceinline__ uint4* a_chunk(__half* buf, int r, int c) {
+  unsigned char* p = reinterpret_cast<unsigned char*>(buf) + (size_t)(c >> 6) * (UB * 128) + (size_t)r * 128 +
+                     ((((c & 63) >> 3) ^ (r & 7)) << 4);
+  return reinterpret_cast<uint4*>(p);
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+__global__ void __launch_bounds__(UTHREADS, 1)
+fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
+  extern __shared__ unsigned char fus_tc_smem_raw[];
+  FusTcSmem& sm = *reinterpret_cast<FusTcSmem*>((reinterpret_cast<uintptr_t>(fus_tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_rows = (long long)P.B * P.T;
+  const int n_tiles = (int)((n_rows + UB - 1) / UB);
+  const int kv = P.dim_v / 64;                          // k-blocks of the video embedding
+
+  for (int i = threadIdx.x; i < FUS_VEC_FLOATS; i += UTHREADS) sm.vec[i] = P.vec[i];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < UST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.m2e, 1);
+    mbar_init(&sm.e2m, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int g = 0; g < 8; ++g)
+          for (int sb = 0; sb < kGroups[g].n_sub; ++sb) {
+            const SubGemm sg = kGroups[g].sub[sb];
+            const int nkb = g == 0 ? kv : 4;
+            for (int nh = 0; nh < sg.n / 128; ++nh)
+              for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % UST;
+                mbar_wait(&sm.empty[s], ((it / UST) & 1) ^ 1);
+                mbar_expect_tx(&sm.full[s], (uint32_t)sizeof(sm.wB[0]));
+                tma_load_2d(sm.wB[s], &tmW, &sm.full[s], kb * 64, sg.row0 + nh * 128);
+              }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(FMT_F16, UB, 128);
+      uint32_t it = 0, op = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int g = 0; g < 8; ++g, ++op) {
+          mbar_wait(&sm.e2m, op & 1);                   // the epilogue has produced this group's A / freed its D
+          tc_fence_after();
+          for (int sb = 0; sb < kGroups[g].n_sub; ++sb) {
+            const SubGemm sg = kGroups[g].sub[sb];
+            const int nkb = g == 0 ? kv : 4;
+            __half* abuf = sg.from_c ? &sm.C[0][0] : &sm.X[0][0];
+            for (int nh = 0; nh < sg.n / 128; ++nh)
+              for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % UST;
+                mbar_wait(&sm.full[s], (it / UST) & 1);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(abuf + (size_t)kb * (UB * 64)));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s]));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(tmem + (uint32_t)(sg.dcol + nh * 128), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&sm.empty[s]);
+              }
+          }
+          umma_commit(&sm.m2e);
+        }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+    const float* V = sm.vec;
+    uint32_t op = 0;
+    auto to_mma = [&]() {           // A operand written / accumulators drained: let the MMA warp start the next group
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&sm.e2m);
+    };
+    auto from_mma = [&]() {
+      mbar_wait(&sm.m2e, op & 1);
+      ++op;
+      tc_fence_after();
+    };
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      long long row = (long long)tile * UB + r;
+      const bool live = row < n_rows;
+      if (!live) row = n_rows - 1;
+      const int b = (int)(row / P.T), t = (int)(row % P.T);
+      const uint32_t gclip = (uint32_t)(P.ds.clip0 + (uint64_t)b), pass = P.ds.t0 + (uint32_t)t;
+      const float* cbuf = P.clipbuf + (size_t)b * (6 * UD);
+      const bool inv0 = P.mask ? (__ldg(P.mask + (size_t)b * 2) <= 0.f) : false;
+      const bool inv1 = P.mask ? (__ldg(P.mask + (size_t)b * 2 + 1) <= 0.f) : false;
+
+      // ---- E0: z_v row -> fp16 A operand ---------------------------------------------------------------------------
+      {
+        const float* zr = P.z_v + (size_t)((long long)b * P.rpc_v + (P.rpc_v == 1 ? 0 : t)) * P.dim_v;
+        for (int c = 0; c < P.dim_v; c += 8) {
+          const float4 u0 = __ldg(reinterpret_cast<const float4*>(zr + c));
+          const float4 u1 = __ldg(reinterpret_cast<const float4*>(zr + c + 4));
+          const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          *a_chunk(&sm.X[0][0], r, c) = pack8(v);
+        }
+      }
+      to_mma();                                                           // -> G1
+
+      // ---- E1: Z_v = pre_ln(proj), x^_v = (Z_v - mean) / std -> X ----------------------------------------------------
+      from_mma();
+      float zmean, zstd;
+      {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < UD; c += 32) {
+          uint32_t a[32];
+          tmem_ld32(tl + (uint32_t)c, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(a[j]) + V[VEC_PROJ_B + c + j]; s1 += x; s2 = fmaf(x, x, s2); }
+        }
+        const float m1 = s1 * (1.f / UD);
+        const float rstd1 = 1.f / sqrtf(fmaxf(s2 * (1.f / UD) - m1 * m1, 0.f) + 1e-5f);
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < UD; c += 32) {
+          uint32_t a[32];
+          tmem_ld32(tl + (uint32_t)c, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(a[j]) + V[VEC_PROJ_B + c + j];
+            const float z = (x - m1) * rstd1 * V[VEC_PRE_W + c + j] + V[VEC_PRE_B + c + j];
+            s1 += z; s2 = fmaf(z, z, s2);
+          }
+        }
+        zmean = s1 * (1.f / UD);
+        zstd = sqrtf(fmaxf(s2 * (1.f / UD) - zmean * zmean, 0.f) + 1e-5f);
+        const float rstd2 = 1.f / zstd;
+#pragma unroll 1
+        for (int c = 0; c < UD; c += 32) {
+          uint32_t a[32];
+          tmem_ld32(tl + (uint32_t)c, a);
+          tmem_ld_wait();
+          float xn[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(a[j]) + V[VEC_PROJ_B + c + j];
+            const float z = (x - m1) * rstd1 * V[VEC_PRE_W + c + j] + V[VEC_PRE_B + c + j];
+            xn[j] = (z - zmean) * rstd2;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) *a_chunk(&sm.X[0][0], r, c + j) = pack8(&xn[j]);
+        }
+      }
+      to_mma();                                                           // -> G2 (K_0v | V_0v)
+
+      float cls0[8], cls1[8], score0 = 0.f, score1 = 0.f;
+      // ---- the two attention layers --------------------------------------------------------------------------------
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        float aa[4], av[4];                                               // attention weights per head: audio / video key
+        if (layer == 0) {
+          from_mma();                                                     // D_a = K_0v, D_b = V_0v
+          // scores: query = audio token (per clip), keys = audio token (per clip) and video token (this row)
+#pragma unroll 1
+          for (int hh = 0; hh < 4; ++hh) {
+            float sa = 0.f, sv = 0.f;
+#pragma unroll 1
+            for (int c = hh * 64; c < hh * 64 + 64; c += 32) {
+              uint32_t a[32];
+              tmem_ld32(tl + (uint32_t)c, a);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float q = __ldg(cbuf + 1 * UD + c + j);
+                sa = fmaf(q, __ldg(cbuf + 2 * UD + c + j), sa);
+                sv = fmaf(q, __uint_as_float(a[j]) + V[VEC_BK0 + c + j], sv);
+              }
+            }
+            aa[hh] = sa; av[hh] = sv;
+          }
+        } else {
+          from_mma();                                                     // D_a = Q_1, D_b = K_1v
+#pragma unroll 1
+          for (int hh = 0; hh < 4; ++hh) {
+            float sa = 0.f, sv = 0.f;
+#pragma unroll 1
+            for (int c = hh * 64; c < hh * 64 + 64; c += 32) {
+              uint32_t a[32], k[32];
+              tmem_ld32(tl + (uint32_t)c, a);
+              tmem_ld32(tl + 256u + (uint32_t)c, k);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float q = __uint_as_float(a[j]) + V[VEC_BQ1 + c + j];
+                sa = fmaf(q, __ldg(cbuf + 4 * UD + c + j), sa);
+                sv = fmaf(q, __uint_as_float(k[j]) + V[VEC_BK1 + c + j], sv);
+              }
+            }
+            aa[hh] = sa; av[hh] = sv;
+          }
+        }
+        // softmax over the two keys, masks, dropout (src/attention.py:112-130)
+        {
+          const Philox4 w0 = philox4x32_10(0u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
+          const Philox4 w1 = philox4x32_10(1u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            float s0 = aa[hh] * 0.125f, s1 = av[hh] * 0.125f;
+            if (inv0) s0 = -1e4f;
+            if (inv1) s1 = -1e4f;
+            const float mx = fmaxf(s0, s1);
+            const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+            const float den = e0 + e1;
+            float a0 = e0 / den, a1 = e1 / den;
+            if (inv0 && inv1) { a0 = 0.f; a1 = 0.f; }
+            if (P.ds.thr != 0u) {
+              const Philox4& w = hh < 2 ? w0 : w1;
+              a0 = philox_word(w, (uint32_t)((hh & 1) * 2)) >= P.ds.thr ? a0 * P.ds.scale : 0.f;
+              a1 = philox_word(w, (uint32_t)((hh & 1) * 2 + 1)) >= P.ds.thr ? a1 * P.ds.scale : 0.f;
+            }
+            aa[hh] = a0; av[hh] = a1;
+          }
+        }
+        if (layer == 1) {
+          to_mma();                                                       // D_a, D_b drained -> G6 (V_1v -> D_a)
+          from_mma();
+        }
+        // context = a_a V_a (per clip) + a_v V_v (this row) -> C     (layer 0: V_0v is in D_b; layer 1: V_1v in D_a)
+        {
+          const uint32_t vcol = layer == 0 ? 256u : 0u;
+          const int vb = layer == 0 ? VEC_BV0 : VEC_BV1, vslot = layer == 0 ? 3 : 5;
+#pragma unroll 1
+          for (int c = 0; c < UD; c += 32) {
+            uint32_t a[32];
+            tmem_ld32(tl + vcol + (uint32_t)c, a);
+            tmem_ld_wait();
+            const int hh = c >> 6;
+            float ctx[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              ctx[j] = aa[hh] * __ldg(cbuf + vslot * UD + c + j) + av[hh] * (__uint_as_float(a[j]) + V[vb + c + j]);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) *a_chunk(&sm.C[0][0], r, c + j) = pack8(&ctx[j]);
+          }
+        }
+        to_mma();                                                         // -> G3 / G7 (out_proj)
+
+        // out_proj + residual -> post_ln -> H: classifier partial sums, fp16 H -> C for the gate GEMM
+        from_mma();
+        {
+          const uint32_t ocol = layer == 0 ? 0u : 256u;
+          const int ob = layer == 0 ? VEC_BO0 : VEC_BO1;
+          float s1 = 0.f, s2 = 0.f;
+          auto residual = [&](int c, float (&res)[32]) {
+            if (layer == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) res[j] = __ldg(cbuf + c + j);                     // Z_a
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {                                             // Z_v = x^ * std + mean
+                const uint4 u = *a_chunk(&sm.X[0][0], r, c + j);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __half22float2(h2[q]);
+                  res[j + 2 * q] = fmaf(f.x, zstd, zmean);
+                  res[j + 2 * q + 1] = fmaf(f.y, zstd, zmean);
+                }
+              }
+            }
+          };
+#pragma unroll 1
+          for (int c = 0; c < UD; c += 32) {
+            uint32_t a[32];
+            float res[32];
+            tmem_ld32(tl + ocol + (uint32_t)c, a);
+            residual(c, res);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(a[j]) + V[ob + c + j] + res[j]; s1 += x; s2 = fmaf(x, x, s2); }
+          }
+          const float mean = s1 * (1.f / UD);
+          const float rstd = 1.f / sqrtf(fmaxf(s2 * (1.f / UD) - mean * mean, 0.f) + 1e-5f);
+          float cls[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cls[q] = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < UD; c += 32) {
+            uint32_t a[32];
+            float res[32], y[32];
+            tmem_ld32(tl + ocol + (uint32_t)c, a);
+            residual(c, res);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(a[j]) + V[ob + c + j] + res[j];
+              y[j] = (x - mean) * rstd * V[VEC_POST_W + c + j] + V[VEC_POST_B + c + j];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) cls[q] = fmaf(y[j], V[VEC_CLS_W + q * UD + c + j], cls[q]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) *a_chunk(&sm.C[0][0], r, c + j) = pack8(&y[j]);
+          }
+          if (layer == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cls0[q] = cls[q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cls1[q] = cls[q];
+          }
+        }
+        to_mma();                                                         // -> G4 / G8 (gate)
+
+        // gate: ReLU -> dropout -> Linear(128 -> 1)   (src/fusion.py:445-450)
+        from_mma();
+        {
+          float sc = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t a[32];
+            tmem_ld32(tl + (uint32_t)c, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              uint32_t wd[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+              if (P.ds.thr != 0u) {
+                const Philox4 w = philox4x32_10((uint32_t)((layer * 128 + c + j4) >> 2), gclip, pass, AVHOT_SITE_GATE,
+                                                P.ds.k0, P.ds.k1);
+                wd[0] = w.x; wd[1] = w.y; wd[2] = w.z; wd[3] = w.w;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float v = fmaxf(__uint_as_float(a[j4 + u]) + V[VEC_G0_B + c + j4 + u], 0.f);
+                v = wd[u] >= P.ds.thr ? v * P.ds.scale : 0.f;
+                sc = fmaf(v, V[VEC_G3_W + c + j4 + u], sc);
+              }
+            }
+          }
+          if (layer == 0) score0 = sc + V[VEC_G3_B]; else score1 = sc + V[VEC_G3_B];
+        }
+        if (layer == 0) to_mma();                                         // D_a drained -> G5 (Q_1 | K_1v)
+      }
+
+      // ---- modality softmax, finite guard, renormalise, logits (src/fusion.py:513-522) --------------------------------
+      {
+        float s0 = inv0 ? -1e4f : score0, s1 = inv1 ? -1e4f : score1;
+        const float mx = fmaxf(s0, s1);
+        const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+        float w0 = e0 / (e0 + e1), w1 = e1 / (e0 + e1);
+        if (!isfinite(w0)) w0 = 0.f;
+        if (!isfinite(w1)) w1 = 0.f;
+        const float den = fmaxf(w0 + w1, 1e-8f);
+        w0 /= den; w1 /= den;
+        if (live) {
+          float* out = P.logits + (size_t)row * P.C;
+          for (int q = 0; q < P.C; ++q) out[q] = w0 * cls0[q] + w1 * cls1[q] + V[VEC_CLS_B + q];
+        }
+      }
+      // the next tile's E0 overwrites X: every MMA that read X (G6) completed before G7's commit, which we have seen
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// out[(row0 + n) * 256 + k] = half(src_t[k * N + n]) for k < K, 0 for K <= k < 256   (src_t is [k][n])
+__global__ void pack_rows_f16_kernel(const float* __restrict__ src_t, __half* __restrict__ out, int row0, int N, int K) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < UD; k += blockDim.x)
+    out[(size_t)(row0 + n) * UD + k] = __float2half_rn(k < K ? src_t[(size_t)k * N + n] : 0.f);
+}
+
+}  // namespace tc
+
+int fusion_tc_pack_rows(const float* src_t, void* packed, int row0, int N, int K, cudaStream_t s) {
+  tc::pack_rows_f16_kernel<<<N, 128, 0, s>>>(src_t, reinterpret_cast<__half*>(packed), row0, N, K);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+size_t fusion_tc_packed_bytes() { return (size_t)tc::ROWS_ALL * tc::UD * sizeof(__half); }
+
+int fusion_tc_forward(const void* packed_w, const FusTcParams& P, cudaStream_t s) {
+  using namespace tc;
+  CUtensorMap tmW;
+  int rc = make_tensor_map_2d(&tmW, packed_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ROWS_ALL, UD, UD, 128, 64);
+  if (rc != AVHOT_OK) return rc;
+  const long long rows = (long long)P.B * P.T;
+  const int n_tiles = (int)((rows + UB - 1) / UB);
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  const int smem = (int)sizeof(FusTcSmem) + 1024;
+  AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ProfScope prof("fusion_tc", s);
+  fusion_tc_kernel<<<grid, UTHREADS, smem, s>>>(tmW, P);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+}  // namespace avhot

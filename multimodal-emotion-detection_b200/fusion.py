@@ -48,6 +48,7 @@ class HybridFusion(nn.Module):
         self.fusion_gate = nn.Sequential(nn.Linear(hidden_dim, gate_hidden), nn.ReLU(), nn.Dropout(dropout),
                                          nn.Linear(gate_hidden, 1))
         self.classifier = nn.Linear(hidden_dim, num_classes)
+        self.precision = _lib.PREC_FP32
         self._handle = Handle("avhot_fusion_destroy")
 
     def _params(self):
@@ -115,7 +116,8 @@ class HybridFusion(nn.Module):
                 ws = _ws.get(lib.avhot_fusion_workspace_bytes(h, B, passes), dev)
                 _lib.check(lib.avhot_fusion_forward(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits), _lib.ptr(fw),
                                                     _lib.ptr(attn), _lib.ptr(hatt), B, passes, float(p), seed, clip0,
-                                                    t0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                                                    t0, self.precision, _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream_ptr(dev)),
                            "HybridFusion.forward")
         return logits, fw, attn, hatt
 
@@ -191,7 +193,8 @@ class ConcatHead(nn.Sequential):
             with torch.cuda.device(dev):
                 h = self._get_handle(dev)
                 _lib.check(_lib.load().avhot_fusion_forward(h, arr, rpc, None, _lib.ptr(logits), None, None, None,
-                                                            B, passes, 0.0, 0, 0, 0, None, 0, _lib.stream_ptr(dev)),
+                                                            B, passes, 0.0, 0, 0, 0, _lib.PREC_FP32, None, 0,
+                                                            _lib.stream_ptr(dev)),
                            "ConcatHead.forward")
         return logits
 

@@ -63,13 +63,15 @@ class AVHotPath(nn.Module):
     def set_precision(self, precision: str) -> "AVHotPath":
         """'fp32': every contraction in fp32 FMA (the 1e-4 parity path).  'tc': the large contractions (video
         Linear, LSTM input projections and recurrence) on the tcgen05 tensor cores (TF32 / fp16 operands, fp32
-        accumulate; tolerance stated in DESIGN.md); the fusion tail stays fp32."""
+        accumulate; tolerance stated in DESIGN.md), and so are the per-pass GEMMs of HybridFusion (fp16 operands)."""
         if precision not in ("fp32", "tc"):
             raise ValueError(f"Unknown precision: {precision}")
         self.precision = precision
         code = _lib.PREC_FP32 if precision == "fp32" else _lib.PREC_TC
         for enc in self.encoders.values():
             enc.precision = code
+        if self.head == "hybrid":
+            self.fusion_model.precision = code
         return self
 
     # ---- stages ----------------------------------------------------------------------------------------

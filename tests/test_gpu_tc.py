@@ -63,3 +63,34 @@ def test_full_path_tc(pkg, dev, world, golden):
     mean, unc, lab, _ = m.mc_forward(feats, mask, num_samples=8, seed=SEED, clip0=50)
     assert rel_err(mean_tc.cpu().numpy(), mean.cpu().numpy()) <= TC_REL_LOGITS
     assert rel_err(unc_tc.cpu().numpy(), unc.cpu().numpy()) <= 5e-2
+
+
+def test_hybrid_fusion_tc(pkg, dev, world, golden):
+    """HybridFusion alone on the tensor-core path (fp16 GEMM operands) vs the reference golden logits and vs the
+    fp32 kernels with dropout on, several 128-row tiles, partial last tile, every mask pattern."""
+    m = make_model(pkg, dev, world).set_precision("tc")
+    fm = m.fusion_model
+    feats = {"audio": torch.from_numpy(golden["z_audio"]).to(dev), "video": torch.from_numpy(golden["z_video"]).to(dev)}
+    masks = {"ones": np.ones((6, 2), np.float32),
+             "mixed": np.array([[1, 1], [1, 0], [0, 1], [0, 0], [1, 1], [0, 1]], np.float32)}
+    for name, mask in masks.items():
+        got = fm(feats, torch.from_numpy(mask).to(dev)).cpu().numpy()
+        err = rel_err(got, golden[f"logits_hybrid_{name}"])
+        print("fusion tc", name, "rel err", err)
+        assert err <= TC_REL_LOGITS
+    # rows = clips x passes, with dropout: 300 clips x 7 passes = 2100 rows = 16.4 tiles
+    rng = np.random.default_rng(11)
+    B, T = 300, 7
+    z_a = torch.from_numpy(rng.normal(size=(B, 128)).astype(np.float32) * 0.3).to(dev)
+    z_v = torch.from_numpy(rng.normal(size=(B * T, 128)).astype(np.float32) * 0.3).to(dev)
+    mask = torch.from_numpy((rng.random(size=(B, 2)) > 0.2).astype(np.float32)).to(dev)
+    pkg.MCDropoutUncertainty._set_dropout_train(fm)
+    p = fm._drop_p()
+    assert p == 0.3
+    tc_logits = fm.run([z_a, z_v], [1, T], mask, B, T, p, SEED, 1234, 5)[0]
+    fm.precision = pkg._lib.PREC_FP32
+    ref_logits = fm.run([z_a, z_v], [1, T], mask, B, T, p, SEED, 1234, 5)[0]
+    err = rel_err(tc_logits.cpu().numpy(), ref_logits.cpu().numpy())
+    print("fusion tc vs fp32 kernels (dropout, 2100 rows) rel err", err)
+    assert err <= TC_REL_LOGITS
+    assert torch.isfinite(tc_logits).all()
