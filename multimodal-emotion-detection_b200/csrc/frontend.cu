@@ -25,6 +25,7 @@ constexpr int FE_WARPS = 8;        // warps per CTA
 constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
 constexpr int ZPAD = 256 + 16;     // padded complex buffer (index i -> i + (i >> 4))
 constexpr int MEL_NNZ_MAX = 640;
+constexpr int DCT_LD = N_MELS + 4; // padded row length of the DCT table
 
 struct FrontendTables {            // device layout, all fp32 unless noted
   float window[N_FFT];
@@ -33,7 +34,7 @@ struct FrontendTables {            // device layout, all fp32 unless noted
   int mel_start[N_MELS];           // first bin of filter m
   int mel_len[N_MELS];
   int mel_off[N_MELS];
-  float dct_t[N_MELS * N_MFCC];    // dct_t[j * 40 + c] = C[c][j]
+  float dct_p[N_MFCC * DCT_LD];    // dct_p[c * 68 + j] = C[c][j]; padded rows: conflict-free 128-bit row reads
 };
 
 static FrontendTables g_host_tables;
@@ -92,7 +93,7 @@ static void build_tables() {
       double v = cos(PI * (j + 0.5) * c / N_MELS) * sqrt(2.0 / N_MELS);
       if (c == 0) v *= sqrt(0.5);
       g_host_dct[c * N_MELS + j] = (float)v;
-      t.dct_t[j * N_MFCC + c] = (float)v;
+      t.dct_p[c * DCT_LD + j] = (float)v;
     }
 }
 
@@ -155,7 +156,7 @@ struct FeSmem {
   float2 tw[N_FFT];
   float melw[MEL_NNZ_MAX];
   int mel_start[N_MELS], mel_len[N_MELS], mel_off[N_MELS];
-  float dct[N_MELS * N_MFCC];
+  float dct[N_MFCC * DCT_LD];
   float2 z[FE_WARPS][ZPAD];
   float pow[FE_WARPS][N_BINS + 3];
   float lm[FE_WARPS][N_MELS];
@@ -164,7 +165,7 @@ struct FeSmem {
 
 __global__ void __launch_bounds__(FE_WARPS * 32)
 frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n_samples, int n_frames,
-                const FrontendTables* __restrict__ tab) {
+                int tiles_per_cta, const FrontendTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char fe_smem_raw[];
   FeSmem& sm = *reinterpret_cast<FeSmem*>(fe_smem_raw);
   float* s_seg = sm.seg;
@@ -180,7 +181,6 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int clip = blockIdx.y;
-  const int t0 = blockIdx.x * FPB;
   const float* y = wave + (size_t)clip * n_samples;
 
   // tables -> smem
@@ -189,8 +189,12 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n
   for (int i = tid; i < N_MELS; i += blockDim.x) {
     s_mel_start[i] = tab->mel_start[i]; s_mel_len[i] = tab->mel_len[i]; s_mel_off[i] = tab->mel_off[i];
   }
-  for (int i = tid; i < N_MELS * N_MFCC; i += blockDim.x) s_dct[i] = tab->dct_t[i];
+  for (int i = tid; i < N_MFCC * DCT_LD; i += blockDim.x) s_dct[i] = tab->dct_p[i];
 
+  // the tables are loaded once; the CTA then walks its tiles of FPB frames
+  for (int tile = blockIdx.x * tiles_per_cta; tile < (blockIdx.x + 1) * tiles_per_cta; ++tile) {
+  const int t0 = tile * FPB;
+  if (t0 >= n_frames) break;
   // pre-emphasised, reflect-padded segment: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
   const int q0 = t0 * HOP;
   for (int i = tid; i < SEG; i += blockDim.x) {
@@ -293,18 +297,32 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n
       s_out[f][m] = lm;
     }
     __syncwarp();
-    // ---- DCT-II (orthonormal), first 40 coefficients
+    // ---- DCT-II (orthonormal), first 40 coefficients: lane c does coefficient c over all 64 bands; the last 8
+    //      coefficients are split four ways over the bands (lane -> coefficient 32 + (lane & 7), bands
+    //      16 (lane >> 3) ..) and combined with two shuffles.  All operands are 128-bit shared loads.
     {
-      float acc0 = 0.f, acc1 = 0.f;
-      const int c1 = lane + 32 < N_MFCC ? lane + 32 : lane;
-#pragma unroll 8
-      for (int j = 0; j < N_MELS; ++j) {
-        const float l = s_lm[warp][j];
-        acc0 = fmaf(l, s_dct[j * N_MFCC + lane], acc0);
-        acc1 = fmaf(l, s_dct[j * N_MFCC + c1], acc1);
+      const float4* lm4 = reinterpret_cast<const float4*>(&s_lm[warp][0]);
+      const float4* d4 = reinterpret_cast<const float4*>(s_dct + lane * DCT_LD);
+      float acc0 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < N_MELS / 4; ++j4) {
+        const float4 l = lm4[j4], d = d4[j4];
+        acc0 = fmaf(l.x, d.x, acc0); acc0 = fmaf(l.y, d.y, acc0);
+        acc0 = fmaf(l.z, d.z, acc0); acc0 = fmaf(l.w, d.w, acc0);
       }
       s_out[f][N_MELS + lane] = acc0;
-      if (lane + 32 < N_MFCC) s_out[f][N_MELS + 32 + lane] = acc1;
+      const int part = lane >> 3;
+      const float4* e4 = reinterpret_cast<const float4*>(s_dct + (32 + (lane & 7)) * DCT_LD + part * 16);
+      float acc1 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 l = lm4[part * 4 + j4], d = e4[j4];
+        acc1 = fmaf(l.x, d.x, acc1); acc1 = fmaf(l.y, d.y, acc1);
+        acc1 = fmaf(l.z, d.z, acc1); acc1 = fmaf(l.w, d.w, acc1);
+      }
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
+      if (lane < 8) s_out[f][N_MELS + 32 + lane] = acc1;
     }
     __syncwarp();
   }
@@ -314,6 +332,8 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n
   float4* dst = reinterpret_cast<float4*>(feats + ((size_t)clip * n_frames + t0) * N_FEATS);
   const float4* srcv = reinterpret_cast<const float4*>(&s_out[0][0]);
   for (int i = tid; i < rows * N_FEATS / 4; i += blockDim.x) dst[i] = srcv[i];
+  __syncthreads();   // s_seg / s_out are rewritten by the next tile
+  }
 }
 
 }  // namespace avhot
@@ -331,13 +351,16 @@ extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samp
   int rc = get_tables(&tab);
   if (rc != AVHOT_OK) return rc;
   const int n_frames = 1 + n_samples / HOP;
-  dim3 grid(ceil_div(n_frames, FPB), B);
+  // many clips: one CTA per clip walks all its tiles (tables staged once per clip); few clips: one tile per CTA
+  const int n_tiles = ceil_div(n_frames, FPB);
+  const int tiles_per_cta = (long long)B * 1 >= 2LL * num_sms() ? n_tiles : 1;
+  dim3 grid(ceil_div(n_tiles, tiles_per_cta), B);
   // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
   AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FeSmem)));
   ProfScope prof("frontend", as_stream(stream));
   frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), as_stream(stream)>>>(wave, feats, n_samples,
-                                                                              n_frames, tab);
+                                                                              n_frames, tiles_per_cta, tab);
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }

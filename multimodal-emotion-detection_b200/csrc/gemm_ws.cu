@@ -1,5 +1,6 @@
 // Weight-stationary tcgen05 GEMM for the LSTM input projections (AVHOT_PREC_TC path):
-//     C[M, N] fp32 = A[M, K] (fp16) * W[N, K]^T (fp16) + bias[N],   M = B*T ~ 10^6 rows, N = 1024, K <= 320.
+//     C[M, N] fp32 = A[M, K] (fp16) * W[N, K]^T (fp16),   M = B*T ~ 10^6 rows, N = 1024, K <= 320
+// (no bias: the recurrent kernel that consumes C adds it).
 // The op is bound by writing C (4 KB per row against <= 640 B of A), so the design minimises everything else:
 // a persistent CTA owns one 128-column block of W for its whole life (<= 80 KB of fp16 in shared memory, loaded
 // once by TMA) and walks down M; A tiles (128 rows x 64 k, 128-byte swizzle) stream through an 8-stage TMA ring;
@@ -8,7 +9,7 @@
 // from HBM once and served to the other seven from L2.
 //   warp 0     TMA producer (W block once, then the A ring)
 //   warp 1     TMEM allocation + one lane issuing tcgen05.mma kind::f16 (M 128, N 128, K 16)
-//   warps 2-9  two epilogue warpgroups (even / odd tiles): tcgen05.ld (thread = row), + bias, 256-bit stores
+//   warps 2-9  two epilogue warpgroups (even / odd tiles): tcgen05.ld (thread = row) -> 256-bit global stores
 // Layer 0's A is the fp16 3-way split [hi | lo | hi] of the features against W = [hi | hi | lo] (see lstm.cu), which
 // makes this single fp16 pass fp32-class; layer 1's A is the fp16 hidden sequence written by the recurrent kernel.
 #include <cuda_fp16.h>
@@ -30,7 +31,7 @@ struct GemmWsSmem {
 
 __global__ void __launch_bounds__(WTHREADS, 1)
 gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int nkb, int n_blocks,
+                   float* __restrict__ C, int ldc, int M, int nkb, int n_blocks,
                    int groups) {
   extern __shared__ unsigned char gemm_ws_smem_raw[];
   GemmWsSmem& sm = *reinterpret_cast<GemmWsSmem*>((reinterpret_cast<uintptr_t>(gemm_ws_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -99,31 +100,32 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     const int wg = (warp - 2) >> 2, quarter = warp & 3;
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (bias) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = __ldg(bias + n0 + lane + 32 * j);   // bias[n0 + c] lives in lane c % 32
-    }
     for (int i = wg; i < my_tiles; i += 2) {
       const int b = i % WACC;
       const int row = (grp + i * groups) * WBM + quarter * 32 + lane;
       mbar_wait(&sm.acc_full[b], (uint32_t)(i / WACC) & 1);
       tc_fence_after();
       float* crow = C + (size_t)row * ldc + n0;
+      // pure TMEM -> global copy: the epilogue is the bottleneck of this output-bound GEMM, so it carries no
+      // arithmetic at all (the LSTM bias is added by the consumer, lstm_tc.cu)
 #pragma unroll
-      for (int c = 0; c < WBN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tlane + (uint32_t)(b * WBN + c), r);
+      for (int c = 0; c < WBN; c += 64) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tlane + (uint32_t)(b * WBN + c), r0);
+        tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bv[c / 32], j);
         if (row < M) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
-            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c + j), "f"(v[j]),
-                         "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]), "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]),
-                         "f"(v[j + 7])
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c + j), "r"(r0[j]),
+                         "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]), "r"(r0[j + 4]), "r"(r0[j + 5]), "r"(r0[j + 6]),
+                         "r"(r0[j + 7])
+                         : "memory");
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c + 32 + j), "r"(r1[j]),
+                         "r"(r1[j + 1]), "r"(r1[j + 2]), "r"(r1[j + 3]), "r"(r1[j + 4]), "r"(r1[j + 5]), "r"(r1[j + 6]),
+                         "r"(r1[j + 7])
                          : "memory");
         }
       }
@@ -139,8 +141,8 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }  // namespace tc
 
 // a, w fp16 row-major (K contiguous); N % 128 == 0; K <= 320; c fp32 with 32-byte aligned rows
-int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, const float* bias, float* c, int ldc, int M, int N,
-                int K, cudaStream_t s, const char* prof_name) {
+int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, float* c, int ldc, int M, int N, int K,
+                cudaStream_t s, const char* prof_name) {
   using namespace tc;
   AVHOT_REQUIRE(a && w && c && M >= 0 && N > 0 && K > 0, AVHOT_ERR_INVALID, "gemm_ws: bad arguments");
   AVHOT_REQUIRE(N % WBN == 0 && K <= 64 * WKB_MAX && (lda & 7) == 0 && (ldw & 7) == 0 && (ldc & 7) == 0 &&
@@ -161,7 +163,7 @@ int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, const float* bia
   const int smem = (int)sizeof(GemmWsSmem) + 1024;
   AVHOT_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ProfScope prof(prof_name, s);
-  gemm_f16_ws_kernel<<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, bias, c, ldc, M, nkb, n_blocks, groups);
+  gemm_f16_ws_kernel<<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, c, ldc, M, nkb, n_blocks, groups);
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }

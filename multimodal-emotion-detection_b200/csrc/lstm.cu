@@ -268,13 +268,13 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
           split3_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x_split, (long long)B * T, in, 0);
           AVHOT_LAUNCH_CHECK();
         }
-        rc = gemm_f16_ws(x_split, 3 * in, h->w_ih_f16[0], 3 * in, h->bias[l], xp, 4 * H, B * T, 4 * H, 3 * in, s,
+        rc = gemm_f16_ws(x_split, 3 * in, h->w_ih_f16[0], 3 * in, xp, 4 * H, B * T, 4 * H, 3 * in, s,
                          "lstm_input_gemm_tc");
       } else {
-        rc = gemm_f16_ws(h_seq, H, h->w_ih_f16[l], H, h->bias[l], xp, 4 * H, B * T, 4 * H, H, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(h_seq, H, h->w_ih_f16[l], H, xp, 4 * H, B * T, 4 * H, H, s, "lstm_input_gemm_tc");
       }
       if (rc == AVHOT_OK)
-        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, last ? nullptr : (void*)h_seq, hl_out, lengths, B, T, s);
+        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, h->bias[l], last ? nullptr : (void*)h_seq, hl_out, lengths, B, T, s);
       if (rc != AVHOT_OK) return rc;
       continue;
     }
