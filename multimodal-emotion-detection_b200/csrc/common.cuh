@@ -70,9 +70,9 @@ int gemm_tf32_tc(const float* a, int lda, const float* w, int ldw, const float* 
 // lstm_tc.cu: W_hh (4H, H) fp32 -> fp16, rows regrouped per 32-unit chunk; and the tcgen05 recurrence of one layer.
 int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s);
 // h_seq_f16: (B, T, H) fp16 hidden sequence (input of the next layer's projection) or NULL
-// xp: (B, T, 4H) input projections WITHOUT bias; bias: (4H) = b_ih + b_hh
-int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, const float* bias, void* h_seq_f16,
-                       float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s);
+// xp: input projections incl. bias, time-major tile-transposed (gemm_ws.cu); h_seq_f16: (T, Bp, h_pitch) fp16 or NULL
+int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, void* h_seq_f16, int h_pitch, float* h_last,
+                       const int32_t* lengths, int B, int T, cudaStream_t s);
 // gemm_ws.cu: weight-stationary tcgen05 GEMM, fp16 operands, fp32 output (LSTM input projections)
 int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, float* c, int ldc, int M, int N, int K,
                 cudaStream_t s, const char* prof_name = "gemm_f16_ws");

@@ -1,6 +1,7 @@
 // Weight-stationary tcgen05 GEMM for the LSTM input projections (AVHOT_PREC_TC path):
-//     C[M, N] fp32 = A[M, K] (fp16) * W[N, K]^T (fp16),   M = B*T ~ 10^6 rows, N = 1024, K <= 320
-// (no bias: the recurrent kernel that consumes C adds it).
+//     C[M, N] fp32 = A[M, K] (fp16) * W[N, K]^T (fp16),   M = B*T ~ 10^6 rows, N = 1024, K <= 320.
+// The bias rides in the GEMM itself: A carries two columns of ones against (bias_hi, bias_lo) columns of W, so the
+// epilogue - the bottleneck of this output-bound op - is a pure copy.
 // The op is bound by writing C (4 KB per row against <= 640 B of A), so the design minimises everything else:
 // a persistent CTA owns one 128-column block of W for its whole life (<= 80 KB of fp16 in shared memory, loaded
 // once by TMA) and walks down M; A tiles (128 rows x 64 k, 128-byte swizzle) stream through an 8-stage TMA ring;
@@ -105,29 +106,21 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int row = (grp + i * groups) * WBM + quarter * 32 + lane;
       mbar_wait(&sm.acc_full[b], (uint32_t)(i / WACC) & 1);
       tc_fence_after();
-      float* crow = C + (size_t)row * ldc + n0;
-      // pure TMEM -> global copy: the epilogue is the bottleneck of this output-bound GEMM, so it carries no
-      // arithmetic at all (the LSTM bias is added by the consumer, lstm_tc.cu)
+      // Output layout [M / 128][N][128] ("tile-transposed"): element (row, col) of M-tile mt lives at
+      // ((mt * N + col) * 128 + row % 128), so for every column the 32 lanes of a warp write 128 contiguous bytes
+      // (1 wavefront per store instead of 32 for row-major rows that are 4 KB apart), and the consumer
+      // (lstm_tc.cu, thread = row) reads it back the same way.  Pure TMEM -> global copy, no arithmetic.
+      float* cbase = C + ((size_t)(row / WBM) * ldc + n0) * WBM + (quarter * 32 + lane);
 #pragma unroll
       for (int c = 0; c < WBN; c += 64) {
         uint32_t r0[32], r1[32];
         tmem_ld32(tlane + (uint32_t)(b * WBN + c), r0);
         tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
         tmem_ld_wait();
-        if (row < M) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c + j), "r"(r0[j]),
-                         "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]), "r"(r0[j + 4]), "r"(r0[j + 5]), "r"(r0[j + 6]),
-                         "r"(r0[j + 7])
-                         : "memory");
+        for (int j = 0; j < 32; ++j) cbase[(size_t)(c + j) * WBM] = __uint_as_float(r0[j]);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c + 32 + j), "r"(r1[j]),
-                         "r"(r1[j + 1]), "r"(r1[j + 2]), "r"(r1[j + 3]), "r"(r1[j + 4]), "r"(r1[j + 5]), "r"(r1[j + 6]),
-                         "r"(r1[j + 7])
-                         : "memory");
-        }
+        for (int j = 0; j < 32; ++j) cbase[(size_t)(c + 32 + j) * WBM] = __uint_as_float(r1[j]);
       }
       tc_fence_before();
       mbar_arrive(&sm.acc_empty[b]);
@@ -140,14 +133,15 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 }  // namespace tc
 
-// a, w fp16 row-major (K contiguous); N % 128 == 0; K <= 320; c fp32 with 32-byte aligned rows
+// a, w fp16 row-major (K contiguous); M % 128 == 0 (caller pads); N % 128 == 0; K <= 320;
+// c fp32 in the tile-transposed layout [M / 128][N = ldc][128]
 int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, float* c, int ldc, int M, int N, int K,
                 cudaStream_t s, const char* prof_name) {
   using namespace tc;
   AVHOT_REQUIRE(a && w && c && M >= 0 && N > 0 && K > 0, AVHOT_ERR_INVALID, "gemm_ws: bad arguments");
-  AVHOT_REQUIRE(N % WBN == 0 && K <= 64 * WKB_MAX && (lda & 7) == 0 && (ldw & 7) == 0 && (ldc & 7) == 0 &&
-                    (reinterpret_cast<uintptr_t>(c) & 31) == 0,
-                AVHOT_ERR_UNSUPPORTED, "gemm_ws: needs N %% 128 == 0, K <= 320, lda/ldw/ldc %% 8 == 0 (N=%d K=%d)", N, K);
+  AVHOT_REQUIRE(M % WBM == 0 && N % WBN == 0 && ldc == N && K <= 64 * WKB_MAX && (lda & 7) == 0 && (ldw & 7) == 0,
+                AVHOT_ERR_UNSUPPORTED, "gemm_ws: needs M, N %% 128 == 0, ldc == N, K <= 320, lda/ldw %% 8 == 0 "
+                "(M=%d N=%d K=%d)", M, N, K);
   if (M == 0) return AVHOT_OK;
   CUtensorMap tmA, tmW;
   int rc = make_tensor_map_2d(&tmA, a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda, WBM, 64);

@@ -116,23 +116,57 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // fp16 tensor-core GEMM over K' = 3K into A W^T - lo(A) lo(W)^T - O(2^-22), i.e. an fp32-class product: used for
 // layer 0's input projection, whose inputs (log-mel features in dB, |x| ~ 100) are far too large for a single
 // half-precision pass (measured 5.7e-3 error with one TF32 pass).  Requires |x| < 65504.
-__global__ void split3_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long rows, int K,
-                                  int weight_order) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * K) return;
-  const long long r = i / K;
-  const int k = (int)(i % K);
-  const float v = x[i];
-  const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
-  __half* o = out + r * 3 * K;
-  o[k] = hi;
-  o[K + k] = weight_order ? hi : lo;
-  o[2 * K + k] = weight_order ? lo : hi;
+// weights: W (N, K) fp32 -> out (N, ldo) fp16 = [W_hi | W_hi | W_lo | bias_hi, bias_lo | 0...]  (ldo >= 3K + 2)
+__global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                     __half* __restrict__ out, int N, int K, int ldo) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
+    float v = 0.f;
+    bool lo = false;
+    if (k < 2 * K) v = w[(size_t)n * K + (k % K)];
+    else if (k < 3 * K) { v = w[(size_t)n * K + (k - 2 * K)]; lo = true; }
+    else if (k == 3 * K) v = bias[n];
+    else if (k == 3 * K + 1) { v = bias[n]; lo = true; }
+    const __half hi = __float2half_rn(v);
+    out[(size_t)n * ldo + k] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+  }
 }
-__global__ void to_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2half_rn(x[i]);
+// weights of layers > 0: W (N, K) fp32 -> out (N, ldo) fp16 = [W | bias_hi, bias_lo | 0...]
+__global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                   __half* __restrict__ out, int N, int K, int ldo) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
+    float v = 0.f;
+    bool lo = false;
+    if (k < K) v = w[(size_t)n * K + k];
+    else if (k == K) v = bias[n];
+    else if (k == K + 1) { v = bias[n]; lo = true; }
+    const __half hi = __float2half_rn(v);
+    out[(size_t)n * ldo + k] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+  }
 }
+// activations: x (B, T, K) batch-major -> out (T, Bp, ldo) time-major [hi | lo | hi | 1, 1 | 0...]; the rows of the
+// padding clips are zero
+__global__ void split3_f16_tm_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int Bp, int T,
+                                     int K, int ldo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * Bp * ldo) return;
+  const int k = (int)(i % ldo);
+  const long long tb = i / ldo;
+  const int b = (int)(tb % Bp), t = (int)(tb / Bp);
+  __half o = __float2half_rn(0.f);
+  if (b < B) {
+    if (k < 3 * K) {
+      const float v = x[((size_t)b * T + t) * K + (k % K)];
+      const __half hi = __float2half_rn(v);
+      o = (k >= K && k < 2 * K) ? __float2half_rn(v - __half2float(hi)) : hi;
+    } else if (k < 3 * K + 2) {
+      o = __float2half_rn(1.f);
+    }
+  }
+  out[i] = o;
+}
+static inline int pad8(int k) { return (k + 7) & ~7; }   // fp16 row pitch: multiple of 16 bytes (TMA)
 
 }  // namespace avhot
 
@@ -159,7 +193,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   }
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
-  total += align256(2 * 4 * H * 3 * d->input_dim) + (L - 1) * align256(2 * 4 * H * H);
+  total += align256(2 * 4 * H * pad8(3 * d->input_dim + 2)) + (L - 1) * align256(2 * 4 * H * pad8(H + 2));
   avhot_lstm* h = new avhot_lstm();
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
@@ -185,16 +219,17 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     if (rc == AVHOT_OK) rc = add_vec(d->bias_ih[l], d->bias_hh[l], h->bias[l], 4 * H, s);
     if (rc == AVHOT_OK) rc = lstm_pack_whh_fp16(d->weight_hh[l], h->w_hh_r16[l], s);
   }
-  for (int l = 0; l < L && rc == AVHOT_OK; ++l) {
+  for (int l = 0; l < L && rc == AVHOT_OK; ++l) {   // after the bias sums above (same stream)
     if (l == 0) {
-      h->w_ih_f16[0] = take(2 * 4 * H * 3 * d->input_dim);
-      const long long n = (long long)4 * H * d->input_dim;
-      split3_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->weight_ih[0], reinterpret_cast<__half*>(h->w_ih_f16[0]),
-                                                                   4 * H, d->input_dim, 1);
+      const int ldo = pad8(3 * d->input_dim + 2);
+      h->w_ih_f16[0] = take(2 * 4 * H * ldo);
+      pack_w_split3_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[0], h->bias[0], reinterpret_cast<__half*>(h->w_ih_f16[0]),
+                                                 4 * H, d->input_dim, ldo);
     } else {
-      h->w_ih_f16[l] = take(2 * 4 * H * H);
-      const long long n = (long long)4 * H * H;
-      to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d->weight_ih[l], reinterpret_cast<__half*>(h->w_ih_f16[l]), n);
+      const int ldo = pad8(H + 2);
+      h->w_ih_f16[l] = take(2 * 4 * H * ldo);
+      pack_w_bias_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[l], h->bias[l], reinterpret_cast<__half*>(h->w_ih_f16[l]),
+                                               4 * H, H, ldo);
     }
     if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
   }
@@ -224,12 +259,15 @@ extern "C" void avhot_lstm_destroy(avhot_lstm_t h) {
 }
 
 // workspace (fp32 path): xp (B*T*4H) + h_seq (B*T*H) + h_last (B*H)
+// workspace: xp (Bp*T*4H fp32) + h_seq (Bp*T*H fp32 / fp16) + h_last (B*H) [+ fp16 split of the input, TC path];
+// Bp = B rounded up to the 128-clip tile of the tensor-core kernels
 extern "C" size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int precision) {
   if (!h || B <= 0 || T <= 0) return 0;
   const size_t H = h->hidden_dim;
-  size_t n = align256(sizeof(float) * (size_t)B * T * 4 * H) + align256(sizeof(float) * (size_t)B * T * H) +
+  const size_t Bp = ((size_t)B + 127) / 128 * 128;
+  size_t n = align256(sizeof(float) * Bp * T * 4 * H) + align256(sizeof(float) * Bp * T * H) +
              align256(sizeof(float) * (size_t)B * H);
-  if (precision == AVHOT_PREC_TC) n += align256(2 * (size_t)B * T * 3 * h->input_dim);   // fp16 split of the input
+  if (precision == AVHOT_PREC_TC) n += align256(2 * Bp * T * (size_t)pad8(3 * h->input_dim + 2));   // fp16 split of the input
   return n;
 }
 
@@ -242,12 +280,13 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
   const size_t need = avhot_lstm_workspace_bytes(h, B, T, precision);
   AVHOT_REQUIRE(workspace && workspace_bytes >= need, AVHOT_ERR_WORKSPACE,
                 "lstm_forward: workspace %zu < %zu bytes", workspace_bytes, need);
-  AVHOT_REQUIRE((size_t)B * T <= 0x7fffffffu / 8, AVHOT_ERR_INVALID, "lstm_forward: B*T too large for one call");
+  AVHOT_REQUIRE(((size_t)B + 127) * T <= 0x7fffffffu / 8, AVHOT_ERR_INVALID, "lstm_forward: B*T too large for one call");
   const int H = h->hidden_dim;
   cudaStream_t s = as_stream(stream);
   char* p = reinterpret_cast<char*>(workspace);
-  float* xp = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * T * 4 * H);
-  float* h_seq = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * T * H);
+  const size_t Bp = ((size_t)B + 127) / 128 * 128;
+  float* xp = reinterpret_cast<float*>(p); p += align256(sizeof(float) * Bp * T * 4 * H);
+  float* h_seq = reinterpret_cast<float*>(p); p += align256(sizeof(float) * Bp * T * H);
   float* h_last = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * H);
   __half* x_split = reinterpret_cast<__half*>(p);   // TC path only
   const bool small = ceil_div(B, 32) * 2 < num_sms();   // few clips: smaller tiles, more CTAs
@@ -260,21 +299,23 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
     if (precision == AVHOT_PREC_TC) {
       // TC path: h_seq holds the fp16 hidden sequence (it is only ever the next layer's GEMM operand)
       int rc;
-      AVHOT_REQUIRE(3 * in <= 320 || l > 0, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d > 106", in);
+      AVHOT_REQUIRE(3 * in + 2 <= 320 || l > 0, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d > 104", in);
+      const int Mp = (int)Bp * T;                      // time-major rows t * Bp + b
+      const int hp = pad8(H + 2);                      // fp16 pitch of h_seq: H columns + (1, 1) for the bias columns
       if (l == 0) {
-        const long long n = (long long)B * T * in;
+        const int ldx = pad8(3 * in + 2);
+        const long long n = (long long)Mp * ldx;
         {
           ProfScope prof("lstm_split3", s);
-          split3_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x_split, (long long)B * T, in, 0);
+          split3_f16_tm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x_split, B, (int)Bp, T, in, ldx);
           AVHOT_LAUNCH_CHECK();
         }
-        rc = gemm_f16_ws(x_split, 3 * in, h->w_ih_f16[0], 3 * in, xp, 4 * H, B * T, 4 * H, 3 * in, s,
-                         "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, xp, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
       } else {
-        rc = gemm_f16_ws(h_seq, H, h->w_ih_f16[l], H, xp, 4 * H, B * T, 4 * H, H, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, xp, 4 * H, Mp, 4 * H, H + 2, s, "lstm_input_gemm_tc");
       }
       if (rc == AVHOT_OK)
-        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, h->bias[l], last ? nullptr : (void*)h_seq, hl_out, lengths, B, T, s);
+        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);
       if (rc != AVHOT_OK) return rc;
       continue;
     }

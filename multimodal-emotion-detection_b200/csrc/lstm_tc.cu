@@ -4,7 +4,7 @@
 // 128 clips for the whole sequence and every step computes
 //     gates[128 clips, 1024] = h_{t-1}[128, 256] (fp16, shared memory) x W_hh^T (fp16, streamed by TMA) + xp_t
 // in 8 chunks of 32 hidden units (N = 4 gates x 32 = 128 accumulator columns, double-buffered in TMEM):
-//   warp 0     TMA producer: W_hh tiles (128 gate rows x 64 k, 128-byte swizzle) through a 5-stage ring; the
+//   warp 0     TMA producer: W_hh tiles (128 gate rows x 64 k, 128-byte swizzle) through a 6-stage ring; the
 //              1024 x 256 weight matrix is re-read from L2 every step (it never fits next to the state);
 //   warp 1     one lane issues tcgen05.mma (M 128 clips, N 128, K 16) x 16 per chunk; A is the fp16 hidden
 //              state the epilogue wrote, ping-ponged between steps;
@@ -24,12 +24,11 @@
 namespace avhot {
 namespace tc {
 
-constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 5, RTHREADS = 320;
+constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 320;
 
 struct RecSmem {
   __half hA[2][RKB][RB * 64];   // hidden state, A operand: [step parity][k-block][128 rows x 128 B, swizzled]
   __half wB[RST][RN * 64];      // W_hh tile ring, B operand
-  float bias[4 * RH];           // b_ih + b_hh (the input-projection GEMM carries no bias)
   uint64_t full[RST], empty[RST], acc_full[2], acc_empty[2], h_ready[RKB];
   uint32_t tmem_base;
 };
@@ -61,6 +60,11 @@ __device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -84,8 +88,8 @@ template <int ACT> __device__ __forceinline__ float act_tanh(float x) {
 
 template <int ACT>
 __global__ void __launch_bounds__(RTHREADS, 1)
-lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp,
-                   const float* __restrict__ bias, __half* __restrict__ h_seq,
+lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp, __half* __restrict__ h_seq,
+                   int h_pitch,
                    float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T) {
   extern __shared__ unsigned char rec_smem_raw[];
   RecSmem& sm = *reinterpret_cast<RecSmem*>((reinterpret_cast<uintptr_t>(rec_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -96,7 +100,6 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     uint4* z = reinterpret_cast<uint4*>(&sm.hA[0][0][0]);
     for (int i = threadIdx.x; i < (int)(sizeof(sm.hA[0]) / 16); i += RTHREADS) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
-    for (int i = threadIdx.x; i < 4 * RH; i += RTHREADS) sm.bias[i] = bias[i];
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
@@ -174,17 +177,23 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       }
       tmem_st_wait();
     }
-    const float* xrow = xp + (size_t)(live ? clip : 0) * T * (4 * RH);
-    __half* hrow = h_seq ? h_seq + (size_t)(live ? clip : 0) * T * RH : nullptr;
+    // xp is time-major and tile-transposed (gemm_ws.cu): [t][clip tile][4H columns][128 clips]; h_seq is the
+    // time-major padded fp16 sequence (T, Bp, H) that is the next layer's GEMM operand (rows of dead clips are
+    // written too, so the operand is fully initialised)
+    const size_t n_ct = gridDim.x;
+    const float* xcol = xp + (size_t)blockIdx.x * (4 * RH) * RB + r;
+    __half* hrow = h_seq ? h_seq + ((size_t)blockIdx.x * RB + r) * h_pitch : nullptr;
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
     uint32_t use = 0;
 
     // xp of item (t, c, q): 4 gates x 8 units, one 256-bit load per gate
     auto load_x = [&](int t, int c, int q, float (&xg)[4][8]) {
-      if (live && t < T) {
-        const float* src = xrow + (size_t)t * (4 * RH) + c * RCH + q * 8;
+      if (t < T) {
+        const float* src = xcol + ((size_t)t * n_ct * (4 * RH) + c * RCH + q * 8) * RB;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ldg256(src + g * RH, xg[g]);
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xg[g][j] = ldg_stream(src + (size_t)(g * RH + j) * RB);
       } else {
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -200,20 +209,13 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     };
     auto item = [&](int t, int c, int q, const float (&xg)[4][8], uint32_t (&acc)[4][8], uint32_t (&cs)[8]) {
       const int u0 = c * RCH + q * 8;
-      float hn[8], bg[4][8];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&sm.bias[g * RH + u0]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&sm.bias[g * RH + u0 + 4]);
-        bg[g][0] = b0.x; bg[g][1] = b0.y; bg[g][2] = b0.z; bg[g][3] = b0.w;
-        bg[g][4] = b1.x; bg[g][5] = b1.y; bg[g][6] = b1.z; bg[g][7] = b1.w;
-      }
+      float hn[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float ig = act_sigmoid<ACT>(__uint_as_float(acc[0][j]) + (xg[0][j] + bg[0][j]));
-        const float fg = act_sigmoid<ACT>(__uint_as_float(acc[1][j]) + (xg[1][j] + bg[1][j]));
-        const float gg = act_tanh<ACT>(__uint_as_float(acc[2][j]) + (xg[2][j] + bg[2][j]));
-        const float og = act_sigmoid<ACT>(__uint_as_float(acc[3][j]) + (xg[3][j] + bg[3][j]));
+        const float ig = act_sigmoid<ACT>(__uint_as_float(acc[0][j]) + xg[0][j]);
+        const float fg = act_sigmoid<ACT>(__uint_as_float(acc[1][j]) + xg[1][j]);
+        const float gg = act_tanh<ACT>(__uint_as_float(acc[2][j]) + xg[2][j]);
+        const float og = act_sigmoid<ACT>(__uint_as_float(acc[3][j]) + xg[3][j]);
         const float cn = fmaf(fg, __uint_as_float(cs[j]), ig * gg);
         cs[j] = __float_as_uint(cn);
         hn[j] = og * act_tanh<ACT>(cn);
@@ -231,10 +233,13 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
                               (size_t)r * 128;
         *reinterpret_cast<uint4*>(tile + ((((u0 & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      if (live) {
-        if (hrow) *reinterpret_cast<uint4*>(hrow + (size_t)t * RH + u0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
+      if (hrow) {
+        __half* ht = hrow + (size_t)t * n_ct * RB * h_pitch;
+        *reinterpret_cast<uint4*>(ht + u0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        // columns H, H + 1 = 1.0: they multiply the (hi, lo) bias columns of the next layer's packed W_ih
+        if (u0 == 0 && h_pitch > RH) *reinterpret_cast<uint4*>(ht + RH) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
       }
+      if (live && h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
     };
 
     float xa[4][8], xb[4][8];
@@ -242,10 +247,6 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     load_x(0, wg, 1, xb);
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-      // pull this clip's xp row of step t + 2 (4 KB) into L2 ahead of the register prefetch
-      if (wg == 0 && live && t + 2 < T)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xrow + (size_t)(t + 2) * (4 * RH)), "r"(4 * RH * 4)
-                     : "memory");
 #pragma unroll 1
       for (int c = wg; c < RNC; c += 2) {
         // the item two ahead of (c, q): same chunk for q < 2, else the next chunk of this warpgroup
@@ -300,8 +301,8 @@ int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s) {
   return AVHOT_OK;
 }
 
-int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, const float* bias, void* h_seq_f16,
-                       float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
+int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, void* h_seq_f16, int h_pitch, float* h_last,
+                       const int32_t* lengths, int B, int T, cudaStream_t s) {
   __half* h_seq = reinterpret_cast<__half*>(h_seq_f16);
   using namespace tc;
   CUtensorMap tmW;
@@ -314,10 +315,10 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, const float
   ProfScope prof("lstm_recurrence_tc", s);
   if (act == 1) {
     AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    lstm_rec_tc_kernel<1><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, bias, h_seq, h_last, lengths, B, T);
+    lstm_rec_tc_kernel<1><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_pitch, h_last, lengths, B, T);
   } else {
     AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    lstm_rec_tc_kernel<0><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, bias, h_seq, h_last, lengths, B, T);
+    lstm_rec_tc_kernel<0><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_pitch, h_last, lengths, B, T);
   }
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
