@@ -146,25 +146,43 @@ __global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __r
   }
 }
 // activations: x (B, T, K) batch-major -> out (T, Bp, ldo) time-major [hi | lo | hi | 1, 1 | 0...]; the rows of the
-// padding clips are zero
-__global__ void split3_f16_tm_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int Bp, int T,
-                                     int K, int ldo) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)T * Bp * ldo) return;
-  const int k = (int)(i % ldo);
-  const long long tb = i / ldo;
-  const int b = (int)(tb % Bp), t = (int)(tb / Bp);
-  __half o = __float2half_rn(0.f);
-  if (b < B) {
-    if (k < 3 * K) {
-      const float v = x[((size_t)b * T + t) * K + (k % K)];
-      const __half hi = __float2half_rn(v);
-      o = (k >= K && k < 2 * K) ? __float2half_rn(v - __half2float(hi)) : hi;
-    } else if (k < 3 * K + 2) {
-      o = __float2half_rn(1.f);
-    }
+// padding clips are zero.  A (16 clips x 4 steps) tile goes through shared memory so that both sides move in long
+// contiguous runs (reads: 4 steps of one clip; writes: 16 clips of one step = 16 * ldo halves).
+constexpr int SPL_CB = 16, SPL_TB = 4;
+__global__ void __launch_bounds__(256)
+split3_f16_tm_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int Bp, int T, int K, int ldo) {
+  extern __shared__ float spl_tile[];          // [SPL_CB][SPL_TB * K]
+  const int b0 = blockIdx.x * SPL_CB, t0 = blockIdx.y * SPL_TB;
+  const int nt = min(SPL_TB, T - t0);
+  const int run = nt * K;                      // contiguous floats per clip
+  for (int idx = threadIdx.x; idx < SPL_CB * run; idx += blockDim.x) {
+    const int i = idx / run, j = idx % run;
+    spl_tile[i * (SPL_TB * K) + j] = b0 + i < B ? __ldg(x + ((size_t)(b0 + i) * T + t0) * K + j) : 0.f;
   }
-  out[i] = o;
+  __syncthreads();
+  const int half2_per_row = ldo / 2;
+  for (int idx = threadIdx.x; idx < nt * SPL_CB * half2_per_row; idx += blockDim.x) {
+    const int k2 = idx % half2_per_row;
+    const int i = (idx / half2_per_row) % SPL_CB, tt = idx / (half2_per_row * SPL_CB);
+    __half v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = 2 * k2 + u;
+      __half o = __float2half_rn(0.f);
+      if (b0 + i < B) {
+        if (k < 3 * K) {
+          const float f = spl_tile[i * (SPL_TB * K) + tt * K + (k % K)];
+          const __half hi = __float2half_rn(f);
+          o = (k >= K && k < 2 * K) ? __float2half_rn(f - __half2float(hi)) : hi;
+        } else if (k < 3 * K + 2) {
+          o = __float2half_rn(1.f);
+        }
+      }
+      v[u] = o;
+    }
+    if (b0 + i < Bp)
+      reinterpret_cast<__half2*>(out + ((size_t)(t0 + tt) * Bp + b0 + i) * ldo)[k2] = __halves2half2(v[0], v[1]);
+  }
 }
 static inline int pad8(int k) { return (k + 7) & ~7; }   // fp16 row pitch: multiple of 16 bytes (TMA)
 
@@ -307,7 +325,11 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
         const long long n = (long long)Mp * ldx;
         {
           ProfScope prof("lstm_split3", s);
-          split3_f16_tm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x_split, B, (int)Bp, T, in, ldx);
+          (void)n;
+          const size_t smem = sizeof(float) * SPL_CB * SPL_TB * in;
+          AVHOT_REQUIRE(smem <= 48 * 1024, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d too large", in);
+          split3_f16_tm_kernel<<<dim3((unsigned)(Bp / SPL_CB), (unsigned)ceil_div(T, SPL_TB)), 256, smem, s>>>(
+              x, x_split, B, (int)Bp, T, in, ldx);
           AVHOT_LAUNCH_CHECK();
         }
         rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, xp, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
