@@ -100,6 +100,12 @@ int avhot_condition_audio(const float* in, const int32_t* lengths, float* out, i
 /* wave (B, n_samples) -> feats (B, 1 + n_samples/160, 104) = [64 log-mel | 40 MFCC]. */
 int avhot_frontend(const float* wave, float* feats, int B, int n_samples,
                    avhot_stream_t stream);
+/* Fused variant for the tensor-core pipeline: besides (or instead of: feats may be NULL) the fp32 features it
+ * writes the LSTM's first GEMM operand directly - fp16, time-major rows (t, clip) with the batch padded to
+ * Bp = B rounded up to 128, pitch = avhot_lstm_split_pitch() halves per row:
+ * [hi(104) | lo(104) | hi(104) | 1, 1 | 0...], hi = fp16(x), lo = fp16(x - hi) - see avhot_lstm_forward_split. */
+int avhot_frontend_ex(const float* wave, float* feats, void* seq_split_f16, int B, int Bp, int pitch,
+                      int n_samples, avhot_stream_t stream);
 /* the fp32 tables the kernel uses, copied to HOST buffers (any may be NULL):
  * mel (64, 257), dct (40, 64), window (512). */
 int avhot_frontend_tables_host(float* mel_host, float* dct_host, float* window_host);
@@ -124,6 +130,12 @@ size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int precision);
 int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_t* lengths, float* out,
                        int B, int T, int precision, void* workspace, size_t workspace_bytes,
                        avhot_stream_t stream);
+
+/* Tensor-core path with the input already in the split layout avhot_frontend_ex writes ((T, Bp, pitch) fp16):
+ * same result as avhot_lstm_forward(..., AVHOT_PREC_TC, ...) on the fp32 features, minus one pass over them. */
+int avhot_lstm_split_pitch(avhot_lstm_t h);
+int avhot_lstm_forward_split(avhot_lstm_t h, const void* seq_split_f16, const int32_t* lengths, float* out,
+                             int B, int T, void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 
 /* ---- a4: src/encoders.py:196-327  FrameEncoder(temporal_pooling='attention') -------- */
 typedef struct avhot_frame* avhot_frame_t;

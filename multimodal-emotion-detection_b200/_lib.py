@@ -76,11 +76,14 @@ PROTOTYPES = {
     "avhot_synth_video": (_I, [_P, _P, _I, _I, _U64, _U64, _P]),
     "avhot_condition_audio": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "avhot_frontend": (_I, [_P, _P, _I, _I, _P]),
+    "avhot_frontend_ex": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "avhot_frontend_tables_host": (_I, [_P, _P, _P]),
     "avhot_lstm_create": (_I, [C.POINTER(LstmDesc), C.POINTER(_P), _P]),
     "avhot_lstm_destroy": (None, [_P]),
     "avhot_lstm_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "avhot_lstm_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
+    "avhot_lstm_split_pitch": (_I, [_P]),
+    "avhot_lstm_forward_split": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "avhot_frame_create": (_I, [C.POINTER(FrameDesc), C.POINTER(_P), _P]),
     "avhot_frame_destroy": (None, [_P]),
     "avhot_frame_workspace_bytes": (_SZ, [_P, _I, _I, _I]),

@@ -15,6 +15,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace avhot {
@@ -164,8 +166,8 @@ struct FeSmem {
 };
 
 __global__ void __launch_bounds__(FE_WARPS * 32)
-frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n_samples, int n_frames,
-                int tiles_per_cta, const FrontendTables* __restrict__ tab) {
+frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __half* __restrict__ xs, int Bp, int ldx,
+                int n_samples, int n_frames, int tiles_per_cta, const FrontendTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char fe_smem_raw[];
   FeSmem& sm = *reinterpret_cast<FeSmem*>(fe_smem_raw);
   float* s_seg = sm.seg;
@@ -329,9 +331,35 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n
   __syncthreads();
   // coalesced store of the CTA's output tile (rows are contiguous in feats)
   const int rows = min(FPB, n_frames - t0);
-  float4* dst = reinterpret_cast<float4*>(feats + ((size_t)clip * n_frames + t0) * N_FEATS);
-  const float4* srcv = reinterpret_cast<const float4*>(&s_out[0][0]);
-  for (int i = tid; i < rows * N_FEATS / 4; i += blockDim.x) dst[i] = srcv[i];
+  if (feats) {
+    float4* dst = reinterpret_cast<float4*>(feats + ((size_t)clip * n_frames + t0) * N_FEATS);
+    const float4* srcv = reinterpret_cast<const float4*>(&s_out[0][0]);
+    for (int i = tid; i < rows * N_FEATS / 4; i += blockDim.x) dst[i] = srcv[i];
+  }
+  if (xs) {
+    // fused operand preparation for the tensor-core LSTM (lstm.cu): time-major rows (t, clip) of
+    // [hi(104) | lo(104) | hi(104) | 1, 1 | 0...] in fp16, hi = fp16(x), lo = fp16(x - hi)
+    const int h2_per_row = ldx >> 1;
+    for (int i = tid; i < rows * h2_per_row; i += blockDim.x) {
+      const int f = i / h2_per_row, k2 = i - f * h2_per_row;
+      __half v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = 2 * k2 + u;
+        __half o = __float2half_rn(0.f);
+        if (k < 3 * N_FEATS) {
+          const int kk = k < N_FEATS ? k : (k < 2 * N_FEATS ? k - N_FEATS : k - 2 * N_FEATS);
+          const float x = s_out[f][kk];
+          const __half hi = __float2half_rn(x);
+          o = (k >= N_FEATS && k < 2 * N_FEATS) ? __float2half_rn(x - __half2float(hi)) : hi;
+        } else if (k < 3 * N_FEATS + 2) {
+          o = __float2half_rn(1.f);
+        }
+        v[u] = o;
+      }
+      reinterpret_cast<__half2*>(xs + ((size_t)(t0 + f) * Bp + clip) * ldx)[k2] = __halves2half2(v[0], v[1]);
+    }
+  }
   __syncthreads();   // s_seg / s_out are rewritten by the next tile
   }
 }
@@ -340,17 +368,24 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, int n
 
 using namespace avhot;
 
-extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samples,
-                              avhot_stream_t stream) {
-  AVHOT_REQUIRE(wave && feats && B >= 0, AVHOT_ERR_INVALID, "frontend: null pointer or B < 0");
+static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, int ldx, int B, int n_samples,
+                           avhot_stream_t stream) {
+  AVHOT_REQUIRE(wave && (feats || xs) && B >= 0, AVHOT_ERR_INVALID, "frontend: null pointer or B < 0");
   AVHOT_REQUIRE(n_samples > N_FFT / 2, AVHOT_ERR_INVALID,
                 "frontend: n_samples=%d must exceed the reflect pad (256)", n_samples);
   AVHOT_REQUIRE(B <= 65535, AVHOT_ERR_INVALID, "frontend: B > 65535 per call");
+  AVHOT_REQUIRE(!xs || (Bp >= B && ldx >= 3 * N_FEATS + 2 && (ldx & 7) == 0), AVHOT_ERR_INVALID,
+                "frontend: split operand needs Bp >= B and a pitch >= 314 that is a multiple of 8");
   if (B == 0) return AVHOT_OK;
   const FrontendTables* tab = nullptr;
   int rc = get_tables(&tab);
   if (rc != AVHOT_OK) return rc;
   const int n_frames = 1 + n_samples / HOP;
+  cudaStream_t s = as_stream(stream);
+  if (xs && Bp > B) {   // rows of the padding clips are zero: one strided memset over the (T, Bp - B) tail of every step
+    AVHOT_CUDA(cudaMemset2DAsync(reinterpret_cast<__half*>(xs) + (size_t)B * ldx, (size_t)Bp * ldx * sizeof(__half), 0,
+                                 (size_t)(Bp - B) * ldx * sizeof(__half), (size_t)n_frames, s));
+  }
   // many clips: one CTA per clip walks all its tiles (tables staged once per clip); few clips: one tile per CTA
   const int n_tiles = ceil_div(n_frames, FPB);
   const int tiles_per_cta = (long long)B * 1 >= 2LL * num_sms() ? n_tiles : 1;
@@ -358,11 +393,21 @@ extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samp
   // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
   AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FeSmem)));
-  ProfScope prof("frontend", as_stream(stream));
-  frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), as_stream(stream)>>>(wave, feats, n_samples,
-                                                                              n_frames, tiles_per_cta, tab);
+  ProfScope prof("frontend", s);
+  frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), s>>>(wave, feats, reinterpret_cast<__half*>(xs), Bp, ldx,
+                                                              n_samples, n_frames, tiles_per_cta, tab);
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
+}
+
+extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samples, avhot_stream_t stream) {
+  AVHOT_REQUIRE(feats, AVHOT_ERR_INVALID, "frontend: feats is NULL");
+  return frontend_launch(wave, feats, nullptr, 0, 0, B, n_samples, stream);
+}
+
+extern "C" int avhot_frontend_ex(const float* wave, float* feats, void* seq_split_f16, int B, int Bp, int pitch,
+                                 int n_samples, avhot_stream_t stream) {
+  return frontend_launch(wave, feats, seq_split_f16, Bp, pitch, B, n_samples, stream);
 }
 
 extern "C" int avhot_frontend_tables_host(float* mel_host, float* dct_host, float* window_host) {

@@ -289,9 +289,29 @@ extern "C" size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int p
   return n;
 }
 
+extern "C" int avhot_lstm_split_pitch(avhot_lstm_t h) { return h ? pad8(3 * h->input_dim + 2) : 0; }
+
+static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_split, const int32_t* lengths, float* out,
+                             int B, int T, int precision, void* workspace, size_t workspace_bytes,
+                             avhot_stream_t stream);
+
 extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_t* lengths, float* out, int B,
-                                  int T, int precision, void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
-  AVHOT_REQUIRE(h && seq && out && B >= 0 && T >= 1, AVHOT_ERR_INVALID, "lstm_forward: bad arguments");
+                                  int T, int precision, void* workspace, size_t workspace_bytes,
+                                  avhot_stream_t stream) {
+  return lstm_forward_impl(h, seq, nullptr, lengths, out, B, T, precision, workspace, workspace_bytes, stream);
+}
+
+extern "C" int avhot_lstm_forward_split(avhot_lstm_t h, const void* seq_split_f16, const int32_t* lengths, float* out,
+                                        int B, int T, void* workspace, size_t workspace_bytes,
+                                        avhot_stream_t stream) {
+  AVHOT_REQUIRE(seq_split_f16, AVHOT_ERR_INVALID, "lstm_forward_split: operand is NULL");
+  return lstm_forward_impl(h, nullptr, seq_split_f16, lengths, out, B, T, AVHOT_PREC_TC, workspace, workspace_bytes,
+                           stream);
+}
+
+static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_split, const int32_t* lengths, float* out,
+                             int B, int T, int precision, void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
+  AVHOT_REQUIRE(h && (seq || seq_split) && out && B >= 0 && T >= 1, AVHOT_ERR_INVALID, "lstm_forward: bad arguments");
   AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
                 "lstm_forward: precision %d not built", precision);
   if (B == 0) return AVHOT_OK;
@@ -320,7 +340,10 @@ extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_
       AVHOT_REQUIRE(3 * in + 2 <= 320 || l > 0, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d > 104", in);
       const int Mp = (int)Bp * T;                      // time-major rows t * Bp + b
       const int hp = pad8(H + 2);                      // fp16 pitch of h_seq: H columns + (1, 1) for the bias columns
-      if (l == 0) {
+      if (l == 0 && seq_split) {                      // operand already prepared by avhot_frontend_ex
+        const int ldx = pad8(3 * in + 2);
+        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, xp, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
+      } else if (l == 0) {
         const int ldx = pad8(3 * in + 2);
         const long long n = (long long)Mp * ldx;
         {

@@ -16,6 +16,7 @@ from . import _lib, _rng
 from ._handles import Handle, Workspace
 
 _ws = Workspace()
+_ws_split = Workspace()
 
 
 class SequenceEncoder(nn.Module):
@@ -94,6 +95,38 @@ class SequenceEncoder(nn.Module):
             _lib.check(lib.avhot_lstm_forward(h, _lib.ptr(x), _lib.ptr(lengths), _lib.ptr(out), B, T,
                                               self.precision, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
                        "SequenceEncoder.forward")
+        return out
+
+
+    @torch.no_grad()
+    def forward_from_waveform(self, wave: torch.Tensor) -> torch.Tensor:
+        """Tensor-core pipeline, front-end fused with the LSTM's operand preparation: (B, N) waveform -> log-mel/MFCC
+        front-end writing the fp16 split operand of the first input GEMM directly (avhot_frontend_ex) -> LSTM
+        (avhot_lstm_forward_split).  Same result as forward(logmel_mfcc(wave)) with precision 'tc'."""
+        from . import dataprocessing as dp
+        dev = _lib.require_cuda(wave)
+        _lib.check_device(dev)
+        if wave.dim() == 3 and wave.shape[-1] == 1:
+            wave = wave[..., 0]
+        if wave.dim() != 2 or self.input_dim != dp.N_FEATS:
+            raise ValueError("forward_from_waveform needs a (B, N) waveform and input_dim == 104")
+        wave = _lib.f32c(wave)
+        B, N = wave.shape
+        T = dp.n_frames(N)
+        out = torch.empty(B, self.output_dim, device=dev, dtype=torch.float32)
+        if B == 0:
+            return out
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._get_handle(dev)
+            Bp = (B + 127) // 128 * 128
+            pitch = lib.avhot_lstm_split_pitch(h)
+            xs = _ws_split.get(2 * T * Bp * pitch, dev)
+            _lib.check(lib.avhot_frontend_ex(_lib.ptr(wave), None, _lib.ptr(xs), B, Bp, pitch, N, _lib.stream_ptr(dev)),
+                       "logmel_mfcc (fused)")
+            ws = _ws.get(lib.avhot_lstm_workspace_bytes(h, B, T, _lib.PREC_TC), dev)
+            _lib.check(lib.avhot_lstm_forward_split(h, _lib.ptr(xs), None, _lib.ptr(out), B, T, _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream_ptr(dev)), "SequenceEncoder.forward (fused)")
         return out
 
 

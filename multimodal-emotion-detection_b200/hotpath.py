@@ -90,7 +90,12 @@ class AVHotPath(nn.Module):
         dev = _lib.require_cuda(audio, video)
         _lib.check_device(dev)
         B = audio.shape[0]
-        z_a = self.encoders["audio"](self.audio_features(audio))                          # (B, out), pass-invariant
+        aenc = self.encoders["audio"]
+        raw = not (audio.dim() == 3 and audio.shape[-1] == aenc.input_dim and aenc.input_dim != 1)
+        if raw and self.precision == "tc" and B <= 65535:
+            z_a = aenc.forward_from_waveform(audio)           # front-end fused with the LSTM operand preparation
+        else:
+            z_a = aenc(self.audio_features(audio))                                        # (B, out), pass-invariant
         venc = self.encoders["video"]
         hid = venc.hidden(video)                                                          # (B, F, H), pass-invariant
         p_enc = venc._drop_p() if stochastic else 0.0

@@ -94,3 +94,16 @@ def test_hybrid_fusion_tc(pkg, dev, world, golden):
     print("fusion tc vs fp32 kernels (dropout, 2100 rows) rel err", err)
     assert err <= TC_REL_LOGITS
     assert torch.isfinite(tc_logits).all()
+
+
+def test_fused_frontend_lstm_operand(pkg, dev, world):
+    """avhot_frontend_ex writes the LSTM's split GEMM operand directly; the result equals running the front-end and
+    the tensor-core LSTM separately (same fp32 features, same hi/lo split), for a batch that needs clip padding."""
+    m = make_model(pkg, dev, world).set_precision("tc")
+    enc = m.encoders["audio"]
+    wave = pkg.synth.synth_audio(37, 900, SEED, dev)
+    fused = enc.forward_from_waveform(wave)
+    separate = enc(pkg.logmel_mfcc(wave))
+    assert (fused == separate).all()
+    short = pkg.synth.synth_audio(3, 5, SEED, dev, n_samples=8000)      # 51 frames: partial last tile of 16
+    assert (enc.forward_from_waveform(short) == enc(pkg.logmel_mfcc(short))).all()
