@@ -26,16 +26,16 @@ constexpr int FPB = 16;            // frames per CTA
 constexpr int FE_WARPS = 8;        // warps per CTA
 constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
 constexpr int ZPAD = 256 + 16;     // padded complex buffer (index i -> i + (i >> 4))
-constexpr int MEL_NNZ_MAX = 640;
+constexpr int MEL_G4_MAX = 320;    // float4 groups of filter weights (each filter padded to aligned groups of 4 bins)
 constexpr int DCT_LD = N_MELS + 4; // padded row length of the DCT table
 
 struct FrontendTables {            // device layout, all fp32 unless noted
   float window[N_FFT];
   float2 tw[N_FFT];                // tw[k] = exp(-2 pi i k / 512)
-  float mel_w[MEL_NNZ_MAX];        // CSR values
-  int mel_start[N_MELS];           // first bin of filter m
-  int mel_len[N_MELS];
-  int mel_off[N_MELS];
+  float4 mel_w4[MEL_G4_MAX];       // filter weights in aligned groups of 4 bins (zeros outside the triangle)
+  int mel_g0[N_MELS];              // first 4-bin group of filter m
+  int mel_ng[N_MELS];              // number of groups
+  int mel_off[N_MELS];             // offset of the filter's first group in mel_w4
   float dct_p[N_MFCC * DCT_LD];    // dct_p[c * 68 + j] = C[c][j]; padded rows: conflict-free 128-bit row reads
 };
 
@@ -82,12 +82,19 @@ static void build_tables() {
         g_host_mel_dense[m * N_BINS + k] = (float)(w * enorm);
       }
     }
-    if (start < 0) start = 0;
-    t.mel_start[m] = start;
-    t.mel_len[m] = len;
+    if (start < 0) { start = 0; len = 1; }
+    const int g0 = start / 4, g1 = (start + len - 1) / 4;
+    t.mel_g0[m] = g0;
+    t.mel_ng[m] = g1 - g0 + 1;
     t.mel_off[m] = off;
-    for (int i = 0; i < len; ++i) t.mel_w[off + i] = g_host_mel_dense[m * N_BINS + start + i];
-    off += len;
+    for (int g = g0; g <= g1; ++g, ++off) {
+      float w[4];
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * g + e;
+        w[e] = k < N_BINS ? g_host_mel_dense[m * N_BINS + k] : 0.f;
+      }
+      if (off < MEL_G4_MAX) t.mel_w4[off] = make_float4(w[0], w[1], w[2], w[3]);
+    }
   }
   g_host_dct.assign(N_MFCC * N_MELS, 0.f);
   for (int c = 0; c < N_MFCC; ++c)
@@ -156,8 +163,8 @@ struct FeSmem {
   float seg[SEG];
   float win[N_FFT];
   float2 tw[N_FFT];
-  float melw[MEL_NNZ_MAX];
-  int mel_start[N_MELS], mel_len[N_MELS], mel_off[N_MELS];
+  float4 melw4[MEL_G4_MAX];
+  int mel_g0[N_MELS], mel_ng[N_MELS], mel_off[N_MELS];
   float dct[N_MFCC * DCT_LD];
   float2 z[FE_WARPS][ZPAD];
   float pow[FE_WARPS][N_BINS + 3];
@@ -165,7 +172,7 @@ struct FeSmem {
   float out[FPB][N_FEATS];
 };
 
-__global__ void __launch_bounds__(FE_WARPS * 32)
+__global__ void __launch_bounds__(FE_WARPS * 32, 3)
 frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __half* __restrict__ xs, int Bp, int ldx,
                 int n_samples, int n_frames, int tiles_per_cta, const FrontendTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char fe_smem_raw[];
@@ -173,8 +180,8 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   float* s_seg = sm.seg;
   float* s_win = sm.win;
   float2* s_tw = sm.tw;
-  float* s_melw = sm.melw;
-  int *s_mel_start = sm.mel_start, *s_mel_len = sm.mel_len, *s_mel_off = sm.mel_off;
+  float4* s_melw4 = sm.melw4;
+  int *s_mel_g0 = sm.mel_g0, *s_mel_ng = sm.mel_ng, *s_mel_off = sm.mel_off;
   float* s_dct = sm.dct;
   float2 (*s_z)[ZPAD] = sm.z;
   float (*s_pow)[N_BINS + 3] = sm.pow;
@@ -187,31 +194,44 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 
   // tables -> smem
   for (int i = tid; i < N_FFT; i += blockDim.x) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
-  for (int i = tid; i < MEL_NNZ_MAX; i += blockDim.x) s_melw[i] = tab->mel_w[i];
+  for (int i = tid; i < MEL_G4_MAX; i += blockDim.x) s_melw4[i] = tab->mel_w4[i];
+  if (lane < 3) sm.pow[warp][N_BINS + lane] = 0.f;    // bins 257..259 pad the last group of 4
   for (int i = tid; i < N_MELS; i += blockDim.x) {
-    s_mel_start[i] = tab->mel_start[i]; s_mel_len[i] = tab->mel_len[i]; s_mel_off[i] = tab->mel_off[i];
+    s_mel_g0[i] = tab->mel_g0[i]; s_mel_ng[i] = tab->mel_ng[i]; s_mel_off[i] = tab->mel_off[i];
   }
   for (int i = tid; i < N_MFCC * DCT_LD; i += blockDim.x) s_dct[i] = tab->dct_p[i];
 
-  // the tables are loaded once; the CTA then walks its tiles of FPB frames
-  for (int tile = blockIdx.x * tiles_per_cta; tile < (blockIdx.x + 1) * tiles_per_cta; ++tile) {
+  // The tables are loaded once; the CTA then walks its tiles of FPB frames.  The raw samples of the NEXT tile are
+  // fetched into registers before the frame loop of the current one, so their HBM latency hides behind the FFTs
+  // (ncu: a quarter of all stall samples sat on the pre-emphasis FMA waiting for these loads).
+  constexpr int SPT = (SEG + FE_WARPS * 32 - 1) / (FE_WARPS * 32);   // samples per thread
+  float cur[SPT], prv[SPT];
+  auto fetch = [&](int tile_t0) {
+    const int q0 = tile_t0 * HOP;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = tid + j * (FE_WARPS * 32);
+      int n = q0 + i - N_FFT / 2;                       // reflect padding (numpy "reflect": no edge repeat)
+      if (n < 0) n = -n;
+      if (n >= n_samples) n = 2 * (n_samples - 1) - n;
+      const bool ok = i < SEG && n >= 0 && n < n_samples;
+      cur[j] = ok ? __ldg(y + n) : 0.f;
+      prv[j] = ok && n > 0 ? __ldg(y + n - 1) : 0.f;
+    }
+  };
+  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = (blockIdx.x + 1) * tiles_per_cta;
+  if (tile_begin * FPB < n_frames) fetch(tile_begin * FPB);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
   const int t0 = tile * FPB;
   if (t0 >= n_frames) break;
   // pre-emphasised, reflect-padded segment: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
-  const int q0 = t0 * HOP;
-  for (int i = tid; i < SEG; i += blockDim.x) {
-    int n = q0 + i - N_FFT / 2;
-    if (n < 0) n = -n;
-    if (n >= n_samples) n = 2 * (n_samples - 1) - n;
-    float v = 0.f;
-    if (n >= 0 && n < n_samples) {
-      const float cur = __ldg(y + n);
-      const float prev = n > 0 ? __ldg(y + n - 1) : 0.f;
-      v = fmaf(-0.97f, prev, cur);
-    }
-    s_seg[i] = v;
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    const int i = tid + j * (FE_WARPS * 32);
+    if (i < SEG) s_seg[i] = fmaf(-0.97f, prv[j], cur[j]);
   }
   __syncthreads();
+  if (tile + 1 < tile_end && (tile + 1) * FPB < n_frames) fetch((tile + 1) * FPB);
 
   float2* z = s_z[warp];
   for (int f = warp; f < FPB; f += FE_WARPS) {
@@ -287,13 +307,20 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
       pw[256] = X * X;
     }
     __syncwarp();
-    // ---- sparse mel filters + log
+    // ---- sparse mel filters + log: lane -> filters (lane, 63 - lane) (a short and a long triangle), each walked in
+    //      aligned groups of 4 bins with 128-bit shared loads of the spectrum and of the zero-padded weights
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int m = lane + 32 * h;
-      const int st = s_mel_start[m], len = s_mel_len[m], off = s_mel_off[m];
+      const int m = h == 0 ? lane : N_MELS - 1 - lane;
+      const int ng = s_mel_ng[m];
+      const float4* p4 = reinterpret_cast<const float4*>(pw) + s_mel_g0[m];
+      const float4* w4 = s_melw4 + s_mel_off[m];
       float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(pw[st + i], s_melw[off + i], acc);
+      for (int i = 0; i < ng; ++i) {
+        const float4 pv = p4[i], wv = w4[i];
+        acc = fmaf(pv.x, wv.x, acc); acc = fmaf(pv.y, wv.y, acc);
+        acc = fmaf(pv.z, wv.z, acc); acc = fmaf(pv.w, wv.w, acc);
+      }
       const float lm = 3.01029995663981195f * log2f(fmaxf(acc, 1e-10f));   // 10 log10(.)
       s_lm[warp][m] = lm;
       s_out[f][m] = lm;
