@@ -251,32 +251,47 @@ def run_b200_arm(args):
     stages = {}
     for name, (tot, n) in sorted(prof.items()):
         stages[name] = {"ms_per_step": tot / args.steps, "launches_per_step": n / args.steps}
-    rec_name = "lstm_recurrence_tc" if args.precision == "tc" else "lstm_recurrence"
-    rec_ms, rec_n = prof.get(rec_name, (0.0, 0))
-    roofline = None
-    if rec_n:
-        per_launch_s = rec_ms / rec_n / 1e3
-        achieved = B * FLOPS_LSTM_RECURRENT_PER_LAYER / per_launch_s / 1e12
-        kname = ("lstm_rec_tc_kernel (tcgen05 fp16 x fp16 -> fp32, one launch per LSTM layer)" if args.precision == "tc"
-                 else "lstm_recurrence_kernel (fp32 FMA, one launch per LSTM layer)")
-        roofline = {"kernel": kname, "bound": "tensor",
-                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tf_sustained"], "traffic": None,
-                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                    "algorithmic_flops_per_launch": B * FLOPS_LSTM_RECURRENT_PER_LAYER,
-                    "avg_launch_ms": rec_ms / rec_n, "share_of_step": rec_ms / args.steps / (ms / args.steps)}
+    # ---- rooflines: algorithmic bytes / FLOPs per launch over the CUDA-event time of the launch
+    tc = args.precision == "tc"
+    pitch = 320                                   # fp16 halves per row of the split LSTM operand (3 * 104 + 2, padded)
+    Bp = (B + 127) // 128 * 128
+    xp_bytes = Bp * T_FEATS * 4096                # one layer's input projections, fp32
+    algo = {   # name -> (bound, algorithmic bytes per step over all its launches, algorithmic FLOPs per step)
+        "frontend": ("hbm", B * N_SAMPLES * 4 + (Bp * T_FEATS * pitch * 2 if tc else B * T_FEATS * 104 * 4), 0),
+        "frame_gemm": ("hbm", B * BYTES_FRAMES + B * 16 * 256 * 4, B * FLOPS_FRAME_GEMM),
+        "lstm_input_gemm_tc": ("hbm", 2 * xp_bytes + Bp * T_FEATS * (pitch + 264) * 2, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
+        "lstm_recurrence_tc": ("hbm", 2 * xp_bytes + Bp * T_FEATS * 264 * 2, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
+        "lstm_recurrence": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
+        "lstm_input_gemm": ("tensor", 0, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
+    }
     extra = {}
-    fe_ms, fe_n = prof.get("frontend", (0.0, 0))
-    if fe_n:
-        gbs = B * BYTES_FRONTEND / (fe_ms / fe_n / 1e3) / 1e9
-        extra["frontend"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": gbs / peaks["hbm_gbs"]}
-    fg_ms, fg_n = prof.get("frame_gemm", (0.0, 0))
-    if fg_n:
-        gbs = B * BYTES_FRAMES / (fg_ms / fg_n / 1e3) / 1e9
-        extra["frame_gemm"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                               "frac": gbs / peaks["hbm_gbs"],
-                               "tflops": B * FLOPS_FRAME_GEMM / (fg_ms / fg_n / 1e3) / 1e12}
+    for name, (bound, nbytes, nflops) in algo.items():
+        tot, n = prof.get(name, (0.0, 0))
+        if not n:
+            continue
+        sec = tot / args.steps / 1e3
+        ent = {"bound": bound, "ms_per_step": tot / args.steps, "launches_per_step": n / args.steps}
+        if nbytes:
+            ent.update({"hbm_gbs": nbytes / sec / 1e9, "hbm_frac": nbytes / sec / 1e9 / peaks["hbm_gbs"],
+                        "algorithmic_bytes_per_step": nbytes})
+        if nflops:
+            ent.update({"tflops": nflops / sec / 1e12, "tensor_frac": nflops / sec / 1e12 / peaks["tf_sustained"]})
+        extra[name] = ent
+    # the dominant kernel = the one with the most device time per step among the stages with a stated roofline
+    roofline = None
+    if extra:
+        dom = max(extra, key=lambda k: extra[k]["ms_per_step"])
+        e = extra[dom]
+        tot, n = prof[dom]
+        if e["bound"] == "hbm":
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": e["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": e["hbm_frac"], "traffic": None}
+        else:
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": e["tflops"], "peak": peaks["tf_sustained"],
+                        "unit": "TFLOP/s", "frac": e["tensor_frac"], "traffic": None}
+        roofline.update({"peak_source": peaks["source"], "avg_launch_ms": tot / n,
+                         "share_of_step": tot / args.steps / (ms / args.steps),
+                         "note": "dominant kernel by device time per step; every stage is in stage_rooflines"})
 
     # labels of the timed precision against the fp32 CUDA path (itself checked against the oracle) on one batch
     parity = None
@@ -404,7 +419,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=148 * 128,
                     help="clips per GPU per step (default: one 128-clip CTA of the recurrent kernel per SM)")
-    ap.add_argument("--e2e-chunk", type=int, default=4096, help="clips per host->device sub-batch in the e2e leg")
+    ap.add_argument("--e2e-chunk", type=int, default=2048, help="clips per host->device sub-batch in the e2e leg")
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=32, help="clips in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
