@@ -366,25 +366,24 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   if (xs) {
     // fused operand preparation for the tensor-core LSTM (lstm.cu): time-major rows (t, clip) of
     // [hi(104) | lo(104) | hi(104) | 1, 1 | 0...] in fp16, hi = fp16(x), lo = fp16(x - hi)
+    // 64 threads per row, 4 rows at a time: thread j < 52 converts one pair of features and stores it three times
+    // (hi at [j], lo at [52 + j], hi at [104 + j], in half2 units); threads 52.. write the (1, 1) pair and the zero pad
+    const int j = tid & 63, rsub = tid >> 6;
     const int h2_per_row = ldx >> 1;
-    for (int i = tid; i < rows * h2_per_row; i += blockDim.x) {
-      const int f = i / h2_per_row, k2 = i - f * h2_per_row;
-      __half v[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int k = 2 * k2 + u;
-        __half o = __float2half_rn(0.f);
-        if (k < 3 * N_FEATS) {
-          const int kk = k < N_FEATS ? k : (k < 2 * N_FEATS ? k - N_FEATS : k - 2 * N_FEATS);
-          const float x = s_out[f][kk];
-          const __half hi = __float2half_rn(x);
-          o = (k >= N_FEATS && k < 2 * N_FEATS) ? __float2half_rn(x - __half2float(hi)) : hi;
-        } else if (k < 3 * N_FEATS + 2) {
-          o = __float2half_rn(1.f);
-        }
-        v[u] = o;
+    for (int f = rsub; f < rows; f += 4) {
+      __half2* row = reinterpret_cast<__half2*>(xs + ((size_t)(t0 + f) * Bp + clip) * ldx);
+      if (j < N_FEATS / 2) {
+        const float2 x = *reinterpret_cast<const float2*>(&s_out[f][2 * j]);
+        const __half2 hi = __floats2half2_rn(x.x, x.y);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+        row[j] = hi;
+        row[N_FEATS / 2 + j] = lo;
+        row[N_FEATS + j] = hi;
+      } else {
+        for (int k2 = 3 * N_FEATS / 2 + (j - N_FEATS / 2); k2 < h2_per_row; k2 += 64 - N_FEATS / 2)
+          row[k2] = k2 == 3 * N_FEATS / 2 ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
       }
-      reinterpret_cast<__half2*>(xs + ((size_t)(t0 + f) * Bp + clip) * ldx)[k2] = __halves2half2(v[0], v[1]);
     }
   }
   __syncthreads();   // s_seg / s_out are rewritten by the next tile
