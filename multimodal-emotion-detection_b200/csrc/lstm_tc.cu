@@ -9,7 +9,7 @@
 //   warp 1     one lane issues tcgen05.mma (M 128 clips, N 128, K 16) x 16 per chunk; A is the fp16 hidden
 //              state the epilogue wrote, ping-ponged between steps;
 //   warps 2-9  two epilogue warpgroups (even / odd chunks), thread = clip = TMEM lane: tcgen05.ld the four gate
-//              pre-activations of 8 units, add xp_t (256-bit loads, prefetched two items ahead in registers),
+//              pre-activations of 8 units, add xp_t (coalesced loads, prefetched three items ahead in registers),
 //              sigmoid / tanh, update the fp32 cell state that lives in 256 further TMEM columns of the same
 //              lane (tcgen05.ld / .st), write h_t as fp16 straight into the swizzled A-operand layout of the
 //              next step and (layer 0) as fp32 to h_seq.
@@ -242,35 +242,30 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       if (live && h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
     };
 
-    float xa[4][8], xb[4][8];
-    load_x(0, wg, 0, xa);
-    load_x(0, wg, 1, xb);
-#pragma unroll 1
-    for (int t = 0; t < T; ++t) {
-#pragma unroll 1
-      for (int c = wg; c < RNC; c += 2) {
-        // the item two ahead of (c, q): same chunk for q < 2, else the next chunk of this warpgroup
-        const int cn = c + 2 < RNC ? c + 2 : wg, tn = c + 2 < RNC ? t : t + 1;
+    // Items of this warpgroup in execution order: n -> step n / 16, chunk wg + 2 ((n % 16) / 4), quarter n % 4.
+    // xp of item n + 3 is requested while item n is computed: three named register buffers rotate, so 96 values
+    // per thread (48 KB per SM) are in flight - HBM latency under load is 2-3 us and the kernel's floor is the xp
+    // stream (ncu: long-scoreboard stalls on these loads were the top stall with two buffers).
+    const int n_items = T * 16;
+    auto coords = [&](int n, int& t, int& c, int& q) { t = n >> 4; c = wg + 2 * ((n & 15) >> 2); q = n & 3; };
+    auto load_n = [&](int n, float (&xg)[4][8]) {
+      int t, c, q;
+      coords(n, t, c, q);
+      load_x(t, c, q, xg);              // zero-fills past the last step
+    };
+    auto run_n = [&](int n, float (&xg)[4][8]) {
+      int t, c, q;
+      coords(n, t, c, q);
+      if (q == 0) {
         mbar_wait(&sm.acc_full[wg], use & 1);
         tc_fence_after();
-        // TMEM loads of item q + 1 are in flight while item q is computed (two named register sets)
-        uint32_t accA[4][8], csA[8], accB[4][8], csB[8];
-        load_t(c, 0, accA, csA);
-        tmem_ld_wait();
-        load_t(c, 1, accB, csB);
-        item(t, c, 0, xa, accA, csA);
-        load_x(t, c, 2, xa);
-        tmem_ld_wait();
-        load_t(c, 2, accA, csA);
-        item(t, c, 1, xb, accB, csB);
-        load_x(t, c, 3, xb);
-        tmem_ld_wait();
-        load_t(c, 3, accB, csB);
-        item(t, c, 2, xa, accA, csA);
-        load_x(tn, cn, 0, xa);
-        tmem_ld_wait();
-        item(t, c, 3, xb, accB, csB);
-        load_x(tn, cn, 1, xb);
+      }
+      uint32_t acc[4][8], cs[8];
+      load_t(c, q, acc, cs);
+      tmem_ld_wait();
+      item(t, c, q, xg, acc, cs);
+      load_n(n + 3, xg);
+      if (q == 3) {
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&sm.acc_empty[wg]);
@@ -278,6 +273,16 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
         fence_proxy_async_smem();              // this thread's part of k-block c/2 of h_t is written
         mbar_arrive(&sm.h_ready[c >> 1]);
       }
+    };
+    float xa[4][8], xb[4][8], xc[4][8];
+    load_n(0, xa);
+    load_n(1, xb);
+    load_n(2, xc);
+#pragma unroll 1
+    for (int n = 0; n < n_items; n += 3) {
+      run_n(n, xa);
+      if (n + 1 < n_items) run_n(n + 1, xb);
+      if (n + 2 < n_items) run_n(n + 2, xc);
     }
   }
   tc_fence_before();
