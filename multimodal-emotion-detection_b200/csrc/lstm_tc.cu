@@ -8,11 +8,11 @@
 //              1024 x 256 weight matrix is re-read from L2 every step (it never fits next to the state);
 //   warp 1     one lane issues tcgen05.mma (M 128 clips, N 128, K 16) x 16 per chunk; A is the fp16 hidden
 //              state the epilogue wrote, ping-ponged between steps;
-//   warps 2-9  two epilogue warpgroups (even / odd chunks), thread = clip = TMEM lane: tcgen05.ld the four gate
-//              pre-activations of 8 units, add xp_t (coalesced loads, prefetched three items ahead in registers),
-//              sigmoid / tanh, update the fp32 cell state that lives in 256 further TMEM columns of the same
-//              lane (tcgen05.ld / .st), write h_t as fp16 straight into the swizzled A-operand layout of the
-//              next step and (layer 0) as fp32 to h_seq.
+//   warps 2-17 sixteen epilogue warps = (TMEM lane quarter) x (8-unit quarter of a chunk), thread = (clip, 8 units):
+//              tcgen05.ld the four gate pre-activations of its units, add xp_t (coalesced loads, prefetched two
+//              chunks ahead in registers), sigmoid / tanh, update the fp32 cell state that lives in 256 further
+//              TMEM columns of the same lane (tcgen05.ld / .st), write h_t as fp16 straight into the swizzled
+//              A-operand layout of the next step and (layer 0) into the next layer's fp16 GEMM operand.
 // mbarriers: full/empty per weight stage, acc_full/acc_empty per TMEM buffer, h_ready per 64-unit k-block of
 // the hidden state (so step t+1 starts on k-block 0 while the epilogue of step t finishes k-block 3).
 #include <cuda_fp16.h>
@@ -24,7 +24,7 @@
 namespace avhot {
 namespace tc {
 
-constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 320;
+constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 64 + 512;
 
 struct RecSmem {
   __half hA[2][RKB][RB * 64];   // hidden state, A operand: [step parity][k-block][128 rows x 128 B, swizzled]
@@ -104,8 +104,8 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < RST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 128); }
-    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 256);   // both warpgroups write half of a k-block
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 512); }
+    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 1024);   // 512 epilogue threads x the 2 chunks of a k-block
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -156,38 +156,34 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       }
     }
   } else {
-    // Two epilogue warpgroups: warpgroup g owns the chunks c = g (mod 2), i.e. TMEM buffer g, so each has two
-    // chunk-times of MMA to finish one chunk.  Work item = 8 hidden units of one chunk; xp for the item two ahead
-    // is already in flight in registers (two named buffers) while the current one is computed.
-    const int wg = (warp - 2) >> 2;
+    // 16 epilogue warps = (TMEM lane quarter, quarter q of a chunk): thread (clip r, q) owns hidden units
+    // 32 c + 8 q .. + 7 of every chunk c, so the four 8-unit items of a chunk are computed in parallel by four
+    // warps per lane quarter (4 epilogue warps per scheduler hide each other's TMEM / MUFU / memory latency) and a
+    // chunk's epilogue takes one item time.  xp of the item two chunks ahead is in flight in registers.
+    const int q = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // clip row = TMEM lane
     const int clip = blockIdx.x * RB + r;
     const bool live = clip < B;
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
     const int last_t = (live && lengths ? min(max(__ldg(lengths + clip), 1), T) : T) - 1;
-    {                                                         // c_{-1} = 0 for the units this warpgroup owns
-      uint32_t z[16];
+    {                                                         // c_{-1} = 0 for the units this thread owns
+      uint32_t z[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) z[i] = 0u;
+      for (int i = 0; i < 8; ++i) z[i] = 0u;
 #pragma unroll 1
-      for (int c = wg; c < RNC; c += 2) {
-        tmem_st16(tlane + 256u + (uint32_t)(c * RCH), z);
-        tmem_st16(tlane + 256u + (uint32_t)(c * RCH + 16), z);
-      }
+      for (int c = 0; c < RNC; ++c) tmem_st8(tlane + 256u + (uint32_t)(c * RCH + q * 8), z);
       tmem_st_wait();
     }
     // xp is time-major and tile-transposed (gemm_ws.cu): [t][clip tile][4H columns][128 clips]; h_seq is the
-    // time-major padded fp16 sequence (T, Bp, H) that is the next layer's GEMM operand (rows of dead clips are
+    // time-major padded fp16 sequence (T, Bp, pitch) that is the next layer's GEMM operand (rows of dead clips are
     // written too, so the operand is fully initialised)
     const size_t n_ct = gridDim.x;
     const float* xcol = xp + (size_t)blockIdx.x * (4 * RH) * RB + r;
     __half* hrow = h_seq ? h_seq + ((size_t)blockIdx.x * RB + r) * h_pitch : nullptr;
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
-    uint32_t use = 0;
 
-    // xp of item (t, c, q): 4 gates x 8 units, one 256-bit load per gate
-    auto load_x = [&](int t, int c, int q, float (&xg)[4][8]) {
+    auto load_x = [&](int t, int c, float (&xg)[4][8]) {      // 4 gates x 8 units, coalesced across the 32 clips
       if (t < T) {
         const float* src = xcol + ((size_t)t * n_ct * (4 * RH) + c * RCH + q * 8) * RB;
 #pragma unroll
@@ -201,14 +197,16 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
           for (int j = 0; j < 8; ++j) xg[g][j] = 0.f;
       }
     };
-    // TMEM side of an item: the four gate accumulators and the cell state of its 8 units
-    auto load_t = [&](int c, int q, uint32_t (&acc)[4][8], uint32_t (&cs)[8]) {
+    uint32_t use[2] = {0, 0};
+    auto run = [&](int t, int c, float (&xg)[4][8]) {
+      const int b = c & 1, u0 = c * RCH + q * 8;
+      mbar_wait(&sm.acc_full[b], use[b] & 1);
+      tc_fence_after();
+      uint32_t acc[4][8], cs[8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tmem_ld8(tlane + (uint32_t)(wg * RN + g * RCH + q * 8), acc[g]);
-      tmem_ld8(tlane + 256u + (uint32_t)(c * RCH + q * 8), cs);
-    };
-    auto item = [&](int t, int c, int q, const float (&xg)[4][8], uint32_t (&acc)[4][8], uint32_t (&cs)[8]) {
-      const int u0 = c * RCH + q * 8;
+      for (int g = 0; g < 4; ++g) tmem_ld8(tlane + (uint32_t)(b * RN + g * RCH + q * 8), acc[g]);
+      tmem_ld8(tlane + 256u + (uint32_t)u0, cs);
+      tmem_ld_wait();
       float hn[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -223,16 +221,14 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       tmem_st8(tlane + 256u + (uint32_t)u0, cs);
       // h_t (fp16) -> A operand of step t+1: k-block u0 / 64, 16-byte chunk (u0 % 64) / 8, XOR-swizzled by the row
       uint32_t pk[4];
-      {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
-          pk[j] = *reinterpret_cast<const uint32_t*>(&v);
-        }
-        unsigned char* tile = hbase + (size_t)((t + 1) & 1) * sizeof(sm.hA[0]) + (size_t)(u0 >> 6) * (RB * 128) +
-                              (size_t)r * 128;
-        *reinterpret_cast<uint4*>(tile + ((((u0 & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int j = 0; j < 4; ++j) {
+        const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&v);
       }
+      unsigned char* tile = hbase + (size_t)((t + 1) & 1) * sizeof(sm.hA[0]) + (size_t)(u0 >> 6) * (RB * 128) +
+                            (size_t)r * 128;
+      *reinterpret_cast<uint4*>(tile + ((((u0 & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       if (hrow) {
         __half* ht = hrow + (size_t)t * n_ct * RB * h_pitch;
         *reinterpret_cast<uint4*>(ht + u0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -240,49 +236,25 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
         if (u0 == 0 && h_pitch > RH) *reinterpret_cast<uint4*>(ht + RH) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
       }
       if (live && h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
+      // next use of this register buffer: the same quarter of chunk c + 2 (or of the next step)
+      load_x(c + 2 < RNC ? t : t + 1, c + 2 < RNC ? c + 2 : c + 2 - RNC, xg);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sm.acc_empty[b]);
+      ++use[b];
+      fence_proxy_async_smem();                // this thread's part of k-block c/2 of h_t is written
+      mbar_arrive(&sm.h_ready[c >> 1]);
     };
-
-    // Items of this warpgroup in execution order: n -> step n / 16, chunk wg + 2 ((n % 16) / 4), quarter n % 4.
-    // xp of item n + 3 is requested while item n is computed: three named register buffers rotate, so 96 values
-    // per thread (48 KB per SM) are in flight - HBM latency under load is 2-3 us and the kernel's floor is the xp
-    // stream (ncu: long-scoreboard stalls on these loads were the top stall with two buffers).
-    const int n_items = T * 16;
-    auto coords = [&](int n, int& t, int& c, int& q) { t = n >> 4; c = wg + 2 * ((n & 15) >> 2); q = n & 3; };
-    auto load_n = [&](int n, float (&xg)[4][8]) {
-      int t, c, q;
-      coords(n, t, c, q);
-      load_x(t, c, q, xg);              // zero-fills past the last step
-    };
-    auto run_n = [&](int n, float (&xg)[4][8]) {
-      int t, c, q;
-      coords(n, t, c, q);
-      if (q == 0) {
-        mbar_wait(&sm.acc_full[wg], use & 1);
-        tc_fence_after();
-      }
-      uint32_t acc[4][8], cs[8];
-      load_t(c, q, acc, cs);
-      tmem_ld_wait();
-      item(t, c, q, xg, acc, cs);
-      load_n(n + 3, xg);
-      if (q == 3) {
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&sm.acc_empty[wg]);
-        ++use;
-        fence_proxy_async_smem();              // this thread's part of k-block c/2 of h_t is written
-        mbar_arrive(&sm.h_ready[c >> 1]);
-      }
-    };
-    float xa[4][8], xb[4][8], xc[4][8];
-    load_n(0, xa);
-    load_n(1, xb);
-    load_n(2, xc);
+    float xa[4][8], xb[4][8];
+    load_x(0, 0, xa);
+    load_x(0, 1, xb);
 #pragma unroll 1
-    for (int n = 0; n < n_items; n += 3) {
-      run_n(n, xa);
-      if (n + 1 < n_items) run_n(n + 1, xb);
-      if (n + 2 < n_items) run_n(n + 2, xc);
+    for (int t = 0; t < T; ++t) {
+#pragma unroll 1
+      for (int c = 0; c < RNC; c += 2) {
+        run(t, c, xa);
+        run(t, c + 1, xb);
+      }
     }
   }
   tc_fence_before();
