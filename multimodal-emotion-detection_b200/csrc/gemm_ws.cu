@@ -30,6 +30,7 @@ struct GemmWsSmem {
   uint32_t tmem_base;
 };
 
+template <bool OUT_F16>
 __global__ void __launch_bounds__(WTHREADS, 1)
 gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    float* __restrict__ C, int ldc, int M, int nkb, int n_blocks,
@@ -110,17 +111,35 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ((mt * N + col) * 128 + row % 128), so for every column the 32 lanes of a warp write 128 contiguous bytes
       // (1 wavefront per store instead of 32 for row-major rows that are 4 KB apart), and the consumer
       // (lstm_tc.cu, thread = row) reads it back the same way.  Pure TMEM -> global copy, no arithmetic.
-      float* cbase = C + ((size_t)(row / WBM) * ldc + n0) * WBM + (quarter * 32 + lane);
+      if (!OUT_F16) {
+        float* cbase = C + ((size_t)(row / WBM) * ldc + n0) * WBM + (quarter * 32 + lane);
 #pragma unroll
-      for (int c = 0; c < WBN; c += 64) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tlane + (uint32_t)(b * WBN + c), r0);
-        tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
-        tmem_ld_wait();
+        for (int c = 0; c < WBN; c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tlane + (uint32_t)(b * WBN + c), r0);
+          tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cbase[(size_t)(c + j) * WBM] = __uint_as_float(r0[j]);
+          for (int j = 0; j < 32; ++j) cbase[(size_t)(c + j) * WBM] = __uint_as_float(r0[j]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cbase[(size_t)(c + 32 + j) * WBM] = __uint_as_float(r1[j]);
+          for (int j = 0; j < 32; ++j) cbase[(size_t)(c + 32 + j) * WBM] = __uint_as_float(r1[j]);
+        }
+      } else {
+        // fp16 output: columns (2j, 2j + 1) of a row packed into one half2 -> [M / 128][N / 2][128] half2
+        __half2* cbase = reinterpret_cast<__half2*>(C) + ((size_t)(row / WBM) * (ldc / 2) + n0 / 2) * WBM + (quarter * 32 + lane);
+#pragma unroll
+        for (int c = 0; c < WBN; c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tlane + (uint32_t)(b * WBN + c), r0);
+          tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            cbase[(size_t)((c + j) / 2) * WBM] = __floats2half2_rn(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            cbase[(size_t)((c + 32 + j) / 2) * WBM] = __floats2half2_rn(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+        }
       }
       tc_fence_before();
       mbar_arrive(&sm.acc_empty[b]);
@@ -134,9 +153,10 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }  // namespace tc
 
 // a, w fp16 row-major (K contiguous); M % 128 == 0 (caller pads); N % 128 == 0; K <= 320;
-// c fp32 in the tile-transposed layout [M / 128][N = ldc][128]
-int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, float* c, int ldc, int M, int N, int K,
-                cudaStream_t s, const char* prof_name) {
+// c in the tile-transposed layout: fp32 [M / 128][N = ldc][128], or fp16 column pairs [M / 128][N / 2][128] half2
+int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, void* c_out, bool out_f16, int ldc, int M, int N,
+                int K, cudaStream_t s, const char* prof_name) {
+  float* c = reinterpret_cast<float*>(c_out);
   using namespace tc;
   AVHOT_REQUIRE(a && w && c && M >= 0 && N > 0 && K > 0, AVHOT_ERR_INVALID, "gemm_ws: bad arguments");
   AVHOT_REQUIRE(M % WBM == 0 && N % WBN == 0 && ldc == N && K <= 64 * WKB_MAX && (lda & 7) == 0 && (ldw & 7) == 0,
@@ -155,9 +175,14 @@ int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, float* c, int ld
   if (groups > m_tiles) groups = m_tiles;
   const int nkb = ceil_div(K, 64);
   const int smem = (int)sizeof(GemmWsSmem) + 1024;
-  AVHOT_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ProfScope prof(prof_name, s);
-  gemm_f16_ws_kernel<<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, c, ldc, M, nkb, n_blocks, groups);
+  if (out_f16) {
+    AVHOT_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm_f16_ws_kernel<true><<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, c, ldc, M, nkb, n_blocks, groups);
+  } else {
+    AVHOT_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm_f16_ws_kernel<false><<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, c, ldc, M, nkb, n_blocks, groups);
+  }
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }

@@ -342,7 +342,7 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
       const int hp = pad8(H + 2);                      // fp16 pitch of h_seq: H columns + (1, 1) for the bias columns
       if (l == 0 && seq_split) {                      // operand already prepared by avhot_frontend_ex
         const int ldx = pad8(3 * in + 2);
-        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, xp, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, xp, false, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
       } else if (l == 0) {
         const int ldx = pad8(3 * in + 2);
         const long long n = (long long)Mp * ldx;
@@ -355,12 +355,13 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
               x, x_split, B, (int)Bp, T, in, ldx);
           AVHOT_LAUNCH_CHECK();
         }
-        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, xp, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, xp, false, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
       } else {
-        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, xp, 4 * H, Mp, 4 * H, H + 2, s, "lstm_input_gemm_tc");
+        // layers > 0: inputs |h| < 1 keep |xp| ~ 1, so fp16 storage (2^-12 absolute) halves the xp stream
+        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, xp, true, 4 * H, Mp, 4 * H, H + 2, s, "lstm_input_gemm_tc");
       }
       if (rc == AVHOT_OK)
-        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);
+        rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, l > 0, last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);
       if (rc != AVHOT_OK) return rc;
       continue;
     }

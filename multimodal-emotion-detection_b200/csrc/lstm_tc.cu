@@ -86,7 +86,7 @@ template <int ACT> __device__ __forceinline__ float act_tanh(float x) {
   return y;
 }
 
-template <int ACT>
+template <int ACT, bool XP16>
 __global__ void __launch_bounds__(RTHREADS, 1)
 lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp, __half* __restrict__ h_seq,
                    int h_pitch,
@@ -184,17 +184,31 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
 
     auto load_x = [&](int t, int c, float (&xg)[4][8]) {      // 4 gates x 8 units, coalesced across the 32 clips
-      if (t < T) {
+      if (t >= T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xg[g][j] = 0.f;
+      } else if (!XP16) {
         const float* src = xcol + ((size_t)t * n_ct * (4 * RH) + c * RCH + q * 8) * RB;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int j = 0; j < 8; ++j) xg[g][j] = ldg_stream(src + (size_t)(g * RH + j) * RB);
       } else {
+        // fp16 xp (layers > 0): column pairs packed as half2, [t][clip tile][2H pairs][128 clips]
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(xp) + (size_t)blockIdx.x * (2 * RH) * RB + r +
+                              ((size_t)t * n_ct * (2 * RH) + (c * RCH + q * 8) / 2) * RB;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) xg[g][j] = 0.f;
+          for (int j = 0; j < 8; j += 2) {
+            uint32_t u;
+            asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(u) : "l"(src + (size_t)((g * RH + j) / 2) * RB));
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+            xg[g][j] = f.x;
+            xg[g][j + 1] = f.y;
+          }
       }
     };
     uint32_t use[2] = {0, 0};
@@ -278,8 +292,9 @@ int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s) {
   return AVHOT_OK;
 }
 
-int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, void* h_seq_f16, int h_pitch, float* h_last,
-                       const int32_t* lengths, int B, int T, cudaStream_t s) {
+int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_f16, void* h_seq_f16, int h_pitch,
+                       float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
+  const float* xp = reinterpret_cast<const float*>(xp_any);
   __half* h_seq = reinterpret_cast<__half*>(h_seq_f16);
   using namespace tc;
   CUtensorMap tmW;
@@ -290,13 +305,16 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const float* xp, void* h_seq
   // error is set by the fp16 state); AVHOT_LSTM_ACT=0 selects the ex2 + rcp form.
   static const int act = [] { const char* e = getenv("AVHOT_LSTM_ACT"); return e ? atoi(e) : 1; }();
   ProfScope prof("lstm_recurrence_tc", s);
-  if (act == 1) {
-    AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    lstm_rec_tc_kernel<1><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_pitch, h_last, lengths, B, T);
-  } else {
-    AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    lstm_rec_tc_kernel<0><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_pitch, h_last, lengths, B, T);
-  }
+#define AVHOT_REC_LAUNCH(ACT_, X16_)                                                                                \
+  do {                                                                                                              \
+    AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<ACT_, X16_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    lstm_rec_tc_kernel<ACT_, X16_><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_pitch, h_last, lengths, B, T); \
+  } while (0)
+  if (act == 1 && xp_f16) AVHOT_REC_LAUNCH(1, true);
+  else if (act == 1) AVHOT_REC_LAUNCH(1, false);
+  else if (xp_f16) AVHOT_REC_LAUNCH(0, true);
+  else AVHOT_REC_LAUNCH(0, false);
+#undef AVHOT_REC_LAUNCH
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }
