@@ -32,6 +32,8 @@ constexpr int DCT_LD = N_MELS + 4; // padded row length of the DCT table
 struct FrontendTables {            // device layout, all fp32 unless noted
   float window[N_FFT];
   float2 tw[N_FFT];                // tw[k] = exp(-2 pi i k / 512)
+  float2 tw2[64];                  // tw2[r * 8 + k]  = exp(-2 pi i r k / 64)   (pass 2; lanes read consecutive entries)
+  float2 tw3[256];                 // tw3[r * 64 + j] = exp(-2 pi i r j / 256)  (pass 3)
   float4 mel_w4[MEL_G4_MAX];       // filter weights in aligned groups of 4 bins (zeros outside the triangle)
   int mel_g0[N_MELS];              // first 4-bin group of filter m
   int mel_ng[N_MELS];              // number of groups
@@ -61,6 +63,10 @@ static void build_tables() {
     t.window[n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / N_FFT));
     t.tw[n] = make_float2((float)cos(2.0 * PI * n / N_FFT), (float)(-sin(2.0 * PI * n / N_FFT)));
   }
+  for (int r = 0; r < 8; ++r)
+    for (int k = 0; k < 8; ++k) t.tw2[r * 8 + k] = t.tw[(r * k * 8) % N_FFT];
+  for (int r = 0; r < 4; ++r)
+    for (int j = 0; j < 64; ++j) t.tw3[r * 64 + j] = t.tw[(r * j * 2) % N_FFT];
   // Slaney mel filterbank, Slaney area normalisation, 0..8000 Hz (oracle/frontend.py mel_filterbank)
   const double sr = 16000.0, f_lo = 0.0, f_hi = 8000.0;
   std::vector<double> hz(N_MELS + 2);
@@ -163,12 +169,13 @@ struct FeSmem {
   float seg[SEG];
   float win[N_FFT];
   float2 tw[N_FFT];
+  float2 tw2[64], tw3[256];
   float4 melw4[MEL_G4_MAX];
   int mel_g0[N_MELS], mel_ng[N_MELS], mel_off[N_MELS];
   float dct[N_MFCC * DCT_LD];
   float2 z[FE_WARPS][ZPAD];
   float pow[FE_WARPS][N_BINS + 3];
-  float lm[FE_WARPS][N_MELS];
+  float lm[FE_WARPS][FPB / FE_WARPS][N_MELS];
   float out[FPB][N_FEATS];
 };
 
@@ -185,7 +192,7 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   float* s_dct = sm.dct;
   float2 (*s_z)[ZPAD] = sm.z;
   float (*s_pow)[N_BINS + 3] = sm.pow;
-  float (*s_lm)[N_MELS] = sm.lm;
+  float (*s_lm)[FPB / FE_WARPS][N_MELS] = sm.lm;
   float (*s_out)[N_FEATS] = sm.out;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,6 +201,8 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 
   // tables -> smem
   for (int i = tid; i < N_FFT; i += blockDim.x) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
+  for (int i = tid; i < 64; i += blockDim.x) sm.tw2[i] = tab->tw2[i];
+  for (int i = tid; i < 256; i += blockDim.x) sm.tw3[i] = tab->tw3[i];
   for (int i = tid; i < MEL_G4_MAX; i += blockDim.x) s_melw4[i] = tab->mel_w4[i];
   if (lane < 3) sm.pow[warp][N_BINS + lane] = 0.f;    // bins 257..259 pad the last group of 4
   for (int i = tid; i < N_MELS; i += blockDim.x) {
@@ -257,7 +266,7 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float2 a = z[zpad(lane + 32 * r)];
-        v[r] = r == 0 ? a : cmul(a, s_tw[r * k * 8]);   // exp(-2 pi i r k / 64)
+        v[r] = r == 0 ? a : cmul(a, sm.tw2[r * 8 + k]);   // exp(-2 pi i r k / 64), bank-conflict-free layout
       }
       dft8(v);
       __syncwarp();
@@ -276,7 +285,7 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const float2 a = z[zpad(j + 64 * r)];
-          u[jj][r] = r == 0 ? a : cmul(a, s_tw[r * j * 2]);   // exp(-2 pi i r j / 256)
+          u[jj][r] = r == 0 ? a : cmul(a, sm.tw3[r * 64 + j]);   // exp(-2 pi i r j / 256)
         }
         dft4(u[jj][0], u[jj][1], u[jj][2], u[jj][3]);
       }
@@ -322,38 +331,46 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
         acc = fmaf(pv.z, wv.z, acc); acc = fmaf(pv.w, wv.w, acc);
       }
       const float lm = 3.01029995663981195f * log2f(fmaxf(acc, 1e-10f));   // 10 log10(.)
-      s_lm[warp][m] = lm;
+      s_lm[warp][f / FE_WARPS][m] = lm;
       s_out[f][m] = lm;
     }
     __syncwarp();
-    // ---- DCT-II (orthonormal), first 40 coefficients: lane c does coefficient c over all 64 bands; the last 8
-    //      coefficients are split four ways over the bands (lane -> coefficient 32 + (lane & 7), bands
-    //      16 (lane >> 3) ..) and combined with two shuffles.  All operands are 128-bit shared loads.
-    {
-      const float4* lm4 = reinterpret_cast<const float4*>(&s_lm[warp][0]);
+  }
+  // ---- DCT-II (orthonormal), first 40 coefficients, for the warp's two frames at once (every 128-bit row of the
+  //      table is loaded once and used twice): lane c does coefficient c over all 64 bands; the last 8
+  //      coefficients are split four ways over the bands (lane -> coefficient 32 + (lane & 7), bands
+  //      16 (lane >> 3) ..) and combined with two shuffles.
+  {
+    const bool two = t0 + warp + FE_WARPS < n_frames;         // warp-uniform: does the second frame exist?
+    if (t0 + warp < n_frames) {
+      const float4* lmA = reinterpret_cast<const float4*>(&s_lm[warp][0][0]);
+      const float4* lmB = reinterpret_cast<const float4*>(&s_lm[warp][two ? 1 : 0][0]);
       const float4* d4 = reinterpret_cast<const float4*>(s_dct + lane * DCT_LD);
-      float acc0 = 0.f;
+      float a0 = 0.f, b0 = 0.f;
 #pragma unroll
       for (int j4 = 0; j4 < N_MELS / 4; ++j4) {
-        const float4 l = lm4[j4], d = d4[j4];
-        acc0 = fmaf(l.x, d.x, acc0); acc0 = fmaf(l.y, d.y, acc0);
-        acc0 = fmaf(l.z, d.z, acc0); acc0 = fmaf(l.w, d.w, acc0);
+        const float4 d = d4[j4], la = lmA[j4], lb = lmB[j4];
+        a0 = fmaf(la.x, d.x, a0); a0 = fmaf(la.y, d.y, a0); a0 = fmaf(la.z, d.z, a0); a0 = fmaf(la.w, d.w, a0);
+        b0 = fmaf(lb.x, d.x, b0); b0 = fmaf(lb.y, d.y, b0); b0 = fmaf(lb.z, d.z, b0); b0 = fmaf(lb.w, d.w, b0);
       }
-      s_out[f][N_MELS + lane] = acc0;
       const int part = lane >> 3;
       const float4* e4 = reinterpret_cast<const float4*>(s_dct + (32 + (lane & 7)) * DCT_LD + part * 16);
-      float acc1 = 0.f;
+      float a1 = 0.f, b1 = 0.f;
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 l = lm4[part * 4 + j4], d = e4[j4];
-        acc1 = fmaf(l.x, d.x, acc1); acc1 = fmaf(l.y, d.y, acc1);
-        acc1 = fmaf(l.z, d.z, acc1); acc1 = fmaf(l.w, d.w, acc1);
+        const float4 d = e4[j4], la = lmA[part * 4 + j4], lb = lmB[part * 4 + j4];
+        a1 = fmaf(la.x, d.x, a1); a1 = fmaf(la.y, d.y, a1); a1 = fmaf(la.z, d.z, a1); a1 = fmaf(la.w, d.w, a1);
+        b1 = fmaf(lb.x, d.x, b1); b1 = fmaf(lb.y, d.y, b1); b1 = fmaf(lb.z, d.z, b1); b1 = fmaf(lb.w, d.w, b1);
       }
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
-      if (lane < 8) s_out[f][N_MELS + 32 + lane] = acc1;
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 8);  a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, 8);  b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+      s_out[warp][N_MELS + lane] = a0;
+      if (lane < 8) s_out[warp][N_MELS + 32 + lane] = a1;
+      if (two) {
+        s_out[warp + FE_WARPS][N_MELS + lane] = b0;
+        if (lane < 8) s_out[warp + FE_WARPS][N_MELS + 32 + lane] = b1;
+      }
     }
-    __syncwarp();
   }
   __syncthreads();
   // coalesced store of the CTA's output tile (rows are contiguous in feats)
