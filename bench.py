@@ -241,6 +241,9 @@ def run_b200_arm(args):
 
     # ---- end to end through the public API with host buffers --------------------------------------------------
     e2e = run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier)
+    # the same leg with the frames kept as the uint8 pixels they are decoded to (src/dataprocessing.py:261-265
+    # divides by 255 on the host; here the division happens on the device): a quarter of the dominant H2D stream
+    e2e_u8 = run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8_frames=True)
 
     if rank != 0:
         if world > 1:
@@ -290,6 +293,16 @@ def run_b200_arm(args):
         else:
             roofline = {"kernel": dom, "bound": "tensor", "achieved": e["tflops"], "peak": peaks["tf_sustained"],
                         "unit": "TFLOP/s", "frac": e["tensor_frac"], "traffic": None}
+        # DRAM traffic of that kernel per launch from the committed ncu capture of the same workload, if there is one
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            if tr.get("batch") == B and tr.get("precision") == args.precision:
+                roofline["traffic"] = tr["bytes_per_launch"].get(dom)
+                roofline["traffic_source"] = "profiles/ncu_traffic.json"
+                roofline["algorithmic_bytes_per_launch"] = e.get("algorithmic_bytes_per_step", 0) / (n / args.steps)
+        except (OSError, ValueError):
+            pass
         roofline.update({"peak_source": peaks["source"], "avg_launch_ms": tot / n,
                          "share_of_step": tot / args.steps / (ms / args.steps),
                          "note": "dominant kernel by device time per step; every stage is in stage_rooflines"})
@@ -331,7 +344,7 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/f16 tensor-core operands, f32 accumulate",
             "data": "synthetic", "config": workload_config(args, B),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "e2e": e2e, "e2e_u8_frames": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity, "stages": stages, "stage_rooflines": extra}
     print(json.dumps(line))
     if world > 1:
@@ -339,7 +352,7 @@ def run_b200_arm(args):
     return 0
 
 
-def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier):
+def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8_frames=False):
     """Same step through the public API (AVHotPath.mc_forward = MCDropoutUncertainty's fast path) with inputs in
     pinned HOST memory: every step uploads its B clips host->device in sub-batches of --e2e-chunk clips and reads the
     packed results back; the upload of sub-batch i+1 overlaps the kernels of sub-batch i on a second stream (two
@@ -353,14 +366,15 @@ def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier):
     for j in range(2):
         c0 = clip0_of(j)
         a = pkg.synth.synth_audio(C, c0, SEED, dev)
-        v = pkg.synth.synth_video(C, c0, SEED, dev)
+        v = pkg.synth.synth_video(C, c0, SEED, dev, dtype=torch.uint8 if u8_frames else torch.float32)
         m = pkg.synth.modality_mask(C, c0, P_MODALITY, SEED, dev)
         ha = torch.empty(a.shape, dtype=a.dtype, pin_memory=True).copy_(a)
         hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v)
         hm = torch.empty(m.shape, dtype=m.dtype, pin_memory=True).copy_(m)
         host.append((ha, hv, hm))
         del a, v, m
-    slots = [(torch.empty(C, N_SAMPLES, device=dev), torch.empty(C, N_FRAMES, FRAME_DIM, device=dev),
+    slots = [(torch.empty(C, N_SAMPLES, device=dev),
+              torch.empty(C, N_FRAMES, FRAME_DIM, device=dev, dtype=torch.uint8 if u8_frames else torch.float32),
               torch.empty(C, 2, device=dev)) for _ in range(2)]
     packed_dev = torch.empty(B, N_CLASSES + 1, device=dev)
     result_host = torch.empty(B * world, N_CLASSES + 1, pin_memory=True)
@@ -406,10 +420,12 @@ def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    in_bytes = N_SAMPLES * 4 + N_FRAMES * FRAME_DIM * (1 if u8_frames else 4) + 2 * 4
     return {"value": world * B * args.steps / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms / args.steps,
-            "h2d_bytes_per_step": B * BYTES_IN_PER_CLIP, "d2h_bytes_per_step": B * world * BYTES_OUT_PER_CLIP,
-            "api": f"AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), fp32 pinned host buffers, "
-                   f"{n_sub} sub-batches of <= {C} clips per step, uploads double-buffered on a copy stream"}
+            "h2d_bytes_per_step": B * in_bytes, "d2h_bytes_per_step": B * world * BYTES_OUT_PER_CLIP,
+            "api": f"AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), pinned host buffers "
+                   f"(fp32 audio, {'uint8' if u8_frames else 'fp32'} frames), {n_sub} sub-batches of <= {C} clips per "
+                   f"step, uploads double-buffered on a copy stream"}
 
 
 def main():

@@ -149,6 +149,19 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
 
 static size_t align256f(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// u8 pixels -> fp32 k / 255 (src/dataprocessing.py:261-265), 16 pixels per thread, for the tensor-core GEMM
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 p = __ldg(reinterpret_cast<const uint4*>(in) + i);
+  const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+  float4* o = reinterpret_cast<float4*>(out) + i * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = make_float4(__fdiv_rn((float)(w[j] & 255u), 255.f), __fdiv_rn((float)((w[j] >> 8) & 255u), 255.f),
+                       __fdiv_rn((float)((w[j] >> 16) & 255u), 255.f), __fdiv_rn((float)(w[j] >> 24), 255.f));
+}
+
 }  // namespace avhot
 
 using namespace avhot;
@@ -208,21 +221,35 @@ extern "C" void avhot_frame_destroy(avhot_frame_t h) {
   delete h;
 }
 
+// scratch: only the tensor-core path with u8 frames needs one (the fp32 image of the pixels)
 extern "C" size_t avhot_frame_workspace_bytes(avhot_frame_t h, int B, int F, int precision) {
-  (void)h; (void)B; (void)F; (void)precision;
-  return 0;   // the fp32 path needs no scratch
+  if (!h || B <= 0 || F <= 0 || precision != AVHOT_PREC_TC) return 0;
+  return sizeof(float) * (size_t)B * F * h->frame_dim;
 }
 
 extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, const uint8_t* frames_u8, float* hid,
                                   int B, int F, int precision, void* workspace, size_t workspace_bytes,
                                   avhot_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   AVHOT_REQUIRE(h && hid && B >= 0 && F >= 1, AVHOT_ERR_INVALID, "frame_hidden: bad arguments");
   AVHOT_REQUIRE((frames_f32 != nullptr) != (frames_u8 != nullptr), AVHOT_ERR_INVALID,
                 "frame_hidden: exactly one of frames_f32 / frames_u8");
   AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
                 "frame_hidden: precision %d not built", precision);
   AVHOT_REQUIRE((long long)B * F <= 0x7fffffff / 2, AVHOT_ERR_INVALID, "frame_hidden: B*F too large for one call");
+  if (precision == AVHOT_PREC_TC && frames_u8 && (((size_t)B * F * h->frame_dim) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(frames_u8) & 15) == 0 && workspace &&
+      workspace_bytes >= avhot_frame_workspace_bytes(h, B, F, precision)) {
+    // u8 ingest on the tensor-core path: widen to fp32 k/255 once, then the same TF32 GEMM
+    const size_t n16 = (size_t)B * F * h->frame_dim / 16;
+    {
+      ProfScope prof("frame_u8_to_f32", as_stream(stream));
+      u8_to_f32_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, as_stream(stream)>>>(
+          frames_u8, reinterpret_cast<float*>(workspace), n16);
+      AVHOT_LAUNCH_CHECK();
+    }
+    frames_f32 = reinterpret_cast<const float*>(workspace);
+    frames_u8 = nullptr;
+  }
   if (precision == AVHOT_PREC_TC && frames_f32)
     return gemm_tf32_tc(frames_f32, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim, B * F,
                         h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");

@@ -17,6 +17,7 @@ from ._handles import Handle, Workspace
 
 _ws = Workspace()
 _ws_split = Workspace()
+_ws_frames = Workspace()
 
 
 class SequenceEncoder(nn.Module):
@@ -193,8 +194,8 @@ class FrameEncoder(nn.Module):
         lib = _lib.load()
         with torch.cuda.device(dev):
             h = self._get_handle(dev)
-            nbytes = lib.avhot_frame_workspace_bytes(h, B, F, self.precision)
-            ws = _ws.get(nbytes, dev)
+            nbytes = lib.avhot_frame_workspace_bytes(h, B, F, self.precision) if u8 else 0
+            ws = _ws_frames.get(nbytes, dev)
             _lib.check(lib.avhot_frame_hidden(h, None if u8 else _lib.ptr(x), _lib.ptr(x) if u8 else None,
                                               _lib.ptr(hid), B, F, self.precision, _lib.ptr(ws), ws.numel(),
                                               _lib.stream_ptr(dev)), "FrameEncoder.hidden")

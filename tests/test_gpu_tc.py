@@ -107,3 +107,12 @@ def test_fused_frontend_lstm_operand(pkg, dev, world):
     assert (fused == separate).all()
     short = pkg.synth.synth_audio(3, 5, SEED, dev, n_samples=8000)      # 51 frames: partial last tile of 16
     assert (enc.forward_from_waveform(short) == enc(pkg.logmel_mfcc(short))).all()
+
+
+def test_u8_ingest_tc(pkg, dev, world):
+    """uint8 pixels on the tensor-core path: widened to fp32 k/255 on the device, bit-identical to feeding fp32."""
+    m = make_model(pkg, dev, world).set_precision("tc")
+    enc = m.encoders["video"]
+    h32 = enc.hidden(torch.from_numpy(world["frames"]).to(dev))
+    h8 = enc.hidden(torch.from_numpy(world["frames_u8"]).to(dev))
+    assert (h32 == h8).all()
