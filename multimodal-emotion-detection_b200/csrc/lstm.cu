@@ -351,10 +351,8 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
         rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, xp, xf16, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
       } else if (l == 0) {
         const int ldx = pad8(3 * in + 2);
-        const long long n = (long long)Mp * ldx;
         {
           ProfScope prof("lstm_split3", s);
-          (void)n;
           const size_t smem = sizeof(float) * SPL_CB * SPL_TB * in;
           AVHOT_REQUIRE(smem <= 48 * 1024, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d too large", in);
           split3_f16_tm_kernel<<<dim3((unsigned)(Bp / SPL_CB), (unsigned)ceil_div(T, SPL_TB)), 256, smem, s>>>(

@@ -116,3 +116,20 @@ def test_u8_ingest_tc(pkg, dev, world):
     h32 = enc.hidden(torch.from_numpy(world["frames"]).to(dev))
     h8 = enc.hidden(torch.from_numpy(world["frames_u8"]).to(dev))
     assert (h32 == h8).all()
+
+
+@pytest.mark.parametrize("B", [1, 129])
+def test_tc_edge_batches(pkg, dev, world, B):
+    """One clip, and 128 + 1 clips (a second 128-clip tile with a single live row): tensor-core path == fp32 path
+    within tolerance for the whole MC pipeline, labels equal up to near-ties."""
+    m = make_model(pkg, dev, world)
+    pkg.MCDropoutUncertainty._set_dropout_train(m)
+    feats = {"audio": pkg.synth.synth_audio(B, 77, SEED, dev), "video": pkg.synth.synth_video(B, 77, SEED, dev)}
+    mask = pkg.synth.modality_mask(B, 77, 0.05, SEED, dev)
+    ref = m.mc_forward(feats, mask, num_samples=4, seed=SEED, clip0=77)
+    m.set_precision("tc")
+    got = m.mc_forward(feats, mask, num_samples=4, seed=SEED, clip0=77)
+    assert rel_err(got[0].cpu().numpy(), ref[0].cpu().numpy()) <= TC_REL_LOGITS
+    assert rel_err(got[1].cpu().numpy(), ref[1].cpu().numpy()) <= 5e-2
+    assert torch.isfinite(got[3]).all()
+    assert (got[2] != ref[2]).sum().item() <= max(1, B // 100)
