@@ -217,10 +217,15 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       mbar_wait(&sm.acc_full[b], use[b] & 1);
       tc_fence_after();
       uint32_t acc[4][8], cs[8];
+      tmem_st_wait();                          // the cell-state store of this thread's previous item has landed
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(tlane + (uint32_t)(b * RN + g * RCH + q * 8), acc[g]);
       tmem_ld8(tlane + 256u + (uint32_t)u0, cs);
       tmem_ld_wait();
+      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the activation math
+      tc_fence_before();
+      mbar_arrive(&sm.acc_empty[b]);
+      ++use[b];
       float hn[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -252,10 +257,6 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       if (live && h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
       // next use of this register buffer: the same quarter of chunk c + 2 (or of the next step)
       load_x(c + 2 < RNC ? t : t + 1, c + 2 < RNC ? c + 2 : c + 2 - RNC, xg);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&sm.acc_empty[b]);
-      ++use[b];
       fence_proxy_async_smem();                // this thread's part of k-block c/2 of h_t is written
       mbar_arrive(&sm.h_ready[c >> 1]);
     };
