@@ -185,7 +185,7 @@ def run_b200_arm(args):
     B, T = args.batch, args.passes
     sd_np = osynth.synth_weights(SEED)
     model = pkg.AVHotPath("hybrid")
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items() if not k.startswith("fusion_head.")},
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in osynth.state_dict_for("hybrid", sd_np).items()},
                           strict=True)
     model = model.to(dev).eval().set_precision(args.precision)
     pkg.MCDropoutUncertainty._set_dropout_train(model)            # what MCDropoutUncertainty.forward does (:58-59)

@@ -224,6 +224,45 @@ int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
 /* workspace (optional, avhot_fusion_workspace_bytes): lets the hybrid path compute the pass-invariant
  * half of modality 0 once per clip when z_rows_per_clip[0] == 1 (same results, fewer FLOPs). */
 
+/* ---- SURVEY.md 8(f) "next": the other fusion heads behind build_fusion_model and the calibration metrics ------ */
+typedef struct avhot_head* avhot_head_t;
+/* src/fusion.py:19-138  EarlyFusion: mlp = Linear(sum dims -> D), LayerNorm, ReLU, Dropout, Linear(D -> D), LayerNorm,
+ * ReLU, Dropout, Linear(D -> C)  (state-dict keys mlp.0, mlp.1, mlp.4, mlp.5, mlp.8) */
+typedef struct {
+  int num_modalities, hidden_dim, num_classes;
+  int modality_dim[AVHOT_MAX_MODALITIES];
+  const float *w0, *b0, *ln1_w, *ln1_b, *w4, *b4, *ln5_w, *ln5_b, *w8, *b8;
+} avhot_early_desc;
+/* src/fusion.py:141-248  LateFusion: classifiers.<m> = Linear(dim_m -> D), ReLU, Dropout, Linear(D -> C); fusion_logits (M) */
+typedef struct {
+  int num_modalities, hidden_dim, num_classes;
+  int modality_dim[AVHOT_MAX_MODALITIES];
+  const float* w0[AVHOT_MAX_MODALITIES];
+  const float* b0[AVHOT_MAX_MODALITIES];
+  const float* w3[AVHOT_MAX_MODALITIES];
+  const float* b3[AVHOT_MAX_MODALITIES];
+  const float* fusion_logits;
+} avhot_late_desc;
+int avhot_early_create(const avhot_early_desc* desc, avhot_head_t* out, avhot_stream_t stream);
+int avhot_late_create(const avhot_late_desc* desc, avhot_head_t* out, avhot_stream_t stream);
+void avhot_head_destroy(avhot_head_t h);
+/* forward(modality_features, modality_mask) for R = B*T rows; z / z_rows_per_clip / mask as in avhot_fusion_forward.
+ * present_mask: bit m set = modality m was given (LateFusion gives a missing modality zero logits, :222-225;
+ * EarlyFusion callers pass zeros, :120-121).  per_modality_logits: (M, R, C), LateFusion only, may be NULL.
+ * Dropout (p > 0): sites AVHOT_SITE_EARLY0 / EARLY1 (mlp.3, mlp.7) and AVHOT_SITE_LATE + m (classifiers.<m>.2). */
+int avhot_head_forward(avhot_head_t h, const float* const* z_host_array, const int* z_rows_per_clip_host,
+                       int present_mask, const float* mask, float* logits, float* per_modality_logits,
+                       int B, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                       avhot_stream_t stream);
+/* src/uncertainty.py:88-183, :512-544  calibration statistics, accumulated into acc (device, doubles, caller-zeroed):
+ * [0,nb) bin counts, [nb,2nb) sum of confidences, [2nb,3nb) correct counts, [3nb] NLL sum (logits given),
+ * [3nb+1] correct total, [3nb+2] samples.  Either logits (N, C) - confidence = max softmax, prediction = argmax,
+ * NLL = cross-entropy - or (confidences, predictions) as CalibrationMetrics' static methods take them.
+ * bin_edges: (num_bins + 1) fp32, torch.linspace(0, 1, num_bins + 1); last bin is closed on the right. */
+int avhot_calibration_accumulate(const float* logits, const float* confidences, const int64_t* predictions,
+                                 const int64_t* labels, long long N, int C, const float* bin_edges,
+                                 int num_bins, double* acc, avhot_stream_t stream);
+
 /* ---- a8: src/uncertainty.py:17-86  MCDropoutUncertainty statistics ------------------ */
 /* logits (B, T, C) -> mean_logits (B, C), uncertainty (B) = mean_c Var_t softmax (population
  * variance, src/uncertainty.py:77-84), labels (B) = argmax mean_logits (first max wins,
@@ -237,7 +276,10 @@ int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
 #define AVHOT_SITE_FRAME_POOL 1u
 #define AVHOT_SITE_GATE 2u
 #define AVHOT_SITE_MODMASK 3u
+#define AVHOT_SITE_EARLY0 4u
+#define AVHOT_SITE_EARLY1 5u
 #define AVHOT_SITE_ATTN 16u
+#define AVHOT_SITE_LATE 32u
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libavhot.so")
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 PREC_FP32, PREC_BF16X3, PREC_TC = 0, 1, 2
 SITE_FRAME_MLP, SITE_FRAME_POOL, SITE_GATE, SITE_MODMASK, SITE_ATTN = 0, 1, 2, 3, 16
+SITE_EARLY0, SITE_EARLY1, SITE_LATE = 4, 5, 32
 MAX_MODALITIES = 4
 
 c_float_p = C.c_void_p  # device pointers travel as integers
@@ -50,6 +51,20 @@ class FusionDesc(C.Structure):
                 ("attn", XattnDesc * MAX_MODALITIES)] + [(n, C.c_void_p) for n in (
                     "pre_ln_w", "pre_ln_b", "post_ln_w", "post_ln_b",
                     "gate0_w", "gate0_b", "gate3_w", "gate3_b", "cls_w", "cls_b")]
+
+
+class EarlyDesc(C.Structure):
+    _fields_ = [("num_modalities", C.c_int), ("hidden_dim", C.c_int), ("num_classes", C.c_int),
+                ("modality_dim", C.c_int * MAX_MODALITIES)] + [(n, C.c_void_p) for n in (
+                    "w0", "b0", "ln1_w", "ln1_b", "w4", "b4", "ln5_w", "ln5_b", "w8", "b8")]
+
+
+class LateDesc(C.Structure):
+    _fields_ = [("num_modalities", C.c_int), ("hidden_dim", C.c_int), ("num_classes", C.c_int),
+                ("modality_dim", C.c_int * MAX_MODALITIES),
+                ("w0", C.c_void_p * MAX_MODALITIES), ("b0", C.c_void_p * MAX_MODALITIES),
+                ("w3", C.c_void_p * MAX_MODALITIES), ("b3", C.c_void_p * MAX_MODALITIES),
+                ("fusion_logits", C.c_void_p)]
 
 
 class HeadDesc(C.Structure):
@@ -99,6 +114,11 @@ PROTOTYPES = {
     "avhot_fusion_workspace_bytes": (_SZ, [_P, _I, _I]),
     "avhot_fusion_forward": (_I, [_P, C.POINTER(_P), C.POINTER(_I), _P, _P, _P, _P, _P, _I, _I, _F,
                                   _U64, _U64, _U32, _I, _P, _SZ, _P]),
+    "avhot_early_create": (_I, [C.POINTER(EarlyDesc), C.POINTER(_P), _P]),
+    "avhot_late_create": (_I, [C.POINTER(LateDesc), C.POINTER(_P), _P]),
+    "avhot_head_destroy": (None, [_P]),
+    "avhot_head_forward": (_I, [_P, C.POINTER(_P), C.POINTER(_I), _I, _P, _P, _P, _I, _I, _F, _U64, _U64, _U32, _P]),
+    "avhot_calibration_accumulate": (_I, [_P, _P, _P, _P, C.c_longlong, _I, _P, _I, _P, _P]),
     "avhot_mc_reduce": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
 }
 

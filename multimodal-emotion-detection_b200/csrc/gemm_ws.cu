@@ -125,8 +125,10 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int j = 0; j < 32; ++j) cbase[(size_t)(c + 32 + j) * WBM] = __uint_as_float(r1[j]);
         }
       } else {
-        // fp16 output: columns (2j, 2j + 1) of a row packed into one half2 -> [M / 128][N / 2][128] half2
-        __half2* cbase = reinterpret_cast<__half2*>(C) + ((size_t)(row / WBM) * (ldc / 2) + n0 / 2) * WBM + (quarter * 32 + lane);
+        // fp16 output: groups of 8 consecutive columns of a row packed into 16 bytes ->
+        // [M / 128][N / 8][128 rows][8 halves]: a warp stores 512 contiguous bytes per instruction and the consumer
+        // (lstm_tc.cu, thread = row) reads the 8 units of a gate with one 128-bit load
+        uint4* cbase = reinterpret_cast<uint4*>(C) + ((size_t)(row / WBM) * (ldc / 8) + n0 / 8) * WBM + (quarter * 32 + lane);
 #pragma unroll
         for (int c = 0; c < WBN; c += 64) {
           uint32_t r0[32], r1[32];
@@ -134,11 +136,25 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 2)
-            cbase[(size_t)((c + j) / 2) * WBM] = __floats2half2_rn(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2)
-            cbase[(size_t)((c + 32 + j) / 2) * WBM] = __floats2half2_rn(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+            for (int e = 0; e < 4; ++e) {
+              const __half2 v = __floats2half2_rn(__uint_as_float(r0[j + 2 * e]), __uint_as_float(r0[j + 2 * e + 1]));
+              pk[e] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            cbase[(size_t)((c + j) / 8) * WBM] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 v = __floats2half2_rn(__uint_as_float(r1[j + 2 * e]), __uint_as_float(r1[j + 2 * e + 1]));
+              pk[e] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            cbase[(size_t)((c + 32 + j) / 8) * WBM] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
       }
       tc_fence_before();
@@ -153,7 +169,7 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }  // namespace tc
 
 // a, w fp16 row-major (K contiguous); M % 128 == 0 (caller pads); N % 128 == 0; K <= 320;
-// c in the tile-transposed layout: fp32 [M / 128][N = ldc][128], or fp16 column pairs [M / 128][N / 2][128] half2
+// c in the tile-transposed layout: fp32 [M / 128][N = ldc][128], or fp16 column octets [M / 128][N / 8][128][8]
 int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, void* c_out, bool out_f16, int ldc, int M, int N,
                 int K, cudaStream_t s, const char* prof_name) {
   float* c = reinterpret_cast<float*>(c_out);

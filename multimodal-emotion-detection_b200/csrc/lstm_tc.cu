@@ -183,36 +183,40 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     __half* hrow = h_seq ? h_seq + ((size_t)blockIdx.x * RB + r) * h_pitch : nullptr;
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
 
-    auto load_x = [&](int t, int c, float (&xg)[4][8]) {      // 4 gates x 8 units, coalesced across the 32 clips
+    // xp registers hold what was loaded, unconverted: the loads of the item two chunks ahead stay in flight until
+    // the values are used (converting at load time made every thread wait for its own prefetch: a third of all
+    // stall samples in the r1y profile).  fp32 xp: 4 gates x 8 floats; fp16 xp: 4 gates x one 128-bit octet.
+    constexpr int XR = XP16 ? 16 : 32;
+    auto load_x = [&](int t, int c, uint32_t (&xr)[XR]) {     // coalesced across the 32 clips of the warp
       if (t >= T) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xg[g][j] = 0.f;
+        for (int i = 0; i < XR; ++i) xr[i] = 0u;
       } else if (!XP16) {
         const float* src = xcol + ((size_t)t * n_ct * (4 * RH) + c * RCH + q * 8) * RB;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) xg[g][j] = ldg_stream(src + (size_t)(g * RH + j) * RB);
+          for (int j = 0; j < 8; ++j) xr[g * 8 + j] = __float_as_uint(ldg_stream(src + (size_t)(g * RH + j) * RB));
       } else {
-        // fp16 xp (layers > 0): column pairs packed as half2, [t][clip tile][2H pairs][128 clips]
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(xp) + (size_t)blockIdx.x * (2 * RH) * RB + r +
-                              ((size_t)t * n_ct * (2 * RH) + (c * RCH + q * 8) / 2) * RB;
+        // fp16 xp: [t][clip tile][4H / 8 octets][128 clips][8 halves] (gemm_ws.cu)
+        const uint4* src = reinterpret_cast<const uint4*>(xp) + ((size_t)t * n_ct + blockIdx.x) * (4 * RH / 8) * RB + r +
+                           (size_t)((c * RCH + q * 8) / 8) * RB;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            uint32_t u;
-            asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(u) : "l"(src + (size_t)((g * RH + j) / 2) * RB));
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
-            xg[g][j] = f.x;
-            xg[g][j + 1] = f.y;
-          }
+        for (int g = 0; g < 4; ++g) {
+          const uint4* p = src + (size_t)(g * RH / 8) * RB;
+          asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(xr[4 * g]), "=r"(xr[4 * g + 1]), "=r"(xr[4 * g + 2]), "=r"(xr[4 * g + 3])
+                       : "l"(p));
+        }
       }
     };
+    auto xval = [&](const uint32_t (&xr)[XR], int g, int j) -> float {
+      if (!XP16) return __uint_as_float(xr[g * 8 + j]);
+      const __half2 h2 = *reinterpret_cast<const __half2*>(&xr[4 * g + (j >> 1)]);
+      return (j & 1) ? __high2float(h2) : __low2float(h2);
+    };
     uint32_t use[2] = {0, 0};
-    auto run = [&](int t, int c, float (&xg)[4][8]) {
+    auto run = [&](int t, int c, uint32_t (&xg)[XR]) {
       const int b = c & 1, u0 = c * RCH + q * 8;
       mbar_wait(&sm.acc_full[b], use[b] & 1);
       tc_fence_after();
@@ -229,10 +233,10 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       float hn[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float ig = act_sigmoid<ACT>(__uint_as_float(acc[0][j]) + xg[0][j]);
-        const float fg = act_sigmoid<ACT>(__uint_as_float(acc[1][j]) + xg[1][j]);
-        const float gg = act_tanh<ACT>(__uint_as_float(acc[2][j]) + xg[2][j]);
-        const float og = act_sigmoid<ACT>(__uint_as_float(acc[3][j]) + xg[3][j]);
+        const float ig = act_sigmoid<ACT>(__uint_as_float(acc[0][j]) + xval(xg, 0, j));
+        const float fg = act_sigmoid<ACT>(__uint_as_float(acc[1][j]) + xval(xg, 1, j));
+        const float gg = act_tanh<ACT>(__uint_as_float(acc[2][j]) + xval(xg, 2, j));
+        const float og = act_sigmoid<ACT>(__uint_as_float(acc[3][j]) + xval(xg, 3, j));
         const float cn = fmaf(fg, __uint_as_float(cs[j]), ig * gg);
         cs[j] = __float_as_uint(cn);
         hn[j] = og * act_tanh<ACT>(cn);
@@ -260,7 +264,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       fence_proxy_async_smem();                // this thread's part of k-block c/2 of h_t is written
       mbar_arrive(&sm.h_ready[c >> 1]);
     };
-    float xa[4][8], xb[4][8];
+    uint32_t xa[XR], xb[XR];
     load_x(0, 0, xa);
     load_x(0, 1, xb);
 #pragma unroll 1

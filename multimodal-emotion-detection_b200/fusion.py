@@ -1,5 +1,6 @@
-"""Drop-in for the cross-modal path of src/fusion.py: HybridFusion and build_fusion_model, plus the live
-baseline head of src/train.py:81-85 as ConcatHead.  Same signatures, parameter names and return values."""
+"""Drop-in for src/fusion.py: HybridFusion (the cross-modal hot path), EarlyFusion, LateFusion and
+build_fusion_model, plus the live baseline head of src/train.py:81-85 as ConcatHead.  Same signatures, parameter
+names and return values."""
 from __future__ import annotations
 
 import ctypes as C
@@ -158,6 +159,183 @@ class HybridFusion(nn.Module):
         return logits
 
 
+class _HeadBase(nn.Module):
+    """Shared run()/mask plumbing of EarlyFusion / LateFusion (avhot_head_forward)."""
+
+    def _drop_p(self) -> float:
+        mods = [m for m in self.modules() if isinstance(m, nn.Dropout)]
+        modes = {m.training for m in mods}
+        if len(modes) != 1:
+            raise ValueError(f"{type(self).__name__} dropout modules must all be in the same mode")
+        ps = {float(m.p) for m in mods}
+        if len(ps) != 1:
+            raise ValueError(f"{type(self).__name__} dropout modules must share one p (one ctor argument)")
+        return ps.pop() if modes.pop() else 0.0
+
+    @torch.no_grad()
+    def run(self, zs, rows_per_clip, mask, B: int, passes: int, p: float, seed: int, clip0: int, t0: int,
+            present: Optional[int] = None, want_per_modality: bool = False):
+        """logits (B, passes, C) [and per-modality logits (M, B, passes, C)] for embeddings zs[m] of
+        (B * rows_per_clip[m], dim_m); zs[m] may be None for a modality that was not given (LateFusion)."""
+        dev = next(z for z in zs if z is not None).device
+        M = len(zs)
+        if present is None:
+            present = sum(1 << m for m in range(M) if zs[m] is not None)
+        logits = torch.empty(B, passes, self.num_classes, device=dev, dtype=torch.float32)
+        per = torch.empty(M, B, passes, self.num_classes, device=dev, dtype=torch.float32) if want_per_modality else None
+        if B > 0:
+            arr = (C.c_void_p * M)(*[None if z is None else z.data_ptr() for z in zs])
+            rpc = (C.c_int * M)(*rows_per_clip)
+            with torch.cuda.device(dev):
+                h = self._get_handle(dev)
+                _lib.check(_lib.load().avhot_head_forward(h, arr, rpc, present, _lib.ptr(mask), _lib.ptr(logits),
+                                                          _lib.ptr(per), B, passes, float(p), seed, clip0, t0,
+                                                          _lib.stream_ptr(dev)),
+                           f"{type(self).__name__}.forward")
+        return logits, per
+
+    def _ref_and_mask(self, modality_features, modality_mask):
+        ref = None
+        for name in self.modality_names:                                                 # src/fusion.py:93-99
+            if name in modality_features:
+                ref = modality_features[name]
+                break
+        if ref is None:
+            raise ValueError("No expected modalities were provided.")
+        if ref.dim() != 2:
+            raise ValueError(f"Expected rank-2 modality tensors [B, D], got {tuple(ref.shape)}.")
+        dev = _lib.require_cuda(ref)
+        _lib.check_device(dev)
+        B = ref.size(0)
+        mask_f = None
+        if modality_mask is not None:                                                    # :103-106
+            if modality_mask.dim() != 2 or modality_mask.size(0) != B or \
+                    modality_mask.size(1) != len(self.modality_names):
+                raise ValueError(f"modality_mask must be [B, {len(self.modality_names)}]")
+            mask_f = _lib.f32c(modality_mask.to(device=dev))
+        return dev, B, mask_f
+
+
+class EarlyFusion(_HeadBase):
+    """src/fusion.py:19-138: concat(mask_m * z_m) -> Linear-LayerNorm-ReLU-Dropout x2 -> Linear (state-dict keys
+    mlp.0, mlp.1, mlp.4, mlp.5, mlp.8)."""
+
+    def __init__(self, modality_dims: Dict[str, int], hidden_dim: int = 256, num_classes: int = 11,
+                 dropout: float = 0.1, num_heads: int = 4, **kwargs):
+        super().__init__()
+        self._num_heads = num_heads
+        self.modality_names = list(modality_dims.keys())
+        self.modality_dims = dict(modality_dims)
+        self.hidden_dim, self.num_classes = hidden_dim, num_classes
+        concat_dim = sum(modality_dims.values())
+        self.mlp = nn.Sequential(                                                        # :60-72
+            nn.Linear(concat_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
+            nn.Linear(hidden_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
+            nn.Linear(hidden_dim, num_classes))
+        self._handle = Handle("avhot_head_destroy")
+
+    def _get_handle(self, dev):
+        ps = [p for p in self.parameters()]
+
+        def create():
+            if len(self.modality_names) > _lib.MAX_MODALITIES:
+                raise ValueError(f"at most {_lib.MAX_MODALITIES} modalities")
+            ts = [_lib.f32c(p.detach()) for p in ps]
+            _lib.require_cuda(*ts)
+            d = _lib.EarlyDesc()
+            d.num_modalities, d.hidden_dim, d.num_classes = len(self.modality_names), self.hidden_dim, self.num_classes
+            for i, n in enumerate(self.modality_names):
+                d.modality_dim[i] = self.modality_dims[n]
+            (d.w0, d.b0, d.ln1_w, d.ln1_b, d.w4, d.b4, d.ln5_w, d.ln5_b, d.w8, d.b8) = [t.data_ptr() for t in ts]
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_early_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)), "EarlyFusion")
+            torch.cuda.current_stream(dev).synchronize()       # the handle copies from `ts` on the stream
+            return out.value
+
+        return self._handle.get(ps, create)
+
+    def forward(self, modality_features: Dict[str, torch.Tensor],
+                modality_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev, B, mask_f = self._ref_and_mask(modality_features, modality_mask)
+        zs = []
+        for name in self.modality_names:
+            Dm = self.modality_dims[name]
+            x = modality_features.get(name)
+            if x is None:                                                                # :120-121
+                x = torch.zeros(B, Dm, device=dev, dtype=torch.float32)
+            elif x.dim() != 2 or x.size(0) != B or x.size(1) != Dm:
+                raise ValueError(f"Modality '{name}' must be [B, {Dm}], got {tuple(x.shape)}")
+            zs.append(_lib.f32c(x.to(dev)))
+        seed, t, clip0 = _rng.current()
+        logits, _ = self.run(zs, [1] * len(zs), mask_f, B, 1, self._drop_p(), seed, clip0, t)
+        return logits[:, 0, :]
+
+
+class LateFusion(_HeadBase):
+    """src/fusion.py:141-248: per-modality Linear-ReLU-Dropout-Linear classifiers; softmax(fusion_logits) times the
+    mask, renormalised; returns (fused_logits, {name: per-modality logits})."""
+
+    def __init__(self, modality_dims: Dict[str, int], hidden_dim: int = 256, num_classes: int = 11,
+                 dropout: float = 0.1, num_heads: int = 4, **kwargs):
+        super().__init__()
+        self._num_heads = num_heads
+        self.modality_names = list(modality_dims.keys())
+        self.num_modalities = len(self.modality_names)
+        self.modality_dims = dict(modality_dims)
+        self.hidden_dim, self.num_classes = hidden_dim, num_classes
+        self.classifiers = nn.ModuleDict({                                               # :180-188
+            name: nn.Sequential(nn.Linear(dim, hidden_dim), nn.ReLU(), nn.Dropout(dropout),
+                                nn.Linear(hidden_dim, num_classes))
+            for name, dim in modality_dims.items()})
+        self.fusion_logits = nn.Parameter(torch.zeros(self.num_modalities))              # :189
+        self._handle = Handle("avhot_head_destroy")
+
+    def _get_handle(self, dev):
+        ps = [p for p in self.parameters()]
+
+        def create():
+            if self.num_modalities > _lib.MAX_MODALITIES:
+                raise ValueError(f"at most {_lib.MAX_MODALITIES} modalities")
+            keep = []
+
+            def dp(t):
+                t = _lib.f32c(t.detach())
+                _lib.require_cuda(t)
+                keep.append(t)
+                return t.data_ptr()
+
+            d = _lib.LateDesc()
+            d.num_modalities, d.hidden_dim, d.num_classes = self.num_modalities, self.hidden_dim, self.num_classes
+            for i, n in enumerate(self.modality_names):
+                seq = self.classifiers[n]
+                d.modality_dim[i] = self.modality_dims[n]
+                d.w0[i], d.b0[i], d.w3[i], d.b3[i] = dp(seq[0].weight), dp(seq[0].bias), dp(seq[3].weight), dp(seq[3].bias)
+            d.fusion_logits = dp(self.fusion_logits)
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_late_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)), "LateFusion")
+            torch.cuda.current_stream(dev).synchronize()
+            return out.value
+
+        return self._handle.get(ps, create)
+
+    def forward(self, modality_features: Dict[str, torch.Tensor], modality_mask: Optional[torch.Tensor] = None):
+        dev, B, mask_f = self._ref_and_mask(modality_features, modality_mask)
+        if mask_f is not None and mask_f.shape != (B, self.num_modalities):
+            raise ValueError(f"modality_mask must be [B, {self.num_modalities}]")
+        zs = []
+        for name in self.modality_names:
+            x = modality_features.get(name)
+            if x is not None:
+                if x.dim() != 2 or x.size(0) != B or x.size(1) != self.modality_dims[name]:
+                    raise ValueError(f"Modality '{name}' must be [B, {self.modality_dims[name]}], got {tuple(x.shape)}")
+                x = _lib.f32c(x.to(dev))
+            zs.append(x)                                                                 # None: zero logits (:222-225)
+        seed, t, clip0 = _rng.current()
+        logits, per = self.run(zs, [1] * len(zs), mask_f, B, 1, self._drop_p(), seed, clip0, t,
+                               want_per_modality=True)
+        return logits[:, 0, :], {n: per[i, :, 0, :] for i, n in enumerate(self.modality_names)}
+
+
 class ConcatHead(nn.Sequential):
     """The live fusion_head of MultimodalFusionModule: Linear -> ReLU -> Linear on the concatenated encoder
     outputs (src/train.py:81-85, :153-164).  State-dict keys 0.weight, 0.bias, 2.weight, 2.bias."""
@@ -211,11 +389,11 @@ class ConcatHead(nn.Sequential):
 
 
 def build_fusion_model(fusion_type: str, modality_dims: Dict[str, int], num_classes: int, **kwargs) -> nn.Module:
-    """src/fusion.py:659-702.  'hybrid' is the cross-modal path; 'early' / 'late' are valid in the reference and
-    not built here."""
-    if fusion_type == "hybrid":
-        return HybridFusion(modality_dims=modality_dims, num_classes=num_classes, **kwargs)
-    if fusion_type in ("early", "late"):
-        raise ValueError(f"fusion type '{fusion_type}' exists in the reference but is not built in this library "
-                         "(hot path = 'hybrid')")
-    raise ValueError(f"Unknown fusion type: {fusion_type}")                              # :696
+    """src/fusion.py:659-702.  'hybrid' is the cross-modal path; 'early' / 'late' are SURVEY.md 8(f) rows;
+    'uncertainty' (LateFusionWithUncertainty) exists in the reference and is not built here."""
+    if fusion_type == "uncertainty":
+        raise ValueError("fusion type 'uncertainty' exists in the reference but is not built in this library")
+    fusion_classes = {"early": EarlyFusion, "late": LateFusion, "hybrid": HybridFusion}
+    if fusion_type not in fusion_classes:
+        raise ValueError(f"Unknown fusion type: {fusion_type}")                          # :696
+    return fusion_classes[fusion_type](modality_dims=modality_dims, num_classes=num_classes, **kwargs)

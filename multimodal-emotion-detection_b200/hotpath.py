@@ -1,8 +1,8 @@
 """The per-clip audio-visual inference hot path as one module.
 
 AVHotPath mirrors MultimodalFusionModule (src/train.py:34-164) without Lightning: ``encoders`` (ModuleDict, in
-``modalities`` order, :55-66), then either ``fusion_model`` = HybridFusion (the commented composition :69-76,
-:138-147) or ``fusion_head`` = Linear-ReLU-Linear on the concatenation (:81-85, :153-164, the live path, which
+``modalities`` order, :55-66), then either ``fusion_model`` = HybridFusion / EarlyFusion / LateFusion (the commented
+composition :69-76, :138-147, `model.fusion_type`) or ``fusion_head`` = Linear-ReLU-Linear on the concatenation (:81-85, :153-164, the live path, which
 ignores the mask) - same attribute names, so state-dict keys match SURVEY.md Appendix A.
 
 forward(features, mask)   one pass, like the reference's forward.
@@ -39,7 +39,7 @@ class AVHotPath(nn.Module):
                  output_dim: int = 128, hidden_dim: int = 256, num_heads: int = 4, num_classes: int = 8,
                  dropout: float = 0.3, precision: str = "fp32"):
         super().__init__()
-        if head not in ("hybrid", "concat"):
+        if head not in ("hybrid", "concat", "early", "late"):
             raise ValueError(f"Unknown head: {head}")
         self.head = head
         self.modalities = list(modalities)
@@ -51,8 +51,8 @@ class AVHotPath(nn.Module):
             self.encoders[m] = build_encoder(modality=m, input_dim=cfg.get("input_dim", 64), output_dim=output_dim,
                                              encoder_config=cfg)
             dims[m] = output_dim
-        if head == "hybrid":
-            self.fusion_model = build_fusion_model("hybrid", dims, num_classes, hidden_dim=hidden_dim,
+        if head != "concat":                                                             # hybrid / early / late
+            self.fusion_model = build_fusion_model(head, dims, num_classes, hidden_dim=hidden_dim,
                                                    num_heads=num_heads, dropout=dropout)  # :69-76
         else:
             self.fusion_head = ConcatHead(output_dim * len(self.modalities), hidden_dim, num_classes,
@@ -111,6 +111,14 @@ class AVHotPath(nn.Module):
                     raise ValueError("mask must be (B, 2)")
             p_f = fm._drop_p() if stochastic else 0.0
             logits, _, _, _ = fm.run(zs, rpc, mask_f, B, passes, p_f, seed, clip0, t0)
+        elif self.head in ("early", "late"):
+            fm = self.fusion_model
+            mask_f = None
+            if mask is not None:
+                mask_f = torch.as_tensor(mask).to(device=dev, dtype=torch.float32).contiguous()
+                if mask_f.shape != (B, 2):
+                    raise ValueError("mask must be (B, 2)")
+            logits, _ = fm.run(zs, rpc, mask_f, B, passes, fm._drop_p() if stochastic else 0.0, seed, clip0, t0)
         else:
             logits = self.fusion_head.run(zs, rpc, B, passes)                             # mask ignored (F2)
         return logits                                                                     # (B, passes, C)

@@ -12,7 +12,7 @@ Two execution paths, same results:
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Dict, Tuple
 
 import torch
 import torch.nn as nn
@@ -75,3 +75,104 @@ class MCDropoutUncertainty(nn.Module):
             else:
                 self.model.eval()
         return mean, unc
+
+
+# ---- calibration metrics (src/uncertainty.py:88-183, :471-544) on the GPU ---------------------
+def calibration_accumulate(acc: torch.Tensor, labels: torch.Tensor, num_bins: int, logits: torch.Tensor = None,
+                           confidences: torch.Tensor = None, predictions: torch.Tensor = None) -> torch.Tensor:
+    """Adds one batch to the (3 * num_bins + 3,) float64 CUDA accumulator of avhot_calibration_accumulate:
+    [bin counts | sum of confidences | correct counts | NLL sum, correct total, samples]."""
+    dev = _lib.require_cuda(acc, labels, logits, confidences, predictions)
+    _lib.check_device(dev)
+    labels = labels.long().contiguous()
+    n = labels.shape[0]
+    edges = torch.linspace(0, 1, steps=num_bins + 1, device=dev)                          # :118
+    cn = 0
+    if logits is not None:
+        logits = _lib.f32c(logits)
+        assert logits.ndim == 2 and logits.shape[0] == n, "logits (N,C), labels (N,)"
+        cn = logits.shape[1]
+    else:
+        confidences = _lib.f32c(confidences.detach())
+        predictions = predictions.detach().long().contiguous()
+    if n > 0:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().avhot_calibration_accumulate(
+                _lib.ptr(logits), _lib.ptr(confidences), _lib.ptr(predictions), _lib.ptr(labels), n, cn,
+                _lib.ptr(edges), num_bins, _lib.ptr(acc), _lib.stream_ptr(dev)), "calibration")
+    return acc
+
+
+def calibration_finalize(acc: torch.Tensor, num_bins: int) -> Dict[str, float]:
+    """ECE / MCE / NLL / accuracy from the accumulator, exactly as the reference combines its per-bin statistics
+    (empty bins skipped, :132-152; ECE :163-171; MCE :183; NLL = sum / max(1, N), :533)."""
+    a = acc.detach().cpu().double()
+    cnt, conf, cor = a[:num_bins], a[num_bins:2 * num_bins], a[2 * num_bins:3 * num_bins]
+    nll_sum, cor_tot, n = float(a[3 * num_bins]), float(a[3 * num_bins + 1]), float(a[3 * num_bins + 2])
+    tot = float(cnt.sum())
+    ece, mce = 0.0, 0.0
+    for b in range(num_bins):
+        if cnt[b] > 0:
+            gap = abs(float(cor[b] / cnt[b]) - float(conf[b] / cnt[b]))
+            ece += gap * float(cnt[b]) / tot
+            mce = max(mce, gap)
+    return {"ece": ece, "mce": mce, "nll": nll_sum / max(1.0, n), "accuracy": cor_tot / n if n else 0.0}
+
+
+class CalibrationMetrics:
+    """src/uncertainty.py:88-202 with the binning done by one CUDA histogram kernel (inputs must be CUDA tensors)."""
+
+    @staticmethod
+    def _acc(confidences, predictions, labels, num_bins):
+        assert confidences.ndim == predictions.ndim == labels.ndim == 1, "Use 1D tensors"             # :108
+        assert confidences.shape[0] == predictions.shape[0] == labels.shape[0], "Mismatched shapes"   # :109
+        acc = torch.zeros(3 * num_bins + 3, device=confidences.device, dtype=torch.float64)
+        return calibration_accumulate(acc, labels, num_bins, confidences=confidences, predictions=predictions)
+
+    @staticmethod
+    def expected_calibration_error(confidences, predictions, labels, num_bins: int = 15) -> float:
+        return calibration_finalize(CalibrationMetrics._acc(confidences, predictions, labels, num_bins), num_bins)["ece"]
+
+    @staticmethod
+    def maximum_calibration_error(confidences, predictions, labels, num_bins: int = 15) -> float:
+        return calibration_finalize(CalibrationMetrics._acc(confidences, predictions, labels, num_bins), num_bins)["mce"]
+
+    @staticmethod
+    def negative_log_likelihood(logits: torch.Tensor, labels: torch.Tensor) -> float:
+        assert logits.ndim == 2 and labels.ndim == 1, "logits (N,C), labels (N,)"                      # :197
+        acc = torch.zeros(3 + 3, device=logits.device, dtype=torch.float64)
+        return calibration_finalize(calibration_accumulate(acc, labels, 1, logits=logits), 1)["nll"]
+
+
+def compute_calibration_metrics(model: nn.Module, dataloader, device: str = "cuda", num_bins: int = 15) -> Dict[str, float]:
+    """src/uncertainty.py:471-544: ECE, MCE, NLL, accuracy over a dataloader of (inputs, labels) or
+    (features_dict, labels, mask) batches; models returning (logits, aux) are unwrapped.  The per-batch statistics
+    stay on the GPU (one histogram kernel per batch into a float64 accumulator); one D2H copy at the end."""
+    model.eval().to(device)
+    acc = None
+    for batch in dataloader:
+        if isinstance(batch, (tuple, list)):
+            if len(batch) == 2:
+                inputs, labels = batch
+                mask = None
+            elif len(batch) == 3:
+                inputs, labels, mask = batch
+            else:
+                raise ValueError(f"Unexpected batch shape: len={len(batch)}")
+        else:
+            raise ValueError("Batch must be a tuple/list")
+        labels = labels.to(device)
+        if isinstance(inputs, dict):
+            inputs = {k: v.to(device) for k, v in inputs.items()}
+            mask = mask.to(device) if mask is not None else None
+            logits = model(inputs, mask)
+        else:
+            logits = model(inputs.to(device))
+        if isinstance(logits, (tuple, list)):
+            logits = logits[0]
+        if acc is None:
+            acc = torch.zeros(3 * num_bins + 3, device=logits.device, dtype=torch.float64)
+        calibration_accumulate(acc, labels, num_bins, logits=logits)
+    if acc is None:
+        return {"ece": 0.0, "mce": 0.0, "nll": 0.0, "accuracy": 0.0}
+    return calibration_finalize(acc, num_bins)

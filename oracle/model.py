@@ -233,6 +233,77 @@ def hybrid_fusion(feats: Dict[str, torch.Tensor], mask, sd, prefix="fusion_model
     return logits
 
 
+def early_fusion(feats: Dict[str, torch.Tensor], mask, sd, prefix="fusion_model.",
+                 modalities: Sequence[str] = ("audio", "video"), ctx: Optional[DropCtx] = None):
+    """EarlyFusion.forward.  src/fusion.py:74-138: features multiplied by their mask column (no missing-modality
+    embeddings exist in the reference, :124-128 falls to `x = m * x`), concatenated, then
+    Linear-LN-ReLU-Dropout-Linear-LN-ReLU-Dropout-Linear (:60-72)."""
+    parts = []
+    for i, m in enumerate(modalities):
+        x = feats[m]
+        if mask is not None:
+            x = torch.as_tensor(mask).to(x.dtype)[:, i:i + 1] * x
+        parts.append(x)
+    h = torch.cat(parts, dim=-1)
+    p = ctx.p_fusion if ctx is not None else 0.0
+    for lin, ln, site in (("0", "1", px.SITE_EARLY0), ("4", "5", px.SITE_EARLY1)):
+        h = _lin(h, sd, f"{prefix}mlp.{lin}")
+        h = torch.relu(_layer_norm(h, sd[f"{prefix}mlp.{ln}.weight"], sd[f"{prefix}mlp.{ln}.bias"]))
+        if ctx is not None:
+            h = ctx.apply(h, site, p)
+    return _lin(h, sd, prefix + "mlp.8")
+
+
+def late_fusion(feats: Dict[str, torch.Tensor], mask, sd, prefix="fusion_model.",
+                modalities: Sequence[str] = ("audio", "video"), ctx: Optional[DropCtx] = None):
+    """LateFusion.forward.  src/fusion.py:190-248: per-modality Linear-ReLU-Dropout-Linear classifiers (:180-188),
+    weights softmax(fusion_logits) (:236), multiplied by the mask and renormalised with clamp_min(1e-8) (:238-241).
+    Returns (fused_logits, [per-modality logits])."""
+    p = ctx.p_fusion if ctx is not None else 0.0
+    per = []
+    for i, m in enumerate(modalities):
+        h = torch.relu(_lin(feats[m], sd, f"{prefix}classifiers.{m}.0"))
+        if ctx is not None:
+            h = ctx.apply(h, px.SITE_LATE + i, p)
+        per.append(_lin(h, sd, f"{prefix}classifiers.{m}.3"))
+    stacked = torch.stack(per, dim=1)
+    base_w = _softmax(sd[prefix + "fusion_logits"], dim=0)
+    B = stacked.shape[0]
+    if mask is not None:
+        w = base_w.unsqueeze(0) * torch.as_tensor(mask).to(stacked.dtype)
+        w = w / w.sum(dim=1, keepdim=True).clamp_min(1e-8)
+    else:
+        w = base_w.unsqueeze(0).expand(B, -1)
+    return (w.unsqueeze(-1) * stacked).sum(dim=1), per
+
+
+def calibration_metrics(logits, labels, num_bins=15):
+    """compute_calibration_metrics after the logits are collected (src/uncertainty.py:512-544) with
+    CalibrationMetrics._bin_stats / ECE / MCE (:98-183): returns dict(ece, mce, nll, accuracy)."""
+    logits = logits.float()
+    labels = labels.long()
+    n = labels.shape[0]
+    logp = logits - torch.logsumexp(logits, dim=1, keepdim=True)
+    nll = float(-(logp[torch.arange(n), labels]).sum() / max(1, n))
+    probs = _softmax(logits, dim=1)
+    conf, pred = probs.max(dim=1)
+    conf = conf.clamp(0, 1)
+    edges = torch.linspace(0, 1, steps=num_bins + 1)
+    ece, mce, tot = 0.0, 0.0, 0
+    stats = []
+    for b in range(num_bins):
+        lo, hi = edges[b], edges[b + 1]
+        in_bin = (conf >= lo) & ((conf < hi) if b < num_bins - 1 else (conf <= hi))
+        if in_bin.any():
+            stats.append((int(in_bin.sum()), float(conf[in_bin].mean()), float((pred[in_bin] == labels[in_bin]).float().mean())))
+    tot = sum(s[0] for s in stats)
+    for nb, c, a in stats:
+        ece += abs(a - c) * nb / tot
+        mce = max(mce, abs(a - c))
+    acc = float((pred == labels).float().mean()) if n else 0.0
+    return {"ece": ece, "mce": mce, "nll": nll, "accuracy": acc}
+
+
 def baseline_head(z_list, sd, prefix="fusion_head."):
     """Live path of MultimodalFusionModule.forward: concat -> Linear -> ReLU -> Linear.
 
@@ -256,6 +327,10 @@ def av_forward(feats, frames, mask, sd, head="hybrid", ctx: Optional[DropCtx] = 
     z_video = frame_encoder_tail(hid, sd, ctx=ctx)
     if head == "hybrid":
         return hybrid_fusion({"audio": z_audio, "video": z_video}, mask, sd, ctx=ctx)
+    if head == "early":
+        return early_fusion({"audio": z_audio, "video": z_video}, mask, sd, prefix="early_model.", ctx=ctx)
+    if head == "late":
+        return late_fusion({"audio": z_audio, "video": z_video}, mask, sd, prefix="late_model.", ctx=ctx)[0]
     return baseline_head([z_audio, z_video], sd)
 
 

@@ -25,8 +25,11 @@ the per-clip mask tensor):
     SITE_FRAME_POOL  1   encoders.video._dropout      (H,)        src/encoders.py:230,296
     SITE_GATE        2   fusion_model.fusion_gate.2   (M, G)      src/fusion.py:448
     SITE_MODMASK     3   modality dropout             (M,)        src/data.py:111-118
+    SITE_EARLY0      4   EarlyFusion mlp.3            (hidden,)   src/fusion.py:65
+    SITE_EARLY1      5   EarlyFusion mlp.7            (hidden,)   src/fusion.py:69
     SITE_ATTN + i    16+i fusion_model.attn_layers[i].attn_dropout (heads, Tq, Tk)
                                                                   src/attention.py:51,130
+    SITE_LATE + i    32+i LateFusion classifiers[i].2  (hidden,)   src/fusion.py:184
 Synthetic-data streams use c3 >= 0x100 (see oracle/synth.py).
 """
 from __future__ import annotations
@@ -43,7 +46,10 @@ SITE_FRAME_MLP = 0
 SITE_FRAME_POOL = 1
 SITE_GATE = 2
 SITE_MODMASK = 3
+SITE_EARLY0 = 4
+SITE_EARLY1 = 5
 SITE_ATTN = 16
+SITE_LATE = 32
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

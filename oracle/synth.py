@@ -142,6 +142,24 @@ def model_shapes(audio_dim=104, frame_dim=FRAME_DIM, enc_hidden=256, out_dim=128
     s["fusion_model.classifier.weight"] = ((num_classes, D), "u", D)
     s["fusion_model.classifier.bias"] = ((num_classes,), "u", D)
     cat = out_dim * len(modalities)
+    # EarlyFusion (src/fusion.py:60-72) and LateFusion (:180-189) at the same dims; they are alternatives to
+    # fusion_model, kept under their own prefixes here and loaded as `fusion_model.*` by the consumers
+    s["early_model.mlp.0.weight"] = ((D, cat), "u", cat)
+    s["early_model.mlp.0.bias"] = ((D,), "u", cat)
+    s["early_model.mlp.1.weight"] = ((D,), "lnw", 0)
+    s["early_model.mlp.1.bias"] = ((D,), "lnb", 0)
+    s["early_model.mlp.4.weight"] = ((D, D), "u", D)
+    s["early_model.mlp.4.bias"] = ((D,), "u", D)
+    s["early_model.mlp.5.weight"] = ((D,), "lnw", 0)
+    s["early_model.mlp.5.bias"] = ((D,), "lnb", 0)
+    s["early_model.mlp.8.weight"] = ((num_classes, D), "u", D)
+    s["early_model.mlp.8.bias"] = ((num_classes,), "u", D)
+    for m in modalities:
+        s[f"late_model.classifiers.{m}.0.weight"] = ((D, out_dim), "u", out_dim)
+        s[f"late_model.classifiers.{m}.0.bias"] = ((D,), "u", out_dim)
+        s[f"late_model.classifiers.{m}.3.weight"] = ((num_classes, D), "u", D)
+        s[f"late_model.classifiers.{m}.3.bias"] = ((num_classes,), "u", D)
+    s["late_model.fusion_logits"] = ((len(modalities),), "lnb", 0)
     s["fusion_head.0.weight"] = ((D, cat), "u", cat)
     s["fusion_head.0.bias"] = ((D,), "u", cat)
     s["fusion_head.2.weight"] = ((num_classes, D), "u", D)
@@ -165,4 +183,19 @@ def synth_weights(seed: int, gain: float = 1.0, **shape_kwargs) -> "OrderedDict[
         else:
             v = 0.1 * u
         out[name] = v.astype(np.float32)
+    return out
+
+
+def state_dict_for(head: str, sd):
+    """The tensors a model with the given head holds, under the reference's key names:
+    encoders.* plus fusion_model.* (hybrid / early / late: the three alternatives of build_fusion_model share the
+    attribute name, src/train.py:69) or fusion_head.* (concat, the live path)."""
+    src = {"hybrid": "fusion_model.", "early": "early_model.", "late": "late_model.", "concat": "fusion_head."}[head]
+    dst = "fusion_head." if head == "concat" else "fusion_model."
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.startswith("encoders."):
+            out[k] = v
+        elif k.startswith(src):
+            out[dst + k[len(src):]] = v
     return out

@@ -63,14 +63,14 @@ class RefAVModel(nn.Module):
                 modality=m, input_dim=cfg.get("input_dim", 64), output_dim=128, encoder_config=cfg)
             dims[m] = 128
         self.fusion_model = ref_fusion.build_fusion_model(     # train.py:69-76 (commented there)
-            fusion_type="hybrid", modality_dims=dims, num_classes=8, hidden_dim=256,
-            num_heads=4, dropout=0.3)
+            fusion_type=head if head in ("early", "late") else "hybrid", modality_dims=dims, num_classes=8,
+            hidden_dim=256, num_heads=4, dropout=0.3)
         self.fusion_head = nn.Sequential(                      # train.py:81-85
             nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 8))
 
     def forward(self, features, mask=None):
         enc = {m: e(features[m]) for m, e in self.encoders.items() if m in features}  # :134-136
-        if self.head == "hybrid":
+        if self.head in ("hybrid", "early", "late"):
             out = self.fusion_model(enc, mask)                 # :139
             return out[0] if isinstance(out, tuple) else out   # :142-145
         fused = torch.cat([enc[m] for m in MODALITIES if m in enc], dim=-1)           # :153-161
@@ -80,16 +80,23 @@ class RefAVModel(nn.Module):
 class MaskInjector:
     """Gives each nn.Dropout of the reference model its Philox spec mask."""
 
-    SITES = {
+    ENC_SITES = {
         "encoders.video.frame_mlp.2": px.SITE_FRAME_MLP,
         "encoders.video._dropout": px.SITE_FRAME_POOL,
-        "fusion_model.attn_layers.audio.attn_dropout": px.SITE_ATTN + 0,
-        "fusion_model.attn_layers.video.attn_dropout": px.SITE_ATTN + 1,
-        "fusion_model.fusion_gate.2": px.SITE_GATE,
+    }
+    HEAD_SITES = {
+        "hybrid": {"fusion_model.attn_layers.audio.attn_dropout": px.SITE_ATTN + 0,
+                   "fusion_model.attn_layers.video.attn_dropout": px.SITE_ATTN + 1,
+                   "fusion_model.fusion_gate.2": px.SITE_GATE},
+        "early": {"fusion_model.mlp.3": px.SITE_EARLY0, "fusion_model.mlp.7": px.SITE_EARLY1},
+        "late": {"fusion_model.classifiers.audio.2": px.SITE_LATE + 0,
+                 "fusion_model.classifiers.video.2": px.SITE_LATE + 1},
     }
 
     def __init__(self, model, seed, clip_ids):
         self.seed, self.clip_ids, self.t = seed, clip_ids, -1
+        self.SITES = dict(self.ENC_SITES)
+        self.SITES.update(self.HEAD_SITES["hybrid" if model.head == "concat" else model.head])
         model.register_forward_pre_hook(self._bump)
         found = {n for n, m in model.named_modules() if isinstance(m, nn.Dropout)}
         assert found == set(self.SITES), (found, set(self.SITES))
@@ -140,9 +147,10 @@ def main():
         s = ref_t.abs().max().item()
         worst[name] = (d, s)
 
-    for head in ("hybrid", "concat"):
+    for head in ("hybrid", "concat", "early", "late"):
         model = RefAVModel(head)
-        full = {k: v for k, v in sd.items()}
+        full = dict(synth.state_dict_for("hybrid" if head == "concat" else head, sd))
+        full.update({k: v for k, v in sd.items() if k.startswith("fusion_head.")})
         missing = model.load_state_dict(full, strict=True)       # layout check, Appendix A
         model.eval()
         inj = MaskInjector(model, SEED, CLIP_IDS)
@@ -169,7 +177,17 @@ def main():
                     rec(f"attn_video_{mname}", info["per_modality_attention"]["video"],
                         oinfo["per_modality_attention"][1])
         # MC-dropout: the reference wrapper, unmodified, over the mask-injected model
-        for mname in (("ones", "p05") if head == "hybrid" else ("ones",)):
+        if head in ("early", "late"):
+            with torch.inference_mode():
+                for mname in ("mixed",):
+                    logits = model({"audio": feats, "video": frames}, masks[mname].clone())
+                    rec(f"logits_{head}_{mname}", logits, om.av_forward(feats, frames, masks[mname], sd, head))
+                if head == "late":
+                    _, per = model.fusion_model({"audio": z_a, "video": z_v}, masks["mixed"].clone())
+                    _, oper = om.late_fusion({"audio": z_a, "video": z_v}, masks["mixed"], sd, prefix="late_model.")
+                    rec("late_per_audio_mixed", per["audio"], oper[0])
+                    rec("late_per_video_mixed", per["video"], oper[1])
+        for mname in (("ones", "p05") if head != "concat" else ("ones",)):
             mask = masks[mname]
             inj.t = -1
             mc = ref_uncertainty.MCDropoutUncertainty(model, num_samples=T_MC)
@@ -199,6 +217,26 @@ def main():
     out["xattn.q"], out["xattn.kv"], out["xattn.invalid"] = q.numpy(), kv.numpy(), inv.numpy()
     rec("xattn.out", o, oo)
     rec("xattn.attn", a, oa)
+
+    # calibration metrics (src/uncertainty.py:88-183, :512-544) on seeded random logits / labels
+    g = torch.Generator().manual_seed(5)
+    cal_logits = torch.randn(4000, 8, generator=g) * 2.0
+    cal_labels = torch.randint(0, 8, (4000,), generator=g)
+    cal_labels[:1500] = cal_logits[:1500].argmax(1)                      # make a third of them correct
+    probs = torch.softmax(cal_logits, dim=1)
+    confs, preds = probs.max(dim=1)
+    ref_cal = {
+        "ece": ref_uncertainty.CalibrationMetrics.expected_calibration_error(confs, preds, cal_labels, 15),
+        "mce": ref_uncertainty.CalibrationMetrics.maximum_calibration_error(confs, preds, cal_labels, 15),
+        "nll": ref_uncertainty.CalibrationMetrics.negative_log_likelihood(cal_logits, cal_labels),
+        "accuracy": float((preds == cal_labels).float().mean()),
+        "ece10": ref_uncertainty.CalibrationMetrics.expected_calibration_error(confs, preds, cal_labels, 10),
+    }
+    ora_cal = om.calibration_metrics(cal_logits, cal_labels, 15)
+    ora_cal["ece10"] = om.calibration_metrics(cal_logits, cal_labels, 10)["ece"]
+    out["cal.logits"], out["cal.labels"] = cal_logits.numpy(), cal_labels.numpy()
+    for k_ in ref_cal:
+        rec("cal." + k_, torch.tensor(ref_cal[k_], dtype=torch.float64), torch.tensor(ora_cal[k_], dtype=torch.float64))
 
     print("reference vs oracle/model.py (max abs diff, max |ref|):")
     bad = False

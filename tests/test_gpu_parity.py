@@ -48,8 +48,7 @@ def world(golden):
 
 def make_model(pkg, dev, world, head="hybrid"):
     m = pkg.AVHotPath(head)
-    drop = "fusion_head." if head == "hybrid" else "fusion_model."
-    m.load_state_dict({k: v for k, v in world["sd"].items() if not k.startswith(drop)}, strict=True)
+    m.load_state_dict(osynth.state_dict_for(head, world["sd"]), strict=True)
     return m.to(dev).eval()
 
 
@@ -305,7 +304,7 @@ def _features(world, dev, u8=False):
     return {"audio": torch.from_numpy(world["wave"]).to(dev), "video": v}
 
 
-@pytest.mark.parametrize("head", ["hybrid", "concat"])
+@pytest.mark.parametrize("head", ["hybrid", "concat", "early", "late"])
 def test_full_path_vs_reference_golden(pkg, dev, world, golden, head):
     m = make_model(pkg, dev, world, head)
     feats = _features(world, dev)
@@ -322,7 +321,8 @@ def test_full_path_vs_reference_golden(pkg, dev, world, golden, head):
     assert rel_err(pre, golden[f"logits_{head}_ones"]) <= REL      # precomputed (B, 301, 104) features accepted
 
 
-@pytest.mark.parametrize("head,names", [("hybrid", ("ones", "p05")), ("concat", ("ones",))])
+@pytest.mark.parametrize("head,names", [("hybrid", ("ones", "p05")), ("concat", ("ones",)),
+                                        ("early", ("ones", "p05")), ("late", ("ones", "p05"))])
 def test_mc_dropout_vs_reference_golden(pkg, dev, world, golden, head, names):
     """The reference's MCDropoutUncertainty ran unmodified over mask-injected reference modules (make_golden.py);
     clip ids there are NOT contiguous, so each clip runs with its own clip0."""
@@ -389,3 +389,94 @@ def test_shard_invariance_and_determinism(pkg, dev, world):
     # the LSTM / fusion tile kernels reduce in a fixed order per clip, so batching does not change a single bit
     assert (parts == whole).all()
     assert torch.isfinite(whole).all() and (whole[:, 8] >= 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# EarlyFusion / LateFusion modules and the calibration metrics
+# ---------------------------------------------------------------------------------------------------------
+def test_early_late_modules_vs_reference_golden(pkg, dev, world, golden):
+    z = {"audio": torch.from_numpy(golden["z_audio"]).to(dev), "video": torch.from_numpy(golden["z_video"]).to(dev)}
+    dims = {"audio": 128, "video": 128}
+    early = pkg.build_fusion_model("early", dims, 8, hidden_dim=256, num_heads=4, dropout=0.3)
+    late = pkg.build_fusion_model("late", dims, 8, hidden_dim=256, num_heads=4, dropout=0.3)
+    sd = world["sd"]
+    early.load_state_dict({k[len("early_model."):]: v for k, v in sd.items() if k.startswith("early_model.")}, strict=True)
+    late.load_state_dict({k[len("late_model."):]: v for k, v in sd.items() if k.startswith("late_model.")}, strict=True)
+    early, late = early.to(dev).eval(), late.to(dev).eval()
+    for name, mask in _masks(world).items():
+        mk = torch.from_numpy(mask).to(dev)
+        assert rel_err(early(z, mk).cpu().numpy(), golden[f"logits_early_{name}"]) <= REL
+        lg, per = late(z, mk)
+        assert rel_err(lg.cpu().numpy(), golden[f"logits_late_{name}"]) <= REL
+        if name == "mixed":
+            assert rel_err(per["audio"].cpu().numpy(), golden["late_per_audio_mixed"]) <= REL
+            assert rel_err(per["video"].cpu().numpy(), golden["late_per_video_mixed"]) <= REL
+    # no mask; a modality that is not given at all: zeros (early, src/fusion.py:120-121) / zero logits (late, :222-225)
+    sdo = world["sd"]
+    zc = {k: v.cpu() for k, v in z.items()}
+    want = om.early_fusion(zc, None, sdo, prefix="early_model.")
+    assert rel_err(early(z).cpu().numpy(), want.numpy()) <= REL
+    want = om.early_fusion({"audio": zc["audio"], "video": torch.zeros_like(zc["video"])}, None, sdo, prefix="early_model.")
+    assert rel_err(early({"audio": z["audio"]}).cpu().numpy(), want.numpy()) <= REL
+    lg, per = late({"video": z["video"]})
+    wl, wper = om.late_fusion(zc, None, sdo, prefix="late_model.")
+    assert float(per["audio"].abs().max()) == 0.0
+    assert rel_err(per["video"].cpu().numpy(), wper[1].numpy()) <= REL
+    w = torch.softmax(sdo["late_model.fusion_logits"], dim=0)
+    assert rel_err(lg.cpu().numpy(), (w[1] * wper[1]).numpy()) <= REL
+    with pytest.raises(ValueError):
+        early({"imu": z["audio"]})
+    with pytest.raises(ValueError):
+        early(z, torch.ones(6, 3, device=dev))
+    with pytest.raises(ValueError):
+        pkg.build_fusion_model("mid", dims, 8)
+
+
+def test_early_late_dropout_vs_oracle(pkg, dev, world, golden):
+    """Dropout sites EARLY0 / EARLY1 / LATE+m draw the spec masks: compare one stochastic pass with the oracle."""
+    z = {"audio": torch.from_numpy(golden["z_audio"]), "video": torch.from_numpy(golden["z_video"])}
+    zd = {k: v.to(dev) for k, v in z.items()}
+    dims = {"audio": 128, "video": 128}
+    ids = world["ids"]
+    mask = torch.from_numpy(_masks(world)["mixed"])
+    for head, fn in (("early", om.early_fusion), ("late", om.late_fusion)):
+        mod = pkg.build_fusion_model(head, dims, 8, hidden_dim=256, dropout=0.3)
+        mod.load_state_dict({k[len(head) + 7:]: v for k, v in world["sd"].items() if k.startswith(head + "_model.")},
+                            strict=True)
+        mod = mod.to(dev).train()
+        for b, g in enumerate(ids):
+            ctx = om.DropCtx(SEED, 3, np.asarray([g], dtype=np.uint64), p_fusion=0.3)
+            want = fn({k: v[b:b + 1] for k, v in z.items()}, mask[b:b + 1], world["sd"], prefix=head + "_model.", ctx=ctx)
+            want = want[0] if isinstance(want, tuple) else want
+            with pkg.philox_context(SEED, 3, int(g)):
+                got = mod({k: v[b:b + 1] for k, v in zd.items()}, mask[b:b + 1].to(dev))
+            got = got[0] if isinstance(got, tuple) else got
+            assert rel_err(got.cpu().numpy(), want.numpy()) <= REL, (head, b)
+
+
+def test_calibration_metrics_vs_reference_golden(pkg, dev, golden):
+    logits = torch.from_numpy(golden["cal.logits"]).to(dev)
+    labels = torch.from_numpy(golden["cal.labels"]).to(dev)
+    probs = torch.softmax(logits, dim=1)
+    confs, preds = probs.max(dim=1)
+    CM = pkg.CalibrationMetrics
+    assert abs(CM.expected_calibration_error(confs, preds, labels, 15) - float(golden["cal.ece"])) <= 1e-6
+    assert abs(CM.maximum_calibration_error(confs, preds, labels, 15) - float(golden["cal.mce"])) <= 1e-6
+    assert abs(CM.expected_calibration_error(confs, preds, labels, 10) - float(golden["cal.ece10"])) <= 1e-6
+    assert abs(CM.negative_log_likelihood(logits, labels) - float(golden["cal.nll"])) <= 1e-5
+
+    class Ident(torch.nn.Module):
+        def forward(self, x):
+            return x, None                                                     # (logits, aux) is unwrapped
+
+    loader = [(logits[i:i + 1000], labels[i:i + 1000]) for i in range(0, 4000, 1000)]
+    got = pkg.compute_calibration_metrics(Ident(), loader, device=dev, num_bins=15)
+    for k in ("ece", "mce", "nll", "accuracy"):
+        assert abs(got[k] - float(golden["cal." + k])) <= 1e-5, k
+    # size-independent property: accumulating in any batching gives the same histogram
+    a1 = pkg.uncertainty.calibration_accumulate(torch.zeros(48, device=dev, dtype=torch.float64), labels, 15, logits=logits)
+    a2 = torch.zeros(48, device=dev, dtype=torch.float64)
+    for i in range(0, 4000, 37):
+        pkg.uncertainty.calibration_accumulate(a2, labels[i:i + 37], 15, logits=logits[i:i + 37])
+    assert (a1[:15] == a2[:15]).all() and (a1[30:45] == a2[30:45]).all() and a1[47] == a2[47] == 4000
+    assert torch.allclose(a1, a2, rtol=1e-12, atol=1e-9)

@@ -34,14 +34,14 @@ def test_signatures_match_reference():
 
 def test_state_dict_layout_appendix_a():
     want = synth.model_shapes()
-    for head, drop in (("hybrid", "fusion_head."), ("concat", "fusion_model.")):
+    for head in ("hybrid", "concat", "early", "late"):
         sd = pkg.AVHotPath(head).state_dict()
-        exp = {k: v[0] for k, v in want.items() if not k.startswith(drop)}
-        assert set(sd) == set(exp)
+        exp = synth.state_dict_for(head, {k: v[0] for k, v in want.items()})
+        assert set(sd) == set(exp), head
         for k, shape in exp.items():
             assert tuple(sd[k].shape) == tuple(shape), k
     m = pkg.AVHotPath("hybrid")
-    w = {k: torch.from_numpy(v) for k, v in synth.synth_weights(42).items() if not k.startswith("fusion_head.")}
+    w = {k: torch.from_numpy(v) for k, v in synth.state_dict_for("hybrid", synth.synth_weights(42)).items()}
     m.load_state_dict(w, strict=True)
     assert sum(p.numel() for p in m.encoders["audio"].parameters()) == 929920
     assert sum(p.numel() for p in m.encoders["video"].parameters()) == 3245185

@@ -41,12 +41,33 @@ def test_encoders_and_heads(golden):
     np.testing.assert_allclose(lg.numpy(), golden["logits_concat_ones"], **TOL)
     # MC-dropout through the oracle's Philox masks == the reference wrapper over mask-injected reference modules
     T = int(golden["t_mc"])
-    for head, names in (("hybrid", ("ones", "p05")), ("concat", ("ones",))):
+    for head, names in (("hybrid", ("ones", "p05")), ("concat", ("ones",)), ("early", ("ones", "p05")),
+                        ("late", ("ones", "p05"))):
         for name in names:
             mean, unc, _ = om.mc_dropout_forward(feats, frames, masks[name], sd, T, seed, ids, head)
             np.testing.assert_allclose(mean.numpy(), golden[f"mc_mean_logits_{head}_{name}"], **TOL)
             np.testing.assert_allclose(unc.numpy(), golden[f"mc_uncertainty_{head}_{name}"], rtol=1e-3, atol=1e-7)
             assert (mean.argmax(dim=1).numpy() == golden[f"mc_labels_{head}_{name}"]).all()
+
+
+def test_early_late_fusion_and_calibration(golden):
+    """EarlyFusion / LateFusion / CalibrationMetrics restatements against the reference's
+    own outputs (make_golden.py)."""
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    z = {"audio": om.sequence_encoder_lstm(feats, sd), "video": om.frame_encoder(frames, sd)}
+    for name, mask in masks.items():
+        lg = om.early_fusion(z, mask, sd, prefix="early_model.")
+        np.testing.assert_allclose(lg.numpy(), golden[f"logits_early_{name}"], **TOL)
+        lg, per = om.late_fusion(z, mask, sd, prefix="late_model.")
+        np.testing.assert_allclose(lg.numpy(), golden[f"logits_late_{name}"], **TOL)
+        if name == "mixed":
+            np.testing.assert_allclose(per[0].numpy(), golden["late_per_audio_mixed"], **TOL)
+            np.testing.assert_allclose(per[1].numpy(), golden["late_per_video_mixed"], **TOL)
+    cal = om.calibration_metrics(torch.from_numpy(golden["cal.logits"]), torch.from_numpy(golden["cal.labels"]), 15)
+    for k in ("ece", "mce", "nll", "accuracy"):
+        assert abs(cal[k] - float(golden["cal." + k])) <= 1e-6, k
+    cal10 = om.calibration_metrics(torch.from_numpy(golden["cal.logits"]), torch.from_numpy(golden["cal.labels"]), 10)
+    assert abs(cal10["ece"] - float(golden["cal.ece10"])) <= 1e-6
 
 
 def test_cross_modal_attention_general_shapes(golden):
