@@ -74,8 +74,8 @@ int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s);
 int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp, bool xp_f16, void* h_seq_f16, int h_pitch,
                        float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s);
 // gemm_ws.cu: weight-stationary tcgen05 GEMM, fp16 operands, fp32 output (LSTM input projections)
-int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, void* c, bool out_f16, int ldc, int M, int N, int K,
-                cudaStream_t s, const char* prof_name = "gemm_f16_ws");
+int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, const float* bias, void* c, bool out_f16, int ldc, int M,
+                int N, int K, cudaStream_t s, const char* prof_name = "gemm_f16_ws");
 
 // ---------------------------------------------------------------------------
 // Philox-4x32-10 (oracle/philox.py is the written spec; Random123 algorithm).

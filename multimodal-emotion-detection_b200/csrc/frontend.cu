@@ -3,13 +3,22 @@
 //
 //   wave (B, N) fp32 -> feats (B, 1 + N/160, 104) fp32 = [64 log-mel | 40 MFCC]
 //
-// One CTA = FPB consecutive frames of one clip.  The pre-emphasised, reflect-padded samples
-// the frames share are staged once in shared memory with coalesced loads (frames overlap
-// 3.2x, so HBM is read once).  One warp = one frame at a time:
-//   window + pack 512 reals as 256 complex -> in-place Stockham FFT-256 in shared memory,
-//   radix 8 x 8 x 4 (last pass stays in registers) -> real-FFT split + |X|^2 with the
-//   mirrored bin fetched by warp shuffle -> sparse (triangular) mel filters -> 10 log10 ->
-//   40 x 64 DCT-II -> output tile in shared memory -> coalesced 128-bit stores.
+// One CTA walks the tiles of FPB = 16 consecutive frames of one clip.  The pre-emphasised, reflect-padded samples
+// the frames share are staged once in shared memory with coalesced loads (frames overlap 3.2x, so HBM is read
+// once).  Per tile:
+//   FFT phase   one warp = one frame at a time: window + pack 512 reals as 256 complex -> in-place Stockham FFT-256
+//               in shared memory, radix 8 x 8 x 4 (last pass stays in registers) -> real-FFT split + |X|^2 with the
+//               mirrored bin fetched by warp shuffle -> power spectrum row of the tile (16 x 256, pitch 260);
+//   mel phase   the 64 x 257 filterbank as tensor-core tiles: warp j = filters 8j .. 8j+7 for all 16 frames,
+//               mma.sync m16n8k8 TF32 over the 8-bin steps its filters actually cover (41 steps in all instead of
+//               the 264 of a dense projection); the power spectrum is split hi + lo (two MMAs per step, exact to
+//               fp32), the weights are TF32-rounded once on the host (<= 2^-11 relative on a filter tap, i.e.
+//               <= 0.002 dB on a log-mel value); B fragments are stored in lane order (one 64-bit load per step);
+//               10 log10 in the accumulator registers -> output tile;
+//   DCT phase   40 x 64 DCT-II in fp32 FMA, a warp's two frames per table read -> output tile;
+//   store       coalesced 128-bit stores of the fp32 features and / or the LSTM's fp16 split operand.
+// (The sparse per-lane filter walk this replaces cost ~130 of the ~480 shared-memory wavefronts per frame of a
+// kernel that ncu shows bound by shared-memory bandwidth: l1tex 88 %, r1y.)
 #include <math.h>
 
 #include <mutex>
@@ -26,7 +35,8 @@ constexpr int FPB = 16;            // frames per CTA
 constexpr int FE_WARPS = 8;        // warps per CTA
 constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
 constexpr int ZPAD = 256 + 16;     // padded complex buffer (index i -> i + (i >> 4))
-constexpr int MEL_G4_MAX = 320;    // float4 groups of filter weights (each filter padded to aligned groups of 4 bins)
+constexpr int MEL_KS_MAX = 44;     // 8-bin steps summed over the eight 8-filter tiles (41 for the Slaney bank used here)
+constexpr int POW_LD = 260;        // pitch of a power-spectrum row: 256 bins + 4 (conflict-free A-fragment loads)
 constexpr int DCT_LD = N_MELS + 4; // padded row length of the DCT table
 
 struct FrontendTables {            // device layout, all fp32 unless noted
@@ -34,16 +44,18 @@ struct FrontendTables {            // device layout, all fp32 unless noted
   float2 tw[N_FFT];                // tw[k] = exp(-2 pi i k / 512)
   float2 tw2[64];                  // tw2[r * 8 + k]  = exp(-2 pi i r k / 64)   (pass 2; lanes read consecutive entries)
   float2 tw3[256];                 // tw3[r * 64 + j] = exp(-2 pi i r j / 256)  (pass 3)
-  float4 mel_w4[MEL_G4_MAX];       // filter weights in aligned groups of 4 bins (zeros outside the triangle)
-  int mel_g0[N_MELS];              // first 4-bin group of filter m
-  int mel_ng[N_MELS];              // number of groups
-  int mel_off[N_MELS];             // offset of the filter's first group in mel_w4
+  float2 mel_b[MEL_KS_MAX * 32];   // B fragments of mma.m16n8k8 in lane order, TF32-rounded: step i, lane l ->
+                                   //   (W[8j + (l >> 2)][8k + (l & 3)], W[8j + (l >> 2)][8k + (l & 3) + 4])
+  int mel_k0[8];                   // first 8-bin step of filter tile j
+  int mel_nk[8];                   // number of steps
+  int mel_off[8];                  // index of the tile's first step in mel_b
   float dct_p[N_MFCC * DCT_LD];    // dct_p[c * 68 + j] = C[c][j]; padded rows: conflict-free 128-bit row reads
 };
 
 static FrontendTables g_host_tables;
 static std::vector<float> g_host_mel_dense, g_host_dct;
 static std::once_flag g_tables_once;
+static bool g_tables_ok = false;
 
 static double hz_to_mel(double f) {
   const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
@@ -73,33 +85,45 @@ static void build_tables() {
   const double m_lo = hz_to_mel(f_lo), m_hi = hz_to_mel(f_hi);
   for (int i = 0; i < N_MELS + 2; ++i) hz[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (N_MELS + 1));
   g_host_mel_dense.assign(N_MELS * N_BINS, 0.f);
-  int off = 0;
   for (int m = 0; m < N_MELS; ++m) {
     const double enorm = 2.0 / (hz[m + 2] - hz[m]);
-    int start = -1, len = 0;
     for (int k = 0; k < N_BINS; ++k) {
       const double f = (sr / 2.0) * k / (N_BINS - 1);
       const double lower = (f - hz[m]) / (hz[m + 1] - hz[m]);
       const double upper = (hz[m + 2] - f) / (hz[m + 2] - hz[m + 1]);
       const double w = lower < upper ? lower : upper;
-      if (w > 0.0) {
-        if (start < 0) start = k;
-        len = k - start + 1;
-        g_host_mel_dense[m * N_BINS + k] = (float)(w * enorm);
-      }
+      if (w > 0.0) g_host_mel_dense[m * N_BINS + k] = (float)(w * enorm);
     }
-    if (start < 0) { start = 0; len = 1; }
-    const int g0 = start / 4, g1 = (start + len - 1) / 4;
-    t.mel_g0[m] = g0;
-    t.mel_ng[m] = g1 - g0 + 1;
-    t.mel_off[m] = off;
-    for (int g = g0; g <= g1; ++g, ++off) {
-      float w[4];
-      for (int e = 0; e < 4; ++e) {
-        const int k = 4 * g + e;
-        w[e] = k < N_BINS ? g_host_mel_dense[m * N_BINS + k] : 0.f;
+  }
+  // tensor-core layout: per 8-filter tile, the 8-bin steps its filters cover.  The Nyquist bin carries no weight
+  // (the last filter ends there), so the kernel keeps bins 0..255 only.
+  g_tables_ok = true;
+  for (int m = 0; m < N_MELS; ++m) if (g_host_mel_dense[m * N_BINS + (N_BINS - 1)] != 0.f) g_tables_ok = false;
+  auto tf32_round = [](float v) {
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u += 0xFFFu + ((u >> 13) & 1u);
+    u &= ~0x1FFFu;
+    memcpy(&v, &u, 4);
+    return v;
+  };
+  int off = 0;
+  for (int j = 0; j < 8; ++j) {
+    int lo = N_BINS, hi = -1;
+    for (int m = 8 * j; m < 8 * j + 8; ++m)
+      for (int k = 0; k < N_BINS - 1; ++k)
+        if (g_host_mel_dense[m * N_BINS + k] != 0.f) { lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+    if (hi < 0) { lo = 0; hi = 0; }
+    t.mel_k0[j] = lo / 8;
+    t.mel_nk[j] = hi / 8 - lo / 8 + 1;
+    t.mel_off[j] = off;
+    for (int ks = 0; ks < t.mel_nk[j]; ++ks, ++off) {
+      if (off >= MEL_KS_MAX) { g_tables_ok = false; continue; }
+      for (int l = 0; l < 32; ++l) {
+        const int m = 8 * j + (l >> 2), k = 8 * (t.mel_k0[j] + ks) + (l & 3);
+        t.mel_b[off * 32 + l] = make_float2(tf32_round(g_host_mel_dense[m * N_BINS + k]),
+                                            tf32_round(g_host_mel_dense[m * N_BINS + k + 4]));
       }
-      if (off < MEL_G4_MAX) t.mel_w4[off] = make_float4(w[0], w[1], w[2], w[3]);
     }
   }
   g_host_dct.assign(N_MFCC * N_MELS, 0.f);
@@ -118,6 +142,7 @@ static std::mutex g_dev_mutex;
 
 static int get_tables(const FrontendTables** out) {
   std::call_once(g_tables_once, build_tables);
+  AVHOT_REQUIRE(g_tables_ok, AVHOT_ERR_UNSUPPORTED, "frontend: mel filterbank does not fit the tensor-core layout");
   int dev = 0;
   AVHOT_CUDA(cudaGetDevice(&dev));
   AVHOT_REQUIRE(dev >= 0 && dev < MAX_DEVICES, AVHOT_ERR_INVALID, "frontend: device index %d", dev);
@@ -168,16 +193,34 @@ __device__ __forceinline__ int zpad(int i) { return i + (i >> 4); }
 struct FeSmem {
   float seg[SEG];
   float win[N_FFT];
-  float2 tw[N_FFT];
+  float2 tw[N_FFT / 2];
   float2 tw2[64], tw3[256];
-  float4 melw4[MEL_G4_MAX];
-  int mel_g0[N_MELS], mel_ng[N_MELS], mel_off[N_MELS];
+  float2 melb[MEL_KS_MAX * 32];
+  int mel_k0[8], mel_nk[8], mel_off[8];
   float dct[N_MFCC * DCT_LD];
-  float2 z[FE_WARPS][ZPAD];
-  float pow[FE_WARPS][N_BINS + 3];
-  float lm[FE_WARPS][FPB / FE_WARPS][N_MELS];
-  float out[FPB][N_FEATS];
+  union {                              // FFT scratch during the FFT phase, output tile afterwards
+    float2 z[FE_WARPS][ZPAD];
+    float out[FPB][N_FEATS];
+  } u;
+  float pow[FPB][POW_LD];
 };
+static_assert(sizeof(FeSmem) <= 75 * 1024, "three CTAs per SM");
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// D (16 x 8, fp32) += A (16 x 8, tf32, row) * B (8 x 8, tf32, col); fragment layouts per the PTX ISA:
+// g = lane >> 2, t = lane & 3: a = {A[g][t], A[g+8][t], A[g][t+4], A[g+8][t+4]}, b = {B[t][g], B[t+4][g]},
+// d = {D[g][2t], D[g][2t+1], D[g+8][2t], D[g+8][2t+1]}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(FE_WARPS * 32, 3)
 frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __half* __restrict__ xs, int Bp, int ldx,
@@ -187,27 +230,22 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   float* s_seg = sm.seg;
   float* s_win = sm.win;
   float2* s_tw = sm.tw;
-  float4* s_melw4 = sm.melw4;
-  int *s_mel_g0 = sm.mel_g0, *s_mel_ng = sm.mel_ng, *s_mel_off = sm.mel_off;
   float* s_dct = sm.dct;
-  float2 (*s_z)[ZPAD] = sm.z;
-  float (*s_pow)[N_BINS + 3] = sm.pow;
-  float (*s_lm)[FPB / FE_WARPS][N_MELS] = sm.lm;
-  float (*s_out)[N_FEATS] = sm.out;
+  float2 (*s_z)[ZPAD] = sm.u.z;
+  float (*s_pow)[POW_LD] = sm.pow;
+  float (*s_out)[N_FEATS] = sm.u.out;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int clip = blockIdx.y;
   const float* y = wave + (size_t)clip * n_samples;
 
   // tables -> smem
-  for (int i = tid; i < N_FFT; i += blockDim.x) { s_win[i] = tab->window[i]; s_tw[i] = tab->tw[i]; }
+  for (int i = tid; i < N_FFT; i += blockDim.x) s_win[i] = tab->window[i];
+  for (int i = tid; i < N_FFT / 2; i += blockDim.x) s_tw[i] = tab->tw[i];
   for (int i = tid; i < 64; i += blockDim.x) sm.tw2[i] = tab->tw2[i];
   for (int i = tid; i < 256; i += blockDim.x) sm.tw3[i] = tab->tw3[i];
-  for (int i = tid; i < MEL_G4_MAX; i += blockDim.x) s_melw4[i] = tab->mel_w4[i];
-  if (lane < 3) sm.pow[warp][N_BINS + lane] = 0.f;    // bins 257..259 pad the last group of 4
-  for (int i = tid; i < N_MELS; i += blockDim.x) {
-    s_mel_g0[i] = tab->mel_g0[i]; s_mel_ng[i] = tab->mel_ng[i]; s_mel_off[i] = tab->mel_off[i];
-  }
+  for (int i = tid; i < MEL_KS_MAX * 32; i += blockDim.x) sm.melb[i] = tab->mel_b[i];
+  if (tid < 8) { sm.mel_k0[tid] = tab->mel_k0[tid]; sm.mel_nk[tid] = tab->mel_nk[tid]; sm.mel_off[tid] = tab->mel_off[tid]; }
   for (int i = tid; i < N_MFCC * DCT_LD; i += blockDim.x) s_dct[i] = tab->dct_p[i];
 
   // The tables are loaded once; the CTA then walks its tiles of FPB frames.  The raw samples of the NEXT tile are
@@ -295,7 +333,7 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     // ---- real-FFT split + power.  Bin k = lane + 32 m needs Z[(256 - k) & 255], which is
     //      register v[7 - m] (m' = 7 - m) of lane (32 - lane) & 31, or v[(8 - m) & 7] of lane 0
     //      when lane == 0.
-    float* pw = s_pow[warp];
+    float* pw = s_pow[f];
     const int src = (32 - lane) & 31;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -311,31 +349,37 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
       const float2 X = cadd(xe, cmul(s_tw[k], xo));
       pw[k] = X.x * X.x + X.y * X.y;
     }
-    if (lane == 0) {  // k = 256: X = Re(Z0) - Im(Z0)
-      const float X = v[0].x - v[0].y;
-      pw[256] = X * X;
-    }
-    __syncwarp();
-    // ---- sparse mel filters + log: lane -> filters (lane, 63 - lane) (a short and a long triangle), each walked in
-    //      aligned groups of 4 bins with 128-bit shared loads of the spectrum and of the zero-padded weights
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = h == 0 ? lane : N_MELS - 1 - lane;
-      const int ng = s_mel_ng[m];
-      const float4* p4 = reinterpret_cast<const float4*>(pw) + s_mel_g0[m];
-      const float4* w4 = s_melw4 + s_mel_off[m];
-      float acc = 0.f;
-      for (int i = 0; i < ng; ++i) {
-        const float4 pv = p4[i], wv = w4[i];
-        acc = fmaf(pv.x, wv.x, acc); acc = fmaf(pv.y, wv.y, acc);
-        acc = fmaf(pv.z, wv.z, acc); acc = fmaf(pv.w, wv.w, acc);
-      }
-      const float lm = 3.01029995663981195f * log2f(fmaxf(acc, 1e-10f));   // 10 log10(.)
-      s_lm[warp][f / FE_WARPS][m] = lm;
-      s_out[f][m] = lm;
-    }
+    // (bin 256 carries no filter weight - checked when the tables are built - and is not formed)
     __syncwarp();
   }
+  __syncthreads();                   // power spectra of the tile complete; the FFT scratch is free
+  // ---- mel filterbank on the tensor cores + log: warp j = filters 8j .. 8j+7 of all 16 frames
+  {
+    const int g = lane >> 2, t4 = lane & 3;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nk = sm.mel_nk[warp];
+    const float2* bt = sm.melb + sm.mel_off[warp] * 32 + lane;
+    const float* pa = &s_pow[g][8 * sm.mel_k0[warp] + t4];
+    for (int ks = 0; ks < nk; ++ks) {
+      const float x[4] = {pa[0], pa[8 * POW_LD], pa[4], pa[8 * POW_LD + 4]};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ah[e] = to_tf32(x[e]);
+        al[e] = to_tf32(x[e] - __uint_as_float(ah[e]));
+      }
+      const float2 b = bt[ks * 32];
+      mma_tf32_16x8x8(acc, ah, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32_16x8x8(acc, al, __float_as_uint(b.x), __float_as_uint(b.y));
+      pa += 8;
+    }
+    float lm[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lm[e] = 3.01029995663981195f * log2f(fmaxf(acc[e], 1e-10f));   // 10 log10(.)
+    *reinterpret_cast<float2*>(&s_out[g][8 * warp + 2 * t4]) = make_float2(lm[0], lm[1]);
+    *reinterpret_cast<float2*>(&s_out[g + 8][8 * warp + 2 * t4]) = make_float2(lm[2], lm[3]);
+  }
+  __syncthreads();                   // log-mel rows of the tile complete
   // ---- DCT-II (orthonormal), first 40 coefficients, for the warp's two frames at once (every 128-bit row of the
   //      table is loaded once and used twice): lane c does coefficient c over all 64 bands; the last 8
   //      coefficients are split four ways over the bands (lane -> coefficient 32 + (lane & 7), bands
@@ -343,8 +387,8 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   {
     const bool two = t0 + warp + FE_WARPS < n_frames;         // warp-uniform: does the second frame exist?
     if (t0 + warp < n_frames) {
-      const float4* lmA = reinterpret_cast<const float4*>(&s_lm[warp][0][0]);
-      const float4* lmB = reinterpret_cast<const float4*>(&s_lm[warp][two ? 1 : 0][0]);
+      const float4* lmA = reinterpret_cast<const float4*>(&s_out[warp][0]);
+      const float4* lmB = reinterpret_cast<const float4*>(&s_out[two ? warp + FE_WARPS : warp][0]);
       const float4* d4 = reinterpret_cast<const float4*>(s_dct + lane * DCT_LD);
       float a0 = 0.f, b0 = 0.f;
 #pragma unroll

@@ -81,7 +81,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < UST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     mbar_init(&sm.m2e, 1);
-    mbar_init(&sm.e2m, 128);
+    mbar_init(&sm.e2m, 4);                              // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -147,7 +147,8 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
     auto to_mma = [&]() {           // A operand written / accumulators drained: let the MMA warp start the next group
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&sm.e2m);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.e2m);
     };
     auto from_mma = [&]() {
       mbar_wait(&sm.m2e, op & 1);

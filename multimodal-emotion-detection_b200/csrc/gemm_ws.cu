@@ -1,16 +1,18 @@
 // Weight-stationary tcgen05 GEMM for the LSTM input projections (AVHOT_PREC_TC path):
-//     C[M, N] fp32 = A[M, K] (fp16) * W[N, K]^T (fp16),   M = B*T ~ 10^6 rows, N = 1024, K <= 320.
-// The bias rides in the GEMM itself: A carries two columns of ones against (bias_hi, bias_lo) columns of W, so the
-// epilogue - the bottleneck of this output-bound op - is a pure copy.
-// The op is bound by writing C (4 KB per row against <= 640 B of A), so the design minimises everything else:
-// a persistent CTA owns one 128-column block of W for its whole life (<= 80 KB of fp16 in shared memory, loaded
-// once by TMA) and walks down M; A tiles (128 rows x 64 k, 128-byte swizzle) stream through an 8-stage TMA ring;
-// accumulators rotate through four 128-column TMEM buffers so the epilogue of tile i overlaps the MMAs of tiles
-// i+1..i+3.  The 8 CTAs that share an M tile (one per column block) walk the same tile sequence, so A is read
-// from HBM once and served to the other seven from L2.
+//     C[M, N] = A[M, K] (fp16) * W[N, K]^T (fp16) + bias[N] (fp32),   M = B*T ~ 10^6 rows, N = 1024, K <= 320.
+// The op writes 2-4 KB per row against <= 640 B of A, and what bounded the first version (128-column blocks, ncu
+// r1y / r2b: epilogue warps idle on acc_full half of the time, the MMA thread waiting for A tiles) was the L2 -> SM
+// delivery of A: every SM pulled the whole A stream once per 128 output columns (~40 B/clk/SM, the same ceiling the
+// recurrent kernel's weight stream hits; TMA multicast across the column-block CTAs did not move it - each SM still
+// ingests every tile).  So a persistent CTA now owns a 256-column block of W for its whole life (160 KB of fp16 in
+// shared memory, loaded once by TMA) and walks down M; A tiles (128 rows x 64 k, 128-byte swizzle) stream through a
+// TMA ring (4 stages; 6 when K <= 256 leaves the fifth weight slot free - the ring depth is what covers the ~2 us
+// loaded L2 latency) and are used for twice the columns; two 256-column TMEM accumulators alternate so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  K is consumed in steps of 16 (the last k-block may be partial).  The 4 CTAs that share an M tile walk the same tile sequence, so A is read
+// from HBM once and served to the other three from L2.
 //   warp 0     TMA producer (W block once, then the A ring)
-//   warp 1     TMEM allocation + one lane issuing tcgen05.mma kind::f16 (M 128, N 128, K 16)
-//   warps 2-9  two epilogue warpgroups (even / odd tiles): tcgen05.ld (thread = row) -> 256-bit global stores
+//   warp 1     TMEM allocation + one lane issuing tcgen05.mma kind::f16 (M 128, N 256, K 16)
+//   warps 2-9  two epilogue warpgroups (even / odd tiles): tcgen05.ld (thread = row) -> 128-bit global stores
 // Layer 0's A is the fp16 3-way split [hi | lo | hi] of the features against W = [hi | hi | lo] (see lstm.cu), which
 // makes this single fp16 pass fp32-class; layer 1's A is the fp16 hidden sequence written by the recurrent kernel.
 #include <cuda_fp16.h>
@@ -21,19 +23,20 @@
 namespace avhot {
 namespace tc {
 
-constexpr int WBM = 128, WBN = 128, WKB_MAX = 5, WST = 8, WACC = 4, WTHREADS = 320;
+constexpr int WBM = 128, WBN = 256, WKB_MAX = 5, WST = 4, WST_MAX = 6, WACC = 2, WTHREADS = 320;
 
 struct GemmWsSmem {
-  __half w[WKB_MAX][WBN * 64];   // the CTA's weight block, one 16 KB tile per 64-wide k-block
-  __half a[WST][WBM * 64];       // A ring
-  uint64_t w_full, full[WST], empty[WST], acc_full[WACC], acc_empty[WACC];
+  __half w[WKB_MAX][WBN * 64];   // the CTA's weight block, one 32 KB tile per 64-wide k-block
+  __half a[WST][WBM * 64];       // A ring (stages 4, 5 live in w[4] when nkb <= 4)
+  float bias[WBN];
+  uint64_t w_full, full[WST_MAX], empty[WST_MAX], acc_full[WACC], acc_empty[WACC];
   uint32_t tmem_base;
 };
 
 template <bool OUT_F16>
 __global__ void __launch_bounds__(WTHREADS, 1)
 gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   float* __restrict__ C, int ldc, int M, int nkb, int n_blocks,
+                   const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int nk16, int n_blocks,
                    int groups) {
   extern __shared__ unsigned char gemm_ws_smem_raw[];
   GemmWsSmem& sm = *reinterpret_cast<GemmWsSmem*>((reinterpret_cast<uintptr_t>(gemm_ws_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -42,13 +45,17 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int n0 = nb * WBN;
   const int m_tiles = (M + WBM - 1) / WBM;
   const int my_tiles = grp < m_tiles ? (m_tiles - grp + groups - 1) / groups : 0;
+  const int nkb = (nk16 + 3) >> 2;
+  const int n_st = nkb <= 4 ? WST_MAX : WST;
+  auto stage = [&](int s) -> __half* { return s < WST ? sm.a[s] : sm.w[WKB_MAX - 1] + (s - WST) * (WBM * 64); };
+  for (int i = threadIdx.x; i < WBN; i += WTHREADS) sm.bias[i] = bias ? __ldg(bias + n0 + i) : 0.f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     mbar_init(&sm.w_full, 1);
-    for (int s = 0; s < WST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < WACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 128); }
+    for (int s = 0; s < WST_MAX; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < WACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -64,14 +71,22 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       mbar_expect_tx(&sm.w_full, (uint32_t)(nkb * sizeof(sm.w[0])));
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sm.w[kb], &tmW, &sm.w_full, kb * 64, n0);
+      // A tiles come from HBM for the first of the n_blocks CTAs that touches them, while HBM is busy absorbing C
+      // (ncu r2h: tensor pipe 50 % active, the MMA thread waiting for A): the CTA whose column block matches the
+      // tile index pulls the tile WPF iterations ahead into L2
+      constexpr int WPF = 3;
       uint32_t it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int m0 = (grp + i * groups) * WBM;
+        if (i + WPF < my_tiles && (i + WPF) % n_blocks == nb) {
+          const int mp = (grp + (i + WPF) * groups) * WBM;
+          for (int kb = 0; kb < nkb; ++kb) tma_prefetch_l2_2d(&tmA, kb * 64, mp);
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % WST;
-          mbar_wait(&sm.empty[s], ((it / WST) & 1) ^ 1);
+          const int s = it % n_st;
+          mbar_wait(&sm.empty[s], ((it / n_st) & 1) ^ 1);
           mbar_expect_tx(&sm.full[s], (uint32_t)sizeof(sm.a[0]));
-          tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * 64, m0);
+          tma_load_2d(stage(s), &tmA, &sm.full[s], kb * 64, m0);
         }
       }
     }
@@ -86,13 +101,13 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&sm.acc_empty[b], ((uint32_t)(i / WACC) & 1) ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % WST;
-          mbar_wait(&sm.full[s], (it / WST) & 1);
+          const int s = it % n_st;
+          mbar_wait(&sm.full[s], (it / n_st) & 1);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sm.a[s]));
+          const uint64_t adesc = umma_desc_sw128(smem_u32(stage(s)));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.w[kb]));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
+          const int nk = min(4, nk16 - 4 * kb);
+          for (int k = 0; k < nk; ++k)
             umma_f16(tmem + (uint32_t)(b * WBN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&sm.empty[s]);
         }
@@ -120,9 +135,9 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tmem_ld32(tlane + (uint32_t)(b * WBN + c + 32), r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cbase[(size_t)(c + j) * WBM] = __uint_as_float(r0[j]);
+          for (int j = 0; j < 32; ++j) cbase[(size_t)(c + j) * WBM] = __uint_as_float(r0[j]) + sm.bias[c + j];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cbase[(size_t)(c + 32 + j) * WBM] = __uint_as_float(r1[j]);
+          for (int j = 0; j < 32; ++j) cbase[(size_t)(c + 32 + j) * WBM] = __uint_as_float(r1[j]) + sm.bias[c + 32 + j];
         }
       } else {
         // fp16 output: groups of 8 consecutive columns of a row packed into 16 bytes ->
@@ -140,7 +155,8 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const __half2 v = __floats2half2_rn(__uint_as_float(r0[j + 2 * e]), __uint_as_float(r0[j + 2 * e + 1]));
+              const float2 bb = *reinterpret_cast<const float2*>(&sm.bias[c + j + 2 * e]);
+              const __half2 v = __floats2half2_rn(__uint_as_float(r0[j + 2 * e]) + bb.x, __uint_as_float(r0[j + 2 * e + 1]) + bb.y);
               pk[e] = *reinterpret_cast<const uint32_t*>(&v);
             }
             cbase[(size_t)((c + j) / 8) * WBM] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -150,7 +166,8 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const __half2 v = __floats2half2_rn(__uint_as_float(r1[j + 2 * e]), __uint_as_float(r1[j + 2 * e + 1]));
+              const float2 bb = *reinterpret_cast<const float2*>(&sm.bias[c + 32 + j + 2 * e]);
+              const __half2 v = __floats2half2_rn(__uint_as_float(r1[j + 2 * e]) + bb.x, __uint_as_float(r1[j + 2 * e + 1]) + bb.y);
               pk[e] = *reinterpret_cast<const uint32_t*>(&v);
             }
             cbase[(size_t)((c + 32 + j) / 8) * WBM] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -158,7 +175,8 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
       tc_fence_before();
-      mbar_arrive(&sm.acc_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.acc_empty[b]);      // one arrival per epilogue warp
     }
   }
   tc_fence_before();
@@ -168,15 +186,15 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 }  // namespace tc
 
-// a, w fp16 row-major (K contiguous); M % 128 == 0 (caller pads); N % 128 == 0; K <= 320;
+// a, w fp16 row-major (K contiguous); M % 128 == 0 (caller pads); N % 256 == 0; K <= 320;
 // c in the tile-transposed layout: fp32 [M / 128][N = ldc][128], or fp16 column octets [M / 128][N / 8][128][8]
-int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, void* c_out, bool out_f16, int ldc, int M, int N,
-                int K, cudaStream_t s, const char* prof_name) {
+int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, const float* bias, void* c_out, bool out_f16, int ldc,
+                int M, int N, int K, cudaStream_t s, const char* prof_name) {
   float* c = reinterpret_cast<float*>(c_out);
   using namespace tc;
   AVHOT_REQUIRE(a && w && c && M >= 0 && N > 0 && K > 0, AVHOT_ERR_INVALID, "gemm_ws: bad arguments");
   AVHOT_REQUIRE(M % WBM == 0 && N % WBN == 0 && ldc == N && K <= 64 * WKB_MAX && (lda & 7) == 0 && (ldw & 7) == 0,
-                AVHOT_ERR_UNSUPPORTED, "gemm_ws: needs M, N %% 128 == 0, ldc == N, K <= 320, lda/ldw %% 8 == 0 "
+                AVHOT_ERR_UNSUPPORTED, "gemm_ws: needs M %% 128 == 0, N %% 256 == 0, ldc == N, K <= 320, lda/ldw %% 8 == 0 "
                 "(M=%d N=%d K=%d)", M, N, K);
   if (M == 0) return AVHOT_OK;
   CUtensorMap tmA, tmW;
@@ -189,15 +207,15 @@ int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, void* c_out, boo
   int groups = num_sms() / n_blocks;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
-  const int nkb = ceil_div(K, 64);
+  const int nk16 = ceil_div(K, 16);
   const int smem = (int)sizeof(GemmWsSmem) + 1024;
   ProfScope prof(prof_name, s);
   if (out_f16) {
     AVHOT_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm_f16_ws_kernel<true><<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, c, ldc, M, nkb, n_blocks, groups);
+    gemm_f16_ws_kernel<true><<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, bias, c, ldc, M, nk16, n_blocks, groups);
   } else {
     AVHOT_CUDA(cudaFuncSetAttribute(gemm_f16_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm_f16_ws_kernel<false><<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, c, ldc, M, nkb, n_blocks, groups);
+    gemm_f16_ws_kernel<false><<<n_blocks * groups, WTHREADS, smem, s>>>(tmA, tmW, bias, c, ldc, M, nk16, n_blocks, groups);
   }
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;

@@ -117,7 +117,8 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // fp16 tensor-core GEMM over K' = 3K into A W^T - lo(A) lo(W)^T - O(2^-22), i.e. an fp32-class product: used for
 // layer 0's input projection, whose inputs (log-mel features in dB, |x| ~ 100) are far too large for a single
 // half-precision pass (measured 5.7e-3 error with one TF32 pass).  Requires |x| < 65504.
-// weights: W (N, K) fp32 -> out (N, ldo) fp16 = [W_hi | W_hi | W_lo | bias_hi, bias_lo | 0...]  (ldo >= 3K + 2)
+// weights: W (N, K) fp32 -> out (N, ldo) fp16 = [W_hi | W_hi | W_lo | 0...]  (ldo >= 3K + 2; the operand's
+// (1, 1) columns meet zeros: the bias is added in fp32 by the GEMM epilogue)
 __global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                      __half* __restrict__ out, int N, int K, int ldo) {
   const int n = blockIdx.x;
@@ -126,13 +127,11 @@ __global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* _
     bool lo = false;
     if (k < 2 * K) v = w[(size_t)n * K + (k % K)];
     else if (k < 3 * K) { v = w[(size_t)n * K + (k - 2 * K)]; lo = true; }
-    else if (k == 3 * K) v = bias[n];
-    else if (k == 3 * K + 1) { v = bias[n]; lo = true; }
     const __half hi = __float2half_rn(v);
     out[(size_t)n * ldo + k] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
   }
 }
-// weights of layers > 0: W (N, K) fp32 -> out (N, ldo) fp16 = [W | bias_hi, bias_lo | 0...]
+// weights of layers > 0: W (N, K) fp32 -> out (N, ldo) fp16 = [W | 0...]
 __global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                    __half* __restrict__ out, int N, int K, int ldo) {
   const int n = blockIdx.x;
@@ -140,10 +139,7 @@ __global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __r
     float v = 0.f;
     bool lo = false;
     if (k < K) v = w[(size_t)n * K + k];
-    else if (k == K) v = bias[n];
-    else if (k == K + 1) { v = bias[n]; lo = true; }
-    const __half hi = __float2half_rn(v);
-    out[(size_t)n * ldo + k] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+    out[(size_t)n * ldo + k] = __float2half_rn(v);
   }
 }
 // activations: x (B, T, K) batch-major -> out (T, Bp, ldo) time-major [hi | lo | hi | 1, 1 | 0...]; the rows of the
@@ -212,7 +208,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   }
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
-  total += align256(2 * 4 * H * pad8(3 * d->input_dim + 2)) + (L - 1) * align256(2 * 4 * H * pad8(H + 2));
+  total += align256(2 * 4 * H * pad8(3 * d->input_dim + 2)) + (L - 1) * align256(2 * 4 * H * H);
   avhot_lstm* h = new avhot_lstm();
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
@@ -245,7 +241,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
       pack_w_split3_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[0], h->bias[0], reinterpret_cast<__half*>(h->w_ih_f16[0]),
                                                  4 * H, d->input_dim, ldo);
     } else {
-      const int ldo = pad8(H + 2);
+      const int ldo = H;
       h->w_ih_f16[l] = take(2 * 4 * H * ldo);
       pack_w_bias_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[l], h->bias[l], reinterpret_cast<__half*>(h->w_ih_f16[l]),
                                                4 * H, H, ldo);
@@ -345,10 +341,13 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
       // layer 0's pre-activations reach |xp| ~ 20; AVHOT_XP0_F32=1 keeps layer 0's xp in fp32.
       static const bool xp0_f32 = [] { const char* e = getenv("AVHOT_XP0_F32"); return e && atoi(e) != 0; }();
       const bool xf16 = l > 0 || !xp0_f32;
-      const int hp = pad8(H + 2);                      // fp16 pitch of h_seq: H columns + (1, 1) for the bias columns
+      const int hp = H;                                // fp16 pitch of h_seq
+      // layer 0: A = [hi | lo | hi] x W = [W_hi | W_hi | W_lo] (K = 3 in), an fp32-class product; AVHOT_L0_TERMS=2
+      // drops the hi x W_lo term (K = 2 in: the first two blocks of the same operands)
+      static const int l0_terms = [] { const char* e = getenv("AVHOT_L0_TERMS"); return e && atoi(e) == 2 ? 2 : 3; }();
       if (l == 0 && seq_split) {                      // operand already prepared by avhot_frontend_ex
         const int ldx = pad8(3 * in + 2);
-        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, xp, xf16, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, h->bias[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
       } else if (l == 0) {
         const int ldx = pad8(3 * in + 2);
         {
@@ -359,9 +358,9 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
               x, x_split, B, (int)Bp, T, in, ldx);
           AVHOT_LAUNCH_CHECK();
         }
-        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, xp, xf16, 4 * H, Mp, 4 * H, 3 * in + 2, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, h->bias[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
       } else {
-        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, xp, true, 4 * H, Mp, 4 * H, H + 2, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, h->bias[l], xp, true, 4 * H, Mp, 4 * H, H, s, "lstm_input_gemm_tc");
       }
       if (rc == AVHOT_OK)
         rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, xf16, last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);

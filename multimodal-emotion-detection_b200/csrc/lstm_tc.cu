@@ -16,7 +16,10 @@
 // mbarriers: full/empty per weight stage, acc_full/acc_empty per TMEM buffer, h_ready per 64-unit k-block of
 // the hidden state (so step t+1 starts on k-block 0 while the epilogue of step t finishes k-block 3).
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -86,11 +89,28 @@ template <int ACT> __device__ __forceinline__ float act_tanh(float x) {
   return y;
 }
 
-template <int ACT, bool XP16>
+// TRACE (debug, AVHOT_REC_TRACE=<file>): CTA 0 records clock64() at eight points of every chunk of steps
+// [TRACE_T0, TRACE_T0 + TRACE_NT) into `trace` ([step][chunk][event]); see lstm_recurrence_tc for the dump.
+constexpr int TRACE_T0 = 100, TRACE_NT = 4;
+// CL > 1: launched in clusters of CL CTAs that share the W_hh stream - CTA rank r loads rows [r, r + 1) * 128 / CL of
+// every weight tile and multicasts them to all CL CTAs (the r2c trace showed the MMA thread paced by the arrival
+// of the weight tiles: 148 CTAs x 512 KB per step is ~2/3 of this kernel's L2 traffic).  A stage may be refilled only
+// when every CTA of the cluster has consumed it, so the MMA thread's release is a multicast commit and empty[] counts
+// CL arrivals.  The grid is rounded up to a multiple of CL; CTAs past n_ct redo the last clip tile and write nothing.
+template <int ACT, bool XP16, bool TRACE = false, int CL = 1>
 __global__ void __launch_bounds__(RTHREADS, 1)
 lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp, __half* __restrict__ h_seq,
                    int h_pitch,
-                   float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T) {
+                   float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T, int n_ct_arg,
+                   long long* __restrict__ trace = nullptr) {
+  const int ctile = min((int)blockIdx.x, n_ct_arg - 1);
+  const bool writer = (int)blockIdx.x < n_ct_arg;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  auto tr = [&](int t, int c, int ev) {
+    if (TRACE && blockIdx.x == 0 && t >= TRACE_T0 && t < TRACE_T0 + TRACE_NT)
+      trace[((t - TRACE_T0) * RNC + c) * 8 + ev] = clock64();
+  };
   extern __shared__ unsigned char rec_smem_raw[];
   RecSmem& sm = *reinterpret_cast<RecSmem*>((reinterpret_cast<uintptr_t>(rec_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,9 +123,9 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < RST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 512); }
-    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 1024);   // 512 epilogue threads x the 2 chunks of a k-block
+    for (int s = 0; s < RST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 16); }
+    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 32);   // 16 epilogue warps x the 2 chunks of a k-block
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -114,6 +134,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();             // every CTA's barriers are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
@@ -126,7 +147,11 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
             const int s = it % RST;
             mbar_wait(&sm.empty[s], ((it / RST) & 1) ^ 1);
             mbar_expect_tx(&sm.full[s], (uint32_t)sizeof(sm.wB[0]));
-            tma_load_2d(sm.wB[s], &tmW, &sm.full[s], kb * 64, c * RN);
+            if (CL == 1)
+              tma_load_2d(sm.wB[s], &tmW, &sm.full[s], kb * 64, c * RN);
+            else
+              tma_load_2d_mc(sm.wB[s] + crank * (RN / CL) * 64, &tmW, &sm.full[s], kb * 64,
+                             c * RN + (int)crank * (RN / CL), cmask);
           }
     }
   } else if (warp == 1) {
@@ -138,19 +163,24 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
           const int b = c & 1;
           mbar_wait(&sm.acc_empty[b], (use[b] & 1) ^ 1);
           tc_fence_after();
+          tr(t, c, 0);
           for (int kb = 0; kb < RKB; ++kb, ++it) {
             if (c == 0 && t > 0) mbar_wait(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+            if (kb == RKB - 1) tr(t, c, 7);
             const int s = it % RST;
             mbar_wait(&sm.full[s], (it / RST) & 1);
             tc_fence_after();
+            if (kb == RKB - 1) tr(t, c, 1);
             const uint64_t adesc = umma_desc_sw128(smem_u32(sm.hA[t & 1][kb]));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s]));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_f16(tmem + (uint32_t)(b * RN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&sm.empty[s]);
+            if (CL == 1) umma_commit(&sm.empty[s]);
+            else umma_commit_mc(&sm.empty[s], cmask);
           }
           umma_commit(&sm.acc_full[b]);
+          tr(t, c, 2);
           ++use[b];
         }
       }
@@ -163,8 +193,8 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     const int q = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // clip row = TMEM lane
-    const int clip = blockIdx.x * RB + r;
-    const bool live = clip < B;
+    const int clip = ctile * RB + r;
+    const bool live = writer && clip < B;
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
     const int last_t = (live && lengths ? min(max(__ldg(lengths + clip), 1), T) : T) - 1;
     {                                                         // c_{-1} = 0 for the units this thread owns
@@ -178,9 +208,9 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     // xp is time-major and tile-transposed (gemm_ws.cu): [t][clip tile][4H columns][128 clips]; h_seq is the
     // time-major padded fp16 sequence (T, Bp, pitch) that is the next layer's GEMM operand (rows of dead clips are
     // written too, so the operand is fully initialised)
-    const size_t n_ct = gridDim.x;
-    const float* xcol = xp + (size_t)blockIdx.x * (4 * RH) * RB + r;
-    __half* hrow = h_seq ? h_seq + ((size_t)blockIdx.x * RB + r) * h_pitch : nullptr;
+    const size_t n_ct = (size_t)n_ct_arg;
+    const float* xcol = xp + (size_t)ctile * (4 * RH) * RB + r;
+    __half* hrow = h_seq && writer ? h_seq + ((size_t)ctile * RB + r) * h_pitch : nullptr;
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
 
     // xp registers hold what was loaded, unconverted: the loads of the item two chunks ahead stay in flight until
@@ -199,7 +229,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
           for (int j = 0; j < 8; ++j) xr[g * 8 + j] = __float_as_uint(ldg_stream(src + (size_t)(g * RH + j) * RB));
       } else {
         // fp16 xp: [t][clip tile][4H / 8 octets][128 clips][8 halves] (gemm_ws.cu)
-        const uint4* src = reinterpret_cast<const uint4*>(xp) + ((size_t)t * n_ct + blockIdx.x) * (4 * RH / 8) * RB + r +
+        const uint4* src = reinterpret_cast<const uint4*>(xp) + ((size_t)t * n_ct + ctile) * (4 * RH / 8) * RB + r +
                            (size_t)((c * RCH + q * 8) / 8) * RB;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -220,15 +250,20 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       const int b = c & 1, u0 = c * RCH + q * 8;
       mbar_wait(&sm.acc_full[b], use[b] & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) tr(t, c, 3);
       uint32_t acc[4][8], cs[8];
       tmem_st_wait();                          // the cell-state store of this thread's previous item has landed
 #pragma unroll
       for (int g = 0; g < 4; ++g) tmem_ld8(tlane + (uint32_t)(b * RN + g * RCH + q * 8), acc[g]);
       tmem_ld8(tlane + 256u + (uint32_t)u0, cs);
       tmem_ld_wait();
+      if (threadIdx.x == 64) tr(t, c, 4);
       // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the activation math
+      // (one arrival per warp: 512 per-thread arrivals on one mbarrier serialised into ~1000 cycles per chunk -
+      // the r2c / r2d clock traces showed the MMA thread passing acc_empty 600-800 cycles after the loads were done)
       tc_fence_before();
-      mbar_arrive(&sm.acc_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.acc_empty[b]);
       ++use[b];
       float hn[8];
 #pragma unroll
@@ -241,6 +276,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
         cs[j] = __float_as_uint(cn);
         hn[j] = og * act_tanh<ACT>(cn);
       }
+      if (threadIdx.x == 64) tr(t, c, 5);
       tmem_st8(tlane + 256u + (uint32_t)u0, cs);
       // h_t (fp16) -> A operand of step t+1: k-block u0 / 64, 16-byte chunk (u0 % 64) / 8, XOR-swizzled by the row
       uint32_t pk[4];
@@ -262,7 +298,9 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       // next use of this register buffer: the same quarter of chunk c + 2 (or of the next step)
       load_x(c + 2 < RNC ? t : t + 1, c + 2 < RNC ? c + 2 : c + 2 - RNC, xg);
       fence_proxy_async_smem();                // this thread's part of k-block c/2 of h_t is written
-      mbar_arrive(&sm.h_ready[c >> 1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.h_ready[c >> 1]);
+      if (threadIdx.x == 64) tr(t, c, 6);
     };
     uint32_t xa[XR], xb[XR];
     load_x(0, 0, xa);
@@ -278,6 +316,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();             // no CTA leaves while a peer can still signal its barriers
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -297,29 +336,115 @@ int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s) {
   return AVHOT_OK;
 }
 
+template <typename Kern, typename... Args>
+static int rec_launch(Kern kern, int cl, int n_ct, int smem, cudaStream_t s, Args... args) {
+  AVHOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ceil_div(n_ct, cl) * cl));
+  cfg.blockDim = dim3(tc::RTHREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cl > 1 ? 1 : 0;
+  AVHOT_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return AVHOT_OK;
+}
+
+// how many CTAs may share the weight stream: the largest cluster size in {4, 2} whose clusters are all co-resident
+// for this grid (one CTA per SM; a second wave would double the run time), else 1.  AVHOT_REC_CLUSTER overrides.
+template <typename K2, typename K4>
+static int rec_cluster_size(K2 k2, K4 k4, int n_ct, int smem) {
+  static const int forced = [] { const char* e = getenv("AVHOT_REC_CLUSTER"); return e ? atoi(e) : 0; }();
+  if (forced == 1) return 1;
+  int best = 1;
+  for (int cl = 2; cl <= 4; cl *= 2) {
+    if (forced && forced != cl) continue;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ceil_div(n_ct, cl) * cl));
+    cfg.blockDim = dim3(tc::RTHREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e;
+    if (cl == 2) {
+      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      e = cudaOccupancyMaxActiveClusters(&n, k2, &cfg);
+    } else {
+      cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      e = cudaOccupancyMaxActiveClusters(&n, k4, &cfg);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); continue; }
+    if (n * cl >= ceil_div(n_ct, cl) * cl) best = cl;
+  }
+  return best;
+}
+
 int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_f16, void* h_seq_f16, int h_pitch,
                        float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
   const float* xp = reinterpret_cast<const float*>(xp_any);
   __half* h_seq = reinterpret_cast<__half*>(h_seq_f16);
   using namespace tc;
-  CUtensorMap tmW;
-  int rc = make_tensor_map_2d(&tmW, whh_packed_fp16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * RH, RH, RH, RN, 64);
-  if (rc != AVHOT_OK) return rc;
   const int smem = (int)sizeof(RecSmem) + 1024;
+  const int n_ct = ceil_div(B, RB);
   // tanh.approx (one MUFU per activation) measured as accurate as ex2 + rcp here (5e-4 vs the fp64 oracle: the
   // error is set by the fp16 state); AVHOT_LSTM_ACT=0 selects the ex2 + rcp form.
   static const int act = [] { const char* e = getenv("AVHOT_LSTM_ACT"); return e ? atoi(e) : 1; }();
+  const bool fast = act == 1 && xp_f16;                       // the benchmarked configuration
+  const int cl = fast && n_ct > 1 ? rec_cluster_size(lstm_rec_tc_kernel<1, true, false, 2>,
+                                                     lstm_rec_tc_kernel<1, true, false, 4>, n_ct, smem) : 1;
+  CUtensorMap tmW;
+  int rc = make_tensor_map_2d(&tmW, whh_packed_fp16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * RH, RH, RH, RN / cl, 64);
+  if (rc != AVHOT_OK) return rc;
+  static const char* trace_path = getenv("AVHOT_REC_TRACE");
+  if (trace_path && fast && T >= TRACE_T0 + TRACE_NT) {     // debug: one traced launch, dumped as text
+    long long* d_trace = nullptr;
+    const size_t n = (size_t)TRACE_NT * RNC * 8;
+    AVHOT_CUDA(cudaMalloc(&d_trace, n * sizeof(long long)));
+    AVHOT_CUDA(cudaMemsetAsync(d_trace, 0, n * sizeof(long long), s));
+    if (cl == 4) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, 4>, 4, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    else if (cl == 2) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, 2>, 2, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    else rc = rec_launch(lstm_rec_tc_kernel<1, true, true, 1>, 1, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    if (rc != AVHOT_OK) return rc;
+    AVHOT_LAUNCH_CHECK();
+    std::vector<long long> host(n);
+    AVHOT_CUDA(cudaMemcpyAsync(host.data(), d_trace, n * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    AVHOT_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_trace);
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "# B=%d T=%d cluster=%d  events: 0 mma:acc_empty 7 mma:h_ready(kb3) 1 mma:w_full(kb3) 2 mma:commit 3 epi:acc_full 4 epi:ld 5 epi:math 6 epi:end\n", B, T, cl);
+      for (int i = 0; i < TRACE_NT * RNC; ++i) {
+        fprintf(f, "t=%d c=%d", TRACE_T0 + i / RNC, i % RNC);
+        for (int e = 0; e < 8; ++e) fprintf(f, " %lld", host[i * 8 + e] - host[0]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    return AVHOT_OK;
+  }
   ProfScope prof("lstm_recurrence_tc", s);
-#define AVHOT_REC_LAUNCH(ACT_, X16_)                                                                                \
-  do {                                                                                                              \
-    AVHOT_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<ACT_, X16_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    lstm_rec_tc_kernel<ACT_, X16_><<<ceil_div(B, RB), RTHREADS, smem, s>>>(tmW, xp, h_seq, h_pitch, h_last, lengths, B, T); \
-  } while (0)
-  if (act == 1 && xp_f16) AVHOT_REC_LAUNCH(1, true);
-  else if (act == 1) AVHOT_REC_LAUNCH(1, false);
-  else if (xp_f16) AVHOT_REC_LAUNCH(0, true);
-  else AVHOT_REC_LAUNCH(0, false);
+  long long* no_trace = nullptr;
+#define AVHOT_REC_LAUNCH(ACT_, X16_, CL_)                                                                           \
+  rc = rec_launch(lstm_rec_tc_kernel<ACT_, X16_, false, CL_>, CL_, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last,  \
+                  lengths, B, T, n_ct, no_trace)
+  if (fast && cl == 4) AVHOT_REC_LAUNCH(1, true, 4);
+  else if (fast && cl == 2) AVHOT_REC_LAUNCH(1, true, 2);
+  else if (fast) AVHOT_REC_LAUNCH(1, true, 1);
+  else if (act == 1) AVHOT_REC_LAUNCH(1, false, 1);
+  else if (xp_f16) AVHOT_REC_LAUNCH(0, true, 1);
+  else AVHOT_REC_LAUNCH(0, false, 1);
 #undef AVHOT_REC_LAUNCH
+  if (rc != AVHOT_OK) return rc;
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }
