@@ -15,7 +15,10 @@
 //               fp32), the weights are TF32-rounded once on the host (<= 2^-11 relative on a filter tap, i.e.
 //               <= 0.002 dB on a log-mel value); B fragments are stored in lane order (one 64-bit load per step);
 //               10 log10 in the accumulator registers -> output tile;
-//   DCT phase   40 x 64 DCT-II in fp32 FMA, a warp's two frames per table read -> output tile;
+//   DCT phase   40 x 64 orthonormal DCT-II, also mma.sync TF32 tiles, folded by the symmetry D[c][63-j] = (-1)^c D[c][j]
+//               (even coefficients see lm[j] + lm[63-j], odd ones lm[j] - lm[63-j]: K = 32) and error-compensated
+//               (operands split hi + lo, three MMAs per step: fp32-class, the log-mel values are ~100 dB);
+//               warp (parity, 8-coefficient tile) = six warps -> output tile;
 //   store       coalesced 128-bit stores of the fp32 features and / or the LSTM's fp16 split operand.
 // (The sparse per-lane filter walk this replaces cost ~130 of the ~480 shared-memory wavefronts per frame of a
 // kernel that ncu shows bound by shared-memory bandwidth: l1tex 88 %, r1y.)
@@ -37,7 +40,8 @@ constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
 constexpr int ZPAD = 256 + 16;     // padded complex buffer (index i -> i + (i >> 4))
 constexpr int MEL_KS_MAX = 44;     // 8-bin steps summed over the eight 8-filter tiles (41 for the Slaney bank used here)
 constexpr int POW_LD = 260;        // pitch of a power-spectrum row: 256 bins + 4 (conflict-free A-fragment loads)
-constexpr int DCT_LD = N_MELS + 4; // padded row length of the DCT table
+constexpr int OUT_LD = 108;        // pitch of an output-tile row (conflict-free A-fragment loads of the log-mel part)
+constexpr int DCT_TILES = 6;       // (parity, 8-coefficient tile): coefficient c = 2 (8 tile + n) + parity, n = 0..7
 
 struct FrontendTables {            // device layout, all fp32 unless noted
   float window[N_FFT];
@@ -49,7 +53,9 @@ struct FrontendTables {            // device layout, all fp32 unless noted
   int mel_k0[8];                   // first 8-bin step of filter tile j
   int mel_nk[8];                   // number of steps
   int mel_off[8];                  // index of the tile's first step in mel_b
-  float dct_p[N_MFCC * DCT_LD];    // dct_p[c * 68 + j] = C[c][j]; padded rows: conflict-free 128-bit row reads
+  float4 dct_b[DCT_TILES * 4 * 32];  // B fragments of the folded DCT in lane order, (hi0, hi1, lo0, lo1) per lane:
+                                     //   tile (p, nt) = 3 p + nt, step ks, lane l -> D[c][8 ks + (l & 3) (+ 4)],
+                                     //   c = 2 (8 nt + (l >> 2)) + p (zero rows for c >= 40)
 };
 
 static FrontendTables g_host_tables;
@@ -132,8 +138,17 @@ static void build_tables() {
       double v = cos(PI * (j + 0.5) * c / N_MELS) * sqrt(2.0 / N_MELS);
       if (c == 0) v *= sqrt(0.5);
       g_host_dct[c * N_MELS + j] = (float)v;
-      t.dct_p[c * DCT_LD + j] = (float)v;
     }
+  for (int p = 0; p < 2; ++p)
+    for (int nt = 0; nt < 3; ++nt)
+      for (int ks = 0; ks < 4; ++ks)
+        for (int l = 0; l < 32; ++l) {
+          const int c = 2 * (8 * nt + (l >> 2)) + p, j = 8 * ks + (l & 3);
+          const float d0 = c < N_MFCC ? g_host_dct[c * N_MELS + j] : 0.f;
+          const float d1 = c < N_MFCC ? g_host_dct[c * N_MELS + j + 4] : 0.f;
+          const float h0 = tf32_round(d0), h1 = tf32_round(d1);
+          t.dct_b[((3 * p + nt) * 4 + ks) * 32 + l] = make_float4(h0, h1, tf32_round(d0 - h0), tf32_round(d1 - h1));
+        }
 }
 
 constexpr int MAX_DEVICES = 64;
@@ -197,10 +212,10 @@ struct FeSmem {
   float2 tw2[64], tw3[256];
   float2 melb[MEL_KS_MAX * 32];
   int mel_k0[8], mel_nk[8], mel_off[8];
-  float dct[N_MFCC * DCT_LD];
+  float4 dctb[DCT_TILES * 4 * 32];
   union {                              // FFT scratch during the FFT phase, output tile afterwards
     float2 z[FE_WARPS][ZPAD];
-    float out[FPB][N_FEATS];
+    float out[FPB][OUT_LD];
   } u;
   float pow[FPB][POW_LD];
 };
@@ -230,10 +245,9 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   float* s_seg = sm.seg;
   float* s_win = sm.win;
   float2* s_tw = sm.tw;
-  float* s_dct = sm.dct;
   float2 (*s_z)[ZPAD] = sm.u.z;
   float (*s_pow)[POW_LD] = sm.pow;
-  float (*s_out)[N_FEATS] = sm.u.out;
+  float (*s_out)[OUT_LD] = sm.u.out;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int clip = blockIdx.y;
@@ -246,7 +260,7 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   for (int i = tid; i < 256; i += blockDim.x) sm.tw3[i] = tab->tw3[i];
   for (int i = tid; i < MEL_KS_MAX * 32; i += blockDim.x) sm.melb[i] = tab->mel_b[i];
   if (tid < 8) { sm.mel_k0[tid] = tab->mel_k0[tid]; sm.mel_nk[tid] = tab->mel_nk[tid]; sm.mel_off[tid] = tab->mel_off[tid]; }
-  for (int i = tid; i < N_MFCC * DCT_LD; i += blockDim.x) s_dct[i] = tab->dct_p[i];
+  for (int i = tid; i < DCT_TILES * 4 * 32; i += blockDim.x) sm.dctb[i] = tab->dct_b[i];
 
   // The tables are loaded once; the CTA then walks its tiles of FPB frames.  The raw samples of the NEXT tile are
   // fetched into registers before the frame loop of the current one, so their HBM latency hides behind the FFTs
@@ -380,49 +394,43 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     *reinterpret_cast<float2*>(&s_out[g + 8][8 * warp + 2 * t4]) = make_float2(lm[2], lm[3]);
   }
   __syncthreads();                   // log-mel rows of the tile complete
-  // ---- DCT-II (orthonormal), first 40 coefficients, for the warp's two frames at once (every 128-bit row of the
-  //      table is loaded once and used twice): lane c does coefficient c over all 64 bands; the last 8
-  //      coefficients are split four ways over the bands (lane -> coefficient 32 + (lane & 7), bands
-  //      16 (lane >> 3) ..) and combined with two shuffles.
-  {
-    const bool two = t0 + warp + FE_WARPS < n_frames;         // warp-uniform: does the second frame exist?
-    if (t0 + warp < n_frames) {
-      const float4* lmA = reinterpret_cast<const float4*>(&s_out[warp][0]);
-      const float4* lmB = reinterpret_cast<const float4*>(&s_out[two ? warp + FE_WARPS : warp][0]);
-      const float4* d4 = reinterpret_cast<const float4*>(s_dct + lane * DCT_LD);
-      float a0 = 0.f, b0 = 0.f;
+  // ---- DCT-II (orthonormal), first 40 coefficients, folded and error-compensated on the tensor cores:
+  //      warp = (parity p, tile nt): coefficients c = 2 (8 nt + n) + p over u[j] = lm[j] + (-1)^p lm[63 - j], j < 32
+  if (warp < DCT_TILES) {
+    const int p = warp & 1, nt = warp >> 1;
+    const int g = lane >> 2, t4 = lane & 3;
+    const float sgn = p ? -1.f : 1.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* r0 = &s_out[g][0];
+    const float* r1 = &s_out[g + 8][0];
+    const float4* bt = sm.dctb + (3 * p + nt) * 4 * 32 + lane;
 #pragma unroll
-      for (int j4 = 0; j4 < N_MELS / 4; ++j4) {
-        const float4 d = d4[j4], la = lmA[j4], lb = lmB[j4];
-        a0 = fmaf(la.x, d.x, a0); a0 = fmaf(la.y, d.y, a0); a0 = fmaf(la.z, d.z, a0); a0 = fmaf(la.w, d.w, a0);
-        b0 = fmaf(lb.x, d.x, b0); b0 = fmaf(lb.y, d.y, b0); b0 = fmaf(lb.z, d.z, b0); b0 = fmaf(lb.w, d.w, b0);
-      }
-      const int part = lane >> 3;
-      const float4* e4 = reinterpret_cast<const float4*>(s_dct + (32 + (lane & 7)) * DCT_LD + part * 16);
-      float a1 = 0.f, b1 = 0.f;
+    for (int ks = 0; ks < 4; ++ks) {
+      const int j = 8 * ks + t4;
+      const float x[4] = {fmaf(sgn, r0[63 - j], r0[j]), fmaf(sgn, r1[63 - j], r1[j]),
+                          fmaf(sgn, r0[59 - j], r0[j + 4]), fmaf(sgn, r1[59 - j], r1[j + 4])};
+      uint32_t ah[4], al[4];
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 d = e4[j4], la = lmA[part * 4 + j4], lb = lmB[part * 4 + j4];
-        a1 = fmaf(la.x, d.x, a1); a1 = fmaf(la.y, d.y, a1); a1 = fmaf(la.z, d.z, a1); a1 = fmaf(la.w, d.w, a1);
-        b1 = fmaf(lb.x, d.x, b1); b1 = fmaf(lb.y, d.y, b1); b1 = fmaf(lb.z, d.z, b1); b1 = fmaf(lb.w, d.w, b1);
+      for (int e = 0; e < 4; ++e) {
+        ah[e] = to_tf32(x[e]);
+        al[e] = to_tf32(x[e] - __uint_as_float(ah[e]));
       }
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 8);  a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-      b1 += __shfl_xor_sync(0xffffffffu, b1, 8);  b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-      s_out[warp][N_MELS + lane] = a0;
-      if (lane < 8) s_out[warp][N_MELS + 32 + lane] = a1;
-      if (two) {
-        s_out[warp + FE_WARPS][N_MELS + lane] = b0;
-        if (lane < 8) s_out[warp + FE_WARPS][N_MELS + 32 + lane] = b1;
-      }
+      const float4 b = bt[ks * 32];
+      mma_tf32_16x8x8(acc, ah, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32_16x8x8(acc, al, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32_16x8x8(acc, ah, __float_as_uint(b.z), __float_as_uint(b.w));
     }
+    const int ca = 2 * (8 * nt + 2 * t4) + p, cb = ca + 2;
+    if (ca < N_MFCC) { s_out[g][N_MELS + ca] = acc[0]; s_out[g + 8][N_MELS + ca] = acc[2]; }
+    if (cb < N_MFCC) { s_out[g][N_MELS + cb] = acc[1]; s_out[g + 8][N_MELS + cb] = acc[3]; }
   }
   __syncthreads();
   // coalesced store of the CTA's output tile (rows are contiguous in feats)
   const int rows = min(FPB, n_frames - t0);
   if (feats) {
     float4* dst = reinterpret_cast<float4*>(feats + ((size_t)clip * n_frames + t0) * N_FEATS);
-    const float4* srcv = reinterpret_cast<const float4*>(&s_out[0][0]);
-    for (int i = tid; i < rows * N_FEATS / 4; i += blockDim.x) dst[i] = srcv[i];
+    for (int i = tid; i < rows * (N_FEATS / 4); i += blockDim.x)
+      dst[i] = *reinterpret_cast<const float4*>(&s_out[i / (N_FEATS / 4)][4 * (i % (N_FEATS / 4))]);
   }
   if (xs) {
     // fused operand preparation for the tensor-core LSTM (lstm.cu): time-major rows (t, clip) of
