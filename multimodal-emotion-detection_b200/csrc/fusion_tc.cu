@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(UTHREADS, 1)
 fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
   extern __shared__ unsigned char fus_tc_smem_raw[];
   FusTcSmem& sm = *reinterpret_cast<FusTcSmem*>((reinterpret_cast<uintptr_t>(fus_tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const long long n_rows = (long long)P.B * P.T;
   const int n_tiles = (int)((n_rows + UB - 1) / UB);
   const int kv = P.dim_v / 64;                          // k-blocks of the video embedding
@@ -111,7 +111,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues (tc.cuh, umma_*_elect)
       constexpr uint32_t idesc = umma_idesc(FMT_F16, UB, 128);
       uint32_t it = 0, op = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -131,11 +131,11 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
                 const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s]));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(tmem + (uint32_t)(sg.dcol + nh * 128), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                umma_commit(&sm.empty[s]);
+                  umma_f16_elect(tmem + (uint32_t)(sg.dcol + nh * 128), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                umma_commit_elect(&sm.empty[s]);
               }
           }
-          umma_commit(&sm.m2e);
+          umma_commit_elect(&sm.m2e);
         }
     }
   } else {

@@ -69,7 +69,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ unsigned char gemm_tc_smem_raw[];
   GemmTcSmem<BN>& sm = *reinterpret_cast<GemmTcSmem<BN>*>(
       (reinterpret_cast<uintptr_t>(gemm_tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
   const int nkb = (K + TBK - 1) / TBK;
 
@@ -101,7 +101,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues (tc.cuh, umma_*_elect)
       constexpr uint32_t idesc = umma_idesc(FMT_TF32, TBM, BN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TSTAGES;
@@ -112,10 +112,10 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.w[s]));
 #pragma unroll
         for (int k = 0; k < TBK / 8; ++k)               // 8 fp32 = 32 bytes per MMA along K: +2 in the >>4 address
-          umma_tf32(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(&sm.empty[s]);                      // stage free once these MMAs have read it
+          umma_tf32_elect(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit_elect(&sm.empty[s]);                      // stage free once these MMAs have read it
       }
-      umma_commit(&sm.acc_full);
+      umma_commit_elect(&sm.acc_full);
     }
   } else {
     const int quarter = warp & 3;                       // the TMEM lanes this warp may access

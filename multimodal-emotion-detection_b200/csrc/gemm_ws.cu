@@ -40,7 +40,7 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    int groups) {
   extern __shared__ unsigned char gemm_ws_smem_raw[];
   GemmWsSmem& sm = *reinterpret_cast<GemmWsSmem*>((reinterpret_cast<uintptr_t>(gemm_ws_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int nb = blockIdx.x % n_blocks, grp = blockIdx.x / n_blocks;
   const int n0 = nb * WBN;
   const int m_tiles = (M + WBM - 1) / WBM;
@@ -91,7 +91,7 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues (tc.cuh, umma_*_elect)
       constexpr uint32_t idesc = umma_idesc(FMT_F16, WBM, WBN);
       mbar_wait(&sm.w_full, 0);
       tc_fence_after();
@@ -108,10 +108,10 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.w[kb]));
           const int nk = min(4, nk16 - 4 * kb);
           for (int k = 0; k < nk; ++k)
-            umma_f16(tmem + (uint32_t)(b * WBN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&sm.empty[s]);
+            umma_f16_elect(tmem + (uint32_t)(b * WBN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_elect(&sm.empty[s]);
         }
-        umma_commit(&sm.acc_full[b]);
+        umma_commit_elect(&sm.acc_full[b]);
       }
     }
   } else {

@@ -32,7 +32,7 @@ constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = 
 struct RecSmem {
   __half hA[2][RKB][RB * 64];   // hidden state, A operand: [step parity][k-block][128 rows x 128 B, swizzled]
   __half wB[RST][RN * 64];      // W_hh tile ring, B operand
-  uint64_t full[RST], empty[RST], acc_full[2], acc_empty[2], h_ready[RKB];
+  uint64_t full[2 * RST], empty[2 * RST], acc_full[2], acc_empty[2], h_ready[RKB];
   uint32_t tmem_base;
 };
 
@@ -91,13 +91,16 @@ template <int ACT> __device__ __forceinline__ float act_tanh(float x) {
 
 // TRACE (debug, AVHOT_REC_TRACE=<file>): CTA 0 records clock64() at eight points of every chunk of steps
 // [TRACE_T0, TRACE_T0 + TRACE_NT) into `trace` ([step][chunk][event]); see lstm_recurrence_tc for the dump.
-constexpr int TRACE_T0 = 100, TRACE_NT = 4;
-// CL > 1: launched in clusters of CL CTAs that share the W_hh stream - CTA rank r loads rows [r, r + 1) * 128 / CL of
-// every weight tile and multicasts them to all CL CTAs (the r2c trace showed the MMA thread paced by the arrival
-// of the weight tiles: 148 CTAs x 512 KB per step is ~2/3 of this kernel's L2 traffic).  A stage may be refilled only
-// when every CTA of the cluster has consumed it, so the MMA thread's release is a multicast commit and empty[] counts
-// CL arrivals.  The grid is rounded up to a multiple of CL; CTAs past n_ct redo the last clip tile and write nothing.
-template <int ACT, bool XP16, bool TRACE = false, int CL = 1>
+constexpr int TRACE_T0 = 100, TRACE_NT = 4, TRACE_EV = 12;
+// PAIR: two CTAs (a cluster of 2 = one tcgen05 CTA pair) share every W_hh tile.  The clock traces (r2c - r2e) and the
+// half-grid experiment (r2j) showed the kernel paced per SM by the arrival of its operands - 512 KB of weights plus
+// 256 KB of xp per step, ~40 B/clk/SM - not by the tensor pipe or the epilogue, and TMA multicast did not help (each SM
+// still ingests every tile).  With cta_group::2 each CTA loads only 64 of a tile's 128 gate rows (8 KB) and the
+// M = 256 MMA, issued by the leader CTA, reads both halves: the weight ingest per SM halves.  The leader's MMA thread
+// owns the pipeline: both CTAs' TMA loads complete the leader's full[] barriers, both CTAs' epilogue warps arrive on
+// the leader's acc_empty[] / h_ready[], and the leader's commits are multicast to both CTAs' empty[] / acc_full[].
+// The grid is rounded up to an even size; a CTA past n_ct redoes the last clip tile and writes nothing.
+template <int ACT, bool XP16, bool TRACE = false, bool PAIR = false>
 __global__ void __launch_bounds__(RTHREADS, 1)
 lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp, __half* __restrict__ h_seq,
                    int h_pitch,
@@ -105,15 +108,21 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
                    long long* __restrict__ trace = nullptr) {
   const int ctile = min((int)blockIdx.x, n_ct_arg - 1);
   const bool writer = (int)blockIdx.x < n_ct_arg;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  constexpr int WROWS = PAIR ? RN / 2 : RN;          // gate rows of a weight tile held by this CTA
+  // PAIR: a ring stage holds the four k-blocks of a whole chunk (4 x 8 KB per CTA), three stages in the same bytes:
+  // the MMA thread, whose serial instruction stream paces the tensor pipe (the issue of tcgen05.mma blocks for about
+  // the ~89 cycles an M128 N128 K16 takes, so every other instruction it executes between two MMAs is a pipe bubble:
+  // r2p trace, 583 cycles per k-block of which 356 are MMAs), then waits and commits once per chunk, not per k-block
+  constexpr int NST = PAIR ? 3 : RST;
   auto tr = [&](int t, int c, int ev) {
-    if (TRACE && blockIdx.x == 0 && t >= TRACE_T0 && t < TRACE_T0 + TRACE_NT)
-      trace[((t - TRACE_T0) * RNC + c) * 8 + ev] = clock64();
+    if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && t >= TRACE_T0 && t < TRACE_T0 + TRACE_NT)
+      trace[((t - TRACE_T0) * RNC + c) * TRACE_EV + ev] = clock64();
   };
   extern __shared__ unsigned char rec_smem_raw[];
   RecSmem& sm = *reinterpret_cast<RecSmem*>((reinterpret_cast<uintptr_t>(rec_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
   // h_{-1} = 0
   {
@@ -123,65 +132,118 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < RST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 16); }
-    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 32);   // 16 epilogue warps x the 2 chunks of a k-block
+    constexpr int NC = PAIR ? 2 : 1;            // CTAs whose epilogue warps arrive on the leader's barriers
+    for (int s = 0; s < NST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 16 * NC); }
+    for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 32 * NC);   // 16 epilogue warps x the 2 chunks of a k-block
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&sm.tmem_base, 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(&sm.tmem_base, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(&sm.tmem_base, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();             // every CTA's barriers are initialised before any remote arrival
+  if (PAIR) cluster_sync_all();               // both CTAs' barriers are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  __half* const ring = &sm.wB[0][0];          // PAIR: 2 RST stages of 8 KB in the same bytes
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = 0; t < T; ++t)
-        for (int c = 0; c < RNC; ++c)
-          for (int kb = 0; kb < RKB; ++kb, ++it) {
-            const int s = it % RST;
-            mbar_wait(&sm.empty[s], ((it / RST) & 1) ^ 1);
-            mbar_expect_tx(&sm.full[s], (uint32_t)sizeof(sm.wB[0]));
-            if (CL == 1)
+      if (!PAIR) {
+        for (int t = 0; t < T; ++t)
+          for (int c = 0; c < RNC; ++c)
+            for (int kb = 0; kb < RKB; ++kb, ++it) {
+              const int s = it % NST;
+              mbar_wait(&sm.empty[s], ((it / NST) & 1) ^ 1);
+              mbar_expect_tx(&sm.full[s], (uint32_t)sizeof(sm.wB[0]));
               tma_load_2d(sm.wB[s], &tmW, &sm.full[s], kb * 64, c * RN);
-            else
-              tma_load_2d_mc(sm.wB[s] + crank * (RN / CL) * 64, &tmW, &sm.full[s], kb * 64,
-                             c * RN + (int)crank * (RN / CL), cmask);
+            }
+      } else {
+        const uint32_t full0 = cluster_map_shared(&sm.full[0], 0);      // the leader's full[] barriers
+        for (int t = 0; t < T; ++t)
+          for (int c = 0; c < RNC; ++c, ++it) {
+            const int s = it % NST;
+            mbar_wait(&sm.empty[s], ((it / NST) & 1) ^ 1);
+            tr(t, c, 8);
+            if (leader) mbar_expect_tx(&sm.full[s], (uint32_t)(2 * RKB * WROWS * 64 * sizeof(__half)));   // 64 KB: both CTAs
+            for (int kb = 0; kb < RKB; ++kb)
+              tma_load_2d_pair(ring + (size_t)(s * RKB + kb) * (WROWS * 64), &tmW, full0 + (uint32_t)s * 8u, kb * 64,
+                               c * RN + (int)crank * WROWS);
+            tr(t, c, 9);
           }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(FMT_F16, RB, RN);
-      uint32_t it = 0, use[2] = {0, 0};
-      for (int t = 0; t < T; ++t) {
-        for (int c = 0; c < RNC; ++c) {
-          const int b = c & 1;
-          mbar_wait(&sm.acc_empty[b], (use[b] & 1) ^ 1);
-          tc_fence_after();
-          tr(t, c, 0);
-          for (int kb = 0; kb < RKB; ++kb, ++it) {
-            if (c == 0 && t > 0) mbar_wait(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
-            if (kb == RKB - 1) tr(t, c, 7);
-            const int s = it % RST;
-            mbar_wait(&sm.full[s], (it / RST) & 1);
+    if (leader) {                               // the whole warp, converged; one elected lane issues
+      constexpr uint32_t idesc = umma_idesc(FMT_F16, PAIR ? 2 * RB : RB, RN);
+      uint32_t it = 0, use[2] = {0, 0};           // (constant-indexed after unrolling c by parity below)
+      if (!PAIR) {
+        for (int t = 0; t < T; ++t) {
+          for (int c = 0; c < RNC; ++c) {
+            const int b = c & 1;
+            mbar_wait(&sm.acc_empty[b], (use[b] & 1) ^ 1);
             tc_fence_after();
-            if (kb == RKB - 1) tr(t, c, 1);
-            const uint64_t adesc = umma_desc_sw128(smem_u32(sm.hA[t & 1][kb]));
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s]));
+            tr(t, c, 0);
+            for (int kb = 0; kb < RKB; ++kb, ++it) {
+              if (c == 0 && t > 0) mbar_wait(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+              if (kb == RKB - 1) tr(t, c, 7);
+              const int s = it % NST;
+              mbar_wait(&sm.full[s], (it / NST) & 1);
+              tc_fence_after();
+              if (kb == RKB - 1) tr(t, c, 1);
+              const uint64_t adesc = umma_desc_sw128(smem_u32(sm.hA[t & 1][kb]));
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s]));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem + (uint32_t)(b * RN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            if (CL == 1) umma_commit(&sm.empty[s]);
-            else umma_commit_mc(&sm.empty[s], cmask);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_elect(tmem + (uint32_t)(b * RN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              umma_commit_elect(&sm.empty[s]);
+            }
+            umma_commit_elect(&sm.acc_full[b]);
+            tr(t, c, 2);
+            ++use[b];
           }
-          umma_commit(&sm.acc_full[b]);
-          tr(t, c, 2);
-          ++use[b];
+        }
+      } else {
+        // the barriers of the next chunk are peeked (test_wait) while this chunk's last MMAs are still queued, so in
+        // the steady state the thread goes from the last MMA of a chunk to the first of the next without a wait
+        bool pre_acc = false, pre_full = false;
+        for (int t = 0; t < T; ++t) {
+          for (int c = 0; c < RNC; ++c, ++it) {
+            const int b = c & 1, s = it % NST;
+            if (TRACE && blockIdx.x == 0 && t >= TRACE_T0 && t < TRACE_T0 + TRACE_NT)
+              trace[((t - TRACE_T0) * RNC + c) * TRACE_EV + 11] = (pre_acc ? 1 : 0) + (pre_full ? 2 : 0);
+            tr(t, c, 10);
+            if (!pre_acc) mbar_wait_cluster(&sm.acc_empty[b], (use[b] & 1) ^ 1);
+            tr(t, c, 1);
+            if (!pre_full) mbar_wait(&sm.full[s], (it / NST) & 1);
+            tc_fence_after();
+            tr(t, c, 0);
+#pragma unroll
+            for (int kb = 0; kb < RKB; ++kb) {
+              if (c == 0 && t > 0) {
+                mbar_wait_cluster(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+                tc_fence_after();
+              }
+              if (kb == RKB - 1) tr(t, c, 7);
+              const uint64_t adesc = umma_desc_sw128(smem_u32(sm.hA[t & 1][kb]));
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + (size_t)(s * RKB + kb) * (WROWS * 64)));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair_elect(tmem + (uint32_t)(b * RN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              if (kb == RKB - 2) {
+                const int bn = b ^ 1;
+                pre_acc = mbar_test_wait_cluster(&sm.acc_empty[bn], (use[bn] & 1) ^ 1);
+                pre_full = mbar_test_wait_cluster(&sm.full[(it + 1) % NST], ((it + 1) / NST) & 1);
+              }
+            }
+            umma_commit_pair_mc_elect(&sm.empty[s], 3);
+            umma_commit_pair_mc_elect(&sm.acc_full[b], 3);
+            tr(t, c, 2);
+            ++use[b];
+          }
         }
       }
     }
@@ -245,6 +307,10 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       const __half2 h2 = *reinterpret_cast<const __half2*>(&xr[4 * g + (j >> 1)]);
       return (j & 1) ? __high2float(h2) : __low2float(h2);
     };
+    // PAIR: the MMA thread that waits on these lives in the leader CTA
+    const uint32_t acc_empty_addr[2] = {PAIR ? cluster_map_shared(&sm.acc_empty[0], 0) : 0u,
+                                        PAIR ? cluster_map_shared(&sm.acc_empty[1], 0) : 0u};
+    const uint32_t h_ready_addr0 = PAIR ? cluster_map_shared(&sm.h_ready[0], 0) : 0u;
     uint32_t use[2] = {0, 0};
     auto run = [&](int t, int c, uint32_t (&xg)[XR]) {
       const int b = c & 1, u0 = c * RCH + q * 8;
@@ -263,7 +329,10 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
       // the r2c / r2d clock traces showed the MMA thread passing acc_empty 600-800 cycles after the loads were done)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.acc_empty[b]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(acc_empty_addr[b]);
+        else mbar_arrive(&sm.acc_empty[b]);
+      }
       ++use[b];
       float hn[8];
 #pragma unroll
@@ -295,11 +364,14 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
         if (u0 == 0 && h_pitch > RH) *reinterpret_cast<uint4*>(ht + RH) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
       }
       if (live && h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
-      // next use of this register buffer: the same quarter of chunk c + 2 (or of the next step)
-      load_x(c + 2 < RNC ? t : t + 1, c + 2 < RNC ? c + 2 : c + 2 - RNC, xg);
       fence_proxy_async_smem();                // this thread's part of k-block c/2 of h_t is written
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.h_ready[c >> 1]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(h_ready_addr0 + (uint32_t)(c >> 1) * 8u);
+        else mbar_arrive(&sm.h_ready[c >> 1]);
+      }
+      // next use of this register buffer: the same quarter of chunk c + 2 (or of the next step)
+      load_x(c + 2 < RNC ? t : t + 1, c + 2 < RNC ? c + 2 : c + 2 - RNC, xg);
       if (threadIdx.x == 64) tr(t, c, 6);
     };
     uint32_t xa[XR], xb[XR];
@@ -316,8 +388,11 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();             // no CTA leaves while a peer can still signal its barriers
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync_all();               // no CTA leaves while its peer can still signal its barriers
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 // out[(c*128 + g*32 + u) * 256 + k] = half(W_hh[(g*256 + c*32 + u) * 256 + k])
@@ -355,39 +430,26 @@ static int rec_launch(Kern kern, int cl, int n_ct, int smem, cudaStream_t s, Arg
   return AVHOT_OK;
 }
 
-// how many CTAs may share the weight stream: the largest cluster size in {4, 2} whose clusters are all co-resident
-// for this grid (one CTA per SM; a second wave would double the run time), else 1.  AVHOT_REC_CLUSTER overrides.
-template <typename K2, typename K4>
-static int rec_cluster_size(K2 k2, K4 k4, int n_ct, int smem) {
-  static const int forced = [] { const char* e = getenv("AVHOT_REC_CLUSTER"); return e ? atoi(e) : 0; }();
-  if (forced == 1) return 1;
-  int best = 1;
-  for (int cl = 2; cl <= 4; cl *= 2) {
-    if (forced && forced != cl) continue;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(ceil_div(n_ct, cl) * cl));
-    cfg.blockDim = dim3(tc::RTHREADS);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cl;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    cudaError_t e;
-    if (cl == 2) {
-      cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      e = cudaOccupancyMaxActiveClusters(&n, k2, &cfg);
-    } else {
-      cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      e = cudaOccupancyMaxActiveClusters(&n, k4, &cfg);
-    }
-    if (e != cudaSuccess) { cudaGetLastError(); continue; }
-    if (n * cl >= ceil_div(n_ct, cl) * cl) best = cl;
-  }
-  return best;
+// can every CTA pair of this grid be co-resident (one CTA per SM; a second wave would double the run time)?
+template <typename K2>
+static bool rec_pairs_fit(K2 k2, int n_ct, int smem) {
+  static const int forced = [] { const char* e = getenv("AVHOT_REC_PAIR"); return e ? atoi(e) : -1; }();
+  if (forced == 0) return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ceil_div(n_ct, 2) * 2));
+  cfg.blockDim = dim3(tc::RTHREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (cudaOccupancyMaxActiveClusters(&n, k2, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  return n * 2 >= ceil_div(n_ct, 2) * 2;
 }
 
 int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_f16, void* h_seq_f16, int h_pitch,
@@ -401,20 +463,18 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_
   // error is set by the fp16 state); AVHOT_LSTM_ACT=0 selects the ex2 + rcp form.
   static const int act = [] { const char* e = getenv("AVHOT_LSTM_ACT"); return e ? atoi(e) : 1; }();
   const bool fast = act == 1 && xp_f16;                       // the benchmarked configuration
-  const int cl = fast && n_ct > 1 ? rec_cluster_size(lstm_rec_tc_kernel<1, true, false, 2>,
-                                                     lstm_rec_tc_kernel<1, true, false, 4>, n_ct, smem) : 1;
+  const int cl = fast && n_ct > 1 && rec_pairs_fit(lstm_rec_tc_kernel<1, true, false, true>, n_ct, smem) ? 2 : 1;
   CUtensorMap tmW;
   int rc = make_tensor_map_2d(&tmW, whh_packed_fp16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * RH, RH, RH, RN / cl, 64);
   if (rc != AVHOT_OK) return rc;
   static const char* trace_path = getenv("AVHOT_REC_TRACE");
   if (trace_path && fast && T >= TRACE_T0 + TRACE_NT) {     // debug: one traced launch, dumped as text
     long long* d_trace = nullptr;
-    const size_t n = (size_t)TRACE_NT * RNC * 8;
+    const size_t n = (size_t)TRACE_NT * RNC * TRACE_EV;
     AVHOT_CUDA(cudaMalloc(&d_trace, n * sizeof(long long)));
     AVHOT_CUDA(cudaMemsetAsync(d_trace, 0, n * sizeof(long long), s));
-    if (cl == 4) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, 4>, 4, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
-    else if (cl == 2) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, 2>, 2, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
-    else rc = rec_launch(lstm_rec_tc_kernel<1, true, true, 1>, 1, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    if (cl == 2) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, true>, 2, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    else rc = rec_launch(lstm_rec_tc_kernel<1, true, true, false>, 1, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
     if (rc != AVHOT_OK) return rc;
     AVHOT_LAUNCH_CHECK();
     std::vector<long long> host(n);
@@ -422,10 +482,10 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_
     AVHOT_CUDA(cudaStreamSynchronize(s));
     cudaFree(d_trace);
     if (FILE* f = fopen(trace_path, "a")) {
-      fprintf(f, "# B=%d T=%d cluster=%d  events: 0 mma:acc_empty 7 mma:h_ready(kb3) 1 mma:w_full(kb3) 2 mma:commit 3 epi:acc_full 4 epi:ld 5 epi:math 6 epi:end\n", B, T, cl);
+      fprintf(f, "# B=%d T=%d cluster=%d  events: 0 mma:acc_empty 7 mma:h_ready(kb3) 1 mma:w_full(kb3) 2 mma:commit 3 epi:acc_full 4 epi:ld 5 epi:math 6 epi:end 8 tma:empty 9 tma:issued 10 mma:top 11 peeks\n", B, T, cl);
       for (int i = 0; i < TRACE_NT * RNC; ++i) {
         fprintf(f, "t=%d c=%d", TRACE_T0 + i / RNC, i % RNC);
-        for (int e = 0; e < 8; ++e) fprintf(f, " %lld", host[i * 8 + e] - host[0]);
+        for (int e = 0; e < TRACE_EV; ++e) fprintf(f, " %lld", e == 11 ? host[i * TRACE_EV + e] : host[i * TRACE_EV + e] - host[0]);
         fprintf(f, "\n");
       }
       fclose(f);
@@ -434,15 +494,14 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_
   }
   ProfScope prof("lstm_recurrence_tc", s);
   long long* no_trace = nullptr;
-#define AVHOT_REC_LAUNCH(ACT_, X16_, CL_)                                                                           \
-  rc = rec_launch(lstm_rec_tc_kernel<ACT_, X16_, false, CL_>, CL_, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last,  \
-                  lengths, B, T, n_ct, no_trace)
-  if (fast && cl == 4) AVHOT_REC_LAUNCH(1, true, 4);
-  else if (fast && cl == 2) AVHOT_REC_LAUNCH(1, true, 2);
-  else if (fast) AVHOT_REC_LAUNCH(1, true, 1);
-  else if (act == 1) AVHOT_REC_LAUNCH(1, false, 1);
-  else if (xp_f16) AVHOT_REC_LAUNCH(0, true, 1);
-  else AVHOT_REC_LAUNCH(0, false, 1);
+#define AVHOT_REC_LAUNCH(ACT_, X16_, PAIR_)                                                                         \
+  rc = rec_launch(lstm_rec_tc_kernel<ACT_, X16_, false, PAIR_>, PAIR_ ? 2 : 1, n_ct, smem, s, tmW, xp, h_seq, h_pitch, \
+                  h_last, lengths, B, T, n_ct, no_trace)
+  if (fast && cl == 2) AVHOT_REC_LAUNCH(1, true, true);
+  else if (fast) AVHOT_REC_LAUNCH(1, true, false);
+  else if (act == 1) AVHOT_REC_LAUNCH(1, false, false);
+  else if (xp_f16) AVHOT_REC_LAUNCH(0, true, false);
+  else AVHOT_REC_LAUNCH(0, false, false);
 #undef AVHOT_REC_LAUNCH
   if (rc != AVHOT_OK) return rc;
   AVHOT_LAUNCH_CHECK();
