@@ -263,8 +263,8 @@ def run_b200_arm(args):
         "frontend": ("hbm", B * N_SAMPLES * 4 + (Bp * T_FEATS * pitch * 2 if tc else B * T_FEATS * 104 * 4), 0),
         "frame_gemm": ("hbm", B * BYTES_FRAMES + B * 16 * 256 * 4, B * FLOPS_FRAME_GEMM),
         # xp is fp16 for both layers -> 2 x half an fp32 layer, written by the GEMM and read by the recurrence
-        "lstm_input_gemm_tc": ("hbm", xp_bytes + Bp * T_FEATS * (pitch + 264) * 2, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
-        "lstm_recurrence_tc": ("hbm", xp_bytes + Bp * T_FEATS * 264 * 2, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
+        "lstm_input_gemm_tc": ("hbm", xp_bytes + Bp * T_FEATS * (pitch + 256) * 2, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
+        "lstm_recurrence_tc": ("hbm", xp_bytes + Bp * T_FEATS * 256 * 2, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
         "lstm_recurrence": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
         "lstm_input_gemm": ("tensor", 0, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
     }

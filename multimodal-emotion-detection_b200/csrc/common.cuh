@@ -109,6 +109,15 @@ __host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, uint3
   return i == 0 ? p.x : (i == 1 ? p.y : (i == 2 ? p.z : p.w));
 }
 
+// Dense sites - masks of >= AVHOT_DENSE_SITE_ELEMS elements per (clip, pass), i.e. the (F, H) mask of FrameEncoder's
+// frame_mlp dropout - draw 16 bits per element instead of 32 (oracle/philox.py): element e uses half-word e & 1
+// (0 = low) of word (e >> 1) & 3 of block e >> 3 and is kept iff half >= threshold >> 16 = floor(p * 2^16).
+constexpr int AVHOT_DENSE_SITE_ELEMS = 1024;
+__host__ __device__ __forceinline__ uint32_t philox_half(const Philox4& p, uint32_t i) {   // i = e & 7
+  const uint32_t w = philox_word(p, i >> 1);
+  return (i & 1u) ? (w >> 16) : (w & 0xFFFFu);
+}
+
 // floor(p * 2^32) clamped to uint32: an element is kept iff word >= threshold.
 static inline uint32_t drop_threshold(float p) {
   double v = (double)p * 4294967296.0;

@@ -8,8 +8,8 @@
 //   avhot_frame_hidden   Linear + ReLU, pass-invariant, the 102.8 MFLOP/clip contraction (gemm.cu);
 //   avhot_frame_tail     everything after the ReLU for T passes.  One CTA = 32 rows (clip, pass);
 //                        one warp per row streams the (F, H) activations once with an online
-//                        softmax (Philox keep bits drawn in registers, lane <-> 2 x 4 consecutive
-//                        columns = 2 Philox blocks per frame), then LayerNorm by warp shuffles;
+//                        softmax (Philox keep bits drawn in registers, lane <-> 8 consecutive columns =
+//                        one Philox block of eight 16-bit draws per frame), then LayerNorm by warp shuffles;
 //                        the 32 normalised rows are staged in shared memory and the H -> out
 //                        projection runs as one 32-row tile so the weights are read once per CTA.
 #include <float.h>
@@ -47,12 +47,13 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_rows = (long long)B * T;
   const long long row0 = (long long)blockIdx.x * FT_ROWS;
-  const int c0 = 4 * lane, c1 = 128 + 4 * lane;   // this lane's two column groups
+  const int c0 = 8 * lane, c1 = 8 * lane + 4;     // this lane's eight columns (two float4 groups)
 
   const float4 aw0 = __ldg(reinterpret_cast<const float4*>(attn_w + c0));
   const float4 aw1 = __ldg(reinterpret_cast<const float4*>(attn_w + c1));
   const float ab = __ldg(attn_b);
   const bool drop = ds.thr != 0u;
+  const uint32_t thr16 = ds.thr >> 16;
 
   for (int i = warp; i < FT_ROWS; i += FT_WARPS) {
     const long long row = row0 + i;
@@ -69,12 +70,10 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(hb + (size_t)f * FH + c0));
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(hb + (size_t)f * FH + c1));
         float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (drop) {   // site FRAME_MLP: element e = f*H + col, block e >> 2
-          const Philox4 r0 = philox4x32_10((uint32_t)(f * 64 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds.k0, ds.k1);
-          const Philox4 r1 = philox4x32_10((uint32_t)(f * 64 + 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds.k0, ds.k1);
-          const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        if (drop) {   // site FRAME_MLP (dense: 16-bit draws): element e = f*H + col, block e >> 3 = f*32 + lane
+          const Philox4 r = philox4x32_10((uint32_t)(f * 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds.k0, ds.k1);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) x[q] = w[q] >= ds.thr ? x[q] * ds.scale : 0.f;
+          for (int q = 0; q < 8; ++q) x[q] = philox_half(r, (uint32_t)q) >= thr16 ? x[q] * ds.scale : 0.f;
         }
         float s = x[0] * aw0.x + x[1] * aw0.y + x[2] * aw0.z + x[3] * aw0.w +
                   x[4] * aw1.x + x[5] * aw1.y + x[6] * aw1.z + x[7] * aw1.w;
@@ -90,9 +89,9 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
       const float inv = 1.f / denom;
 #pragma unroll
       for (int q = 0; q < 8; ++q) pooled[q] *= inv;
-      if (drop) {     // site FRAME_POOL: element e = col
-        const Philox4 r0 = philox4x32_10((uint32_t)lane, g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
-        const Philox4 r1 = philox4x32_10((uint32_t)(32 + lane), g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
+      if (drop) {     // site FRAME_POOL (32-bit draws): element e = col, block e >> 2
+        const Philox4 r0 = philox4x32_10((uint32_t)(2 * lane), g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
+        const Philox4 r1 = philox4x32_10((uint32_t)(2 * lane + 1), g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
         const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) pooled[q] = w[q] >= ds.thr ? pooled[q] * ds.scale : 0.f;

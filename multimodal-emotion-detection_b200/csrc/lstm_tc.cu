@@ -27,12 +27,13 @@
 namespace avhot {
 namespace tc {
 
-constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 64 + 512;
+constexpr int RB = 128, RH = 256, RCH = 32, RNC = RH / RCH, RN = 4 * RCH, RKB = RH / 64, RST = 6, RTHREADS = 64 + 512 + 32;
 
 struct RecSmem {
   __half hA[2][RKB][RB * 64];   // hidden state, A operand: [step parity][k-block][128 rows x 128 B, swizzled]
   __half wB[RST][RN * 64];      // W_hh tile ring, B operand
   uint64_t full[2 * RST], empty[2 * RST], acc_full[2], acc_empty[2], h_ready[RKB];
+  uint64_t h_done[2][RKB], h_free[2][RKB];   // layer-output store: k-block of buffer p written / read out by the TMA store
   uint32_t tmem_base;
 };
 
@@ -102,8 +103,8 @@ constexpr int TRACE_T0 = 100, TRACE_NT = 4, TRACE_EV = 12;
 // The grid is rounded up to an even size; a CTA past n_ct redoes the last clip tile and writes nothing.
 template <int ACT, bool XP16, bool TRACE = false, bool PAIR = false>
 __global__ void __launch_bounds__(RTHREADS, 1)
-lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ xp, __half* __restrict__ h_seq,
-                   int h_pitch,
+lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                   const float* __restrict__ xp, __half* __restrict__ h_seq, int h_pitch,
                    float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T, int n_ct_arg,
                    long long* __restrict__ trace = nullptr) {
   const int ctile = min((int)blockIdx.x, n_ct_arg - 1);
@@ -136,6 +137,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     for (int s = 0; s < NST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 16 * NC); }
     for (int k = 0; k < RKB; ++k) mbar_init(&sm.h_ready[k], 32 * NC);   // 16 epilogue warps x the 2 chunks of a k-block
+    for (int k = 0; k < 2 * RKB; ++k) { mbar_init(&sm.h_done[0][0] + k, 32); mbar_init(&sm.h_free[0][0] + k, 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -247,6 +249,28 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
         }
       }
     }
+  } else if (warp >= 18) {
+    // ---- store warp: the layer's output sequence (the next layer's GEMM operand) leaves through TMA.  A k-block of
+    // h_t in the A-operand buffer is exactly a (128 clips x 64 units) box of the time-major (T * Bp, H) fp16 tensor in
+    // the 128-byte-swizzled layout, so one bulk store per k-block and step replaces 512 scattered 16-byte stores per
+    // chunk (the r2t trace: layer 0's epilogue tail, 300 - 1600 cycles per chunk, bound the whole kernel).
+    if (h_seq && writer) {
+      if (lane == 0) tma_prefetch_desc(&tmH);
+      for (int t = 0; t < T; ++t) {
+        const int pbuf = (t + 1) & 1;
+        for (int kb = 0; kb < RKB; ++kb) {
+          mbar_wait(&sm.h_done[pbuf][kb], (uint32_t)(t >> 1) & 1);      // all 16 epilogue warps wrote + fenced it
+          if (lane == 0) {
+            tma_store_2d(&tmH, sm.hA[pbuf][kb], kb * 64, (t * n_ct_arg + ctile) * RB);
+            tma_store_commit();
+            tma_store_wait_read0();
+            mbar_arrive(&sm.h_free[pbuf][kb]);                            // the epilogue may overwrite it (step t + 2)
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) tma_store_wait0();
+    }
   } else {
     // 16 epilogue warps = (TMEM lane quarter, quarter q of a chunk): thread (clip r, q) owns hidden units
     // 32 c + 8 q .. + 7 of every chunk c, so the four 8-unit items of a chunk are computed in parallel by four
@@ -272,7 +296,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
     // written too, so the operand is fully initialised)
     const size_t n_ct = (size_t)n_ct_arg;
     const float* xcol = xp + (size_t)ctile * (4 * RH) * RB + r;
-    __half* hrow = h_seq && writer ? h_seq + ((size_t)ctile * RB + r) * h_pitch : nullptr;
+    const bool hstore = h_seq && writer;                     // this layer's h_t sequence goes out through the store warp
     unsigned char* const hbase = reinterpret_cast<unsigned char*>(&sm.hA[0][0][0]);
 
     // xp registers hold what was loaded, unconverted: the loads of the item two chunks ahead stay in flight until
@@ -354,21 +378,18 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restr
         const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
         pk[j] = *reinterpret_cast<const uint32_t*>(&v);
       }
+      // (a k-block of this buffer is read out by the store warp's TMA store issued two steps ago)
+      if (hstore && t >= 2) mbar_wait(&sm.h_free[(t + 1) & 1][c >> 1], (uint32_t)((t - 2) >> 1) & 1);
       unsigned char* tile = hbase + (size_t)((t + 1) & 1) * sizeof(sm.hA[0]) + (size_t)(u0 >> 6) * (RB * 128) +
                             (size_t)r * 128;
       *reinterpret_cast<uint4*>(tile + ((((u0 & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      if (hrow) {
-        __half* ht = hrow + (size_t)t * n_ct * RB * h_pitch;
-        *reinterpret_cast<uint4*>(ht + u0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        // columns H, H + 1 = 1.0: they multiply the (hi, lo) bias columns of the next layer's packed W_ih
-        if (u0 == 0 && h_pitch > RH) *reinterpret_cast<uint4*>(ht + RH) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-      }
       if (live && h_last && t == last_t) stg256(h_last + (size_t)clip * RH + u0, hn);
       fence_proxy_async_smem();                // this thread's part of k-block c/2 of h_t is written
       __syncwarp();
       if (lane == 0) {
         if (PAIR) mbar_arrive_cluster(h_ready_addr0 + (uint32_t)(c >> 1) * 8u);
         else mbar_arrive(&sm.h_ready[c >> 1]);
+        if (hstore) mbar_arrive(&sm.h_done[(t + 1) & 1][c >> 1]);
       }
       // next use of this register buffer: the same quarter of chunk c + 2 (or of the next step)
       load_x(c + 2 < RNC ? t : t + 1, c + 2 < RNC ? c + 2 : c + 2 - RNC, xg);
@@ -467,14 +488,21 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_
   CUtensorMap tmW;
   int rc = make_tensor_map_2d(&tmW, whh_packed_fp16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * RH, RH, RH, RN / cl, 64);
   if (rc != AVHOT_OK) return rc;
+  CUtensorMap tmH = tmW;                        // unused without an output sequence
+  if (h_seq) {
+    AVHOT_REQUIRE(h_pitch >= RH && (h_pitch & 7) == 0, AVHOT_ERR_INVALID, "lstm_recurrence_tc: bad h_seq pitch %d", h_pitch);
+    rc = make_tensor_map_2d(&tmH, h_seq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)T * n_ct * RB, RH, (uint64_t)h_pitch,
+                            RB, 64);
+    if (rc != AVHOT_OK) return rc;
+  }
   static const char* trace_path = getenv("AVHOT_REC_TRACE");
   if (trace_path && fast && T >= TRACE_T0 + TRACE_NT) {     // debug: one traced launch, dumped as text
     long long* d_trace = nullptr;
     const size_t n = (size_t)TRACE_NT * RNC * TRACE_EV;
     AVHOT_CUDA(cudaMalloc(&d_trace, n * sizeof(long long)));
     AVHOT_CUDA(cudaMemsetAsync(d_trace, 0, n * sizeof(long long), s));
-    if (cl == 2) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, true>, 2, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
-    else rc = rec_launch(lstm_rec_tc_kernel<1, true, true, false>, 1, n_ct, smem, s, tmW, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    if (cl == 2) rc = rec_launch(lstm_rec_tc_kernel<1, true, true, true>, 2, n_ct, smem, s, tmW, tmH, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
+    else rc = rec_launch(lstm_rec_tc_kernel<1, true, true, false>, 1, n_ct, smem, s, tmW, tmH, xp, h_seq, h_pitch, h_last, lengths, B, T, n_ct, d_trace);
     if (rc != AVHOT_OK) return rc;
     AVHOT_LAUNCH_CHECK();
     std::vector<long long> host(n);
@@ -495,8 +523,8 @@ int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp_any, bool xp_
   ProfScope prof("lstm_recurrence_tc", s);
   long long* no_trace = nullptr;
 #define AVHOT_REC_LAUNCH(ACT_, X16_, PAIR_)                                                                         \
-  rc = rec_launch(lstm_rec_tc_kernel<ACT_, X16_, false, PAIR_>, PAIR_ ? 2 : 1, n_ct, smem, s, tmW, xp, h_seq, h_pitch, \
-                  h_last, lengths, B, T, n_ct, no_trace)
+  rc = rec_launch(lstm_rec_tc_kernel<ACT_, X16_, false, PAIR_>, PAIR_ ? 2 : 1, n_ct, smem, s, tmW, tmH, xp, h_seq, \
+                  h_pitch, h_last, lengths, B, T, n_ct, no_trace)
   if (fast && cl == 2) AVHOT_REC_LAUNCH(1, true, true);
   else if (fast) AVHOT_REC_LAUNCH(1, true, false);
   else if (act == 1) AVHOT_REC_LAUNCH(1, false, false);

@@ -97,8 +97,12 @@ __global__ void dropout_keep_kernel(uint8_t* __restrict__ keep, int n_elems, uin
                                     uint32_t site, uint32_t thr, uint32_t k0, uint32_t k1) {
   const uint32_t g = (uint32_t)(clip0 + blockIdx.y);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
-    const uint32_t w = philox_word(philox4x32_10((uint32_t)e >> 2, g, t, site, k0, k1), e & 3);
-    keep[(size_t)blockIdx.y * n_elems + e] = w >= thr ? 1 : 0;
+    bool k;
+    if (n_elems >= AVHOT_DENSE_SITE_ELEMS)
+      k = philox_half(philox4x32_10((uint32_t)e >> 3, g, t, site, k0, k1), e & 7) >= (thr >> 16);
+    else
+      k = philox_word(philox4x32_10((uint32_t)e >> 2, g, t, site, k0, k1), e & 3) >= thr;
+    keep[(size_t)blockIdx.y * n_elems + e] = k ? 1 : 0;
   }
 }
 

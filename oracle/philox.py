@@ -17,6 +17,8 @@ not depend on batch size, sharding or launch geometry):
 
     dropout keep bit for element e of clip g, MC pass t, site s, drop-prob p:
         keep = words(e >> 2, g, t, s)[e & 3] >= floor(p * 2**32)
+        (dense sites, >= 1024 mask elements per clip and pass - the (F, H) frame_mlp mask: 16-bit draws,
+         keep = half(e & 1) of words(e >> 3, g, t, s)[(e >> 1) & 3] >= floor(p * 2**32) >> 16; see dropout_keep)
         kept activations are multiplied by fp32(1) / fp32(1 - p)   (nn.Dropout)
 
 Site ids (element index is the row-major index inside
@@ -111,10 +113,23 @@ def keep_scale(p: float) -> np.float32:
     return np.float32(1.0) / np.float32(1.0 - float(p))
 
 
+DENSE_SITE_ELEMS = 1024
+
+
 def dropout_keep(n_elems: int, clip_ids, t: int, site: int, p: float, seed: int) -> np.ndarray:
-    """Boolean keep mask, shape (B, n_elems), for MC pass t at a dropout site."""
-    w = element_words(n_elems, np.asarray(clip_ids), t, site, seed)
-    return w >= np.uint32(drop_threshold(p))
+    """Boolean keep mask, shape (B, n_elems), for MC pass t at a dropout site.
+
+    Sites whose mask has fewer than DENSE_SITE_ELEMS elements per (clip, pass) draw one 32-bit word per element:
+    word(e) = words(e >> 2)[e & 3], kept iff word >= floor(p * 2**32).  Dense sites (the (F, H) = 4096-element
+    frame_mlp mask, 94 % of all draws) use 16 bits per element: half-word e & 1 (0 = low) of word (e >> 1) & 3 of
+    block e >> 3, kept iff half >= floor(p * 2**32) >> 16 = floor(p * 2**16); p is then realised to within 2**-16."""
+    thr = drop_threshold(p)
+    if n_elems < DENSE_SITE_ELEMS:
+        w = element_words(n_elems, np.asarray(clip_ids), t, site, seed)
+        return w >= np.uint32(thr)
+    w = element_words((n_elems + 1) // 2, np.asarray(clip_ids), t, site, seed)      # word of element pair e >> 1
+    halves = np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], axis=-1).reshape(*w.shape[:-1], -1)[..., :n_elems]
+    return halves >= np.uint32(thr >> 16)
 
 
 def modality_mask(clip_ids, num_modalities: int, p: float, seed: int) -> np.ndarray:
