@@ -117,8 +117,11 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
 #pragma unroll
       for (int q = 0; q < 8; ++q) y[q] = 0.f;
     }
+    // staged [column][row]; the 16-byte row groups of a column are XOR-permuted by the owning lane (= column >> 3)
+    // so the 32 lanes of this store do not all hit one bank (4-way instead of 32-way conflicts)
+    const int ri = (((i >> 2) ^ (lane & 7)) << 2) | (i & 3);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { ys[c0 + q][i] = y[q]; ys[c1 + q][i] = y[4 + q]; }
+    for (int q = 0; q < 4; ++q) { ys[c0 + q][ri] = y[q]; ys[c1 + q][ri] = y[4 + q]; }
   }
   __syncthreads();
   // projection H -> out for the 32 rows of this CTA: thread = (output o, half of the rows)
@@ -132,7 +135,7 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
       const float w = __ldg(proj_wt + (size_t)j * out_dim + o);
 #pragma unroll
       for (int r4 = 0; r4 < 16; r4 += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&ys[j][half * 16 + r4]);
+        const float4 v = *reinterpret_cast<const float4*>(&ys[j][(((half * 16 + r4) >> 2) ^ ((j >> 3) & 7)) << 2]);
         acc[r4] = fmaf(w, v.x, acc[r4]); acc[r4 + 1] = fmaf(w, v.y, acc[r4 + 1]);
         acc[r4 + 2] = fmaf(w, v.z, acc[r4 + 2]); acc[r4 + 3] = fmaf(w, v.w, acc[r4 + 3]);
       }
