@@ -137,6 +137,16 @@ int avhot_lstm_split_pitch(avhot_lstm_t h);
 int avhot_lstm_forward_split(avhot_lstm_t h, const void* seq_split_f16, const int32_t* lengths, float* out,
                              int B, int T, void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 
+/* ---- src/encoders.py:65-77, :137-155  SequenceEncoder(encoder_type='gru') ---------- */
+/* Same descriptor as the LSTM with nn.GRU's tensors: weight_ih_l{k} (3H, in_k), weight_hh_l{k} (3H, H), bias_ih /
+ * bias_hh (3H), gate rows r, z, n.  fp32 path; lengths as in avhot_lstm_forward. */
+typedef struct avhot_gru* avhot_gru_t;
+int avhot_gru_create(const avhot_lstm_desc* desc, avhot_gru_t* out, avhot_stream_t stream);
+void avhot_gru_destroy(avhot_gru_t h);
+size_t avhot_gru_workspace_bytes(avhot_gru_t h, int B, int T);
+int avhot_gru_forward(avhot_gru_t h, const float* seq, const int32_t* lengths, float* out, int B, int T,
+                      void* workspace, size_t workspace_bytes, avhot_stream_t stream);
+
 /* ---- a4: src/encoders.py:196-327  FrameEncoder(temporal_pooling='attention') -------- */
 typedef struct avhot_frame* avhot_frame_t;
 typedef struct {

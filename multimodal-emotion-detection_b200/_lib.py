@@ -97,6 +97,10 @@ PROTOTYPES = {
     "avhot_lstm_destroy": (None, [_P]),
     "avhot_lstm_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "avhot_lstm_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
+    "avhot_gru_create": (_I, [C.POINTER(LstmDesc), C.POINTER(_P), _P]),
+    "avhot_gru_destroy": (None, [_P]),
+    "avhot_gru_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "avhot_gru_forward": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "avhot_lstm_split_pitch": (_I, [_P]),
     "avhot_lstm_forward_split": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "avhot_frame_create": (_I, [C.POINTER(FrameDesc), C.POINTER(_P), _P]),

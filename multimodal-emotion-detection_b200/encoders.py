@@ -21,8 +21,9 @@ _ws_frames = Workspace()
 
 
 class SequenceEncoder(nn.Module):
-    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru', 'cnn',
-    'transformer' are valid in the reference and not built here (ValueError says so)."""
+    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru' (SURVEY.md 8f
+    row 1) runs on the fp32 kernels of csrc/gru.cu; 'cnn' and 'transformer' are valid in the reference and not built
+    here (ValueError says so)."""
 
     def __init__(self, input_dim: int, hidden_dim: int = 256, output_dim: int = 128, num_layers: int = 2,
                  encoder_type: str = 'lstm', dropout: float = 0.1):
@@ -38,12 +39,17 @@ class SequenceEncoder(nn.Module):
                                batch_first=True, dropout=dropout if num_layers > 1 else 0.0,
                                bidirectional=False)                                  # src/encoders.py:54-61
             self.projection = nn.Linear(hidden_dim, output_dim)                      # :62
-        elif encoder_type in ('gru', 'cnn', 'transformer'):
+        elif encoder_type == 'gru':
+            self.rnn = nn.GRU(input_size=input_dim, hidden_size=hidden_dim, num_layers=num_layers,
+                              batch_first=True, dropout=dropout if num_layers > 1 else 0.0,
+                              bidirectional=False)                                   # src/encoders.py:68-75
+            self.projection = nn.Linear(hidden_dim, output_dim)                      # :76
+        elif encoder_type in ('cnn', 'transformer'):
             raise ValueError(f"encoder type '{encoder_type}' exists in the reference but is not built in this "
                              "library (hot path = 'lstm')")
         else:
             raise ValueError(f"Unknown encoder type: {encoder_type}")                # :115
-        self._handle = Handle("avhot_lstm_destroy")
+        self._handle = Handle("avhot_gru_destroy" if encoder_type == 'gru' else "avhot_lstm_destroy")
 
     def _params(self):
         ps = []
@@ -65,8 +71,10 @@ class SequenceEncoder(nn.Module):
                 d.bias_ih[l], d.bias_hh[l] = ps[4 * l + 2].data_ptr(), ps[4 * l + 3].data_ptr()
             d.proj_weight, d.proj_bias = ps[-2].data_ptr(), ps[-1].data_ptr()
             out = C.c_void_p()
-            _lib.check(_lib.load().avhot_lstm_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
-                       "SequenceEncoder")
+            create_fn = _lib.load().avhot_gru_create if self.encoder_type == 'gru' else _lib.load().avhot_lstm_create
+            _lib.check(create_fn(C.byref(d), C.byref(out), _lib.stream_ptr(dev)), "SequenceEncoder")
+            if self.encoder_type == 'gru':
+                torch.cuda.current_stream(dev).synchronize()   # the handle copies from temporaries on the stream
             return out.value
 
         return self._handle.get(self._params(), create)
@@ -91,6 +99,11 @@ class SequenceEncoder(nn.Module):
         lib = _lib.load()
         with torch.cuda.device(dev):
             h = self._get_handle(dev)
+            if self.encoder_type == 'gru':
+                ws = _ws.get(lib.avhot_gru_workspace_bytes(h, B, T), dev)
+                _lib.check(lib.avhot_gru_forward(h, _lib.ptr(x), _lib.ptr(lengths), _lib.ptr(out), B, T, _lib.ptr(ws),
+                                                 ws.numel(), _lib.stream_ptr(dev)), "SequenceEncoder.forward (gru)")
+                return out
             nbytes = lib.avhot_lstm_workspace_bytes(h, B, T, self.precision)
             ws = _ws.get(nbytes, dev)
             _lib.check(lib.avhot_lstm_forward(h, _lib.ptr(x), _lib.ptr(lengths), _lib.ptr(out), B, T,
@@ -109,8 +122,8 @@ class SequenceEncoder(nn.Module):
         _lib.check_device(dev)
         if wave.dim() == 3 and wave.shape[-1] == 1:
             wave = wave[..., 0]
-        if wave.dim() != 2 or self.input_dim != dp.N_FEATS:
-            raise ValueError("forward_from_waveform needs a (B, N) waveform and input_dim == 104")
+        if wave.dim() != 2 or self.input_dim != dp.N_FEATS or self.encoder_type != 'lstm':
+            raise ValueError("forward_from_waveform needs a (B, N) waveform, input_dim == 104 and encoder_type 'lstm'")
         wave = _lib.f32c(wave)
         B, N = wave.shape
         T = dp.n_frames(N)

@@ -92,7 +92,7 @@ class AVHotPath(nn.Module):
         B = audio.shape[0]
         aenc = self.encoders["audio"]
         raw = not (audio.dim() == 3 and audio.shape[-1] == aenc.input_dim and aenc.input_dim != 1)
-        if raw and self.precision == "tc" and B <= 65535:
+        if raw and self.precision == "tc" and B <= 65535 and aenc.encoder_type == "lstm":
             z_a = aenc.forward_from_waveform(audio)           # front-end fused with the LSTM operand preparation
         else:
             z_a = aenc(self.audio_features(audio))                                        # (B, out), pass-invariant

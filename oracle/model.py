@@ -95,6 +95,39 @@ def sequence_encoder_lstm(seq, sd, prefix="encoders.audio.", num_layers=2):
     return _lin(h, sd, prefix + "projection")
 
 
+def sequence_encoder_gru(seq, sd, prefix="gru_enc.", num_layers=2, lengths=None):
+    """SequenceEncoder(encoder_type='gru').forward.  src/encoders.py:68-76 (nn.GRU batch_first, unidirectional, zero
+    initial state), :137-155 (h_n[-1] -> projection; with `lengths` h_n is the state after each clip's last valid
+    step, the packed-sequence branch :139-147).  nn.GRU cell, gate rows r, z, n:
+    r = sig(W_ir x + b_ir + W_hr h + b_hr), z likewise, n = tanh(W_in x + b_in + r * (W_hn h + b_hn)),
+    h' = (1 - z) * n + z * h."""
+    B, T, _ = seq.shape
+    x = seq
+    last = None
+    for l in range(num_layers):
+        w_ih, w_hh = sd[f"{prefix}rnn.weight_ih_l{l}"], sd[f"{prefix}rnn.weight_hh_l{l}"]
+        b_ih, b_hh = sd[f"{prefix}rnn.bias_ih_l{l}"], sd[f"{prefix}rnn.bias_hh_l{l}"]
+        H = w_hh.shape[1]
+        xp = x @ w_ih.T + b_ih
+        h = torch.zeros(B, H, dtype=seq.dtype)
+        last = torch.zeros(B, H, dtype=seq.dtype)
+        outs = []
+        for t in range(T):
+            hp = h @ w_hh.T + b_hh
+            r = torch.sigmoid(xp[:, t, 0 * H:1 * H] + hp[:, 0 * H:1 * H])
+            z = torch.sigmoid(xp[:, t, 1 * H:2 * H] + hp[:, 1 * H:2 * H])
+            n = torch.tanh(xp[:, t, 2 * H:3 * H] + r * hp[:, 2 * H:3 * H])
+            h = (1 - z) * n + z * h
+            outs.append(h)
+            if lengths is not None:
+                sel = (torch.as_tensor(lengths).clamp(1, T) - 1) == t
+                last[sel] = h[sel]
+        if lengths is None:
+            last = h
+        x = torch.stack(outs, dim=1)
+    return _lin(last, sd, prefix + "projection")
+
+
 _LSTM_CACHE = {}
 
 

@@ -111,6 +111,16 @@ def model_shapes(audio_dim=104, frame_dim=FRAME_DIM, enc_hidden=256, out_dim=128
         s[f"encoders.audio.rnn.bias_hh_l{l}"] = ((4 * H,), "u", H)
     s["encoders.audio.projection.weight"] = ((out_dim, H), "u", H)
     s["encoders.audio.projection.bias"] = ((out_dim,), "u", H)
+    # SequenceEncoder(encoder_type='gru') at the same dims (src/encoders.py:65-77), an alternative audio encoder kept
+    # under its own prefix and loaded as a standalone module by its consumers
+    for l in range(lstm_layers):
+        ind = audio_dim if l == 0 else H
+        s[f"gru_enc.rnn.weight_ih_l{l}"] = ((3 * H, ind), "u", H)
+        s[f"gru_enc.rnn.weight_hh_l{l}"] = ((3 * H, H), "u", H)
+        s[f"gru_enc.rnn.bias_ih_l{l}"] = ((3 * H,), "u", H)
+        s[f"gru_enc.rnn.bias_hh_l{l}"] = ((3 * H,), "u", H)
+    s["gru_enc.projection.weight"] = ((out_dim, H), "u", H)
+    s["gru_enc.projection.bias"] = ((out_dim,), "u", H)
     s["encoders.video.frame_mlp.0.weight"] = ((H, frame_dim), "u", frame_dim)
     s["encoders.video.frame_mlp.0.bias"] = ((H,), "u", frame_dim)
     s["encoders.video.attention.weight"] = ((1, H), "u", H)

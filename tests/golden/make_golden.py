@@ -218,6 +218,17 @@ def main():
     rec("xattn.out", o, oo)
     rec("xattn.attn", a, oa)
 
+    # SequenceEncoder(encoder_type='gru') (src/encoders.py:65-77, :137-155), with and without lengths
+    gru = ref_encoders.SequenceEncoder(input_dim=104, hidden_dim=256, output_dim=128, num_layers=2, encoder_type="gru",
+                                       dropout=0.1)
+    gru.load_state_dict({k[len("gru_enc."):]: v for k, v in sd.items() if k.startswith("gru_enc.")}, strict=True)
+    gru.eval()
+    gru_lengths = torch.tensor([301, 1, 17, 300, 128, 64])
+    with torch.inference_mode():
+        rec("gru.z", gru(feats), om.sequence_encoder_gru(feats, sd))
+        rec("gru.z_lengths", gru(feats, gru_lengths), om.sequence_encoder_gru(feats, sd, lengths=gru_lengths))
+    out["gru.lengths"] = gru_lengths.numpy()
+
     # calibration metrics (src/uncertainty.py:88-183, :512-544) on seeded random logits / labels
     g = torch.Generator().manual_seed(5)
     cal_logits = torch.randn(4000, 8, generator=g) * 2.0

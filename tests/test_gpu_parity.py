@@ -480,3 +480,23 @@ def test_calibration_metrics_vs_reference_golden(pkg, dev, golden):
         pkg.uncertainty.calibration_accumulate(a2, labels[i:i + 37], 15, logits=logits[i:i + 37])
     assert (a1[:15] == a2[:15]).all() and (a1[30:45] == a2[30:45]).all() and a1[47] == a2[47] == 4000
     assert torch.allclose(a1, a2, rtol=1e-12, atol=1e-9)
+
+
+def test_gru_sequence_encoder_vs_reference_golden(pkg, dev, world, golden):
+    """SequenceEncoder(encoder_type='gru') (src/encoders.py:65-77, :137-155)."""
+    enc = pkg.SequenceEncoder(input_dim=104, hidden_dim=256, output_dim=128, num_layers=2, encoder_type="gru")
+    enc.load_state_dict({k[len("gru_enc."):]: v for k, v in world["sd"].items() if k.startswith("gru_enc.")}, strict=True)
+    enc = enc.to(dev).eval()
+    feats = torch.from_numpy(world["feats"]).to(dev)
+    assert rel_err(enc(feats).cpu().numpy(), golden["gru.z"]) <= REL
+    lengths = torch.from_numpy(golden["gru.lengths"])
+    assert rel_err(enc(feats, lengths).cpu().numpy(), golden["gru.z_lengths"]) <= REL
+    # a batch that spans several recurrence tiles, ragged lengths, against the fp64 oracle
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.normal(size=(70, 23, 104)).astype(np.float32))
+    ln = torch.from_numpy(rng.integers(1, 24, size=70))
+    sd64 = {k: v.double() for k, v in world["sd"].items() if k.startswith("gru_enc.")}
+    want = om.sequence_encoder_gru(x.double(), sd64, lengths=ln)
+    assert rel_err(enc(x.to(dev), ln).cpu().numpy(), want.numpy()) <= REL
+    with pytest.raises(ValueError):
+        pkg.SequenceEncoder(input_dim=104, encoder_type="cnn")

@@ -70,6 +70,14 @@ def test_early_late_fusion_and_calibration(golden):
     assert abs(cal10["ece"] - float(golden["cal.ece10"])) <= 1e-6
 
 
+def test_gru_sequence_encoder(golden):
+    """SequenceEncoder(encoder_type='gru') restatement against the reference module's outputs."""
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    np.testing.assert_allclose(om.sequence_encoder_gru(feats, sd).numpy(), golden["gru.z"], **TOL)
+    z = om.sequence_encoder_gru(feats, sd, lengths=torch.from_numpy(golden["gru.lengths"]))
+    np.testing.assert_allclose(z.numpy(), golden["gru.z_lengths"], **TOL)
+
+
 def test_cross_modal_attention_general_shapes(golden):
     sd = {k[len("xattn."):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("xattn.att.")}
     q, kv = torch.from_numpy(golden["xattn.q"]), torch.from_numpy(golden["xattn.kv"])
