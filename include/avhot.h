@@ -147,6 +147,26 @@ size_t avhot_gru_workspace_bytes(avhot_gru_t h, int B, int T);
 int avhot_gru_forward(avhot_gru_t h, const float* seq, const int32_t* lengths, float* out, int B, int T,
                       void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 
+/* src/encoders.py:79-94, :157-168  SequenceEncoder(encoder_type='cnn'): Conv1d(k 5) - BatchNorm1d (eval) - ReLU - Dropout -
+ * Conv1d(k 3) - BatchNorm1d - ReLU - mean over T - Dropout - Linear.  fp32 path.  z (B, passes, out): pass t of clip b
+ * draws the masks of (seed, t0 + t, clip0 + b) at sites AVHOT_SITE_CNN0 ((H, T) activation) and AVHOT_SITE_CNN1
+ * (pooled vector); passes = 1 with p = 0 is eval mode.  `lengths` is ignored by the reference for this type. */
+typedef struct avhot_cnn* avhot_cnn_t;
+typedef struct {
+  int input_dim, hidden_dim, output_dim;
+  const float *conv1_weight, *conv1_bias;                       /* conv1.weight (H, in, 5), conv1.bias (H) */
+  const float *bn1_weight, *bn1_bias, *bn1_mean, *bn1_var;      /* bn1.weight / bias / running_mean / running_var */
+  const float *conv2_weight, *conv2_bias;                       /* conv2.weight (H, H, 3), conv2.bias (H) */
+  const float *bn2_weight, *bn2_bias, *bn2_mean, *bn2_var;
+  const float *proj_weight, *proj_bias;                         /* projection.weight (out, H), projection.bias */
+  float bn_eps;                                                 /* BatchNorm1d eps (1e-5) */
+} avhot_cnn_desc;
+int avhot_cnn_create(const avhot_cnn_desc* desc, avhot_cnn_t* out, avhot_stream_t stream);
+void avhot_cnn_destroy(avhot_cnn_t h);
+size_t avhot_cnn_workspace_bytes(avhot_cnn_t h, int B, int T, int passes);
+int avhot_cnn_forward(avhot_cnn_t h, const float* seq, float* z, int B, int T, int passes, float p, uint64_t seed,
+                      uint64_t clip0, uint32_t t0, void* workspace, size_t workspace_bytes, avhot_stream_t stream);
+
 /* ---- a4: src/encoders.py:196-327  FrameEncoder(temporal_pooling='attention') -------- */
 typedef struct avhot_frame* avhot_frame_t;
 typedef struct {
@@ -288,6 +308,8 @@ int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
 #define AVHOT_SITE_MODMASK 3u
 #define AVHOT_SITE_EARLY0 4u
 #define AVHOT_SITE_EARLY1 5u
+#define AVHOT_SITE_CNN0 6u
+#define AVHOT_SITE_CNN1 7u
 #define AVHOT_SITE_ATTN 16u
 #define AVHOT_SITE_LATE 32u
 

@@ -15,6 +15,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 PREC_FP32, PREC_BF16X3, PREC_TC = 0, 1, 2
 SITE_FRAME_MLP, SITE_FRAME_POOL, SITE_GATE, SITE_MODMASK, SITE_ATTN = 0, 1, 2, 3, 16
 SITE_EARLY0, SITE_EARLY1, SITE_LATE = 4, 5, 32
+SITE_CNN0, SITE_CNN1 = 6, 7
 MAX_MODALITIES = 4
 
 c_float_p = C.c_void_p  # device pointers travel as integers
@@ -26,6 +27,13 @@ class LstmDesc(C.Structure):
                 ("weight_ih", C.c_void_p * 4), ("weight_hh", C.c_void_p * 4),
                 ("bias_ih", C.c_void_p * 4), ("bias_hh", C.c_void_p * 4),
                 ("proj_weight", C.c_void_p), ("proj_bias", C.c_void_p)]
+
+
+class CnnDesc(C.Structure):
+    _fields_ = [("input_dim", C.c_int), ("hidden_dim", C.c_int), ("output_dim", C.c_int)] + [(n, C.c_void_p) for n in (
+        "conv1_weight", "conv1_bias", "bn1_weight", "bn1_bias", "bn1_mean", "bn1_var",
+        "conv2_weight", "conv2_bias", "bn2_weight", "bn2_bias", "bn2_mean", "bn2_var",
+        "proj_weight", "proj_bias")] + [("bn_eps", C.c_float)]
 
 
 class FrameDesc(C.Structure):
@@ -97,6 +105,10 @@ PROTOTYPES = {
     "avhot_lstm_destroy": (None, [_P]),
     "avhot_lstm_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "avhot_lstm_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
+    "avhot_cnn_create": (_I, [C.POINTER(CnnDesc), C.POINTER(_P), _P]),
+    "avhot_cnn_destroy": (None, [_P]),
+    "avhot_cnn_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "avhot_cnn_forward": (_I, [_P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P, _SZ, _P]),
     "avhot_gru_create": (_I, [C.POINTER(LstmDesc), C.POINTER(_P), _P]),
     "avhot_gru_destroy": (None, [_P]),
     "avhot_gru_workspace_bytes": (_SZ, [_P, _I, _I]),

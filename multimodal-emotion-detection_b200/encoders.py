@@ -21,9 +21,9 @@ _ws_frames = Workspace()
 
 
 class SequenceEncoder(nn.Module):
-    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru' (SURVEY.md 8f
-    row 1) runs on the fp32 kernels of csrc/gru.cu; 'cnn' and 'transformer' are valid in the reference and not built
-    here (ValueError says so)."""
+    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru' and 'cnn'
+     run on the fp32 kernels of csrc/gru.cu / csrc/cnn.cu; 'transformer' is valid in the
+    reference and not built here (ValueError says so)."""
 
     def __init__(self, input_dim: int, hidden_dim: int = 256, output_dim: int = 128, num_layers: int = 2,
                  encoder_type: str = 'lstm', dropout: float = 0.1):
@@ -44,12 +44,76 @@ class SequenceEncoder(nn.Module):
                               batch_first=True, dropout=dropout if num_layers > 1 else 0.0,
                               bidirectional=False)                                   # src/encoders.py:68-75
             self.projection = nn.Linear(hidden_dim, output_dim)                      # :76
-        elif encoder_type in ('cnn', 'transformer'):
+        elif encoder_type == 'cnn':
+            self.conv1 = nn.Conv1d(input_dim, hidden_dim, kernel_size=5, padding=2)  # src/encoders.py:86-93
+            self.bn1 = nn.BatchNorm1d(hidden_dim)
+            self.conv2 = nn.Conv1d(hidden_dim, hidden_dim, kernel_size=3, padding=1)
+            self.bn2 = nn.BatchNorm1d(hidden_dim)
+            self.act = nn.ReLU(inplace=True)
+            self.dropout_layer = nn.Dropout(p=dropout)
+            self.pool = nn.AdaptiveAvgPool1d(1)
+            self.projection = nn.Linear(hidden_dim, output_dim)
+        elif encoder_type == 'transformer':
             raise ValueError(f"encoder type '{encoder_type}' exists in the reference but is not built in this "
                              "library (hot path = 'lstm')")
         else:
             raise ValueError(f"Unknown encoder type: {encoder_type}")                # :115
-        self._handle = Handle("avhot_gru_destroy" if encoder_type == 'gru' else "avhot_lstm_destroy")
+        self._handle = Handle({"gru": "avhot_gru_destroy", "cnn": "avhot_cnn_destroy"}.get(encoder_type,
+                                                                                            "avhot_lstm_destroy"))
+
+    def _cnn_tensors(self):
+        return [self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self.bn1.running_mean,
+                self.bn1.running_var, self.conv2.weight, self.conv2.bias, self.bn2.weight, self.bn2.bias,
+                self.bn2.running_mean, self.bn2.running_var, self.projection.weight, self.projection.bias]
+
+    def _get_cnn_handle(self, dev):
+        src = self._cnn_tensors()
+
+        def create():
+            ts = [_lib.f32c(t.detach()) for t in src]
+            _lib.require_cuda(*ts)
+            d = _lib.CnnDesc()
+            d.input_dim, d.hidden_dim, d.output_dim = self.input_dim, self.hidden_dim, self.output_dim
+            (d.conv1_weight, d.conv1_bias, d.bn1_weight, d.bn1_bias, d.bn1_mean, d.bn1_var, d.conv2_weight,
+             d.conv2_bias, d.bn2_weight, d.bn2_bias, d.bn2_mean, d.bn2_var, d.proj_weight, d.proj_bias) = \
+                [t.data_ptr() for t in ts]
+            d.bn_eps = float(self.bn1.eps)
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_cnn_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
+                       "SequenceEncoder(cnn)")
+            torch.cuda.current_stream(dev).synchronize()       # the handle folds / copies from `ts` on the stream
+            return out.value
+
+        return self._handle.get(src, create)
+
+    @torch.no_grad()
+    def _forward_cnn(self, x: torch.Tensor, passes: int = 1, p: Optional[float] = None, seed: Optional[int] = None,
+                     clip0: Optional[int] = None, t0: Optional[int] = None) -> torch.Tensor:
+        """(B, T, in) -> (B, passes, out).  src/encoders.py:157-168; BatchNorm uses its running statistics (the
+        inference path: MCDropoutUncertainty puts only nn.Dropout modules in train mode, src/uncertainty.py:36-46)."""
+        if self.bn1.training or self.bn2.training:
+            raise ValueError("SequenceEncoder(cnn): training-mode BatchNorm (batch statistics) is not built; call eval()")
+        if float(self.bn1.eps) != float(self.bn2.eps):
+            raise ValueError("SequenceEncoder(cnn): bn1 and bn2 must share eps")
+        dev = x.device
+        B, T, _ = x.shape
+        if p is None:
+            p = float(self.dropout_layer.p) if self.dropout_layer.training else 0.0
+        cs, ct, cc = _rng.current()
+        seed = cs if seed is None else seed
+        t0 = ct if t0 is None else t0
+        clip0 = cc if clip0 is None else clip0
+        z = torch.empty(B, passes, self.output_dim, device=dev, dtype=torch.float32)
+        if B == 0:
+            return z
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._get_cnn_handle(dev)
+            ws = _ws.get(lib.avhot_cnn_workspace_bytes(h, B, T, passes), dev)
+            _lib.check(lib.avhot_cnn_forward(h, _lib.ptr(x), _lib.ptr(z), B, T, passes, float(p), seed, clip0, t0,
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                       "SequenceEncoder.forward (cnn)")
+        return z
 
     def _params(self):
         ps = []
@@ -93,6 +157,8 @@ class SequenceEncoder(nn.Module):
             lengths = torch.as_tensor(lengths).to(device=dev, dtype=torch.int32).contiguous()
             if lengths.shape != (B,):
                 raise ValueError("lengths must be (B,)")
+        if self.encoder_type == 'cnn':
+            return self._forward_cnn(x)[:, 0, :]               # `lengths` is ignored for this type (:157-168)
         out = torch.empty(B, self.output_dim, device=dev, dtype=torch.float32)
         if B == 0:
             return out

@@ -128,6 +128,34 @@ def sequence_encoder_gru(seq, sd, prefix="gru_enc.", num_layers=2, lengths=None)
     return _lin(last, sd, prefix + "projection")
 
 
+def sequence_encoder_cnn(seq, sd, prefix="cnn_enc.", ctx: Optional[DropCtx] = None, eps=1e-5):
+    """SequenceEncoder(encoder_type='cnn').forward.  src/encoders.py:157-168: transpose to (B, C, T), Conv1d(k 5, pad 2),
+    BatchNorm1d (eval: running statistics), ReLU, Dropout, Conv1d(k 3, pad 1), BatchNorm1d, ReLU, mean over T, the same
+    Dropout module again, Linear.  Dropout sites: CNN0 on the (B, H, T) activation (element h * T + t), CNN1 on the
+    pooled (B, H) vector; p = the encoder's dropout (ctx.p_encoder)."""
+    def conv1d(x, w, b, pad):                      # x (B, C, T), w (O, C, K): written out as K shifted matmuls
+        B, C, T = x.shape
+        xp = torch.nn.functional.pad(x, (pad, pad))
+        out = b.view(1, -1, 1).expand(B, w.shape[0], T).clone()
+        for k in range(w.shape[2]):
+            out = out + torch.einsum("oc,bct->bot", w[:, :, k], xp[:, :, k:k + T])
+        return out
+
+    def bn(x, name):
+        g = sd[f"{prefix}{name}.weight"] / torch.sqrt(sd[f"{prefix}{name}.running_var"] + eps)
+        return (x - sd[f"{prefix}{name}.running_mean"].view(1, -1, 1)) * g.view(1, -1, 1) + sd[f"{prefix}{name}.bias"].view(1, -1, 1)
+
+    x = seq.transpose(1, 2)
+    x = torch.relu(bn(conv1d(x, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"], 2), "bn1"))
+    if ctx is not None:
+        x = ctx.apply(x, px.SITE_CNN0, ctx.p_encoder)
+    x = torch.relu(bn(conv1d(x, sd[prefix + "conv2.weight"], sd[prefix + "conv2.bias"], 1), "bn2"))
+    x = x.mean(dim=2)
+    if ctx is not None:
+        x = ctx.apply(x, px.SITE_CNN1, ctx.p_encoder)
+    return _lin(x, sd, prefix + "projection")
+
+
 _LSTM_CACHE = {}
 
 

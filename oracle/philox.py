@@ -29,6 +29,8 @@ the per-clip mask tensor):
     SITE_MODMASK     3   modality dropout             (M,)        src/data.py:111-118
     SITE_EARLY0      4   EarlyFusion mlp.3            (hidden,)   src/fusion.py:65
     SITE_EARLY1      5   EarlyFusion mlp.7            (hidden,)   src/fusion.py:69
+    SITE_CNN0        6   SequenceEncoder(cnn).dropout_layer, 1st use  (H, T)   src/encoders.py:161
+    SITE_CNN1        7   SequenceEncoder(cnn).dropout_layer, 2nd use  (H,)     src/encoders.py:167
     SITE_ATTN + i    16+i fusion_model.attn_layers[i].attn_dropout (heads, Tq, Tk)
                                                                   src/attention.py:51,130
     SITE_LATE + i    32+i LateFusion classifiers[i].2  (hidden,)   src/fusion.py:184
@@ -50,6 +52,8 @@ SITE_GATE = 2
 SITE_MODMASK = 3
 SITE_EARLY0 = 4
 SITE_EARLY1 = 5
+SITE_CNN0 = 6
+SITE_CNN1 = 7
 SITE_ATTN = 16
 SITE_LATE = 32
 

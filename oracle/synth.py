@@ -121,6 +121,19 @@ def model_shapes(audio_dim=104, frame_dim=FRAME_DIM, enc_hidden=256, out_dim=128
         s[f"gru_enc.rnn.bias_hh_l{l}"] = ((3 * H,), "u", H)
     s["gru_enc.projection.weight"] = ((out_dim, H), "u", H)
     s["gru_enc.projection.bias"] = ((out_dim,), "u", H)
+    # SequenceEncoder(encoder_type='cnn') (src/encoders.py:86-93); BatchNorm running statistics perturbed like the
+    # LayerNorm affines so the folded arithmetic is exercised (running_var = 1 + 0.1 u > 0)
+    s["cnn_enc.conv1.weight"] = ((H, audio_dim, 5), "u", 5 * audio_dim)
+    s["cnn_enc.conv1.bias"] = ((H,), "u", 5 * audio_dim)
+    s["cnn_enc.conv2.weight"] = ((H, H, 3), "u", 3 * H)
+    s["cnn_enc.conv2.bias"] = ((H,), "u", 3 * H)
+    for bn in ("bn1", "bn2"):
+        s[f"cnn_enc.{bn}.weight"] = ((H,), "lnw", 0)
+        s[f"cnn_enc.{bn}.bias"] = ((H,), "lnb", 0)
+        s[f"cnn_enc.{bn}.running_mean"] = ((H,), "lnb", 0)
+        s[f"cnn_enc.{bn}.running_var"] = ((H,), "lnw", 0)
+    s["cnn_enc.projection.weight"] = ((out_dim, H), "u", H)
+    s["cnn_enc.projection.bias"] = ((out_dim,), "u", H)
     s["encoders.video.frame_mlp.0.weight"] = ((H, frame_dim), "u", frame_dim)
     s["encoders.video.frame_mlp.0.bias"] = ((H,), "u", frame_dim)
     s["encoders.video.attention.weight"] = ((1, H), "u", H)

@@ -229,6 +229,35 @@ def main():
         rec("gru.z_lengths", gru(feats, gru_lengths), om.sequence_encoder_gru(feats, sd, lengths=gru_lengths))
     out["gru.lengths"] = gru_lengths.numpy()
 
+    # SequenceEncoder(encoder_type='cnn') (src/encoders.py:79-94, :157-168): eval, and MC passes with the spec masks
+    # injected into its one nn.Dropout module, which forward calls twice (sites CNN0, CNN1)
+    cnn = ref_encoders.SequenceEncoder(input_dim=104, hidden_dim=256, output_dim=128, num_layers=2, encoder_type="cnn",
+                                       dropout=0.1)
+    cnn_sd = {k[len("cnn_enc."):]: v for k, v in sd.items() if k.startswith("cnn_enc.")}
+    cnn_sd["bn1.num_batches_tracked"] = torch.tensor(0)
+    cnn_sd["bn2.num_batches_tracked"] = torch.tensor(0)
+    cnn.load_state_dict(cnn_sd, strict=True)
+    cnn.eval()
+    with torch.inference_mode():
+        rec("cnn.z", cnn(feats), om.sequence_encoder_cnn(feats, sd))
+    state = {"t": 0, "call": 0}
+
+    def cnn_drop(x, mod=cnn.dropout_layer):
+        site = (px.SITE_CNN0, px.SITE_CNN1)[state["call"] % 2]
+        state["call"] += 1
+        n = int(np.prod(x.shape[1:]))
+        keep = px.dropout_keep(n, CLIP_IDS, state["t"], site, mod.p, SEED).reshape(x.shape)
+        return x * (torch.from_numpy(keep).float() * float(px.keep_scale(mod.p)))
+    cnn.dropout_layer.forward = cnn_drop
+    passes = []
+    with torch.inference_mode():
+        for t in range(3):
+            state["t"] = t
+            ref_z = cnn(feats)
+            passes.append(ref_z)
+            ora = om.sequence_encoder_cnn(feats, sd, ctx=om.DropCtx(SEED, t, CLIP_IDS))
+            rec(f"cnn.z_pass{t}", ref_z, ora)
+
     # calibration metrics (src/uncertainty.py:88-183, :512-544) on seeded random logits / labels
     g = torch.Generator().manual_seed(5)
     cal_logits = torch.randn(4000, 8, generator=g) * 2.0

@@ -499,4 +499,46 @@ def test_gru_sequence_encoder_vs_reference_golden(pkg, dev, world, golden):
     want = om.sequence_encoder_gru(x.double(), sd64, lengths=ln)
     assert rel_err(enc(x.to(dev), ln).cpu().numpy(), want.numpy()) <= REL
     with pytest.raises(ValueError):
-        pkg.SequenceEncoder(input_dim=104, encoder_type="cnn")
+        pkg.SequenceEncoder(input_dim=104, encoder_type="transformer")
+
+
+def test_cnn_sequence_encoder_vs_reference_golden(pkg, dev, world, golden):
+    """SequenceEncoder(encoder_type='cnn') (src/encoders.py:79-94, :157-168): eval output, the
+    stochastic passes (one nn.Dropout used twice: sites CNN0 / CNN1, clip ids of the golden file are not contiguous so
+    each clip runs with its own clip0), and MCDropoutUncertainty's generic pass-by-pass path over it."""
+    enc = pkg.SequenceEncoder(input_dim=104, hidden_dim=256, output_dim=128, num_layers=2, encoder_type="cnn", dropout=0.1)
+    sd = {k[len("cnn_enc."):]: v for k, v in world["sd"].items() if k.startswith("cnn_enc.")}
+    sd["bn1.num_batches_tracked"] = torch.tensor(0)
+    sd["bn2.num_batches_tracked"] = torch.tensor(0)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(dev).eval()
+    feats = torch.from_numpy(world["feats"]).to(dev)
+    assert rel_err(enc(feats).cpu().numpy(), golden["cnn.z"]) <= REL
+    assert rel_err(enc(feats, torch.tensor([5] * feats.shape[0])).cpu().numpy(), golden["cnn.z"]) <= REL   # lengths ignored
+    pkg.MCDropoutUncertainty._set_dropout_train(enc)
+    for t in range(3):
+        rows = []
+        for b, g in enumerate(world["ids"]):
+            with pkg.philox_context(SEED, t, int(g)):
+                rows.append(enc(feats[b:b + 1]))
+        assert rel_err(torch.cat(rows).cpu().numpy(), golden[f"cnn.z_pass{t}"]) <= REL, t
+    # several passes in one call == pass by pass; the wrapper restores modes
+    many = enc._forward_cnn(feats[:1], passes=3, seed=SEED, clip0=int(world["ids"][0]), t0=0)
+    assert rel_err(many[0].cpu().numpy(), np.stack([golden[f"cnn.z_pass{t}"][0] for t in range(3)])) <= REL
+    enc.eval()
+
+    class FirstEight(torch.nn.Module):               # 8 "logits": avhot_mc_reduce handles up to 32 classes
+        def __init__(self, e):
+            super().__init__()
+            self.e = e
+
+        def forward(self, x):
+            return self.e(x)[:, :8]
+
+    mc = pkg.MCDropoutUncertainty(FirstEight(enc).eval(), num_samples=4)
+    mean, unc = mc(feats)
+    assert mean.shape == (feats.shape[0], 8) and unc.shape == (feats.shape[0],) and float(unc.min()) > 0
+    assert not enc.training and not enc.dropout_layer.training
+    enc.train()
+    with pytest.raises(ValueError):
+        enc(feats)                                   # training-mode BatchNorm is not built

@@ -78,6 +78,16 @@ def test_gru_sequence_encoder(golden):
     np.testing.assert_allclose(z.numpy(), golden["gru.z_lengths"], **TOL)
 
 
+def test_cnn_sequence_encoder(golden):
+    """SequenceEncoder(encoder_type='cnn') restatement against the reference module (eval and
+    three stochastic passes with the spec masks injected into its twice-used nn.Dropout)."""
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    np.testing.assert_allclose(om.sequence_encoder_cnn(feats, sd).numpy(), golden["cnn.z"], rtol=1e-4, atol=1e-4)
+    for t in range(3):
+        z = om.sequence_encoder_cnn(feats, sd, ctx=om.DropCtx(seed, t, ids))
+        np.testing.assert_allclose(z.numpy(), golden[f"cnn.z_pass{t}"], rtol=1e-4, atol=1e-4)
+
+
 def test_cross_modal_attention_general_shapes(golden):
     sd = {k[len("xattn."):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("xattn.att.")}
     q, kv = torch.from_numpy(golden["xattn.q"]), torch.from_numpy(golden["xattn.kv"])
