@@ -22,6 +22,7 @@ struct avhot_lstm {
   float* w_ih[4];    // (4H, in_k) row-major copies
   float* w_hh_t[4];  // [k][gate][j]  = W_hh[gate*H + j][k]
   float* bias[4];    // b_ih + b_hh
+  float* bias_tc[4]; // the same with the i, f, o rows halved (tensor-core path: sigmoid(x) = 0.5 tanh(x / 2) + 0.5)
   void* w_hh_r16[4]; // fp16, rows regrouped per 32-unit chunk (lstm_tc.cu)
   void* w_ih_f16[4];  // fp16 input weights for the tensor-core path: layer 0 (4H, 3*in) = [W_hi | W_hi | W_lo],
                       // layers > 0 (4H, H)
@@ -119,26 +120,34 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // half-precision pass (measured 5.7e-3 error with one TF32 pass).  Requires |x| < 65504.
 // weights: W (N, K) fp32 -> out (N, ldo) fp16 = [W_hi | W_hi | W_lo | 0...]  (ldo >= 3K + 2; the operand's
 // (1, 1) columns meet zeros: the bias is added in fp32 by the GEMM epilogue)
+// Rows of the sigmoid gates (i, f, o: every gate but g = rows [2H, 3H)) are stored halved - exact, a power of two -
+// so that the recurrent kernel's sigmoid(x) = 0.5 tanh(x / 2) + 0.5 needs no pre-scaling multiply (lstm_tc.cu).
+__device__ __forceinline__ float tc_gate_scale(int n, int N) { return (n / (N / 4)) == 2 ? 1.f : 0.5f; }
 __global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                      __half* __restrict__ out, int N, int K, int ldo) {
   const int n = blockIdx.x;
+  const float sc = tc_gate_scale(n, N);
   for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
     float v = 0.f;
     bool lo = false;
-    if (k < 2 * K) v = w[(size_t)n * K + (k % K)];
-    else if (k < 3 * K) { v = w[(size_t)n * K + (k - 2 * K)]; lo = true; }
+    if (k < 2 * K) v = sc * w[(size_t)n * K + (k % K)];
+    else if (k < 3 * K) { v = sc * w[(size_t)n * K + (k - 2 * K)]; lo = true; }
     const __half hi = __float2half_rn(v);
     out[(size_t)n * ldo + k] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
   }
 }
 // weights of layers > 0: W (N, K) fp32 -> out (N, ldo) fp16 = [W | 0...]
+__global__ void scale_gate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) out[n] = tc_gate_scale(n, N) * b[n];
+}
 __global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                    __half* __restrict__ out, int N, int K, int ldo) {
   const int n = blockIdx.x;
   for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
     float v = 0.f;
     bool lo = false;
-    if (k < K) v = w[(size_t)n * K + k];
+    if (k < K) v = tc_gate_scale(n, N) * w[(size_t)n * K + k];
     out[(size_t)n * ldo + k] = __float2half_rn(v);
   }
 }
@@ -204,7 +213,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     AVHOT_REQUIRE(d->weight_ih[l] && d->weight_hh[l] && d->bias_ih[l] && d->bias_hh[l], AVHOT_ERR_INVALID,
                   "lstm_create: layer %d tensors missing", l);
     total += align256(sizeof(float) * 4 * H * in) + align256(sizeof(float) * 4 * H * H) +
-             align256(sizeof(float) * 4 * H) + align256(2 * 4 * H * H);
+             2 * align256(sizeof(float) * 4 * H) + align256(2 * 4 * H * H);
   }
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
@@ -227,6 +236,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     h->w_ih[l] = take(sizeof(float) * 4 * H * in);
     h->w_hh_t[l] = take(sizeof(float) * 4 * H * H);
     h->bias[l] = take(sizeof(float) * 4 * H);
+    h->bias_tc[l] = take(sizeof(float) * 4 * H);
     h->w_hh_r16[l] = take(2 * 4 * H * H);
     if (cudaMemcpyAsync(h->w_ih[l], d->weight_ih[l], sizeof(float) * 4 * H * in, cudaMemcpyDeviceToDevice, s) !=
         cudaSuccess) rc = AVHOT_ERR_CUDA;
@@ -235,6 +245,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     if (rc == AVHOT_OK) rc = lstm_pack_whh_fp16(d->weight_hh[l], h->w_hh_r16[l], s);
   }
   for (int l = 0; l < L && rc == AVHOT_OK; ++l) {   // after the bias sums above (same stream)
+    scale_gate_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, s>>>(h->bias[l], h->bias_tc[l], 4 * H);
     if (l == 0) {
       const int ldo = pad8(3 * d->input_dim + 2);
       h->w_ih_f16[0] = take(2 * 4 * H * ldo);
@@ -347,7 +358,7 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
       static const int l0_terms = [] { const char* e = getenv("AVHOT_L0_TERMS"); return e && atoi(e) == 2 ? 2 : 3; }();
       if (l == 0 && seq_split) {                      // operand already prepared by avhot_frontend_ex
         const int ldx = pad8(3 * in + 2);
-        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, h->bias[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
       } else if (l == 0) {
         const int ldx = pad8(3 * in + 2);
         {
@@ -358,9 +369,9 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
               x, x_split, B, (int)Bp, T, in, ldx);
           AVHOT_LAUNCH_CHECK();
         }
-        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, h->bias[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
       } else {
-        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, h->bias[l], xp, true, 4 * H, Mp, 4 * H, H, s, "lstm_input_gemm_tc");
+        rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, h->bias_tc[l], xp, true, 4 * H, Mp, 4 * H, H, s, "lstm_input_gemm_tc");
       }
       if (rc == AVHOT_OK)
         rc = lstm_recurrence_tc(h->w_hh_r16[l], xp, xf16, last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);

@@ -74,13 +74,15 @@ __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
+// The pre-activations of the sigmoid gates arrive HALVED: W_hh, W_ih and the bias rows of i, f, o are packed times 0.5
+// (exact), so act_sigmoid takes xh = x / 2.
 // ACT = 0: 1 / (1 + 2^(-x log2 e)) by ex2.approx + rcp.approx (~2 ulp each), tanh = 2 sigmoid(2x) - 1: two MUFU
 //          operations per activation.
 // ACT = 1: tanh.approx.f32 (one MUFU, max relative error 2^-11), sigmoid(x) = 0.5 + 0.5 tanh(x / 2).
-template <int ACT> __device__ __forceinline__ float act_sigmoid(float x) {
-  if (ACT == 0) return __fdividef(1.f, 1.f + __expf(-x));
+template <int ACT> __device__ __forceinline__ float act_sigmoid(float xh) {
+  if (ACT == 0) return __fdividef(1.f, 1.f + __expf(-2.f * xh));
   float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(xh));
   return fmaf(0.5f, y, 0.5f);
 }
 template <int ACT> __device__ __forceinline__ float act_tanh(float x) {
@@ -421,7 +423,8 @@ __global__ void pack_whh_fp16_kernel(const float* __restrict__ w, __half* __rest
   const int row = blockIdx.x;                 // packed row
   const int c = row >> 7, g = (row >> 5) & 3, u = row & 31;
   const float* src = w + (size_t)(g * RH + c * RCH + u) * RH;
-  for (int k = threadIdx.x; k < RH; k += blockDim.x) out[(size_t)row * RH + k] = __float2half_rn(src[k]);
+  const float sc = g == 2 ? 1.f : 0.5f;     // sigmoid gates stored halved (see act_sigmoid)
+  for (int k = threadIdx.x; k < RH; k += blockDim.x) out[(size_t)row * RH + k] = __float2half_rn(sc * src[k]);
 }
 
 }  // namespace tc

@@ -81,17 +81,6 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // all committed bulk stores of this thread have finished READING shared memory
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// Multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask` (bit i = cluster rank i)
-// and completes the mbarrier at the same offset in each of them.
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask)
-      : "memory");
-}
 
 // ---- thread-block clusters ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -198,16 +187,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Same for the no-swizzle ("interleaved") K-major layout: 8-row x 16-byte core matrices stored contiguously
-// (128 bytes each); lbo = byte distance between core matrices adjacent in K, sbo = between adjacent 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
 // Instruction descriptor (32 bit): D fp32; A, B of `fmt` (0 = f16, 1 = bf16, 2 = tf32), both K-major; M x N tile.
 //   bits [4,6) D format = 1 (f32)   [7,10) A format   [10,13) B format   bit 15 / 16 A / B major (0 = K)
 //   bits [17,23) N >> 3             [24,29) M >> 4
@@ -217,45 +196,11 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- tcgen05: MMA, commit, TMEM load ---------------------------------------------------------------------------
-// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.  kind::tf32: K = 8 per instruction; kind::f16: K = 16.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-// CTA pair: M = 256 (128 rows from each CTA's A tile), N split in halves over the two CTAs' B tiles; issued by one
-// thread of the leader CTA; descriptors are CTA-relative and apply to both CTAs
-__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
 // Warp-uniform issue: the whole (converged) warp executes the call with warp-uniform operands and one elected lane -
 // always the same one - issues the instruction.  Unlike `if (lane == 0) umma_f16(...)`, whose operands ptxas must move
 // from per-thread to uniform registers with an ELECT / R2UR.BROADCAST loop (~14 instructions per MMA on a warp that
 // competes for issue slots with four epilogue warps), the descriptors then live in uniform registers from the start.
+// D[tmem] (+)= A[smem] * B[smem]^T.  kind::f16: K = 16 per instruction; kind::tf32: K = 8.
 __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -272,6 +217,8 @@ __device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t adesc,
       : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// CTA pair (cta_group::2): M = 256 (128 rows from each CTA's A tile), the N rows of B split in halves over the two CTAs'
+// tiles; issued by the leader CTA only; descriptors are CTA-relative and apply to both CTAs
 __device__ __forceinline__ void umma_f16_pair_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -280,29 +227,18 @@ __device__ __forceinline__ void umma_f16_pair_elect(uint32_t d_tmem, uint64_t ad
       : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// all tcgen05.mma issued so far by the elected thread -> one arrival on `bar` when they have completed
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+// same for a CTA pair, arriving on the mbarrier at this CTA-relative offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_pair_mc_elect(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-// all tcgen05.mma issued so far by this thread -> one arrival on `bar` when they have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// same, arriving on the mbarrier at this CTA-relative offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
       "h"(cta_mask)
       : "memory");
@@ -317,15 +253,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
