@@ -438,7 +438,7 @@ def main():
                     help="clips per GPU per step (default: one 128-clip CTA of the recurrent kernel per SM)")
     ap.add_argument("--e2e-chunk", type=int, default=2048, help="clips per host->device sub-batch in the e2e leg")
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
-    ap.add_argument("--cpu-clips", type=int, default=32, help="clips in the bounded CPU sample")
+    ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU sample (~10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="tc: large contractions on tcgen05 (TF32 / fp16 operands); fp32: CUDA-core fp32 everywhere")
