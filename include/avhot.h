@@ -284,6 +284,31 @@ int avhot_head_forward(avhot_head_t h, const float* const* z_host_array, const i
                        int present_mask, const float* mask, float* logits, float* per_modality_logits,
                        int B, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
                        avhot_stream_t stream);
+/* src/fusion.py:589-655  LateFusionWithUncertainty (build_fusion_model('uncertainty')): per modality a classifier and a
+ * scalar-uncertainty head - hidden_dim > 0: Dropout, Linear(d, D), ReLU, Dropout, Linear(D, C | 1); hidden_dim == 0:
+ * Dropout, Linear(d, C | 1) - softplus on the uncertainty, then UncertaintyWeightedFusion (src/uncertainty.py:279-318):
+ * w_m = (mask_m / (u_m + eps)) / (sum_m + eps).  Tensors with hidden_dim == 0: only *_w3 / *_b3 (the single Linear). */
+typedef struct {
+  int num_modalities, hidden_dim, num_classes;
+  int modality_dim[AVHOT_MAX_MODALITIES];
+  const float *cls_w0[AVHOT_MAX_MODALITIES], *cls_b0[AVHOT_MAX_MODALITIES];   /* classifiers.<m>.1  (D, d), (D)  */
+  const float *cls_w3[AVHOT_MAX_MODALITIES], *cls_b3[AVHOT_MAX_MODALITIES];   /* classifiers.<m>.4  (C, D), (C)  */
+  const float *unc_w0[AVHOT_MAX_MODALITIES], *unc_b0[AVHOT_MAX_MODALITIES];   /* uncert_heads.<m>.1 (D, d), (D)  */
+  const float *unc_w3[AVHOT_MAX_MODALITIES], *unc_b3[AVHOT_MAX_MODALITIES];   /* uncert_heads.<m>.4 (1, D), (1)  */
+  float epsilon;
+} avhot_unc_desc;
+int avhot_unc_create(const avhot_unc_desc* desc, avhot_head_t* out, avhot_stream_t stream);   /* avhot_head_destroy frees */
+/* forward(encoded_features, modality_mask) for R = B*T rows: logits (R, C), per_modality_logits (R, M, C) or NULL,
+ * fusion_weights (R, M) or NULL; mask (B, M) is required (:622).  A modality that is not given (bit clear in
+ * present_mask) is zeros (:629).  Dropout sites AVHOT_SITE_UNC + 4 m + {0 classifier input, 1 classifier hidden,
+ * 2 uncertainty-head input, 3 uncertainty-head hidden}. */
+int avhot_unc_forward(avhot_head_t h, const float* const* z_host_array, const int* z_rows_per_clip_host,
+                      int present_mask, const float* mask, float* logits, float* per_modality_logits,
+                      float* fusion_weights, int B, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                      avhot_stream_t stream);
+/* UncertaintyWeightedFusion.forward on its own: logits (R, M, C), uncert (R, M), mask (R, M) -> fused (R, C), weights (R, M) */
+int avhot_uncertainty_fuse(const float* logits, const float* uncert, const float* mask, float* fused, float* weights,
+                           long long R, int M, int C, float eps, avhot_stream_t stream);
 /* src/uncertainty.py:88-183, :512-544  calibration statistics, accumulated into acc (device, doubles, caller-zeroed):
  * [0,nb) bin counts, [nb,2nb) sum of confidences, [2nb,3nb) correct counts, [3nb] NLL sum (logits given),
  * [3nb+1] correct total, [3nb+2] samples.  Either logits (N, C) - confidence = max softmax, prediction = argmax,
@@ -312,6 +337,7 @@ int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
 #define AVHOT_SITE_CNN1 7u
 #define AVHOT_SITE_ATTN 16u
 #define AVHOT_SITE_LATE 32u
+#define AVHOT_SITE_UNC 48u
 
 #ifdef __cplusplus
 }

@@ -7,8 +7,9 @@ from . import _lib, _rng, dataprocessing, encoders, attention, fusion, uncertain
 from ._rng import philox_context  # noqa: F401
 from .encoders import SequenceEncoder, FrameEncoder, build_encoder  # noqa: F401
 from .attention import CrossModalAttention  # noqa: F401
-from .fusion import HybridFusion, EarlyFusion, LateFusion, ConcatHead, build_fusion_model  # noqa: F401
-from .uncertainty import MCDropoutUncertainty, CalibrationMetrics, compute_calibration_metrics, mc_reduce  # noqa: F401
+from .fusion import HybridFusion, EarlyFusion, LateFusion, LateFusionWithUncertainty, ConcatHead, build_fusion_model  # noqa: F401
+from .uncertainty import (MCDropoutUncertainty, CalibrationMetrics, UncertaintyWeightedFusion,  # noqa: F401
+                          compute_calibration_metrics, mc_reduce)  # noqa: F401
 from .dataprocessing import condition_audio, logmel_mfcc, load_raw_audio  # noqa: F401
 from .hotpath import AVHotPath  # noqa: F401
 

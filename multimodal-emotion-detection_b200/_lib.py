@@ -16,6 +16,7 @@ PREC_FP32, PREC_BF16X3, PREC_TC = 0, 1, 2
 SITE_FRAME_MLP, SITE_FRAME_POOL, SITE_GATE, SITE_MODMASK, SITE_ATTN = 0, 1, 2, 3, 16
 SITE_EARLY0, SITE_EARLY1, SITE_LATE = 4, 5, 32
 SITE_CNN0, SITE_CNN1 = 6, 7
+SITE_UNC = 48
 MAX_MODALITIES = 4
 
 c_float_p = C.c_void_p  # device pointers travel as integers
@@ -73,6 +74,13 @@ class LateDesc(C.Structure):
                 ("w0", C.c_void_p * MAX_MODALITIES), ("b0", C.c_void_p * MAX_MODALITIES),
                 ("w3", C.c_void_p * MAX_MODALITIES), ("b3", C.c_void_p * MAX_MODALITIES),
                 ("fusion_logits", C.c_void_p)]
+
+
+class UncDesc(C.Structure):
+    _fields_ = [("num_modalities", C.c_int), ("hidden_dim", C.c_int), ("num_classes", C.c_int),
+                ("modality_dim", C.c_int * MAX_MODALITIES)] + [(n, C.c_void_p * MAX_MODALITIES) for n in (
+                    "cls_w0", "cls_b0", "cls_w3", "cls_b3", "unc_w0", "unc_b0", "unc_w3", "unc_b3")] + \
+               [("epsilon", C.c_float)]
 
 
 class HeadDesc(C.Structure):
@@ -134,6 +142,9 @@ PROTOTYPES = {
     "avhot_late_create": (_I, [C.POINTER(LateDesc), C.POINTER(_P), _P]),
     "avhot_head_destroy": (None, [_P]),
     "avhot_head_forward": (_I, [_P, C.POINTER(_P), C.POINTER(_I), _I, _P, _P, _P, _I, _I, _F, _U64, _U64, _U32, _P]),
+    "avhot_unc_create": (_I, [C.POINTER(UncDesc), C.POINTER(_P), _P]),
+    "avhot_unc_forward": (_I, [_P, C.POINTER(_P), C.POINTER(_I), _I, _P, _P, _P, _P, _I, _I, _F, _U64, _U64, _U32, _P]),
+    "avhot_uncertainty_fuse": (_I, [_P, _P, _P, _P, _P, C.c_longlong, _I, _I, _F, _P]),
     "avhot_calibration_accumulate": (_I, [_P, _P, _P, _P, C.c_longlong, _I, _P, _I, _P, _P]),
     "avhot_mc_reduce": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
 }

@@ -8,7 +8,11 @@
 #include "common.cuh"
 
 struct avhot_head {
-  int kind;              // 0 early, 1 late
+  int kind;              // 0 early, 1 late, 2 late with uncertainty
+  // late with uncertainty (hidden_dim D > 0: Linear(d, D)-ReLU-Linear(D, C | 1); D == 0: Linear(d, C | 1))
+  float *uw0t[2][AVHOT_MAX_MODALITIES], *ub0[2][AVHOT_MAX_MODALITIES];   // [0] classifier, [1] uncertainty head
+  float *uw3[2][AVHOT_MAX_MODALITIES], *ub3[2][AVHOT_MAX_MODALITIES];
+  float eps;
   int M, D, C, in_dim;
   int dim[AVHOT_MAX_MODALITIES];
   // early
@@ -311,6 +315,148 @@ calibration_kernel(const float* __restrict__ logits, const float* __restrict__ c
   }
 }
 
+// ---- LateFusionWithUncertainty (src/fusion.py:589-655) + UncertaintyWeightedFusion (src/uncertainty.py:279-318) ------
+// inverse-uncertainty weights of one row: w_m = (mask_m / (u_m + eps)) / (sum + eps)
+__device__ __forceinline__ void unc_weights(const float* u, const float* mask, int M, float eps, float* w) {
+  float sum = 0.f;
+  for (int m = 0; m < M; ++m) { w[m] = (1.f / (u[m] + eps)) * mask[m]; sum += w[m]; }
+  for (int m = 0; m < M; ++m) w[m] = w[m] / (sum + eps);
+}
+__device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // F.softplus defaults
+
+struct UncParams {
+  const float* z[AVHOT_MAX_MODALITIES];
+  int rpc[AVHOT_MAX_MODALITIES], dim[AVHOT_MAX_MODALITIES];
+  const float* mask;
+  float *logits, *per_modality, *weights;     // (R, C); (R, M, C) or NULL; (R, M) or NULL
+  int M, B, T, C, D, present;
+  const float *w0t[2][AVHOT_MAX_MODALITIES], *b0[2][AVHOT_MAX_MODALITIES], *w3[2][AVHOT_MAX_MODALITIES], *b3[2][AVHOT_MAX_MODALITIES];
+  float eps;
+  DropSpec ds;
+};
+
+constexpr int UNC_DMAX = 256;   // largest modality feature dim staged in shared memory
+
+__global__ void __launch_bounds__(HTH) unc_fusion_kernel(const UncParams P) {
+  __shared__ __align__(16) float xs[HRT16][UNC_DMAX];
+  __shared__ __align__(16) float hid[HRT16][HD];
+  __shared__ float lg[HRT16][AVHOT_MAX_MODALITIES][HCMAX];
+  __shared__ float us[HRT16][AVHOT_MAX_MODALITIES];
+  const int n = threadIdx.x, lane = n & 31, warp = n >> 5;
+  const long long n_rows = (long long)P.B * P.T, row0 = (long long)blockIdx.x * HRT16;
+  const int r2 = n >> 4, c2 = n & 15;
+  for (int m = 0; m < P.M; ++m) {
+    const int d = P.dim[m];
+    const bool present = (P.present >> m) & 1;
+    for (int head = 0; head < 2; ++head) {                    // 0: classifier, 1: uncertainty head
+      const uint32_t site_in = AVHOT_SITE_UNC + 4u * m + 2u * head, site_hid = site_in + 1u;
+      __syncthreads();
+      // input dropout (classifiers[m][0] / uncert_heads[m][0]); a modality that is not given is zeros (:629)
+      for (int idx = n; idx < HRT16 * d; idx += HTH) {
+        const int r = idx / d, k = idx % d;
+        const HeadRow hr = head_row(row0, r, n_rows, P.T);
+        float x = present ? __ldg(P.z[m] + (size_t)((long long)hr.b * P.rpc[m] + (P.rpc[m] == 1 ? 0 : hr.t)) * d + k) : 0.f;
+        if (P.ds.thr != 0u) {
+          const Philox4 pw = philox4x32_10((uint32_t)(k >> 2), (uint32_t)(P.ds.clip0 + (uint64_t)hr.b),
+                                           P.ds.t0 + (uint32_t)hr.t, site_in, P.ds.k0, P.ds.k1);
+          x = philox_word(pw, k & 3) >= P.ds.thr ? x * P.ds.scale : 0.f;
+        }
+        xs[r][k] = x;
+      }
+      __syncthreads();
+      const float* src;                                         // the rows the output Linear reads
+      int kdim;
+      if (P.D > 0) {
+        float acc[HRT16];
+        const float b = __ldg(P.b0[head][m] + n);
+#pragma unroll
+        for (int r = 0; r < HRT16; ++r) acc[r] = b;
+        const float* w = P.w0t[head][m] + n;
+        for (int k = 0; k < d; k += 4) {
+          float c[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) c[u] = __ldg(w + (size_t)(k + u) * HD);
+#pragma unroll
+          for (int r = 0; r < HRT16; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(&xs[r][k]);
+            acc[r] = fmaf(c[0], x.x, acc[r]); acc[r] = fmaf(c[1], x.y, acc[r]);
+            acc[r] = fmaf(c[2], x.z, acc[r]); acc[r] = fmaf(c[3], x.w, acc[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < HRT16; ++r) {
+          float v = fmaxf(acc[r], 0.f);
+          if (P.ds.thr != 0u) {
+            const HeadRow hr = head_row(row0, r, n_rows, P.T);
+            const Philox4 pw = philox4x32_10((uint32_t)(n >> 2), (uint32_t)(P.ds.clip0 + (uint64_t)hr.b),
+                                             P.ds.t0 + (uint32_t)hr.t, site_hid, P.ds.k0, P.ds.k1);
+            v = philox_word(pw, n & 3) >= P.ds.thr ? v * P.ds.scale : 0.f;
+          }
+          hid[r][n] = v;
+        }
+        __syncthreads();
+        src = &hid[0][0]; kdim = HD;
+      } else {
+        src = &xs[0][0]; kdim = d;
+      }
+      const int pitch = P.D > 0 ? HD : UNC_DMAX;
+      if (head == 0) {
+        if (c2 < P.C) {
+          const float* wc = P.w3[0][m] + (size_t)c2 * kdim;
+          const float* x = src + (size_t)r2 * pitch;
+          float a = 0.f;
+          for (int k = 0; k < kdim; k += 4) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(wc + k)), v = *reinterpret_cast<const float4*>(x + k);
+            a = fmaf(u.x, v.x, a); a = fmaf(u.y, v.y, a); a = fmaf(u.z, v.z, a); a = fmaf(u.w, v.w, a);
+          }
+          lg[r2][m][c2] = a + __ldg(P.b3[0][m] + c2);
+        }
+      } else {
+        for (int r = warp; r < HRT16; r += HTH / 32) {          // warp = row: dot product with the 1-row weight
+          const float* x = src + (size_t)r * pitch;
+          float a = 0.f;
+          for (int k = lane; k < kdim; k += 32) a = fmaf(__ldg(P.w3[1][m] + k), x[k], a);
+          a = warp_sum(a);
+          if (lane == 0) us[r][m] = softplus_ref(a + __ldg(P.b3[1][m]));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (c2 < P.C && row0 + r2 < n_rows) {
+    const HeadRow hr = head_row(row0, r2, n_rows, P.T);
+    float mk[AVHOT_MAX_MODALITIES], w[AVHOT_MAX_MODALITIES];
+    for (int m = 0; m < P.M; ++m) mk[m] = __ldg(P.mask + (size_t)hr.b * P.M + m);
+    unc_weights(us[r2], mk, P.M, P.eps, w);
+    float fused = 0.f;
+    for (int m = 0; m < P.M; ++m) {
+      fused = fmaf(w[m], lg[r2][m][c2], fused);
+      if (P.per_modality) P.per_modality[((size_t)(row0 + r2) * P.M + m) * P.C + c2] = lg[r2][m][c2];
+    }
+    P.logits[(size_t)(row0 + r2) * P.C + c2] = fused;
+    if (P.weights && c2 == 0)
+      for (int m = 0; m < P.M; ++m) P.weights[(size_t)(row0 + r2) * P.M + m] = w[m];
+  }
+}
+
+// UncertaintyWeightedFusion.forward on its own: logits (R, M, C), uncert (R, M), mask (R, M) -> fused (R, C), weights (R, M)
+__global__ void unc_fuse_kernel(const float* __restrict__ logits, const float* __restrict__ uncert,
+                                const float* __restrict__ mask, float* __restrict__ fused, float* __restrict__ weights,
+                                long long R, int M, int C, float eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  float u[AVHOT_MAX_MODALITIES], mk[AVHOT_MAX_MODALITIES], w[AVHOT_MAX_MODALITIES];
+  for (int m = 0; m < M; ++m) { u[m] = uncert[r * M + m]; mk[m] = mask[r * M + m]; }
+  unc_weights(u, mk, M, eps, w);
+  float a = 0.f;
+  for (int m = 0; m < M; ++m) a = fmaf(w[m], logits[(r * M + m) * C + c], a);
+  fused[i] = a;
+  if (c == 0)
+    for (int m = 0; m < M; ++m) weights[r * M + m] = w[m];
+}
+
 static size_t alh(size_t n_floats) { return (n_floats * sizeof(float) + 255) & ~(size_t)255; }
 
 }  // namespace avhot
@@ -412,6 +558,110 @@ extern "C" int avhot_late_create(const avhot_late_desc* d, avhot_head_t* out, av
     return AVHOT_ERR_INVALID;
   }
   *out = h;
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_unc_create(const avhot_unc_desc* d, avhot_head_t* out, avhot_stream_t stream) {
+  AVHOT_REQUIRE(d && out, AVHOT_ERR_INVALID, "unc_create: null argument");
+  AVHOT_REQUIRE(d->num_modalities >= 1 && d->num_modalities <= AVHOT_MAX_MODALITIES && (d->hidden_dim == HD || d->hidden_dim == 0) &&
+                    d->num_classes >= 1 && d->num_classes <= HCMAX, AVHOT_ERR_UNSUPPORTED,
+                "unc_create: this build needs 1..4 modalities, hidden_dim 0 or 256, <= 16 classes (got M=%d D=%d C=%d)",
+                d->num_modalities, d->hidden_dim, d->num_classes);
+  cudaStream_t s = as_stream(stream);
+  avhot_head* h = new avhot_head();
+  memset(h, 0, sizeof(*h));
+  h->kind = 2; h->M = d->num_modalities; h->D = d->hidden_dim; h->C = d->num_classes; h->eps = d->epsilon;
+  const int D = h->D;
+  size_t total = 0;
+  for (int m = 0; m < h->M; ++m) {
+    const int dm = d->modality_dim[m];
+    if (dm <= 0 || (dm & 3) || dm > UNC_DMAX) {
+      delete h;
+      set_error("unc_create: modality_dim[%d]=%d must be a positive multiple of 4, <= %d", m, dm, UNC_DMAX);
+      return AVHOT_ERR_UNSUPPORTED;
+    }
+    h->dim[m] = dm;
+    for (int head = 0; head < 2; ++head) {
+      const int outs = head == 0 ? h->C : 1;
+      total += D > 0 ? alh((size_t)dm * D) + alh(D) + alh((size_t)outs * D) + alh(outs) : alh((size_t)outs * dm) + alh(outs);
+    }
+  }
+  if (cudaMalloc(&h->arena, total) != cudaSuccess) {
+    delete h;
+    set_error("unc_create: cudaMalloc(%zu) failed", total);
+    return AVHOT_ERR_CUDA;
+  }
+  char* p = reinterpret_cast<char*>(h->arena);
+  auto take = [&](size_t n) { float* r = reinterpret_cast<float*>(p); p += alh(n); return r; };
+  bool ok = true;
+  for (int m = 0; m < h->M && ok; ++m)
+    for (int head = 0; head < 2 && ok; ++head) {
+      const int outs = head == 0 ? h->C : 1, dm = h->dim[m];
+      const float* w_in = head == 0 ? d->cls_w0[m] : d->unc_w0[m];
+      const float* b_in = head == 0 ? d->cls_b0[m] : d->unc_b0[m];
+      const float* w_out = head == 0 ? d->cls_w3[m] : d->unc_w3[m];
+      const float* b_out = head == 0 ? d->cls_b3[m] : d->unc_b3[m];
+      if (D > 0) {
+        h->uw0t[head][m] = take((size_t)dm * D); h->ub0[head][m] = take(D);
+        h->uw3[head][m] = take((size_t)outs * D); h->ub3[head][m] = take(outs);
+        ok = transpose_to(h->uw0t[head][m], w_in, D, dm, s) && copy_to(h->ub0[head][m], b_in, D, s) &&
+             copy_to(h->uw3[head][m], w_out, (size_t)outs * D, s) && copy_to(h->ub3[head][m], b_out, outs, s);
+      } else {                                                  // a single Linear(d -> outs): w3 / b3 slots
+        h->uw3[head][m] = take((size_t)outs * dm); h->ub3[head][m] = take(outs);
+        ok = copy_to(h->uw3[head][m], w_out, (size_t)outs * dm, s) && copy_to(h->ub3[head][m], b_out, outs, s);
+      }
+    }
+  if (!ok) {
+    cudaFree(h->arena);
+    delete h;
+    set_error("unc_create: missing tensor or device copy failure");
+    return AVHOT_ERR_INVALID;
+  }
+  *out = h;
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_unc_forward(avhot_head_t h, const float* const* z_host_array, const int* z_rows_per_clip_host,
+                                 int present_mask, const float* mask, float* logits, float* per_modality_logits,
+                                 float* fusion_weights, int B, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                                 avhot_stream_t stream) {
+  AVHOT_REQUIRE(h && h->kind == 2 && z_host_array && z_rows_per_clip_host && logits && mask && B >= 0 && T >= 1,
+                AVHOT_ERR_INVALID, "unc_forward: bad arguments (modality_mask is required, src/fusion.py:622)");
+  AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "unc_forward: dropout p=%g outside [0, 1)", (double)p);
+  if (B == 0) return AVHOT_OK;
+  const long long rows = (long long)B * T, grid = (rows + HRT16 - 1) / HRT16;
+  AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "unc_forward: B*T too large for one call");
+  UncParams P;
+  memset(&P, 0, sizeof(P));
+  for (int m = 0; m < h->M; ++m) {
+    const bool present = (present_mask >> m) & 1;
+    AVHOT_REQUIRE(!present || (z_host_array[m] && (z_rows_per_clip_host[m] == 1 || z_rows_per_clip_host[m] == T)),
+                  AVHOT_ERR_INVALID, "unc_forward: z[%d] is NULL or z_rows_per_clip is not 1 / T", m);
+    P.z[m] = z_host_array[m]; P.rpc[m] = present ? z_rows_per_clip_host[m] : 1; P.dim[m] = h->dim[m];
+    for (int head = 0; head < 2; ++head) {
+      P.w0t[head][m] = h->uw0t[head][m]; P.b0[head][m] = h->ub0[head][m];
+      P.w3[head][m] = h->uw3[head][m]; P.b3[head][m] = h->ub3[head][m];
+    }
+  }
+  P.mask = mask; P.logits = logits; P.per_modality = per_modality_logits; P.weights = fusion_weights;
+  P.M = h->M; P.B = B; P.T = T; P.C = h->C; P.D = h->D; P.present = present_mask; P.eps = h->eps;
+  P.ds = make_drop(p, seed, clip0, t0);
+  ProfScope prof("uncertainty_fusion", as_stream(stream));
+  unc_fusion_kernel<<<(unsigned)grid, HTH, 0, as_stream(stream)>>>(P);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_uncertainty_fuse(const float* logits, const float* uncert, const float* mask, float* fused,
+                                      float* weights, long long R, int M, int C, float eps, avhot_stream_t stream) {
+  AVHOT_REQUIRE(logits && uncert && mask && fused && weights && R >= 0 && M >= 1 && M <= AVHOT_MAX_MODALITIES && C >= 1,
+                AVHOT_ERR_INVALID, "uncertainty_fuse: bad arguments (1..4 modalities)");
+  if (R == 0) return AVHOT_OK;
+  const long long n = R * C;
+  AVHOT_REQUIRE((n + 255) / 256 <= 0x7fffffffLL, AVHOT_ERR_INVALID, "uncertainty_fuse: too many rows");
+  ProfScope prof("uncertainty_fuse", as_stream(stream));
+  unc_fuse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(logits, uncert, mask, fused, weights, R, M, C, eps);
+  AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }
 

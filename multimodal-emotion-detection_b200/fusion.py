@@ -336,6 +336,110 @@ class LateFusion(_HeadBase):
         return logits[:, 0, :], {n: per[i, :, 0, :] for i, n in enumerate(self.modality_names)}
 
 
+class LateFusionWithUncertainty(nn.Module):
+    """src/fusion.py:589-655 (build_fusion_model('uncertainty')): per modality a classifier and a scalar-uncertainty
+    head (softplus), fused by inverse uncertainty (UncertaintyWeightedFusion).  forward(encoded_features,
+    modality_mask) -> (fused_logits, {"per_modality_logits": (B, M, C), "fusion_weights": (B, M)})."""
+
+    def __init__(self, modality_dims: Dict[str, int], num_classes: int, hidden_dim: int = 0, num_heads: int = 0,
+                 dropout: float = 0.0, epsilon: float = 1e-6):
+        super().__init__()
+        from .uncertainty import UncertaintyWeightedFusion
+        self.modalities = list(modality_dims.keys())
+        self.modality_dims = modality_dims
+        self.num_classes = num_classes
+        self.hidden_dim = hidden_dim if hidden_dim and hidden_dim > 0 else 0
+        self.classifiers = nn.ModuleDict()
+        self.uncert_heads = nn.ModuleDict()
+        for m, d in modality_dims.items():                                               # :611-627
+            if self.hidden_dim:
+                self.classifiers[m] = nn.Sequential(nn.Dropout(dropout), nn.Linear(d, hidden_dim), nn.ReLU(inplace=True),
+                                                    nn.Dropout(dropout), nn.Linear(hidden_dim, num_classes))
+                self.uncert_heads[m] = nn.Sequential(nn.Dropout(dropout), nn.Linear(d, hidden_dim), nn.ReLU(inplace=True),
+                                                     nn.Dropout(dropout), nn.Linear(hidden_dim, 1))
+            else:
+                self.classifiers[m] = nn.Sequential(nn.Dropout(dropout), nn.Linear(d, num_classes))
+                self.uncert_heads[m] = nn.Sequential(nn.Dropout(dropout), nn.Linear(d, 1))
+        self.fuser = UncertaintyWeightedFusion(epsilon=epsilon)
+        self._handle = Handle("avhot_head_destroy")
+
+    _drop_p = _HeadBase._drop_p
+
+    def _get_handle(self, dev):
+        ps = [p for p in self.parameters()]
+
+        def create():
+            if len(self.modalities) > _lib.MAX_MODALITIES:
+                raise ValueError(f"at most {_lib.MAX_MODALITIES} modalities")
+            keep = []
+
+            def dp(t):
+                t = _lib.f32c(t.detach())
+                _lib.require_cuda(t)
+                keep.append(t)
+                return t.data_ptr()
+
+            d = _lib.UncDesc()
+            d.num_modalities, d.hidden_dim, d.num_classes = len(self.modalities), self.hidden_dim, self.num_classes
+            d.epsilon = float(self.fuser.epsilon)
+            for i, n in enumerate(self.modalities):
+                d.modality_dim[i] = self.modality_dims[n]
+                c, u = self.classifiers[n], self.uncert_heads[n]
+                if self.hidden_dim:
+                    d.cls_w0[i], d.cls_b0[i], d.cls_w3[i], d.cls_b3[i] = dp(c[1].weight), dp(c[1].bias), dp(c[4].weight), dp(c[4].bias)
+                    d.unc_w0[i], d.unc_b0[i], d.unc_w3[i], d.unc_b3[i] = dp(u[1].weight), dp(u[1].bias), dp(u[4].weight), dp(u[4].bias)
+                else:
+                    d.cls_w3[i], d.cls_b3[i] = dp(c[1].weight), dp(c[1].bias)
+                    d.unc_w3[i], d.unc_b3[i] = dp(u[1].weight), dp(u[1].bias)
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_unc_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
+                       "LateFusionWithUncertainty")
+            torch.cuda.current_stream(dev).synchronize()
+            return out.value
+
+        return self._handle.get(ps, create)
+
+    @torch.no_grad()
+    def run(self, zs, rows_per_clip, mask, B: int, passes: int, p: float, seed: int, clip0: int, t0: int):
+        dev = mask.device
+        M = len(zs)
+        present = sum(1 << m for m in range(M) if zs[m] is not None)
+        logits = torch.empty(B, passes, self.num_classes, device=dev, dtype=torch.float32)
+        per = torch.empty(B, passes, M, self.num_classes, device=dev, dtype=torch.float32)
+        fw = torch.empty(B, passes, M, device=dev, dtype=torch.float32)
+        if B > 0:
+            arr = (C.c_void_p * M)(*[None if z is None else z.data_ptr() for z in zs])
+            rpc = (C.c_int * M)(*rows_per_clip)
+            with torch.cuda.device(dev):
+                h = self._get_handle(dev)
+                _lib.check(_lib.load().avhot_unc_forward(h, arr, rpc, present, _lib.ptr(mask), _lib.ptr(logits),
+                                                         _lib.ptr(per), _lib.ptr(fw), B, passes, float(p), seed, clip0,
+                                                         t0, _lib.stream_ptr(dev)), "LateFusionWithUncertainty.forward")
+        return logits, per, fw
+
+    def forward(self, encoded_features: Dict[str, torch.Tensor], modality_mask: torch.Tensor):
+        assert modality_mask is not None, "modality_mask (B,M) is required."           # :622
+        dev = _lib.require_cuda(modality_mask, *encoded_features.values())
+        _lib.check_device(dev)
+        B = modality_mask.size(0)
+        mask_f = _lib.f32c(modality_mask)
+        if mask_f.shape != (B, len(self.modalities)):
+            raise ValueError(f"modality_mask must be [B, {len(self.modalities)}]")
+        zs = []
+        for m in self.modalities:
+            x = encoded_features.get(m)
+            if x is not None:
+                if x.size(0) != B:
+                    raise ValueError(f"Batch mismatch for modality '{m}': {x.size(0)} vs {B}")   # :631
+                if x.dim() != 2 or x.size(1) != self.modality_dims[m]:
+                    raise ValueError(f"Modality '{m}' must be [B, {self.modality_dims[m]}], got {tuple(x.shape)}")
+                x = _lib.f32c(x)
+            zs.append(x)
+        seed, t, clip0 = _rng.current()
+        logits, per, fw = self.run(zs, [1] * len(zs), mask_f, B, 1, self._drop_p(), seed, clip0, t)
+        return logits[:, 0, :], {"per_modality_logits": per[:, 0], "fusion_weights": fw[:, 0]}
+
+
 class ConcatHead(nn.Sequential):
     """The live fusion_head of MultimodalFusionModule: Linear -> ReLU -> Linear on the concatenated encoder
     outputs (src/train.py:81-85, :153-164).  State-dict keys 0.weight, 0.bias, 2.weight, 2.bias."""
@@ -389,10 +493,12 @@ class ConcatHead(nn.Sequential):
 
 
 def build_fusion_model(fusion_type: str, modality_dims: Dict[str, int], num_classes: int, **kwargs) -> nn.Module:
-    """src/fusion.py:659-702.  'hybrid' is the cross-modal path; 'early' / 'late' are SURVEY.md 8(f) rows;
-    'uncertainty' (LateFusionWithUncertainty) exists in the reference and is not built here."""
-    if fusion_type == "uncertainty":
-        raise ValueError("fusion type 'uncertainty' exists in the reference but is not built in this library")
+    """src/fusion.py:659-702.  'hybrid' is the cross-modal path; 'early' / 'late' / 'uncertainty'
+    (LateFusionWithUncertainty) are SURVEY.md 8(f) rows."""
+    if fusion_type in {"uncertainty"}:                                                   # :676-686
+        return LateFusionWithUncertainty(modality_dims=modality_dims, num_classes=num_classes,
+                                         hidden_dim=kwargs.get("hidden_dim", 0), num_heads=kwargs.get("num_heads", 0),
+                                         dropout=kwargs.get("dropout", 0.0), epsilon=kwargs.get("epsilon", 1e-6))
     fusion_classes = {"early": EarlyFusion, "late": LateFusion, "hybrid": HybridFusion}
     if fusion_type not in fusion_classes:
         raise ValueError(f"Unknown fusion type: {fusion_type}")                          # :696

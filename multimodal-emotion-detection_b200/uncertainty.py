@@ -77,6 +77,37 @@ class MCDropoutUncertainty(nn.Module):
         return mean, unc
 
 
+class UncertaintyWeightedFusion(nn.Module):
+    """src/uncertainty.py:279-318: fuse per-modality logits weighted by inverse uncertainty,
+    w_m = (mask_m / (u_m + eps)) / (sum_m + eps).  One small kernel (avhot_uncertainty_fuse)."""
+
+    def __init__(self, epsilon: float = 1e-6):
+        super().__init__()
+        self.epsilon = epsilon
+
+    def forward(self, modality_predictions: Dict[str, torch.Tensor], modality_uncertainties: Dict[str, torch.Tensor],
+                modality_mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        assert isinstance(modality_predictions, dict) and isinstance(modality_uncertainties, dict)      # :301
+        modalities = list(modality_predictions.keys())
+        logits = _lib.f32c(torch.stack([modality_predictions[m] for m in modalities], dim=1))           # (B, M, C)
+        dev = _lib.require_cuda(logits)
+        _lib.check_device(dev)
+        uncert = _lib.f32c(torch.stack([modality_uncertainties[m] for m in modalities], dim=1).to(dev))
+        mask = _lib.f32c(modality_mask.to(device=dev))
+        B, M, Cn = logits.shape
+        if uncert.shape != (B, M) or mask.shape != (B, M):
+            raise ValueError(f"uncertainties and mask must be (B, {M})")
+        fused = torch.empty(B, Cn, device=dev, dtype=torch.float32)
+        weights = torch.empty(B, M, device=dev, dtype=torch.float32)
+        if B > 0:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().avhot_uncertainty_fuse(_lib.ptr(logits), _lib.ptr(uncert), _lib.ptr(mask),
+                                                              _lib.ptr(fused), _lib.ptr(weights), B, M, Cn,
+                                                              float(self.epsilon), _lib.stream_ptr(dev)),
+                           "UncertaintyWeightedFusion")
+        return fused, weights
+
+
 # ---- SURVEY.md 8(f) row 3: calibration metrics (src/uncertainty.py:88-183, :471-544) on the GPU ---------------------
 def calibration_accumulate(acc: torch.Tensor, labels: torch.Tensor, num_bins: int, logits: torch.Tensor = None,
                            confidences: torch.Tensor = None, predictions: torch.Tensor = None) -> torch.Tensor:

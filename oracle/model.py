@@ -338,6 +338,35 @@ def late_fusion(feats: Dict[str, torch.Tensor], mask, sd, prefix="fusion_model."
     return (w.unsqueeze(-1) * stacked).sum(dim=1), per
 
 
+def late_fusion_with_uncertainty(feats: Dict[str, torch.Tensor], mask, sd, prefix="unc_model.",
+                                 modalities: Sequence[str] = ("audio", "video"), ctx: Optional[DropCtx] = None,
+                                 eps: float = 1e-6):
+    """LateFusionWithUncertainty.forward (hidden_dim > 0).  src/fusion.py:629-641: per modality
+    logits = classifiers[m](x) and u = softplus(uncert_heads[m](x)) with each head = Dropout, Linear, ReLU, Dropout,
+    Linear (:613-620); a modality that is not given is zeros (:629).  UncertaintyWeightedFusion
+    (src/uncertainty.py:303-317): w = mask / (u + eps), normalised by (sum + eps).
+    Returns (fused (B, C), per-modality logits (B, M, C), weights (B, M))."""
+    p = ctx.p_fusion if ctx is not None else 0.0
+    B = torch.as_tensor(mask).shape[0]
+    per, us = [], []
+    for i, m in enumerate(modalities):
+        x0 = feats[m] if m in feats else torch.zeros(B, sd[f"{prefix}classifiers.{m}.1.weight"].shape[1])
+        outs = []
+        for j, head in enumerate(("classifiers", "uncert_heads")):
+            x = ctx.apply(x0, px.SITE_UNC + 4 * i + 2 * j, p) if ctx is not None else x0
+            h = torch.relu(_lin(x, sd, f"{prefix}{head}.{m}.1"))
+            if ctx is not None:
+                h = ctx.apply(h, px.SITE_UNC + 4 * i + 2 * j + 1, p)
+            outs.append(_lin(h, sd, f"{prefix}{head}.{m}.4"))
+        per.append(outs[0])
+        us.append(torch.nn.functional.softplus(outs[1]).squeeze(-1))
+    logits = torch.stack(per, dim=1)
+    uncert = torch.stack(us, dim=1)
+    inv_w = (1.0 / (uncert + eps)) * torch.as_tensor(mask).to(logits.dtype)
+    w = inv_w / (inv_w.sum(dim=1, keepdim=True) + eps)
+    return (w.unsqueeze(-1) * logits).sum(dim=1), logits, w
+
+
 def calibration_metrics(logits, labels, num_bins=15):
     """compute_calibration_metrics after the logits are collected (src/uncertainty.py:512-544) with
     CalibrationMetrics._bin_stats / ECE / MCE (:98-183): returns dict(ece, mce, nll, accuracy)."""

@@ -34,6 +34,8 @@ the per-clip mask tensor):
     SITE_ATTN + i    16+i fusion_model.attn_layers[i].attn_dropout (heads, Tq, Tk)
                                                                   src/attention.py:51,130
     SITE_LATE + i    32+i LateFusion classifiers[i].2  (hidden,)   src/fusion.py:184
+    SITE_UNC + 4i+j  48+  LateFusionWithUncertainty modality i: j = 0 classifiers[i][0] (dim,), 1 classifiers[i][3]
+                          (hidden,), 2 uncert_heads[i][0] (dim,), 3 uncert_heads[i][3] (hidden,)   src/fusion.py:613-620
 Synthetic-data streams use c3 >= 0x100 (see oracle/synth.py).
 """
 from __future__ import annotations
@@ -56,6 +58,7 @@ SITE_CNN0 = 6
 SITE_CNN1 = 7
 SITE_ATTN = 16
 SITE_LATE = 32
+SITE_UNC = 48
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

@@ -183,6 +183,13 @@ def model_shapes(audio_dim=104, frame_dim=FRAME_DIM, enc_hidden=256, out_dim=128
         s[f"late_model.classifiers.{m}.3.weight"] = ((num_classes, D), "u", D)
         s[f"late_model.classifiers.{m}.3.bias"] = ((num_classes,), "u", D)
     s["late_model.fusion_logits"] = ((len(modalities),), "lnb", 0)
+    # LateFusionWithUncertainty (src/fusion.py:611-620) with hidden_dim = D
+    for m in modalities:
+        for head, outs in (("classifiers", num_classes), ("uncert_heads", 1)):
+            s[f"unc_model.{head}.{m}.1.weight"] = ((D, out_dim), "u", out_dim)
+            s[f"unc_model.{head}.{m}.1.bias"] = ((D,), "u", out_dim)
+            s[f"unc_model.{head}.{m}.4.weight"] = ((outs, D), "u", D)
+            s[f"unc_model.{head}.{m}.4.bias"] = ((outs,), "u", D)
     s["fusion_head.0.weight"] = ((D, cat), "u", cat)
     s["fusion_head.0.bias"] = ((D,), "u", cat)
     s["fusion_head.2.weight"] = ((num_classes, D), "u", D)

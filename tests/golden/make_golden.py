@@ -258,6 +258,41 @@ def main():
             ora = om.sequence_encoder_cnn(feats, sd, ctx=om.DropCtx(SEED, t, CLIP_IDS))
             rec(f"cnn.z_pass{t}", ref_z, ora)
 
+    # LateFusionWithUncertainty (src/fusion.py:589-655) behind build_fusion_model('uncertainty'): eval and one stochastic
+    # pass with the spec masks injected into its eight nn.Dropout modules
+    unc = ref_fusion.build_fusion_model("uncertainty", {"audio": 128, "video": 128}, 8, hidden_dim=256, num_heads=4, dropout=0.3)
+    unc.load_state_dict({k[len("unc_model."):]: v for k, v in sd.items() if k.startswith("unc_model.")}, strict=True)
+    unc.eval()
+    zz = {"audio": z_a, "video": z_v}
+    with torch.inference_mode():
+        for mname in ("ones", "mixed"):
+            lg, info = unc(zz, masks[mname].clone())
+            olg, oper, ow = om.late_fusion_with_uncertainty(zz, masks[mname], sd)
+            rec(f"unc.logits_{mname}", lg, olg)
+            rec(f"unc.per_{mname}", info["per_modality_logits"], oper)
+            rec(f"unc.weights_{mname}", info["fusion_weights"], ow)
+        lg, info = unc({"video": z_v}, masks["mixed"].clone())                 # audio not given: zeros (:629)
+        olg, oper, ow = om.late_fusion_with_uncertainty({"video": z_v}, masks["mixed"], sd)
+        rec("unc.logits_video_only", lg, olg)
+    sites = {}
+    for i, m in enumerate(MODALITIES):
+        for j, head in enumerate(("classifiers", "uncert_heads")):
+            sites[f"{head}.{m}.0"] = px.SITE_UNC + 4 * i + 2 * j
+            sites[f"{head}.{m}.3"] = px.SITE_UNC + 4 * i + 2 * j + 1
+    T_UNC = 2
+    for name, mod in unc.named_modules():
+        if isinstance(mod, nn.Dropout):
+            def fwd(x, mod=mod, site=sites[name]):
+                n = int(np.prod(x.shape[1:]))
+                keep = px.dropout_keep(n, CLIP_IDS, T_UNC, site, mod.p, SEED).reshape(x.shape)
+                return x * (torch.from_numpy(keep).float() * float(px.keep_scale(mod.p)))
+            mod.forward = fwd
+    with torch.inference_mode():
+        lg, info = unc(zz, masks["mixed"].clone())
+        olg, oper, ow = om.late_fusion_with_uncertainty(zz, masks["mixed"], sd, ctx=om.DropCtx(SEED, T_UNC, CLIP_IDS))
+        rec("unc.logits_drop", lg, olg)
+        rec("unc.weights_drop", info["fusion_weights"], ow)
+
     # calibration metrics (src/uncertainty.py:88-183, :512-544) on seeded random logits / labels
     g = torch.Generator().manual_seed(5)
     cal_logits = torch.randn(4000, 8, generator=g) * 2.0

@@ -542,3 +542,51 @@ def test_cnn_sequence_encoder_vs_reference_golden(pkg, dev, world, golden):
     enc.train()
     with pytest.raises(ValueError):
         enc(feats)                                   # training-mode BatchNorm is not built
+
+
+def test_late_fusion_with_uncertainty_vs_reference_golden(pkg, dev, world, golden):
+    """build_fusion_model('uncertainty') = LateFusionWithUncertainty (src/fusion.py:589-655) and
+    UncertaintyWeightedFusion (src/uncertainty.py:279-318)."""
+    dims = {"audio": 128, "video": 128}
+    mod = pkg.build_fusion_model("uncertainty", dims, 8, hidden_dim=256, num_heads=4, dropout=0.3)
+    mod.load_state_dict({k[len("unc_model."):]: v for k, v in world["sd"].items() if k.startswith("unc_model.")}, strict=True)
+    mod = mod.to(dev).eval()
+    z = {"audio": torch.from_numpy(golden["z_audio"]).to(dev), "video": torch.from_numpy(golden["z_video"]).to(dev)}
+    masks = _masks(world)
+    for name in ("ones", "mixed"):
+        lg, info = mod(z, torch.from_numpy(masks[name]).to(dev))
+        assert rel_err(lg.cpu().numpy(), golden[f"unc.logits_{name}"]) <= REL
+        assert rel_err(info["per_modality_logits"].cpu().numpy(), golden[f"unc.per_{name}"]) <= REL
+        assert rel_err(info["fusion_weights"].cpu().numpy(), golden[f"unc.weights_{name}"]) <= REL
+    lg, _ = mod({"video": z["video"]}, torch.from_numpy(masks["mixed"]).to(dev))
+    assert rel_err(lg.cpu().numpy(), golden["unc.logits_video_only"]) <= REL
+    # one stochastic pass: eight dropout sites, clip ids of the golden file are not contiguous
+    mod.train()
+    rows, wrows = [], []
+    mk = torch.from_numpy(masks["mixed"]).to(dev)
+    for b, g in enumerate(world["ids"]):
+        with pkg.philox_context(SEED, 2, int(g)):
+            lg, info = mod({k: v[b:b + 1] for k, v in z.items()}, mk[b:b + 1])
+        rows.append(lg)
+        wrows.append(info["fusion_weights"])
+    assert rel_err(torch.cat(rows).cpu().numpy(), golden["unc.logits_drop"]) <= REL
+    assert rel_err(torch.cat(wrows).cpu().numpy(), golden["unc.weights_drop"]) <= REL
+    # the fuser on its own, and the hidden_dim = 0 variant (a single Linear per head) against torch arithmetic
+    fuser = pkg.UncertaintyWeightedFusion(epsilon=1e-6)
+    per = torch.from_numpy(golden["unc.per_mixed"]).to(dev)
+    u = torch.rand(per.shape[0], 2, device=dev) + 0.1
+    fused, w = fuser({"audio": per[:, 0], "video": per[:, 1]}, {"audio": u[:, 0], "video": u[:, 1]}, mk)
+    inv = (1.0 / (u + 1e-6)) * mk
+    want_w = inv / (inv.sum(1, keepdim=True) + 1e-6)
+    assert rel_err(w.cpu().numpy(), want_w.cpu().numpy()) <= 1e-6
+    assert rel_err(fused.cpu().numpy(), (want_w.unsqueeze(-1) * per).sum(1).cpu().numpy()) <= 1e-6
+    lin = pkg.LateFusionWithUncertainty(dims, 8).to(dev).eval()                      # hidden_dim = 0 (the ctor default)
+    lg, info = lin(z, mk)
+    logits = torch.stack([z[m] @ lin.classifiers[m][1].weight.T + lin.classifiers[m][1].bias for m in dims], dim=1)
+    uu = torch.stack([torch.nn.functional.softplus(z[m] @ lin.uncert_heads[m][1].weight.T + lin.uncert_heads[m][1].bias).squeeze(-1)
+                      for m in dims], dim=1)
+    inv = (1.0 / (uu + 1e-6)) * mk
+    ww = inv / (inv.sum(1, keepdim=True) + 1e-6)
+    assert rel_err(lg.cpu().numpy(), (ww.unsqueeze(-1) * logits).sum(1).detach().cpu().numpy()) <= REL
+    with pytest.raises(AssertionError):
+        mod(z, None)

@@ -88,6 +88,22 @@ def test_cnn_sequence_encoder(golden):
         np.testing.assert_allclose(z.numpy(), golden[f"cnn.z_pass{t}"], rtol=1e-4, atol=1e-4)
 
 
+def test_late_fusion_with_uncertainty(golden):
+    """LateFusionWithUncertainty + UncertaintyWeightedFusion restatement vs the reference."""
+    ids, seed, sd, feats, frames, masks = _inputs(golden)
+    z = {"audio": torch.from_numpy(golden["z_audio"]), "video": torch.from_numpy(golden["z_video"])}
+    for name in ("ones", "mixed"):
+        lg, per, w = om.late_fusion_with_uncertainty(z, masks[name], sd)
+        np.testing.assert_allclose(lg.numpy(), golden[f"unc.logits_{name}"], **TOL)
+        np.testing.assert_allclose(per.numpy(), golden[f"unc.per_{name}"], **TOL)
+        np.testing.assert_allclose(w.numpy(), golden[f"unc.weights_{name}"], **TOL)
+    lg, _, _ = om.late_fusion_with_uncertainty({"video": z["video"]}, masks["mixed"], sd)
+    np.testing.assert_allclose(lg.numpy(), golden["unc.logits_video_only"], **TOL)
+    lg, _, w = om.late_fusion_with_uncertainty(z, masks["mixed"], sd, ctx=om.DropCtx(seed, 2, ids))
+    np.testing.assert_allclose(lg.numpy(), golden["unc.logits_drop"], **TOL)
+    np.testing.assert_allclose(w.numpy(), golden["unc.weights_drop"], **TOL)
+
+
 def test_cross_modal_attention_general_shapes(golden):
     sd = {k[len("xattn."):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("xattn.att.")}
     q, kv = torch.from_numpy(golden["xattn.q"]), torch.from_numpy(golden["xattn.kv"])
