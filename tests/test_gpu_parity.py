@@ -590,3 +590,30 @@ def test_late_fusion_with_uncertainty_vs_reference_golden(pkg, dev, world, golde
     assert rel_err(lg.cpu().numpy(), (ww.unsqueeze(-1) * logits).sum(1).detach().cpu().numpy()) <= REL
     with pytest.raises(AssertionError):
         mod(z, None)
+
+
+def test_split_reader_feeds_the_path(pkg, dev, world, tmp_path):
+    """the .npy split format (src/data.py:51-84) read through pinned buffers, batches in the
+    reference's (features, labels, mask) form, consumed by AVHotPath and compute_calibration_metrics."""
+    n = 6
+    audio = world["wave"][:n].reshape(n, -1, 1)                           # (N, 48000, 1) as load_raw_audio saves it
+    video = world["frames_u8"][:n]
+    labels = np.arange(n) % 8
+    d = {"audio": audio, "video": video, "labels": labels}
+    pkg.save_splits_to_disk(d, d, d, str(tmp_path))
+    m = make_model(pkg, dev, world)
+    want = m({"audio": torch.from_numpy(world["wave"][:n]).to(dev), "video": torch.from_numpy(video).to(dev)})
+    got, labs = [], []
+    for feats, lab, mask in pkg.SplitReader(str(tmp_path), ["audio", "video"], "val", batch_size=4, device=dev):
+        assert feats["video"].dtype == torch.uint8 and feats["audio"].shape[1:] == (48000, 1) and (mask == 1).all()
+        got.append(m(feats, mask))
+        labs.append(lab)
+    assert (torch.cat(got) == want).all() and (torch.cat(labs).cpu().numpy() == labels).all()
+    tr = pkg.SplitReader(str(tmp_path), ["audio", "video"], "train", batch_size=4, modality_dropout=0.5, device=dev)
+    masks = torch.cat([mk for _, _, mk in tr]).cpu().numpy()
+    assert (masks == px.modality_mask(np.arange(n, dtype=np.uint64), 2, 0.5, pkg._rng.DEFAULT_SEED)).all()
+    cal = pkg.compute_calibration_metrics(m, pkg.SplitReader(str(tmp_path), ["audio", "video"], "test", batch_size=4, device=dev),
+                                          device=dev, num_bins=15)
+    ref = om.calibration_metrics(want.cpu(), torch.from_numpy(labels), 15)
+    for k in ("ece", "mce", "nll", "accuracy"):
+        assert abs(cal[k] - ref[k]) <= 1e-5, k

@@ -106,3 +106,24 @@ def test_shard_ranges():
             assert sum(c) == n and max(c) - min(c) <= 1
     with pytest.raises(ValueError):
         par.shard_range(10, 2, 2)
+
+
+def test_split_format_round_trip(tmp_path):
+    """The reference's on-disk split format (src/dataprocessing.py:450-490 writes it, src/data.py:51-84 reads it)."""
+    rng = np.random.default_rng(0)
+    def split(n):
+        return {"audio": rng.normal(size=(n, 100, 1)).astype(np.float32),
+                "video": rng.integers(0, 256, size=(n, 2, 16), dtype=np.uint8), "labels": rng.integers(0, 8, size=n)}
+    tr, va, te = split(7), split(3), split(5)
+    pkg.save_splits_to_disk(tr, va, te, str(tmp_path))
+    for name, d in (("train", tr), ("val", va), ("test", te)):
+        for k in ("audio", "video", "labels"):
+            assert (np.load(tmp_path / name / f"{k}.npy") == d[k]).all()
+    rd = pkg.SplitReader(str(tmp_path), ["audio", "video"], split="test", batch_size=2, modality_dropout=0.3, device="cpu")
+    assert len(rd) == 3 and rd.modality_dropout == 0.0                    # dropout on the train split only (src/data.py:46)
+    with pytest.raises(RuntimeError):
+        next(iter(rd))                                                    # no CPU fallback
+    with pytest.raises(FileNotFoundError):
+        pkg.SplitReader(str(tmp_path), ["imu"], split="train")
+    with pytest.raises(KeyError):
+        pkg.save_splits_to_disk({"audio": tr["audio"], "labels": tr["labels"]}, va, te, str(tmp_path / "x"), ["audio", "imu"])
