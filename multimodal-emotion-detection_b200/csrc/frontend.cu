@@ -37,7 +37,7 @@ constexpr int N_FFT = 512, HOP = 160, N_BINS = 257, N_MELS = 64, N_MFCC = 40, N_
 constexpr int FPB = 16;            // frames per CTA
 constexpr int FE_WARPS = 8;        // warps per CTA
 constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
-constexpr int ZPAD = 256 + 16;     // padded complex buffer (index i -> i + (i >> 4))
+constexpr int ZPAD = 256;          // complex FFT scratch, XOR-swizzled (zpad below)
 constexpr int MEL_KS_MAX = 44;     // 8-bin steps summed over the eight 8-filter tiles (41 for the Slaney bank used here)
 constexpr int POW_LD = 260;        // pitch of a power-spectrum row: 256 bins + 4 (conflict-free A-fragment loads)
 constexpr int OUT_LD = 108;        // pitch of an output-tile row (conflict-free A-fragment loads of the log-mel part)
@@ -127,8 +127,9 @@ static void build_tables() {
       if (off >= MEL_KS_MAX) { g_tables_ok = false; continue; }
       for (int l = 0; l < 32; ++l) {
         const int m = 8 * j + (l >> 2), k = 8 * (t.mel_k0[j] + ks) + (l & 3);
-        t.mel_b[off * 32 + l] = make_float2(tf32_round(g_host_mel_dense[m * N_BINS + k]),
-                                            tf32_round(g_host_mel_dense[m * N_BINS + k + 4]));
+        // x 0.25: the kernel's power spectrum is 4 |X|^2 (it skips the two halvings of the real-FFT split)
+        t.mel_b[off * 32 + l] = make_float2(0.25f * tf32_round(g_host_mel_dense[m * N_BINS + k]),
+                                            0.25f * tf32_round(g_host_mel_dense[m * N_BINS + k + 4]));
       }
     }
   }
@@ -203,7 +204,10 @@ __device__ __forceinline__ void dft8(float2* v) {
   v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
   v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
-__device__ __forceinline__ int zpad(int i) { return i + (i >> 4); }
+// index i -> i ^ ((i >> 3) & 15): every access pattern of the three passes (stores of lane * 8 + r and
+// 64 q + k + 8 r, loads of lane + 32 r and lane + 32 jj + 64 r) then hits 16 distinct 8-byte bank pairs per half-warp
+// (the previous i + (i >> 4) padding left a 2-way conflict on the pass-2 stores)
+__device__ __forceinline__ int zpad(int i) { return i ^ ((i >> 3) & 15); }
 
 struct FeSmem {
   float seg[SEG];
@@ -357,9 +361,9 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
       const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);  // conj(Z[N-k])
       const float2 zk = v[m];
       const int k = lane + 32 * m;
-      const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-      const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
-      const float2 xo = mul_mi(d);                       // (Zk - Zc) / (2i)
+      // 2 X_k = (Zk + Zc) + w^k (Zk - Zc) / i: the factor 4 on |X|^2 lives in the mel weights (x 0.25, exact)
+      const float2 xe = cadd(zk, zc);
+      const float2 xo = mul_mi(csub(zk, zc));
       const float2 X = cadd(xe, cmul(s_tw[k], xo));
       pw[k] = X.x * X.x + X.y * X.y;
     }
@@ -435,23 +439,31 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   if (xs) {
     // fused operand preparation for the tensor-core LSTM (lstm.cu): time-major rows (t, clip) of
     // [hi(104) | lo(104) | hi(104) | 1, 1 | 0...] in fp16, hi = fp16(x), lo = fp16(x - hi)
-    // 64 threads per row, 4 rows at a time: thread j < 52 converts one pair of features and stores it three times
-    // (hi at [j], lo at [52 + j], hi at [104 + j], in half2 units); threads 52.. write the (1, 1) pair and the zero pad
-    const int j = tid & 63, rsub = tid >> 6;
-    const int h2_per_row = ldx >> 1;
-    for (int f = rsub; f < rows; f += 4) {
-      __half2* row = reinterpret_cast<__half2*>(xs + ((size_t)(t0 + f) * Bp + clip) * ldx);
-      if (j < N_FEATS / 2) {
-        const float2 x = *reinterpret_cast<const float2*>(&s_out[f][2 * j]);
-        const __half2 hi = __floats2half2_rn(x.x, x.y);
-        const float2 hf = __half22float2(hi);
-        const __half2 lo = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
-        row[j] = hi;
-        row[N_FEATS / 2 + j] = lo;
-        row[N_FEATS + j] = hi;
+    // thread = (row, 8-feature chunk): 13 chunks per row convert 8 features and store them three times with 128-bit
+    // stores (hi at [8c], lo at [104 + 8c], hi at [208 + 8c]); a 14th thread per row writes the (1, 1, 0...) tail
+    for (int i = tid; i < rows * 14; i += blockDim.x) {
+      const int f = i / 14, c = i % 14;
+      __half* row = xs + ((size_t)(t0 + f) * Bp + clip) * ldx;
+      if (c < 13) {
+        const float4 x0 = *reinterpret_cast<const float4*>(&s_out[f][8 * c]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&s_out[f][8 * c + 4]);
+        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(row + 8 * c) = vh;
+        *reinterpret_cast<uint4*>(row + N_FEATS + 8 * c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(row + 2 * N_FEATS + 8 * c) = vh;
       } else {
-        for (int k2 = 3 * N_FEATS / 2 + (j - N_FEATS / 2); k2 < h2_per_row; k2 += 64 - N_FEATS / 2)
-          row[k2] = k2 == 3 * N_FEATS / 2 ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
+        for (int k8 = 3 * N_FEATS; k8 < ldx; k8 += 8)
+          *reinterpret_cast<uint4*>(row + k8) = make_uint4(k8 == 3 * N_FEATS ? 0x3C003C00u : 0u, 0u, 0u, 0u);
       }
     }
   }

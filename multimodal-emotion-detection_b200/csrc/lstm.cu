@@ -353,9 +353,9 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
       static const bool xp0_f32 = [] { const char* e = getenv("AVHOT_XP0_F32"); return e && atoi(e) != 0; }();
       const bool xf16 = l > 0 || !xp0_f32;
       const int hp = H;                                // fp16 pitch of h_seq
-      // layer 0: A = [hi | lo | hi] x W = [W_hi | W_hi | W_lo] (K = 3 in), an fp32-class product; AVHOT_L0_TERMS=2
-      // drops the hi x W_lo term (K = 2 in: the first two blocks of the same operands)
-      static const int l0_terms = [] { const char* e = getenv("AVHOT_L0_TERMS"); return e && atoi(e) == 2 ? 2 : 3; }();
+      // layer 0: A = [hi | lo | hi] x W = [W_hi | W_hi | W_lo] (K = 3 in), an fp32-class product (dropping the
+      // hi x W_lo term measured 5.4e-3 on the logits, outside the stated tolerance)
+      constexpr int l0_terms = 3;
       if (l == 0 && seq_split) {                      // operand already prepared by avhot_frontend_ex
         const int ldx = pad8(3 * in + 2);
         rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
