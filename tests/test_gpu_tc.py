@@ -47,6 +47,36 @@ def test_lstm_tc_vs_oracle(pkg, dev, world, golden):
     assert (again == ref_out).all()
 
 
+def test_lstm_tc_pair_kernel_equals_single_cta_kernel(pkg, dev, world, tmp_path):
+    """The CTA-pair recurrence (cta_group::2, M = 256) and the single-CTA kernel (AVHOT_REC_PAIR=0, also what runs when
+    the pairs of a grid cannot all be co-resident) compute the same rows: bit-identical embeddings.  The switch is read
+    once per process, so the single-CTA run happens in a child process."""
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(300, 24, 104)).astype(np.float32)
+    lengths = rng.integers(1, 25, size=300)
+    np.save(tmp_path / "x.npy", x)
+    np.save(tmp_path / "len.npy", lengths)
+    enc = make_model(pkg, dev, world).set_precision("tc").encoders["audio"]
+    torch.save(enc.state_dict(), tmp_path / "enc.pt")
+    pair = enc(torch.from_numpy(x).to(dev), torch.from_numpy(lengths)).cpu().numpy()
+    code = (
+        "import sys, numpy as np, torch\n"
+        "import multimodal_emotion_detection_b200 as pkg\n"
+        "d = sys.argv[1]\n"
+        "enc = pkg.SequenceEncoder(104, 256, 128, 2, 'lstm')\n"
+        "enc.load_state_dict(torch.load(d + '/enc.pt'))\n"
+        "enc = enc.to('cuda:0').eval(); enc.precision = pkg._lib.PREC_TC\n"
+        "out = enc(torch.from_numpy(np.load(d + '/x.npy')).to('cuda:0'), torch.from_numpy(np.load(d + '/len.npy')))\n"
+        "np.save(d + '/single.npy', out.cpu().numpy())\n")
+    env = dict(os.environ, AVHOT_REC_PAIR="0", PYTHONPATH=os.pathsep.join(sys.path))
+    subprocess.run([sys.executable, "-c", code, str(tmp_path)], check=True, env=env, timeout=300)
+    single = np.load(tmp_path / "single.npy")
+    assert (pair == single).all()
+
+
 def test_full_path_tc(pkg, dev, world, golden):
     m = make_model(pkg, dev, world).set_precision("tc")
     feats = {"audio": torch.from_numpy(world["wave"]).to(dev), "video": torch.from_numpy(world["frames"]).to(dev)}
