@@ -285,18 +285,26 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     }
   };
   const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = (blockIdx.x + 1) * tiles_per_cta;
-  if (tile_begin * FPB < n_frames) fetch(tile_begin * FPB);
+  // pre-emphasised, reflect-padded segment of a tile: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
+  auto stage_segment = [&]() {
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = tid + j * (FE_WARPS * 32);
+      if (i < SEG) s_seg[i] = fmaf(-0.97f, prv[j], cur[j]);
+    }
+  };
+  if (tile_begin * FPB < n_frames) {
+    fetch(tile_begin * FPB);
+    stage_segment();
+  }
+  __syncthreads();
   for (int tile = tile_begin; tile < tile_end; ++tile) {
   const int t0 = tile * FPB;
   if (t0 >= n_frames) break;
-  // pre-emphasised, reflect-padded segment: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
-#pragma unroll
-  for (int j = 0; j < SPT; ++j) {
-    const int i = tid + j * (FE_WARPS * 32);
-    if (i < SEG) s_seg[i] = fmaf(-0.97f, prv[j], cur[j]);
-  }
-  __syncthreads();
-  if (tile + 1 < tile_end && (tile + 1) * FPB < n_frames) fetch((tile + 1) * FPB);
+  // the next tile's samples travel to registers during this tile's FFTs and are staged right after them (the segment
+  // buffer is free once the FFT phase is over), so a tile costs four block barriers, not five
+  const bool have_next = tile + 1 < tile_end && (tile + 1) * FPB < n_frames;
+  if (have_next) fetch((tile + 1) * FPB);
 
   float2* z = s_z[warp];
   for (int f = warp; f < FPB; f += FE_WARPS) {
@@ -348,29 +356,32 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 #pragma unroll
       for (int r = 0; r < 4; ++r) { v[2 * r] = u[0][r]; v[2 * r + 1] = u[1][r]; }
     }
-    // ---- real-FFT split + power.  Bin k = lane + 32 m needs Z[(256 - k) & 255], which is
-    //      register v[7 - m] (m' = 7 - m) of lane (32 - lane) & 31, or v[(8 - m) & 7] of lane 0
-    //      when lane == 0.
+    // ---- real-FFT split + power, two bins per butterfly: bin k = lane + 32 m (m < 4) and its mirror 256 - k come from
+    //      the same pair (Z_k, Z_{256-k}): with Zc = conj(Z_{256-k}), E = Z_k + Zc, T = w^k (Z_k - Zc) / i,
+    //      2 X_k = E + T and 2 X_{256-k} = conj(E - T).  Z_{256-k} is register 7 - m of lane 32 - lane (register 8 - m
+    //      of lane 0 itself for lane 0, whose m = 0 "mirror" is the unused Nyquist bin, written into the row's pad).
     float* pw = s_pow[f];
     const int src = (32 - lane) & 31;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      // value from the mirrored lane: for lane != 0 we need its v[7-m]; for lane 0 its v[(8-m)&7]
+    for (int m = 0; m < 4; ++m) {
       const float2 a = v[7 - m], b = v[(8 - m) & 7];
       const float mx_a = __shfl_sync(0xffffffffu, a.x, src), my_a = __shfl_sync(0xffffffffu, a.y, src);
-      const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);  // conj(Z[N-k])
+      const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);  // conj(Z[256-k])
       const float2 zk = v[m];
       const int k = lane + 32 * m;
-      // 2 X_k = (Zk + Zc) + w^k (Zk - Zc) / i: the factor 4 on |X|^2 lives in the mel weights (x 0.25, exact)
+      // the factor 4 on |X|^2 lives in the mel weights (x 0.25, exact)
       const float2 xe = cadd(zk, zc);
-      const float2 xo = mul_mi(csub(zk, zc));
-      const float2 X = cadd(xe, cmul(s_tw[k], xo));
-      pw[k] = X.x * X.x + X.y * X.y;
+      const float2 T = cmul(s_tw[k], mul_mi(csub(zk, zc)));
+      const float2 Xa = cadd(xe, T), Xb = csub(xe, T);
+      pw[k] = Xa.x * Xa.x + Xa.y * Xa.y;
+      pw[256 - k] = Xb.x * Xb.x + Xb.y * Xb.y;
     }
+    if (lane == 0) pw[128] = 4.f * (v[4].x * v[4].x + v[4].y * v[4].y);   // Z_128 is its own mirror, w^128 = -i
     // (bin 256 carries no filter weight - checked when the tables are built - and is not formed)
     __syncwarp();
   }
-  __syncthreads();                   // power spectra of the tile complete; the FFT scratch is free
+  __syncthreads();                   // power spectra of the tile complete; the FFT scratch and the segment are free
+  if (have_next) stage_segment();
   // ---- mel filterbank on the tensor cores + log: warp j = filters 8j .. 8j+7 of all 16 frames
   {
     const int g = lane >> 2, t4 = lane & 3;
