@@ -318,6 +318,62 @@ int avhot_calibration_accumulate(const float* logits, const float* confidences, 
                                  const int64_t* labels, long long N, int C, const float* bin_edges,
                                  int num_bins, double* acc, avhot_stream_t stream);
 
+/* ---- src/encoders.py:96-113, :170-192  SequenceEncoder(encoder_type='transformer') ----------
+ * input_proj -> + pos_embedding[min(t, max_len - 1)] -> num_layers x nn.TransformerEncoderLayer (post-norm, GELU,
+ * nhead heads, dim_feedforward = ffn_dim) with key padding from `lengths` -> mean over the valid steps ->
+ * projection.  seq (B, T, input_dim) fp32, lengths (B) int32 or NULL -> z (B, passes, output_dim).  Pass t draws the
+ * masks of (seed, t0 + t, clip0 + b) at sites AVHOT_SITE_TFM + 3 l + {0 dropout1 (T, H), 1 dropout (T, ffn),
+ * 2 dropout2 (T, H)} of layer l; p = 0 is the eval forward.  Weights are nn.Linear / nn.MultiheadAttention layouts:
+ * in_proj (3H, H) = [q | k | v] rows.  fp32 path. */
+#define AVHOT_TFM_MAX_LAYERS 4
+typedef struct avhot_tfm* avhot_tfm_t;
+typedef struct {
+  int input_dim, hidden_dim, output_dim, num_layers, num_heads, ffn_dim, max_len;
+  float ln_eps;
+  const float *input_w, *input_b, *pos, *proj_w, *proj_b;
+  const float *in_proj_w[AVHOT_TFM_MAX_LAYERS], *in_proj_b[AVHOT_TFM_MAX_LAYERS];
+  const float *out_w[AVHOT_TFM_MAX_LAYERS], *out_b[AVHOT_TFM_MAX_LAYERS];
+  const float *lin1_w[AVHOT_TFM_MAX_LAYERS], *lin1_b[AVHOT_TFM_MAX_LAYERS];
+  const float *lin2_w[AVHOT_TFM_MAX_LAYERS], *lin2_b[AVHOT_TFM_MAX_LAYERS];
+  const float *n1_w[AVHOT_TFM_MAX_LAYERS], *n1_b[AVHOT_TFM_MAX_LAYERS];
+  const float *n2_w[AVHOT_TFM_MAX_LAYERS], *n2_b[AVHOT_TFM_MAX_LAYERS];
+} avhot_tfm_desc;
+int avhot_tfm_create(const avhot_tfm_desc* desc, avhot_tfm_t* out, avhot_stream_t stream);
+void avhot_tfm_destroy(avhot_tfm_t h);
+size_t avhot_tfm_workspace_bytes(avhot_tfm_t h, int B, int T, int passes);
+int avhot_tfm_forward(avhot_tfm_t h, const float* seq, const int32_t* lengths, float* z, int B, int T, int passes,
+                      float p, uint64_t seed, uint64_t clip0, uint32_t t0, void* workspace, size_t workspace_bytes,
+                      avhot_stream_t stream);
+
+/* ---- src/attention.py:143-274  TemporalAttention -------------------------------------------
+ * forward(sequence (B, S, feature_dim), mask (B, S) 1 = valid or NULL) -> attended (B, S, hidden), weights
+ * (B, heads, S, S) (may be NULL).  Masked keys score -inf, the context of masked queries is multiplied by 0
+ * (:219-236); the reference never applies its two nn.Dropout modules (its forward tests `hasattr(self, "attn_drop")`,
+ * an attribute that does not exist, :227, :240), so the module is deterministic. */
+typedef struct avhot_tattn* avhot_tattn_t;
+typedef struct {
+  int feature_dim, hidden_dim, num_heads;
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
+} avhot_tattn_desc;
+int avhot_tattn_create(const avhot_tattn_desc* desc, avhot_tattn_t* out, avhot_stream_t stream);
+void avhot_tattn_destroy(avhot_tattn_t h);
+size_t avhot_tattn_workspace_bytes(avhot_tattn_t h, int B, int S);
+int avhot_tattn_forward(avhot_tattn_t h, const float* seq, const uint8_t* valid, float* attended, float* weights, int B,
+                        int S, void* workspace, size_t workspace_bytes, avhot_stream_t stream);
+/* pool_sequence (:245-274): key importance = mean over heads and queries of the weights, renormalised with + 1e-9;
+ * pooled (B, D) = importance-weighted sum of sequence (B, S, D). */
+int avhot_tattn_pool(const float* seq, const float* weights, float* pooled, int B, int S, int D, int heads,
+                     avhot_stream_t stream);
+
+/* ---- src/attention.py:421-548  PairwiseModalityAttention, aggregation per target modality ----
+ * out (B, H) = LayerNorm(self_feat + dropout(sum_j msgs[j])) * avail   (:527-545).  msgs_host_array: n_msgs <= 3 device
+ * pointers (B, H), summed left to right; avail (B) bytes or NULL; dropout site = `site` (AVHOT_SITE_PAIR_MSG + m),
+ * element = column.  The directional messages are CrossModalAttention outputs (avhot_xattn_forward). */
+int avhot_pair_combine(const float* self_feat, const float* const* msgs_host_array, int n_msgs, const uint8_t* avail,
+                       const float* ln_w, const float* ln_b, float ln_eps, float* out, int B, int H, float p,
+                       uint64_t seed, uint64_t clip0, uint32_t t, uint32_t site, avhot_stream_t stream);
+
+
 /* ---- a8: src/uncertainty.py:17-86  MCDropoutUncertainty statistics ------------------ */
 /* logits (B, T, C) -> mean_logits (B, C), uncertainty (B) = mean_c Var_t softmax (population
  * variance, src/uncertainty.py:77-84), labels (B) = argmax mean_logits (first max wins,
@@ -338,6 +394,8 @@ int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
 #define AVHOT_SITE_ATTN 16u
 #define AVHOT_SITE_LATE 32u
 #define AVHOT_SITE_UNC 48u
+#define AVHOT_SITE_TFM 64u      /* + 3 layer + {0, 1, 2} */
+#define AVHOT_SITE_PAIR_MSG 80u /* + target modality index */
 
 #ifdef __cplusplus
 }

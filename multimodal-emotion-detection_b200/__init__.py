@@ -6,7 +6,7 @@ through the C ABI in include/avhot.h (libavhot.so).  There is no CPU fallback.""
 from . import _lib, _rng, dataprocessing, encoders, attention, fusion, uncertainty, synth, parallel, hotpath, data  # noqa: F401
 from ._rng import philox_context  # noqa: F401
 from .encoders import SequenceEncoder, FrameEncoder, build_encoder  # noqa: F401
-from .attention import CrossModalAttention  # noqa: F401
+from .attention import CrossModalAttention, TemporalAttention, PairwiseModalityAttention  # noqa: F401
 from .fusion import HybridFusion, EarlyFusion, LateFusion, LateFusionWithUncertainty, ConcatHead, build_fusion_model  # noqa: F401
 from .uncertainty import (MCDropoutUncertainty, CalibrationMetrics, UncertaintyWeightedFusion,  # noqa: F401
                           compute_calibration_metrics, mc_reduce)  # noqa: F401

@@ -17,6 +17,8 @@ SITE_FRAME_MLP, SITE_FRAME_POOL, SITE_GATE, SITE_MODMASK, SITE_ATTN = 0, 1, 2, 3
 SITE_EARLY0, SITE_EARLY1, SITE_LATE = 4, 5, 32
 SITE_CNN0, SITE_CNN1 = 6, 7
 SITE_UNC = 48
+SITE_TFM, SITE_PAIR_MSG = 64, 80
+TFM_MAX_LAYERS = 4
 MAX_MODALITIES = 4
 
 c_float_p = C.c_void_p  # device pointers travel as integers
@@ -35,6 +37,19 @@ class CnnDesc(C.Structure):
         "conv1_weight", "conv1_bias", "bn1_weight", "bn1_bias", "bn1_mean", "bn1_var",
         "conv2_weight", "conv2_bias", "bn2_weight", "bn2_bias", "bn2_mean", "bn2_var",
         "proj_weight", "proj_bias")] + [("bn_eps", C.c_float)]
+
+
+class TfmDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("input_dim", "hidden_dim", "output_dim", "num_layers", "num_heads", "ffn_dim",
+                                       "max_len")] + [("ln_eps", C.c_float)] + \
+               [(n, C.c_void_p) for n in ("input_w", "input_b", "pos", "proj_w", "proj_b")] + \
+               [(n, C.c_void_p * 4) for n in ("in_proj_w", "in_proj_b", "out_w", "out_b", "lin1_w", "lin1_b", "lin2_w",
+                                              "lin2_b", "n1_w", "n1_b", "n2_w", "n2_b")]
+
+
+class TattnDesc(C.Structure):
+    _fields_ = [("feature_dim", C.c_int), ("hidden_dim", C.c_int), ("num_heads", C.c_int)] + [(n, C.c_void_p) for n in (
+        "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b")]
 
 
 class FrameDesc(C.Structure):
@@ -147,6 +162,16 @@ PROTOTYPES = {
     "avhot_uncertainty_fuse": (_I, [_P, _P, _P, _P, _P, C.c_longlong, _I, _I, _F, _P]),
     "avhot_calibration_accumulate": (_I, [_P, _P, _P, _P, C.c_longlong, _I, _P, _I, _P, _P]),
     "avhot_mc_reduce": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "avhot_tfm_create": (_I, [C.POINTER(TfmDesc), C.POINTER(_P), _P]),
+    "avhot_tfm_destroy": (None, [_P]),
+    "avhot_tfm_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "avhot_tfm_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P, _SZ, _P]),
+    "avhot_tattn_create": (_I, [C.POINTER(TattnDesc), C.POINTER(_P), _P]),
+    "avhot_tattn_destroy": (None, [_P]),
+    "avhot_tattn_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "avhot_tattn_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "avhot_tattn_pool": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "avhot_pair_combine": (_I, [_P, C.POINTER(_P), _I, _P, _P, _P, _F, _P, _I, _I, _F, _U64, _U64, _U32, _U32, _P]),
 }
 
 _lock = threading.Lock()

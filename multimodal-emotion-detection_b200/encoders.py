@@ -21,9 +21,8 @@ _ws_frames = Workspace()
 
 
 class SequenceEncoder(nn.Module):
-    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru' and 'cnn'
-     run on the fp32 kernels of csrc/gru.cu / csrc/cnn.cu; 'transformer' is valid in the
-    reference and not built here (ValueError says so)."""
+    """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru', 'cnn' and
+    'transformer'  run on the fp32 kernels of csrc/gru.cu / csrc/cnn.cu / csrc/seqattn.cu."""
 
     def __init__(self, input_dim: int, hidden_dim: int = 256, output_dim: int = 128, num_layers: int = 2,
                  encoder_type: str = 'lstm', dropout: float = 0.1):
@@ -54,12 +53,88 @@ class SequenceEncoder(nn.Module):
             self.pool = nn.AdaptiveAvgPool1d(1)
             self.projection = nn.Linear(hidden_dim, output_dim)
         elif encoder_type == 'transformer':
-            raise ValueError(f"encoder type '{encoder_type}' exists in the reference but is not built in this "
-                             "library (hot path = 'lstm')")
+            self.input_proj = nn.Linear(input_dim, hidden_dim)                       # src/encoders.py:100-112
+            encoder_layer = nn.TransformerEncoderLayer(d_model=hidden_dim, nhead=4, dim_feedforward=hidden_dim * 4,
+                                                       dropout=dropout, batch_first=False, activation='gelu')
+            self.transformer = nn.TransformerEncoder(encoder_layer, num_layers=num_layers, enable_nested_tensor=False)
+            self.max_len = 4096
+            self.pos_embedding = nn.Embedding(self.max_len, hidden_dim)
+            self.projection = nn.Linear(hidden_dim, output_dim)
         else:
             raise ValueError(f"Unknown encoder type: {encoder_type}")                # :115
-        self._handle = Handle({"gru": "avhot_gru_destroy", "cnn": "avhot_cnn_destroy"}.get(encoder_type,
-                                                                                            "avhot_lstm_destroy"))
+        self._handle = Handle({"gru": "avhot_gru_destroy", "cnn": "avhot_cnn_destroy",
+                               "transformer": "avhot_tfm_destroy"}.get(encoder_type, "avhot_lstm_destroy"))
+
+    # ---- transformer (csrc/seqattn.cu) -----------------------------------------------------------------------------
+    def _tfm_tensors(self):
+        ts = [self.input_proj.weight, self.input_proj.bias, self.pos_embedding.weight, self.projection.weight,
+              self.projection.bias]
+        for layer in self.transformer.layers:
+            ts += [layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias, layer.self_attn.out_proj.weight,
+                   layer.self_attn.out_proj.bias, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight,
+                   layer.linear2.bias, layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias]
+        return ts
+
+    def _get_tfm_handle(self, dev):
+        src = self._tfm_tensors()
+
+        def create():
+            ts = [_lib.f32c(t.detach()) for t in src]
+            _lib.require_cuda(*ts)
+            layer0 = self.transformer.layers[0]
+            if len(self.transformer.layers) > _lib.TFM_MAX_LAYERS:
+                raise ValueError(f"SequenceEncoder(transformer): at most {_lib.TFM_MAX_LAYERS} layers are built")
+            if layer0.norm_first or self.transformer.norm is not None:
+                raise ValueError("SequenceEncoder(transformer): only the post-norm layer the reference builds")
+            d = _lib.TfmDesc()
+            d.input_dim, d.hidden_dim, d.output_dim = self.input_dim, self.hidden_dim, self.output_dim
+            d.num_layers, d.num_heads = len(self.transformer.layers), layer0.self_attn.num_heads
+            d.ffn_dim, d.max_len, d.ln_eps = layer0.linear1.out_features, self.max_len, float(layer0.norm1.eps)
+            d.input_w, d.input_b, d.pos, d.proj_w, d.proj_b = [t.data_ptr() for t in ts[:5]]
+            names = ("in_proj_w", "in_proj_b", "out_w", "out_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b", "n1_w", "n1_b",
+                     "n2_w", "n2_b")
+            for l in range(d.num_layers):
+                for j, n in enumerate(names):
+                    getattr(d, n)[l] = ts[5 + 12 * l + j].data_ptr()
+            out = C.c_void_p()
+            _lib.check(_lib.load().avhot_tfm_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
+                       "SequenceEncoder(transformer)")
+            torch.cuda.current_stream(dev).synchronize()       # the handle copies from `ts` on the stream
+            return out.value
+
+        return self._handle.get(src, create)
+
+    def _tfm_drop_p(self) -> float:
+        # the six nn.Dropout modules of the layers share p; MCDropoutUncertainty flips all of them (src/uncertainty.py:36-46)
+        mods = [m for layer in self.transformer.layers for m in (layer.dropout1, layer.dropout, layer.dropout2)]
+        if len({m.training for m in mods}) != 1:
+            raise ValueError("SequenceEncoder(transformer): the layers' dropout modules must be in the same mode")
+        return float(mods[0].p) if mods[0].training else 0.0
+
+    @torch.no_grad()
+    def _forward_transformer(self, x: torch.Tensor, lengths=None, passes: int = 1, p: Optional[float] = None,
+                             seed: Optional[int] = None, clip0: Optional[int] = None,
+                             t0: Optional[int] = None) -> torch.Tensor:
+        """(B, T, in) -> (B, passes, out).  src/encoders.py:170-192; pass t draws the masks of (seed, t0 + t)."""
+        dev = x.device
+        B, T, _ = x.shape
+        if p is None:
+            p = self._tfm_drop_p()
+        cs, ct, cc = _rng.current()
+        seed = cs if seed is None else seed
+        t0 = ct if t0 is None else t0
+        clip0 = cc if clip0 is None else clip0
+        z = torch.empty(B, passes, self.output_dim, device=dev, dtype=torch.float32)
+        if B == 0:
+            return z
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._get_tfm_handle(dev)
+            ws = _ws.get(lib.avhot_tfm_workspace_bytes(h, B, T, passes), dev)
+            _lib.check(lib.avhot_tfm_forward(h, _lib.ptr(x), _lib.ptr(lengths), _lib.ptr(z), B, T, passes, float(p), seed,
+                                             clip0, t0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                       "SequenceEncoder.forward (transformer)")
+        return z
 
     def _cnn_tensors(self):
         return [self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self.bn1.running_mean,
@@ -159,6 +234,8 @@ class SequenceEncoder(nn.Module):
                 raise ValueError("lengths must be (B,)")
         if self.encoder_type == 'cnn':
             return self._forward_cnn(x)[:, 0, :]               # `lengths` is ignored for this type (:157-168)
+        if self.encoder_type == 'transformer':
+            return self._forward_transformer(x, lengths)[:, 0, :]
         out = torch.empty(B, self.output_dim, device=dev, dtype=torch.float32)
         if B == 0:
             return out

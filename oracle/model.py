@@ -156,6 +156,140 @@ def sequence_encoder_cnn(seq, sd, prefix="cnn_enc.", ctx: Optional[DropCtx] = No
     return _lin(x, sd, prefix + "projection")
 
 
+
+# ---- transformer encoder, TemporalAttention, PairwiseModalityAttention ---------------
+def _mha_self(x, valid, w_in, b_in, w_out, b_out, num_heads):
+    """nn.MultiheadAttention(x, x, x, key_padding_mask=~valid) in eval mode (torch/nn/functional.py
+    multi_head_attention_forward): packed in_proj (3H, H) = [q | k | v], scores scaled by 1/sqrt(head dim), padded
+    keys -inf, softmax, out_proj.  x (B, T, H); valid (B, T) bool or None."""
+    B, T, H = x.shape
+    dh = H // num_heads
+    qkv = x @ w_in.T + b_in
+    q, k, v = (t.view(B, T, num_heads, dh).transpose(1, 2) for t in qkv.split(H, dim=-1))
+    scores = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(dh))
+    if valid is not None:
+        scores = scores.masked_fill(~valid[:, None, None, :], float("-inf"))
+    attn = _softmax(scores, dim=-1)
+    ctx = (attn @ v).transpose(1, 2).reshape(B, T, H)
+    return ctx @ w_out.T + b_out
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))       # F.gelu, approximate='none'
+
+
+def sequence_encoder_transformer(seq, sd, prefix="tfm_enc.", num_layers=2, num_heads=4, lengths=None,
+                                 ctx: Optional[DropCtx] = None, p: float = 0.1, max_len=4096):
+    """SequenceEncoder(encoder_type='transformer').forward.  src/encoders.py:170-192 over the modules built at
+    :100-112: input_proj, + pos_embedding[min(t, max_len - 1)], num_layers post-norm nn.TransformerEncoderLayer
+    (nhead 4, dim_feedforward 4 H, GELU; x = norm1(x + dropout1(SA(x))), x = norm2(x + dropout2(linear2(dropout(
+    gelu(linear1(x)))))), torch/nn/modules/transformer.py), key padding from `lengths`, mean over the valid steps,
+    projection.  Dropout sites (only the nn.Dropout modules are stochastic under MC): SITE_TFM + 3 l + {0, 1, 2} with
+    per-clip masks (T, H), (T, 4H), (T, H) - the reference holds these tensors as (T, B, .); the clip axis is 1 there."""
+    B, T, _ = seq.shape
+    x = _lin(seq, sd, prefix + "input_proj")
+    pos_idx = torch.arange(T).clamp_max(max_len - 1)
+    x = x + sd[prefix + "pos_embedding.weight"][pos_idx].unsqueeze(0)
+    valid = None
+    if lengths is not None:
+        valid = torch.arange(T).unsqueeze(0) < torch.as_tensor(lengths).view(-1, 1)
+    for l in range(num_layers):
+        lp = f"{prefix}transformer.layers.{l}."
+        sa = _mha_self(x, valid, sd[lp + "self_attn.in_proj_weight"], sd[lp + "self_attn.in_proj_bias"],
+                       sd[lp + "self_attn.out_proj.weight"], sd[lp + "self_attn.out_proj.bias"], num_heads)
+        if ctx is not None:
+            sa = ctx.apply(sa, px.SITE_TFM + 3 * l, p)
+        x = _layer_norm(x + sa, sd[lp + "norm1.weight"], sd[lp + "norm1.bias"])
+        ff = _gelu(_lin(x, sd, lp + "linear1"))
+        if ctx is not None:
+            ff = ctx.apply(ff, px.SITE_TFM + 3 * l + 1, p)
+        ff = _lin(ff, sd, lp + "linear2")
+        if ctx is not None:
+            ff = ctx.apply(ff, px.SITE_TFM + 3 * l + 2, p)
+        x = _layer_norm(x + ff, sd[lp + "norm2.weight"], sd[lp + "norm2.bias"])
+    if valid is not None:
+        m = valid.to(x.dtype).unsqueeze(-1)
+        pooled = (x * m).sum(dim=1) / m.sum(dim=1).clamp_min(1.0)                          # :186-190
+    else:
+        pooled = x.mean(dim=1)                                                              # :192
+    return _lin(pooled, sd, prefix + "projection")
+
+
+def temporal_attention(seq, mask, sd, prefix="tattn.", num_heads=4):
+    """TemporalAttention.forward.  src/attention.py:201-243: q / k / v projections of the same sequence, scaled
+    scores, masked keys -inf (:219-224), softmax, context, masked queries zeroed (:232-236), out_proj.  Neither
+    nn.Dropout of the module is ever applied (:227, :240 test attributes that do not exist).
+    seq (B, S, F); mask (B, S) 1 = valid or None -> (attended (B, S, H), weights (B, heads, S, S))."""
+    B, S, _ = seq.shape
+    q, k, v = (_lin(seq, sd, prefix + n) for n in ("q_proj", "k_proj", "v_proj"))
+    H = q.shape[-1]
+    dh = H // num_heads
+    q, k, v = (t.view(B, S, num_heads, dh).permute(0, 2, 1, 3) for t in (q, k, v))
+    logits = (q @ k.transpose(-2, -1)) * (dh ** -0.5)
+    if mask is not None:
+        km = torch.as_tensor(mask).bool()
+        logits = logits.masked_fill(~km[:, None, None, :], float("-inf"))
+    w = _softmax(logits, dim=-1)
+    ctxv = w @ v
+    if mask is not None:
+        ctxv = ctxv * km[:, None, :, None]
+    ctxv = ctxv.permute(0, 2, 1, 3).reshape(B, S, H)
+    return _lin(ctxv, sd, prefix + "out_proj"), w
+
+
+def temporal_pool_sequence(seq, weights):
+    """TemporalAttention.pool_sequence.  src/attention.py:264-274."""
+    imp = weights.mean(dim=1).mean(dim=1)
+    imp = imp / (imp.sum(dim=1, keepdim=True) + 1e-9)
+    return torch.bmm(imp.unsqueeze(1), seq).squeeze(1)
+
+
+def pairwise_modality_attention(feats: Dict[str, torch.Tensor], mask, sd, modality_dims: Dict[str, int],
+                                prefix="pair.", num_heads=4, ctx: Optional[DropCtx] = None, p: float = 0.1):
+    """PairwiseModalityAttention.forward (the second class of that name, src/attention.py:421-548, which replaces the
+    first at import).  For every unordered pair (a, b): a attends to b with b's availability as the key mask if any
+    clip has b (:497-507), and vice versa (:509-517); per modality: LayerNorm(self_proj(x) + msg_dropout(sum of
+    messages)) (:527-536), zeroed where the modality is missing (:539-541).  Dropout sites: the CrossModalAttention
+    blocks SITE_ATTN + their index in cross_attn (ModuleDict order), msg_dropout SITE_PAIR_MSG + modality index.
+    -> (attended {name: (B, H)}, attention maps {"a_to_b": (B, heads, 1, 1)})."""
+    names = list(modality_dims.keys())
+    first = next(iter(feats.values()))
+    B = first.shape[0]
+    if mask is not None:
+        mask = torch.as_tensor(mask)
+        avail = {m: (mask[:, i] > 0) if mask.dtype != torch.bool else mask[:, i] for i, m in enumerate(names)}
+    else:
+        avail = {m: torch.ones(B, dtype=torch.bool) for m in names}
+    order = []
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            order += [f"{names[i]}_to_{names[j]}", f"{names[j]}_to_{names[i]}"]
+    msgs = {m: [] for m in names}
+    maps = {}
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            a, b = names[i], names[j]
+            for tgt, src in ((a, b), (b, a)):
+                if avail[src].any():
+                    key = f"{tgt}_to_{src}"
+                    o, att = cross_modal_attention(feats[tgt], feats[src], feats[src], (~avail[src]).view(B, 1), sd,
+                                                   f"{prefix}cross_attn.{key}.", num_heads, ctx=ctx,
+                                                   site=px.SITE_ATTN + order.index(key), p=p if ctx is not None else 0.0)
+                    msgs[tgt].append(o)
+                    maps[key] = att
+    out = {}
+    H = sd[prefix + "out_ln.weight"].shape[0]
+    for i, m in enumerate(names):
+        msg = torch.stack(msgs[m], dim=0).sum(dim=0) if msgs[m] else torch.zeros(B, H, dtype=first.dtype)
+        if ctx is not None:
+            msg = ctx.apply(msg, px.SITE_PAIR_MSG + i, p)
+        agg = _layer_norm(_lin(feats[m], sd, f"{prefix}self_proj.{m}") + msg, sd[prefix + "out_ln.weight"],
+                          sd[prefix + "out_ln.bias"])
+        if not avail[m].all():
+            agg = agg * avail[m].to(agg.dtype).unsqueeze(1)
+        out[m] = agg
+    return out, maps
+
 _LSTM_CACHE = {}
 
 

@@ -36,6 +36,9 @@ the per-clip mask tensor):
     SITE_LATE + i    32+i LateFusion classifiers[i].2  (hidden,)   src/fusion.py:184
     SITE_UNC + 4i+j  48+  LateFusionWithUncertainty modality i: j = 0 classifiers[i][0] (dim,), 1 classifiers[i][3]
                           (hidden,), 2 uncert_heads[i][0] (dim,), 3 uncert_heads[i][3] (hidden,)   src/fusion.py:613-620
+    SITE_TFM + 3l+j  64+  SequenceEncoder(transformer) layer l: j = 0 dropout1 (T, H), 1 dropout (T, 4H), 2 dropout2 (T, H)
+                          torch/nn/modules/transformer.py (TransformerEncoderLayer), built at src/encoders.py:101-108
+    SITE_PAIR_MSG + i 80+i PairwiseModalityAttention.msg_dropout for target modality i  (hidden,)  src/attention.py:468,536
 Synthetic-data streams use c3 >= 0x100 (see oracle/synth.py).
 """
 from __future__ import annotations
@@ -59,6 +62,8 @@ SITE_CNN1 = 7
 SITE_ATTN = 16
 SITE_LATE = 32
 SITE_UNC = 48
+SITE_TFM = 64
+SITE_PAIR_MSG = 80
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

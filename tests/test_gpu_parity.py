@@ -499,7 +499,7 @@ def test_gru_sequence_encoder_vs_reference_golden(pkg, dev, world, golden):
     want = om.sequence_encoder_gru(x.double(), sd64, lengths=ln)
     assert rel_err(enc(x.to(dev), ln).cpu().numpy(), want.numpy()) <= REL
     with pytest.raises(ValueError):
-        pkg.SequenceEncoder(input_dim=104, encoder_type="transformer")
+        pkg.SequenceEncoder(input_dim=104, encoder_type="conformer")
 
 
 def test_cnn_sequence_encoder_vs_reference_golden(pkg, dev, world, golden):

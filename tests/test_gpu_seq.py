@@ -1,0 +1,171 @@
+"""SURVEY.md 8(f) rows 1 and 4 on the GPU: SequenceEncoder(encoder_type='transformer'), TemporalAttention and
+PairwiseModalityAttention (csrc/seqattn.cu, csrc/xattn.cu) against the golden vectors the REFERENCE's own classes
+produced (tests/golden/make_golden_seq.py) and, at the benchmark dimensions, against the fp64 oracle those vectors
+pin.  fp32 path: 1e-4 norm-wise relative; dropout masks are the Philox spec's, so stochastic passes are compared too."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import model as om
+
+from _seq_fixture import PAIR_DIMS, load, state_dict
+
+REL = 1e-4
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert (np.isnan(got) == np.isnan(want)).all()
+    got, want = np.nan_to_num(got), np.nan_to_num(want)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import multimodal_emotion_detection_b200 as p
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    p._lib.check_device(torch.device("cuda:0"))
+    return p
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def g():
+    return load()
+
+
+def test_transformer_encoder_vs_reference_golden(pkg, dev, g):
+    """src/encoders.py:96-113, :170-192: eval forward with and without lengths, stochastic passes clip by clip (the
+    fixture's clip ids are not contiguous), several passes in one call, MCDropoutUncertainty's generic path."""
+    enc = pkg.SequenceEncoder(input_dim=104, hidden_dim=64, output_dim=32, num_layers=2, encoder_type="transformer", dropout=0.1)
+    enc.load_state_dict(state_dict(g, "tfm_enc."), strict=True)
+    enc = enc.to(dev).eval()
+    ids, seed = g["clip_ids"], int(g["seed"])
+    xl, xs = torch.from_numpy(g["tfm.x_long"]).to(dev), torch.from_numpy(g["tfm.x_short"]).to(dev)
+    ln = torch.from_numpy(g["tfm.lengths"])
+    assert rel_err(enc(xl).cpu().numpy(), g["tfm.z_long"]) <= REL
+    assert rel_err(enc(xl, ln).cpu().numpy(), g["tfm.z_long_lengths"]) <= REL
+    assert rel_err(enc(xs).cpu().numpy(), g["tfm.z_short"]) <= REL
+    pkg.MCDropoutUncertainty._set_dropout_train(enc)
+    for t in range(2):
+        rows_l, rows_s = [], []
+        for b, gid in enumerate(ids):
+            with pkg.philox_context(seed, t, int(gid)):
+                rows_l.append(enc(xl[b:b + 1], ln[b:b + 1]))
+                rows_s.append(enc(xs[b:b + 1]))
+        assert rel_err(torch.cat(rows_l).cpu().numpy(), g[f"tfm.z_long_pass{t}"]) <= REL, t
+        assert rel_err(torch.cat(rows_s).cpu().numpy(), g[f"tfm.z_short_pass{t}"]) <= REL, t
+    # clips 0 and 1 are contiguous: one call, two passes, equals pass by pass
+    many = enc._forward_transformer(xl[:2].contiguous(), ln[:2].to(dev).int(), passes=2, seed=seed, clip0=0, t0=0)
+    want = np.stack([g["tfm.z_long_pass0"][:2], g["tfm.z_long_pass1"][:2]], axis=1)
+    assert rel_err(many.cpu().numpy(), want) <= REL
+    enc.eval()
+
+    class FirstEight(torch.nn.Module):
+        def __init__(self, e):
+            super().__init__()
+            self.e = e
+
+        def forward(self, x):
+            return self.e(x)[:, :8]
+
+    mean, unc = pkg.MCDropoutUncertainty(FirstEight(enc).eval(), num_samples=4)(xl)
+    assert mean.shape == (4, 8) and unc.shape == (4,) and float(unc.min()) > 0
+    assert not any(m.training for m in enc.modules())
+    with pytest.raises(ValueError):
+        enc(torch.zeros(2, 5, 100, device=dev))
+
+
+def test_transformer_encoder_benchmark_dims_vs_oracle(pkg, dev):
+    """hidden 256 / 4 heads of 64 / T = 301 (the audio sequence of the benchmark), ragged lengths incl. 1 and T, one
+    stochastic pass, against the fp64 oracle pinned by the golden vectors."""
+    torch.manual_seed(11)
+    enc = pkg.SequenceEncoder(input_dim=104, hidden_dim=256, output_dim=128, num_layers=2, encoder_type="transformer", dropout=0.1)
+    sd = {"tfm_enc." + k: v.detach().double() for k, v in enc.state_dict().items()}
+    enc = enc.to(dev).eval()
+    B, T = 5, 301
+    x = torch.randn(B, T, 104)
+    ln = torch.tensor([301, 1, 150, 33, 300])
+    want = om.sequence_encoder_transformer(x.double(), sd, lengths=ln)
+    assert rel_err(enc(x.to(dev), ln).cpu().numpy(), want.numpy()) <= REL
+    want = om.sequence_encoder_transformer(x.double(), sd)
+    assert rel_err(enc(x.to(dev)).cpu().numpy(), want.numpy()) <= REL
+    pkg.MCDropoutUncertainty._set_dropout_train(enc)
+    ids = np.arange(B, dtype=np.uint64) + np.uint64(7000)
+    with pkg.philox_context(42, 5, 7000):
+        got = enc(x.to(dev), ln)
+    want = om.sequence_encoder_transformer(x.double(), sd, lengths=ln, ctx=om.DropCtx(42, 5, ids))
+    assert rel_err(got.cpu().numpy(), want.numpy()) <= REL
+
+
+def test_temporal_attention_vs_reference_golden(pkg, dev, g):
+    """src/attention.py:143-274 incl. pool_sequence; a fully masked clip is NaN in the reference and here."""
+    ta = pkg.TemporalAttention(feature_dim=40, hidden_dim=64, num_heads=4)
+    ta.load_state_dict(state_dict(g, "tattn."), strict=True)
+    ta = ta.to(dev).eval()
+    seq, mask = torch.from_numpy(g["tattn.seq"]).to(dev), torch.from_numpy(g["tattn.mask"]).to(dev)
+    for tag, mk in (("nomask", None), ("mask", mask)):
+        att, w = ta(seq, mk)
+        assert att.shape == (4, 19, 64) and w.shape == (4, 4, 19, 19)
+        assert rel_err(att.cpu().numpy(), g[f"tattn.attended_{tag}"]) <= REL
+        assert rel_err(w.cpu().numpy(), g[f"tattn.weights_{tag}"]) <= REL
+        assert rel_err(ta.pool_sequence(att, w).cpu().numpy(), g[f"tattn.pooled_{tag}"]) <= REL
+    ta.train()                                        # the reference's dropouts are dead code (:227, :240)
+    assert torch.equal(ta(seq, mask)[0], ta.eval()(seq, mask)[0])
+    # benchmark-like dims, a sequence longer than one key tile and not a multiple of it, one clip fully masked
+    torch.manual_seed(12)
+    big = pkg.TemporalAttention(feature_dim=104, hidden_dim=256, num_heads=4)
+    sd = {"tattn." + k: v.detach().double() for k, v in big.state_dict().items()}
+    big = big.to(dev).eval()
+    x = torch.randn(3, 77, 104)
+    mk = torch.ones(3, 77)
+    mk[1, 40:] = 0
+    mk[2, :] = 0
+    att, w = big(x.to(dev), mk.to(dev))
+    oatt, ow = om.temporal_attention(x.double(), mk, sd)
+    assert torch.isnan(att[2]).all() and torch.isnan(oatt[2]).all()
+    assert rel_err(att.cpu().numpy(), oatt.numpy()) <= REL
+    assert rel_err(w.cpu().numpy(), ow.numpy()) <= REL
+    with pytest.raises(ValueError):
+        big(x.to(dev), mk[:, :5].to(dev))
+
+
+def test_pairwise_modality_attention_vs_reference_golden(pkg, dev, g):
+    """src/attention.py:421-548 (second definition): three modalities, masks incl. a modality no clip has (its
+    directions are skipped, :497/:509), and one stochastic pass (attention dropout per direction + msg_dropout)."""
+    pm = pkg.PairwiseModalityAttention(PAIR_DIMS, hidden_dim=64, num_heads=4, dropout=0.1)
+    pm.load_state_dict(state_dict(g, "pair."), strict=True)
+    pm = pm.to(dev).eval()
+    feats = {m: torch.from_numpy(g[f"pair.x_{m}"]).to(dev) for m in PAIR_DIMS}
+    for tag in ("nomask", "mixed", "noimu"):
+        mk = None if tag == "nomask" else torch.from_numpy(g[f"pair.mask_{tag}"]).to(dev)
+        out, maps = pm(feats, mk)
+        assert sorted(maps) == list(g[f"pair.map_keys_{tag}"])
+        for m in PAIR_DIMS:
+            assert out[m].shape == (6, 64)
+            assert rel_err(out[m].cpu().numpy(), g[f"pair.out_{tag}_{m}"]) <= REL, (tag, m)
+        for k in maps:
+            assert rel_err(maps[k].cpu().numpy(), g[f"pair.map_{tag}_{k}"]) <= REL, (tag, k)
+    pkg.MCDropoutUncertainty._set_dropout_train(pm)
+    ids, seed, t = g["pair.clip_ids"], int(g["seed"]), int(g["pair.t_pass"])
+    mk = torch.from_numpy(g["pair.mask_mixed"]).to(dev)
+    # clips 0..3 of the fixture have contiguous ids and, among them, every modality is available somewhere, so the
+    # same directions run as in the reference's 6-clip batch (a direction is skipped only when NO clip of the batch
+    # has the source modality, :497/:509 - a batch-level rule, which is why this is not checked clip by clip)
+    assert int(ids[0]) == 0 and list(ids[:4]) == [0, 1, 2, 3]
+    with pkg.philox_context(seed, t, 0):
+        o, mp = pm({m: v[:4].contiguous() for m, v in feats.items()}, mk[:4].contiguous())
+    for m in PAIR_DIMS:
+        assert rel_err(o[m].cpu().numpy(), g[f"pair.out_drop_{m}"][:4]) <= REL, m
+    assert sorted(mp) == sorted(k[len("pair.map_drop_"):] for k in g.files if k.startswith("pair.map_drop_"))
+    for k, v in mp.items():
+        assert rel_err(v.cpu().numpy(), g[f"pair.map_drop_{k}"][:4]) <= REL, k
+    with pytest.raises(AssertionError):
+        pm(feats, mk[:, :2])
