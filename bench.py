@@ -188,6 +188,7 @@ def run_b200_arm(args):
     model.load_state_dict({k: torch.from_numpy(v) for k, v in osynth.state_dict_for("hybrid", sd_np).items()},
                           strict=True)
     model = model.to(dev).eval().set_precision(args.precision)
+    model.fold_video_projection = not args.no_fold
     pkg.MCDropoutUncertainty._set_dropout_train(model)            # what MCDropoutUncertainty.forward does (:58-59)
 
     def clip0_of(step):                                            # global clip index of this rank's batch
@@ -240,10 +241,10 @@ def run_b200_arm(args):
     pkg._lib.prof_reset()
 
     # ---- end to end through the public API with host buffers --------------------------------------------------
-    e2e = run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier)
+    e2e = None if args.no_e2e else run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier)
     # the same leg with the frames kept as the uint8 pixels they are decoded to (src/dataprocessing.py:261-265
     # divides by 255 on the host; here the division happens on the device): a quarter of the dominant H2D stream
-    e2e_u8 = run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8_frames=True)
+    e2e_u8 = None if args.no_e2e else run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8_frames=True)
 
     if rank != 0:
         if world > 1:
@@ -440,6 +441,9 @@ def main():
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU sample (~10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (kernel A/B runs)")
+    ap.add_argument("--no-fold", action="store_true",
+                    help="keep z_v materialised instead of folding FrameEncoder.projection[1] into the fusion GEMM (A/B)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="tc: large contractions on tcgen05 (TF32 / fp16 operands); fp32: CUDA-core fp32 everywhere")
     args = ap.parse_args()

@@ -197,6 +197,12 @@ int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, const uint8_t* 
 int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z,
                      int B, int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
                      avhot_stream_t stream);
+/* The same up to and including projection[0] = LayerNorm (src/encoders.py:246-248): y (B, T, hidden) fp32.  The
+ * tensor-core hot path feeds y to a HybridFusion handle whose proj_layers.video is the product of projection[1]
+ * (src/encoders.py:249) and proj_layers.video (src/fusion.py:486) - two linear maps with nothing in between. */
+int avhot_frame_tail_norm(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* y,
+                          int B, int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                          avhot_stream_t stream);
 
 /* ---- a5: src/attention.py:14-141  CrossModalAttention (general shapes) ------------- */
 typedef struct avhot_xattn* avhot_xattn_t;

@@ -143,6 +143,7 @@ PROTOTYPES = {
     "avhot_frame_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "avhot_frame_hidden": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
     "avhot_frame_tail": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P]),
+    "avhot_frame_tail_norm": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P]),
     "avhot_xattn_create": (_I, [C.POINTER(XattnDesc), C.POINTER(_P), _P]),
     "avhot_xattn_destroy": (None, [_P]),
     "avhot_xattn_workspace_bytes": (_SZ, [_P, _I, _I, _I]),

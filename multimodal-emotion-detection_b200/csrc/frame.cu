@@ -35,7 +35,12 @@ constexpr int FH = 256;         // hidden size this kernel is specialised for
 constexpr int FT_ROWS = 32;     // rows (clip, pass) per CTA
 constexpr int FT_WARPS = 8;
 
-__global__ void __launch_bounds__(FT_WARPS * 32)
+// PROJECT = false stops after the LayerNorm and writes the normalised rows (B, T, H): the tensor-core hot path folds
+// projection[1] into HybridFusion's proj_layers.video (two linear maps with nothing in between, src/encoders.py:249 ->
+// src/fusion.py:486), so the H -> out projection - 31 % of this kernel's instructions - runs as part of a GEMM that is
+// on the tensor cores anyway (avhot_frame_tail_norm).
+template <bool PROJECT>
+__global__ void __launch_bounds__(FT_WARPS * 32, PROJECT ? 3 : 4)
 frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, pre-dropout
                   const uint8_t* __restrict__ valid,    // (B, F) 1 = valid frame, or NULL
                   float* __restrict__ z,                // (B, T, out)
@@ -117,12 +122,20 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
 #pragma unroll
       for (int q = 0; q < 8; ++q) y[q] = 0.f;
     }
+    if (!PROJECT) {
+      if (row < n_rows) {
+        *reinterpret_cast<float4*>(z + (size_t)row * FH + c0) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(z + (size_t)row * FH + c1) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      continue;
+    }
     // staged [column][row]; the 16-byte row groups of a column are XOR-permuted by the owning lane (= column >> 3)
     // so the 32 lanes of this store do not all hit one bank (4-way instead of 32-way conflicts)
     const int ri = (((i >> 2) ^ (lane & 7)) << 2) | (i & 3);
 #pragma unroll
     for (int q = 0; q < 4; ++q) { ys[c0 + q][ri] = y[q]; ys[c1 + q][ri] = y[4 + q]; }
   }
+  if (!PROJECT) return;
   __syncthreads();
   // projection H -> out for the 32 rows of this CTA: thread = (output o, half of the rows)
   const int half = tid >> 7;
@@ -270,8 +283,27 @@ extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t
   const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
   AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail: B*T too large for one call");
   ProfScope prof("frame_tail", as_stream(stream));
-  frame_tail_kernel<<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
+  frame_tail_kernel<true><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
       hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
+      make_drop(p, seed, clip0, t0));
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_frame_tail_norm(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* y, int B,
+                                     int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                                     avhot_stream_t stream) {
+  AVHOT_REQUIRE(h && hid && y && B >= 0 && F >= 1 && T >= 1, AVHOT_ERR_INVALID, "frame_tail_norm: bad arguments");
+  AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "frame_tail_norm: dropout p=%g outside [0, 1)", (double)p);
+  AVHOT_REQUIRE((long long)F * 64 + 64 <= 0xffffffffLL, AVHOT_ERR_INVALID, "frame_tail_norm: F too large");
+  AVHOT_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, AVHOT_ERR_INVALID, "frame_tail_norm: y must be 16-byte aligned");
+  if (B == 0) return AVHOT_OK;
+  const long long rows = (long long)B * T;
+  const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
+  AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail_norm: B*T too large for one call");
+  ProfScope prof("frame_tail", as_stream(stream));
+  frame_tail_kernel<false><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
+      hid, frame_valid, y, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
       make_drop(p, seed, clip0, t0));
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;

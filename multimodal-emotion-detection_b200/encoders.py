@@ -359,8 +359,10 @@ class FrameEncoder(nn.Module):
 
     @torch.no_grad()
     def tail(self, hid: torch.Tensor, mask: Optional[torch.Tensor] = None, passes: int = 1, p: float = 0.0,
-             seed: int = 0, clip0: int = 0, t0: int = 0) -> torch.Tensor:
-        """Everything after the ReLU for `passes` stochastic passes: (B, F, H) -> (B, passes, out)."""
+             seed: int = 0, clip0: int = 0, t0: int = 0, project: bool = True) -> torch.Tensor:
+        """Everything after the ReLU for `passes` stochastic passes: (B, F, H) -> (B, passes, out).
+        project=False stops after projection[0] (the LayerNorm) and returns (B, passes, H): the tensor-core hot path
+        folds projection[1] into HybridFusion's proj_layers.video (HybridFusion.run(..., video_norm_from=...))."""
         dev = _lib.require_cuda(hid, mask)
         B, F, _ = hid.shape
         valid = None
@@ -368,14 +370,14 @@ class FrameEncoder(nn.Module):
             valid = torch.as_tensor(mask).to(device=dev).bool().to(torch.uint8).contiguous()
             if valid.shape != (B, F):
                 raise ValueError("mask must be (B, num_frames)")
-        z = torch.empty(B, passes, self.output_dim, device=dev, dtype=torch.float32)
+        z = torch.empty(B, passes, self.output_dim if project else self.hidden_dim, device=dev, dtype=torch.float32)
         if B == 0:
             return z
         with torch.cuda.device(dev):
             h = self._get_handle(dev)
-            _lib.check(_lib.load().avhot_frame_tail(h, _lib.ptr(hid), _lib.ptr(valid), _lib.ptr(z), B, F, passes,
-                                                    float(p), seed, clip0, t0, _lib.stream_ptr(dev)),
-                       "FrameEncoder.tail")
+            fn = _lib.load().avhot_frame_tail if project else _lib.load().avhot_frame_tail_norm
+            _lib.check(fn(h, _lib.ptr(hid), _lib.ptr(valid), _lib.ptr(z), B, F, passes, float(p), seed, clip0, t0,
+                          _lib.stream_ptr(dev)), "FrameEncoder.tail")
         return z
 
     def _drop_p(self) -> float:

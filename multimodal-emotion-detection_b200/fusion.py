@@ -51,11 +51,14 @@ class HybridFusion(nn.Module):
         self.classifier = nn.Linear(hidden_dim, num_classes)
         self.precision = _lib.PREC_FP32
         self._handle = Handle("avhot_fusion_destroy")
+        self._handle_folded = Handle("avhot_fusion_destroy")
 
     def _params(self):
         return [p for p in self.parameters()]
 
-    def _get_handle(self, dev):
+    def _get_handle(self, dev, folded=None):
+        """folded = (index, in_dim, weight (hidden, in_dim), bias (hidden), source tensors): a second handle whose
+        proj_layers[index] is replaced by a projection the caller has folded an upstream linear map into."""
         def create():
             keep = []
             d = _lib.FusionDesc()
@@ -73,6 +76,9 @@ class HybridFusion(nn.Module):
             for i, n in enumerate(self.modality_names):
                 d.modality_dim[i] = self.modality_dims[n]
                 d.proj_w[i], d.proj_b[i] = dp(self.proj_layers[n].weight), dp(self.proj_layers[n].bias)
+                if folded is not None and folded[0] == i:
+                    d.modality_dim[i] = folded[1]
+                    d.proj_w[i], d.proj_b[i] = dp(folded[2]), dp(folded[3])
                 self.attn_layers[n].fill_desc(d.attn[i], keep)
             d.pre_ln_w, d.pre_ln_b = dp(self.pre_ln.weight), dp(self.pre_ln.bias)
             d.post_ln_w, d.post_ln_b = dp(self.post_ln.weight), dp(self.post_ln.bias)
@@ -82,9 +88,34 @@ class HybridFusion(nn.Module):
             out = C.c_void_p()
             _lib.check(_lib.load().avhot_fusion_create(C.byref(d), None, C.byref(out), _lib.stream_ptr(dev)),
                        "HybridFusion")
+            if folded is not None:
+                torch.cuda.current_stream(dev).synchronize()   # the handle packs from the folded temporaries on the stream
             return out.value
 
+        if folded is not None:
+            return self._handle_folded.get(self._params() + list(folded[4]), create)
         return self._handle.get(self._params(), create)
+
+    def _fold_video_projection(self, index: int, lin: nn.Linear, dev):
+        """proj_layers[index] o lin as one Linear(lin.in_features -> hidden): W' = W_p W_l, b' = W_p b_l + b_p, computed
+        with the library's fp32 GEMM (two linear maps with no non-linearity between them: FrameEncoder.projection[1],
+        src/encoders.py:249, feeding proj_layers.video, src/fusion.py:486)."""
+        name = self.modality_names[index]
+        pl = self.proj_layers[name]
+        w_p, b_p = _lib.f32c(pl.weight.detach()), _lib.f32c(pl.bias.detach())              # (hidden, out), (hidden)
+        w_l, b_l = _lib.f32c(lin.weight.detach()), _lib.f32c(lin.bias.detach())            # (out, in), (out)
+        _lib.require_cuda(w_p, b_p, w_l, b_l)
+        w_lt = w_l.t().contiguous()                                                        # (in, out): layout copy only
+        hidden, k, n_in = w_p.shape[0], w_p.shape[1], w_l.shape[1]
+        w = torch.empty(hidden, n_in, device=dev, dtype=torch.float32)
+        b = torch.empty(1, hidden, device=dev, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.avhot_gemm(_lib.ptr(w_p), _lib.ptr(w_lt), None, _lib.ptr(w), hidden, n_in, k, 0, _lib.PREC_FP32,
+                                      _lib.stream_ptr(dev)), "HybridFusion fold (weight)")
+            _lib.check(lib.avhot_gemm(_lib.ptr(b_l.view(1, -1)), _lib.ptr(w_p), _lib.ptr(b_p), _lib.ptr(b), 1, hidden, k, 0,
+                                      _lib.PREC_FP32, _lib.stream_ptr(dev)), "HybridFusion fold (bias)")
+        return w, b.view(-1)
 
     def _drop_p(self) -> float:
         mods = [self.fusion_gate[2]] + [self.attn_layers[n].attn_dropout for n in self.modality_names]
@@ -98,8 +129,10 @@ class HybridFusion(nn.Module):
 
     @torch.no_grad()
     def run(self, zs, rows_per_clip, mask, B: int, passes: int, p: float, seed: int, clip0: int, t0: int,
-            want_info: bool = False):
-        """logits (B, passes, C) for per-modality embeddings zs[m] of (B * rows_per_clip[m], dim_m)."""
+            want_info: bool = False, folded_from=None):
+        """logits (B, passes, C) for per-modality embeddings zs[m] of (B * rows_per_clip[m], dim_m).
+        folded_from = (index, nn.Linear): zs[index] is the INPUT of that Linear (whose output is modality `index`'s
+        embedding); the Linear is folded into proj_layers[index] of a second handle."""
         dev = zs[0].device
         R = B * passes
         logits = torch.empty(B, passes, self.num_classes, device=dev, dtype=torch.float32)
@@ -112,7 +145,17 @@ class HybridFusion(nn.Module):
         if B > 0:
             arr, rpc = _z_args(zs, rows_per_clip)
             with torch.cuda.device(dev):
-                h = self._get_handle(dev)
+                if folded_from is not None:
+                    idx, lin = folded_from
+                    src = [lin.weight, lin.bias]
+                    key = Handle.key_of(self._params() + src)
+                    if self._handle_folded._h is None or self._handle_folded._key != key:
+                        w, b = self._fold_video_projection(idx, lin, dev)
+                        h = self._get_handle(dev, folded=(idx, lin.in_features, w, b, src))
+                    else:
+                        h = self._get_handle(dev, folded=(idx, lin.in_features, None, None, src))
+                else:
+                    h = self._get_handle(dev)
                 lib = _lib.load()
                 ws = _ws.get(lib.avhot_fusion_workspace_bytes(h, B, passes), dev)
                 _lib.check(lib.avhot_fusion_forward(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits), _lib.ptr(fw),

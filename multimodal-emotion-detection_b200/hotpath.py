@@ -58,6 +58,7 @@ class AVHotPath(nn.Module):
             self.fusion_head = ConcatHead(output_dim * len(self.modalities), hidden_dim, num_classes,
                                           len(self.modalities))                          # :81-85
         self.num_classes = num_classes
+        self.fold_video_projection = True     # tc + hybrid only; False keeps z_v materialised (A/B tests)
         self.set_precision(precision)
 
     def set_precision(self, precision: str) -> "AVHotPath":
@@ -99,7 +100,11 @@ class AVHotPath(nn.Module):
         venc = self.encoders["video"]
         hid = venc.hidden(video)                                                          # (B, F, H), pass-invariant
         p_enc = venc._drop_p() if stochastic else 0.0
-        z_v = venc.tail(hid, None, passes, p_enc, seed, clip0, t0)                        # (B, passes, out)
+        # tensor-core hybrid path: the frame encoder stops after its LayerNorm and its 256 -> 128 projection is folded
+        # into HybridFusion's proj_layers.video (two linear maps back to back), which is a tcgen05 GEMM anyway
+        fold = (self.head == "hybrid" and self.precision == "tc" and self.modalities[0] == "audio"
+                and venc.hidden_dim % 64 == 0 and venc.hidden_dim <= 256 and self.fold_video_projection)
+        z_v = venc.tail(hid, None, passes, p_enc, seed, clip0, t0, project=not fold)      # (B, passes, out | hidden)
         zs = [z_a, z_v.reshape(B * passes, -1)] if self.modalities[0] == "audio" else [z_v.reshape(B * passes, -1), z_a]
         rpc = [1, passes] if self.modalities[0] == "audio" else [passes, 1]
         if self.head == "hybrid":
@@ -110,7 +115,8 @@ class AVHotPath(nn.Module):
                 if mask_f.shape != (B, 2):
                     raise ValueError("mask must be (B, 2)")
             p_f = fm._drop_p() if stochastic else 0.0
-            logits, _, _, _ = fm.run(zs, rpc, mask_f, B, passes, p_f, seed, clip0, t0)
+            logits, _, _, _ = fm.run(zs, rpc, mask_f, B, passes, p_f, seed, clip0, t0,
+                                     folded_from=(1, venc.projection[1]) if fold else None)
         elif self.head in ("early", "late"):
             fm = self.fusion_model
             mask_f = None

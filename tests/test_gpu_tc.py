@@ -163,3 +163,41 @@ def test_tc_edge_batches(pkg, dev, world, B):
     assert rel_err(got[1].cpu().numpy(), ref[1].cpu().numpy()) <= 5e-2
     assert torch.isfinite(got[3]).all()
     assert (got[2] != ref[2]).sum().item() <= max(1, B // 100)
+
+
+def test_folded_video_projection(pkg, dev, world):
+    """The tensor-core hybrid path folds FrameEncoder.projection[1] into HybridFusion.proj_layers.video (two linear maps
+    back to back) and hands the fusion kernel the LayerNorm output instead of z_v: same masks, same result up to the
+    rounding of the folded fp16 weight; the unfolded pipeline stays selectable."""
+    m = make_model(pkg, dev, world).set_precision("tc")
+    B, T, clip0 = 300, 6, 4242
+    feats = {"audio": pkg.synth.synth_audio(B, clip0, SEED, dev), "video": pkg.synth.synth_video(B, clip0, SEED, dev)}
+    mask = pkg.synth.modality_mask(B, clip0, 0.05, SEED, dev)
+    pkg.MCDropoutUncertainty._set_dropout_train(m)
+    assert m.fold_video_projection
+    folded = m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=clip0)
+    m.fold_video_projection = False
+    plain = m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=clip0)
+    m.set_precision("fp32")
+    exact = m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=clip0)
+    e_fold, e_plain = rel_err(folded[0].cpu().numpy(), exact[0].cpu().numpy()), rel_err(plain[0].cpu().numpy(), exact[0].cpu().numpy())
+    print("folded vs fp32", e_fold, "unfolded vs fp32", e_plain, "folded vs unfolded",
+          rel_err(folded[0].cpu().numpy(), plain[0].cpu().numpy()))
+    assert e_fold <= TC_REL_LOGITS and e_plain <= TC_REL_LOGITS
+    assert rel_err(folded[1].cpu().numpy(), exact[1].cpu().numpy()) <= 5e-2
+    # the LayerNorm rows themselves (avhot_frame_tail_norm) against the oracle, one stochastic pass
+    venc = m.encoders["video"]
+    hid = venc.hidden(feats["video"][:4])
+    y = venc.tail(hid, None, 2, 0.1, SEED, clip0, 0, project=False)
+    z = venc.tail(hid, None, 2, 0.1, SEED, clip0, 0, project=True)
+    lin = venc.projection[1]
+    assert y.shape == (4, 2, 256)
+    want = torch.nn.functional.linear(y.double(), lin.weight.double(), lin.bias.double())
+    assert rel_err(z.cpu().numpy(), want.cpu().numpy()) <= 1e-5
+    # a changed projection weight rebuilds the folded handle
+    m.set_precision("tc")
+    m.fold_video_projection = True
+    with torch.no_grad():
+        lin.weight.mul_(1.5)
+    again = m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=clip0)
+    assert rel_err(again[0].cpu().numpy(), folded[0].cpu().numpy()) > 1e-3
