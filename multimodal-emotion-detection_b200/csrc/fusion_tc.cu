@@ -14,7 +14,15 @@
 // the 128-byte-swizzled K-major layout (two 64 KB buffers X and C), fp16 weights streamed by TMA through a
 // 4-stage ring, and two 256-column fp32 accumulators in TMEM.  The classifier is linear, so
 // logits = w_0 cls(H_0) + w_1 cls(H_1) + b and H_m never has to outlive its own epilogue.
-//   warp 0  TMA producer      warp 1  TMEM alloc + MMA issue      warps 2-5  epilogue (thread = row)
+//   warp 0  TMA producer      warp 1  TMEM alloc + MMA issue      warps 2-5 (6-9)  epilogue (thread = row)
+// NH = 2 (default): eight epilogue warps.  Warps w and w + 4 own the same 32 rows (the same TMEM lane quarter) and split
+// the accumulator COLUMNS in halves - heads {0, 1} / {2, 3}, 128 of the 256 LayerNorm columns, 64 of the 128 gate
+// units - exchanging only the LayerNorm partial sums (through a 4 KB shared-memory mailbox and a 64-thread named
+// barrier per warp pair) and, once per tile, the gate / classifier partial sums.  With one epilogue warp per scheduler
+// (NH = 1) the kernel issued 0.24 instructions per cycle per warp: every dependent instruction exposed its full
+// latency; two warps per scheduler nearly double the epilogue rate.
+#include <stdlib.h>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -24,7 +32,7 @@
 namespace avhot {
 namespace tc {
 
-constexpr int UB = 128, UD = 256, UST = 4, UTHREADS = 192;
+constexpr int UB = 128, UD = 256, UST = 4;
 // rows of the packed fp16 weight tensor (K = 256 columns each)
 constexpr int ROW_PROJ = 0, ROW_K0 = 256, ROW_V0 = 512, ROW_Q1 = 768, ROW_K1 = 1024, ROW_V1 = 1280, ROW_O0 = 1536,
               ROW_O1 = 1792, ROW_G0 = 2048, ROWS_ALL = 2176;
@@ -34,6 +42,7 @@ struct FusTcSmem {
   __half C[4][UB * 64];      // A operand: ctx_0 -> H_0 -> ctx_1 -> H_1
   __half wB[UST][128 * 64];  // weight ring, 128 output rows x 64 k per stage
   float vec[FUS_VEC_FLOATS];
+  float2 xch[2][2][UB];      // LayerNorm partial sums: [parity of the exchange][column half][row]
   uint64_t full[UST], empty[UST], m2e, e2m;
   uint32_t tmem_base;
 };
@@ -67,8 +76,11 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
-__global__ void __launch_bounds__(UTHREADS, 1)
+template <int NH>
+__global__ void __launch_bounds__(64 + 128 * NH, 1)
 fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
+  constexpr int UTHREADS = 64 + 128 * NH;
+  constexpr int HC = UD / NH;                           // accumulator columns per epilogue thread
   extern __shared__ unsigned char fus_tc_smem_raw[];
   FusTcSmem& sm = *reinterpret_cast<FusTcSmem*>((reinterpret_cast<uintptr_t>(fus_tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
@@ -81,7 +93,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < UST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     mbar_init(&sm.m2e, 1);
-    mbar_init(&sm.e2m, 4);                              // one arrival per epilogue warp
+    mbar_init(&sm.e2m, 4 * NH);                         // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -140,7 +152,21 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
     }
   } else {
     const int quarter = warp & 3;
+    const int half = NH == 1 ? 0 : (warp - 2) >> 2;     // column half of this warp (warps w and w + 4 share a quarter)
+    const int cb = half * HC;                           // first accumulator column of this thread
     const int r = quarter * 32 + lane;
+    uint32_t xn_ = 0;                                   // exchanges done so far (mailbox parity)
+    // total of a per-row partial (sum, sum of squares) over the column halves
+    auto row_total = [&](float& a, float& b) {
+      if (NH == 1) return;
+      sm.xch[xn_ & 1][half][r] = make_float2(a, b);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      const float2 o = sm.xch[xn_ & 1][half ^ 1][r];
+      // the same order of addition in both halves, so both see bit-identical statistics
+      a = half == 0 ? a + o.x : o.x + a;
+      b = half == 0 ? b + o.y : o.y + b;
+      ++xn_;
+    };
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
     const float* V = sm.vec;
     uint32_t op = 0;
@@ -168,7 +194,8 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
       // ---- E0: z_v row -> fp16 A operand ---------------------------------------------------------------------------
       {
         const float* zr = P.z_v + (size_t)((long long)b * P.rpc_v + (P.rpc_v == 1 ? 0 : t)) * P.dim_v;
-        for (int c = 0; c < P.dim_v; c += 8) {
+        const int ch = P.dim_v / NH;
+        for (int c = half * ch; c < (half + 1) * ch; c += 8) {
           const float4 u0 = __ldg(reinterpret_cast<const float4*>(zr + c));
           const float4 u1 = __ldg(reinterpret_cast<const float4*>(zr + c + 4));
           const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -183,18 +210,19 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
       {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < UD; c += 32) {
+        for (int c = cb; c < cb + HC; c += 32) {
           uint32_t a[32];
           tmem_ld32(tl + (uint32_t)c, a);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(a[j]) + V[VEC_PROJ_B + c + j]; s1 += x; s2 = fmaf(x, x, s2); }
         }
+        row_total(s1, s2);
         const float m1 = s1 * (1.f / UD);
         const float rstd1 = 1.f / sqrtf(fmaxf(s2 * (1.f / UD) - m1 * m1, 0.f) + 1e-5f);
         s1 = 0.f; s2 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < UD; c += 32) {
+        for (int c = cb; c < cb + HC; c += 32) {
           uint32_t a[32];
           tmem_ld32(tl + (uint32_t)c, a);
           tmem_ld_wait();
@@ -205,11 +233,12 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             s1 += z; s2 = fmaf(z, z, s2);
           }
         }
+        row_total(s1, s2);
         zmean = s1 * (1.f / UD);
         zstd = sqrtf(fmaxf(s2 * (1.f / UD) - zmean * zmean, 0.f) + 1e-5f);
         const float rstd2 = 1.f / zstd;
 #pragma unroll 1
-        for (int c = 0; c < UD; c += 32) {
+        for (int c = cb; c < cb + HC; c += 32) {
           uint32_t a[32];
           tmem_ld32(tl + (uint32_t)c, a);
           tmem_ld_wait();
@@ -230,15 +259,17 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
       // ---- the two attention layers --------------------------------------------------------------------------------
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        float aa[4], av[4];                                               // attention weights per head: audio / video key
+        constexpr int HPT = 4 / NH;                                       // heads per thread: heads hb .. hb + HPT - 1
+        const int hb = half * HPT;
+        float aa[HPT], av[HPT];                                           // attention weights per head: audio / video key
         if (layer == 0) {
           from_mma();                                                     // D_a = K_0v, D_b = V_0v
           // scores: query = audio token (per clip), keys = audio token (per clip) and video token (this row)
 #pragma unroll 1
-          for (int hh = 0; hh < 4; ++hh) {
+          for (int hh = 0; hh < HPT; ++hh) {
             float sa = 0.f, sv = 0.f;
 #pragma unroll 1
-            for (int c = hh * 64; c < hh * 64 + 64; c += 32) {
+            for (int c = (hb + hh) * 64; c < (hb + hh) * 64 + 64; c += 32) {
               uint32_t a[32];
               tmem_ld32(tl + (uint32_t)c, a);
               tmem_ld_wait();
@@ -254,10 +285,10 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
         } else {
           from_mma();                                                     // D_a = Q_1, D_b = K_1v
 #pragma unroll 1
-          for (int hh = 0; hh < 4; ++hh) {
+          for (int hh = 0; hh < HPT; ++hh) {
             float sa = 0.f, sv = 0.f;
 #pragma unroll 1
-            for (int c = hh * 64; c < hh * 64 + 64; c += 32) {
+            for (int c = (hb + hh) * 64; c < (hb + hh) * 64 + 64; c += 32) {
               uint32_t a[32], k[32];
               tmem_ld32(tl + (uint32_t)c, a);
               tmem_ld32(tl + 256u + (uint32_t)c, k);
@@ -274,10 +305,12 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
         }
         // softmax over the two keys, masks, dropout (src/attention.py:112-130)
         {
-          const Philox4 w0 = philox4x32_10(0u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
-          const Philox4 w1 = philox4x32_10(1u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
+          // element (head, key) = 2 head + key of the (4, 1, 2) mask: block 0 = heads 0, 1; block 1 = heads 2, 3
+          const Philox4 w0 = philox4x32_10((uint32_t)(hb >> 1), gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
+          Philox4 w1 = w0;
+          if (NH == 1) w1 = philox4x32_10(1u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
 #pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
+          for (int hh = 0; hh < HPT; ++hh) {
             float s0 = aa[hh] * 0.125f, s1 = av[hh] * 0.125f;
             if (inv0) s0 = -1e4f;
             if (inv1) s1 = -1e4f;
@@ -303,11 +336,11 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           const uint32_t vcol = layer == 0 ? 256u : 0u;
           const int vb = layer == 0 ? VEC_BV0 : VEC_BV1, vslot = layer == 0 ? 3 : 5;
 #pragma unroll 1
-          for (int c = 0; c < UD; c += 32) {
+          for (int c = cb; c < cb + HC; c += 32) {
             uint32_t a[32];
             tmem_ld32(tl + vcol + (uint32_t)c, a);
             tmem_ld_wait();
-            const int hh = c >> 6;
+            const int hh = (c >> 6) - hb;
             float ctx[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -343,7 +376,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             }
           };
 #pragma unroll 1
-          for (int c = 0; c < UD; c += 32) {
+          for (int c = cb; c < cb + HC; c += 32) {
             uint32_t a[32];
             float res[32];
             tmem_ld32(tl + ocol + (uint32_t)c, a);
@@ -352,13 +385,14 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(a[j]) + V[ob + c + j] + res[j]; s1 += x; s2 = fmaf(x, x, s2); }
           }
+          row_total(s1, s2);
           const float mean = s1 * (1.f / UD);
           const float rstd = 1.f / sqrtf(fmaxf(s2 * (1.f / UD) - mean * mean, 0.f) + 1e-5f);
           float cls[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) cls[q] = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < UD; c += 32) {
+          for (int c = cb; c < cb + HC; c += 32) {
             uint32_t a[32];
             float res[32], y[32];
             tmem_ld32(tl + ocol + (uint32_t)c, a);
@@ -389,7 +423,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
         {
           float sc = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
+          for (int c = half * (128 / NH); c < (half + 1) * (128 / NH); c += 32) {
             uint32_t a[32];
             tmem_ld32(tl + (uint32_t)c, a);
             tmem_ld_wait();
@@ -409,13 +443,31 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
               }
             }
           }
-          if (layer == 0) score0 = sc + V[VEC_G3_B]; else score1 = sc + V[VEC_G3_B];
+          if (layer == 0) score0 = sc; else score1 = sc;                  // + gate bias after the halves are combined
         }
         if (layer == 0) to_mma();                                         // D_a drained -> G5 (Q_1 | K_1v)
       }
 
       // ---- modality softmax, finite guard, renormalise, logits (src/fusion.py:513-522) --------------------------------
-      {
+      if (NH == 2) {
+        // gate scores and classifier partial sums of the upper column half -> the lower half's thread of the same row,
+        // through the C operand buffer (free: G8, its last reader, has completed; nobody writes it before the next
+        // tile's G1 has been seen by every epilogue warp)
+        float* mail = reinterpret_cast<float*>(&sm.C[0][0]) + r * 20;
+        if (half == 1) {
+          mail[0] = score0; mail[1] = score1;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { mail[2 + q] = cls0[q]; mail[10 + q] = cls1[q]; }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (half == 0) {
+          score0 += mail[0]; score1 += mail[1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { cls0[q] += mail[2 + q]; cls1[q] += mail[10 + q]; }
+        }
+      }
+      if (half == 0) {
+        score0 += V[VEC_G3_B]; score1 += V[VEC_G3_B];
         float s0 = inv0 ? -1e4f : score0, s1 = inv1 ? -1e4f : score1;
         const float mx = fmaxf(s0, s1);
         const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
@@ -463,9 +515,16 @@ int fusion_tc_forward(const void* packed_w, const FusTcParams& P, cudaStream_t s
   const int n_tiles = (int)((rows + UB - 1) / UB);
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   const int smem = (int)sizeof(FusTcSmem) + 1024;
-  AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // AVHOT_FUSION_HALVES=1 selects the four-epilogue-warp form (thread = whole row) for A/B runs and tests
+  static const int halves = [] { const char* e = getenv("AVHOT_FUSION_HALVES"); return e && e[0] == '1' ? 1 : 2; }();
   ProfScope prof("fusion_tc", s);
-  fusion_tc_kernel<<<grid, UTHREADS, smem, s>>>(tmW, P);
+  if (halves == 2) {
+    AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fusion_tc_kernel<2><<<grid, 64 + 128 * 2, smem, s>>>(tmW, P);
+  } else {
+    AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fusion_tc_kernel<1><<<grid, 64 + 128, smem, s>>>(tmW, P);
+  }
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }

@@ -193,7 +193,7 @@ def test_folded_video_projection(pkg, dev, world):
     lin = venc.projection[1]
     assert y.shape == (4, 2, 256)
     want = torch.nn.functional.linear(y.double(), lin.weight.double(), lin.bias.double())
-    assert rel_err(z.cpu().numpy(), want.cpu().numpy()) <= 1e-5
+    assert rel_err(z.cpu().numpy(), want.detach().cpu().numpy()) <= 1e-5
     # a changed projection weight rebuilds the folded handle
     m.set_precision("tc")
     m.fold_video_projection = True
@@ -201,3 +201,38 @@ def test_folded_video_projection(pkg, dev, world):
         lin.weight.mul_(1.5)
     again = m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=clip0)
     assert rel_err(again[0].cpu().numpy(), folded[0].cpu().numpy()) > 1e-3
+
+
+def test_fusion_tc_column_halves_equal_whole_rows(pkg, dev, world, tmp_path):
+    """The eight-epilogue-warp fusion kernel (two warps share a row and split its columns) against the four-warp form
+    (thread = whole row, AVHOT_FUSION_HALVES=1, read once per process -> child process): same masks, same arithmetic
+    up to the order in which the two halves of a LayerNorm / classifier sum are added."""
+    import os
+    import subprocess
+    import sys
+    fm = make_model(pkg, dev, world).set_precision("tc").fusion_model
+    torch.save(fm.state_dict(), tmp_path / "fm.pt")
+    rng = np.random.default_rng(21)
+    B, T = 37, 9                                           # 333 rows: two full tiles and a partial one
+    za = rng.normal(size=(B, 128)).astype(np.float32)
+    zv = rng.normal(size=(B * T, 128)).astype(np.float32)
+    mask = (rng.uniform(size=(B, 2)) > 0.2).astype(np.float32)
+    np.save(tmp_path / "za.npy", za); np.save(tmp_path / "zv.npy", zv); np.save(tmp_path / "mask.npy", mask)
+    code = (
+        "import sys, numpy as np, torch\n"
+        "import multimodal_emotion_detection_b200 as pkg\n"
+        "d, out = sys.argv[1], sys.argv[2]\n"
+        "fm = pkg.build_fusion_model('hybrid', {'audio': 128, 'video': 128}, 8, hidden_dim=256, num_heads=4, dropout=0.3)\n"
+        "fm.load_state_dict(torch.load(d + '/fm.pt'))\n"
+        "fm = fm.to('cuda:0').eval(); fm.precision = pkg._lib.PREC_TC\n"
+        "L = lambda n: torch.from_numpy(np.load(d + '/' + n + '.npy')).to('cuda:0')\n"
+        "lg = fm.run([L('za'), L('zv')], [1, 9], L('mask'), 37, 9, 0.3, 42, 777, 0)[0]\n"
+        "np.save(d + '/' + out, lg.cpu().numpy())\n")
+    for halves, out in (("1", "rows.npy"), ("2", "halves.npy")):
+        env = dict(os.environ, AVHOT_FUSION_HALVES=halves, PYTHONPATH=os.pathsep.join(sys.path))
+        subprocess.run([sys.executable, "-c", code, str(tmp_path), out], check=True, env=env, timeout=300)
+    rows, halves = np.load(tmp_path / "rows.npy"), np.load(tmp_path / "halves.npy")
+    assert rows.shape == (B, T, 8) and np.isfinite(rows).all()
+    err = rel_err(halves, rows)
+    print("fusion_tc halves vs rows", err)
+    assert err <= 2e-5
