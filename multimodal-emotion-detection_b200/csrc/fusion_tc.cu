@@ -42,7 +42,7 @@ struct FusTcSmem {
   __half C[4][UB * 64];      // A operand: ctx_0 -> H_0 -> ctx_1 -> H_1
   __half wB[UST][128 * 64];  // weight ring, 128 output rows x 64 k per stage
   float vec[FUS_VEC_FLOATS];
-  float2 xch[2][2][UB];      // LayerNorm partial sums: [parity of the exchange][column half][row]
+  float2 xch[2][4][UB];      // LayerNorm partial sums: [parity of the exchange][column part][row]
   uint64_t full[UST], empty[UST], m2e, e2m;
   uint32_t tmem_base;
 };
@@ -160,11 +160,12 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
     auto row_total = [&](float& a, float& b) {
       if (NH == 1) return;
       sm.xch[xn_ & 1][half][r] = make_float2(a, b);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      const float2 o = sm.xch[xn_ & 1][half ^ 1][r];
-      // the same order of addition in both halves, so both see bit-identical statistics
-      a = half == 0 ? a + o.x : o.x + a;
-      b = half == 0 ? b + o.y : o.y + b;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NH) : "memory");
+      // the same order of addition in every part, so all see bit-identical statistics
+      float2 t = sm.xch[xn_ & 1][0][r];
+#pragma unroll
+      for (int h2 = 1; h2 < NH; ++h2) { const float2 o = sm.xch[xn_ & 1][h2][r]; t.x += o.x; t.y += o.y; }
+      a = t.x; b = t.y;
       ++xn_;
     };
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -321,8 +322,8 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             if (inv0 && inv1) { a0 = 0.f; a1 = 0.f; }
             if (P.ds.thr != 0u) {
               const Philox4& w = hh < 2 ? w0 : w1;
-              a0 = philox_word(w, (uint32_t)((hh & 1) * 2)) >= P.ds.thr ? a0 * P.ds.scale : 0.f;
-              a1 = philox_word(w, (uint32_t)((hh & 1) * 2 + 1)) >= P.ds.thr ? a1 * P.ds.scale : 0.f;
+              a0 = philox_word(w, (uint32_t)(((hb + hh) & 1) * 2)) >= P.ds.thr ? a0 * P.ds.scale : 0.f;
+              a1 = philox_word(w, (uint32_t)(((hb + hh) & 1) * 2 + 1)) >= P.ds.thr ? a1 * P.ds.scale : 0.f;
             }
             aa[hh] = a0; av[hh] = a1;
           }
@@ -449,21 +450,26 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
       }
 
       // ---- modality softmax, finite guard, renormalise, logits (src/fusion.py:513-522) --------------------------------
-      if (NH == 2) {
+      if (NH > 1) {
         // gate scores and classifier partial sums of the upper column half -> the lower half's thread of the same row,
         // through the C operand buffer (free: G8, its last reader, has completed; nobody writes it before the next
         // tile's G1 has been seen by every epilogue warp)
-        float* mail = reinterpret_cast<float*>(&sm.C[0][0]) + r * 20;
-        if (half == 1) {
-          mail[0] = score0; mail[1] = score1;
+        float* mail = reinterpret_cast<float*>(&sm.C[0][0]) + r * (20 * (NH - 1));
+        if (half != 0) {
+          float* mine = mail + 20 * (half - 1);
+          mine[0] = score0; mine[1] = score1;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { mail[2 + q] = cls0[q]; mail[10 + q] = cls1[q]; }
+          for (int q = 0; q < 8; ++q) { mine[2 + q] = cls0[q]; mine[10 + q] = cls1[q]; }
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NH) : "memory");
         if (half == 0) {
-          score0 += mail[0]; score1 += mail[1];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { cls0[q] += mail[2 + q]; cls1[q] += mail[10 + q]; }
+          for (int h2 = 1; h2 < NH; ++h2) {
+            const float* o = mail + 20 * (h2 - 1);
+            score0 += o[0]; score1 += o[1];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { cls0[q] += o[2 + q]; cls1[q] += o[10 + q]; }
+          }
         }
       }
       if (half == 0) {
@@ -516,9 +522,15 @@ int fusion_tc_forward(const void* packed_w, const FusTcParams& P, cudaStream_t s
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   const int smem = (int)sizeof(FusTcSmem) + 1024;
   // AVHOT_FUSION_HALVES=1 selects the four-epilogue-warp form (thread = whole row) for A/B runs and tests
-  static const int halves = [] { const char* e = getenv("AVHOT_FUSION_HALVES"); return e && e[0] == '1' ? 1 : 2; }();
+  static const int halves = [] {
+    const char* e = getenv("AVHOT_FUSION_HALVES");
+    return e && e[0] == '1' ? 1 : (e && e[0] == '4' ? 4 : 2);
+  }();
   ProfScope prof("fusion_tc", s);
-  if (halves == 2) {
+  if (halves == 4) {
+    AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fusion_tc_kernel<4><<<grid, 64 + 128 * 4, smem, s>>>(tmW, P);
+  } else if (halves == 2) {
     AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     fusion_tc_kernel<2><<<grid, 64 + 128 * 2, smem, s>>>(tmW, P);
   } else {

@@ -206,7 +206,8 @@ def test_folded_video_projection(pkg, dev, world):
 def test_fusion_tc_column_halves_equal_whole_rows(pkg, dev, world, tmp_path):
     """The eight-epilogue-warp fusion kernel (two warps share a row and split its columns) against the four-warp form
     (thread = whole row, AVHOT_FUSION_HALVES=1, read once per process -> child process): same masks, same arithmetic
-    up to the order in which the two halves of a LayerNorm / classifier sum are added."""
+    up to the order in which the parts of a LayerNorm / classifier sum are added (which can flip the last bit of an
+    fp16 operand of the next GEMM: 5e-4 relative on one element)."""
     import os
     import subprocess
     import sys
@@ -228,11 +229,12 @@ def test_fusion_tc_column_halves_equal_whole_rows(pkg, dev, world, tmp_path):
         "L = lambda n: torch.from_numpy(np.load(d + '/' + n + '.npy')).to('cuda:0')\n"
         "lg = fm.run([L('za'), L('zv')], [1, 9], L('mask'), 37, 9, 0.3, 42, 777, 0)[0]\n"
         "np.save(d + '/' + out, lg.cpu().numpy())\n")
-    for halves, out in (("1", "rows.npy"), ("2", "halves.npy")):
+    for halves, out in (("1", "rows.npy"), ("2", "halves.npy"), ("4", "quarters.npy")):
         env = dict(os.environ, AVHOT_FUSION_HALVES=halves, PYTHONPATH=os.pathsep.join(sys.path))
         subprocess.run([sys.executable, "-c", code, str(tmp_path), out], check=True, env=env, timeout=300)
-    rows, halves = np.load(tmp_path / "rows.npy"), np.load(tmp_path / "halves.npy")
+    rows = np.load(tmp_path / "rows.npy")
     assert rows.shape == (B, T, 8) and np.isfinite(rows).all()
-    err = rel_err(halves, rows)
-    print("fusion_tc halves vs rows", err)
-    assert err <= 2e-5
+    for name in ("halves.npy", "quarters.npy"):
+        err = rel_err(np.load(tmp_path / name), rows)
+        print("fusion_tc", name, "vs rows", err)
+        assert err <= 3e-4
