@@ -75,23 +75,34 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(hb + (size_t)f * FH + c0));
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(hb + (size_t)f * FH + c1));
         float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (drop) {   // site FRAME_MLP (dense: 16-bit draws): element e = f*H + col, block e >> 3 = f*32 + lane
-          const Philox4 r = philox4x32_10((uint32_t)(f * 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds.k0, ds.k1);
+        // site FRAME_MLP (dense: 16-bit draws): element e = f*H + col, block e >> 3 = f*32 + lane.  Dropped elements
+        // become 0 here; the common factor 1 / (1 - p) of the kept ones is applied once to the score and once to the
+        // pooled row instead of to each of the F * H elements.
+        if (drop) {
+          const Philox4 r = philox4x32_10_rk((uint32_t)(f * 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) x[q] = philox_half(r, (uint32_t)q) >= thr16 ? x[q] * ds.scale : 0.f;
+          for (int q = 0; q < 8; ++q) x[q] = philox_half(r, (uint32_t)q) >= thr16 ? x[q] : 0.f;
         }
         float s = x[0] * aw0.x + x[1] * aw0.y + x[2] * aw0.z + x[3] * aw0.w +
                   x[4] * aw1.x + x[5] * aw1.y + x[6] * aw1.z + x[7] * aw1.w;
-        s = warp_sum(s) + ab;
+        s = fmaf(warp_sum(s), ds.scale, ab);
         if (valid && !valid[(size_t)b * F + f]) s = -FLT_MAX;       // masked_fill(finfo.min), :322-324
-        const float mn = fmaxf(m, s);
-        const float corr = expf(m - mn), e = expf(s - mn);           // exp(-inf) = 0 on the first frame
-        denom = denom * corr + e;
+        // online softmax; the running maximum changes ~log(F) times, so the rescale of the pooled row sits in the
+        // (warp-uniform) branch that handles a new maximum
+        if (s > m) {
+          const float corr = __expf(m - s);                           // exp(-inf) = 0 on the first frame
+          denom = fmaf(denom, corr, 1.f);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) pooled[q] = pooled[q] * corr + e * x[q];
-        m = mn;
+          for (int q = 0; q < 8; ++q) pooled[q] = fmaf(pooled[q], corr, x[q]);
+          m = s;
+        } else {
+          const float e = __expf(s - m);
+          denom += e;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pooled[q] = fmaf(e, x[q], pooled[q]);
+        }
       }
-      const float inv = 1.f / denom;
+      const float inv = ds.scale / denom;
 #pragma unroll
       for (int q = 0; q < 8; ++q) pooled[q] *= inv;
       if (drop) {     // site FRAME_POOL (32-bit draws): element e = col, block e >> 2
