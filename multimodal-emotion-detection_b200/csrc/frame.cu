@@ -106,8 +106,8 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
 #pragma unroll
       for (int q = 0; q < 8; ++q) pooled[q] *= inv;
       if (drop) {     // site FRAME_POOL (32-bit draws): element e = col, block e >> 2
-        const Philox4 r0 = philox4x32_10((uint32_t)(2 * lane), g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
-        const Philox4 r1 = philox4x32_10((uint32_t)(2 * lane + 1), g, pass, AVHOT_SITE_FRAME_POOL, ds.k0, ds.k1);
+        const Philox4 r0 = philox4x32_10_rk((uint32_t)(2 * lane), g, pass, AVHOT_SITE_FRAME_POOL, ds);
+        const Philox4 r1 = philox4x32_10_rk((uint32_t)(2 * lane + 1), g, pass, AVHOT_SITE_FRAME_POOL, ds);
         const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) pooled[q] = w[q] >= ds.thr ? pooled[q] * ds.scale : 0.f;

@@ -270,9 +270,29 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   // fetched into registers before the frame loop of the current one, so their HBM latency hides behind the FFTs
   // (ncu: a quarter of all stall samples sat on the pre-emphasis FMA waiting for these loads).
   constexpr int SPT = (SEG + FE_WARPS * 32 - 1) / (FE_WARPS * 32);   // samples per thread
+  constexpr int QPT = (SEG / 4 + FE_WARPS * 32 - 1) / (FE_WARPS * 32);   // float4 groups per thread (SEG % 4 == 0)
+  static_assert(SEG % 4 == 0 && QPT * 4 <= SPT, "segment staged in float4 groups");
   float cur[SPT], prv[SPT];
+  bool vec_tile = false;   // how the registers were filled (block-uniform)
+  // Interior tiles (no reflection, 16-byte aligned): one 128-bit load per four samples plus the one sample before the
+  // group - 6 loads per thread instead of 24, no reflection arithmetic.  cur[4 j + k] = sample 4 (tid + 256 j) + k.
+  const bool can_vec = (n_samples & 3) == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
   auto fetch = [&](int tile_t0) {
     const int q0 = tile_t0 * HOP;
+    const int base = q0 - N_FFT / 2;
+    vec_tile = can_vec && base >= 4 && base + SEG <= n_samples;
+    if (vec_tile) {
+#pragma unroll
+      for (int j = 0; j < QPT; ++j) {
+        const int i4 = tid + j * (FE_WARPS * 32);
+        if (i4 < SEG / 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(y + base) + i4);
+          cur[4 * j] = v.x; cur[4 * j + 1] = v.y; cur[4 * j + 2] = v.z; cur[4 * j + 3] = v.w;
+          prv[4 * j] = __ldg(y + base + 4 * i4 - 1);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       const int i = tid + j * (FE_WARPS * 32);
@@ -287,6 +307,17 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = (blockIdx.x + 1) * tiles_per_cta;
   // pre-emphasised, reflect-padded segment of a tile: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
   auto stage_segment = [&]() {
+    if (vec_tile) {
+#pragma unroll
+      for (int j = 0; j < QPT; ++j) {
+        const int i4 = tid + j * (FE_WARPS * 32);
+        if (i4 < SEG / 4)
+          *reinterpret_cast<float4*>(s_seg + 4 * i4) =
+              make_float4(fmaf(-0.97f, prv[4 * j], cur[4 * j]), fmaf(-0.97f, cur[4 * j], cur[4 * j + 1]),
+                          fmaf(-0.97f, cur[4 * j + 1], cur[4 * j + 2]), fmaf(-0.97f, cur[4 * j + 2], cur[4 * j + 3]));
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       const int i = tid + j * (FE_WARPS * 32);

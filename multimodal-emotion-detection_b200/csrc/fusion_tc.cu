@@ -307,9 +307,9 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
         // softmax over the two keys, masks, dropout (src/attention.py:112-130)
         {
           // element (head, key) = 2 head + key of the (4, 1, 2) mask: block 0 = heads 0, 1; block 1 = heads 2, 3
-          const Philox4 w0 = philox4x32_10((uint32_t)(hb >> 1), gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
+          const Philox4 w0 = philox4x32_10_rk((uint32_t)(hb >> 1), gclip, pass, AVHOT_SITE_ATTN + layer, P.ds);
           Philox4 w1 = w0;
-          if (NH == 1) w1 = philox4x32_10(1u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds.k0, P.ds.k1);
+          if (NH == 1) w1 = philox4x32_10_rk(1u, gclip, pass, AVHOT_SITE_ATTN + layer, P.ds);
 #pragma unroll
           for (int hh = 0; hh < HPT; ++hh) {
             float s0 = aa[hh] * 0.125f, s1 = av[hh] * 0.125f;
@@ -432,8 +432,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             for (int j4 = 0; j4 < 32; j4 += 4) {
               uint32_t wd[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
               if (P.ds.thr != 0u) {
-                const Philox4 w = philox4x32_10((uint32_t)((layer * 128 + c + j4) >> 2), gclip, pass, AVHOT_SITE_GATE,
-                                                P.ds.k0, P.ds.k1);
+                const Philox4 w = philox4x32_10_rk((uint32_t)((layer * 128 + c + j4) >> 2), gclip, pass, AVHOT_SITE_GATE, P.ds);
                 wd[0] = w.x; wd[1] = w.y; wd[2] = w.z; wd[3] = w.w;
               }
 #pragma unroll
