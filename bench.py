@@ -175,6 +175,9 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     import multimodal_emotion_detection_b200 as pkg
@@ -281,6 +284,8 @@ def run_b200_arm(args):
                         "algorithmic_bytes_per_step": nbytes})
         if nflops:
             ent.update({"tflops": nflops / sec / 1e12, "tensor_frac": nflops / sec / 1e12 / peaks["tf_sustained"]})
+        if nbytes and nflops:       # a kernel that streams and contracts: the roofline it sits closer to is its bound
+            ent["bound"] = "tensor" if ent["tensor_frac"] > ent["hbm_frac"] else "hbm"
         extra[name] = ent
     # the dominant kernel = the one with the most device time per step among the stages with a stated roofline
     roofline = None
