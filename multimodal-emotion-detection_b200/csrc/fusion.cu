@@ -1031,7 +1031,7 @@ extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host
         FusTcParams Q;
         Q.z_v = P.z[1]; Q.rpc_v = P.rpc[1]; Q.dim_v = P.dim[1];
         Q.clipbuf = clipbuf; Q.mask = mask; Q.logits = logits;
-        Q.B = B; Q.T = T; Q.C = h->C; Q.vec = h->tc_vec; Q.ds = P.ds;
+        Q.B = B; Q.T = T; Q.C = h->C; Q.vec = h->tc_vec; Q.ds = P.ds; Q.trace = nullptr;
         return fusion_tc_forward(h->tc_w, Q, s);
       }
       const long long grid2 = (rows + HRT - 1) / HRT;

@@ -21,6 +21,7 @@
 // barrier per warp pair) and, once per tile, the gate / classifier partial sums.  With one epilogue warp per scheduler
 // (NH = 1) the kernel issued 0.24 instructions per cycle per warp: every dependent instruction exposed its full
 // latency; two warps per scheduler nearly double the epilogue rate.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <cuda_fp16.h>
@@ -82,7 +83,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
   constexpr int UTHREADS = 64 + 128 * NH;
   constexpr int HC = UD / NH;                           // accumulator columns per epilogue thread
   extern __shared__ unsigned char fus_tc_smem_raw[];
-  FusTcSmem& sm = *reinterpret_cast<FusTcSmem*>((reinterpret_cast<uintptr_t>(fus_tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  FusTcSmem& sm = *reinterpret_cast<FusTcSmem*>(fus_tc_smem_raw + ((1024u - (smem_u32(fus_tc_smem_raw) & 1023u)) & 1023u));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const long long n_rows = (long long)P.B * P.T;
   const int n_tiles = (int)((n_rows + UB - 1) / UB);
@@ -182,31 +183,54 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
       ++op;
       tc_fence_after();
     };
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // debug trace: the first epilogue thread of CTA 0 stamps clock64() at every phase boundary of its third tile
+    const bool probe = P.trace && blockIdx.x == 0 && warp == 2 && lane == 0;
+    int tile_no = 0, ev = 0;
+    auto TR = [&]() { if (probe && tile_no == 2 && ev < 64) P.trace[ev++] = clock64(); };
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
       long long row = (long long)tile * UB + r;
+      TR();                                                               // 0: tile start
       const bool live = row < n_rows;
       if (!live) row = n_rows - 1;
-      const int b = (int)(row / P.T), t = (int)(row % P.T);
+      const int b = (int)((uint32_t)row / (uint32_t)P.T), t = (int)((uint32_t)row - (uint32_t)b * (uint32_t)P.T);
       const uint32_t gclip = (uint32_t)(P.ds.clip0 + (uint64_t)b), pass = P.ds.t0 + (uint32_t)t;
       const float* cbuf = P.clipbuf + (size_t)b * (6 * UD);
       const bool inv0 = P.mask ? (__ldg(P.mask + (size_t)b * 2) <= 0.f) : false;
       const bool inv1 = P.mask ? (__ldg(P.mask + (size_t)b * 2 + 1) <= 0.f) : false;
 
-      // ---- E0: z_v row -> fp16 A operand ---------------------------------------------------------------------------
+      // ---- E0: the tile's z_v rows -> fp16 A operand ----------------------------------------------------------------
+      // A cooperative, coalesced copy: the 4 NH epilogue warps take the tile's rows round robin, lane l converts floats
+      // [8 l, 8 l + 8) of a row (a warp reads a whole 1 KB row with two instructions) and writes the 16-byte chunk where
+      // the UMMA layout wants it.  (Thread = row loads - 32 different lines per instruction - cost 11 k of a tile's 124 k
+      // cycles in the r4l clock trace.)  Only the MMA reads these rows, and it waits for every warp's to_mma().
       {
-        const float* zr = P.z_v + (size_t)((long long)b * P.rpc_v + (P.rpc_v == 1 ? 0 : t)) * P.dim_v;
-        const int ch = P.dim_v / NH;
-        for (int c = half * ch; c < (half + 1) * ch; c += 8) {
-          const float4 u0 = __ldg(reinterpret_cast<const float4*>(zr + c));
-          const float4 u1 = __ldg(reinterpret_cast<const float4*>(zr + c + 4));
-          const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-          *a_chunk(&sm.X[0][0], r, c) = pack8(v);
+        const int ew = warp - 2;
+        if (8 * lane < P.dim_v) {
+#pragma unroll 4
+          for (int rr = ew; rr < UB; rr += 4 * NH) {
+            // 32-bit row arithmetic (fusion_tc_forward checks B * T < 2^31): a 64-bit division per row cost more than
+            // the loads themselves
+            uint32_t grow = (uint32_t)tile * UB + (uint32_t)rr;
+            if (grow >= (uint32_t)n_rows) grow = (uint32_t)n_rows - 1u;
+            const uint32_t gb = grow / (uint32_t)P.T, gt = grow - gb * (uint32_t)P.T;
+            const float* zr = P.z_v + ((size_t)gb * P.rpc_v + (P.rpc_v == 1 ? 0u : gt)) * P.dim_v + 8 * lane;
+            // the same row of this CTA's next tile -> L2 (rows of consecutive (clip, pass) are consecutive in memory);
+            // one request per 128-byte line
+            if (P.rpc_v != 1 && (lane & 3) == 0 && (long long)grow + (long long)gridDim.x * UB < n_rows)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(zr + (size_t)gridDim.x * UB * P.dim_v));
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(zr));
+            const float4 u1 = __ldg(reinterpret_cast<const float4*>(zr + 4));
+            const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            *a_chunk(&sm.X[0][0], rr, 8 * lane) = pack8(v);
+          }
         }
       }
+      TR();                                                               // 1: E0 done
       to_mma();                                                           // -> G1
 
       // ---- E1: Z_v = pre_ln(proj), x^_v = (Z_v - mean) / std -> X ----------------------------------------------------
       from_mma();
+      TR();                                                               // 2: G1 arrived
       float zmean, zstd;
       {
         float s1 = 0.f, s2 = 0.f;
@@ -254,6 +278,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           for (int j = 0; j < 32; j += 8) *a_chunk(&sm.X[0][0], r, c + j) = pack8(&xn[j]);
         }
       }
+      TR();                                                               // 3: E1 done
       to_mma();                                                           // -> G2 (K_0v | V_0v)
 
       float cls0[8], cls1[8], score0 = 0.f, score1 = 0.f;
@@ -265,6 +290,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
         float aa[HPT], av[HPT];                                           // attention weights per head: audio / video key
         if (layer == 0) {
           from_mma();                                                     // D_a = K_0v, D_b = V_0v
+          TR();                                                           // 4: G2 arrived
           // scores: query = audio token (per clip), keys = audio token (per clip) and video token (this row)
 #pragma unroll 1
           for (int hh = 0; hh < HPT; ++hh) {
@@ -285,6 +311,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           }
         } else {
           from_mma();                                                     // D_a = Q_1, D_b = K_1v
+          TR();                                                           // 12: G5 arrived
 #pragma unroll 1
           for (int hh = 0; hh < HPT; ++hh) {
             float sa = 0.f, sv = 0.f;
@@ -328,9 +355,11 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             aa[hh] = a0; av[hh] = a1;
           }
         }
+        TR();                                                             // 5 / 13: scores + softmax done
         if (layer == 1) {
           to_mma();                                                       // D_a, D_b drained -> G6 (V_1v -> D_a)
           from_mma();
+          TR();                                                           // 14: G6 arrived
         }
         // context = a_a V_a (per clip) + a_v V_v (this row) -> C     (layer 0: V_0v is in D_b; layer 1: V_1v in D_a)
         {
@@ -350,10 +379,12 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             for (int j = 0; j < 32; j += 8) *a_chunk(&sm.C[0][0], r, c + j) = pack8(&ctx[j]);
           }
         }
+        TR();                                                             // 6 / 15: context written
         to_mma();                                                         // -> G3 / G7 (out_proj)
 
         // out_proj + residual -> post_ln -> H: classifier partial sums, fp16 H -> C for the gate GEMM
         from_mma();
+        TR();                                                             // 7 / 16: G3 / G7 arrived
         {
           const uint32_t ocol = layer == 0 ? 0u : 256u;
           const int ob = layer == 0 ? VEC_BO0 : VEC_BO1;
@@ -417,10 +448,12 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             for (int q = 0; q < 8; ++q) cls1[q] = cls[q];
           }
         }
+        TR();                                                             // 8 / 17: post_ln + classifier sums done
         to_mma();                                                         // -> G4 / G8 (gate)
 
         // gate: ReLU -> dropout -> Linear(128 -> 1)   (src/fusion.py:445-450)
         from_mma();
+        TR();                                                             // 9 / 18: G4 / G8 arrived
         {
           float sc = 0.f;
 #pragma unroll 1
@@ -445,7 +478,8 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           }
           if (layer == 0) score0 = sc; else score1 = sc;                  // + gate bias after the halves are combined
         }
-        if (layer == 0) to_mma();                                         // D_a drained -> G5 (Q_1 | K_1v)
+        TR();                                                             // 10 / 19: gate done
+        if (layer == 0) { to_mma(); TR(); }                               // D_a drained -> G5 (Q_1 | K_1v); 11
       }
 
       // ---- modality softmax, finite guard, renormalise, logits (src/fusion.py:513-522) --------------------------------
@@ -486,6 +520,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           for (int q = 0; q < P.C; ++q) out[q] = w0 * cls0[q] + w1 * cls1[q] + V[VEC_CLS_B + q];
         }
       }
+      TR();                                                               // 20: logits written
       // the next tile's E0 overwrites X: every MMA that read X (G6) completed before G7's commit, which we have seen
     }
   }
@@ -517,6 +552,7 @@ int fusion_tc_forward(const void* packed_w, const FusTcParams& P, cudaStream_t s
   int rc = make_tensor_map_2d(&tmW, packed_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ROWS_ALL, UD, UD, 128, 64);
   if (rc != AVHOT_OK) return rc;
   const long long rows = (long long)P.B * P.T;
+  AVHOT_REQUIRE(rows < 0x7fffffffLL, AVHOT_ERR_INVALID, "fusion_tc: B * T too large for one call");
   const int n_tiles = (int)((rows + UB - 1) / UB);
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   const int smem = (int)sizeof(FusTcSmem) + 1024;
@@ -525,16 +561,39 @@ int fusion_tc_forward(const void* packed_w, const FusTcParams& P, cudaStream_t s
     const char* e = getenv("AVHOT_FUSION_HALVES");
     return e && e[0] == '1' ? 1 : (e && e[0] == '4' ? 4 : 2);
   }();
+  // debug: AVHOT_FUS_TRACE=<file> appends the clock64() stamps of one epilogue thread (fusion_tc_kernel, TR()) per launch
+  static const char* trace_path = getenv("AVHOT_FUS_TRACE");
+  FusTcParams PT = P;
+  long long* d_trace = nullptr;
+  if (trace_path && n_tiles >= 3 * grid) {
+    AVHOT_CUDA(cudaMalloc(&d_trace, 64 * sizeof(long long)));
+    AVHOT_CUDA(cudaMemsetAsync(d_trace, 0, 64 * sizeof(long long), s));
+    PT.trace = d_trace;
+  }
+  struct TraceDump {
+    long long* d; cudaStream_t s; const char* path;
+    ~TraceDump() {
+      if (!d) return;
+      long long h[64];
+      if (cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess)
+        if (FILE* f = fopen(path, "a")) {
+          for (int i = 1; i < 64 && h[i]; ++i) fprintf(f, "%d:%lld ", i, h[i] - h[i - 1]);
+          fprintf(f, "| total %lld\n", h[20] - h[0]);
+          fclose(f);
+        }
+      cudaFree(d);
+    }
+  } dump{d_trace, s, trace_path};
   ProfScope prof("fusion_tc", s);
   if (halves == 4) {
     AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    fusion_tc_kernel<4><<<grid, 64 + 128 * 4, smem, s>>>(tmW, P);
+    fusion_tc_kernel<4><<<grid, 64 + 128 * 4, smem, s>>>(tmW, PT);
   } else if (halves == 2) {
     AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    fusion_tc_kernel<2><<<grid, 64 + 128 * 2, smem, s>>>(tmW, P);
+    fusion_tc_kernel<2><<<grid, 64 + 128 * 2, smem, s>>>(tmW, PT);
   } else {
     AVHOT_CUDA(cudaFuncSetAttribute(fusion_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    fusion_tc_kernel<1><<<grid, 64 + 128, smem, s>>>(tmW, P);
+    fusion_tc_kernel<1><<<grid, 64 + 128, smem, s>>>(tmW, PT);
   }
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;

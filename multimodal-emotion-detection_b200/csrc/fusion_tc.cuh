@@ -26,6 +26,7 @@ struct FusTcParams {
   int B, T, C;
   const float* vec;       // FUS_VEC_FLOATS floats
   DropSpec ds;
+  long long* trace;       // debug (AVHOT_FUS_TRACE=<file>): clock64() at the epilogue's phase boundaries, or NULL
 };
 
 size_t fusion_tc_packed_bytes();

@@ -39,7 +39,7 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int nk16, int n_blocks,
                    int groups) {
   extern __shared__ unsigned char gemm_ws_smem_raw[];
-  GemmWsSmem& sm = *reinterpret_cast<GemmWsSmem*>((reinterpret_cast<uintptr_t>(gemm_ws_smem_raw) + 1023) & ~(uintptr_t)1023);
+  GemmWsSmem& sm = *reinterpret_cast<GemmWsSmem*>(gemm_ws_smem_raw + ((1024u - (smem_u32(gemm_ws_smem_raw) & 1023u)) & 1023u));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int nb = blockIdx.x % n_blocks, grp = blockIdx.x / n_blocks;
   const int n0 = nb * WBN;

@@ -124,7 +124,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       trace[((t - TRACE_T0) * RNC + c) * TRACE_EV + ev] = clock64();
   };
   extern __shared__ unsigned char rec_smem_raw[];
-  RecSmem& sm = *reinterpret_cast<RecSmem*>((reinterpret_cast<uintptr_t>(rec_smem_raw) + 1023) & ~(uintptr_t)1023);
+  RecSmem& sm = *reinterpret_cast<RecSmem*>(rec_smem_raw + ((1024u - (smem_u32(rec_smem_raw) & 1023u)) & 1023u));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
   // h_{-1} = 0
