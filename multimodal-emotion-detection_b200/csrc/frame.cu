@@ -64,7 +64,8 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
     const long long row = row0 + i;
     float y[8];
     if (row < n_rows) {                                    // warp-uniform
-      const int b = (int)(row / T), t = (int)(row % T);
+      // 32-bit row arithmetic (the entry points check B * T < 2^31): a 64-bit division costs ~100 instructions
+      const int b = (int)((uint32_t)row / (uint32_t)T), t = (int)((uint32_t)row - (uint32_t)b * (uint32_t)T);
       const uint32_t g = (uint32_t)(ds.clip0 + (uint64_t)b), pass = ds.t0 + (uint32_t)t;
       const float* hb = hid + (size_t)b * F * FH;
       float m = -INFINITY, denom = 0.f;
@@ -292,7 +293,7 @@ extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t
   if (B == 0) return AVHOT_OK;
   const long long rows = (long long)B * T;
   const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
-  AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail: B*T too large for one call");
+  AVHOT_REQUIRE(rows < 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail: B*T too large for one call");
   ProfScope prof("frame_tail", as_stream(stream));
   frame_tail_kernel<true><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
       hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
@@ -311,7 +312,7 @@ extern "C" int avhot_frame_tail_norm(avhot_frame_t h, const float* hid, const ui
   if (B == 0) return AVHOT_OK;
   const long long rows = (long long)B * T;
   const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
-  AVHOT_REQUIRE(grid <= 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail_norm: B*T too large for one call");
+  AVHOT_REQUIRE(rows < 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail_norm: B*T too large for one call");
   ProfScope prof("frame_tail", as_stream(stream));
   frame_tail_kernel<false><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
       hid, frame_valid, y, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,

@@ -183,12 +183,16 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   } else if (warp == 1) {
     if (leader) {                               // the whole warp, converged; one elected lane issues
       constexpr uint32_t idesc = umma_idesc(FMT_F16, PAIR ? 2 * RB : RB, RN);
-      uint32_t it = 0, use[2] = {0, 0};           // (constant-indexed after unrolling c by parity below)
+      // An accumulator buffer is used once every two chunks and RNC / 2 = 4 times per step, so the parity of its use
+      // count at chunk c is (c >> 1) & 1 in every step: no counters (as a run-time-indexed array they lived in local
+      // memory, an LDL in front of every barrier wait of the thread that paces the kernel)
+      static_assert((RNC / 2) % 2 == 0, "accumulator parity repeats every step");
+      uint32_t it = 0;
       if (!PAIR) {
         for (int t = 0; t < T; ++t) {
           for (int c = 0; c < RNC; ++c) {
             const int b = c & 1;
-            mbar_wait(&sm.acc_empty[b], (use[b] & 1) ^ 1);
+            mbar_wait(&sm.acc_empty[b], (uint32_t)((c >> 1) & 1) ^ 1u);
             tc_fence_after();
             tr(t, c, 0);
             for (int kb = 0; kb < RKB; ++kb, ++it) {
@@ -207,7 +211,6 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             }
             umma_commit_elect(&sm.acc_full[b]);
             tr(t, c, 2);
-            ++use[b];
           }
         }
       } else {
@@ -220,7 +223,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             if (TRACE && blockIdx.x == 0 && t >= TRACE_T0 && t < TRACE_T0 + TRACE_NT)
               trace[((t - TRACE_T0) * RNC + c) * TRACE_EV + 11] = (pre_acc ? 1 : 0) + (pre_full ? 2 : 0);
             tr(t, c, 10);
-            if (!pre_acc) mbar_wait_cluster(&sm.acc_empty[b], (use[b] & 1) ^ 1);
+            if (!pre_acc) mbar_wait_cluster(&sm.acc_empty[b], (uint32_t)((c >> 1) & 1) ^ 1u);
             tr(t, c, 1);
             if (!pre_full) mbar_wait(&sm.full[s], (it / NST) & 1);
             tc_fence_after();
@@ -239,14 +242,13 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                 umma_f16_pair_elect(tmem + (uint32_t)(b * RN), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
               if (kb == RKB - 2) {
                 const int bn = b ^ 1;
-                pre_acc = mbar_test_wait_cluster(&sm.acc_empty[bn], (use[bn] & 1) ^ 1);
+                pre_acc = mbar_test_wait_cluster(&sm.acc_empty[bn], (uint32_t)((((c + 1) % RNC) >> 1) & 1) ^ 1u);
                 pre_full = mbar_test_wait_cluster(&sm.full[(it + 1) % NST], ((it + 1) / NST) & 1);
               }
             }
             umma_commit_pair_mc_elect(&sm.empty[s], 3);
             umma_commit_pair_mc_elect(&sm.acc_full[b], 3);
             tr(t, c, 2);
-            ++use[b];
           }
         }
       }
@@ -337,10 +339,11 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const uint32_t acc_empty_addr[2] = {PAIR ? cluster_map_shared(&sm.acc_empty[0], 0) : 0u,
                                         PAIR ? cluster_map_shared(&sm.acc_empty[1], 0) : 0u};
     const uint32_t h_ready_addr0 = PAIR ? cluster_map_shared(&sm.h_ready[0], 0) : 0u;
-    uint32_t use[2] = {0, 0};
-    auto run = [&](int t, int c, uint32_t (&xg)[XR]) {
-      const int b = c & 1, u0 = c * RCH + q * 8;
-      mbar_wait(&sm.acc_full[b], use[b] & 1);
+    // b = c & 1 is passed as a literal from the two call sites: as a run-time index it put use[] and acc_empty_addr[] in
+    // local memory (LDL / STL in front of every barrier wait)
+    auto run = [&](int t, int c, uint32_t (&xg)[XR], const int b) {
+      const int u0 = c * RCH + q * 8;
+      mbar_wait(&sm.acc_full[b], (uint32_t)((c >> 1) & 1));
       tc_fence_after();
       if (threadIdx.x == 64) tr(t, c, 3);
       uint32_t acc[4][8], cs[8];
@@ -359,7 +362,6 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (PAIR) mbar_arrive_cluster(acc_empty_addr[b]);
         else mbar_arrive(&sm.acc_empty[b]);
       }
-      ++use[b];
       float hn[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -404,8 +406,8 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     for (int t = 0; t < T; ++t) {
 #pragma unroll 1
       for (int c = 0; c < RNC; c += 2) {
-        run(t, c, xa);
-        run(t, c + 1, xb);
+        run(t, c, xa, 0);
+        run(t, c + 1, xb, 1);
       }
     }
   }
