@@ -23,6 +23,8 @@
 // (The sparse per-lane filter walk this replaces cost ~130 of the ~480 shared-memory wavefronts per frame of a
 // kernel that ncu shows bound by shared-memory bandwidth: l1tex 88 %, r1y.)
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -243,7 +245,8 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
 
 __global__ void __launch_bounds__(FE_WARPS * 32, 3)
 frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __half* __restrict__ xs, int Bp, int ldx,
-                int n_samples, int n_frames, int tiles_per_cta, const FrontendTables* __restrict__ tab) {
+                int n_samples, int n_frames, int tiles_per_cta, const FrontendTables* __restrict__ tab,
+                long long* __restrict__ trace = nullptr) {
   extern __shared__ __align__(16) unsigned char fe_smem_raw[];
   FeSmem& sm = *reinterpret_cast<FeSmem*>(fe_smem_raw);
   float* s_seg = sm.seg;
@@ -329,13 +332,18 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     stage_segment();
   }
   __syncthreads();
+  // debug (AVHOT_FE_TRACE=<file>): thread 0 of CTA (0, 0) stamps clock64() at the phase boundaries of its sixth tile
+  int ev = 0;
+  auto TR = [&](int tile) { if (trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && tile == tile_begin + 5 && ev < 16) trace[ev++] = clock64(); };
   for (int tile = tile_begin; tile < tile_end; ++tile) {
   const int t0 = tile * FPB;
   if (t0 >= n_frames) break;
   // the next tile's samples travel to registers during this tile's FFTs and are staged right after them (the segment
   // buffer is free once the FFT phase is over), so a tile costs four block barriers, not five
   const bool have_next = tile + 1 < tile_end && (tile + 1) * FPB < n_frames;
+  TR(tile);                            // 0: tile start
   if (have_next) fetch((tile + 1) * FPB);
+  TR(tile);                            // 1: next tile's loads issued
 
   float2* z = s_z[warp];
   for (int f = warp; f < FPB; f += FE_WARPS) {
@@ -411,8 +419,11 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     // (bin 256 carries no filter weight - checked when the tables are built - and is not formed)
     __syncwarp();
   }
+  TR(tile);                            // 2: this thread's FFTs done
   __syncthreads();                   // power spectra of the tile complete; the FFT scratch and the segment are free
+  TR(tile);                            // 3: every warp's FFTs done
   if (have_next) stage_segment();
+  TR(tile);                            // 4: next segment staged
   // ---- mel filterbank on the tensor cores + log: warp j = filters 8j .. 8j+7 of all 16 frames
   {
     const int g = lane >> 2, t4 = lane & 3;
@@ -439,7 +450,9 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     *reinterpret_cast<float2*>(&s_out[g][8 * warp + 2 * t4]) = make_float2(lm[0], lm[1]);
     *reinterpret_cast<float2*>(&s_out[g + 8][8 * warp + 2 * t4]) = make_float2(lm[2], lm[3]);
   }
+  TR(tile);                            // 5: this warp's mel tile done
   __syncthreads();                   // log-mel rows of the tile complete
+  TR(tile);                            // 6
   // ---- DCT-II (orthonormal), first 40 coefficients, folded and error-compensated on the tensor cores:
   //      warp = (parity p, tile nt): coefficients c = 2 (8 nt + n) + p over u[j] = lm[j] + (-1)^p lm[63 - j], j < 32
   if (warp < DCT_TILES) {
@@ -470,7 +483,9 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
     if (ca < N_MFCC) { s_out[g][N_MELS + ca] = acc[0]; s_out[g + 8][N_MELS + ca] = acc[2]; }
     if (cb < N_MFCC) { s_out[g][N_MELS + cb] = acc[1]; s_out[g + 8][N_MELS + cb] = acc[3]; }
   }
+  TR(tile);                            // 7: this warp's DCT tile done
   __syncthreads();
+  TR(tile);                            // 8
   // coalesced store of the CTA's output tile (rows are contiguous in feats)
   const int rows = min(FPB, n_frames - t0);
   if (feats) {
@@ -509,7 +524,9 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
       }
     }
   }
+  TR(tile);                            // 9: this thread's stores issued
   __syncthreads();   // s_seg / s_out are rewritten by the next tile
+  TR(tile);                            // 10: tile end
   }
 }
 
@@ -542,10 +559,29 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
   // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
   AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FeSmem)));
-  ProfScope prof("frontend", s);
-  frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), s>>>(wave, feats, reinterpret_cast<__half*>(xs), Bp, ldx,
-                                                              n_samples, n_frames, tiles_per_cta, tab);
-  AVHOT_LAUNCH_CHECK();
+  static const char* trace_path = getenv("AVHOT_FE_TRACE");
+  long long* d_trace = nullptr;
+  if (trace_path && tiles_per_cta >= 6) {
+    AVHOT_CUDA(cudaMalloc(&d_trace, 16 * sizeof(long long)));
+    AVHOT_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), s));
+  }
+  {
+    ProfScope prof("frontend", s);
+    frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), s>>>(wave, feats, reinterpret_cast<__half*>(xs), Bp, ldx,
+                                                                n_samples, n_frames, tiles_per_cta, tab, d_trace);
+    AVHOT_LAUNCH_CHECK();
+  }
+  if (d_trace) {
+    long long h[16];
+    AVHOT_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
+    AVHOT_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_trace);
+    if (FILE* f = fopen(trace_path, "a")) {
+      for (int i = 1; i < 11; ++i) fprintf(f, "%d:%lld ", i, h[i] - h[i - 1]);
+      fprintf(f, "| tile %lld\n", h[10] - h[0]);
+      fclose(f);
+    }
+  }
   return AVHOT_OK;
 }
 
