@@ -9,7 +9,7 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libavhot.so")
+LIB_PATH = os.environ.get("AVHOT_LIB_PATH") or os.path.join(HERE, "libavhot.so")   # override: A/B runs of two builds
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 PREC_FP32, PREC_BF16X3, PREC_TC = 0, 1, 2
