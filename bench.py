@@ -145,6 +145,34 @@ def run_reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """One process per GPU: run this process (and so allocate its pinned host buffers, first touch) on the CPU socket the
+    GPU hangs off, so the host->device copies of the e2e leg do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        bus_id = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus_id = (bus_id.decode() if isinstance(bus_id, bytes) else bus_id).lower()
+        if len(bus_id.split(":")[0]) == 8:               # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus_id = bus_id[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus_id}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:                                  # noqa: BLE001 - placement is an optimisation, never a failure
+        pass
+    return None
+
+
 def workload_config(args, batch):
     return {"workload": "BASELINE.json configs[4] shard: synthetic RAVDESS-shaped clips (3 s 16 kHz audio, 16 frames "
                         "112x112 fp32) -> log-mel/MFCC front-end (n_fft 512, hop 160, 64 mel + 40 MFCC) -> LSTM 2x256 "
@@ -174,6 +202,7 @@ def run_b200_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -351,7 +380,8 @@ def run_b200_arm(args):
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/f16 tensor-core operands, f32 accumulate",
             "data": "synthetic", "config": workload_config(args, B),
             "e2e": e2e, "e2e_u8_frames": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "stages": stages, "stage_rooflines": extra}
+            "cpu_baseline": cpu_baseline, "parity": parity, "stages": stages, "stage_rooflines": extra,
+            "host_numa_node_rank0": numa}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -22,6 +22,10 @@ class Handle:
     def key_of(tensors):
         return tuple((t.data_ptr(), t._version, str(t.device), tuple(t.shape)) for t in tensors)
 
+    def is_current(self, tensors) -> bool:
+        """True when the cached handle was built from exactly these tensors (same storage, version, device, shape)."""
+        return self._h is not None and self._key == self.key_of(tensors)
+
     def get(self, tensors, create):
         """tensors: the parameters the handle is derived from; create() -> raw handle (int)."""
         key = self.key_of(tensors)

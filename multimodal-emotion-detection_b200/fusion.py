@@ -148,12 +148,10 @@ class HybridFusion(nn.Module):
                 if folded_from is not None:
                     idx, lin = folded_from
                     src = [lin.weight, lin.bias]
-                    key = Handle.key_of(self._params() + src)
-                    if self._handle_folded._h is None or self._handle_folded._key != key:
+                    w = b = None
+                    if not self._handle_folded.is_current(self._params() + src):     # (re)fold only when a weight changed
                         w, b = self._fold_video_projection(idx, lin, dev)
-                        h = self._get_handle(dev, folded=(idx, lin.in_features, w, b, src))
-                    else:
-                        h = self._get_handle(dev, folded=(idx, lin.in_features, None, None, src))
+                    h = self._get_handle(dev, folded=(idx, lin.in_features, w, b, src))
                 else:
                     h = self._get_handle(dev)
                 lib = _lib.load()
