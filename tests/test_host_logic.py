@@ -30,6 +30,34 @@ def test_signatures_match_reference():
     assert inspect.signature(pkg.HybridFusion.__init__).parameters["num_classes"].default == 11
     assert inspect.signature(pkg.MCDropoutUncertainty.__init__).parameters["num_samples"].default == 10
     assert sig(pkg.load_raw_audio) == ["wav_path", "sr", "max_duration"]                  # src/dataprocessing.py:184-188
+    # SURVEY.md 8(f) row 4
+    assert sig(pkg.TemporalAttention.__init__)[1:] == ["feature_dim", "hidden_dim", "num_heads", "dropout"]   # src/attention.py:150-156
+    assert sig(pkg.TemporalAttention.forward)[1:] == ["sequence", "mask"]                  # :181-185
+    assert sig(pkg.TemporalAttention.pool_sequence)[1:] == ["sequence", "attention_weights"]   # :245-249
+    assert sig(pkg.PairwiseModalityAttention.__init__)[1:] == ["modality_dims", "hidden_dim", "num_heads", "dropout"]   # :427-433
+    assert sig(pkg.PairwiseModalityAttention.forward)[1:] == ["modality_features", "modality_mask"]           # :470-474
+    assert inspect.signature(pkg.TemporalAttention.__init__).parameters["hidden_dim"].default == 256
+
+
+def test_sequence_attention_modules_parameter_layout():
+    """Parameter names / shapes of the 8(f) modules as the reference's classes create them (counts from the reference:
+    SequenceEncoder(transformer, 104 -> 256 -> 128, 2 layers) 2 687 872 incl. the 4096-row position table;
+    TemporalAttention(104, 256) 146 432; PairwiseModalityAttention({a: 128, v: 128}, 256) 397 824)."""
+    enc = pkg.SequenceEncoder(input_dim=104, hidden_dim=256, output_dim=128, num_layers=2, encoder_type="transformer")
+    sd = enc.state_dict()
+    assert sd["pos_embedding.weight"].shape == (4096, 256) and sd["input_proj.weight"].shape == (256, 104)
+    assert sd["transformer.layers.1.self_attn.in_proj_weight"].shape == (768, 256)
+    assert sd["transformer.layers.0.linear1.weight"].shape == (1024, 256) and sd["projection.weight"].shape == (128, 256)
+    assert sum(p.numel() for p in enc.parameters()) == 2_687_872
+    ta = pkg.TemporalAttention(104, 256)
+    assert sorted(ta.state_dict()) == sorted(f"{n}.{w}" for n in ("q_proj", "k_proj", "v_proj", "out_proj") for w in ("weight", "bias"))
+    assert sum(p.numel() for p in ta.parameters()) == 3 * (104 * 256 + 256) + 256 * 256 + 256 == 146_432
+    pm = pkg.PairwiseModalityAttention({"audio": 128, "video": 128}, hidden_dim=256)
+    assert set(k.split(".")[0] for k in pm.state_dict()) == {"cross_attn", "self_proj", "out_ln"}
+    per_dir = 3 * 2 * 128 + 3 * (128 * 256 + 256) + 256 * 256 + 256          # three input LayerNorms, q / k / v, out_proj
+    assert sum(p.numel() for p in pm.parameters()) == 2 * per_dir + 2 * (128 * 256 + 256) + 2 * 256 == 397_824
+    with pytest.raises(ValueError):
+        pkg.PairwiseModalityAttention({str(i): 8 for i in range(5)})
 
 
 def test_state_dict_layout_appendix_a():
