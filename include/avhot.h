@@ -330,7 +330,8 @@ int avhot_calibration_accumulate(const float* logits, const float* confidences, 
  * projection.  seq (B, T, input_dim) fp32, lengths (B) int32 or NULL -> z (B, passes, output_dim).  Pass t draws the
  * masks of (seed, t0 + t, clip0 + b) at sites AVHOT_SITE_TFM + 3 l + {0 dropout1 (T, H), 1 dropout (T, ffn),
  * 2 dropout2 (T, H)} of layer l; p = 0 is the eval forward.  Weights are nn.Linear / nn.MultiheadAttention layouts:
- * in_proj (3H, H) = [q | k | v] rows.  fp32 path. */
+ * in_proj (3H, H) = [q | k | v] rows.  precision: AVHOT_PREC_FP32, or AVHOT_PREC_TC = every nn.Linear on the tcgen05
+ * TF32 GEMM (stated tolerance 2e-3), attention / LayerNorm / GELU / pooling in fp32 either way. */
 #define AVHOT_TFM_MAX_LAYERS 4
 typedef struct avhot_tfm* avhot_tfm_t;
 typedef struct {
@@ -348,8 +349,8 @@ int avhot_tfm_create(const avhot_tfm_desc* desc, avhot_tfm_t* out, avhot_stream_
 void avhot_tfm_destroy(avhot_tfm_t h);
 size_t avhot_tfm_workspace_bytes(avhot_tfm_t h, int B, int T, int passes);
 int avhot_tfm_forward(avhot_tfm_t h, const float* seq, const int32_t* lengths, float* z, int B, int T, int passes,
-                      float p, uint64_t seed, uint64_t clip0, uint32_t t0, void* workspace, size_t workspace_bytes,
-                      avhot_stream_t stream);
+                      float p, uint64_t seed, uint64_t clip0, uint32_t t0, int precision, void* workspace,
+                      size_t workspace_bytes, avhot_stream_t stream);
 
 /* ---- src/attention.py:143-274  TemporalAttention -------------------------------------------
  * forward(sequence (B, S, feature_dim), mask (B, S) 1 = valid or NULL) -> attended (B, S, hidden), weights

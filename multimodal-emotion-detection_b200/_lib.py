@@ -166,7 +166,7 @@ PROTOTYPES = {
     "avhot_tfm_create": (_I, [C.POINTER(TfmDesc), C.POINTER(_P), _P]),
     "avhot_tfm_destroy": (None, [_P]),
     "avhot_tfm_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
-    "avhot_tfm_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P, _SZ, _P]),
+    "avhot_tfm_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _I, _P, _SZ, _P]),
     "avhot_tattn_create": (_I, [C.POINTER(TattnDesc), C.POINTER(_P), _P]),
     "avhot_tattn_destroy": (None, [_P]),
     "avhot_tattn_workspace_bytes": (_SZ, [_P, _I, _I]),

@@ -480,9 +480,11 @@ extern "C" size_t avhot_tfm_workspace_bytes(avhot_tfm_t h, int B, int T, int pas
 }
 
 extern "C" int avhot_tfm_forward(avhot_tfm_t h, const float* seq, const int32_t* lengths, float* z, int B, int T,
-                                 int passes, float p, uint64_t seed, uint64_t clip0, uint32_t t0, void* workspace,
-                                 size_t workspace_bytes, avhot_stream_t stream) {
+                                 int passes, float p, uint64_t seed, uint64_t clip0, uint32_t t0, int precision,
+                                 void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
   AVHOT_REQUIRE(h && seq && z && B >= 0 && T >= 1 && passes >= 1, AVHOT_ERR_INVALID, "tfm_forward: bad arguments");
+  AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
+                "tfm_forward: precision %d not built", precision);
   AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "tfm_forward: dropout p=%g outside [0, 1)", (double)p);
   if (B == 0) return AVHOT_OK;
   AVHOT_REQUIRE((long long)B * T <= 0x7fffffff / 8 && (long long)T * h->F <= 0x7fffffffLL, AVHOT_ERR_INVALID,
@@ -505,10 +507,17 @@ extern "C" int avhot_tfm_forward(avhot_tfm_t h, const float* seq, const int32_t*
   float* pooled = take((size_t)B * passes * H);
   const int M = (int)rows;
   const int ew_grid = num_sms() * 8;
+  // every nn.Linear of the encoder: fp32 FMA (parity path) or the tcgen05 TF32 GEMM the video Linear uses (AVHOT_PREC_TC:
+  // fp32 operands read as TF32, fp32 accumulate; attention, LayerNorm, GELU and the pooled projection stay fp32)
+  const bool tc = precision == AVHOT_PREC_TC;
+  auto gemm = [&](const float* a, int lda, const float* w, int ldw, const float* bias, float* c, int ldc, int m, int n, int k,
+                  const char* name) -> int {
+    return tc ? gemm_tf32_tc(a, lda, w, ldw, bias, c, ldc, m, n, k, ACT_NONE, s, name)
+              : gemm_f32(a, nullptr, lda, w, ldw, bias, c, ldc, m, n, k, ACT_NONE, s, name);
+  };
 
   // x0 = input_proj(seq) + pos   (src/encoders.py:172, :180-182)
-  int rc = gemm_f32(seq, nullptr, h->in_dim, h->input_w, h->in_dim, h->input_b, x0, H, M, H, h->in_dim, ACT_NONE, s,
-                    "tfm_input_proj");
+  int rc = gemm(seq, h->in_dim, h->input_w, h->in_dim, h->input_b, x0, H, M, H, h->in_dim, "tfm_input_proj");
   if (rc != AVHOT_OK) return rc;
   {
     ProfScope prof("tfm_add_pos", s);
@@ -517,12 +526,12 @@ extern "C" int avhot_tfm_forward(avhot_tfm_t h, const float* seq, const int32_t*
   }
   // self-attention block of one layer: y_out = out_proj(MHA(x_in))
   auto sa_block = [&](int l, const float* x_in, float* y_out) -> int {
-    int r = gemm_f32(x_in, nullptr, H, h->in_proj_w[l], H, h->in_proj_b[l], qkv, 3 * H, M, 3 * H, H, ACT_NONE, s, "tfm_qkv");
+    int r = gemm(x_in, H, h->in_proj_w[l], H, h->in_proj_b[l], qkv, 3 * H, M, 3 * H, H, "tfm_qkv");
     if (r != AVHOT_OK) return r;
     r = launch_self_attn(qkv, 3 * H, 0, H, 2 * H, lengths, nullptr, nullptr, ctx, H, nullptr, B, T, h->heads, d, s,
                          "tfm_self_attn");
     if (r != AVHOT_OK) return r;
-    return gemm_f32(ctx, nullptr, H, h->out_w[l], H, h->out_b[l], y_out, H, M, H, H, ACT_NONE, s, "tfm_out_proj");
+    return gemm(ctx, H, h->out_w[l], H, h->out_b[l], y_out, H, M, H, H, "tfm_out_proj");
   };
   rc = sa_block(0, x0, sa0);     // pass-invariant: every dropout of layer 0 comes after it
   if (rc != AVHOT_OK) return rc;
@@ -543,14 +552,14 @@ extern "C" int avhot_tfm_forward(avhot_tfm_t h, const float* seq, const int32_t*
                                                      AVHOT_SITE_TFM + 3u * (uint32_t)l, pass, ds);
         AVHOT_LAUNCH_CHECK();
       }
-      rc = gemm_f32(x, nullptr, H, h->lin1_w[l], H, h->lin1_b[l], ff, F, M, F, H, ACT_NONE, s, "tfm_linear1");
+      rc = gemm(x, H, h->lin1_w[l], H, h->lin1_b[l], ff, F, M, F, H, "tfm_linear1");
       if (rc != AVHOT_OK) return rc;
       {
         ProfScope prof("tfm_gelu", s);
         gelu_drop_kernel<<<ew_grid, 256, 0, s>>>(ff, rows, T, F, AVHOT_SITE_TFM + 3u * (uint32_t)l + 1u, pass, ds);
         AVHOT_LAUNCH_CHECK();
       }
-      rc = gemm_f32(ff, nullptr, F, h->lin2_w[l], F, h->lin2_b[l], y, H, M, H, F, ACT_NONE, s, "tfm_linear2");
+      rc = gemm(ff, F, h->lin2_w[l], F, h->lin2_b[l], y, H, M, H, F, "tfm_linear2");
       if (rc != AVHOT_OK) return rc;
       {
         ProfScope prof("tfm_resid_ln", s);

@@ -22,7 +22,8 @@ _ws_frames = Workspace()
 
 class SequenceEncoder(nn.Module):
     """src/encoders.py:15-192.  encoder_type 'lstm' is the hot path (configs/base.yaml:32-38); 'gru', 'cnn' and
-    'transformer'  run on the fp32 kernels of csrc/gru.cu / csrc/cnn.cu / csrc/seqattn.cu."""
+    'transformer'  run on the fp32 kernels of csrc/gru.cu / csrc/cnn.cu / csrc/seqattn.cu; with
+    precision = PREC_TC the transformer's nn.Linear layers run on the tcgen05 TF32 GEMM."""
 
     def __init__(self, input_dim: int, hidden_dim: int = 256, output_dim: int = 128, num_layers: int = 2,
                  encoder_type: str = 'lstm', dropout: float = 0.1):
@@ -131,8 +132,9 @@ class SequenceEncoder(nn.Module):
         with torch.cuda.device(dev):
             h = self._get_tfm_handle(dev)
             ws = _ws.get(lib.avhot_tfm_workspace_bytes(h, B, T, passes), dev)
+            prec = _lib.PREC_TC if self.precision == _lib.PREC_TC else _lib.PREC_FP32
             _lib.check(lib.avhot_tfm_forward(h, _lib.ptr(x), _lib.ptr(lengths), _lib.ptr(z), B, T, passes, float(p), seed,
-                                             clip0, t0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                                             clip0, t0, prec, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
                        "SequenceEncoder.forward (transformer)")
         return z
 

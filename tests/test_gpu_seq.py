@@ -103,6 +103,14 @@ def test_transformer_encoder_benchmark_dims_vs_oracle(pkg, dev):
         got = enc(x.to(dev), ln)
     want = om.sequence_encoder_transformer(x.double(), sd, lengths=ln, ctx=om.DropCtx(42, 5, ids))
     assert rel_err(got.cpu().numpy(), want.numpy()) <= REL
+    # the same stochastic pass with every nn.Linear on the tcgen05 TF32 GEMM: same masks, stated tolerance 2e-3
+    enc.precision = pkg._lib.PREC_TC
+    with pkg.philox_context(42, 5, 7000):
+        got_tc = enc(x.to(dev), ln)
+    err = rel_err(got_tc.cpu().numpy(), want.numpy())
+    print("transformer encoder, TF32 GEMMs: rel err", err)
+    assert err <= 2e-3
+    enc.precision = pkg._lib.PREC_FP32
 
 
 def test_temporal_attention_vs_reference_golden(pkg, dev, g):
