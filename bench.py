@@ -211,14 +211,14 @@ def run_b200_arm(args):
 
     import multimodal_emotion_detection_b200 as pkg
     from multimodal_emotion_detection_b200 import parallel as par
-    from oracle import synth as osynth
 
     pkg._lib.check_device(dev)
     B, T = args.batch, args.passes
-    sd_np = osynth.synth_weights(SEED)
+    # random-init weights of the architecture: torch's default init under the reference's seed (configs/base.yaml:4,
+    # src/train.py:472).  The product arm touches nothing under oracle/; the CPU leg below is handed these tensors.
+    torch.manual_seed(SEED)
     model = pkg.AVHotPath("hybrid")
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in osynth.state_dict_for("hybrid", sd_np).items()},
-                          strict=True)
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.to(dev).eval().set_precision(args.precision)
     model.fold_video_projection = not args.no_fold
     pkg.MCDropoutUncertainty._set_dropout_train(model)            # what MCDropoutUncertainty.forward does (:58-59)
@@ -359,7 +359,7 @@ def run_b200_arm(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import model as om
-        sd = om.to_torch(sd_np)
+        sd = sd_cpu                                                  # AVHotPath("hybrid") keys = the oracle's (Appendix A)
         threads = os.cpu_count() or 1
         cpu_reference_step(min(8, args.cpu_clips), 2, 0, sd, threads)          # warm-up
         dt, cpu_mean = cpu_reference_step(args.cpu_clips, T, clip0_of(0), sd, threads)
