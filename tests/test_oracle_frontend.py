@@ -61,3 +61,25 @@ def test_golden_features(golden):
     f = fe.logmel_mfcc(w)
     np.testing.assert_allclose(f[0], golden["feats_clip0"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(f[1], golden["feats_last"], rtol=0, atol=1e-4)
+
+
+def test_whole_front_end_matches_torchaudio_pipeline():
+    """End to end against an independent implementation of the same conventions: torchaudio's MelSpectrogram (Slaney
+    scale and normalisation - the options torchaudio added to reproduce librosa's filters.mel), AmplitudeToDB (power,
+    amin 1e-10, no top_db = librosa.power_to_db(ref=1, top_db=None)) and create_dct(norm="ortho") (= scipy dct type 2,
+    what librosa.feature.mfcc applies), on the pre-emphasised waveform."""
+    ta = pytest.importorskip("torchaudio")
+    w = _wave(2)
+    p = torch.from_numpy(fe.preemphasis(w))                                     # fp64
+    mel = ta.transforms.MelSpectrogram(sample_rate=16000, n_fft=512, hop_length=160, f_min=0.0, f_max=8000.0, n_mels=64,
+                                       window_fn=torch.hann_window, power=2.0, center=True, pad_mode="reflect",
+                                       norm="slaney", mel_scale="slaney").double()
+    logmel = ta.transforms.AmplitudeToDB(stype="power", top_db=None)(mel(p))    # (B, 64, 301)
+    dct = ta.functional.create_dct(40, 64, norm="ortho").double()               # (64, 40)
+    mfcc = logmel.transpose(1, 2) @ dct
+    want = torch.cat([logmel.transpose(1, 2), mfcc], dim=-1).numpy()
+    got = fe.logmel_mfcc(w, out_dtype=np.float64)
+    assert got.shape == want.shape == (2, 301, 104)
+    # torchaudio builds its filterbank in fp32 (2e-4 relative on a tap): a few 1e-3 dB on a log-mel value
+    assert np.abs(got - want).max() <= 5e-3
+    assert np.abs(got - want).max() / np.abs(want).max() <= 1e-5
