@@ -2,14 +2,19 @@
 """Benchmark of the per-clip audio-visual inference hot path (BASELINE.json metric: clips/sec, front-end + fused
 forward + T-pass MC-dropout uncertainty).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py [--gpus N] [--steps K] [--warmup W]                # this repo's CUDA path
     python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU path (oracle port)
+    python bench.py --sweep 1000000 [--gpus N]                         # configs[4] literally: strong scaling over N ranks
 
 A step = one batch of synthetic RAVDESS-shaped clips per GPU through: log-mel/MFCC front-end -> LSTM audio encoder
 + frame encoder -> hybrid cross-modal attention fusion -> T = 32 MC-dropout passes -> (mean logits, uncertainty,
-label) per clip; with N > 1 ranks (one process per GPU, weak scaling) the packed (B, 9) records are all-gathered
-over NCCL.  `value` times the steps with inputs resident in HBM; `e2e` times the same call with HOST (pinned)
-buffers, host->device copies and the device->host read of the result inside the timed region.
+label) per clip, labels made identical to the fp32 path's by re-evaluating the near-tie clips (exact.py; flushed every
+--resolve-every steps inside the timed region); with N > 1 ranks (one process per GPU, weak scaling) the packed (B, 9)
+records are all-gathered over NCCL.  `value` times the steps with fp32 inputs resident in HBM; `e2e` times the same
+call with HOST (pinned) buffers holding the clips as the decoders deliver them (uint8 pixels, 16-bit PCM), host->device
+copies and the device->host read of the result inside the timed region; `e2e_fp32_inputs` is the same with the fp32
+arrays the reference's loaders convert them to.  `extra` holds the timed legs of BASELINE configs[0..3] and the 1 M-clip
+sweep of configs[4].
 """
 from __future__ import annotations
 
@@ -30,14 +35,18 @@ SEED = 42
 N_SAMPLES, N_FRAMES, FRAME_DIM, N_CLASSES = 48000, 16, 112 * 112, 8
 T_FEATS = 1 + N_SAMPLES // 160
 P_MODALITY = 0.05
-# algorithmic work per clip (derivations in DESIGN.md)
-FLOPS_LSTM_RECURRENT_PER_LAYER = T_FEATS * 2 * 1024 * 256          # h_{t-1} @ W_hh^T, one layer
-FLOPS_LSTM = 537_542_656
-FLOPS_FRAME_GEMM = 16 * 2 * FRAME_DIM * 256
-BYTES_FRONTEND = N_SAMPLES * 4 + T_FEATS * 104 * 4
-BYTES_FRAMES = N_FRAMES * FRAME_DIM * 4
-BYTES_IN_PER_CLIP = N_SAMPLES * 4 + BYTES_FRAMES + 2 * 4
+# Algorithmic work per clip, exactly SURVEY.md 8(d) / Appendix B (derivations in DESIGN.md section 4)
+BYTES_FRONTEND = N_SAMPLES * 4 + T_FEATS * 104 * 4            # 192 000 in + 125 216 out = 317 216
+BYTES_LSTM = T_FEATS * 104 * 4 + 512                          # 125 216 in + 512 out
+FLOPS_LSTM = 537_542_656 + 65_536                             # two layers + projection
+FLOPS_LSTM_RECURRENT_PER_LAYER = T_FEATS * 2 * 1024 * 256     # h_{t-1} @ W_hh^T, one layer
+BYTES_VIDEO = N_FRAMES * FRAME_DIM * 4 + 512                  # 802 816 fp32 in + 512 out
+FLOPS_FRAME_GEMM = 16 * 2 * FRAME_DIM * 256                   # 102 760 448
+FLOPS_MC_PASS = 1_923_584                                     # pass-dependent part (video tail + fusion), per pass
+BYTES_MC_TAIL = 16 * 256 * 4 + 36                             # pre-dropout activations in + packed record out
+BYTES_IN_PER_CLIP = N_SAMPLES * 4 + N_FRAMES * FRAME_DIM * 4 + 2 * 4
 BYTES_OUT_PER_CLIP = (N_CLASSES + 1) * 4
+FLOPS_E2E_T1 = 657e6
 
 
 def load_peaks():
@@ -97,22 +106,35 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's execution of the path (oracle port), on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(n_clips: int, passes: int, clip0: int, sd, threads: int):
+def cpu_reference_step(n_clips: int, passes: int, clip0: int, sd, threads: int, warm: bool = True):
     """One bounded sample: n_clips synthetic clips through the front-end restatement (once: the reference would
     precompute features offline) and MCDropoutUncertainty as the reference executes it (T full forwards,
-    torch.nn.LSTM).  Returns (seconds, mean_logits)."""
+    torch.nn.LSTM).  Input generation and the numpy restatement of the Philox masks are outside the timed region (the
+    reference's nn.Dropout draws from torch's native generator): an untimed pass over the video / fusion half of the
+    model fills the mask cache and warms the threads up.  Returns (seconds total, seconds front-end, mean_logits)."""
     import numpy as np
     import torch
     from oracle import frontend as ofe, model as om, philox as px, synth as osynth
     torch.set_num_threads(threads)
     ids = np.arange(n_clips, dtype=np.uint64) + np.uint64(clip0)
-    wave = osynth.synth_audio(ids, SEED)                       # input generation is not timed
+    wave = osynth.synth_audio(ids, SEED)
     frames = torch.from_numpy(osynth.synth_video(ids, SEED))
     mask = torch.from_numpy(px.modality_mask(ids, 2, P_MODALITY, SEED))
-    t0 = time.perf_counter()
-    feats = torch.from_numpy(ofe.logmel_mfcc(wave))
-    mean, unc, _ = om.mc_dropout_forward_as_reference(feats, frames, mask, sd, passes, SEED, ids, "hybrid")
-    return time.perf_counter() - t0, mean
+    om.MASK_CACHE = {}
+    try:
+        if warm:   # every mask the timed passes will ask for (all dropout sites sit after the encoders' contractions)
+            with torch.inference_mode():
+                for t in range(passes):
+                    om.av_forward(None, frames, mask, sd, "hybrid", om.DropCtx(seed=SEED, t=t, clip_ids=np.asarray(ids)),
+                                  z_audio=torch.zeros(n_clips, 128))
+        t0 = time.perf_counter()
+        feats = torch.from_numpy(ofe.logmel_mfcc(wave))
+        t1 = time.perf_counter()
+        mean, unc, _ = om.mc_dropout_forward_as_reference(feats, frames, mask, sd, passes, SEED, ids, "hybrid")
+        t2 = time.perf_counter()
+    finally:
+        om.MASK_CACHE = None
+    return t2 - t0, t1 - t0, mean
 
 
 def run_reference_arm(args):
@@ -125,20 +147,24 @@ def run_reference_arm(args):
     sd = om.to_torch(osynth.synth_weights(SEED))
     n = args.cpu_clips
     for w in range(args.warmup):
-        cpu_reference_step(n, args.passes, w * n, sd, threads)
-    total = 0.0
+        cpu_reference_step(min(n, 32), args.passes, w * n, sd, threads, warm=False)
+    total = fe = 0.0
     for s in range(args.steps):
-        dt, _ = cpu_reference_step(n, args.passes, (args.warmup + s) * n, sd, threads)
+        dt, dfe, _ = cpu_reference_step(n, args.passes, (args.warmup + s) * n, sd, threads)
         total += dt
+        fe += dfe
     value = n * args.steps / total
-    sample = (f"{n} synthetic clips per step: fp64 numpy front-end restatement once + MCDropoutUncertainty as the "
-              f"reference runs it (T={args.passes} full forwards, torch.nn.LSTM + torch CPU ops, fp32, "
-              f"{threads} threads, torch {torch.__version__})")
+    sample = (f"{n} synthetic clips per step: fp64 numpy front-end restatement once ({1e3 * fe / args.steps:.0f} ms of the "
+              f"{1e3 * total / args.steps:.0f} ms step; without it {n * args.steps / (total - fe):.1f} clips/s) + "
+              f"MCDropoutUncertainty as the reference runs it (T={args.passes} full forwards, torch.nn.LSTM + torch CPU "
+              f"ops, fp32, {threads} threads, torch {torch.__version__}); Philox masks and inputs generated outside the "
+              f"timed region")
     line = {"impl": "reference", "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n),
-            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample,
+                             "value_without_frontend": n * args.steps / (total - fe)},
             "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -179,6 +205,8 @@ def workload_config(args, batch):
                         "+ frame encoder -> hybrid cross-modal attention fusion -> MC-dropout uncertainty",
             "clips_per_gpu_per_step": batch, "mc_passes": args.passes, "modality_dropout_p": P_MODALITY,
             "classes": N_CLASSES, "precision": args.precision, "parallelism": f"clip-sharded x{args.gpus}, all-gather of (B,9) fp32",
+            "label_exactness": f"near-tie clips re-evaluated in fp32 every {args.resolve_every} steps, inside the timed region"
+                               if args.precision == "tc" else "fp32 path",
             "l2_policy": f"inputs larger than L2 ({batch * BYTES_IN_PER_CLIP / 1e9:.1f} GB per step per GPU), two "
                          "batches alternate"}
 
@@ -186,6 +214,37 @@ def workload_config(args, batch):
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def synth_inputs(ctx, n, c0, audio="f32", video="f32"):
+    """Device-resident synthetic clips [c0, c0 + n): fp32 waveform or 16-bit PCM, fp32 frames or uint8 pixels."""
+    torch, pkg, dev = ctx.torch, ctx.pkg, ctx.dev
+    a = pkg.synth.synth_audio(n, c0, SEED, dev)
+    if audio == "i16":                    # what a 16-bit .wav of the same (peak-normalised) clip holds
+        a = (a * 32767.0).round_().to(torch.int16)
+    v = pkg.synth.synth_video(n, c0, SEED, dev, dtype=torch.uint8 if video == "u8" else torch.float32)
+    m = pkg.synth.modality_mask(n, c0, P_MODALITY, SEED, dev)
+    return {"audio": a, "video": v}, m
+
+
+def timed(ctx, fn, iters):
+    """CUDA-event time of iters calls of fn(i) on the current stream, barrier + synchronize on both sides, max over ranks."""
+    torch = ctx.torch
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    ctx.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(ms, op=ctx.dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -216,38 +275,70 @@ def run_b200_arm(args):
     B, T = args.batch, args.passes
     # random-init weights of the architecture: torch's default init under the reference's seed (configs/base.yaml:4,
     # src/train.py:472).  The product arm touches nothing under oracle/; the CPU leg below is handed these tensors.
-    torch.manual_seed(SEED)
+    torch.manual_seed(args.weight_seed)
     model = pkg.AVHotPath("hybrid")
     sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.to(dev).eval().set_precision(args.precision)
     model.fold_video_projection = not args.no_fold
     pkg.MCDropoutUncertainty._set_dropout_train(model)            # what MCDropoutUncertainty.forward does (:58-59)
 
-    def clip0_of(step):                                            # global clip index of this rank's batch
-        return (step * world + rank) * B
-
-    # two resident batches, alternated (each 4 GB >> 126 MB of L2)
-    pool = []
-    for j in range(2):
-        c0 = clip0_of(j)
-        pool.append(({"audio": pkg.synth.synth_audio(B, c0, SEED, dev), "video": pkg.synth.synth_video(B, c0, SEED, dev)},
-                     pkg.synth.modality_mask(B, c0, P_MODALITY, SEED, dev), c0))
-    torch.cuda.synchronize()
-
-    def step(j):
-        feats, mask, c0 = pool[j % 2]
-        mean, unc, labels, packed = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=c0)
-        if world > 1:
-            packed = par.all_gather_packed(packed, B * world)
-        return packed
+    ctx = Ctx()
+    ctx.torch, ctx.dist, ctx.pkg, ctx.par, ctx.dev, ctx.world, ctx.rank = torch, dist, pkg, par, dev, world, rank
+    ctx.model, ctx.args = model, args
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    ctx.barrier = barrier
 
-    for j in range(args.warmup):
-        step(j)
+    def clip0_of(step):                                            # global clip index of this rank's batch
+        return (step * world + rank) * B
+
+    tc = args.precision == "tc"
+    resolver = pkg.NearTieResolver(model, capacity=max(1024, B // 4)) if tc else None
+    ctx.resolver = resolver
+
+    if args.sweep:
+        line = run_sweep(ctx, args.sweep, B, T)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # two resident batches, alternated (each 18.8 GB >> 126 MB of L2)
+    pool = []
+    for j in range(2):
+        c0 = clip0_of(j)
+        feats, mask = synth_inputs(ctx, B, c0)
+        pool.append((feats, mask, c0))
+    torch.cuda.synchronize()
+
+    records = {}                     # step -> (labels, packed) of this rank, final after the window's flush
+
+    def run_steps(first, n, keep):
+        """n steps starting at `first`: windows of --resolve-every steps end with the near-tie flush, then the window's
+        packed records are all-gathered (one collective per window)."""
+        window = []
+        out = None
+        for j in range(first, first + n):
+            feats, mask, c0 = pool[j % 2]
+            mean, unc, labels, packed = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=c0,
+                                                         exact_labels=resolver if tc else False)
+            window.append((j, labels, packed))
+            if len(window) == args.resolve_every or j == first + n - 1:
+                if tc:
+                    resolver.flush()
+                local = window[0][2] if len(window) == 1 else torch.cat([w[2] for w in window], dim=0)
+                out = par.all_gather_packed(local, local.shape[0] * world) if world > 1 else local
+                if keep:
+                    for jj, lab, pk in window:
+                        records[jj] = (lab, pk)
+                window = []
+        return out
+
+    run_steps(0, args.warmup, False)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -255,10 +346,10 @@ def run_b200_arm(args):
     pkg._lib.prof_reset()
     pkg._lib.prof_enable(True)
     launches0 = pkg._lib.launch_count()
+    flagged0 = resolver.flagged_total if tc else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for j in range(args.steps):
-        out = step(args.warmup + j)
+    run_steps(args.warmup, args.steps, True)
     e1.record()
     barrier()
     launches = pkg._lib.launch_count() - launches0
@@ -271,12 +362,83 @@ def run_b200_arm(args):
     value = world * B * args.steps / (ms / 1e3)
     prof = pkg._lib.prof_report()
     pkg._lib.prof_reset()
+    flagged = (resolver.flagged_total - flagged0) if tc else 0
+
+    # ---- labels of every timed step against the fp32 CUDA path (itself checked against the oracle in tests/ and
+    # below), on a rotating sample of >= 1024 clips per step; outside the timed region ----------------------------
+    parity = None
+    if tc:
+        nchk = min(B, args.check_clips)
+        mism, worst, checked = 0, 0.0, 0
+        model.set_precision("fp32")
+        for j in range(args.warmup, args.warmup + args.steps):
+            feats, mask, c0 = pool[j % 2]
+            r0 = ((j - args.warmup) * nchk) % max(1, B - nchk + 1)
+            sub = {k: v[r0:r0 + nchk] for k, v in feats.items()}
+            ref = model.mc_forward(sub, mask[r0:r0 + nchk], num_samples=T, seed=SEED, clip0=c0 + r0)
+            lab, pk = records[j]
+            mism += int((lab[r0:r0 + nchk] != ref[2]).sum().item())
+            worst = max(worst, float((pk[r0:r0 + nchk, :N_CLASSES] - ref[0]).abs().max() / ref[0].abs().max()))
+            checked += nchk
+        model.set_precision(args.precision)
+        stats = torch.tensor([mism, checked, flagged], device=dev, dtype=torch.float64)
+        worst_t = torch.tensor([worst], device=dev)
+        if world > 1:
+            dist.all_reduce(stats)
+            dist.all_reduce(worst_t, op=dist.ReduceOp.MAX)
+        parity = {"label_mismatches": int(stats[0].item()), "clips_checked": int(stats[1].item()),
+                  "steps_checked": args.steps, "against": "fp32 CUDA path, rotating sample of every timed step, all ranks",
+                  "mean_logits_rel_err_vs_fp32_path": float(worst_t.item()),
+                  "near_tie_clips_reevaluated_in_fp32": int(stats[2].item()),
+                  "near_tie_fraction": float(stats[2].item()) / (world * B * args.steps)}
+    records.clear()
 
     # ---- end to end through the public API with host buffers --------------------------------------------------
-    e2e = None if args.no_e2e else run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier)
-    # the same leg with the frames kept as the uint8 pixels they are decoded to (src/dataprocessing.py:261-265
-    # divides by 255 on the host; here the division happens on the device): a quarter of the dominant H2D stream
-    e2e_u8 = None if args.no_e2e else run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8_frames=True)
+    e2e = e2e_f32 = h2d_peak = None
+    if not args.no_e2e:
+        h2d_peak = measure_h2d_peak(ctx)
+        # the clips as the decoders deliver them: uint8 pixels (src/dataprocessing.py:261-265 divides by 255 on the host;
+        # here on the device) and 16-bit PCM (the .wav's samples; load_raw_audio's peak normalisation on the device)
+        e2e = run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8")
+        e2e_f32 = run_e2e(ctx, B, T, clip0_of, audio="f32", video="f32")
+        for leg in (e2e, e2e_f32):
+            agg = h2d_peak["aggregate_gbs"]
+            leg["h2d_gbs_achieved"] = leg["h2d_bytes_per_step"] * world / (leg["ms_per_step"] / 1e3) / 1e9
+            leg["frac_of_measured_h2d_peak"] = leg["h2d_gbs_achieved"] / agg if agg else None
+
+    extra = {}
+    if not args.no_extra:
+        extra["config0_b8_concat_head"] = leg_config0(ctx)
+        extra["config1_frontend_4096"] = leg_config1(ctx)
+        extra["config2_forward_b512"] = leg_config2(ctx)
+        extra["config3_uncertainty_b256_t32"] = leg_config3(ctx)
+        extra["value_u8_i16_resident"] = leg_resident_decoded(ctx, B, T, clip0_of)
+        del pool
+        torch.cuda.empty_cache()
+        sw = run_sweep(ctx, args.extra_sweep, B, T)
+        extra["sweep_1m"] = {k: sw[k] for k in ("value", "unit", "scaling", "n_gpus", "ms_total", "config", "parity")}
+
+    # the oracle on a bounded sample of the same workload: labels must agree (rank 0; a smaller sample at N > 1)
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import model as om   # noqa: F401  (the checker / baseline leg)
+        threads = os.cpu_count() or 1
+        n = args.cpu_clips if world == 1 else max(32, args.cpu_clips // 4)
+        dt, dfe, cpu_mean = cpu_reference_step(n, T, clip0_of(0), sd_cpu, threads)
+        feats, mask = synth_inputs(ctx, n, clip0_of(0))
+        g = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=clip0_of(0))
+        rel = float((g[0].cpu() - cpu_mean).abs().max() / cpu_mean.abs().max())
+        cpu_baseline = {"value": n / dt, "unit": "clips/s", "cores": threads, "kind": "port",
+                        "value_without_frontend": n / (dt - dfe),
+                        "sample": f"{n} clips of the same workload, T={T} full forwards as src/uncertainty.py:62-65 runs "
+                                  f"them (torch.nn.LSTM + torch CPU ops fp32), {dt:.1f} s of which {dfe:.2f} s the numpy "
+                                  f"fp64 front-end (once per clip); Philox masks and inputs generated outside the timed "
+                                  f"region",
+                        "labels_equal_to_gpu": bool((g[2].cpu().long() == cpu_mean.argmax(1)).all()),
+                        "label_mismatches_vs_gpu": int((g[2].cpu().long() != cpu_mean.argmax(1)).sum()),
+                        "mean_logits_rel_err_vs_gpu": rel}
+    if world > 1:
+        dist.barrier()
 
     if rank != 0:
         if world > 1:
@@ -284,134 +446,295 @@ def run_b200_arm(args):
         return 0
 
     peaks = load_peaks()
-    stages = {}
-    for name, (tot, n) in sorted(prof.items()):
-        stages[name] = {"ms_per_step": tot / args.steps, "launches_per_step": n / args.steps}
-    # ---- rooflines: algorithmic bytes / FLOPs per launch over the CUDA-event time of the launch
-    tc = args.precision == "tc"
-    pitch = 320                                   # fp16 halves per row of the split LSTM operand (3 * 104 + 2, padded)
-    Bp = (B + 127) // 128 * 128
-    xp_bytes = Bp * T_FEATS * 4096                # one layer's input projections, fp32
-    algo = {   # name -> (bound, algorithmic bytes per step over all its launches, algorithmic FLOPs per step)
-        "frontend": ("hbm", B * N_SAMPLES * 4 + (Bp * T_FEATS * pitch * 2 if tc else B * T_FEATS * 104 * 4), 0),
-        "frame_gemm": ("hbm", B * BYTES_FRAMES + B * 16 * 256 * 4, B * FLOPS_FRAME_GEMM),
-        # xp is fp16 for both layers -> 2 x half an fp32 layer, written by the GEMM and read by the recurrence
-        "lstm_input_gemm_tc": ("hbm", xp_bytes + Bp * T_FEATS * (pitch + 256) * 2, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
-        "lstm_recurrence_tc": ("hbm", xp_bytes + Bp * T_FEATS * 256 * 2, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
-        "lstm_recurrence": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
-        "lstm_input_gemm": ("tensor", 0, B * (FLOPS_LSTM - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
-    }
-    extra = {}
-    for name, (bound, nbytes, nflops) in algo.items():
-        tot, n = prof.get(name, (0.0, 0))
-        if not n:
-            continue
-        sec = tot / args.steps / 1e3
-        ent = {"bound": bound, "ms_per_step": tot / args.steps, "launches_per_step": n / args.steps}
-        if nbytes:
-            ent.update({"hbm_gbs": nbytes / sec / 1e9, "hbm_frac": nbytes / sec / 1e9 / peaks["hbm_gbs"],
-                        "algorithmic_bytes_per_step": nbytes})
-        if nflops:
-            ent.update({"tflops": nflops / sec / 1e12, "tensor_frac": nflops / sec / 1e12 / peaks["tf_sustained"]})
-        if nbytes and nflops:       # a kernel that streams and contracts: the roofline it sits closer to is its bound
-            ent["bound"] = "tensor" if ent["tensor_frac"] > ent["hbm_frac"] else "hbm"
-        extra[name] = ent
-    # the dominant kernel = the one with the most device time per step among the stages with a stated roofline
-    roofline = None
-    if extra:
-        dom = max(extra, key=lambda k: extra[k]["ms_per_step"])
-        e = extra[dom]
-        tot, n = prof[dom]
-        if e["bound"] == "hbm":
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": e["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": e["hbm_frac"], "traffic": None}
-        else:
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": e["tflops"], "peak": peaks["tf_sustained"],
-                        "unit": "TFLOP/s", "frac": e["tensor_frac"], "traffic": None}
-        # DRAM traffic of that kernel per launch from the committed ncu capture of the same workload, if there is one
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                tr = json.load(f)
-            if tr.get("batch") == B and tr.get("precision") == args.precision:
-                roofline["traffic"] = tr["bytes_per_launch"].get(dom)
-                roofline["traffic_source"] = "profiles/ncu_traffic.json"
-                roofline["algorithmic_bytes_per_launch"] = e.get("algorithmic_bytes_per_step", 0) / (n / args.steps)
-        except (OSError, ValueError):
-            pass
-        roofline.update({"peak_source": peaks["source"], "avg_launch_ms": tot / n,
-                         "share_of_step": tot / args.steps / (ms / args.steps),
-                         "note": "dominant kernel by device time per step; every stage is in stage_rooflines"})
-
-    # labels of the timed precision against the fp32 CUDA path (itself checked against the oracle) on one batch
-    parity = None
-    if args.precision != "fp32":
-        feats, mask, c0 = pool[0]
-        nchk = min(B, 1024)
-        sub = {k: v[:nchk] for k, v in feats.items()}
-        a = model.mc_forward(sub, mask[:nchk], num_samples=T, seed=SEED, clip0=c0)
-        model.set_precision("fp32")
-        b = model.mc_forward(sub, mask[:nchk], num_samples=T, seed=SEED, clip0=c0)
-        model.set_precision(args.precision)
-        parity = {"clips": nchk, "label_mismatches_vs_fp32_path": int((a[2] != b[2]).sum().item()),
-                  "mean_logits_rel_err_vs_fp32_path": float((a[0] - b[0]).abs().max() / b[0].abs().max()),
-                  "uncertainty_rel_err_vs_fp32_path": float((a[1] - b[1]).abs().max() / b[1].abs().max())}
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import model as om
-        sd = sd_cpu                                                  # AVHotPath("hybrid") keys = the oracle's (Appendix A)
-        threads = os.cpu_count() or 1
-        cpu_reference_step(min(8, args.cpu_clips), 2, 0, sd, threads)          # warm-up
-        dt, cpu_mean = cpu_reference_step(args.cpu_clips, T, clip0_of(0), sd, threads)
-        # same clips through the CUDA path: labels must agree
-        feats, mask, c0 = pool[0]
-        n = args.cpu_clips
-        g_mean = model.mc_forward({k: v[:n] for k, v in feats.items()}, mask[:n], num_samples=T, seed=SEED, clip0=c0)[0]
-        rel = float((g_mean.cpu() - cpu_mean).abs().max() / cpu_mean.abs().max())
-        cpu_baseline = {"value": args.cpu_clips / dt, "unit": "clips/s", "cores": threads, "kind": "port",
-                        "sample": f"{args.cpu_clips} clips of the same workload, T={T} full forwards as "
-                                  f"src/uncertainty.py:62-65 runs them (torch.nn.LSTM + torch CPU ops fp32, numpy fp64 "
-                                  f"front-end once), {dt:.1f} s",
-                        "labels_equal_to_gpu": bool((g_mean.argmax(1).cpu() == cpu_mean.argmax(1)).all()),
-                        "mean_logits_rel_err_vs_gpu": rel}
-
     line = {"metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/f16 tensor-core operands, f32 accumulate",
             "data": "synthetic", "config": workload_config(args, B),
-            "e2e": e2e, "e2e_u8_frames": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "stages": stages, "stage_rooflines": extra,
+            "e2e": e2e, "e2e_fp32_inputs": e2e_f32, "h2d_copy_peak": h2d_peak, "gpu_launches": int(launches),
+            "clocks": clocks, "cpu_baseline": cpu_baseline, "parity": parity, "extra": extra,
             "host_numa_node_rank0": numa}
+    line.update(rooflines(prof, args, B, ms, peaks))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8_frames=False):
+def rooflines(prof, args, B, ms, peaks):
+    """Per-kernel CUDA-event times (avhot_prof_*) -> stages, stage rooflines and the dominant kernel's roofline.
+    Algorithmic bytes / FLOPs are SURVEY.md 8(d)'s per-clip figures x the clips of a launch; the bound of a stage is
+    fixed (8(d)'s column), design-imposed intermediates (xp, split operands) are NOT algorithmic bytes - they show up
+    in `traffic`, the DRAM bytes ncu measured for the same launch (profiles/ncu_traffic.json)."""
+    steps = args.steps
+    stages = {n: {"ms_per_step": t / steps, "launches_per_step": k / steps} for n, (t, k) in sorted(prof.items())}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("batch") != B or tr.get("precision") != args.precision or "bytes_per_step" not in tr:
+            tr = None
+    except (OSError, ValueError):
+        tr = None
+    hbm, tfs = peaks["hbm_gbs"], peaks["tf_sustained"]      # kernels timed inside a long step: the sustained figure
+
+    def ms_of(names):
+        return sum(prof.get(n, (0.0, 0))[0] for n in names) / steps
+
+    def traffic_of(names):
+        if not tr:
+            return None
+        vals = [tr["bytes_per_step"].get(n) for n in names if n in prof]
+        return sum(vals) if vals and all(v is not None for v in vals) else None
+
+    groups = {   # stage -> (kernels, bound, algorithmic bytes per step, algorithmic FLOPs per step)
+        "frontend": (["frontend"], "hbm", B * BYTES_FRONTEND, 0),
+        "lstm": (["lstm_split3", "lstm_input_gemm_tc", "lstm_recurrence_tc", "lstm_input_gemm", "lstm_recurrence",
+                  "lstm_fused_tc", "lstm_projection"], "tensor", B * BYTES_LSTM, B * FLOPS_LSTM),
+        "video": (["frame_u8_to_f32", "frame_gemm"], "hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
+        "mc_tail": (["frame_tail", "fusion_clip", "fusion_tc", "fusion_pass", "hybrid_fusion", "mc_reduce"], "tensor",
+                    B * BYTES_MC_TAIL, B * args.passes * FLOPS_MC_PASS),
+    }
+    stage_rooflines = {}
+    for name, (kernels, bound, nbytes, nflops) in groups.items():
+        t = ms_of(kernels)
+        if t <= 0:
+            continue
+        sec = t / 1e3
+        ent = {"kernels": [k for k in kernels if k in prof], "bound": bound, "ms_per_step": t,
+               "algorithmic_bytes_per_step": nbytes, "algorithmic_flops_per_step": nflops,
+               "dram_traffic_bytes_per_step": traffic_of(kernels)}
+        if bound == "hbm":
+            ent.update({"achieved": nbytes / sec / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / sec / 1e9 / hbm})
+        else:
+            ent.update({"achieved": nflops / sec / 1e12, "peak": tfs, "unit": "TFLOP/s",
+                        "frac": nflops / sec / 1e12 / tfs})
+        if ent["dram_traffic_bytes_per_step"]:
+            ent["traffic_over_algorithmic"] = ent["dram_traffic_bytes_per_step"] / nbytes
+        stage_rooflines[name] = ent
+    # the dominant kernel = the single kernel with the most device time per step; its roofline is its stage's bound with
+    # the stage's algorithmic work attributed to the kernels of the stage in proportion... no: a kernel that is a whole
+    # stage (front-end, video GEMM) carries the stage's figures; the LSTM kernels carry their own FLOPs.
+    per_kernel = {
+        "frontend": ("hbm", B * BYTES_FRONTEND, 0),
+        "frame_gemm": ("hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
+        "lstm_recurrence_tc": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
+        "lstm_input_gemm_tc": ("tensor", 0, B * (537_542_656 - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
+        "lstm_fused_tc": ("tensor", 0, B * 537_542_656),
+        "lstm_recurrence": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
+        "lstm_input_gemm": ("tensor", 0, B * (537_542_656 - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
+        "fusion_tc": ("tensor", 0, B * args.passes * 1_841_664),
+    }
+    roofline = None
+    timed_kernels = {k: v for k, v in prof.items() if v[1] and k in per_kernel}
+    if timed_kernels:
+        dom = max(timed_kernels, key=lambda k: timed_kernels[k][0])
+        tot, n = prof[dom]
+        bound, nbytes, nflops = per_kernel[dom]
+        per_launch_s = tot / n / 1e3
+        lps = n / steps
+        if bound == "hbm":
+            ach = nbytes / lps / per_launch_s / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "algorithmic_bytes_per_launch": nbytes / lps}
+        else:
+            ach = nflops / lps / per_launch_s / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tfs, "unit": "TFLOP/s",
+                        "frac": ach / tfs, "algorithmic_flops_per_launch": nflops / lps}
+        roofline["traffic"] = (tr["bytes_per_step"].get(dom) / lps) if tr and tr["bytes_per_step"].get(dom) else None
+        roofline.update({"traffic_source": "profiles/ncu_traffic.json (ncu --set full of this command)" if tr else None,
+                         "peak_source": peaks["source"] + (", sustained bf16 figure: the kernel is timed inside a long step"
+                                                           if bound == "tensor" else ""),
+                         "avg_launch_ms": tot / n, "share_of_step": tot / steps / (ms / steps),
+                         "note": "dominant kernel by device time per step; every stage is in stage_rooflines"})
+    e2e_roof = {"bound": "tensor", "algorithmic_flops_per_clip": FLOPS_E2E_T1 + args.passes * FLOPS_MC_PASS,
+                "roofline_clips_per_sec_sustained": tfs * 1e12 / (FLOPS_E2E_T1 + args.passes * FLOPS_MC_PASS)}
+    return {"roofline": roofline, "stages": stages, "stage_rooflines": stage_rooflines, "end_to_end_roofline": e2e_roof}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# extra legs: BASELINE configs[0..3], decoded-format resident inputs, the 1 M-clip sweep
+# ---------------------------------------------------------------------------------------------------------------
+def _leg(ctx, fn, clips_per_iter, iters=10, warm=3, **kw):
+    for i in range(warm):
+        fn(i)
+    ms = timed(ctx, lambda i: fn(warm + i), iters)
+    out = {"ms_per_iter": ms / iters, "clips_per_iter": clips_per_iter, "iters": iters, "warmup": warm,
+           "clips_per_sec": ctx.world * clips_per_iter * iters / (ms / 1e3)}
+    out.update(kw)
+    return out
+
+
+def leg_config0(ctx):
+    """configs[0]: configs/base.yaml audio+video baseline forward, batch 8 -> 8-class logits (front-end + LSTM + frame
+    encoder + the live concat head, src/train.py:153-164), fp32 kernels, eval mode.  32 distinct batches rotate
+    (256 MB > L2)."""
+    torch, pkg, dev = ctx.torch, ctx.pkg, ctx.dev
+    torch.manual_seed(SEED)
+    m = pkg.AVHotPath("concat").to(dev).eval()
+    feats, _ = synth_inputs(ctx, 8 * 32, 7_000_000)
+    batches = [{k: v[8 * i:8 * i + 8] for k, v in feats.items()} for i in range(32)]
+    return _leg(ctx, lambda i: m(batches[i % 32], None), 8, iters=32, precision="fp32",
+                l2_policy="32 distinct batches rotate (256 MB of inputs > 126 MB L2)")
+
+
+def leg_config1(ctx):
+    """configs[1]: log-mel front-end only on 4096 synthetic 3 s clips; roofline 4096 x 317 216 B / measured HBM copy
+    bandwidth (burst figure: the kernel is timed alone)."""
+    pkg, dev = ctx.pkg, ctx.dev
+    waves = [pkg.synth.synth_audio(4096, 8_000_000 + 4096 * j, SEED, dev) for j in range(2)]
+    out = _leg(ctx, lambda i: pkg.logmel_mfcc(waves[i % 2]), 4096, l2_policy="inputs larger than L2 (786 MB), two alternate")
+    peaks = load_peaks()
+    nbytes = 4096 * BYTES_FRONTEND
+    floor_ms = nbytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    out.update({"roofline": {"bound": "hbm", "algorithmic_bytes": nbytes, "roofline_ms": floor_ms,
+                             "achieved": nbytes / (out["ms_per_iter"] / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": floor_ms / out["ms_per_iter"]}})
+    return out
+
+
+def leg_config2(ctx):
+    """configs[2]: full audio+video cross-modal attention fusion forward, batch 512, tensor-core precision, T = 1, eval."""
+    feats = [synth_inputs(ctx, 512, 9_000_000 + 512 * j) for j in range(2)]
+    m, args = ctx.model, ctx.args
+    m.eval()
+    try:
+        return _leg(ctx, lambda i: m(feats[i % 2][0], feats[i % 2][1]), 512, precision=args.precision,
+                    l2_policy="inputs larger than L2 (510 MB), two alternate")
+    finally:
+        ctx.pkg.MCDropoutUncertainty._set_dropout_train(m)
+
+
+def leg_config3(ctx):
+    """configs[3]: uncertainty inference, T = 32 MC-dropout passes, modality dropout p = 0.05, batch 256 (labels made
+    exact before returning: mc_forward's immediate mode, one host round trip per call)."""
+    feats = [synth_inputs(ctx, 256, 9_500_000 + 256 * j) for j in range(2)]
+    m, args = ctx.model, ctx.args
+    return _leg(ctx, lambda i: m.mc_forward(feats[i % 2][0], feats[i % 2][1], num_samples=args.passes, seed=SEED,
+                                            clip0=9_500_000 + 256 * (i % 2)), 256, precision=args.precision,
+                l2_policy="inputs larger than L2 (255 MB), two alternate")
+
+
+def leg_resident_decoded(ctx, B, T, clip0_of):
+    """The main step with the inputs resident in HBM in the decoders' formats (uint8 pixels, 16-bit PCM)."""
+    pool = [synth_inputs(ctx, B, clip0_of(j), audio="i16", video="u8") + (clip0_of(j),) for j in range(2)]
+    m, res, args = ctx.model, ctx.resolver, ctx.args
+
+    def fn(i):
+        feats, mask, c0 = pool[i % 2]
+        m.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=c0, exact_labels=res if res else False)
+        if res and (i + 1) % args.resolve_every == 0:
+            res.flush()
+    out = _leg(ctx, fn, B, iters=max(4, args.resolve_every), warm=3, precision=args.precision)
+    if res:
+        res.flush()
+    return out
+
+
+def run_sweep(ctx, n_total, B, T):
+    """configs[4]: n_total synthetic clips, index-sharded over the ranks (contiguous ranges, parallel.shard_range), each
+    rank walking its shard in steps of B clips; the near-tie flush and one all-gather of the packed records every
+    --resolve-every steps.  Strong scaling: total work fixed.  The clip INPUTS come from two resident batches that
+    alternate (1 M clips are 1 TB); the clip indices - and so every Philox mask and modality mask - are the sweep's."""
+    torch, pkg, par, dev, world, rank, args = ctx.torch, ctx.pkg, ctx.par, ctx.dev, ctx.world, ctx.rank, ctx.args
+    model, res = ctx.model, ctx.resolver
+    lo, hi = par.shard_range(n_total, rank, world)
+    counts = par.shard_counts(n_total, world)
+    pool = [synth_inputs(ctx, B, lo + j * B) for j in range(2)]
+    n_steps = (max(counts) + B - 1) // B                       # every rank runs the same number of steps / collectives
+
+    def sweep():
+        window, flips_checked = [], None
+        for j in range(n_steps):
+            c0 = lo + j * B
+            n = max(0, min(B, hi - c0))
+            feats, _ = pool[j % 2]
+            sub = {k: v[:n] for k, v in feats.items()} if n < B else feats
+            mask = pkg.synth.modality_mask(n, c0, P_MODALITY, SEED, dev)
+            packed = model.mc_forward(sub, mask, num_samples=T, seed=SEED, clip0=c0,
+                                      exact_labels=res if res else False)[3]
+            window.append(packed)
+            if len(window) == args.resolve_every or j == n_steps - 1:
+                if res:
+                    res.flush()
+                local = torch.cat(window, dim=0)
+                if world > 1:                                  # ranks may hold different row counts in the last window
+                    pad = torch.zeros(len(window) * B, local.shape[1], device=dev)
+                    pad[:local.shape[0]] = local
+                    out = torch.empty(world * pad.shape[0], pad.shape[1], device=dev)
+                    ctx.dist.all_gather_into_tensor(out, pad)
+                window = []
+        return None
+
+    # warm-up: three steps of the same shapes
+    for j in range(3):
+        feats, mask = pool[j % 2]
+        model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=lo + j * B, exact_labels=res if res else False)
+    if res:
+        res.flush()
+    f0 = res.flagged_total if res else 0
+    ms = timed(ctx, lambda i: sweep(), 1)
+    # labels of the last full step against the fp32 path on a 1024-clip sample (outside the timed region)
+    parity = None
+    if res and counts[rank] >= B:
+        j = counts[rank] // B - 1
+        c0, nchk = lo + j * B, min(B, 1024)
+        feats, _ = pool[j % 2]
+        sub = {k: v[:nchk] for k, v in feats.items()}
+        mask = pkg.synth.modality_mask(nchk, c0, P_MODALITY, SEED, dev)
+        a = model.mc_forward(sub, mask, num_samples=T, seed=SEED, clip0=c0)
+        model.set_precision("fp32")
+        b = model.mc_forward(sub, mask, num_samples=T, seed=SEED, clip0=c0)
+        model.set_precision(args.precision)
+        parity = {"label_mismatches": int((a[2] != b[2]).sum().item()), "clips_checked": nchk,
+                  "near_tie_clips_reevaluated_in_fp32_rank0": res.flagged_total - f0}
+    del pool
+    return {"metric": "clips_per_sec", "value": n_total / (ms / 1e3), "unit": "clips/s", "n_gpus": world,
+            "steps": n_steps, "warmup": 3, "ms_per_step": ms / n_steps, "ms_total": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "tf32/f16 tensor-core operands, f32 accumulate",
+            "data": "synthetic", "parity": parity,
+            "config": {"workload": f"BASELINE.json configs[4]: {n_total}-clip synthetic sweep, index-sharded over {world} "
+                                   f"rank(s), steps of {B} clips, all-gather of the packed (B, 9) records every "
+                                   f"{args.resolve_every} steps", "mc_passes": T, "modality_dropout_p": P_MODALITY,
+                       "precision": args.precision,
+                       "l2_policy": "inputs larger than L2, two resident batches alternate; clip indices (masks) advance"}}
+
+
+def measure_h2d_peak(ctx):
+    """What the host can feed: pinned host -> device copy of 1 GiB, all ranks at once, best of 3 (max over ranks of the
+    time, so the aggregate is what the ranks achieve together) - the ceiling of the e2e legs."""
+    torch, dev, world = ctx.torch, ctx.dev, ctx.world
+    n = 1 << 30
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h.zero_()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    best = None
+    for _ in range(3):
+        ms = timed(ctx, lambda i: d.copy_(h, non_blocking=True), 1)
+        best = ms if best is None else min(best, ms)
+    per_rank = n / (best / 1e3) / 1e9
+    del h, d
+    return {"per_rank_gbs": per_rank, "aggregate_gbs": per_rank * world, "ranks": world,
+            "how": "cudaMemcpyAsync pinned host -> device, 1 GiB per rank, all ranks concurrently, best of 3"}
+
+
+def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
     """Same step through the public API (AVHotPath.mc_forward = MCDropoutUncertainty's fast path) with inputs in
     pinned HOST memory: every step uploads its B clips host->device in sub-batches of --e2e-chunk clips and reads the
     packed results back; the upload of sub-batch i+1 overlaps the kernels of sub-batch i on a second stream (two
     device staging slots).  The pinned source ring holds two sub-batches (real copies every time; clip indices for
-    the Philox masks advance normally)."""
-    import torch
-    import torch.distributed as dist
+    the Philox masks advance normally).  The near-tie flush runs once per step, before the results are read back."""
+    torch, dist, pkg, par, dev, world, args = ctx.torch, ctx.dist, ctx.pkg, ctx.par, ctx.dev, ctx.world, ctx.args
+    model, res = ctx.model, ctx.resolver
     C = min(args.e2e_chunk, B)
     n_sub = (B + C - 1) // C
-    host = []
+    host, slots = [], []
     for j in range(2):
-        c0 = clip0_of(j)
-        a = pkg.synth.synth_audio(C, c0, SEED, dev)
-        v = pkg.synth.synth_video(C, c0, SEED, dev, dtype=torch.uint8 if u8_frames else torch.float32)
-        m = pkg.synth.modality_mask(C, c0, P_MODALITY, SEED, dev)
-        ha = torch.empty(a.shape, dtype=a.dtype, pin_memory=True).copy_(a)
-        hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v)
-        hm = torch.empty(m.shape, dtype=m.dtype, pin_memory=True).copy_(m)
-        host.append((ha, hv, hm))
-        del a, v, m
-    slots = [(torch.empty(C, N_SAMPLES, device=dev),
-              torch.empty(C, N_FRAMES, FRAME_DIM, device=dev, dtype=torch.uint8 if u8_frames else torch.float32),
-              torch.empty(C, 2, device=dev)) for _ in range(2)]
+        feats, m = synth_inputs(ctx, C, clip0_of(j), audio=audio, video=video)
+        a, v = feats["audio"], feats["video"]
+        host.append(tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (a, v, m)))
+        slots.append(tuple(torch.empty_like(t) for t in (a, v, m)))
+        del feats, a, v, m
     packed_dev = torch.empty(B, N_CLASSES + 1, device=dev)
     result_host = torch.empty(B * world, N_CLASSES + 1, pin_memory=True)
     copy_stream = torch.cuda.Stream(dev)
@@ -423,45 +746,51 @@ def run_e2e(args, pkg, par, model, dev, world, rank, B, T, clip0_of, barrier, u8
     def run(n_steps, step0):
         for j in range(n_steps):
             base = clip0_of(step0 + j)
+            parts = []
             for i in range(n_sub):
                 n = min(C, B - i * C)
                 k = counter[0]
                 counter[0] += 1
                 s = k % 2
-                ha, hv, hm = host[s]
                 with torch.cuda.stream(copy_stream):
                     if k >= 2:
                         copy_stream.wait_event(consumed[s])
-                    slots[s][0][:n].copy_(ha[:n], non_blocking=True)
-                    slots[s][1][:n].copy_(hv[:n], non_blocking=True)
-                    slots[s][2][:n].copy_(hm[:n], non_blocking=True)
+                    for dst, src in zip(slots[s], host[s]):
+                        dst[:n].copy_(src[:n], non_blocking=True)
                     uploaded[s].record(copy_stream)
                 main.wait_event(uploaded[s])
                 packed = model.mc_forward({"audio": slots[s][0][:n], "video": slots[s][1][:n]}, slots[s][2][:n],
-                                          num_samples=T, seed=SEED, clip0=base + i * C)[3]
+                                          num_samples=T, seed=SEED, clip0=base + i * C,
+                                          exact_labels=res if res else False)[3]
                 consumed[s].record(main)
+                parts.append((i, n, packed))
+            if res:
+                res.flush()                               # patches the sub-batches' packed records in place
+            for i, n, packed in parts:
                 packed_dev[i * C:i * C + n].copy_(packed)
             out = par.all_gather_packed(packed_dev, B * world) if world > 1 else packed_dev
             result_host.copy_(out, non_blocking=True)
 
     run(1, 0)
-    barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
     copy_stream.wait_event(e0)
     run(args.steps, 1)
     e1.record(main)
-    barrier()
+    ctx.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    in_bytes = N_SAMPLES * 4 + N_FRAMES * FRAME_DIM * (1 if u8_frames else 4) + 2 * 4
+    in_bytes = N_SAMPLES * (2 if audio == "i16" else 4) + N_FRAMES * FRAME_DIM * (1 if video == "u8" else 4) + 2 * 4
     return {"value": world * B * args.steps / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms / args.steps,
             "h2d_bytes_per_step": B * in_bytes, "d2h_bytes_per_step": B * world * BYTES_OUT_PER_CLIP,
-            "api": f"AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), pinned host buffers "
-                   f"(fp32 audio, {'uint8' if u8_frames else 'fp32'} frames), {n_sub} sub-batches of <= {C} clips per "
-                   f"step, uploads double-buffered on a copy stream"}
+            "input_format": {"audio": "16-bit PCM" if audio == "i16" else "fp32 waveform",
+                             "video": "uint8 pixels" if video == "u8" else "fp32 k/255"},
+            "api": f"AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), pinned host buffers, {n_sub} "
+                   f"sub-batches of <= {C} clips per step, uploads double-buffered on a copy stream, near-tie flush once per "
+                   f"step"}
 
 
 def main():
@@ -475,8 +804,15 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=2048, help="clips per host->device sub-batch in the e2e leg")
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU sample (~10 s of host work)")
+    ap.add_argument("--check-clips", type=int, default=1024, help="clips of every timed step checked against the fp32 path")
+    ap.add_argument("--resolve-every", type=int, default=5,
+                    help="steps per near-tie window: the flagged clips of a window are re-evaluated in fp32 together")
+    ap.add_argument("--weight-seed", type=int, default=SEED, help="torch.manual_seed for the random-init weights")
+    ap.add_argument("--sweep", type=int, default=0, help="strong-scaling mode: this many clips in total over all ranks")
+    ap.add_argument("--extra-sweep", type=int, default=1_000_000, help="size of the sweep leg under `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (kernel A/B runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[0..3] / sweep legs")
     ap.add_argument("--no-fold", action="store_true",
                     help="keep z_v materialised instead of folding FrameEncoder.projection[1] into the fusion GEMM (A/B)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
@@ -484,6 +820,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                                         # timing rule: W >= 3
+    args.resolve_every = max(1, args.resolve_every)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)

@@ -46,7 +46,6 @@ typedef enum {
  * outside the contractions is fp32 in every mode. */
 typedef enum {
   AVHOT_PREC_FP32 = 0,   /* fp32 FMA on CUDA cores: the parity path (1e-4 relative)            */
-  AVHOT_PREC_BF16X3 = 1, /* reserved: split operands, 3 tensor-core passes (not built)         */
   AVHOT_PREC_TC = 2      /* tcgen05 tensor cores, operands rounded once: TF32 for the
                             time-batched GEMMs, fp16 for the recurrent GEMM; stated tolerance
                             in DESIGN.md                                                       */
@@ -95,6 +94,10 @@ int avhot_synth_video(float* frames_f32, uint8_t* frames_u8, int B, int n_elems_
  * divided by max|.| when that is > 0.  lengths may be NULL (= in_stride). */
 int avhot_condition_audio(const float* in, const int32_t* lengths, float* out, int B,
                           int in_stride, int n_out, avhot_stream_t stream);
+/* The same for 16-bit PCM as a .wav file holds it (sample k = k / 32768, the conversion librosa.load applies at
+ * src/dataprocessing.py:196): bit-identical to avhot_condition_audio on the converted samples, half the bytes in. */
+int avhot_condition_audio_i16(const int16_t* in, const int32_t* lengths, float* out, int B,
+                              int in_stride, int n_out, avhot_stream_t stream);
 
 /* ---- a2: log-mel + MFCC front-end (no reference code; spec in oracle/frontend.py) --- */
 /* wave (B, n_samples) -> feats (B, 1 + n_samples/160, 104) = [64 log-mel | 40 MFCC]. */
@@ -173,8 +176,8 @@ typedef struct {
   int frame_dim, hidden_dim, output_dim; /* ctor args, src/encoders.py:203-210 */
   const float* mlp_weight;               /* frame_mlp.0.weight (H, frame_dim)  */
   const float* mlp_bias;                 /* frame_mlp.0.bias   (H)             */
-  const float* attn_weight;              /* attention.weight   (1, H)          */
-  const float* attn_bias;                /* attention.bias     (1)             */
+  const float* attn_weight;              /* attention.weight   (1, H); both NULL for      */
+  const float* attn_bias;                /* attention.bias     (1)     average/max pooling */
   const float* ln_weight;                /* projection.0.weight (H)            */
   const float* ln_bias;                  /* projection.0.bias   (H)            */
   const float* proj_weight;              /* projection.1.weight (out, H)       */
@@ -197,6 +200,21 @@ int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, const uint8_t* 
 int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z,
                      int B, int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
                      avhot_stream_t stream);
+/* forward with temporal_pooling = 'average' / 'max' (src/encoders.py:276-293; `mask` = frame_valid: masked mean with
+ * the count clamped to >= 1, masked max with invalid frames at finfo.min), or 'attention' (= avhot_frame_tail). */
+enum { AVHOT_POOL_ATTENTION = 0, AVHOT_POOL_AVERAGE = 1, AVHOT_POOL_MAX = 2 };
+int avhot_frame_tail_pool(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z,
+                          int B, int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                          int pooling, avhot_stream_t stream);
+/* FrameEncoder.attention_pool (src/encoders.py:300-327) on its own: frames (B, F, hidden) already encoded ->
+ * pooled (B, hidden) = softmax_f(attention(frames)) weighted sum; frame_valid as above or NULL. */
+int avhot_frame_attention_pool(avhot_frame_t h, const float* frames, const uint8_t* frame_valid,
+                               float* pooled, int B, int F, avhot_stream_t stream);
+/* avhot_frame_tail with the global index of every clip given explicitly - clip_ids (B) uint32, device - instead of
+ * clip0 + b: rows of scattered clips draw the masks they would draw at their place in the full batch (exact.py). */
+int avhot_frame_tail_ids(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z,
+                         int B, int F, int T, float p, uint64_t seed, const uint32_t* clip_ids, uint32_t t0,
+                         avhot_stream_t stream);
 /* The same up to and including projection[0] = LayerNorm (src/encoders.py:246-248): y (B, T, hidden) fp32.  The
  * tensor-core hot path feeds y to a HybridFusion handle whose proj_layers.video is the product of projection[1]
  * (src/encoders.py:249) and proj_layers.video (src/fusion.py:486) - two linear maps with nothing in between. */
@@ -259,6 +277,11 @@ int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
                          void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 /* workspace (optional, avhot_fusion_workspace_bytes): lets the hybrid path compute the pass-invariant
  * half of modality 0 once per clip when z_rows_per_clip[0] == 1 (same results, fewer FLOPs). */
+/* logits only, with per-row global clip indices clip_ids (B) uint32 (device) instead of clip0 + b (exact.py) */
+int avhot_fusion_forward_ids(avhot_fusion_t h, const float* const* z_host_array,
+                             const int* z_rows_per_clip_host, const float* mask, float* logits, int B, int T,
+                             float p, uint64_t seed, const uint32_t* clip_ids, uint32_t t0, int precision,
+                             void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 
 /* ---- SURVEY.md 8(f) "next": the other fusion heads behind build_fusion_model and the calibration metrics ------ */
 typedef struct avhot_head* avhot_head_t;
@@ -389,6 +412,27 @@ int avhot_pair_combine(const float* self_feat, const float* const* msgs_host_arr
 int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
                     int32_t* labels, float* packed, int B, int T, int C,
                     avhot_stream_t stream);
+
+/* ---- label exactness of AVHOT_PREC_TC (north star: labels identical to the reference, whose prediction is
+ * argmax of the fp32 mean logits, src/uncertainty.py:77).  A clip whose top-2 margin of mean_logits is below
+ * margin_rel * max|mean_logits| (margin_rel = twice the stated tolerance of the tensor-core path) is appended to a
+ * pending list: entry e < capacity gets entry_tag[e] = tag (the caller's id of this call), entry_row[e] = b,
+ * entry_clip[e] = low 32 bits of clip0 + b.  state: 4 uint32 on the device, zeroed by the caller when a window of
+ * calls starts: [0] entries appended (can exceed capacity), [1] overflow flag, [2] entries before the latest call,
+ * [3] max|mean_logits| of the latest call (float bits).  No host synchronisation. */
+int avhot_flag_near_ties(const float* mean_logits, int B, int C, float margin_rel, uint32_t tag,
+                         uint64_t clip0, uint32_t* state, uint32_t* entry_tag, uint32_t* entry_row,
+                         uint32_t* entry_clip, int capacity, avhot_stream_t stream);
+/* rows entry_row[e] of src (B rows of row_bytes bytes, a multiple of 16) -> pool row e, for the entries the latest
+ * avhot_flag_near_ties call appended: the inputs of the pending clips, kept for their fp32 re-evaluation */
+int avhot_gather_flagged(const void* src, size_t row_bytes, int B, const uint32_t* state,
+                         const uint32_t* entry_row, void* pool, int capacity, avhot_stream_t stream);
+/* records of the n re-evaluated entries (src_packed (n, C+1), src_labels (n)) -> the result tensors of the call
+ * whose tag is `tag` (rows entry_row[e] where entry_tag[e] == tag); any destination may be NULL */
+int avhot_scatter_resolved(const uint32_t* entry_tag, const uint32_t* entry_row, int n, uint32_t tag,
+                           const float* src_packed, const int32_t* src_labels, float* mean_logits,
+                           float* uncertainty, int32_t* labels, float* packed, int C,
+                           avhot_stream_t stream);
 
 #define AVHOT_SITE_FRAME_MLP 0u
 #define AVHOT_SITE_FRAME_POOL 1u

@@ -47,16 +47,18 @@ class Handle:
 
 
 class Workspace:
-    """Grow-only scratch buffer per device (the C ABI never allocates in the forward calls)."""
+    """Grow-only scratch buffer per (device, current stream): the C ABI never allocates in the forward calls, and two
+    forwards issued on different streams of one device must not share scratch memory."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, nbytes: int, dev: torch.device):
         nbytes = max(int(nbytes), 256)
-        b = self._buf.get(dev)
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
-            self._buf[dev] = None
+            self._buf[key] = None
             b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._buf[dev] = b
+            self._buf[key] = b
         return b

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AVHOT_LIB_PATH") or os.path.join(HERE, "libavhot.so")   # override: A/B runs of two builds
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
-PREC_FP32, PREC_BF16X3, PREC_TC = 0, 1, 2
+PREC_FP32, PREC_TC = 0, 2
+POOL_ATTENTION, POOL_AVERAGE, POOL_MAX = 0, 1, 2
 SITE_FRAME_MLP, SITE_FRAME_POOL, SITE_GATE, SITE_MODMASK, SITE_ATTN = 0, 1, 2, 3, 16
 SITE_EARLY0, SITE_EARLY1, SITE_LATE = 4, 5, 32
 SITE_CNN0, SITE_CNN1 = 6, 7
@@ -121,6 +122,7 @@ PROTOTYPES = {
     "avhot_synth_audio": (_I, [_P, _I, _I, _U64, _U64, _P]),
     "avhot_synth_video": (_I, [_P, _P, _I, _I, _U64, _U64, _P]),
     "avhot_condition_audio": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "avhot_condition_audio_i16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "avhot_frontend": (_I, [_P, _P, _I, _I, _P]),
     "avhot_frontend_ex": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "avhot_frontend_tables_host": (_I, [_P, _P, _P]),
@@ -144,6 +146,14 @@ PROTOTYPES = {
     "avhot_frame_hidden": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
     "avhot_frame_tail": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P]),
     "avhot_frame_tail_norm": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _P]),
+    "avhot_frame_tail_pool": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _U64, _U32, _I, _P]),
+    "avhot_frame_attention_pool": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "avhot_frame_tail_ids": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _U64, _P, _U32, _P]),
+    "avhot_fusion_forward_ids": (_I, [_P, C.POINTER(_P), C.POINTER(_I), _P, _P, _I, _I, _F, _U64, _P, _U32, _I, _P, _SZ,
+                                      _P]),
+    "avhot_flag_near_ties": (_I, [_P, _I, _I, _F, _U32, _U64, _P, _P, _P, _P, _I, _P]),
+    "avhot_gather_flagged": (_I, [_P, _SZ, _I, _P, _P, _P, _I, _P]),
+    "avhot_scatter_resolved": (_I, [_P, _P, _I, _U32, _P, _P, _P, _P, _P, _P, _I, _P]),
     "avhot_xattn_create": (_I, [C.POINTER(XattnDesc), C.POINTER(_P), _P]),
     "avhot_xattn_destroy": (None, [_P]),
     "avhot_xattn_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
@@ -185,9 +195,12 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        if not os.environ.get("AVHOT_LIB_PATH"):
+            # stamp-checked: a library built from other sources than the ones on disk (a stale binary would be loaded
+            # with mismatching ctypes struct layouts) is rebuilt; an up-to-date one costs a hash of csrc/
             from . import build as _build      # nvcc cross-compiles without a GPU
-            _build.build()
+            if os.path.exists(_build.NVCC) or not os.path.exists(LIB_PATH):
+                _build.build()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)            # AttributeError here = header/library mismatch

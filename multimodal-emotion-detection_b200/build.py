@@ -34,12 +34,20 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+LAST_ACTION = None      # "compiled" | "reused" after build(): which of the two the last call did
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libavhot.so unless the library on disk was built from exactly these sources and flags
+    (sha256 stamp over csrc/, include/ and the flags)."""
+    global LAST_ACTION
     os.makedirs(OBJ, exist_ok=True)
     stamp_file = os.path.join(OBJ, "stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        LAST_ACTION = "reused"
         return LIB
+    LAST_ACTION = "compiled"
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
@@ -66,4 +74,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv), f"({LAST_ACTION})")

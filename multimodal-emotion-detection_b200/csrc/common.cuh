@@ -133,6 +133,8 @@ struct DropSpec {  // what a kernel needs to draw the masks of one launch
   uint32_t thr;          // drop threshold (0 => dropout off)
   float scale;           // 1/(1-p)
   uint64_t clip0;        // global index of clip 0 of this launch
+  const uint32_t* clip_ids;   // optional (device): global index of clip b = clip_ids[b] instead of clip0 + b (the fp32
+                              // re-evaluation of scattered near-tie clips, avhot_*_ids)
   uint32_t t0;           // pass index of pass 0 of this launch
   uint32_t rk0[10], rk1[10];   // the ten round keys of (k0, k1): kernel parameters live in the constant bank, so the
                                // XOR of a round reads them as an operand instead of re-deriving them (philox4x32_10_rk)
@@ -144,12 +146,17 @@ static inline DropSpec make_drop(float p, uint64_t seed, uint64_t clip0, uint32_
   d.thr = p > 0.f ? drop_threshold(p) : 0u;
   d.scale = p > 0.f ? keep_scale(p) : 1.0f;
   d.clip0 = clip0;
+  d.clip_ids = nullptr;
   d.t0 = t0;
   for (int r = 0; r < 10; ++r) {
     d.rk0[r] = d.k0 + (uint32_t)r * 0x9E3779B9u;
     d.rk1[r] = d.k1 + (uint32_t)r * 0xBB67AE85u;
   }
   return d;
+}
+// Philox counter word of clip b of the launch (low 32 bits of its global index)
+__device__ __forceinline__ uint32_t ds_clip(const DropSpec& ds, int b) {
+  return ds.clip_ids ? __ldg(ds.clip_ids + b) : (uint32_t)(ds.clip0 + (uint64_t)b);
 }
 // philox4x32_10(c0, c1, c2, c3, ds.k0, ds.k1) with the key schedule taken from the DropSpec (a kernel parameter): saves
 // the 18 key additions per block that the compiler otherwise re-issues for every block (frame_tail_kernel draws 34 M

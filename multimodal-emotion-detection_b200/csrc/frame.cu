@@ -27,6 +27,7 @@ struct avhot_frame {
   float* proj_wt;   // [j][o] = projection.1.weight[o][j]
   float* proj_b;    // (out)
   float* arena;
+  bool has_attention;
 };
 
 namespace avhot {
@@ -39,7 +40,10 @@ constexpr int FT_WARPS = 8;
 // projection[1] into HybridFusion's proj_layers.video (two linear maps with nothing in between, src/encoders.py:249 ->
 // src/fusion.py:486), so the H -> out projection - 31 % of this kernel's instructions - runs as part of a GEMM that is
 // on the tensor cores anyway (avhot_frame_tail_norm).
-template <bool PROJECT>
+// POOL: 0 = attention pooling (the hot path, configs/base.yaml:43), 1 = average, 2 = max (src/encoders.py:276-293).
+// RAW (with PROJECT = false): write the pooled row before the second dropout / LayerNorm = FrameEncoder.attention_pool
+// (src/encoders.py:300-327).
+template <bool PROJECT, int POOL = 0, bool RAW = false>
 __global__ void __launch_bounds__(FT_WARPS * 32, PROJECT ? 3 : 4)
 frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, pre-dropout
                   const uint8_t* __restrict__ valid,    // (B, F) 1 = valid frame, or NULL
@@ -66,7 +70,7 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
     if (row < n_rows) {                                    // warp-uniform
       // 32-bit row arithmetic (the entry points check B * T < 2^31): a 64-bit division costs ~100 instructions
       const int b = (int)((uint32_t)row / (uint32_t)T), t = (int)((uint32_t)row - (uint32_t)b * (uint32_t)T);
-      const uint32_t g = (uint32_t)(ds.clip0 + (uint64_t)b), pass = ds.t0 + (uint32_t)t;
+      const uint32_t g = ds_clip(ds, b), pass = ds.t0 + (uint32_t)t;
       const float* hb = hid + (size_t)b * F * FH;
       float m = -INFINITY, denom = 0.f;
       float pooled[8];
@@ -83,6 +87,20 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
           const Philox4 r = philox4x32_10_rk((uint32_t)(f * 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds);
 #pragma unroll
           for (int q = 0; q < 8; ++q) x[q] = philox_half(r, (uint32_t)q) >= thr16 ? x[q] : 0.f;
+        }
+        if (POOL != 0) {
+          const bool ok = !valid || valid[(size_t)b * F + f];
+          if (POOL == 1) {            // masked mean: sum of the valid frames (:277-283)
+            if (ok) {
+              denom += 1.f;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) pooled[q] += x[q];
+            }
+          } else {                    // masked max: invalid frames count as finfo.min (:285-292)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pooled[q] = f == 0 ? (ok ? x[q] : -FLT_MAX) : fmaxf(pooled[q], ok ? x[q] : -FLT_MAX);
+          }
+          continue;
         }
         float s = x[0] * aw0.x + x[1] * aw0.y + x[2] * aw0.z + x[3] * aw0.w +
                   x[4] * aw1.x + x[5] * aw1.y + x[6] * aw1.z + x[7] * aw1.w;
@@ -103,9 +121,16 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
           for (int q = 0; q < 8; ++q) pooled[q] = fmaf(e, x[q], pooled[q]);
         }
       }
-      const float inv = ds.scale / denom;
+      // the deferred 1 / (1 - p) of the frame_mlp dropout; average: clamp_min(count, 1) (:280); max of nothing but
+      // invalid frames stays finfo.min
+      const float inv = POOL == 2 ? ds.scale : ds.scale / (POOL == 1 ? fmaxf(denom, 1.f) : denom);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) pooled[q] *= inv;
+      for (int q = 0; q < 8; ++q) pooled[q] = (POOL == 2 && pooled[q] == -FLT_MAX) ? pooled[q] : pooled[q] * inv;
+      if (RAW) {
+        *reinterpret_cast<float4*>(z + (size_t)row * FH + c0) = make_float4(pooled[0], pooled[1], pooled[2], pooled[3]);
+        *reinterpret_cast<float4*>(z + (size_t)row * FH + c1) = make_float4(pooled[4], pooled[5], pooled[6], pooled[7]);
+        continue;
+      }
       if (drop) {     // site FRAME_POOL (32-bit draws): element e = col, block e >> 2
         const Philox4 r0 = philox4x32_10_rk((uint32_t)(2 * lane), g, pass, AVHOT_SITE_FRAME_POOL, ds);
         const Philox4 r1 = philox4x32_10_rk((uint32_t)(2 * lane + 1), g, pass, AVHOT_SITE_FRAME_POOL, ds);
@@ -201,8 +226,9 @@ extern "C" int avhot_frame_create(const avhot_frame_desc* d, avhot_frame_t* out,
                 "(configs/base.yaml:44)", d->hidden_dim);
   AVHOT_REQUIRE((d->frame_dim & 3) == 0, AVHOT_ERR_UNSUPPORTED, "frame_create: frame_dim=%d must be a multiple of 4",
                 d->frame_dim);
-  AVHOT_REQUIRE(d->mlp_weight && d->mlp_bias && d->attn_weight && d->attn_bias && d->ln_weight && d->ln_bias &&
-                    d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "frame_create: tensors missing");
+  // attention.* may be NULL: FrameEncoder(temporal_pooling='average' | 'max') has no attention layer (src/encoders.py:236-241)
+  AVHOT_REQUIRE(d->mlp_weight && d->mlp_bias && (d->attn_weight != nullptr) == (d->attn_bias != nullptr) && d->ln_weight &&
+                    d->ln_bias && d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "frame_create: tensors missing");
   const int H = FH, O = d->output_dim;
   const size_t sizes[8] = {(size_t)H * d->frame_dim, (size_t)H, (size_t)H, 1, (size_t)H, (size_t)H, (size_t)O * H, (size_t)O};
   size_t total = 0;
@@ -225,6 +251,9 @@ extern "C" int avhot_frame_create(const avhot_frame_desc* d, avhot_frame_t* out,
   const float* src[8] = {d->mlp_weight, d->mlp_bias, d->attn_weight, d->attn_bias, d->ln_weight, d->ln_bias,
                          nullptr, d->proj_bias};
   int rc = AVHOT_OK;
+  h->has_attention = d->attn_weight != nullptr;
+  if (!h->has_attention && cudaMemsetAsync(dst[2], 0, align256f(sizes[2] * sizeof(float)) + align256f(sizeof(float)), s) != cudaSuccess)
+    rc = AVHOT_ERR_CUDA;
   for (int i = 0; i < 8 && rc == AVHOT_OK; ++i) {
     if (!src[i]) continue;
     if (cudaMemcpyAsync(dst[i], src[i], sizes[i] * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
@@ -284,39 +313,72 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
                   B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
 }
 
-extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B,
-                                int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
-                                avhot_stream_t stream) {
+static int frame_tail_impl(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B, int F, int T,
+                           float p, uint64_t seed, uint64_t clip0, const uint32_t* clip_ids, uint32_t t0, bool project,
+                           avhot_stream_t stream, int pooling = AVHOT_POOL_ATTENTION, bool raw = false) {
   AVHOT_REQUIRE(h && hid && z && B >= 0 && F >= 1 && T >= 1, AVHOT_ERR_INVALID, "frame_tail: bad arguments");
   AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "frame_tail: dropout p=%g outside [0, 1)", (double)p);
   AVHOT_REQUIRE((long long)F * 64 + 64 <= 0xffffffffLL, AVHOT_ERR_INVALID, "frame_tail: F too large");
+  AVHOT_REQUIRE(h->has_attention || (pooling != AVHOT_POOL_ATTENTION && !raw), AVHOT_ERR_INVALID,
+                "frame_tail: attention pooling on an encoder created without attention.weight / attention.bias");
+  AVHOT_REQUIRE(project || (reinterpret_cast<uintptr_t>(z) & 15) == 0, AVHOT_ERR_INVALID,
+                "frame_tail_norm: y must be 16-byte aligned");
   if (B == 0) return AVHOT_OK;
   const long long rows = (long long)B * T;
   const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
   AVHOT_REQUIRE(rows < 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail: B*T too large for one call");
+  DropSpec ds = make_drop(p, seed, clip0, t0);
+  ds.clip_ids = clip_ids;
   ProfScope prof("frame_tail", as_stream(stream));
-  frame_tail_kernel<true><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
-      hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
-      make_drop(p, seed, clip0, t0));
+#define AVHOT_TAIL_LAUNCH(...)                                                                                       \
+  frame_tail_kernel<__VA_ARGS__><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(                            \
+      hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim, ds)
+  if (raw) {
+    AVHOT_TAIL_LAUNCH(false, 0, true);
+  } else if (pooling == AVHOT_POOL_AVERAGE) {
+    AVHOT_TAIL_LAUNCH(true, 1, false);
+  } else if (pooling == AVHOT_POOL_MAX) {
+    AVHOT_TAIL_LAUNCH(true, 2, false);
+  } else if (project)
+    frame_tail_kernel<true><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
+        hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim, ds);
+  else
+    frame_tail_kernel<false><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
+        hid, frame_valid, z, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim, ds);
+#undef AVHOT_TAIL_LAUNCH
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
+}
+
+extern "C" int avhot_frame_tail_pool(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B,
+                                     int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0, int pooling,
+                                     avhot_stream_t stream) {
+  AVHOT_REQUIRE(pooling == AVHOT_POOL_ATTENTION || pooling == AVHOT_POOL_AVERAGE || pooling == AVHOT_POOL_MAX,
+                AVHOT_ERR_INVALID, "frame_tail_pool: unknown pooling %d", pooling);
+  return frame_tail_impl(h, hid, frame_valid, z, B, F, T, p, seed, clip0, nullptr, t0, true, stream, pooling);
+}
+
+extern "C" int avhot_frame_attention_pool(avhot_frame_t h, const float* frames, const uint8_t* frame_valid,
+                                          float* pooled, int B, int F, avhot_stream_t stream) {
+  return frame_tail_impl(h, frames, frame_valid, pooled, B, F, 1, 0.f, 0, 0, nullptr, 0, false, stream,
+                         AVHOT_POOL_ATTENTION, true);
+}
+
+extern "C" int avhot_frame_tail(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B,
+                                int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
+                                avhot_stream_t stream) {
+  return frame_tail_impl(h, hid, frame_valid, z, B, F, T, p, seed, clip0, nullptr, t0, true, stream);
+}
+
+extern "C" int avhot_frame_tail_ids(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B,
+                                    int F, int T, float p, uint64_t seed, const uint32_t* clip_ids, uint32_t t0,
+                                    avhot_stream_t stream) {
+  AVHOT_REQUIRE(clip_ids, AVHOT_ERR_INVALID, "frame_tail_ids: clip_ids is NULL");
+  return frame_tail_impl(h, hid, frame_valid, z, B, F, T, p, seed, 0, clip_ids, t0, true, stream);
 }
 
 extern "C" int avhot_frame_tail_norm(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* y, int B,
                                      int F, int T, float p, uint64_t seed, uint64_t clip0, uint32_t t0,
                                      avhot_stream_t stream) {
-  AVHOT_REQUIRE(h && hid && y && B >= 0 && F >= 1 && T >= 1, AVHOT_ERR_INVALID, "frame_tail_norm: bad arguments");
-  AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "frame_tail_norm: dropout p=%g outside [0, 1)", (double)p);
-  AVHOT_REQUIRE((long long)F * 64 + 64 <= 0xffffffffLL, AVHOT_ERR_INVALID, "frame_tail_norm: F too large");
-  AVHOT_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, AVHOT_ERR_INVALID, "frame_tail_norm: y must be 16-byte aligned");
-  if (B == 0) return AVHOT_OK;
-  const long long rows = (long long)B * T;
-  const long long grid = (rows + FT_ROWS - 1) / FT_ROWS;
-  AVHOT_REQUIRE(rows < 0x7fffffffLL, AVHOT_ERR_INVALID, "frame_tail_norm: B*T too large for one call");
-  ProfScope prof("frame_tail", as_stream(stream));
-  frame_tail_kernel<false><<<(unsigned)grid, FT_WARPS * 32, 0, as_stream(stream)>>>(
-      hid, frame_valid, y, h->attn_w, h->attn_b, h->ln_w, h->ln_b, h->proj_wt, h->proj_b, B, F, T, h->output_dim,
-      make_drop(p, seed, clip0, t0));
-  AVHOT_LAUNCH_CHECK();
-  return AVHOT_OK;
+  return frame_tail_impl(h, hid, frame_valid, y, B, F, T, p, seed, clip0, nullptr, t0, false, stream);
 }

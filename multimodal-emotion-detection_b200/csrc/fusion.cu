@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) hybrid_fusion_kernel(const Fusion
       float a[FM] = {e0 / den, e1 / den};
       if (all_inv) { a[0] = 0.f; a[1] = 0.f; }                                       // :124-128
       if (P.ds.thr != 0u) {                                                          // :130, site ATTN + i
-        const Philox4 w = philox4x32_10((uint32_t)(hh >> 1), (uint32_t)(P.ds.clip0 + (uint64_t)b),
+        const Philox4 w = philox4x32_10((uint32_t)(hh >> 1), ds_clip(P.ds, b),
                                         P.ds.t0 + (uint32_t)t, AVHOT_SITE_ATTN + i, P.ds.k0, P.ds.k1);
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) hybrid_fusion_kernel(const Fusion
         if (row >= n_rows) row = n_rows - 1;
         const int b = (int)(row / P.T), t = (int)(row % P.T);
         const uint32_t e = (uint32_t)(m * FG + g);
-        const Philox4 w = philox4x32_10(e >> 2, (uint32_t)(P.ds.clip0 + (uint64_t)b), P.ds.t0 + (uint32_t)t,
+        const Philox4 w = philox4x32_10(e >> 2, ds_clip(P.ds, b), P.ds.t0 + (uint32_t)t,
                                         AVHOT_SITE_GATE, P.ds.k0, P.ds.k1);
         v = philox_word(w, e & 3) >= P.ds.thr ? v * P.ds.scale : 0.f;
       }
@@ -624,7 +624,7 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
       float a0 = e0 / den, a1 = e1 / den;
       if (inv0 && inv1) { a0 = 0.f; a1 = 0.f; }
       if (P.ds.thr != 0u) {
-        const Philox4 w = philox4x32_10((uint32_t)(head >> 1), (uint32_t)(P.ds.clip0 + (uint64_t)b),
+        const Philox4 w = philox4x32_10((uint32_t)(head >> 1), ds_clip(P.ds, b),
                                         P.ds.t0 + (uint32_t)tpass[j], AVHOT_SITE_ATTN + i, P.ds.k0, P.ds.k1);
         a0 = philox_word(w, (uint32_t)((head & 1) * 2)) >= P.ds.thr ? a0 * P.ds.scale : 0.f;
         a1 = philox_word(w, (uint32_t)((head & 1) * 2 + 1)) >= P.ds.thr ? a1 * P.ds.scale : 0.f;
@@ -709,7 +709,7 @@ fusion_pass_kernel(const FusionParams P, const float* __restrict__ clipbuf) {
       float va = fmaxf(a0[j], 0.f), vb = fmaxf(a1[j], 0.f);
       if (P.ds.thr != 0u) {
         const uint32_t e = (uint32_t)(m * FG + g0);           // even: both elements are in one Philox block
-        const Philox4 w = philox4x32_10(e >> 2, (uint32_t)(P.ds.clip0 + (uint64_t)bclip[j]),
+        const Philox4 w = philox4x32_10(e >> 2, ds_clip(P.ds, bclip[j]),
                                         P.ds.t0 + (uint32_t)tpass[j], AVHOT_SITE_GATE, P.ds.k0, P.ds.k1);
         va = philox_word(w, e & 3) >= P.ds.thr ? va * P.ds.scale : 0.f;
         vb = philox_word(w, (e & 3) + 1) >= P.ds.thr ? vb * P.ds.scale : 0.f;
@@ -982,11 +982,35 @@ extern "C" size_t avhot_fusion_workspace_bytes(avhot_fusion_t h, int B, int T) {
   return sizeof(float) * (size_t)B * FCB * FD;
 }
 
+static int fusion_forward_impl(avhot_fusion_t h, const float* const* z_host_array,
+                               const int* z_rows_per_clip_host, const float* mask, float* logits,
+                               float* fusion_weights, float* attn, float* h_att, int B, int T, float p,
+                               uint64_t seed, uint64_t clip0, const uint32_t* clip_ids, uint32_t t0, int precision,
+                               void* workspace, size_t workspace_bytes, avhot_stream_t stream);
+
 extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host_array,
                                     const int* z_rows_per_clip_host, const float* mask, float* logits,
                                     float* fusion_weights, float* attn, float* h_att, int B, int T, float p,
                                     uint64_t seed, uint64_t clip0, uint32_t t0, int precision, void* workspace,
                                     size_t workspace_bytes, avhot_stream_t stream) {
+  return fusion_forward_impl(h, z_host_array, z_rows_per_clip_host, mask, logits, fusion_weights, attn, h_att, B, T, p,
+                             seed, clip0, nullptr, t0, precision, workspace, workspace_bytes, stream);
+}
+
+extern "C" int avhot_fusion_forward_ids(avhot_fusion_t h, const float* const* z_host_array,
+                                        const int* z_rows_per_clip_host, const float* mask, float* logits, int B, int T,
+                                        float p, uint64_t seed, const uint32_t* clip_ids, uint32_t t0, int precision,
+                                        void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
+  AVHOT_REQUIRE(clip_ids, AVHOT_ERR_INVALID, "fusion_forward_ids: clip_ids is NULL");
+  return fusion_forward_impl(h, z_host_array, z_rows_per_clip_host, mask, logits, nullptr, nullptr, nullptr, B, T, p,
+                             seed, 0, clip_ids, t0, precision, workspace, workspace_bytes, stream);
+}
+
+static int fusion_forward_impl(avhot_fusion_t h, const float* const* z_host_array,
+                               const int* z_rows_per_clip_host, const float* mask, float* logits,
+                               float* fusion_weights, float* attn, float* h_att, int B, int T, float p,
+                               uint64_t seed, uint64_t clip0, const uint32_t* clip_ids, uint32_t t0, int precision,
+                               void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
   AVHOT_REQUIRE(h && z_host_array && z_rows_per_clip_host && logits && B >= 0 && T >= 1, AVHOT_ERR_INVALID,
                 "fusion_forward: bad arguments");
   AVHOT_REQUIRE(p >= 0.f && p < 1.f, AVHOT_ERR_INVALID, "fusion_forward: dropout p=%g outside [0, 1)", (double)p);
@@ -1018,6 +1042,7 @@ extern "C" int avhot_fusion_forward(avhot_fusion_t h, const float* const* z_host
     P.g0_wt = h->g0_wt; P.g0_b = h->g0_b; P.g3_w = h->g3_w; P.g3_b = h->g3_b;
     P.cls_w = h->cls_w; P.cls_b = h->cls_b;
     P.ds = make_drop(p, seed, clip0, t0);
+    P.ds.clip_ids = clip_ids;
     // token 0 given once per clip and no per-row diagnostics requested: hoist its pass-invariant half
     if (P.rpc[0] == 1 && !fusion_weights && !attn && !h_att && workspace &&
         workspace_bytes >= avhot_fusion_workspace_bytes(h, B, T)) {

@@ -193,7 +193,7 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
       const bool live = row < n_rows;
       if (!live) row = n_rows - 1;
       const int b = (int)((uint32_t)row / (uint32_t)P.T), t = (int)((uint32_t)row - (uint32_t)b * (uint32_t)P.T);
-      const uint32_t gclip = (uint32_t)(P.ds.clip0 + (uint64_t)b), pass = P.ds.t0 + (uint32_t)t;
+      const uint32_t gclip = ds_clip(P.ds, b), pass = P.ds.t0 + (uint32_t)t;
       const float* cbuf = P.clipbuf + (size_t)b * (6 * UD);
       const bool inv0 = P.mask ? (__ldg(P.mask + (size_t)b * 2) <= 0.f) : false;
       const bool inv1 = P.mask ? (__ldg(P.mask + (size_t)b * 2 + 1) <= 0.f) : false;

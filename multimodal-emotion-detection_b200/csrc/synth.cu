@@ -93,6 +93,26 @@ __global__ void __launch_bounds__(1024) condition_audio_kernel(const float* __re
   }
 }
 
+// the same for 16-bit PCM (what a RAVDESS .wav holds): sample k means k / 32768 (soundfile / librosa.load's conversion,
+// src/dataprocessing.py:196); (k / 32768) / (peak / 32768) == fp32(k) / fp32(peak) exactly, both being the correctly
+// rounded quotient of the same real number, so the result is bit-identical to the fp32 entry point's
+__global__ void __launch_bounds__(1024) condition_audio_i16_kernel(const int16_t* __restrict__ in,
+                                                                   const int32_t* __restrict__ lengths,
+                                                                   float* __restrict__ out, int in_stride, int n_out) {
+  __shared__ float red[32];
+  const int16_t* x = in + (size_t)blockIdx.x * in_stride;
+  float* y = out + (size_t)blockIdx.x * n_out;
+  int len = lengths ? lengths[blockIdx.x] : in_stride;
+  len = max(0, min(len, min(in_stride, n_out)));
+  float peak = 0.f;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) peak = fmaxf(peak, i < len ? fabsf((float)x[i]) : 0.f);
+  peak = block_max_1024(peak, red);
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const float v = i < len ? (float)x[i] : 0.f;
+    y[i] = peak > 0.f ? __fdiv_rn(v, peak) : 0.f;
+  }
+}
+
 __global__ void dropout_keep_kernel(uint8_t* __restrict__ keep, int n_elems, uint64_t clip0, uint32_t t,
                                     uint32_t site, uint32_t thr, uint32_t k0, uint32_t k1) {
   const uint32_t g = (uint32_t)(clip0 + blockIdx.y);
@@ -155,6 +175,17 @@ extern "C" int avhot_condition_audio(const float* in, const int32_t* lengths, fl
                 "condition_audio: bad arguments");
   if (B == 0) return AVHOT_OK;
   condition_audio_kernel<<<B, 1024, 0, as_stream(stream)>>>(in, lengths, out, in_stride, n_out);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+extern "C" int avhot_condition_audio_i16(const int16_t* in, const int32_t* lengths, float* out, int B,
+                                         int in_stride, int n_out, avhot_stream_t stream) {
+  AVHOT_REQUIRE(in && out && B >= 0 && in_stride > 0 && n_out > 0, AVHOT_ERR_INVALID,
+                "condition_audio_i16: bad arguments");
+  if (B == 0) return AVHOT_OK;
+  ProfScope prof("condition_audio_i16", as_stream(stream));
+  condition_audio_i16_kernel<<<B, 1024, 0, as_stream(stream)>>>(in, lengths, out, in_stride, n_out);
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }

@@ -80,7 +80,7 @@ xattn_core_kernel(const float* __restrict__ Q, const float* __restrict__ K, cons
       if (all_inv) a[u] = 0.f;                                              // :124-128
       if (ds.thr != 0u) {                                                   // :130
         const uint32_t e = (uint32_t)((h * Tq + tq) * Tk + tk);
-        const Philox4 w = philox4x32_10(e >> 2, (uint32_t)(ds.clip0 + (uint64_t)b), ds.t0, site, ds.k0, ds.k1);
+        const Philox4 w = philox4x32_10(e >> 2, ds_clip(ds, b), ds.t0, site, ds.k0, ds.k1);
         a[u] = philox_word(w, e & 3) >= ds.thr ? a[u] * ds.scale : 0.f;
       }
       if (attn) attn[(((size_t)b * heads + h) * Tq + tq) * Tk + tk] = a[u];

@@ -31,12 +31,14 @@ def n_frames(n_samples: int) -> int:
 
 def condition_audio(wave: torch.Tensor, lengths: torch.Tensor | None = None, n_out: int | None = None) -> torch.Tensor:
     """wave (B, N_in) CUDA -> (B, n_out) fp32: first min(len_b, n_out) samples, right zero padded, divided by
-    max|.| when > 0 (src/dataprocessing.py:198-211)."""
+    max|.| when > 0 (src/dataprocessing.py:198-211).  int16 input is 16-bit PCM (sample k = k / 32768, what
+    librosa.load makes of a 16-bit .wav, :196): same result, bit for bit, as converting first."""
     dev = _lib.require_cuda(wave, lengths)
     _lib.check_device(dev)
     if wave.dim() != 2:
         raise ValueError(f"wave must be (B, N), got {tuple(wave.shape)}")
-    wave = _lib.f32c(wave)
+    pcm = wave.dtype == torch.int16
+    wave = wave.contiguous() if pcm else _lib.f32c(wave)
     B, n_in = wave.shape
     n_out = int(n_out if n_out is not None else n_in)
     if lengths is not None:
@@ -45,8 +47,9 @@ def condition_audio(wave: torch.Tensor, lengths: torch.Tensor | None = None, n_o
             raise ValueError("lengths must be (B,)")
     out = torch.empty(B, n_out, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().avhot_condition_audio(_lib.ptr(wave), _lib.ptr(lengths), _lib.ptr(out), B, n_in,
-                                                     n_out, _lib.stream_ptr(dev)), "condition_audio")
+        fn = _lib.load().avhot_condition_audio_i16 if pcm else _lib.load().avhot_condition_audio
+        _lib.check(fn(_lib.ptr(wave), _lib.ptr(lengths), _lib.ptr(out), B, n_in, n_out, _lib.stream_ptr(dev)),
+                   "condition_audio")
     return out
 
 

@@ -231,6 +231,8 @@ class SequenceEncoder(nn.Module):
         if T < 1:
             raise ValueError("empty sequence")
         if lengths is not None:
+            # values outside [1, T] are clamped by the kernels (the reference's pack_padded_sequence raises for them;
+            # checking here would cost a host round trip per call)
             lengths = torch.as_tensor(lengths).to(device=dev, dtype=torch.int32).contiguous()
             if lengths.shape != (B,):
                 raise ValueError("lengths must be (B,)")
@@ -238,6 +240,11 @@ class SequenceEncoder(nn.Module):
             return self._forward_cnn(x)[:, 0, :]               # `lengths` is ignored for this type (:157-168)
         if self.encoder_type == 'transformer':
             return self._forward_transformer(x, lengths)[:, 0, :]
+        if self.rnn.training and self.rnn.dropout > 0 and self.num_layers > 1:
+            # nn.LSTM / nn.GRU apply inter-layer dropout in train mode; these kernels are the inference path (under
+            # MCDropoutUncertainty the rnn stays in eval mode: it is not an nn.Dropout module, src/uncertainty.py:41-46)
+            raise ValueError(f"SequenceEncoder({self.encoder_type}): train-mode inter-layer dropout is not built; "
+                             "call eval() (MC-dropout passes keep the recurrent layers in eval mode)")
         out = torch.empty(B, self.output_dim, device=dev, dtype=torch.float32)
         if B == 0:
             return out
@@ -304,17 +311,16 @@ class FrameEncoder(nn.Module):
         if temporal_pooling == 'attention':
             self.attention = nn.Linear(hidden_dim, 1)                                 # :236
         elif temporal_pooling in ('average', 'max'):
-            raise ValueError(f"temporal_pooling '{temporal_pooling}' exists in the reference but is not built in "
-                             "this library (hot path = 'attention')")
+            pass                                                                      # :237-240: no extra parameters
         else:
             raise ValueError(f"Unknown pooling: {temporal_pooling}")                  # :242
         self.projection = nn.Sequential(nn.LayerNorm(hidden_dim), nn.Linear(hidden_dim, output_dim))  # :246-249
         self._handle = Handle("avhot_frame_destroy")
 
     def _params(self):
-        return [self.frame_mlp[0].weight, self.frame_mlp[0].bias, self.attention.weight, self.attention.bias,
-                self.projection[0].weight, self.projection[0].bias, self.projection[1].weight,
-                self.projection[1].bias]
+        att = [self.attention.weight, self.attention.bias] if self.temporal_pooling == 'attention' else []
+        return [self.frame_mlp[0].weight, self.frame_mlp[0].bias] + att + [
+            self.projection[0].weight, self.projection[0].bias, self.projection[1].weight, self.projection[1].bias]
 
     def _get_handle(self, dev):
         ps = [_lib.f32c(p.detach()) for p in self._params()]
@@ -323,8 +329,11 @@ class FrameEncoder(nn.Module):
         def create():
             d = _lib.FrameDesc()
             d.frame_dim, d.hidden_dim, d.output_dim = self.frame_dim, self.hidden_dim, self.output_dim
+            ptrs = [p.data_ptr() for p in ps]
+            if self.temporal_pooling != 'attention':
+                ptrs[2:2] = [None, None]                      # no attention layer (average / max pooling)
             (d.mlp_weight, d.mlp_bias, d.attn_weight, d.attn_bias, d.ln_weight, d.ln_bias, d.proj_weight,
-             d.proj_bias) = [p.data_ptr() for p in ps]
+             d.proj_bias) = ptrs
             out = C.c_void_p()
             _lib.check(_lib.load().avhot_frame_create(C.byref(d), C.byref(out), _lib.stream_ptr(dev)),
                        "FrameEncoder")
@@ -361,7 +370,7 @@ class FrameEncoder(nn.Module):
 
     @torch.no_grad()
     def tail(self, hid: torch.Tensor, mask: Optional[torch.Tensor] = None, passes: int = 1, p: float = 0.0,
-             seed: int = 0, clip0: int = 0, t0: int = 0, project: bool = True) -> torch.Tensor:
+             seed: int = 0, clip0: int = 0, t0: int = 0, project: bool = True, clip_ids=None) -> torch.Tensor:
         """Everything after the ReLU for `passes` stochastic passes: (B, F, H) -> (B, passes, out).
         project=False stops after projection[0] (the LayerNorm) and returns (B, passes, H): the tensor-core hot path
         folds projection[1] into HybridFusion's proj_layers.video (HybridFusion.run(..., video_norm_from=...))."""
@@ -377,6 +386,21 @@ class FrameEncoder(nn.Module):
             return z
         with torch.cuda.device(dev):
             h = self._get_handle(dev)
+            if clip_ids is not None:                      # scattered clips: per-row global indices (fp32 path only)
+                if not project:
+                    raise ValueError("clip_ids needs project=True")
+                _lib.check(_lib.load().avhot_frame_tail_ids(h, _lib.ptr(hid), _lib.ptr(valid), _lib.ptr(z), B, F, passes,
+                                                            float(p), seed, _lib.ptr(clip_ids), t0, _lib.stream_ptr(dev)),
+                           "FrameEncoder.tail")
+                return z
+            if self.temporal_pooling != 'attention':
+                if not project:
+                    raise ValueError("project=False is the attention-pooling hot path")
+                pooling = _lib.POOL_AVERAGE if self.temporal_pooling == 'average' else _lib.POOL_MAX
+                _lib.check(_lib.load().avhot_frame_tail_pool(h, _lib.ptr(hid), _lib.ptr(valid), _lib.ptr(z), B, F, passes,
+                                                             float(p), seed, clip0, t0, pooling, _lib.stream_ptr(dev)),
+                           "FrameEncoder.tail")
+                return z
             fn = _lib.load().avhot_frame_tail if project else _lib.load().avhot_frame_tail_norm
             _lib.check(fn(h, _lib.ptr(hid), _lib.ptr(valid), _lib.ptr(z), B, F, passes, float(p), seed, clip0, t0,
                           _lib.stream_ptr(dev)), "FrameEncoder.tail")
@@ -395,14 +419,30 @@ class FrameEncoder(nn.Module):
         seed, t, clip0 = _rng.current()
         return self.tail(hid, mask, 1, self._drop_p(), seed, clip0, t)[:, 0, :]
 
+    @torch.no_grad()
     def attention_pool(self, frames: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """src/encoders.py:300-327 on already-encoded frames (B, F, H) -> (B, H).  Off the hot path (forward fuses
-        it); provided for signature parity with plain torch ops on the caller's device."""
-        scores = torch.nn.functional.linear(frames, self.attention.weight, self.attention.bias).squeeze(-1)
+        """src/encoders.py:300-327 on already-encoded frames (B, F, H) -> (B, H): the pooling stage of the tail kernel
+        on its own (avhot_frame_attention_pool)."""
+        dev = _lib.require_cuda(frames, mask)
+        _lib.check_device(dev)
+        if self.temporal_pooling != 'attention':
+            raise AttributeError("attention_pool needs temporal_pooling='attention'")    # the reference has no self.attention
+        if frames.dim() != 3 or frames.shape[2] != self.hidden_dim:
+            raise ValueError(f"frames must be (B, F, {self.hidden_dim}), got {tuple(frames.shape)}")
+        x = _lib.f32c(frames)
+        B, F, _ = x.shape
+        valid = None
         if mask is not None:
-            scores = scores.masked_fill(~mask.bool(), torch.finfo(scores.dtype).min)
-        weights = torch.softmax(scores, dim=1)
-        return torch.einsum('bt,bth->bh', weights, frames)
+            valid = torch.as_tensor(mask).to(device=dev).bool().to(torch.uint8).contiguous()
+            if valid.shape != (B, F):
+                raise ValueError("mask must be (B, num_frames)")
+        pooled = torch.empty(B, self.hidden_dim, device=dev, dtype=torch.float32)
+        if B > 0:
+            with torch.cuda.device(dev):
+                h = self._get_handle(dev)
+                _lib.check(_lib.load().avhot_frame_attention_pool(h, _lib.ptr(x), _lib.ptr(valid), _lib.ptr(pooled), B, F,
+                                                                  _lib.stream_ptr(dev)), "FrameEncoder.attention_pool")
+        return pooled
 
 
 def build_encoder(modality: str, input_dim: int, output_dim: int, encoder_config: dict = None) -> nn.Module:

@@ -129,8 +129,10 @@ class HybridFusion(nn.Module):
 
     @torch.no_grad()
     def run(self, zs, rows_per_clip, mask, B: int, passes: int, p: float, seed: int, clip0: int, t0: int,
-            want_info: bool = False, folded_from=None):
+            want_info: bool = False, folded_from=None, clip_ids=None):
         """logits (B, passes, C) for per-modality embeddings zs[m] of (B * rows_per_clip[m], dim_m).
+        clip_ids: optional (B,) int32/uint32-valued CUDA tensor of global clip indices (instead of clip0 + b): the fp32
+        re-evaluation of scattered near-tie clips (exact.NearTieResolver).
         folded_from = (index, nn.Linear): zs[index] is the INPUT of that Linear (whose output is modality `index`'s
         embedding); the Linear is folded into proj_layers[index] of a second handle."""
         dev = zs[0].device
@@ -156,11 +158,19 @@ class HybridFusion(nn.Module):
                     h = self._get_handle(dev)
                 lib = _lib.load()
                 ws = _ws.get(lib.avhot_fusion_workspace_bytes(h, B, passes), dev)
-                _lib.check(lib.avhot_fusion_forward(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits), _lib.ptr(fw),
-                                                    _lib.ptr(attn), _lib.ptr(hatt), B, passes, float(p), seed, clip0,
-                                                    t0, self.precision, _lib.ptr(ws), ws.numel(),
-                                                    _lib.stream_ptr(dev)),
-                           "HybridFusion.forward")
+                if clip_ids is not None:
+                    if want_info:
+                        raise ValueError("clip_ids and want_info are mutually exclusive")
+                    _lib.check(lib.avhot_fusion_forward_ids(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits), B, passes,
+                                                            float(p), seed, _lib.ptr(clip_ids), t0, self.precision,
+                                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                               "HybridFusion.forward")
+                else:
+                    _lib.check(lib.avhot_fusion_forward(h, arr, rpc, _lib.ptr(mask), _lib.ptr(logits), _lib.ptr(fw),
+                                                        _lib.ptr(attn), _lib.ptr(hatt), B, passes, float(p), seed, clip0,
+                                                        t0, self.precision, _lib.ptr(ws), ws.numel(),
+                                                        _lib.stream_ptr(dev)),
+                               "HybridFusion.forward")
         return logits, fw, attn, hatt
 
     def forward(self, modality_features: Dict[str, torch.Tensor], modality_mask: Optional[torch.Tensor] = None,
@@ -486,6 +496,10 @@ class ConcatHead(nn.Sequential):
     outputs (src/train.py:81-85, :153-164).  State-dict keys 0.weight, 0.bias, 2.weight, 2.bias."""
 
     def __init__(self, in_dim: int, hidden_dim: int, num_classes: int, num_modalities: int = 2):
+        # the kernel (concat_head_kernel, csrc/fusion.cu) reads exactly two embeddings of in_dim / 2 columns each
+        if num_modalities != 2 or in_dim % 2 != 0 or (in_dim // 2) % 4 != 0:
+            raise ValueError(f"ConcatHead is built for two modalities of equal width (a multiple of 4): got "
+                             f"num_modalities={num_modalities}, in_dim={in_dim}")
         super().__init__(nn.Linear(in_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, num_classes))
         self.in_dim, self.hidden_dim, self.num_classes = in_dim, hidden_dim, num_classes
         self.num_modalities = num_modalities
@@ -509,6 +523,11 @@ class ConcatHead(nn.Sequential):
 
     @torch.no_grad()
     def run(self, zs, rows_per_clip, B: int, passes: int):
+        if len(zs) != 2 or len(rows_per_clip) != 2:
+            raise ValueError(f"ConcatHead.run takes exactly two modality embeddings, got {len(zs)}")
+        for z in zs:
+            if z.dim() != 2 or z.shape[1] != self.in_dim // 2:
+                raise ValueError(f"ConcatHead.run: embeddings must be (rows, {self.in_dim // 2}), got {tuple(z.shape)}")
         dev = zs[0].device
         logits = torch.empty(B, passes, self.num_classes, device=dev, dtype=torch.float32)
         if B > 0:

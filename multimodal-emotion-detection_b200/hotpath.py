@@ -11,7 +11,8 @@ mc_forward(features, mask, num_samples, ...)   MCDropoutUncertainty's result wit
                           the fused tail kernels.
 
 features["audio"] may be the raw waveform (B, 48000) / (B, 48000, 1) as load_raw_audio produces it
-(src/dataprocessing.py:210-211) - the log-mel/MFCC front-end is applied - or precomputed (B, T, 104) features.
+(src/dataprocessing.py:210-211) - the log-mel/MFCC front-end is applied -, the same as 16-bit PCM (int16, as the .wav
+holds it: load_raw_audio's peak normalisation then happens on the device), or precomputed (B, T, 104) features.
 features["video"] is (B, 16, 12544) fp32 in [0, 1] or uint8 pixels.
 """
 from __future__ import annotations
@@ -59,6 +60,7 @@ class AVHotPath(nn.Module):
                                           len(self.modalities))                          # :81-85
         self.num_classes = num_classes
         self.fold_video_projection = True     # tc + hybrid only; False keeps z_v materialised (A/B tests)
+        self._resolver = None                 # exact.NearTieResolver of mc_forward's immediate mode
         self.set_precision(precision)
 
     def set_precision(self, precision: str) -> "AVHotPath":
@@ -84,12 +86,18 @@ class AVHotPath(nn.Module):
 
     @torch.no_grad()
     def _run(self, features: Dict[str, torch.Tensor], mask, passes: int, stochastic: bool, seed: int, clip0: int,
-             t0: int):
+             t0: int, clip_ids=None):
+        """clip_ids: optional (B,) int32 CUDA tensor, the global clip index of every row (instead of clip0 + b); used by
+        exact.NearTieResolver to re-evaluate scattered clips on the fp32 kernels (hybrid / concat heads)."""
         if set(self.modalities) != {"audio", "video"}:
             raise ValueError("AVHotPath is the audio + video path")
         audio, video = features["audio"], features["video"]
         dev = _lib.require_cuda(audio, video)
         _lib.check_device(dev)
+        if audio.dtype == torch.int16:        # 16-bit PCM as decoded from the .wav: load_raw_audio's conditioning here
+            if audio.dim() == 3 and audio.shape[-1] == 1:
+                audio = audio[..., 0]
+            audio = dataprocessing.condition_audio(audio)
         B = audio.shape[0]
         aenc = self.encoders["audio"]
         raw = not (audio.dim() == 3 and audio.shape[-1] == aenc.input_dim and aenc.input_dim != 1)
@@ -104,7 +112,10 @@ class AVHotPath(nn.Module):
         # into HybridFusion's proj_layers.video (two linear maps back to back), which is a tcgen05 GEMM anyway
         fold = (self.head == "hybrid" and self.precision == "tc" and self.modalities[0] == "audio"
                 and venc.hidden_dim % 64 == 0 and venc.hidden_dim <= 256 and self.fold_video_projection)
-        z_v = venc.tail(hid, None, passes, p_enc, seed, clip0, t0, project=not fold)      # (B, passes, out | hidden)
+        if clip_ids is not None and (fold or self.head not in ("hybrid", "concat")):
+            raise ValueError("clip_ids: only the fp32 hybrid / concat paths take per-row clip indices")
+        z_v = venc.tail(hid, None, passes, p_enc, seed, clip0, t0, project=not fold,
+                        clip_ids=clip_ids)                                                # (B, passes, out | hidden)
         zs = [z_a, z_v.reshape(B * passes, -1)] if self.modalities[0] == "audio" else [z_v.reshape(B * passes, -1), z_a]
         rpc = [1, passes] if self.modalities[0] == "audio" else [passes, 1]
         if self.head == "hybrid":
@@ -116,7 +127,7 @@ class AVHotPath(nn.Module):
                     raise ValueError("mask must be (B, 2)")
             p_f = fm._drop_p() if stochastic else 0.0
             logits, _, _, _ = fm.run(zs, rpc, mask_f, B, passes, p_f, seed, clip0, t0,
-                                     folded_from=(1, venc.projection[1]) if fold else None)
+                                     folded_from=(1, venc.projection[1]) if fold else None, clip_ids=clip_ids)
         elif self.head in ("early", "late"):
             fm = self.fusion_model
             mask_f = None
@@ -134,8 +145,32 @@ class AVHotPath(nn.Module):
         return self._run(features, mask, 1, True, seed, clip0, t)[:, 0, :]
 
     def mc_forward(self, features: Dict[str, torch.Tensor], mask: Optional[torch.Tensor] = None,
-                   num_samples: int = 32, seed: int = _rng.DEFAULT_SEED, clip0: int = 0):
+                   num_samples: int = 32, seed: int = _rng.DEFAULT_SEED, clip0: int = 0, exact_labels=None):
         """-> (mean_logits (B, C), uncertainty (B,), labels (B,) int32, packed (B, C + 1)).  Dropout modules must
-        be in the mode the caller wants (MCDropoutUncertainty puts exactly the nn.Dropout modules in train mode)."""
+        be in the mode the caller wants (MCDropoutUncertainty puts exactly the nn.Dropout modules in train mode).
+
+        exact_labels (precision 'tc', hybrid / concat heads): the clips whose top-2 margin of the mean logits is inside
+        the tensor-core path's stated tolerance are re-evaluated on the fp32 kernels, so every label equals the fp32
+        path's (exact.py).  None / True: before returning (one host round trip per call); a NearTieResolver: deferred -
+        the batch is registered and the caller flushes the resolver every few batches; False: off."""
         logits = self._run(features, mask, num_samples, True, seed, clip0, 0)
-        return mc_reduce(logits)
+        results = mc_reduce(logits)
+        if exact_labels is False or self.precision != "tc" or self.head not in ("hybrid", "concat"):
+            return results
+        from .exact import NearTieResolver
+        if isinstance(exact_labels, NearTieResolver):
+            exact_labels.register(features, mask, results, num_samples, seed, clip0)
+            return results
+        B = results[0].shape[0]
+        want = B if B <= 256 else max(256, B // 8)             # near ties are a fraction of a percent of a batch
+        if self._resolver is None or self._resolver.capacity < want:
+            self._resolver = NearTieResolver(self, capacity=want)
+        self._resolver.register(features, mask, results, num_samples, seed, clip0)
+        if self._resolver.flush(raise_on_overflow=False) < 0:
+            # a degenerate model (e.g. all-equal logits) puts most clips inside the tolerance: the fp32 path for all
+            self.set_precision("fp32")
+            try:
+                results = mc_reduce(self._run(features, mask, num_samples, True, seed, clip0, 0))
+            finally:
+                self.set_precision("tc")
+        return results

@@ -44,8 +44,12 @@ class MCDropoutUncertainty(nn.Module):
         assert num_samples >= 1, "num_samples must be >= 1"                               # :31
         self.model = model
         self.num_samples = num_samples
+        # Dropout masks are a pure function of (seed, pass, global clip index): row b of a call is clip `clip0 + b`.
+        # clip0 advances by the batch size after every call, so consecutive batches of a loader draw fresh masks like
+        # the reference's nn.Dropout does (src/uncertainty.py:61-65); set it (or advance = False) to pin the masks.
         self.seed = _rng.DEFAULT_SEED
         self.clip0 = 0
+        self.advance = True
 
     @staticmethod
     def _set_dropout_train(module: nn.Module) -> None:                                    # :36-46
@@ -74,6 +78,8 @@ class MCDropoutUncertainty(nn.Module):
                 self.model.train()
             else:
                 self.model.eval()
+        if self.advance:
+            self.clip0 += int(mean.shape[0])
         return mean, unc
 
 

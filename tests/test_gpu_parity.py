@@ -103,6 +103,22 @@ def test_condition_audio(pkg, dev):
             assert (got[b] == y).all()
 
 
+def test_condition_audio_pcm16_equals_float_path(pkg, dev):
+    """16-bit PCM in (what the .wav holds) == converting to k / 32768 first (librosa.load, src/dataprocessing.py:196) and
+    conditioning the floats: bit-identical, including the -32768 sample, a silent clip and truncation / padding."""
+    rng = np.random.default_rng(1)
+    k = rng.integers(-20000, 20000, size=(5, 6000)).astype(np.int16)
+    k[0, 17] = -32768
+    k[2] = 0
+    k[3] //= 300                                                   # quiet clip: the peak is far from full scale
+    lengths = np.array([6000, 4321, 6000, 6000, 1], dtype=np.int32)
+    for n_out in (4000, 6000, 7001):
+        a = pkg.condition_audio(torch.from_numpy(k).to(dev), torch.from_numpy(lengths).to(dev), n_out)
+        b = pkg.condition_audio(torch.from_numpy(k.astype(np.float32) / 32768.0).to(dev), torch.from_numpy(lengths).to(dev), n_out)
+        assert a.dtype == torch.float32 and torch.equal(a, b)
+        assert float(a[2].abs().max()) == 0.0 and float(a[0].abs().max()) == 1.0
+
+
 # ---------------------------------------------------------------------------------------------------------
 # a2 front-end
 # ---------------------------------------------------------------------------------------------------------
@@ -218,6 +234,47 @@ def test_frame_encoder_dropout_passes_and_mask(pkg, dev, world):
     y = om._layer_norm(pooled, world["sd64"]["encoders.video.projection.0.weight"], world["sd64"]["encoders.video.projection.0.bias"])
     want = om._lin(y, world["sd64"], "encoders.video.projection.1").numpy()
     assert rel_err(got, want) <= REL
+
+
+@pytest.mark.parametrize("pooling", ["average", "max"])
+def test_frame_encoder_average_and_max_pooling(pkg, dev, world, pooling):
+    """FrameEncoder(temporal_pooling='average' | 'max'), src/encoders.py:276-293: eval, frame mask, and MC passes."""
+    torch.manual_seed(3)
+    enc = pkg.FrameEncoder(12544, hidden_dim=256, output_dim=128, temporal_pooling=pooling, dropout=0.1).to(dev).eval()
+    assert not hasattr(enc, "attention")
+    sd64 = {"v." + k: v.detach().double().cpu() for k, v in enc.state_dict().items()}
+    frames = torch.from_numpy(world["frames"])
+    hid64 = om.frame_hidden(frames.double(), sd64, "v.")
+    got = enc(frames.to(dev)).cpu().numpy()
+    assert rel_err(got, om.frame_encoder_tail(hid64, sd64, "v.", pooling=pooling).numpy()) <= REL
+    valid = torch.ones(6, 16, dtype=torch.bool)
+    valid[1, 5:] = False
+    valid[2, :15] = False
+    valid[3, :] = False if pooling == "average" else True          # average: all frames invalid -> zeros / clamp_min(1)
+    got = enc(frames.to(dev), valid.to(dev)).cpu().numpy()
+    assert rel_err(got, om.frame_encoder_tail(hid64, sd64, "v.", pooling=pooling, valid=valid).numpy()) <= REL
+    hid = enc.hidden(frames.to(dev))
+    T = 3
+    z = enc.tail(hid, None, T, 0.1, SEED, 0, 0).cpu().numpy()
+    for t in range(T):
+        ctx = om.DropCtx(seed=SEED, t=t, clip_ids=np.arange(6, dtype=np.uint64), p_encoder=0.1)
+        assert rel_err(z[:, t], om.frame_encoder_tail(hid64, sd64, "v.", ctx=ctx, pooling=pooling).numpy()) <= REL
+
+
+def test_attention_pool_kernel(pkg, dev, world):
+    """FrameEncoder.attention_pool (src/encoders.py:300-327) as a device kernel, with and without a frame mask."""
+    m = make_model(pkg, dev, world)
+    enc = m.encoders["video"]
+    rng = np.random.default_rng(8)
+    x = torch.from_numpy(rng.normal(size=(37, 11, 256)).astype(np.float32))
+    valid = torch.from_numpy(rng.uniform(size=(37, 11)) > 0.3)
+    valid[:, 0] = True
+    for v in (None, valid):
+        got = enc.attention_pool(x.to(dev), None if v is None else v.to(dev)).cpu().numpy()
+        want = om.attention_pool(x.double(), world["sd64"], valid=v).numpy()
+        assert got.shape == (37, 256) and rel_err(got, want) <= REL
+    with pytest.raises(ValueError):
+        enc.attention_pool(torch.zeros(2, 3, 100, device=dev))
 
 
 # ---------------------------------------------------------------------------------------------------------
