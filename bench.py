@@ -205,7 +205,8 @@ def workload_config(args, batch):
                         "+ frame encoder -> hybrid cross-modal attention fusion -> MC-dropout uncertainty",
             "clips_per_gpu_per_step": batch, "mc_passes": args.passes, "modality_dropout_p": P_MODALITY,
             "classes": N_CLASSES, "precision": args.precision, "parallelism": f"clip-sharded x{args.gpus}, all-gather of (B,9) fp32",
-            "label_exactness": f"near-tie clips re-evaluated in fp32 every {args.resolve_every} steps, inside the timed region"
+            "label_exactness": ("off (A/B)" if args.no_exact_labels else
+                                f"near-tie clips re-evaluated in fp32 every {args.resolve_every} steps, inside the timed region")
                                if args.precision == "tc" else "fp32 path",
             "l2_policy": f"inputs larger than L2 ({batch * BYTES_IN_PER_CLIP / 1e9:.1f} GB per step per GPU), two "
                          "batches alternate"}
@@ -296,7 +297,10 @@ def run_b200_arm(args):
         return (step * world + rank) * B
 
     tc = args.precision == "tc"
-    resolver = pkg.NearTieResolver(model, capacity=max(1024, B // 4)) if tc else None
+    resolver = None
+    if tc and not args.no_exact_labels:
+        resolver = pkg.NearTieResolver(model, capacity=max(1024, B // 2),
+                                       margin_rel=args.margin_rel if args.margin_rel is not None else pkg.exact.DEFAULT_MARGIN_REL)
     ctx.resolver = resolver
 
     if args.sweep:
@@ -325,10 +329,10 @@ def run_b200_arm(args):
         for j in range(first, first + n):
             feats, mask, c0 = pool[j % 2]
             mean, unc, labels, packed = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=c0,
-                                                         exact_labels=resolver if tc else False)
+                                                         exact_labels=resolver if resolver else False)
             window.append((j, labels, packed))
             if len(window) == args.resolve_every or j == first + n - 1:
-                if tc:
+                if resolver:
                     resolver.flush()
                 local = window[0][2] if len(window) == 1 else torch.cat([w[2] for w in window], dim=0)
                 out = par.all_gather_packed(local, local.shape[0] * world) if world > 1 else local
@@ -346,7 +350,7 @@ def run_b200_arm(args):
     pkg._lib.prof_reset()
     pkg._lib.prof_enable(True)
     launches0 = pkg._lib.launch_count()
-    flagged0 = resolver.flagged_total if tc else 0
+    flagged0 = resolver.flagged_total if resolver else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_steps(args.warmup, args.steps, True)
@@ -362,7 +366,7 @@ def run_b200_arm(args):
     value = world * B * args.steps / (ms / 1e3)
     prof = pkg._lib.prof_report()
     pkg._lib.prof_reset()
-    flagged = (resolver.flagged_total - flagged0) if tc else 0
+    flagged = (resolver.flagged_total - flagged0) if resolver else 0
 
     # ---- labels of every timed step against the fp32 CUDA path (itself checked against the oracle in tests/ and
     # below), on a rotating sample of >= 1024 clips per step; outside the timed region ----------------------------
@@ -389,6 +393,8 @@ def run_b200_arm(args):
         parity = {"label_mismatches": int(stats[0].item()), "clips_checked": int(stats[1].item()),
                   "steps_checked": args.steps, "against": "fp32 CUDA path, rotating sample of every timed step, all ranks",
                   "mean_logits_rel_err_vs_fp32_path": float(worst_t.item()),
+                  "exact_labels": resolver is not None,
+                  "near_tie_margin_rel": resolver.margin_rel if resolver else None,
                   "near_tie_clips_reevaluated_in_fp32": int(stats[2].item()),
                   "near_tie_fraction": float(stats[2].item()) / (world * B * args.steps)}
     records.clear()
@@ -408,6 +414,10 @@ def run_b200_arm(args):
 
     extra = {}
     if not args.no_extra:
+        if resolver:    # what label exactness costs: the same steps with the tensor-core path's own labels (A/B, same box)
+            extra["value_without_near_tie_resolution"] = _leg(
+                ctx, lambda i: model.mc_forward(pool[i % 2][0], pool[i % 2][1], num_samples=T, seed=SEED,
+                                                clip0=pool[i % 2][2], exact_labels=False), B, iters=6, warm=2)
         extra["config0_b8_concat_head"] = leg_config0(ctx)
         extra["config1_frontend_4096"] = leg_config1(ctx)
         extra["config2_forward_b512"] = leg_config2(ctx)
@@ -805,7 +815,11 @@ def main():
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU sample (~10 s of host work)")
     ap.add_argument("--check-clips", type=int, default=1024, help="clips of every timed step checked against the fp32 path")
-    ap.add_argument("--resolve-every", type=int, default=5,
+    ap.add_argument("--margin-rel", type=float, default=None,
+                    help="near-tie threshold in units of max|mean logit| (default: exact.DEFAULT_MARGIN_REL)")
+    ap.add_argument("--no-exact-labels", action="store_true",
+                    help="A/B: leave the tensor-core path's labels as they are (a few flips per 10 000 clips)")
+    ap.add_argument("--resolve-every", type=int, default=10,
                     help="steps per near-tie window: the flagged clips of a window are re-evaluated in fp32 together")
     ap.add_argument("--weight-seed", type=int, default=SEED, help="torch.manual_seed for the random-init weights")
     ap.add_argument("--sweep", type=int, default=0, help="strong-scaling mode: this many clips in total over all ranks")

@@ -1,10 +1,10 @@
 // Label exactness of the tensor-core path (BASELINE north star: "predicted labels identical to the reference").
 //
-// The tensor-core path's mean logits differ from the fp32 path's by at most tol * max|logit| (the stated tolerance of
-// AVHOT_PREC_TC), so argmax(mean_logits) (src/uncertainty.py:77 feeds the prediction) can differ
-// only for clips whose top-2 margin is below 2 * tol * max|logit|.  Those clips - a fraction of a percent - are
-// appended to a pending list with a copy of their inputs, re-evaluated through the fp32 kernels (each with its own
-// global clip index, so the Philox masks are the ones it drew the first time) and their records overwritten:
+// argmax(mean_logits) (src/uncertainty.py:77 feeds the prediction) of the tensor-core path can differ from the fp32
+// path's only for clips whose top-2 margin is below the error of that difference (measured envelope: exact.py).  Those
+// clips - under one percent - are appended to a pending list with a copy of their inputs, re-evaluated through the fp32
+// kernels (each with its own global clip index, so the Philox masks are the ones it drew the first time) and their
+// records overwritten:
 //   avhot_flag_near_ties    margins + global max on the device, list append by atomics (no host round trip);
 //   avhot_gather_flagged    rows of an input tensor -> the pending pool, for the entries the last flag call appended;
 //   avhot_scatter_resolved  fp32 records of the pending entries of one call -> that call's result tensors.
@@ -29,14 +29,16 @@ __global__ void near_tie_flag_kernel(const float* __restrict__ mean_logits, int 
   if (b >= B) return;
   const float* x = mean_logits + (size_t)b * C;
   float top1 = -INFINITY, top2 = -INFINITY;
+  bool nan = false;
   for (int c = 0; c < C; ++c) {
     const float v = x[c];
+    nan |= v != v;
     if (v > top1) { top2 = top1; top1 = v; }
     else if (v > top2) top2 = v;
   }
   const float thr = margin_rel * __uint_as_float(state[3]);
-  // !(margin >= thr): NaN logits are flagged too, so the fp32 path has the last word on them
-  if (C >= 2 && !(top1 - top2 >= thr)) {
+  // a row with a NaN logit is flagged too, so the fp32 path has the last word on it
+  if (C >= 2 && (nan || !(top1 - top2 >= thr))) {
     const uint32_t e = atomicAdd(&state[0], 1u);
     if (e < (uint32_t)capacity) {
       entry_tag[e] = tag;

@@ -335,7 +335,6 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
   float* h_seq = reinterpret_cast<float*>(p); p += align256(sizeof(float) * Bp * T * H);
   float* h_last = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * H);
   __half* x_split = reinterpret_cast<__half*>(p);   // TC path only
-  const bool small = ceil_div(B, 32) * 2 < num_sms();   // few clips: smaller tiles, more CTAs
   for (int l = 0; l < h->num_layers; ++l) {
     const float* x = l == 0 ? seq : h_seq;
     const int in = l == 0 ? h->input_dim : H;
@@ -382,17 +381,25 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
                       "lstm_input_gemm");
     if (rc != AVHOT_OK) return rc;
     ProfScope prof("lstm_recurrence", s);
-    if (small) {
-      constexpr int BT = 4;
-      const size_t smem = sizeof(float) * 2 * LH * (BT + 4);
-      lstm_recurrence_kernel<BT><<<ceil_div(B, BT), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T);
-    } else {
-      constexpr int BT = 32;
-      const size_t smem = sizeof(float) * 2 * LH * (BT + 4);
-      AVHOT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-      lstm_recurrence_kernel<BT><<<ceil_div(B, BT), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T);
+    // Clips per CTA: a CTA streams all of W_hh (1 MB) from L2 every step whatever its tile, so few large tiles cost the
+    // least L2 traffic, but the 602 dependent steps want every SM busy: the smallest multiple of 4 that fits the batch
+    // into one wave of CTAs (e.g. 2560 near-tie clips of a flush: 20 clips x 128 CTAs instead of 32 x 80, measured
+    // 47 -> 25 ms for the two layers), 32 for large batches.
+    const int want = 4 * ceil_div(B, 4 * num_sms());
+#define AVHOT_REC_CASE(BT_)                                                                                        \
+  case BT_: {                                                                                                       \
+    const size_t smem = sizeof(float) * 2 * LH * (BT_ + 4);                                                         \
+    AVHOT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)smem));                                                                    \
+    lstm_recurrence_kernel<BT_><<<ceil_div(B, BT_), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T); \
+    break;                                                                                                          \
+  }
+    switch (want >= 32 ? 32 : want) {
+      AVHOT_REC_CASE(4) AVHOT_REC_CASE(8) AVHOT_REC_CASE(12) AVHOT_REC_CASE(16) AVHOT_REC_CASE(20) AVHOT_REC_CASE(24)
+      AVHOT_REC_CASE(28)
+      default: AVHOT_REC_CASE(32)
     }
+#undef AVHOT_REC_CASE
     AVHOT_LAUNCH_CHECK();
   }
   return gemm_f32(h_last, nullptr, H, h->proj_w, H, h->proj_b, out, h->output_dim, B, h->output_dim, H, ACT_NONE, s,

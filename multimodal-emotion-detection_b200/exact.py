@@ -1,17 +1,26 @@
 """Label exactness of the tensor-core path.
 
 BASELINE.json's north star asks for "predicted labels identical to the reference" - the reference predicts
-argmax(mean_logits) of its fp32 forward (src/uncertainty.py:77).  The tensor-core path's mean logits differ from the fp32
-path's by at most ``TC_TOLERANCE * max|logit|`` (stated tolerance), so a label can differ only for a
-clip whose top-2 margin is below ``2 * TC_TOLERANCE * max|logit|``.  NearTieResolver finds those clips on the device
-(avhot_flag_near_ties), keeps a copy of their inputs (avhot_gather_flagged), re-evaluates them through the fp32 kernels
-with their own global clip indices - so the Philox masks are the ones they drew the first time - and overwrites their
-records (avhot_scatter_resolved).  A fraction of a percent of the clips take this path.
+argmax(mean_logits) of its fp32 forward (src/uncertainty.py:77).  A label of the tensor-core path can differ from the
+fp32 path's only for a clip whose top-2 margin of the mean logits is smaller than the error of that difference.
+Measured on 56 832 clips of the benchmark workload (tools/measure_near_ties.py, profiles/r2a_near_ties.json), in units
+of max|logit| over the batch: the error of the top-2 difference has RMS 6.6e-5, 99.99 % quantile 4.4e-4, maximum
+5.3e-4 (the per-pass rounding of the fusion GEMMs averages out over the T passes; what remains is the pass-invariant
+TF32 video Linear and the fp16 LSTM state) and a tail that falls a decade per 1.2e-4; the widest margin of a clip whose
+label actually flipped was 1.6e-4.  NearTieResolver takes every clip whose margin is below ``margin_rel * max|logit|``
+(default 6e-4: an undetected flip then needs an error beyond the measured tail, ~3e-9 per clip), keeps a copy of its
+inputs (avhot_flag_near_ties, avhot_gather_flagged: on the device, no host round trip), re-evaluates it through the fp32
+kernels with its own global clip index - so the Philox masks are the ones it drew the first time - and overwrites its
+records (avhot_scatter_resolved).  With the random-init weights of the benchmark the logits of all clips sit close
+together (median top-2 margin 4 % of max|logit|) and 0.83 % of the clips take this path; a trained model's margins are
+wider.  The fp32 kernels cost ~17 x the tensor-core path per clip, which is why the threshold is the measured envelope
+and not the (looser) tolerance the tests assert on every logit.  bench.py checks the premise on every timed step
+(labels and mean logits of a rotating sample against the fp32 path, all ranks).
 
 Two ways to use it:
 * immediate (AVHotPath.mc_forward's default with precision 'tc'): flag, re-evaluate and patch before returning;
-* deferred (bench.py, sweeps): ``register`` every batch, ``flush`` every few batches - the fp32 kernels are latency-bound
-  at a few dozen clips, so one flush over several batches costs about as much as one over a single batch.
+* deferred (bench.py, sweeps): ``register`` every batch, ``flush`` every few batches - the fp32 recurrence is
+  latency-bound below a few hundred clips, so one flush over ten batches costs far less than ten flushes.
 """
 from __future__ import annotations
 
@@ -22,8 +31,7 @@ import torch
 
 from . import _lib
 
-TC_TOLERANCE = 2e-3                      # stated tolerance of precision 'tc' on logits (normwise)
-DEFAULT_MARGIN_REL = 2.0 * TC_TOLERANCE  # both of the two largest mean logits may move by the tolerance
+DEFAULT_MARGIN_REL = 6e-4                # of max|mean logit| over the batch; see the measurement above
 
 
 class NearTieResolver:

@@ -17,7 +17,7 @@ P_MOD = 0.05
 def test_flag_gather_scatter_vs_numpy(pkg, dev):
     lib, L = pkg._lib.load(), pkg._lib
     rng = np.random.default_rng(3)
-    B, Cn, cap = 1000, 8, 64
+    B, Cn, cap = 1000, 8, 128
     mean = rng.normal(size=(B, Cn)).astype(np.float32)
     mean[17] = mean[17, 0]                                   # exact tie
     mean[400, 3] = np.nan                                    # NaN rows are flagged
@@ -26,7 +26,7 @@ def test_flag_gather_scatter_vs_numpy(pkg, dev):
     margin = srt[:, -1] - srt[:, -2]
     gmax = np.nanmax(np.abs(mean))
     want = set(np.nonzero(~(margin >= np.float32(margin_rel) * np.float32(gmax)) | np.isnan(mean).any(1))[0].tolist())
-    assert 2 <= len(want) <= cap
+    assert 2 <= len(want) <= cap // 2
     d_mean = torch.from_numpy(mean).to(dev)
     state = torch.zeros(4, dtype=torch.int32, device=dev)
     ent = torch.zeros(3, cap, dtype=torch.int32, device=dev)
