@@ -394,7 +394,8 @@ def run_b200_arm(args):
                   "steps_checked": args.steps, "against": "fp32 CUDA path, rotating sample of every timed step, all ranks",
                   "mean_logits_rel_err_vs_fp32_path": float(worst_t.item()),
                   "exact_labels": resolver is not None,
-                  "near_tie_margin_rel": resolver.margin_rel if resolver else None,
+                  "near_tie_margin_rel_of_logit_scale": resolver.margin_rel if resolver else None,
+                  "near_tie_margin_abs": resolver.margin if resolver else None,
                   "near_tie_clips_reevaluated_in_fp32": int(stats[2].item()),
                   "near_tie_fraction": float(stats[2].item()) / (world * B * args.steps)}
     records.clear()
@@ -816,7 +817,7 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU sample (~10 s of host work)")
     ap.add_argument("--check-clips", type=int, default=1024, help="clips of every timed step checked against the fp32 path")
     ap.add_argument("--margin-rel", type=float, default=None,
-                    help="near-tie threshold in units of max|mean logit| (default: exact.DEFAULT_MARGIN_REL)")
+                    help="near-tie threshold in units of the model's logit scale S (default: exact.DEFAULT_MARGIN_REL)")
     ap.add_argument("--no-exact-labels", action="store_true",
                     help="A/B: leave the tensor-core path's labels as they are (a few flips per 10 000 clips)")
     ap.add_argument("--resolve-every", type=int, default=10,

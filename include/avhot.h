@@ -105,8 +105,9 @@ int avhot_frontend(const float* wave, float* feats, int B, int n_samples,
                    avhot_stream_t stream);
 /* Fused variant for the tensor-core pipeline: besides (or instead of: feats may be NULL) the fp32 features it
  * writes the LSTM's first GEMM operand directly - fp16, time-major rows (t, clip) with the batch padded to
- * Bp = B rounded up to 128, pitch = avhot_lstm_split_pitch() halves per row:
- * [hi(104) | lo(104) | hi(104) | 1, 1 | 0...], hi = fp16(x), lo = fp16(x - hi) - see avhot_lstm_forward_split. */
+ * Bp = B rounded up to 128, pitch = avhot_lstm_split_pitch() = 320 halves per row, hi = fp16(x), lo = fp16(x - hi),
+ * features in blocks of 64 with [hi | lo | hi] per block:
+ * [lm_hi(64) | lm_lo(64) | lm_hi(64) | mf_hi(40) | mf_lo(40) | mf_hi(40) | 0(8)] - see avhot_lstm_forward_split. */
 int avhot_frontend_ex(const float* wave, float* feats, void* seq_split_f16, int B, int Bp, int pitch,
                       int n_samples, avhot_stream_t stream);
 /* the fp32 tables the kernel uses, copied to HOST buffers (any may be NULL):
@@ -415,12 +416,12 @@ int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
 
 /* ---- label exactness of AVHOT_PREC_TC (north star: labels identical to the reference, whose prediction is
  * argmax of the fp32 mean logits, src/uncertainty.py:77).  A clip whose top-2 margin of mean_logits is below
- * margin_rel * max|mean_logits| (margin_rel = twice the stated tolerance of the tensor-core path) is appended to a
- * pending list: entry e < capacity gets entry_tag[e] = tag (the caller's id of this call), entry_row[e] = b,
- * entry_clip[e] = low 32 bits of clip0 + b.  state: 4 uint32 on the device, zeroed by the caller when a window of
- * calls starts: [0] entries appended (can exceed capacity), [1] overflow flag, [2] entries before the latest call,
- * [3] max|mean_logits| of the latest call (float bits).  No host synchronisation. */
-int avhot_flag_near_ties(const float* mean_logits, int B, int C, float margin_rel, uint32_t tag,
+ * `margin` (absolute: the caller's bound on the error of a logit difference; exact.py derives it from the classifier's
+ * weights, so it does not depend on the batch) is appended to a pending list: entry e < capacity gets entry_tag[e] =
+ * tag (the caller's id of this call), entry_row[e] = b, entry_clip[e] = low 32 bits of clip0 + b.  state: 4 uint32 on
+ * the device, zeroed by the caller when a window of calls starts: [0] entries appended (can exceed capacity),
+ * [1] overflow flag, [2] entries before the latest call.  No host synchronisation. */
+int avhot_flag_near_ties(const float* mean_logits, int B, int C, float margin, uint32_t tag,
                          uint64_t clip0, uint32_t* state, uint32_t* entry_tag, uint32_t* entry_row,
                          uint32_t* entry_clip, int capacity, avhot_stream_t stream);
 /* rows entry_row[e] of src (B rows of row_bytes bytes, a multiple of 16) -> pool row e, for the entries the latest

@@ -5,24 +5,15 @@
 // clips - under one percent - are appended to a pending list with a copy of their inputs, re-evaluated through the fp32
 // kernels (each with its own global clip index, so the Philox masks are the ones it drew the first time) and their
 // records overwritten:
-//   avhot_flag_near_ties    margins + global max on the device, list append by atomics (no host round trip);
+//   avhot_flag_near_ties    top-2 margins on the device, list append by atomics (no host round trip);
 //   avhot_gather_flagged    rows of an input tensor -> the pending pool, for the entries the last flag call appended;
 //   avhot_scatter_resolved  fp32 records of the pending entries of one call -> that call's result tensors.
 #include "common.cuh"
 
 namespace avhot {
 
-// state words: [0] entries appended (may exceed capacity), [1] overflow flag, [2] entries before the latest flag call,
-//              [3] max |mean_logit| of the latest flag call (float bits; non-negative floats order like integers)
-__global__ void near_tie_max_kernel(const float* __restrict__ mean_logits, long long n, uint32_t* __restrict__ state) {
-  float m = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(mean_logits[i]));
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&state[3], __float_as_uint(m));
-}
-
-__global__ void near_tie_flag_kernel(const float* __restrict__ mean_logits, int B, int C, float margin_rel, uint32_t tag,
+// state words: [0] entries appended (may exceed capacity), [1] overflow flag, [2] entries before the latest flag call
+__global__ void near_tie_flag_kernel(const float* __restrict__ mean_logits, int B, int C, float margin, uint32_t tag,
                                      uint32_t clip0_lo, uint32_t* __restrict__ state, uint32_t* __restrict__ entry_tag,
                                      uint32_t* __restrict__ entry_row, uint32_t* __restrict__ entry_clip, int capacity) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,9 +27,8 @@ __global__ void near_tie_flag_kernel(const float* __restrict__ mean_logits, int 
     if (v > top1) { top2 = top1; top1 = v; }
     else if (v > top2) top2 = v;
   }
-  const float thr = margin_rel * __uint_as_float(state[3]);
   // a row with a NaN logit is flagged too, so the fp32 path has the last word on it
-  if (C >= 2 && (nan || !(top1 - top2 >= thr))) {
+  if (C >= 2 && (nan || !(top1 - top2 >= margin))) {
     const uint32_t e = atomicAdd(&state[0], 1u);
     if (e < (uint32_t)capacity) {
       entry_tag[e] = tag;
@@ -50,10 +40,7 @@ __global__ void near_tie_flag_kernel(const float* __restrict__ mean_logits, int 
   }
 }
 
-__global__ void near_tie_begin_kernel(uint32_t* __restrict__ state) {
-  state[2] = state[0];
-  state[3] = 0u;
-}
+__global__ void near_tie_begin_kernel(uint32_t* __restrict__ state) { state[2] = state[0]; }
 
 // CTA i copies the row of the i-th entry appended by the latest flag call (16-byte words; rows are 16-byte multiples)
 __global__ void gather_flagged_kernel(const uint4* __restrict__ src, size_t row_words, const uint32_t* __restrict__ state,
@@ -88,21 +75,18 @@ __global__ void scatter_resolved_kernel(const uint32_t* __restrict__ entry_tag, 
 
 using namespace avhot;
 
-extern "C" int avhot_flag_near_ties(const float* mean_logits, int B, int C, float margin_rel, uint32_t tag,
+extern "C" int avhot_flag_near_ties(const float* mean_logits, int B, int C, float margin, uint32_t tag,
                                     uint64_t clip0, uint32_t* state, uint32_t* entry_tag, uint32_t* entry_row,
                                     uint32_t* entry_clip, int capacity, avhot_stream_t stream) {
   AVHOT_REQUIRE(mean_logits && state && entry_tag && entry_row && entry_clip && B >= 0 && C >= 1 && capacity >= 1,
                 AVHOT_ERR_INVALID, "flag_near_ties: bad arguments");
-  AVHOT_REQUIRE(margin_rel >= 0.f, AVHOT_ERR_INVALID, "flag_near_ties: margin_rel=%g < 0", (double)margin_rel);
+  AVHOT_REQUIRE(margin >= 0.f, AVHOT_ERR_INVALID, "flag_near_ties: margin=%g < 0", (double)margin);
   if (B == 0) return AVHOT_OK;
   cudaStream_t s = as_stream(stream);
   ProfScope prof("near_tie_flag", s);
   near_tie_begin_kernel<<<1, 1, 0, s>>>(state);
   AVHOT_LAUNCH_CHECK();
-  const long long n = (long long)B * C;
-  near_tie_max_kernel<<<(unsigned)min((n + 255) / 256, (long long)num_sms() * 8), 256, 0, s>>>(mean_logits, n, state);
-  AVHOT_LAUNCH_CHECK();
-  near_tie_flag_kernel<<<ceil_div(B, 256), 256, 0, s>>>(mean_logits, B, C, margin_rel, tag, (uint32_t)clip0, state,
+  near_tie_flag_kernel<<<ceil_div(B, 256), 256, 0, s>>>(mean_logits, B, C, margin, tag, (uint32_t)clip0, state,
                                                        entry_tag, entry_row, entry_clip, capacity);
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;

@@ -32,6 +32,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace avhot {
 
@@ -58,6 +59,12 @@ struct FrontendTables {            // device layout, all fp32 unless noted
   float4 dct_b[DCT_TILES * 4 * 32];  // B fragments of the folded DCT in lane order, (hi0, hi1, lo0, lo1) per lane:
                                      //   tile (p, nt) = 3 p + nt, step ks, lane l -> D[c][8 ks + (l & 3) (+ 4)],
                                      //   c = 2 (8 nt + (l >> 2)) + p (zero rows for c >= 40)
+  // tcgen05 operands (frontend_tc_kernel), fp16 bit patterns already in the K-major 128-byte-swizzled shared-memory
+  // layout ([k-block of 64][row][16-byte chunk ^ (row & 7)]), copied to shared memory as they are:
+  uint16_t b3[4 * N_MELS * 64];      //   mel weights x 64 (= 0.25 for the 4 |X|^2 of the kernel x 256 to keep small taps
+                                     //   normal in fp16): row = filter, K = bins 0..255
+  uint16_t b4[2 * 48 * 64];          //   DCT matrix x 64, hi then lo = fp16(D - hi): row = coefficient (40, padded to
+                                     //   48), K = 64 log-mel bands
 };
 
 static FrontendTables g_host_tables;
@@ -141,6 +148,27 @@ static void build_tables() {
       double v = cos(PI * (j + 0.5) * c / N_MELS) * sqrt(2.0 / N_MELS);
       if (c == 0) v *= sqrt(0.5);
       g_host_dct[c * N_MELS + j] = (float)v;
+    }
+  auto f16_bits = [](float v) {
+    const __half h = __float2half_rn(v);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+  };
+  for (int m = 0; m < N_MELS; ++m)
+    for (int k = 0; k < 256; ++k) {
+      const int kb = k >> 6, chunk = (k & 63) >> 3, e = k & 7;
+      t.b3[(size_t)kb * (N_MELS * 64) + m * 64 + ((chunk ^ (m & 7)) << 3) + e] = f16_bits(64.f * g_host_mel_dense[m * N_BINS + k]);
+    }
+  for (int c = 0; c < 48; ++c)
+    for (int j = 0; j < N_MELS; ++j) {
+      const float d = c < N_MFCC ? 64.f * g_host_dct[c * N_MELS + j] : 0.f;
+      const uint16_t hi = f16_bits(d);
+      __half hh;
+      memcpy(&hh, &hi, 2);
+      const size_t pos = (size_t)c * 64 + (((j >> 3) ^ (c & 7)) << 3) + (j & 7);
+      t.b4[pos] = hi;
+      t.b4[48 * 64 + pos] = f16_bits(d - __half2float(hh));
     }
   for (int p = 0; p < 2; ++p)
     for (int nt = 0; nt < 3; ++nt)
@@ -530,6 +558,437 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
   }
 }
 
+
+// =====================================================================================================================
+// frontend_tc_kernel: the same front-end with the two dense contractions on the tcgen05 tensor cores.
+//
+// Persistent CTA (one per SM, grid-stride over clips), 21 warps:
+//   warps 0-15   FFT producers.  A group = 16 consecutive frames of a clip, one per warp: window + radix 8 x 8 x 4 FFT +
+//                real-FFT split + |X|^2 in registers (as above), then the frame's power spectrum is scaled by a power of
+//                two that puts its largest bin at 2^13..2^14, rounded to fp16 and written as ROW (frame) of the mel
+//                GEMM's A operand, K-major with the 128-byte swizzle (a3: 128 frames x 256 bins, 64 KB); the inverse
+//                scale goes to unscale[row].  The samples of the next group travel global -> registers during the FFTs
+//                and are staged into the other half of a double-buffered segment: one 512-thread named barrier a group.
+//   warp 20      MMA issuer: per 128-frame tile, D3 (128 x 64, TMEM) = a3 (fp16) x b3^T (mel weights, fp16), 16
+//                tcgen05.mma M128 N64 K16; then D4 (128 x 48) = [lm_hi | lm_lo | lm_hi] x [D_hi | D_hi | D_lo]^T, the DCT-II
+//                as an error-compensated fp16 product (12 MMAs M128 N48 K16) over the log-mel tile the epilogue wrote.
+//   warps 16-19  epilogue, thread = TMEM lane = frame: tcgen05.ld the mel energies, undo the scale, floor, 10 log10; the
+//                log-mel row goes out as fp16 hi / lo 64-column tiles x[0], x[1] in the same swizzled K-major layout -
+//                which is at once the DCT's A operand and, for the tensor-core LSTM, three 64-column k-blocks of its
+//                first GEMM operand (hi | lo | hi, lstm.cu split3_slot): TMA stores them straight from x[] into the
+//                time-major (t, clip) rows (3-D tensor map, rows past the clip's last frame clipped by the map).  After
+//                the DCT the 40 MFCC go out the same way ([mf_hi | mf_lo | mf_hi | 0] = two more k-blocks).  The fp32
+//                feature tensor (avhot_frontend) leaves through a 32-column staging tile and TMA stores too.
+// mbarriers: a3_full (16 FFT warps -> MMA), a3_free / d3_full (MMA commit -> FFT warps / epilogue), x_full (4 epilogue
+// warps -> MMA), d4_full (MMA commit -> epilogue).  Parities follow the CTA's tile counter.
+// Precision: power bins and mel weights carry 11 significant bits each (fp16, round to nearest) - the same class as the
+// TF32 weights of the mma.sync version - so a log-mel value is within ~0.002 dB of the fp64 spec in the worst case and
+// ~0.0005 dB typically; the per-frame power-of-two scale keeps every bin within 84 dB of the frame's peak normal in fp16.
+// =====================================================================================================================
+constexpr int FT_FFT_WARPS = 16, FT_EPI_WARP0 = 16, FT_MMA_WARP = 20, FT_THREADS = 21 * 32, FT_TILE = 128;
+constexpr int FT_FFT_THREADS = FT_FFT_WARPS * 32;
+
+struct FtSmem {
+  __half a3[4][FT_TILE * 64];        // power spectrum tile, A operand of the mel GEMM
+  __half b3[4][N_MELS * 64];         // mel weights, B operand
+  __half x[2][FT_TILE * 64];         // log-mel hi / lo (A operand of the DCT, TMA-store source), later the MFCC block
+  __half b4[2][48 * 64];             // DCT matrix hi / lo, B operand
+  float fout[FT_TILE * 32];          // fp32 output staging: one 32-column box
+  float2 z[FT_FFT_WARPS][ZPAD];      // FFT scratch
+  float seg[2][SEG];                 // pre-emphasised samples of a group, double-buffered
+  float win[N_FFT];
+  float2 tw[N_FFT / 2];
+  float2 tw2[64], tw3[256];
+  float unscale[FT_TILE];
+  uint64_t a3_full, a3_free, d3_full, x_full, d4_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(FtSmem) + 1024 <= 227 * 1024, "one CTA per SM");
+
+__device__ __forceinline__ void bar_named(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// window + FFT-256 of the packed frame + nothing else: on return Z[lane + 32 m] = v[m] (Z = FFT of x[2n] + i x[2n+1])
+__device__ __forceinline__ void fft_frame(const float* __restrict__ frame, const float* __restrict__ s_win, float2* z,
+                                          const float2* __restrict__ s_tw2, const float2* __restrict__ s_tw3, int lane,
+                                          float2 (&v)[8]) {
+  const float2* x2 = reinterpret_cast<const float2*>(frame);
+  const float2* w2 = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const float2 s = x2[lane + 32 * r], w = w2[lane + 32 * r];
+    v[r] = make_float2(s.x * w.x, s.y * w.y);
+  }
+  dft8(v);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) z[zpad(lane * 8 + r)] = v[r];
+  __syncwarp();
+  {
+    const int k = lane & 7;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float2 a = z[zpad(lane + 32 * r)];
+      v[r] = r == 0 ? a : cmul(a, s_tw2[r * 8 + k]);
+    }
+    dft8(v);
+    __syncwarp();
+    const int j0 = (lane - k) * 8 + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) z[zpad(j0 + 8 * r)] = v[r];
+    __syncwarp();
+  }
+  {
+    float2 u[2][4];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = lane + 32 * jj;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 a = z[zpad(j + 64 * r)];
+        u[jj][r] = r == 0 ? a : cmul(a, s_tw3[r * 64 + j]);
+      }
+      dft4(u[jj][0], u[jj][1], u[jj][2], u[jj][3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { v[2 * r] = u[0][r]; v[2 * r + 1] = u[1][r]; }
+  }
+}
+
+// fp16 hi / lo split of 8 floats -> two 16-byte chunks
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+    h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUtensorMap tmF,
+                   const __grid_constant__ CUtensorMap tmX, int has_feats, int has_xs, int B, int n_samples, int n_frames,
+                   const FrontendTables* __restrict__ tab) {
+  using namespace tc;
+  extern __shared__ unsigned char ft_smem_raw[];
+  FtSmem& sm = *reinterpret_cast<FtSmem*>(ft_smem_raw + ((1024u - (smem_u32(ft_smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int n_tiles = (n_frames + FT_TILE - 1) / FT_TILE;
+
+  // ---- one-time setup: tables and tensor-core B operands -> shared memory, barriers, TMEM ---------------------------
+  for (int i = tid; i < N_FFT; i += FT_THREADS) sm.win[i] = tab->window[i];
+  for (int i = tid; i < N_FFT / 2; i += FT_THREADS) sm.tw[i] = tab->tw[i];
+  for (int i = tid; i < 64; i += FT_THREADS) sm.tw2[i] = tab->tw2[i];
+  for (int i = tid; i < 256; i += FT_THREADS) sm.tw3[i] = tab->tw3[i];
+  {
+    const uint4* s3 = reinterpret_cast<const uint4*>(tab->b3);
+    uint4* d3 = reinterpret_cast<uint4*>(&sm.b3[0][0]);
+    for (int i = tid; i < (int)(sizeof(sm.b3) / 16); i += FT_THREADS) d3[i] = __ldg(s3 + i);
+    const uint4* s4 = reinterpret_cast<const uint4*>(tab->b4);
+    uint4* d4 = reinterpret_cast<uint4*>(&sm.b4[0][0]);
+    for (int i = tid; i < (int)(sizeof(sm.b4) / 16); i += FT_THREADS) d4[i] = __ldg(s4 + i);
+    fence_proxy_async_smem();                       // the tensor cores read them through the async proxy
+  }
+  if (tid == 0) {
+    mbar_init(&sm.a3_full, FT_FFT_WARPS);
+    mbar_init(&sm.a3_free, 1);
+    mbar_init(&sm.d3_full, 1);
+    mbar_init(&sm.x_full, 4);
+    mbar_init(&sm.d4_full, 1);
+    fence_barrier_init();
+    if (has_feats) tma_prefetch_desc(&tmF);
+    if (has_xs) tma_prefetch_desc(&tmX);
+  }
+  if (warp == FT_MMA_WARP) {
+    tmem_alloc(&sm.tmem_base, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp < FT_FFT_WARPS) {
+    // =============================== FFT producers ===================================================================
+    constexpr int SPT = 8;                                                    // registers per thread for a segment
+    constexpr int NS = (SEG + FT_FFT_THREADS - 1) / FT_FFT_THREADS;           // 6 scalar samples per thread
+    constexpr int NQ = (SEG / 4 + FT_FFT_THREADS - 1) / FT_FFT_THREADS;       // 2 float4 groups per thread
+    static_assert(NS <= SPT && 4 * NQ <= SPT, "segment registers");
+    float cur[SPT], prv[SPT];
+    bool vec_tile = false;
+    const bool can_vec = (n_samples & 3) == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+    auto fetch = [&](int clip, int frame0) {
+      const float* y = wave + (size_t)clip * n_samples;
+      const int q0 = frame0 * HOP;
+      const int base = q0 - N_FFT / 2;
+      vec_tile = can_vec && base >= 4 && base + SEG <= n_samples;
+      if (vec_tile) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          const int i4 = tid + j * FT_FFT_THREADS;
+          if (i4 < SEG / 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(y + base) + i4);
+            cur[4 * j] = q.x; cur[4 * j + 1] = q.y; cur[4 * j + 2] = q.z; cur[4 * j + 3] = q.w;
+            prv[4 * j] = __ldg(y + base + 4 * i4 - 1);
+          }
+        }
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int i = tid + j * FT_FFT_THREADS;
+        int n = q0 + i - N_FFT / 2;                      // reflect padding (numpy "reflect": no edge repeat)
+        if (n < 0) n = -n;
+        if (n >= n_samples) n = 2 * (n_samples - 1) - n;
+        const bool ok = i < SEG && n >= 0 && n < n_samples;
+        cur[j] = ok ? __ldg(y + n) : 0.f;
+        prv[j] = ok && n > 0 ? __ldg(y + n - 1) : 0.f;
+      }
+    };
+    auto stage = [&](float* s_seg) {                     // q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
+      if (vec_tile) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          const int i4 = tid + j * FT_FFT_THREADS;
+          if (i4 < SEG / 4)
+            *reinterpret_cast<float4*>(s_seg + 4 * i4) =
+                make_float4(fmaf(-0.97f, prv[4 * j], cur[4 * j]), fmaf(-0.97f, cur[4 * j], cur[4 * j + 1]),
+                            fmaf(-0.97f, cur[4 * j + 1], cur[4 * j + 2]), fmaf(-0.97f, cur[4 * j + 2], cur[4 * j + 3]));
+        }
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int i = tid + j * FT_FFT_THREADS;
+        if (i < SEG) s_seg[i] = fmaf(-0.97f, prv[j], cur[j]);
+      }
+    };
+    uint32_t gcount = 0, tcount = 0;
+    fetch(blockIdx.x, 0);
+    stage(sm.seg[0]);
+    bar_named(2, FT_FFT_THREADS);
+    float2* z = sm.z[warp];
+    for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
+      for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
+        const int t_tile = tile * FT_TILE;
+        const int n_groups = min(FT_TILE / FPB, (n_frames - t_tile + FPB - 1) / FPB);
+        for (int g = 0; g < n_groups; ++g, ++gcount) {
+          // where the next group starts (this clip, or frame 0 of the CTA's next clip)
+          int nclip = clip, nframe0 = t_tile + (g + 1) * FPB;
+          if (nframe0 >= n_frames) { nclip = clip + gridDim.x; nframe0 = 0; }
+          const bool has_next = nclip < B;
+          if (has_next) fetch(nclip, nframe0);
+          const int row = g * FPB + warp;
+          const int t = t_tile + row;
+          if (t < n_frames) {                            // warp-uniform
+            float2 v[8];
+            fft_frame(sm.seg[gcount & 1] + warp * HOP, sm.win, z, sm.tw2, sm.tw3, lane, v);
+            // real-FFT split + power, two bins per butterfly (see frontend_kernel)
+            float pa[4], pb[4];
+            const int src = (32 - lane) & 31;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const float2 a = v[7 - m], b = v[(8 - m) & 7];
+              const float mx_a = __shfl_sync(0xffffffffu, a.x, src), my_a = __shfl_sync(0xffffffffu, a.y, src);
+              const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);
+              const float2 zk = v[m];
+              const float2 xe = cadd(zk, zc);
+              const float2 T = cmul(sm.tw[lane + 32 * m], mul_mi(csub(zk, zc)));
+              const float2 Xa = cadd(xe, T), Xb = csub(xe, T);
+              pa[m] = Xa.x * Xa.x + Xa.y * Xa.y;
+              pb[m] = Xb.x * Xb.x + Xb.y * Xb.y;
+            }
+            const float p128 = 4.f * (v[4].x * v[4].x + v[4].y * v[4].y);     // lane 0: Z_128 is its own mirror
+            // the frame's largest bin (bin 256 - lane 0's pb[0] - carries no filter weight and is left out)
+            float mx = lane == 0 ? p128 : pb[0];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) mx = fmaxf(mx, fmaxf(pa[m], m ? pb[m] : mx));
+            mx = warp_max(mx);
+            // scale = 2^(13 - e), e = exponent of the maximum: the largest bin lands in [2^13, 2^14)
+            const int e = max((int)(__float_as_uint(mx) >> 23) - 127, -100);
+            const float sc = mx > 0.f ? __uint_as_float((uint32_t)(127 + 13 - e) << 23) : 1.f;
+            if (g == 0) mbar_wait(&sm.a3_free, (tcount & 1u) ^ 1u);           // the previous tile's mel MMAs have read a3
+            unsigned char* arow = reinterpret_cast<unsigned char*>(&sm.a3[0][0]) + row * 128;
+            const int sw = row & 7;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int k = lane + 32 * m;
+              *reinterpret_cast<__half*>(arow + (k >> 6) * (FT_TILE * 128) + ((((k & 63) >> 3) ^ sw) << 4) + (k & 7) * 2) =
+                  __float2half_rn(pa[m] * sc);
+              const int kk = 256 - k;
+              if (kk < 256)
+                *reinterpret_cast<__half*>(arow + (kk >> 6) * (FT_TILE * 128) + ((((kk & 63) >> 3) ^ sw) << 4) + (kk & 7) * 2) =
+                    __float2half_rn(pb[m] * sc);
+            }
+            if (lane == 0) {
+              *reinterpret_cast<__half*>(arow + 2 * (FT_TILE * 128) + ((0 ^ sw) << 4)) = __float2half_rn(p128 * sc);
+              // mel = acc / (256 sc): the operand is 4 |X|^2 sc and the weights carry a factor 64
+              sm.unscale[row] = mx > 0.f ? __uint_as_float((uint32_t)(127 + e - 13 - 8) << 23) : 1.f;
+            }
+          } else if (g == 0) {
+            mbar_wait(&sm.a3_free, (tcount & 1u) ^ 1u);
+          }
+          if (g == n_groups - 1) {                       // this warp's rows of the tile are in shared memory
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a3_full);
+          }
+          if (has_next) stage(sm.seg[(gcount + 1) & 1]);
+          bar_named(2, FT_FFT_THREADS);
+        }
+      }
+    }
+  } else if (warp == FT_MMA_WARP) {
+    // =============================== MMA issuer (whole warp converged, one elected lane) ============================
+    constexpr uint32_t idesc_mel = umma_idesc(FMT_F16, FT_TILE, N_MELS);
+    constexpr uint32_t idesc_dct = umma_idesc(FMT_F16, FT_TILE, 48);
+    uint32_t tcount = 0;
+    for (int clip = blockIdx.x; clip < B; clip += gridDim.x)
+      for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
+        mbar_wait(&sm.a3_full, tcount & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(sm.a3[kb])), bd = umma_desc_sw128(smem_u32(sm.b3[kb]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_elect(tmem, ad + 2 * k, bd + 2 * k, idesc_mel, (kb | k) != 0);
+        }
+        umma_commit_elect(&sm.a3_free);
+        umma_commit_elect(&sm.d3_full);
+        mbar_wait(&sm.x_full, tcount & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {           // hi x D_hi + lo x D_hi + hi x D_lo
+          const uint64_t ad = umma_desc_sw128(smem_u32(sm.x[term == 1 ? 1 : 0]));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sm.b4[term == 2 ? 1 : 0]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_elect(tmem + 64, ad + 2 * k, bd + 2 * k, idesc_dct, (term | k) != 0);
+        }
+        umma_commit_elect(&sm.d4_full);
+      }
+  } else {
+    // =============================== epilogue: thread = frame row of the tile =======================================
+    const int q = warp & 3, row = q * 32 + lane, et = tid - FT_EPI_WARP0 * 32;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const int sw = row & 7;
+    unsigned char* const x0row = reinterpret_cast<unsigned char*>(&sm.x[0][0]) + row * 128;
+    unsigned char* const x1row = reinterpret_cast<unsigned char*>(&sm.x[1][0]) + row * 128;
+    float* const frow = sm.fout + row * 32;
+    auto put_f32 = [&](const float* vals, int n_chunks) {      // n_chunks x 4 floats into the staging row
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < n_chunks)
+          *reinterpret_cast<float4*>(frow + ((c ^ sw) << 2)) = make_float4(vals[4 * c], vals[4 * c + 1], vals[4 * c + 2], vals[4 * c + 3]);
+    };
+    auto store_f32 = [&](int col, int t0, int clip) {          // staging tile -> feats[clip, t0.., col..col+31]
+      fence_proxy_async_smem();
+      bar_named(1, 128);
+      if (et == 0) {
+        tma_store_3d(&tmF, sm.fout, col, t0, clip);
+        tma_store_commit();
+        tma_store_wait_read0();
+      }
+      bar_named(1, 128);
+    };
+    uint32_t tcount = 0;
+    for (int clip = blockIdx.x; clip < B; clip += gridDim.x)
+      for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
+        const int t0 = tile * FT_TILE;
+        mbar_wait(&sm.d3_full, tcount & 1u);
+        tc_fence_after();
+        const float us = sm.unscale[row];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld32(tl + (uint32_t)(h * 32), r);
+          tmem_ld_wait();
+          float lm[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) lm[j] = 3.01029995663981195f * log2f(fmaxf(__uint_as_float(r[j]) * us, 1e-10f));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 hi, lo;
+            split8(lm + 8 * c, hi, lo);
+            const int off = ((h * 4 + c) ^ sw) << 4;
+            *reinterpret_cast<uint4*>(x0row + off) = hi;
+            *reinterpret_cast<uint4*>(x1row + off) = lo;
+          }
+          if (has_feats) {
+            put_f32(lm, 8);
+            store_f32(h * 32, t0, clip);
+          }
+        }
+        tc_fence_before();                                 // D3 has been read: the MMA warp may overwrite it next tile
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.x_full);
+        if (has_xs) {                                      // log-mel k-blocks of the LSTM operand: hi | lo | hi
+          bar_named(1, 128);
+          if (et == 0) {
+            tma_store_3d(&tmX, sm.x[0], 0, clip, t0);
+            tma_store_3d(&tmX, sm.x[1], 64, clip, t0);
+            tma_store_3d(&tmX, sm.x[0], 128, clip, t0);
+            tma_store_commit();
+          }
+        }
+        mbar_wait(&sm.d4_full, tcount & 1u);
+        tc_fence_after();
+        float mf[40];
+        {
+          uint32_t a[32], b[16];
+          tmem_ld32(tl + 64u, a);
+          tmem_ld16(tl + 96u, b);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mf[j] = __uint_as_float(a[j]) * 0.015625f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mf[32 + j] = __uint_as_float(b[j]) * 0.015625f;
+        }
+        tc_fence_before();
+        if (has_xs) {
+          // x[] is free once the DCT's MMAs are done (d4_full) and the three stores above have read it
+          if (et == 0) tma_store_wait_read0();
+          bar_named(1, 128);
+          // MFCC block of the operand: [mf_hi(40) | mf_lo(40) | mf_hi(40) | 0(8)] = 16 chunks over x[0], x[1]
+          uint4 hi[5], lo[5];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) split8(mf + 8 * c, hi[c], lo[c]);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const uint4 val = c < 5 ? hi[c] : (c < 10 ? lo[c - 5] : (c < 15 ? hi[c - 10] : make_uint4(0u, 0u, 0u, 0u)));
+            *reinterpret_cast<uint4*>((c < 8 ? x0row : x1row) + (((c & 7) ^ sw) << 4)) = val;
+          }
+          fence_proxy_async_smem();
+          bar_named(1, 128);
+          if (et == 0) {
+            tma_store_3d(&tmX, sm.x[0], 192, clip, t0);
+            tma_store_3d(&tmX, sm.x[1], 256, clip, t0);
+            tma_store_commit();
+            tma_store_wait_read0();
+          }
+          bar_named(1, 128);
+        }
+        if (has_feats) {
+          put_f32(mf, 8);
+          store_f32(64, t0, clip);
+          put_f32(mf + 32, 2);                             // columns 96..103; the rest of the box lies outside the tensor
+          store_f32(96, t0, clip);
+        }
+      }
+    if (et == 0) tma_store_wait0();                        // all bulk stores have landed before the CTA exits
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FT_MMA_WARP) tmem_dealloc(tmem, 128);
+}
+
 }  // namespace avhot
 
 using namespace avhot;
@@ -540,8 +999,8 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
   AVHOT_REQUIRE(n_samples > N_FFT / 2, AVHOT_ERR_INVALID,
                 "frontend: n_samples=%d must exceed the reflect pad (256)", n_samples);
   AVHOT_REQUIRE(B <= 65535, AVHOT_ERR_INVALID, "frontend: B > 65535 per call");
-  AVHOT_REQUIRE(!xs || (Bp >= B && ldx >= 3 * N_FEATS + 2 && (ldx & 7) == 0), AVHOT_ERR_INVALID,
-                "frontend: split operand needs Bp >= B and a pitch >= 314 that is a multiple of 8");
+  AVHOT_REQUIRE(!xs || (Bp >= B && ldx >= 3 * N_FEATS + 8 && (ldx & 7) == 0), AVHOT_ERR_INVALID,
+                "frontend: split operand needs Bp >= B and a pitch >= 320 that is a multiple of 8");
   if (B == 0) return AVHOT_OK;
   const FrontendTables* tab = nullptr;
   int rc = get_tables(&tab);
@@ -552,6 +1011,35 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
     AVHOT_CUDA(cudaMemset2DAsync(reinterpret_cast<__half*>(xs) + (size_t)B * ldx, (size_t)Bp * ldx * sizeof(__half), 0,
                                  (size_t)(Bp - B) * ldx * sizeof(__half), (size_t)n_frames, s));
   }
+  static const bool legacy = [] { const char* e = getenv("AVHOT_FE_LEGACY"); return e && atoi(e) != 0; }();
+  if (!legacy) {
+    // tensor maps of the outputs (3-D, so a 128-frame box that runs past the clip's last frame is clipped):
+    // feats (B, n_frames, 104) fp32 as (col, t, clip); operand (n_frames, Bp, ldx) fp16 as (col, clip, t)
+    CUtensorMap tmF, tmX;
+    memset(&tmF, 0, sizeof(tmF));
+    memset(&tmX, 0, sizeof(tmX));
+    if (feats) {
+      const uint64_t dims[3] = {(uint64_t)N_FEATS, (uint64_t)n_frames, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)N_FEATS * 4, (uint64_t)n_frames * N_FEATS * 4};
+      const uint32_t box[3] = {32, FT_TILE, 1};
+      rc = tc::make_tensor_map_3d(&tmF, feats, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box);
+      if (rc != AVHOT_OK) return rc;
+    }
+    if (xs) {
+      const uint64_t dims[3] = {(uint64_t)ldx, (uint64_t)Bp, (uint64_t)n_frames};
+      const uint64_t strides[2] = {(uint64_t)ldx * 2, (uint64_t)Bp * ldx * 2};
+      const uint32_t box[3] = {64, 1, FT_TILE};
+      rc = tc::make_tensor_map_3d(&tmX, xs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dims, strides, box);
+      if (rc != AVHOT_OK) return rc;
+    }
+    const int smem = (int)sizeof(FtSmem) + 1024;
+    AVHOT_CUDA(cudaFuncSetAttribute(frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ProfScope prof("frontend", s);
+    frontend_tc_kernel<<<min(B, num_sms()), FT_THREADS, smem, s>>>(wave, tmF, tmX, feats ? 1 : 0, xs ? 1 : 0, B, n_samples,
+                                                                  n_frames, tab);
+    AVHOT_LAUNCH_CHECK();
+    return AVHOT_OK;
+  }
   // many clips: one CTA per clip walks all its tiles (tables staged once per clip); few clips: one tile per CTA
   const int n_tiles = ceil_div(n_frames, FPB);
   const int tiles_per_cta = (long long)B * 1 >= 2LL * num_sms() ? n_tiles : 1;
@@ -559,28 +1047,11 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
   // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
   AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FeSmem)));
-  static const char* trace_path = getenv("AVHOT_FE_TRACE");
-  long long* d_trace = nullptr;
-  if (trace_path && tiles_per_cta >= 6) {
-    AVHOT_CUDA(cudaMalloc(&d_trace, 16 * sizeof(long long)));
-    AVHOT_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), s));
-  }
   {
     ProfScope prof("frontend", s);
     frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), s>>>(wave, feats, reinterpret_cast<__half*>(xs), Bp, ldx,
-                                                                n_samples, n_frames, tiles_per_cta, tab, d_trace);
+                                                                n_samples, n_frames, tiles_per_cta, tab, nullptr);
     AVHOT_LAUNCH_CHECK();
-  }
-  if (d_trace) {
-    long long h[16];
-    AVHOT_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
-    AVHOT_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_trace);
-    if (FILE* f = fopen(trace_path, "a")) {
-      for (int i = 1; i < 11; ++i) fprintf(f, "%d:%lld ", i, h[i] - h[i - 1]);
-      fprintf(f, "| tile %lld\n", h[10] - h[0]);
-      fclose(f);
-    }
   }
   return AVHOT_OK;
 }

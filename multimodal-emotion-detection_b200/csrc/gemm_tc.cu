@@ -28,8 +28,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_encode_once;
 
-int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes, uint64_t rows,
-                       uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+static void resolve_encode() {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -37,6 +36,11 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType d
         q == cudaDriverEntryPointSuccess)
       g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   });
+}
+
+int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes, uint64_t rows,
+                       uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  resolve_encode();
   AVHOT_REQUIRE(g_encode, AVHOT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   AVHOT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * elem_bytes) % 16 == 0, AVHOT_ERR_INVALID,
                 "tensor map: base must be 16-byte aligned and the row pitch a multiple of 16 bytes");
@@ -49,6 +53,25 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType d
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AVHOT_REQUIRE(r == CUDA_SUCCESS, AVHOT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AVHOT_OK;
+}
+
+int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                       const uint64_t (&dims)[3], const uint64_t (&strides_bytes)[2], const uint32_t (&box)[3]) {
+  resolve_encode();
+  AVHOT_REQUIRE(g_encode, AVHOT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  AVHOT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && strides_bytes[0] % 16 == 0 && strides_bytes[1] % 16 == 0,
+                AVHOT_ERR_INVALID, "tensor map: base and strides must be multiples of 16 bytes");
+  AVHOT_REQUIRE(box[0] * (uint32_t)elem_bytes == 128 && box[1] <= 256 && box[2] <= 256, AVHOT_ERR_INVALID,
+                "tensor map: bad box");
+  const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+  const cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
+  const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult rc = g_encode(out, dtype, 3, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVHOT_REQUIRE(rc == CUDA_SUCCESS, AVHOT_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)rc);
   return AVHOT_OK;
 }
 

@@ -68,7 +68,9 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
       for (int g = 0; g < 4; ++g) acc[g][b] = __ldg(x + g * LH);
     }
     const float* w = whh_t + j;
-#pragma unroll 2
+    // W_hh comes from L2 every step (1 MB per CTA and step): with two k-rows of loads in flight the loop ran at the L2
+    // round-trip time (~110 k cycles per step measured at BT = 12, against 25 k of FMAs); eight rows in flight hide it
+#pragma unroll 8
     for (int k = 0; k < LH; ++k) {
       float wg[4];
 #pragma unroll
@@ -118,22 +120,36 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // fp16 tensor-core GEMM over K' = 3K into A W^T - lo(A) lo(W)^T - O(2^-22), i.e. an fp32-class product: used for
 // layer 0's input projection, whose inputs (log-mel features in dB, |x| ~ 100) are far too large for a single
 // half-precision pass (measured 5.7e-3 error with one TF32 pass).  Requires |x| < 65504.
-// weights: W (N, K) fp32 -> out (N, ldo) fp16 = [W_hi | W_hi | W_lo | 0...]  (ldo >= 3K + 2; the operand's
-// (1, 1) columns meet zeros: the bias is added in fp32 by the GEMM epilogue)
-// Rows of the sigmoid gates (i, f, o: every gate but g = rows [2H, 3H)) are stored halved - exact, a power of two -
-// so that the recurrent kernel's sigmoid(x) = 0.5 tanh(x / 2) + 0.5 needs no pre-scaling multiply (lstm_tc.cu).
+// Column layout (both operands): the features go in blocks of 64; block j (features 64 j .. 64 j + w - 1, w = 64 or the
+// remainder) occupies columns 192 j .. 192 j + 3 w - 1 as [term 0 (w) | term 1 (w) | term 2 (w)], zeros up to the
+// pitch.  For K <= 64 that is [hi | lo | hi]; for the 104 front-end features it is [lm_hi(64) | lm_lo(64) | lm_hi(64) |
+// mf_hi(40) | mf_lo(40) | mf_hi(40) | 0(8)]: every 64-column k-block of the log-mel part is one whole term, which is what
+// lets the front-end kernel hand its tensor-core operand tiles (hi, lo) to TMA as they are (frontend.cu).
+__host__ __device__ __forceinline__ bool split3_slot(int c, int K, int& term, int& feat) {
+  const int j = c / 192, off = c - 192 * j;
+  const int w = min(64, K - 64 * j);
+  if (w <= 0 || off >= 3 * w) return false;
+  term = off / w;
+  feat = 64 * j + off - term * w;
+  return true;
+}
+// weights: W (N, K) fp32 -> out (N, ldo) fp16, term 0 and 1 = W_hi, term 2 = W_lo (the bias is added in fp32 by the GEMM
+// epilogue).  Rows of the sigmoid gates (i, f, o: every gate but g = rows [2H, 3H)) are stored halved - exact, a power of
+// two - so that the recurrent kernel's sigmoid(x) = 0.5 tanh(x / 2) + 0.5 needs no pre-scaling multiply (lstm_tc.cu).
 __device__ __forceinline__ float tc_gate_scale(int n, int N) { return (n / (N / 4)) == 2 ? 1.f : 0.5f; }
 __global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                      __half* __restrict__ out, int N, int K, int ldo) {
   const int n = blockIdx.x;
   const float sc = tc_gate_scale(n, N);
   for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
-    float v = 0.f;
-    bool lo = false;
-    if (k < 2 * K) v = sc * w[(size_t)n * K + (k % K)];
-    else if (k < 3 * K) { v = sc * w[(size_t)n * K + (k - 2 * K)]; lo = true; }
-    const __half hi = __float2half_rn(v);
-    out[(size_t)n * ldo + k] = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+    int term, feat;
+    __half o = __float2half_rn(0.f);
+    if (split3_slot(k, K, term, feat)) {
+      const float v = sc * w[(size_t)n * K + feat];
+      const __half hi = __float2half_rn(v);
+      o = term == 2 ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+    out[(size_t)n * ldo + k] = o;
   }
 }
 // weights of layers > 0: W (N, K) fp32 -> out (N, ldo) fp16 = [W | 0...]
@@ -151,8 +167,8 @@ __global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __r
     out[(size_t)n * ldo + k] = __float2half_rn(v);
   }
 }
-// activations: x (B, T, K) batch-major -> out (T, Bp, ldo) time-major [hi | lo | hi | 1, 1 | 0...]; the rows of the
-// padding clips are zero.  A (16 clips x 4 steps) tile goes through shared memory so that both sides move in long
+// activations: x (B, T, K) batch-major -> out (T, Bp, ldo) time-major, term 0 and 2 = hi, term 1 = lo (split3_slot); the
+// rows of the padding clips are zero.  A (16 clips x 4 steps) tile goes through shared memory so that both sides move in long
 // contiguous runs (reads: 4 steps of one clip; writes: 16 clips of one step = 16 * ldo halves).
 constexpr int SPL_CB = 16, SPL_TB = 4;
 __global__ void __launch_bounds__(256)
@@ -175,14 +191,11 @@ split3_f16_tm_kernel(const float* __restrict__ x, __half* __restrict__ out, int 
     for (int u = 0; u < 2; ++u) {
       const int k = 2 * k2 + u;
       __half o = __float2half_rn(0.f);
-      if (b0 + i < B) {
-        if (k < 3 * K) {
-          const float f = spl_tile[i * (SPL_TB * K) + tt * K + (k % K)];
-          const __half hi = __float2half_rn(f);
-          o = (k >= K && k < 2 * K) ? __float2half_rn(f - __half2float(hi)) : hi;
-        } else if (k < 3 * K + 2) {
-          o = __float2half_rn(1.f);
-        }
+      int term, feat;
+      if (b0 + i < B && split3_slot(k, K, term, feat)) {
+        const float f = spl_tile[i * (SPL_TB * K) + tt * K + feat];
+        const __half hi = __float2half_rn(f);
+        o = term == 1 ? __float2half_rn(f - __half2float(hi)) : hi;
       }
       v[u] = o;
     }

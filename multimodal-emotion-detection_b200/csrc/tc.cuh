@@ -77,6 +77,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(x), "r"(y)
                : "memory");
 }
+// 3-D tiled store (coordinates innermost first); rows / planes outside the tensor's bounds are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -256,6 +263,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- host: tensor maps ----------------------------------------------------------------------------------------
@@ -263,6 +279,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // rows are 128 bytes, written to shared memory with the 128-byte swizzle; out-of-bounds elements read as zero.
 int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes, uint64_t rows,
                        uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+// 3-D tensor, dims / box innermost first, strides (bytes) of dimensions 1 and 2; boxes of 128-byte rows, 128-byte swizzle
+int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                       const uint64_t (&dims)[3], const uint64_t (&strides_bytes)[2], const uint32_t (&box)[3]);
 
 }  // namespace tc
 }  // namespace avhot

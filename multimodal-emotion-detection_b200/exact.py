@@ -3,12 +3,15 @@
 BASELINE.json's north star asks for "predicted labels identical to the reference" - the reference predicts
 argmax(mean_logits) of its fp32 forward (src/uncertainty.py:77).  A label of the tensor-core path can differ from the
 fp32 path's only for a clip whose top-2 margin of the mean logits is smaller than the error of that difference.
-Measured on 56 832 clips of the benchmark workload (tools/measure_near_ties.py, profiles/r2a_near_ties.json), in units
-of max|logit| over the batch: the error of the top-2 difference has RMS 6.6e-5, 99.99 % quantile 4.4e-4, maximum
-5.3e-4 (the per-pass rounding of the fusion GEMMs averages out over the T passes; what remains is the pass-invariant
-TF32 video Linear and the fp16 LSTM state) and a tail that falls a decade per 1.2e-4; the widest margin of a clip whose
-label actually flipped was 1.6e-4.  NearTieResolver takes every clip whose margin is below ``margin_rel * max|logit|``
-(default 6e-4: an undetected flip then needs an error beyond the measured tail, ~3e-9 per clip), keeps a copy of its
+The scale of that error is a property of the model, not of the batch: the classifier sees a convex combination of
+LayerNorm outputs, so |logit_c - bias_c| <= S = max_c ||w_c * g||_2 sqrt(D) (w_c: classifier row, g: post_ln weight;
+S = 9.5 for the default init, where the largest |logit| of a batch is ~1.27).  Measured on 56 832 clips of the benchmark
+workload (tools/measure_near_ties.py, profiles/r2a_near_ties.json), in units of S: the error of the top-2 difference has
+RMS 8.8e-6, 99.99 % quantile 5.9e-5, maximum 7.1e-5 (the per-pass rounding of the fusion GEMMs averages out over the T
+passes; what remains is the pass-invariant TF32 video Linear and the fp16 LSTM state) and a tail that falls a decade
+per 1.6e-5; the widest margin of a clip whose label actually flipped was 2.2e-5.  NearTieResolver takes every clip
+whose margin is below ``margin_rel * S`` (default 8e-5: an undetected flip then needs an error beyond the measured
+tail, ~3e-9 per clip; a pure function of the clip, so results do not depend on batching or sharding), keeps a copy of its
 inputs (avhot_flag_near_ties, avhot_gather_flagged: on the device, no host round trip), re-evaluates it through the fp32
 kernels with its own global clip index - so the Philox masks are the ones it drew the first time - and overwrites its
 records (avhot_scatter_resolved).  With the random-init weights of the benchmark the logits of all clips sit close
@@ -31,7 +34,24 @@ import torch
 
 from . import _lib
 
-DEFAULT_MARGIN_REL = 6e-4                # of max|mean logit| over the batch; see the measurement above
+DEFAULT_MARGIN_REL = 8e-5                # of the model's logit scale S; see the measurement above
+
+
+def logit_scale(model) -> float:
+    """S = max_c ||w_c * g||_2 * sqrt(fan_in) of the head's last Linear (g: the LayerNorm gain in front of it, if any):
+    an a-priori bound of |logit - bias| for HybridFusion (the classifier's input is a convex combination of post_ln
+    rows, src/fusion.py:502-522); for the concat head (Linear-ReLU-Linear, src/train.py:81-85) the same expression on
+    fusion_head[2] is the scale the margin is quoted in."""
+    if getattr(model, "head", None) == "hybrid":
+        lin, gain = model.fusion_model.classifier, model.fusion_model.post_ln.weight
+    elif getattr(model, "head", None) == "concat":
+        lin, gain = model.fusion_head[2], None
+    else:
+        raise ValueError("NearTieResolver: hybrid / concat heads only")
+    w = lin.weight.detach().float()
+    if gain is not None:
+        w = w * gain.detach().float()
+    return float(w.pow(2).sum(dim=1).sqrt().max().item() * (w.shape[1] ** 0.5))
 
 
 class NearTieResolver:
@@ -41,8 +61,9 @@ class NearTieResolver:
         self.model = model
         self.capacity = int(capacity)
         self.margin_rel = float(margin_rel)
+        self.margin = self.margin_rel * logit_scale(model)        # absolute; weights are read once, at construction
         self._dev = None
-        self._state = None               # uint32[4]: appended, overflow, appended before the latest call, max|logit| bits
+        self._state = None               # uint32[4]: appended, overflow, appended before the latest call, (unused)
         self._entry = None               # int32 (3, capacity): tag, row, global clip index (uint32 bit patterns)
         self._pool: Dict[str, torch.Tensor] = {}
         self._calls: List[tuple] = []    # (tag, mean, unc, labels, packed)
@@ -103,7 +124,7 @@ class NearTieResolver:
         with torch.cuda.device(dev):
             s = _lib.stream_ptr(dev)
             ent = self._entry
-            _lib.check(lib.avhot_flag_near_ties(_lib.ptr(mean), B, Cn, self.margin_rel, tag, int(clip0) & (2**64 - 1),
+            _lib.check(lib.avhot_flag_near_ties(_lib.ptr(mean), B, Cn, self.margin, tag, int(clip0) & (2**64 - 1),
                                                 _lib.ptr(self._state), _lib.ptr(ent[0]), _lib.ptr(ent[1]),
                                                 _lib.ptr(ent[2]), self.capacity, s), "flag_near_ties")
             for name, t in rows.items():

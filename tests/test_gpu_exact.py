@@ -21,11 +21,10 @@ def test_flag_gather_scatter_vs_numpy(pkg, dev):
     mean = rng.normal(size=(B, Cn)).astype(np.float32)
     mean[17] = mean[17, 0]                                   # exact tie
     mean[400, 3] = np.nan                                    # NaN rows are flagged
-    margin_rel = 0.01
+    margin_abs = 0.04
     srt = np.sort(np.where(np.isnan(mean), -np.inf, mean), axis=1)
     margin = srt[:, -1] - srt[:, -2]
-    gmax = np.nanmax(np.abs(mean))
-    want = set(np.nonzero(~(margin >= np.float32(margin_rel) * np.float32(gmax)) | np.isnan(mean).any(1))[0].tolist())
+    want = set(np.nonzero(~(margin >= np.float32(margin_abs)) | np.isnan(mean).any(1))[0].tolist())
     assert 2 <= len(want) <= cap // 2
     d_mean = torch.from_numpy(mean).to(dev)
     state = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -34,7 +33,7 @@ def test_flag_gather_scatter_vs_numpy(pkg, dev):
     pool = torch.zeros(cap, 48, dtype=torch.uint8, device=dev)
     s = L.stream_ptr(dev)
     for call, clip0 in ((5, 1000), (6, 5000)):              # two calls of one window append one after the other
-        L.check(lib.avhot_flag_near_ties(L.ptr(d_mean), B, Cn, margin_rel, call, clip0, L.ptr(state), L.ptr(ent[0]),
+        L.check(lib.avhot_flag_near_ties(L.ptr(d_mean), B, Cn, margin_abs, call, clip0, L.ptr(state), L.ptr(ent[0]),
                                          L.ptr(ent[1]), L.ptr(ent[2]), cap, s))
         L.check(lib.avhot_gather_flagged(L.ptr(rows), 48, B, L.ptr(state), L.ptr(ent[1]), L.ptr(pool), cap, s))
     st = state.cpu().numpy()
@@ -110,6 +109,10 @@ def test_tc_labels_equal_fp32_labels_every_batch(pkg, dev, weight_seed):
         assert torch.equal(out[0].argmax(1).int(), out[2])
         gmax = float(ref[0].abs().max())
         assert float((out[0] - ref[0]).abs().max()) <= 2e-3 * gmax        # the stated tolerance holds on every clip
+        top = ref[0].topk(2, dim=1)                                        # the resolver's premise: the error of the top-2
+        d = raw[0] - ref[0]                                                # difference stays inside the margin
+        dd = (d.gather(1, top.indices[:, :1]) - d.gather(1, top.indices[:, 1:2])).abs().max()
+        assert float(dd) < 2.0 * res.margin        # sanity (the measured envelope is ~0.9 of the margin at 8 sigma)
     print(f"weight seed {weight_seed}: {res.flagged_total} of {res.clips_total} clips re-evaluated; the unresolved "
           f"tensor-core path had {raw_flips} label flips")
     # immediate mode (the default of mc_forward with precision 'tc')
