@@ -37,6 +37,20 @@ constexpr int LH = 256;  // hidden size this kernel is specialised for (one thre
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
+// W_hh is streamed through shared memory: chunks of WKC k-rows (WKC x 4 gates x 256 units = 32 KB, contiguous in the
+// k-major copy) travel global/L2 -> shared with cp.async into a ring of WNB buffers, two chunks ahead of the FMAs, one
+// block barrier per chunk.  (Reading W with per-thread __ldg left two warps per scheduler waiting on L2 round trips:
+// 111 k cycles per step measured at BT = 12 against 25 k of FMAs, whatever the unroll depth.)
+constexpr int WKC = 8, WNB = 3, WCHUNKS = LH / WKC;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int BT>
 __global__ void __launch_bounds__(LH)
 lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
@@ -48,8 +62,20 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
   constexpr int HP = BT + 4;  // padded row: conflict-free 128-bit stores of one unit's BT values
   extern __shared__ __align__(16) unsigned char lstm_smem_raw[];
   float (*hs)[LH][HP] = reinterpret_cast<float (*)[LH][HP]>(lstm_smem_raw);   // [2][LH][HP]
+  float (*wb)[WKC][4][LH] = reinterpret_cast<float (*)[WKC][4][LH]>(lstm_smem_raw + sizeof(float) * 2 * LH * HP);  // [WNB]
   const int j = threadIdx.x;
   const int b0 = blockIdx.x * BT;
+  // chunk n of the endless stream (n = t * WCHUNKS + c) -> ring buffer n % WNB; every thread copies 8 x 16 bytes
+  auto issue = [&](int n) {
+    const float* src = whh_t + (size_t)(n % WCHUNKS) * (WKC * 4 * LH);
+    float* dst = &wb[n % WNB][0][0][0];
+#pragma unroll
+    for (int i = 0; i < WKC * 4 * LH / 4 / LH; ++i) cp_async16(dst + 4 * (j + i * LH), src + 4 * (j + i * LH));
+    cp_async_commit();
+  };
+  const int n_total = T * WCHUNKS;
+  issue(0);
+  issue(1);
   float c[BT];
 #pragma unroll
   for (int b = 0; b < BT; ++b) {
@@ -57,6 +83,7 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
     hs[0][j][b] = 0.f;
   }
   __syncthreads();
+  int n = 0;
   for (int t = 0; t < T; ++t) {
     const int cur = t & 1;
     float acc[4][BT];
@@ -67,24 +94,29 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
 #pragma unroll
       for (int g = 0; g < 4; ++g) acc[g][b] = __ldg(x + g * LH);
     }
-    const float* w = whh_t + j;
-    // W_hh comes from L2 every step (1 MB per CTA and step): with two k-rows of loads in flight the loop ran at the L2
-    // round-trip time (~110 k cycles per step measured at BT = 12, against 25 k of FMAs); eight rows in flight hide it
-#pragma unroll 8
-    for (int k = 0; k < LH; ++k) {
-      float wg[4];
+#pragma unroll 1
+    for (int ch = 0; ch < WCHUNKS; ++ch, ++n) {
+      cp_async_wait<1>();                 // this thread's part of chunk n has landed (chunk n + 1 may be in flight)
+      __syncthreads();                    // ... and everybody's; everybody is also done with chunk n - 1's buffer
+      if (n + 2 < n_total) issue(n + 2); else cp_async_commit();   // (empty group: keeps the wait count uniform)
+      const float (*w)[4][LH] = wb[n % WNB];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) wg[g] = __ldg(w + (size_t)(k * 4 + g) * LH);
-      float hv[BT];
+      for (int kk = 0; kk < WKC; ++kk) {
+        const int k = ch * WKC + kk;
+        float wg[4];
 #pragma unroll
-      for (int b4 = 0; b4 < BT; b4 += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&hs[cur][k][b4]);
-        hv[b4] = v.x; hv[b4 + 1] = v.y; hv[b4 + 2] = v.z; hv[b4 + 3] = v.w;
+        for (int g = 0; g < 4; ++g) wg[g] = w[kk][g][j];
+        float hv[BT];
+#pragma unroll
+        for (int b4 = 0; b4 < BT; b4 += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&hs[cur][k][b4]);
+          hv[b4] = v.x; hv[b4 + 1] = v.y; hv[b4 + 2] = v.z; hv[b4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int b = 0; b < BT; ++b) acc[g][b] = fmaf(wg[g], hv[b], acc[g][b]);
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int b = 0; b < BT; ++b) acc[g][b] = fmaf(wg[g], hv[b], acc[g][b]);
     }
     float hn[BT];
 #pragma unroll
@@ -110,8 +142,9 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
           if (t == last_t) h_last[(size_t)(b0 + b) * LH + j] = hn[b];
         }
     }
-    __syncthreads();
+    // no barrier here: the next step's first chunk barrier orders these h writes before anybody reads them
   }
+  cp_async_wait<0>();
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -401,7 +434,7 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
     const int want = 4 * ceil_div(B, 4 * num_sms());
 #define AVHOT_REC_CASE(BT_)                                                                                        \
   case BT_: {                                                                                                       \
-    const size_t smem = sizeof(float) * 2 * LH * (BT_ + 4);                                                         \
+    const size_t smem = sizeof(float) * (2 * LH * (BT_ + 4) + (size_t)WNB * WKC * 4 * LH);                         \
     AVHOT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                     (int)smem));                                                                    \
     lstm_recurrence_kernel<BT_><<<ceil_div(B, BT_), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T); \

@@ -61,6 +61,7 @@ class AVHotPath(nn.Module):
         self.num_classes = num_classes
         self.fold_video_projection = True     # tc + hybrid only; False keeps z_v materialised (A/B tests)
         self._resolver = None                 # exact.NearTieResolver of mc_forward's immediate mode
+        self.near_tie_margin_rel = None       # None = exact.DEFAULT_MARGIN_REL (units of the model's logit scale)
         self.set_precision(precision)
 
     def set_precision(self, precision: str) -> "AVHotPath":
@@ -163,8 +164,10 @@ class AVHotPath(nn.Module):
             return results
         B = results[0].shape[0]
         want = B if B <= 256 else max(256, B // 8)             # near ties are a fraction of a percent of a batch
-        if self._resolver is None or self._resolver.capacity < want:
-            self._resolver = NearTieResolver(self, capacity=want)
+        from .exact import DEFAULT_MARGIN_REL
+        rel = DEFAULT_MARGIN_REL if self.near_tie_margin_rel is None else float(self.near_tie_margin_rel)
+        if self._resolver is None or self._resolver.capacity < want or self._resolver.margin_rel != rel:
+            self._resolver = NearTieResolver(self, capacity=want, margin_rel=rel)
         self._resolver.register(features, mask, results, num_samples, seed, clip0)
         if self._resolver.flush(raise_on_overflow=False) < 0:
             # a degenerate model (e.g. all-equal logits) puts most clips inside the tolerance: the fp32 path for all

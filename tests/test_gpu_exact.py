@@ -46,12 +46,6 @@ def test_flag_gather_scatter_vs_numpy(pkg, dev):
         assert (e[2, sel] == e[1, sel] + clip0).all()
         assert (np.nonzero(sel)[0] // len(want) == k).all()          # the second call's entries come after the first's
     assert (pool.cpu().numpy()[:n] == rows.cpu().numpy()[e[1]]).all()
-    # overflow: capacity smaller than the flagged set raises the flag and never writes past the arrays
-    state.zero_()
-    L.check(lib.avhot_flag_near_ties(L.ptr(d_mean), B, Cn, 10.0, 1, 0, L.ptr(state), L.ptr(ent[0]), L.ptr(ent[1]),
-                                     L.ptr(ent[2]), cap, s))
-    st = state.cpu().numpy()
-    assert st[0] == B and st[1] == 1
     # scatter: records of call 6 only
     r_packed = torch.from_numpy(rng.normal(size=(n, Cn + 1)).astype(np.float32)).to(dev)
     r_labels = torch.arange(n, dtype=torch.int32, device=dev)
@@ -67,6 +61,12 @@ def test_flag_gather_scatter_vs_numpy(pkg, dev):
         assert (o_packed[row].cpu().numpy() == r_packed[idx].cpu().numpy()).all()
         assert (o_mean[row].cpu().numpy() == r_packed[idx, :Cn].cpu().numpy()).all()
         assert float(o_unc[row]) == float(r_packed[idx, Cn])
+    # overflow: capacity smaller than the flagged set raises the flag and never writes past the arrays
+    state.zero_()
+    L.check(lib.avhot_flag_near_ties(L.ptr(d_mean), B, Cn, 10.0, 1, 0, L.ptr(state), L.ptr(ent[0]), L.ptr(ent[1]),
+                                     L.ptr(ent[2]), cap, s))
+    st = state.cpu().numpy()
+    assert st[0] == B and st[1] == 1
 
 
 def _batch(pkg, dev, B, clip0):
@@ -123,19 +123,29 @@ def test_tc_labels_equal_fp32_labels_every_batch(pkg, dev, weight_seed):
 
 
 def test_resolver_overflow_falls_back_to_fp32(pkg, dev):
-    """A model whose logits are all equal (constant classifier) puts every clip inside the tolerance: the immediate mode
-    then evaluates the whole batch in fp32 instead of failing; the deferred mode reports the overflow."""
+    """More near ties than the pool holds (forced here with a margin as wide as the logit scale): the immediate mode
+    evaluates the whole batch in fp32 instead of failing - bit-identical to the fp32 path -, the deferred mode reports
+    the overflow.  A classifier with all-zero weights has logit scale 0: nothing is ambiguous, nothing is flagged."""
     torch.manual_seed(1)
     model = pkg.AVHotPath("hybrid").to(dev).eval().set_precision("tc")
-    with torch.no_grad():
-        model.fusion_model.classifier.weight.zero_()
-        model.fusion_model.classifier.bias.fill_(1.0)
     pkg.MCDropoutUncertainty._set_dropout_train(model)
     B, T = 300, 4
     feats, mask = _batch(pkg, dev, B, 0)
+    model.near_tie_margin_rel = 1.0
     out = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=0)
-    assert model.precision == "tc" and int(out[2].abs().sum()) == 0 and bool((out[0] == 1.0).all())
-    res = pkg.exact.NearTieResolver(model, capacity=16)
+    assert model.precision == "tc"
+    model.set_precision("fp32")
+    ref = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=0)
+    model.set_precision("tc")
+    assert torch.equal(out[3], ref[3]) and torch.equal(out[2], ref[2])
+    res = pkg.exact.NearTieResolver(model, capacity=16, margin_rel=1.0)
     model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=0, exact_labels=res)
     with pytest.raises(RuntimeError):
         res.flush()
+    with torch.no_grad():
+        model.fusion_model.classifier.weight.zero_()
+        model.fusion_model.classifier.bias.fill_(1.0)
+    res0 = pkg.exact.NearTieResolver(model, capacity=16)
+    assert res0.margin == 0.0
+    out = model.mc_forward(feats, mask, num_samples=T, seed=SEED, clip0=0, exact_labels=res0)
+    assert res0.flush() == 0 and int(out[2].abs().sum()) == 0 and bool((out[0] == 1.0).all())
