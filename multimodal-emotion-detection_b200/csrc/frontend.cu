@@ -61,10 +61,12 @@ struct FrontendTables {            // device layout, all fp32 unless noted
                                      //   c = 2 (8 nt + (l >> 2)) + p (zero rows for c >= 40)
   // tcgen05 operands (frontend_tc_kernel), fp16 bit patterns already in the K-major 128-byte-swizzled shared-memory
   // layout ([k-block of 64][row][16-byte chunk ^ (row & 7)]), copied to shared memory as they are:
-  uint16_t b3[4 * N_MELS * 64];      //   mel weights x 64 (= 0.25 for the 4 |X|^2 of the kernel x 256 to keep small taps
-                                     //   normal in fp16): row = filter, K = bins 0..255
+  uint16_t b3lo[32 * 64];            //   mel weights x 64 (= 0.25 for the 4 |X|^2 of the kernel x 256 to keep small taps
+  uint16_t b3hi[4 * 32 * 64];        //   normal in fp16), banded: filters 0-31 over bins 0-63 (they reach no further),
+                                     //   filters 32-63 over bins 0-255; row = filter
   uint16_t b4[2 * 48 * 64];          //   DCT matrix x 64, hi then lo = fp16(D - hi): row = coefficient (40, padded to
                                      //   48), K = 64 log-mel bands
+  float2 t1[256];                    // t1[c * 16 + b] = exp(-2 pi i b c / 256): twiddles between the two radix-16 passes
 };
 
 static FrontendTables g_host_tables;
@@ -157,8 +159,17 @@ static void build_tables() {
   };
   for (int m = 0; m < N_MELS; ++m)
     for (int k = 0; k < 256; ++k) {
-      const int kb = k >> 6, chunk = (k & 63) >> 3, e = k & 7;
-      t.b3[(size_t)kb * (N_MELS * 64) + m * 64 + ((chunk ^ (m & 7)) << 3) + e] = f16_bits(64.f * g_host_mel_dense[m * N_BINS + k]);
+      const int kb = k >> 6, chunk = (k & 63) >> 3, e = k & 7, mr = m & 31;
+      const uint16_t wv = f16_bits(64.f * g_host_mel_dense[m * N_BINS + k]);
+      const size_t pos = (size_t)mr * 64 + ((chunk ^ (mr & 7)) << 3) + e;
+      if (m >= 32) t.b3hi[(size_t)kb * (32 * 64) + pos] = wv;
+      else if (kb == 0) t.b3lo[pos] = wv;
+      else if (g_host_mel_dense[m * N_BINS + k] != 0.f) g_tables_ok = false;   // the banded layout assumes it
+    }
+  for (int c = 0; c < 16; ++c)
+    for (int bq = 0; bq < 16; ++bq) {
+      const double ang = -2.0 * PI * (double)(bq * c) / 256.0;
+      t.t1[c * 16 + bq] = make_float2((float)cos(ang), (float)sin(ang));
     }
   for (int c = 0; c < 48; ++c)
     for (int j = 0; j < N_MELS; ++j) {
@@ -560,45 +571,55 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 
 
 // =====================================================================================================================
-// frontend_tc_kernel: the same front-end with the two dense contractions on the tcgen05 tensor cores.
+// frontend_tc_kernel: the front-end with the two dense contractions on the tcgen05 tensor cores.
 //
-// Persistent CTA (one per SM, grid-stride over clips), 21 warps:
-//   warps 0-15   FFT producers.  A group = 16 consecutive frames of a clip, one per warp: window + radix 8 x 8 x 4 FFT +
-//                real-FFT split + |X|^2 in registers (as above), then the frame's power spectrum is scaled by a power of
+// Persistent CTA (one per SM, grid-stride over clips), 20 warps:
+//   warps 0-15   FFT producers, TWO frames per warp (half-warp = frame, lane b of 16).  A group = 32 consecutive frames
+//                of a clip.  Per frame: pre-emphasis + Hann window while loading the packed samples (lane b takes the
+//                complex points 16 a + b), FFT-256 as 16 x 16: a radix-16 pass in registers, the W_256^{bc} twiddles,
+//                ONE exchange through shared memory (slot (c, b ^ c): conflict-free both ways), a second radix-16
+//                pass - lane c then holds Z[c + 16 d], d = 0..15 -, real-FFT split with the mirrored bin Z[256 - k]
+//                fetched from lane 16 - c by warp shuffle, |X|^2.  The frame's power spectrum is scaled by a power of
 //                two that puts its largest bin at 2^13..2^14, rounded to fp16 and written as ROW (frame) of the mel
-//                GEMM's A operand, K-major with the 128-byte swizzle (a3: 128 frames x 256 bins, 64 KB); the inverse
-//                scale goes to unscale[row].  The samples of the next group travel global -> registers during the FFTs
-//                and are staged into the other half of a double-buffered segment: one 512-thread named barrier a group.
-//   warp 20      MMA issuer: per 128-frame tile, D3 (128 x 64, TMEM) = a3 (fp16) x b3^T (mel weights, fp16), 16
-//                tcgen05.mma M128 N64 K16; then D4 (128 x 48) = [lm_hi | lm_lo | lm_hi] x [D_hi | D_hi | D_lo]^T, the DCT-II
-//                as an error-compensated fp16 product (12 MMAs M128 N48 K16) over the log-mel tile the epilogue wrote.
-//   warps 16-19  epilogue, thread = TMEM lane = frame: tcgen05.ld the mel energies, undo the scale, floor, 10 log10; the
-//                log-mel row goes out as fp16 hi / lo 64-column tiles x[0], x[1] in the same swizzled K-major layout -
-//                which is at once the DCT's A operand and, for the tensor-core LSTM, three 64-column k-blocks of its
-//                first GEMM operand (hi | lo | hi, lstm.cu split3_slot): TMA stores them straight from x[] into the
-//                time-major (t, clip) rows (3-D tensor map, rows past the clip's last frame clipped by the map).  After
-//                the DCT the 40 MFCC go out the same way ([mf_hi | mf_lo | mf_hi | 0] = two more k-blocks).  The fp32
-//                feature tensor (avhot_frontend) leaves through a 32-column staging tile and TMA stores too.
+//                GEMM's A operand, K-major with the 128-byte swizzle (a3: 128 frames x 256 bins); the inverse scale goes
+//                to unscale[row].  The raw samples of the next group are copied global -> shared with cp.async as
+//                soon as every warp has read its inputs (one buffer, two named barriers a group); groups that touch
+//                the reflect padding, or unaligned waveforms, are staged with plain loads and read through an
+//                index-reflecting slow path.
+//   warps 16-19  tensor-core side, thread = TMEM lane = frame row of a 128-frame tile.  Warp 16 also issues the MMAs
+//                (one elected lane): D3 (128 x 64, TMEM) = a3 x b3^T, the mel filterbank as two banded N = 32 GEMMs
+//                (filters 0-31 only reach bins 0-63: 4 + 16 tcgen05.mma M128 N32 K16), then D4 (128 x 48) =
+//                [lm_hi | lm_lo | lm_hi] x [D_hi | D_hi | D_lo]^T, the DCT-II as an error-compensated fp16 product (12
+//                MMAs M128 N48 K16) over the log-mel tile the epilogue wrote.  Epilogue: tcgen05.ld the mel energies,
+//                undo the scale, floor, 10 log10; the log-mel row goes out as fp16 hi / lo 64-column tiles x[0], x[1]
+//                in the same swizzled K-major layout - at once the DCT's A operand and, for the tensor-core LSTM, three
+//                64-column k-blocks of its first GEMM operand (hi | lo | hi, lstm.cu split3_slot): TMA stores them
+//                straight from x[] into the time-major (t, clip) rows (3-D tensor map; rows past the clip's last frame
+//                are clipped by the map).  After the DCT the 40 MFCC go out the same way ([mf_hi | mf_lo | mf_hi | 0]
+//                = two more k-blocks).  The fp32 feature tensor (avhot_frontend) is written row by row.
 // mbarriers: a3_full (16 FFT warps -> MMA), a3_free / d3_full (MMA commit -> FFT warps / epilogue), x_full (4 epilogue
 // warps -> MMA), d4_full (MMA commit -> epilogue).  Parities follow the CTA's tile counter.
 // Precision: power bins and mel weights carry 11 significant bits each (fp16, round to nearest) - the same class as the
 // TF32 weights of the mma.sync version - so a log-mel value is within ~0.002 dB of the fp64 spec in the worst case and
 // ~0.0005 dB typically; the per-frame power-of-two scale keeps every bin within 84 dB of the frame's peak normal in fp16.
 // =====================================================================================================================
-constexpr int FT_FFT_WARPS = 16, FT_EPI_WARP0 = 16, FT_MMA_WARP = 20, FT_THREADS = 21 * 32, FT_TILE = 128;
+constexpr int FT_FFT_WARPS = 16, FT_EPI_WARP0 = 16, FT_THREADS = 20 * 32, FT_TILE = 128, FT_GROUP = 32;
 constexpr int FT_FFT_THREADS = FT_FFT_WARPS * 32;
+constexpr int SEG32 = (FT_GROUP - 1) * HOP + N_FFT;   // 5472 samples a group touches
+constexpr int SEG_PRE = 4;                            // samples staged in front of them (pre-emphasis reads one back)
+constexpr int SEG_BUF = 5504;                         // SEG_PRE + SEG32, rounded up
 
 struct FtSmem {
   __half a3[4][FT_TILE * 64];        // power spectrum tile, A operand of the mel GEMM
-  __half b3[4][N_MELS * 64];         // mel weights, B operand
+  __half b3lo[32 * 64];              // mel weights of filters 0-31 over bins 0-63
+  __half b3hi[4][32 * 64];           // mel weights of filters 32-63 over bins 0-255
   __half x[2][FT_TILE * 64];         // log-mel hi / lo (A operand of the DCT, TMA-store source), later the MFCC block
   __half b4[2][48 * 64];             // DCT matrix hi / lo, B operand
-  float fout[FT_TILE * 32];          // fp32 output staging: one 32-column box
-  float2 z[FT_FFT_WARPS][ZPAD];      // FFT scratch
-  float seg[2][SEG];                 // pre-emphasised samples of a group, double-buffered
+  float2 z[FT_FFT_WARPS][2][256];    // FFT exchange, one 16 x 16 tile per frame
+  float seg[SEG_BUF];                // raw samples of a group: seg[SEG_PRE + i] = y[group's first sample + i]
   float win[N_FFT];
-  float2 tw[N_FFT / 2];
-  float2 tw2[64], tw3[256];
+  float2 tw[N_FFT / 2];              // W_512^k
+  float2 t1[256];                    // t1[c * 16 + b] = W_256^{b c}
   float unscale[FT_TILE];
   uint64_t a3_full, a3_free, d3_full, x_full, d4_full;
   uint32_t tmem_base;
@@ -608,52 +629,32 @@ static_assert(sizeof(FtSmem) + 1024 <= 227 * 1024, "one CTA per SM");
 __device__ __forceinline__ void bar_named(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ void fe_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
 
-// window + FFT-256 of the packed frame + nothing else: on return Z[lane + 32 m] = v[m] (Z = FFT of x[2n] + i x[2n+1])
-__device__ __forceinline__ void fft_frame(const float* __restrict__ frame, const float* __restrict__ s_win, float2* z,
-                                          const float2* __restrict__ s_tw2, const float2* __restrict__ s_tw3, int lane,
-                                          float2 (&v)[8]) {
-  const float2* x2 = reinterpret_cast<const float2*>(frame);
-  const float2* w2 = reinterpret_cast<const float2*>(s_win);
+// DFT-16, natural order in and out: a = a1 + 4 a2, c = c2 + 4 c1, W16^{ac} = W16^{a1 c2} W4^{a1 c1} W4^{a2 c2}
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const float2 s = x2[lane + 32 * r], w = w2[lane + 32 * r];
-    v[r] = make_float2(s.x * w.x, s.y * w.y);
-  }
-  dft8(v);
-  __syncwarp();
+  for (int a1 = 0; a1 < 4; ++a1) dft4(v[a1], v[a1 + 4], v[a1 + 8], v[a1 + 12]);   // v[a1 + 4 c2] = t[a1][c2]
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+  auto mulw = [](float2 a, float wr, float wi) { return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr); };
+  v[1 + 4] = mulw(v[1 + 4], c1, -s1);                                   // W16^1
+  v[1 + 8] = make_float2(r * (v[1 + 8].x + v[1 + 8].y), r * (v[1 + 8].y - v[1 + 8].x));      // W16^2 = (1 - i) / sqrt 2
+  v[1 + 12] = mulw(v[1 + 12], s1, -c1);                                 // W16^3
+  v[2 + 4] = make_float2(r * (v[2 + 4].x + v[2 + 4].y), r * (v[2 + 4].y - v[2 + 4].x));      // W16^2
+  v[2 + 8] = mul_mi(v[2 + 8]);                                          // W16^4 = -i
+  v[2 + 12] = make_float2(r * (v[2 + 12].y - v[2 + 12].x), -r * (v[2 + 12].x + v[2 + 12].y));   // W16^6 = (-1 - i) / sqrt 2
+  v[3 + 4] = mulw(v[3 + 4], s1, -c1);                                   // W16^3
+  v[3 + 8] = make_float2(r * (v[3 + 8].y - v[3 + 8].x), -r * (v[3 + 8].x + v[3 + 8].y));       // W16^6
+  v[3 + 12] = mulw(v[3 + 12], -c1, s1);                                 // W16^9
 #pragma unroll
-  for (int r = 0; r < 8; ++r) z[zpad(lane * 8 + r)] = v[r];
-  __syncwarp();
-  {
-    const int k = lane & 7;
+  for (int c2 = 0; c2 < 4; ++c2) dft4(v[4 * c2], v[4 * c2 + 1], v[4 * c2 + 2], v[4 * c2 + 3]);   // v[c1 + 4 c2] = Y[c2 + 4 c1]
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float2 a = z[zpad(lane + 32 * r)];
-      v[r] = r == 0 ? a : cmul(a, s_tw2[r * 8 + k]);
-    }
-    dft8(v);
-    __syncwarp();
-    const int j0 = (lane - k) * 8 + k;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) z[zpad(j0 + 8 * r)] = v[r];
-    __syncwarp();
-  }
-  {
-    float2 u[2][4];
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = lane + 32 * jj;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float2 a = z[zpad(j + 64 * r)];
-        u[jj][r] = r == 0 ? a : cmul(a, s_tw3[r * 64 + j]);
-      }
-      dft4(u[jj][0], u[jj][1], u[jj][2], u[jj][3]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { v[2 * r] = u[0][r]; v[2 * r + 1] = u[1][r]; }
-  }
+    for (int j = i + 1; j < 4; ++j) { const float2 t = v[i + 4 * j]; v[i + 4 * j] = v[j + 4 * i]; v[j + 4 * i] = t; }
 }
 
 // fp16 hi / lo split of 8 floats -> two 16-byte chunks
@@ -672,9 +673,8 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
-frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUtensorMap tmF,
-                   const __grid_constant__ CUtensorMap tmX, int has_feats, int has_xs, int B, int n_samples, int n_frames,
-                   const FrontendTables* __restrict__ tab) {
+frontend_tc_kernel(const float* __restrict__ wave, float* __restrict__ feats, const __grid_constant__ CUtensorMap tmX,
+                   int has_xs, int B, int n_samples, int n_frames, const FrontendTables* __restrict__ tab) {
   using namespace tc;
   extern __shared__ unsigned char ft_smem_raw[];
   FtSmem& sm = *reinterpret_cast<FtSmem*>(ft_smem_raw + ((1024u - (smem_u32(ft_smem_raw) & 1023u)) & 1023u));
@@ -685,12 +685,11 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
   // ---- one-time setup: tables and tensor-core B operands -> shared memory, barriers, TMEM ---------------------------
   for (int i = tid; i < N_FFT; i += FT_THREADS) sm.win[i] = tab->window[i];
   for (int i = tid; i < N_FFT / 2; i += FT_THREADS) sm.tw[i] = tab->tw[i];
-  for (int i = tid; i < 64; i += FT_THREADS) sm.tw2[i] = tab->tw2[i];
-  for (int i = tid; i < 256; i += FT_THREADS) sm.tw3[i] = tab->tw3[i];
+  for (int i = tid; i < 256; i += FT_THREADS) sm.t1[i] = tab->t1[i];
   {
-    const uint4* s3 = reinterpret_cast<const uint4*>(tab->b3);
-    uint4* d3 = reinterpret_cast<uint4*>(&sm.b3[0][0]);
-    for (int i = tid; i < (int)(sizeof(sm.b3) / 16); i += FT_THREADS) d3[i] = __ldg(s3 + i);
+    const uint4* s3 = reinterpret_cast<const uint4*>(tab->b3lo);     // b3lo and b3hi are adjacent in both structs
+    uint4* d3 = reinterpret_cast<uint4*>(&sm.b3lo[0]);
+    for (int i = tid; i < (int)((sizeof(sm.b3lo) + sizeof(sm.b3hi)) / 16); i += FT_THREADS) d3[i] = __ldg(s3 + i);
     const uint4* s4 = reinterpret_cast<const uint4*>(tab->b4);
     uint4* d4 = reinterpret_cast<uint4*>(&sm.b4[0][0]);
     for (int i = tid; i < (int)(sizeof(sm.b4) / 16); i += FT_THREADS) d4[i] = __ldg(s4 + i);
@@ -703,10 +702,9 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
     mbar_init(&sm.x_full, 4);
     mbar_init(&sm.d4_full, 1);
     fence_barrier_init();
-    if (has_feats) tma_prefetch_desc(&tmF);
     if (has_xs) tma_prefetch_desc(&tmX);
   }
-  if (warp == FT_MMA_WARP) {
+  if (warp == FT_EPI_WARP0) {
     tmem_alloc(&sm.tmem_base, 128);
     tmem_relinquish();
   }
@@ -717,120 +715,151 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
 
   if (warp < FT_FFT_WARPS) {
     // =============================== FFT producers ===================================================================
-    constexpr int SPT = 8;                                                    // registers per thread for a segment
-    constexpr int NS = (SEG + FT_FFT_THREADS - 1) / FT_FFT_THREADS;           // 6 scalar samples per thread
-    constexpr int NQ = (SEG / 4 + FT_FFT_THREADS - 1) / FT_FFT_THREADS;       // 2 float4 groups per thread
-    static_assert(NS <= SPT && 4 * NQ <= SPT, "segment registers");
-    float cur[SPT], prv[SPT];
-    bool vec_tile = false;
+    const int h = lane >> 4, b = lane & 15;
+    const int fr = 2 * warp + h;                     // this half-warp's frame of the group
+    const int sw = fr & 7;                           // row & 7 (groups start at multiples of 32 rows)
+    float2* const zf = sm.z[warp][h];
     const bool can_vec = (n_samples & 3) == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
-    auto fetch = [&](int clip, int frame0) {
+    // samples of the group starting at frame0 -> seg (raw; zeros outside the clip): seg[SEG_PRE + i] = y[q0 - 256 + i]
+    auto stage = [&](int clip, int frame0) {
       const float* y = wave + (size_t)clip * n_samples;
-      const int q0 = frame0 * HOP;
-      const int base = q0 - N_FFT / 2;
-      vec_tile = can_vec && base >= 4 && base + SEG <= n_samples;
-      if (vec_tile) {
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-          const int i4 = tid + j * FT_FFT_THREADS;
-          if (i4 < SEG / 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(y + base) + i4);
-            cur[4 * j] = q.x; cur[4 * j + 1] = q.y; cur[4 * j + 2] = q.z; cur[4 * j + 3] = q.w;
-            prv[4 * j] = __ldg(y + base + 4 * i4 - 1);
-          }
+      const int n0 = frame0 * HOP - N_FFT / 2 - SEG_PRE;              // sample index of seg[0]; a multiple of 4
+      for (int j = tid; j < (SEG_PRE + SEG32) / 4; j += FT_FFT_THREADS) {
+        const int n = n0 + 4 * j;
+        if (can_vec && n >= 0 && n + 4 <= n_samples) {
+          fe_cp_async16(&sm.seg[4 * j], y + n);
+        } else {
+          float4 q;
+          q.x = n >= 0 && n < n_samples ? __ldg(y + n) : 0.f;
+          q.y = n + 1 >= 0 && n + 1 < n_samples ? __ldg(y + n + 1) : 0.f;
+          q.z = n + 2 >= 0 && n + 2 < n_samples ? __ldg(y + n + 2) : 0.f;
+          q.w = n + 3 >= 0 && n + 3 < n_samples ? __ldg(y + n + 3) : 0.f;
+          *reinterpret_cast<float4*>(&sm.seg[4 * j]) = q;
         }
-        return;
       }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const int i = tid + j * FT_FFT_THREADS;
-        int n = q0 + i - N_FFT / 2;                      // reflect padding (numpy "reflect": no edge repeat)
-        if (n < 0) n = -n;
-        if (n >= n_samples) n = 2 * (n_samples - 1) - n;
-        const bool ok = i < SEG && n >= 0 && n < n_samples;
-        cur[j] = ok ? __ldg(y + n) : 0.f;
-        prv[j] = ok && n > 0 ? __ldg(y + n - 1) : 0.f;
-      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto stage = [&](float* s_seg) {                     // q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
-      if (vec_tile) {
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-          const int i4 = tid + j * FT_FFT_THREADS;
-          if (i4 < SEG / 4)
-            *reinterpret_cast<float4*>(s_seg + 4 * i4) =
-                make_float4(fmaf(-0.97f, prv[4 * j], cur[4 * j]), fmaf(-0.97f, cur[4 * j], cur[4 * j + 1]),
-                            fmaf(-0.97f, cur[4 * j + 1], cur[4 * j + 2]), fmaf(-0.97f, cur[4 * j + 2], cur[4 * j + 3]));
-        }
-        return;
-      }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const int i = tid + j * FT_FFT_THREADS;
-        if (i < SEG) s_seg[i] = fmaf(-0.97f, prv[j], cur[j]);
-      }
-    };
-    uint32_t gcount = 0, tcount = 0;
-    fetch(blockIdx.x, 0);
-    stage(sm.seg[0]);
+    uint32_t tcount = 0;
+    stage(blockIdx.x, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     bar_named(2, FT_FFT_THREADS);
-    float2* z = sm.z[warp];
+    // per-lane byte offsets of the power-spectrum stores inside a row of a3 (k = b + 16 d, its mirror 256 - k)
+    const uint32_t base_k = ((uint32_t)((b >> 3) ^ sw) << 4) | ((uint32_t)(b & 7) << 1);
+    const int bm = (16 - b) & 15;                    // lane whose registers hold Z[256 - k]
+    const uint32_t base_m = ((uint32_t)((bm >> 3) ^ sw) << 4) | ((uint32_t)(bm & 7) << 1);
+    const int z0 = b == 0 ? 1 : 0;
+    const int src_lane = (lane & 16) | bm;
+    const float2* const w2 = reinterpret_cast<const float2*>(sm.win);
     for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
       for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
         const int t_tile = tile * FT_TILE;
-        const int n_groups = min(FT_TILE / FPB, (n_frames - t_tile + FPB - 1) / FPB);
-        for (int g = 0; g < n_groups; ++g, ++gcount) {
-          // where the next group starts (this clip, or frame 0 of the CTA's next clip)
-          int nclip = clip, nframe0 = t_tile + (g + 1) * FPB;
+        const int n_groups = min(FT_TILE / FT_GROUP, (n_frames - t_tile + FT_GROUP - 1) / FT_GROUP);
+        for (int g = 0; g < n_groups; ++g) {
+          const int frame0 = t_tile + g * FT_GROUP;
+          int nclip = clip, nframe0 = frame0 + FT_GROUP;           // where the next group starts
           if (nframe0 >= n_frames) { nclip = clip + gridDim.x; nframe0 = 0; }
           const bool has_next = nclip < B;
-          if (has_next) fetch(nclip, nframe0);
-          const int row = g * FPB + warp;
-          const int t = t_tile + row;
-          if (t < n_frames) {                            // warp-uniform
-            float2 v[8];
-            fft_frame(sm.seg[gcount & 1] + warp * HOP, sm.win, z, sm.tw2, sm.tw3, lane, v);
-            // real-FFT split + power, two bins per butterfly (see frontend_kernel)
-            float pa[4], pb[4];
-            const int src = (32 - lane) & 31;
+          const int row = g * FT_GROUP + fr;
+          const int t = frame0 + fr;
+          const bool valid = t < n_frames;
+          const bool warp_live = frame0 + 2 * warp < n_frames;      // warp-uniform: at least the first frame exists
+          float2 v[16];
+          if (warp_live) {
+            // ---- load: pre-emphasis + window, complex point m = 16 a + b = samples 2 m, 2 m + 1 of the frame
+            const int q0 = t * HOP;                                 // centre of the frame
+            const bool edge = valid && (q0 < N_FFT / 2 || q0 + N_FFT / 2 > n_samples);
+            if (!__any_sync(0xffffffffu, edge)) {
+              const float* fs = sm.seg + SEG_PRE + fr * HOP;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const float2 a = v[7 - m], b = v[(8 - m) & 7];
-              const float mx_a = __shfl_sync(0xffffffffu, a.x, src), my_a = __shfl_sync(0xffffffffu, a.y, src);
-              const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);
-              const float2 zk = v[m];
-              const float2 xe = cadd(zk, zc);
-              const float2 T = cmul(sm.tw[lane + 32 * m], mul_mi(csub(zk, zc)));
-              const float2 Xa = cadd(xe, T), Xb = csub(xe, T);
-              pa[m] = Xa.x * Xa.x + Xa.y * Xa.y;
-              pb[m] = Xb.x * Xb.x + Xb.y * Xb.y;
+              for (int a = 0; a < 16; ++a) {
+                const int m = 16 * a + b;
+                const float2 s = *reinterpret_cast<const float2*>(fs + 2 * m);
+                const float pm = fs[2 * m - 1];
+                const float2 w = w2[m];
+                v[a] = make_float2(fmaf(-0.97f, pm, s.x) * w.x, fmaf(-0.97f, s.x, s.y) * w.y);
+              }
+            } else {
+              // frames that touch the reflect padding (numpy "reflect": no edge repeat): q[i] = p[reflect(i)],
+              // p[n] = y[n] - 0.97 y[n - 1], y[-1] = 0; y[n] = seg[SEG_PRE + n - (first sample of the group)]
+              const int gbase = frame0 * HOP - N_FFT / 2;
+#pragma unroll
+              for (int a = 0; a < 16; ++a) {
+                const int m = 16 * a + b;
+                float pv[2];
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                  int n = q0 - N_FFT / 2 + 2 * m + e2;
+                  if (n < 0) n = -n;
+                  if (n >= n_samples) n = 2 * (n_samples - 1) - n;
+                  const int idx = min(max(n - gbase, 1 - SEG_PRE), SEG32 - 1);
+                  const float yn = sm.seg[SEG_PRE + idx];
+                  const float yp = n >= 1 ? sm.seg[SEG_PRE + idx - 1] : 0.f;
+                  pv[e2] = fmaf(-0.97f, yp, yn);
+                }
+                const float2 w = w2[m];
+                v[a] = make_float2(pv[0] * w.x, pv[1] * w.y);
+              }
             }
-            const float p128 = 4.f * (v[4].x * v[4].x + v[4].y * v[4].y);     // lane 0: Z_128 is its own mirror
-            // the frame's largest bin (bin 256 - lane 0's pb[0] - carries no filter weight and is left out)
-            float mx = lane == 0 ? p128 : pb[0];
+          }
+          bar_named(2, FT_FFT_THREADS);                             // every warp has read its samples: seg is free
+          if (has_next) stage(nclip, nframe0);
+          if (warp_live) {
+            // ---- FFT-256 = 16 x 16
+            dft16(v);                                               // over a: Y_b[c]
 #pragma unroll
-            for (int m = 0; m < 4; ++m) mx = fmaxf(mx, fmaxf(pa[m], m ? pb[m] : mx));
-            mx = warp_max(mx);
+            for (int c = 1; c < 16; ++c) v[c] = cmul(v[c], sm.t1[c * 16 + b]);
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) zf[c * 16 + (b ^ c)] = v[c];
+            __syncwarp();
+#pragma unroll
+            for (int bb = 0; bb < 16; ++bb) v[bb] = zf[b * 16 + (bb ^ b)];   // lane c = b reads (c, bb)
+            dft16(v);                                               // over b: Z[c + 16 d] = v[d]
+            // ---- real-FFT split + power: bins k = c + 16 d (d < 8) and 256 - k from the pair (Z_k, Z_{256-k});
+            //      Z_{256-k} is register 15 - d of lane 16 - c (register 16 - d of lane 0 itself for c = 0)
+            float pa[8], pb[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+              const float2 snd = v[15 - d];
+              const float px = __shfl_sync(0xffffffffu, snd.x, src_lane), py = __shfl_sync(0xffffffffu, snd.y, src_lane);
+              const float2 own = d == 0 ? v[0] : v[16 - d];
+              const float2 zc = z0 ? make_float2(own.x, -own.y) : make_float2(px, -py);     // conj(Z[256 - k])
+              const float2 zk = v[d];
+              const float2 xe = cadd(zk, zc);
+              const float2 T = cmul(sm.tw[b + 16 * d], mul_mi(csub(zk, zc)));
+              const float2 Xa = cadd(xe, T), Xb = csub(xe, T);
+              pa[d] = Xa.x * Xa.x + Xa.y * Xa.y;                     // 4 |X_k|^2 (the factor lives in the mel weights)
+              pb[d] = Xb.x * Xb.x + Xb.y * Xb.y;                     // 4 |X_{256-k}|^2
+            }
+            const float p128 = 4.f * (v[8].x * v[8].x + v[8].y * v[8].y);   // lane 0: Z_128 is its own mirror
+            // the frame's largest bin (bin 256 - lane 0's pb[0] - carries no filter weight and is left out)
+            float mx = z0 ? p128 : pb[0];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) mx = fmaxf(mx, fmaxf(pa[d], d ? pb[d] : mx));
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             // scale = 2^(13 - e), e = exponent of the maximum: the largest bin lands in [2^13, 2^14)
             const int e = max((int)(__float_as_uint(mx) >> 23) - 127, -100);
             const float sc = mx > 0.f ? __uint_as_float((uint32_t)(127 + 13 - e) << 23) : 1.f;
-            if (g == 0) mbar_wait(&sm.a3_free, (tcount & 1u) ^ 1u);           // the previous tile's mel MMAs have read a3
-            unsigned char* arow = reinterpret_cast<unsigned char*>(&sm.a3[0][0]) + row * 128;
-            const int sw = row & 7;
+            if (g == 0) mbar_wait(&sm.a3_free, (tcount & 1u) ^ 1u);   // the previous tile's mel MMAs have read a3
+            if (valid) {
+              unsigned char* arow = reinterpret_cast<unsigned char*>(&sm.a3[0][0]) + row * 128;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int k = lane + 32 * m;
-              *reinterpret_cast<__half*>(arow + (k >> 6) * (FT_TILE * 128) + ((((k & 63) >> 3) ^ sw) << 4) + (k & 7) * 2) =
-                  __float2half_rn(pa[m] * sc);
-              const int kk = 256 - k;
-              if (kk < 256)
-                *reinterpret_cast<__half*>(arow + (kk >> 6) * (FT_TILE * 128) + ((((kk & 63) >> 3) ^ sw) << 4) + (kk & 7) * 2) =
-                    __float2half_rn(pb[m] * sc);
-            }
-            if (lane == 0) {
-              *reinterpret_cast<__half*>(arow + 2 * (FT_TILE * 128) + ((0 ^ sw) << 4)) = __float2half_rn(p128 * sc);
-              // mel = acc / (256 sc): the operand is 4 |X|^2 sc and the weights carry a factor 64
-              sm.unscale[row] = mx > 0.f ? __uint_as_float((uint32_t)(127 + e - 13 - 8) << 23) : 1.f;
+              for (int d = 0; d < 8; ++d) {
+                // bin k = b + 16 d: k-block d >> 2, chunk (b >> 3) + 2 (d & 3)
+                *reinterpret_cast<__half*>(arow + (d >> 2) * (FT_TILE * 128) + (base_k ^ (uint32_t)((d & 3) << 5))) =
+                    __float2half_rn(pa[d] * sc);
+                // bin 256 - k = bm + 16 dd, dd = 15 - d (16 - d for lane 0, whose d = 0 mirror is the unused bin 256)
+                const int dd = 15 - d + z0;
+                if (dd < 16)
+                  *reinterpret_cast<__half*>(arow + (dd >> 2) * (FT_TILE * 128) + (base_m ^ (uint32_t)((dd & 3) << 5))) =
+                      __float2half_rn(pb[d] * sc);
+              }
+              if (z0) {
+                *reinterpret_cast<__half*>(arow + 2 * (FT_TILE * 128) + ((uint32_t)sw << 4)) = __float2half_rn(p128 * sc);
+                // mel = acc / (256 sc): the operand is 4 |X|^2 sc and the weights carry a factor 64
+                sm.unscale[row] = mx > 0.f ? __uint_as_float((uint32_t)(127 + e - 13 - 8) << 23) : 1.f;
+              }
             }
           } else if (g == 0) {
             mbar_wait(&sm.a3_free, (tcount & 1u) ^ 1u);
@@ -840,74 +869,51 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a3_full);
           }
-          if (has_next) stage(sm.seg[(gcount + 1) & 1]);
-          bar_named(2, FT_FFT_THREADS);
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          bar_named(2, FT_FFT_THREADS);                  // the next group's samples are in seg
         }
       }
     }
-  } else if (warp == FT_MMA_WARP) {
-    // =============================== MMA issuer (whole warp converged, one elected lane) ============================
-    constexpr uint32_t idesc_mel = umma_idesc(FMT_F16, FT_TILE, N_MELS);
-    constexpr uint32_t idesc_dct = umma_idesc(FMT_F16, FT_TILE, 48);
-    uint32_t tcount = 0;
-    for (int clip = blockIdx.x; clip < B; clip += gridDim.x)
-      for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
-        mbar_wait(&sm.a3_full, tcount & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t ad = umma_desc_sw128(smem_u32(sm.a3[kb])), bd = umma_desc_sw128(smem_u32(sm.b3[kb]));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_elect(tmem, ad + 2 * k, bd + 2 * k, idesc_mel, (kb | k) != 0);
-        }
-        umma_commit_elect(&sm.a3_free);
-        umma_commit_elect(&sm.d3_full);
-        mbar_wait(&sm.x_full, tcount & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {           // hi x D_hi + lo x D_hi + hi x D_lo
-          const uint64_t ad = umma_desc_sw128(smem_u32(sm.x[term == 1 ? 1 : 0]));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sm.b4[term == 2 ? 1 : 0]));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_elect(tmem + 64, ad + 2 * k, bd + 2 * k, idesc_dct, (term | k) != 0);
-        }
-        umma_commit_elect(&sm.d4_full);
-      }
   } else {
-    // =============================== epilogue: thread = frame row of the tile =======================================
+    // =============================== tensor-core side: thread = frame row of the tile ==============================
     const int q = warp & 3, row = q * 32 + lane, et = tid - FT_EPI_WARP0 * 32;
+    const bool issuer = warp == FT_EPI_WARP0;            // this warp also issues the MMAs (whole warp, one elected lane)
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     const int sw = row & 7;
+    constexpr uint32_t idesc_mel = umma_idesc(FMT_F16, FT_TILE, 32);
+    constexpr uint32_t idesc_dct = umma_idesc(FMT_F16, FT_TILE, 48);
     unsigned char* const x0row = reinterpret_cast<unsigned char*>(&sm.x[0][0]) + row * 128;
     unsigned char* const x1row = reinterpret_cast<unsigned char*>(&sm.x[1][0]) + row * 128;
-    float* const frow = sm.fout + row * 32;
-    auto put_f32 = [&](const float* vals, int n_chunks) {      // n_chunks x 4 floats into the staging row
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < n_chunks)
-          *reinterpret_cast<float4*>(frow + ((c ^ sw) << 2)) = make_float4(vals[4 * c], vals[4 * c + 1], vals[4 * c + 2], vals[4 * c + 3]);
-    };
-    auto store_f32 = [&](int col, int t0, int clip) {          // staging tile -> feats[clip, t0.., col..col+31]
-      fence_proxy_async_smem();
-      bar_named(1, 128);
-      if (et == 0) {
-        tma_store_3d(&tmF, sm.fout, col, t0, clip);
-        tma_store_commit();
-        tma_store_wait_read0();
-      }
-      bar_named(1, 128);
-    };
     uint32_t tcount = 0;
     for (int clip = blockIdx.x; clip < B; clip += gridDim.x)
       for (int tile = 0; tile < n_tiles; ++tile, ++tcount) {
         const int t0 = tile * FT_TILE;
+        const bool valid = t0 + row < n_frames;
+        float* const frow = feats ? feats + ((size_t)clip * n_frames + t0 + row) * N_FEATS : nullptr;
+        if (issuer) {
+          mbar_wait(&sm.a3_full, tcount & 1u);
+          tc_fence_after();
+          {   // filters 0-31: bins 0-63 only
+            const uint64_t ad = umma_desc_sw128(smem_u32(sm.a3[0])), bd = umma_desc_sw128(smem_u32(sm.b3lo));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_elect(tmem, ad + 2 * k, bd + 2 * k, idesc_mel, k != 0);
+          }
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {   // filters 32-63
+            const uint64_t ad = umma_desc_sw128(smem_u32(sm.a3[kb])), bd = umma_desc_sw128(smem_u32(sm.b3hi[kb]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_elect(tmem + 32, ad + 2 * k, bd + 2 * k, idesc_mel, (kb | k) != 0);
+          }
+          umma_commit_elect(&sm.a3_free);
+          umma_commit_elect(&sm.d3_full);
+        }
         mbar_wait(&sm.d3_full, tcount & 1u);
         tc_fence_after();
         const float us = sm.unscale[row];
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int hh = 0; hh < 2; ++hh) {
           uint32_t r[32];
-          tmem_ld32(tl + (uint32_t)(h * 32), r);
+          tmem_ld32(tl + (uint32_t)(hh * 32), r);
           tmem_ld_wait();
           float lm[32];
 #pragma unroll
@@ -916,19 +922,32 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
           for (int c = 0; c < 4; ++c) {
             uint4 hi, lo;
             split8(lm + 8 * c, hi, lo);
-            const int off = ((h * 4 + c) ^ sw) << 4;
+            const int off = ((hh * 4 + c) ^ sw) << 4;
             *reinterpret_cast<uint4*>(x0row + off) = hi;
             *reinterpret_cast<uint4*>(x1row + off) = lo;
           }
-          if (has_feats) {
-            put_f32(lm, 8);
-            store_f32(h * 32, t0, clip);
+          if (frow && valid) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(frow + hh * 32 + 4 * c) = make_float4(lm[4 * c], lm[4 * c + 1], lm[4 * c + 2], lm[4 * c + 3]);
           }
         }
-        tc_fence_before();                                 // D3 has been read: the MMA warp may overwrite it next tile
+        tc_fence_before();                                 // D3 has been read: the next tile's mel MMAs may overwrite it
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.x_full);
+        if (issuer) {
+          mbar_wait(&sm.x_full, tcount & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {           // hi x D_hi + lo x D_hi + hi x D_lo
+            const uint64_t ad = umma_desc_sw128(smem_u32(sm.x[term == 1 ? 1 : 0]));
+            const uint64_t bd = umma_desc_sw128(smem_u32(sm.b4[term == 2 ? 1 : 0]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_elect(tmem + 64, ad + 2 * k, bd + 2 * k, idesc_dct, (term | k) != 0);
+          }
+          umma_commit_elect(&sm.d4_full);
+        }
         if (has_xs) {                                      // log-mel k-blocks of the LSTM operand: hi | lo | hi
           bar_named(1, 128);
           if (et == 0) {
@@ -942,16 +961,21 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
         tc_fence_after();
         float mf[40];
         {
-          uint32_t a[32], b[16];
+          uint32_t a[32], bq[16];
           tmem_ld32(tl + 64u, a);
-          tmem_ld16(tl + 96u, b);
+          tmem_ld16(tl + 96u, bq);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) mf[j] = __uint_as_float(a[j]) * 0.015625f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) mf[32 + j] = __uint_as_float(b[j]) * 0.015625f;
+          for (int j = 0; j < 8; ++j) mf[32 + j] = __uint_as_float(bq[j]) * 0.015625f;
         }
         tc_fence_before();
+        if (frow && valid) {
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            *reinterpret_cast<float4*>(frow + N_MELS + 4 * c) = make_float4(mf[4 * c], mf[4 * c + 1], mf[4 * c + 2], mf[4 * c + 3]);
+        }
         if (has_xs) {
           // x[] is free once the DCT's MMAs are done (d4_full) and the three stores above have read it
           if (et == 0) tma_store_wait_read0();
@@ -975,18 +999,12 @@ frontend_tc_kernel(const float* __restrict__ wave, const __grid_constant__ CUten
           }
           bar_named(1, 128);
         }
-        if (has_feats) {
-          put_f32(mf, 8);
-          store_f32(64, t0, clip);
-          put_f32(mf + 32, 2);                             // columns 96..103; the rest of the box lies outside the tensor
-          store_f32(96, t0, clip);
-        }
       }
     if (et == 0) tma_store_wait0();                        // all bulk stores have landed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == FT_MMA_WARP) tmem_dealloc(tmem, 128);
+  if (warp == FT_EPI_WARP0) tmem_dealloc(tmem, 128);
 }
 
 }  // namespace avhot
@@ -1013,18 +1031,12 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
   }
   static const bool legacy = [] { const char* e = getenv("AVHOT_FE_LEGACY"); return e && atoi(e) != 0; }();
   if (!legacy) {
-    // tensor maps of the outputs (3-D, so a 128-frame box that runs past the clip's last frame is clipped):
-    // feats (B, n_frames, 104) fp32 as (col, t, clip); operand (n_frames, Bp, ldx) fp16 as (col, clip, t)
-    CUtensorMap tmF, tmX;
-    memset(&tmF, 0, sizeof(tmF));
+    // tensor map of the operand (3-D, so a 128-frame box that runs past the clip's last frame is clipped):
+    // (n_frames, Bp, ldx) fp16 as (col, clip, t)
+    CUtensorMap tmX;
     memset(&tmX, 0, sizeof(tmX));
-    if (feats) {
-      const uint64_t dims[3] = {(uint64_t)N_FEATS, (uint64_t)n_frames, (uint64_t)B};
-      const uint64_t strides[2] = {(uint64_t)N_FEATS * 4, (uint64_t)n_frames * N_FEATS * 4};
-      const uint32_t box[3] = {32, FT_TILE, 1};
-      rc = tc::make_tensor_map_3d(&tmF, feats, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box);
-      if (rc != AVHOT_OK) return rc;
-    }
+    AVHOT_REQUIRE(!feats || (reinterpret_cast<uintptr_t>(feats) & 15) == 0, AVHOT_ERR_INVALID,
+                  "frontend: feats must be 16-byte aligned");
     if (xs) {
       const uint64_t dims[3] = {(uint64_t)ldx, (uint64_t)Bp, (uint64_t)n_frames};
       const uint64_t strides[2] = {(uint64_t)ldx * 2, (uint64_t)Bp * ldx * 2};
@@ -1035,8 +1047,7 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
     const int smem = (int)sizeof(FtSmem) + 1024;
     AVHOT_CUDA(cudaFuncSetAttribute(frontend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ProfScope prof("frontend", s);
-    frontend_tc_kernel<<<min(B, num_sms()), FT_THREADS, smem, s>>>(wave, tmF, tmX, feats ? 1 : 0, xs ? 1 : 0, B, n_samples,
-                                                                  n_frames, tab);
+    frontend_tc_kernel<<<min(B, num_sms()), FT_THREADS, smem, s>>>(wave, feats, tmX, xs ? 1 : 0, B, n_samples, n_frames, tab);
     AVHOT_LAUNCH_CHECK();
     return AVHOT_OK;
   }
