@@ -891,7 +891,7 @@ frontend_tc_kernel(const float* __restrict__ wave, float* __restrict__ feats, co
         const bool valid = t0 + row < n_frames;
         float* const frow = feats ? feats + ((size_t)clip * n_frames + t0 + row) * N_FEATS : nullptr;
         if (issuer) {
-          mbar_wait(&sm.a3_full, tcount & 1u);
+          mbar_wait_sleep(&sm.a3_full, tcount & 1u);
           tc_fence_after();
           {   // filters 0-31: bins 0-63 only
             const uint64_t ad = umma_desc_sw128(smem_u32(sm.a3[0])), bd = umma_desc_sw128(smem_u32(sm.b3lo));
@@ -907,7 +907,7 @@ frontend_tc_kernel(const float* __restrict__ wave, float* __restrict__ feats, co
           umma_commit_elect(&sm.a3_free);
           umma_commit_elect(&sm.d3_full);
         }
-        mbar_wait(&sm.d3_full, tcount & 1u);
+        mbar_wait_sleep(&sm.d3_full, tcount & 1u);
         tc_fence_after();
         const float us = sm.unscale[row];
 #pragma unroll 1
@@ -937,7 +937,7 @@ frontend_tc_kernel(const float* __restrict__ wave, float* __restrict__ feats, co
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.x_full);
         if (issuer) {
-          mbar_wait(&sm.x_full, tcount & 1u);
+          mbar_wait_sleep(&sm.x_full, tcount & 1u);
           tc_fence_after();
 #pragma unroll
           for (int term = 0; term < 3; ++term) {           // hi x D_hi + lo x D_hi + hi x D_lo
@@ -957,7 +957,7 @@ frontend_tc_kernel(const float* __restrict__ wave, float* __restrict__ feats, co
             tma_store_commit();
           }
         }
-        mbar_wait(&sm.d4_full, tcount & 1u);
+        mbar_wait_sleep(&sm.d4_full, tcount & 1u);
         tc_fence_after();
         float mf[40];
         {
