@@ -30,6 +30,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also runs the CPU baseline / reference arm, which is meant to use
+# every host core it may run on: undo that before torch (and its OpenMP runtime) is imported
+ORIG_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set(range(os.cpu_count() or 1))
+if os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(len(ORIG_AFFINITY))
+
+
+def host_threads():
+    """Cores the CPU leg may use: the process's affinity mask at start-up (the e2e leg may have narrowed it to the GPU's
+    NUMA node since; the CPU leg widens it again)."""
+    try:
+        os.sched_setaffinity(0, ORIG_AFFINITY)
+    except (AttributeError, OSError):
+        pass
+    return max(1, len(ORIG_AFFINITY))
 
 SEED = 42
 N_SAMPLES, N_FRAMES, FRAME_DIM, N_CLASSES = 48000, 16, 112 * 112, 8
@@ -143,7 +158,7 @@ def run_reference_arm(args):
         return 0
     import torch
     from oracle import model as om, synth as osynth
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sd = om.to_torch(osynth.synth_weights(SEED))
     n = args.cpu_clips
     for w in range(args.warmup):
@@ -433,7 +448,7 @@ def run_b200_arm(args):
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import model as om   # noqa: F401  (the checker / baseline leg)
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         n = args.cpu_clips if world == 1 else max(32, args.cpu_clips // 4)
         dt, dfe, cpu_mean = cpu_reference_step(n, T, clip0_of(0), sd_cpu, threads)
         feats, mask = synth_inputs(ctx, n, clip0_of(0))
@@ -734,7 +749,8 @@ def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
     pinned HOST memory: every step uploads its B clips host->device in sub-batches of --e2e-chunk clips and reads the
     packed results back; the upload of sub-batch i+1 overlaps the kernels of sub-batch i on a second stream (two
     device staging slots).  The pinned source ring holds two sub-batches (real copies every time; clip indices for
-    the Philox masks advance normally).  The near-tie flush runs once per step, before the results are read back."""
+    the Philox masks advance normally).  The near-tie flush runs once per window of --resolve-every steps, before the
+    window's results are read back (the uploads of the next window's first sub-batches are already in flight)."""
     torch, dist, pkg, par, dev, world, args = ctx.torch, ctx.dist, ctx.pkg, ctx.par, ctx.dev, ctx.world, ctx.args
     model, res = ctx.model, ctx.resolver
     C = min(args.e2e_chunk, B)
@@ -746,8 +762,9 @@ def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
         host.append(tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (a, v, m)))
         slots.append(tuple(torch.empty_like(t) for t in (a, v, m)))
         del feats, a, v, m
-    packed_dev = torch.empty(B, N_CLASSES + 1, device=dev)
-    result_host = torch.empty(B * world, N_CLASSES + 1, pin_memory=True)
+    W = max(1, args.resolve_every)
+    packed_dev = [torch.empty(B, N_CLASSES + 1, device=dev) for _ in range(W)]
+    result_host = torch.empty(W, B * world, N_CLASSES + 1, pin_memory=True)
     copy_stream = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
     uploaded = [torch.cuda.Event() for _ in range(2)]
@@ -755,6 +772,7 @@ def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
     counter = [0]
 
     def run(n_steps, step0):
+        window = []                                       # (slot, [(row0, n, packed of the sub-batch)])
         for j in range(n_steps):
             base = clip0_of(step0 + j)
             parts = []
@@ -774,13 +792,17 @@ def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
                                           num_samples=T, seed=SEED, clip0=base + i * C,
                                           exact_labels=res if res else False)[3]
                 consumed[s].record(main)
-                parts.append((i, n, packed))
-            if res:
-                res.flush()                               # patches the sub-batches' packed records in place
-            for i, n, packed in parts:
-                packed_dev[i * C:i * C + n].copy_(packed)
-            out = par.all_gather_packed(packed_dev, B * world) if world > 1 else packed_dev
-            result_host.copy_(out, non_blocking=True)
+                parts.append((i * C, n, packed))
+            window.append(parts)
+            if len(window) == W or j == n_steps - 1:
+                if res:
+                    res.flush()                           # patches the window's packed records in place
+                for w, parts in enumerate(window):
+                    for row0, n, packed in parts:
+                        packed_dev[w][row0:row0 + n].copy_(packed)
+                    out = par.all_gather_packed(packed_dev[w], B * world) if world > 1 else packed_dev[w]
+                    result_host[w].copy_(out, non_blocking=True)
+                window = []
 
     run(1, 0)
     ctx.barrier()
@@ -800,8 +822,8 @@ def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
             "input_format": {"audio": "16-bit PCM" if audio == "i16" else "fp32 waveform",
                              "video": "uint8 pixels" if video == "u8" else "fp32 k/255"},
             "api": f"AVHotPath.mc_forward (fast path of MCDropoutUncertainty.forward), pinned host buffers, {n_sub} "
-                   f"sub-batches of <= {C} clips per step, uploads double-buffered on a copy stream, near-tie flush once per "
-                   f"step"}
+                   f"sub-batches of <= {C} clips per step, uploads double-buffered on a copy stream, near-tie flush and result "
+                   f"read-back once per {W} steps"}
 
 
 def main():

@@ -26,7 +26,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"].startswith("BASELINE.json configs[4]") and d["config"]["mc_passes"] == 2
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "2 synthetic clips" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == len(os.sched_getaffinity(0)) and cb["value"] == d["value"] and "2 synthetic clips" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
