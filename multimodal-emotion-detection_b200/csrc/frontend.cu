@@ -577,7 +577,7 @@ frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __hal
 //   warps 0-15   FFT producers, TWO frames per warp (half-warp = frame, lane b of 16).  A group = 32 consecutive frames
 //                of a clip.  Per frame: pre-emphasis + Hann window while loading the packed samples (lane b takes the
 //                complex points 16 a + b), FFT-256 as 16 x 16: a radix-16 pass in registers, the W_256^{bc} twiddles,
-//                ONE exchange through shared memory (slot (c, b ^ c): conflict-free both ways), a second radix-16
+//                ONE exchange through shared memory (16 x 16 tile, rows padded to 17: conflict-free both ways), a second radix-16
 //                pass - lane c then holds Z[c + 16 d], d = 0..15 -, real-FFT split with the mirrored bin Z[256 - k]
 //                fetched from lane 16 - c by warp shuffle, |X|^2.  The frame's power spectrum is scaled by a power of
 //                two that puts its largest bin at 2^13..2^14, rounded to fp16 and written as ROW (frame) of the mel
@@ -608,6 +608,9 @@ constexpr int FT_FFT_THREADS = FT_FFT_WARPS * 32;
 constexpr int SEG32 = (FT_GROUP - 1) * HOP + N_FFT;   // 5472 samples a group touches
 constexpr int SEG_PRE = 4;                            // samples staged in front of them (pre-emphasis reads one back)
 constexpr int SEG_BUF = 5504;                         // SEG_PRE + SEG32, rounded up
+constexpr int ZROW = 17;                              // exchange tile row pitch: element (c, b) at c * 17 + b - lanes b write
+                                                      // consecutive slots, lanes c read slots 17 apart (34 words: distinct
+                                                      // bank pairs), and every address is a lane base plus a constant
 
 struct FtSmem {
   __half a3[4][FT_TILE * 64];        // power spectrum tile, A operand of the mel GEMM
@@ -615,7 +618,7 @@ struct FtSmem {
   __half b3hi[4][32 * 64];           // mel weights of filters 32-63 over bins 0-255
   __half x[2][FT_TILE * 64];         // log-mel hi / lo (A operand of the DCT, TMA-store source), later the MFCC block
   __half b4[2][48 * 64];             // DCT matrix hi / lo, B operand
-  float2 z[FT_FFT_WARPS][2][256];    // FFT exchange, one 16 x 16 tile per frame
+  float2 z[FT_FFT_WARPS][2][16 * ZROW];   // FFT exchange, one 16 x 16 tile per frame, rows padded to 17
   float seg[SEG_BUF];                // raw samples of a group: seg[SEG_PRE + i] = y[group's first sample + i]
   float win[N_FFT];
   float2 tw[N_FFT / 2];              // W_512^k
@@ -810,10 +813,10 @@ frontend_tc_kernel(const float* __restrict__ wave, float* __restrict__ feats, co
             for (int c = 1; c < 16; ++c) v[c] = cmul(v[c], sm.t1[c * 16 + b]);
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) zf[c * 16 + (b ^ c)] = v[c];
+            for (int c = 0; c < 16; ++c) zf[c * ZROW + b] = v[c];
             __syncwarp();
 #pragma unroll
-            for (int bb = 0; bb < 16; ++bb) v[bb] = zf[b * 16 + (bb ^ b)];   // lane c = b reads (c, bb)
+            for (int bb = 0; bb < 16; ++bb) v[bb] = zf[b * ZROW + bb];       // lane c = b reads (c, bb)
             dft16(v);                                               // over b: Z[c + 16 d] = v[d]
             // ---- real-FFT split + power: bins k = c + 16 d (d < 8) and 256 - k from the pair (Z_k, Z_{256-k});
             //      Z_{256-k} is register 15 - d of lane 16 - c (register 16 - d of lane 0 itself for c = 0)
