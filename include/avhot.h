@@ -424,7 +424,7 @@ int avhot_mc_reduce(const float* logits, float* mean_logits, float* uncertainty,
 int avhot_flag_near_ties(const float* mean_logits, int B, int C, float margin, uint32_t tag,
                          uint64_t clip0, uint32_t* state, uint32_t* entry_tag, uint32_t* entry_row,
                          uint32_t* entry_clip, int capacity, avhot_stream_t stream);
-/* rows entry_row[e] of src (B rows of row_bytes bytes, a multiple of 16) -> pool row e, for the entries the latest
+/* rows entry_row[e] of src (B rows of row_bytes bytes, a multiple of 4) -> pool row e, for the entries the latest
  * avhot_flag_near_ties call appended: the inputs of the pending clips, kept for their fp32 re-evaluation */
 int avhot_gather_flagged(const void* src, size_t row_bytes, int B, const uint32_t* state,
                          const uint32_t* entry_row, void* pool, int capacity, avhot_stream_t stream);

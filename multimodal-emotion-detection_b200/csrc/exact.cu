@@ -42,13 +42,15 @@ __global__ void near_tie_flag_kernel(const float* __restrict__ mean_logits, int 
 
 __global__ void near_tie_begin_kernel(uint32_t* __restrict__ state) { state[2] = state[0]; }
 
-// CTA i copies the row of the i-th entry appended by the latest flag call (16-byte words; rows are 16-byte multiples)
-__global__ void gather_flagged_kernel(const uint4* __restrict__ src, size_t row_words, const uint32_t* __restrict__ state,
-                                      const uint32_t* __restrict__ entry_row, uint4* __restrict__ pool, int capacity) {
+// CTA i copies the row of the i-th entry appended by the latest flag call, in words of W bytes (uint4 when rows and
+// bases are 16-byte multiples, else 32-bit words: the (B, 2) modality mask has 8-byte rows)
+template <typename W>
+__global__ void gather_flagged_kernel(const W* __restrict__ src, size_t row_words, const uint32_t* __restrict__ state,
+                                      const uint32_t* __restrict__ entry_row, W* __restrict__ pool, int capacity) {
   const uint32_t first = state[2], last = min(state[0], (uint32_t)capacity);
   for (uint32_t e = first + blockIdx.x; e < last; e += gridDim.x) {
-    const uint4* s = src + (size_t)entry_row[e] * row_words;
-    uint4* d = pool + (size_t)e * row_words;
+    const W* s = src + (size_t)entry_row[e] * row_words;
+    W* d = pool + (size_t)e * row_words;
     for (size_t i = threadIdx.x; i < row_words; i += blockDim.x) d[i] = __ldg(s + i);
   }
 }
@@ -96,15 +98,20 @@ extern "C" int avhot_gather_flagged(const void* src, size_t row_bytes, int B, co
                                     const uint32_t* entry_row, void* pool, int capacity, avhot_stream_t stream) {
   AVHOT_REQUIRE(src && state && entry_row && pool && B >= 0 && capacity >= 1, AVHOT_ERR_INVALID,
                 "gather_flagged: bad arguments");
-  AVHOT_REQUIRE(row_bytes > 0 && (row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(pool) & 15) == 0,
-                AVHOT_ERR_INVALID, "gather_flagged: rows must be 16-byte multiples, 16-byte aligned");
+  AVHOT_REQUIRE(row_bytes > 0 && (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(pool) & 3) == 0,
+                AVHOT_ERR_INVALID, "gather_flagged: rows must be 4-byte multiples, 4-byte aligned");
   if (B == 0) return AVHOT_OK;
   cudaStream_t s = as_stream(stream);
   ProfScope prof("near_tie_gather", s);
   // a flag call appends at most B entries; a few hundred CTAs walk them (most calls flag a fraction of a percent)
-  gather_flagged_kernel<<<min(min(B, capacity), 4 * num_sms()), 256, 0, s>>>(
-      reinterpret_cast<const uint4*>(src), row_bytes / 16, state, entry_row, reinterpret_cast<uint4*>(pool), capacity);
+  const int grid = min(min(B, capacity), 4 * num_sms());
+  if ((row_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(pool) & 15) == 0)
+    gather_flagged_kernel<uint4><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), row_bytes / 16, state, entry_row,
+                                                     reinterpret_cast<uint4*>(pool), capacity);
+  else
+    gather_flagged_kernel<uint32_t><<<grid, 32, 0, s>>>(reinterpret_cast<const uint32_t*>(src), row_bytes / 4, state,
+                                                       entry_row, reinterpret_cast<uint32_t*>(pool), capacity);
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }

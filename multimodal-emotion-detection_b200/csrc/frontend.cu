@@ -2,26 +2,11 @@
 // implementation of this stage).
 //
 //   wave (B, N) fp32 -> feats (B, 1 + N/160, 104) fp32 = [64 log-mel | 40 MFCC]
+//   and / or the tensor-core LSTM's first GEMM operand (fp16 hi / lo split, time-major; avhot_frontend_ex)
 //
-// One CTA walks the tiles of FPB = 16 consecutive frames of one clip.  The pre-emphasised, reflect-padded samples
-// the frames share are staged once in shared memory with coalesced loads (frames overlap 3.2x, so HBM is read
-// once).  Per tile:
-//   FFT phase   one warp = one frame at a time: window + pack 512 reals as 256 complex -> in-place Stockham FFT-256
-//               in shared memory, radix 8 x 8 x 4 (last pass stays in registers) -> real-FFT split + |X|^2 with the
-//               mirrored bin fetched by warp shuffle -> power spectrum row of the tile (16 x 256, pitch 260);
-//   mel phase   the 64 x 257 filterbank as tensor-core tiles: warp j = filters 8j .. 8j+7 for all 16 frames,
-//               mma.sync m16n8k8 TF32 over the 8-bin steps its filters actually cover (41 steps in all instead of
-//               the 264 of a dense projection); the power spectrum is split hi + lo (two MMAs per step, exact to
-//               fp32), the weights are TF32-rounded once on the host (<= 2^-11 relative on a filter tap, i.e.
-//               <= 0.002 dB on a log-mel value); B fragments are stored in lane order (one 64-bit load per step);
-//               10 log10 in the accumulator registers -> output tile;
-//   DCT phase   40 x 64 orthonormal DCT-II, also mma.sync TF32 tiles, folded by the symmetry D[c][63-j] = (-1)^c D[c][j]
-//               (even coefficients see lm[j] + lm[63-j], odd ones lm[j] - lm[63-j]: K = 32) and error-compensated
-//               (operands split hi + lo, three MMAs per step: fp32-class, the log-mel values are ~100 dB);
-//               warp (parity, 8-coefficient tile) = six warps -> output tile;
-//   store       coalesced 128-bit stores of the fp32 features and / or the LSTM's fp16 split operand.
-// (The sparse per-lane filter walk this replaces cost ~130 of the ~480 shared-memory wavefronts per frame of a
-// kernel that ncu shows bound by shared-memory bandwidth: l1tex 88 %, r1y.)
+// One persistent kernel (frontend_tc_kernel, below): framing, pre-emphasis and windowing from shared memory, a
+// shared-memory radix-16 x 16 STFT with a warp-shuffle real-FFT split / power spectrum on the CUDA cores, the mel
+// filterbank projection and the MFCC DCT as tcgen05 / TMEM tiles, log and scaling in the epilogues, TMA stores.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,30 +22,12 @@
 namespace avhot {
 
 constexpr int N_FFT = 512, HOP = 160, N_BINS = 257, N_MELS = 64, N_MFCC = 40, N_FEATS = 104;
-constexpr int FPB = 16;            // frames per CTA
-constexpr int FE_WARPS = 8;        // warps per CTA
-constexpr int SEG = (FPB - 1) * HOP + N_FFT;  // samples a CTA stages: 2912
-constexpr int ZPAD = 256;          // complex FFT scratch, XOR-swizzled (zpad below)
-constexpr int MEL_KS_MAX = 44;     // 8-bin steps summed over the eight 8-filter tiles (41 for the Slaney bank used here)
-constexpr int POW_LD = 260;        // pitch of a power-spectrum row: 256 bins + 4 (conflict-free A-fragment loads)
-constexpr int OUT_LD = 108;        // pitch of an output-tile row (conflict-free A-fragment loads of the log-mel part)
-constexpr int DCT_TILES = 6;       // (parity, 8-coefficient tile): coefficient c = 2 (8 tile + n) + parity, n = 0..7
 
-struct FrontendTables {            // device layout, all fp32 unless noted
+struct FrontendTables {            // device layout
   float window[N_FFT];
   float2 tw[N_FFT];                // tw[k] = exp(-2 pi i k / 512)
-  float2 tw2[64];                  // tw2[r * 8 + k]  = exp(-2 pi i r k / 64)   (pass 2; lanes read consecutive entries)
-  float2 tw3[256];                 // tw3[r * 64 + j] = exp(-2 pi i r j / 256)  (pass 3)
-  float2 mel_b[MEL_KS_MAX * 32];   // B fragments of mma.m16n8k8 in lane order, TF32-rounded: step i, lane l ->
-                                   //   (W[8j + (l >> 2)][8k + (l & 3)], W[8j + (l >> 2)][8k + (l & 3) + 4])
-  int mel_k0[8];                   // first 8-bin step of filter tile j
-  int mel_nk[8];                   // number of steps
-  int mel_off[8];                  // index of the tile's first step in mel_b
-  float4 dct_b[DCT_TILES * 4 * 32];  // B fragments of the folded DCT in lane order, (hi0, hi1, lo0, lo1) per lane:
-                                     //   tile (p, nt) = 3 p + nt, step ks, lane l -> D[c][8 ks + (l & 3) (+ 4)],
-                                     //   c = 2 (8 nt + (l >> 2)) + p (zero rows for c >= 40)
-  // tcgen05 operands (frontend_tc_kernel), fp16 bit patterns already in the K-major 128-byte-swizzled shared-memory
-  // layout ([k-block of 64][row][16-byte chunk ^ (row & 7)]), copied to shared memory as they are:
+  // tcgen05 operands, fp16 bit patterns already in the K-major 128-byte-swizzled shared-memory layout
+  // ([k-block of 64][row][16-byte chunk ^ (row & 7)]), copied to shared memory as they are:
   uint16_t b3lo[32 * 64];            //   mel weights x 64 (= 0.25 for the 4 |X|^2 of the kernel x 256 to keep small taps
   uint16_t b3hi[4 * 32 * 64];        //   normal in fp16), banded: filters 0-31 over bins 0-63 (they reach no further),
                                      //   filters 32-63 over bins 0-255; row = filter
@@ -92,10 +59,6 @@ static void build_tables() {
     t.window[n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / N_FFT));
     t.tw[n] = make_float2((float)cos(2.0 * PI * n / N_FFT), (float)(-sin(2.0 * PI * n / N_FFT)));
   }
-  for (int r = 0; r < 8; ++r)
-    for (int k = 0; k < 8; ++k) t.tw2[r * 8 + k] = t.tw[(r * k * 8) % N_FFT];
-  for (int r = 0; r < 4; ++r)
-    for (int j = 0; j < 64; ++j) t.tw3[r * 64 + j] = t.tw[(r * j * 2) % N_FFT];
   // Slaney mel filterbank, Slaney area normalisation, 0..8000 Hz (oracle/frontend.py mel_filterbank)
   const double sr = 16000.0, f_lo = 0.0, f_hi = 8000.0;
   std::vector<double> hz(N_MELS + 2);
@@ -112,38 +75,9 @@ static void build_tables() {
       if (w > 0.0) g_host_mel_dense[m * N_BINS + k] = (float)(w * enorm);
     }
   }
-  // tensor-core layout: per 8-filter tile, the 8-bin steps its filters cover.  The Nyquist bin carries no weight
-  // (the last filter ends there), so the kernel keeps bins 0..255 only.
+  // The Nyquist bin carries no weight (the last filter ends there), so the kernel keeps bins 0..255 only.
   g_tables_ok = true;
   for (int m = 0; m < N_MELS; ++m) if (g_host_mel_dense[m * N_BINS + (N_BINS - 1)] != 0.f) g_tables_ok = false;
-  auto tf32_round = [](float v) {
-    uint32_t u;
-    memcpy(&u, &v, 4);
-    u += 0xFFFu + ((u >> 13) & 1u);
-    u &= ~0x1FFFu;
-    memcpy(&v, &u, 4);
-    return v;
-  };
-  int off = 0;
-  for (int j = 0; j < 8; ++j) {
-    int lo = N_BINS, hi = -1;
-    for (int m = 8 * j; m < 8 * j + 8; ++m)
-      for (int k = 0; k < N_BINS - 1; ++k)
-        if (g_host_mel_dense[m * N_BINS + k] != 0.f) { lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
-    if (hi < 0) { lo = 0; hi = 0; }
-    t.mel_k0[j] = lo / 8;
-    t.mel_nk[j] = hi / 8 - lo / 8 + 1;
-    t.mel_off[j] = off;
-    for (int ks = 0; ks < t.mel_nk[j]; ++ks, ++off) {
-      if (off >= MEL_KS_MAX) { g_tables_ok = false; continue; }
-      for (int l = 0; l < 32; ++l) {
-        const int m = 8 * j + (l >> 2), k = 8 * (t.mel_k0[j] + ks) + (l & 3);
-        // x 0.25: the kernel's power spectrum is 4 |X|^2 (it skips the two halvings of the real-FFT split)
-        t.mel_b[off * 32 + l] = make_float2(0.25f * tf32_round(g_host_mel_dense[m * N_BINS + k]),
-                                            0.25f * tf32_round(g_host_mel_dense[m * N_BINS + k + 4]));
-      }
-    }
-  }
   g_host_dct.assign(N_MFCC * N_MELS, 0.f);
   for (int c = 0; c < N_MFCC; ++c)
     for (int j = 0; j < N_MELS; ++j) {
@@ -181,16 +115,6 @@ static void build_tables() {
       t.b4[pos] = hi;
       t.b4[48 * 64 + pos] = f16_bits(d - __half2float(hh));
     }
-  for (int p = 0; p < 2; ++p)
-    for (int nt = 0; nt < 3; ++nt)
-      for (int ks = 0; ks < 4; ++ks)
-        for (int l = 0; l < 32; ++l) {
-          const int c = 2 * (8 * nt + (l >> 2)) + p, j = 8 * ks + (l & 3);
-          const float d0 = c < N_MFCC ? g_host_dct[c * N_MELS + j] : 0.f;
-          const float d1 = c < N_MFCC ? g_host_dct[c * N_MELS + j + 4] : 0.f;
-          const float h0 = tf32_round(d0), h1 = tf32_round(d1);
-          t.dct_b[((3 * p + nt) * 4 + ks) * 32 + l] = make_float4(h0, h1, tf32_round(d0 - h0), tf32_round(d1 - h1));
-        }
 }
 
 constexpr int MAX_DEVICES = 64;
@@ -230,346 +154,6 @@ __device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2&
   v2 = csub(a0, a2);
   v3 = csub(a1, a3);
 }
-// DFT-8, natural order in and out
-__device__ __forceinline__ void dft8(float2* v) {
-  dft4(v[0], v[2], v[4], v[6]);  // E[0..3] in v0 v2 v4 v6
-  dft4(v[1], v[3], v[5], v[7]);  // O[0..3] in v1 v3 v5 v7
-  const float r = 0.70710678118654752440f;
-  const float2 o0 = v[1];
-  const float2 o1 = make_float2(r * (v[3].x + v[3].y), r * (v[3].y - v[3].x));   // * (1-i)/sqrt2
-  const float2 o2 = mul_mi(v[5]);
-  const float2 o3 = make_float2(r * (v[7].y - v[7].x), -r * (v[7].x + v[7].y));  // * (-1-i)/sqrt2
-  const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
-  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
-  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
-  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
-  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
-}
-// index i -> i ^ ((i >> 3) & 15): every access pattern of the three passes (stores of lane * 8 + r and
-// 64 q + k + 8 r, loads of lane + 32 r and lane + 32 jj + 64 r) then hits 16 distinct 8-byte bank pairs per half-warp
-// (the previous i + (i >> 4) padding left a 2-way conflict on the pass-2 stores)
-__device__ __forceinline__ int zpad(int i) { return i ^ ((i >> 3) & 15); }
-
-struct FeSmem {
-  float seg[SEG];
-  float win[N_FFT];
-  float2 tw[N_FFT / 2];
-  float2 tw2[64], tw3[256];
-  float2 melb[MEL_KS_MAX * 32];
-  int mel_k0[8], mel_nk[8], mel_off[8];
-  float4 dctb[DCT_TILES * 4 * 32];
-  union {                              // FFT scratch during the FFT phase, output tile afterwards
-    float2 z[FE_WARPS][ZPAD];
-    float out[FPB][OUT_LD];
-  } u;
-  float pow[FPB][POW_LD];
-};
-static_assert(sizeof(FeSmem) <= 75 * 1024, "three CTAs per SM");
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-// D (16 x 8, fp32) += A (16 x 8, tf32, row) * B (8 x 8, tf32, col); fragment layouts per the PTX ISA:
-// g = lane >> 2, t = lane & 3: a = {A[g][t], A[g+8][t], A[g][t+4], A[g+8][t+4]}, b = {B[t][g], B[t+4][g]},
-// d = {D[g][2t], D[g][2t+1], D[g+8][2t], D[g+8][2t+1]}
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__global__ void __launch_bounds__(FE_WARPS * 32, 3)
-frontend_kernel(const float* __restrict__ wave, float* __restrict__ feats, __half* __restrict__ xs, int Bp, int ldx,
-                int n_samples, int n_frames, int tiles_per_cta, const FrontendTables* __restrict__ tab,
-                long long* __restrict__ trace = nullptr) {
-  extern __shared__ __align__(16) unsigned char fe_smem_raw[];
-  FeSmem& sm = *reinterpret_cast<FeSmem*>(fe_smem_raw);
-  float* s_seg = sm.seg;
-  float* s_win = sm.win;
-  float2* s_tw = sm.tw;
-  float2 (*s_z)[ZPAD] = sm.u.z;
-  float (*s_pow)[POW_LD] = sm.pow;
-  float (*s_out)[OUT_LD] = sm.u.out;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int clip = blockIdx.y;
-  const float* y = wave + (size_t)clip * n_samples;
-
-  // tables -> smem
-  for (int i = tid; i < N_FFT; i += blockDim.x) s_win[i] = tab->window[i];
-  for (int i = tid; i < N_FFT / 2; i += blockDim.x) s_tw[i] = tab->tw[i];
-  for (int i = tid; i < 64; i += blockDim.x) sm.tw2[i] = tab->tw2[i];
-  for (int i = tid; i < 256; i += blockDim.x) sm.tw3[i] = tab->tw3[i];
-  for (int i = tid; i < MEL_KS_MAX * 32; i += blockDim.x) sm.melb[i] = tab->mel_b[i];
-  if (tid < 8) { sm.mel_k0[tid] = tab->mel_k0[tid]; sm.mel_nk[tid] = tab->mel_nk[tid]; sm.mel_off[tid] = tab->mel_off[tid]; }
-  for (int i = tid; i < DCT_TILES * 4 * 32; i += blockDim.x) sm.dctb[i] = tab->dct_b[i];
-
-  // The tables are loaded once; the CTA then walks its tiles of FPB frames.  The raw samples of the NEXT tile are
-  // fetched into registers before the frame loop of the current one, so their HBM latency hides behind the FFTs
-  // (ncu: a quarter of all stall samples sat on the pre-emphasis FMA waiting for these loads).
-  constexpr int SPT = (SEG + FE_WARPS * 32 - 1) / (FE_WARPS * 32);   // samples per thread
-  constexpr int QPT = (SEG / 4 + FE_WARPS * 32 - 1) / (FE_WARPS * 32);   // float4 groups per thread (SEG % 4 == 0)
-  static_assert(SEG % 4 == 0 && QPT * 4 <= SPT, "segment staged in float4 groups");
-  float cur[SPT], prv[SPT];
-  bool vec_tile = false;   // how the registers were filled (block-uniform)
-  // Interior tiles (no reflection, 16-byte aligned): one 128-bit load per four samples plus the one sample before the
-  // group - 6 loads per thread instead of 24, no reflection arithmetic.  cur[4 j + k] = sample 4 (tid + 256 j) + k.
-  const bool can_vec = (n_samples & 3) == 0 && (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
-  auto fetch = [&](int tile_t0) {
-    const int q0 = tile_t0 * HOP;
-    const int base = q0 - N_FFT / 2;
-    vec_tile = can_vec && base >= 4 && base + SEG <= n_samples;
-    if (vec_tile) {
-#pragma unroll
-      for (int j = 0; j < QPT; ++j) {
-        const int i4 = tid + j * (FE_WARPS * 32);
-        if (i4 < SEG / 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(y + base) + i4);
-          cur[4 * j] = v.x; cur[4 * j + 1] = v.y; cur[4 * j + 2] = v.z; cur[4 * j + 3] = v.w;
-          prv[4 * j] = __ldg(y + base + 4 * i4 - 1);
-        }
-      }
-      return;
-    }
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      const int i = tid + j * (FE_WARPS * 32);
-      int n = q0 + i - N_FFT / 2;                       // reflect padding (numpy "reflect": no edge repeat)
-      if (n < 0) n = -n;
-      if (n >= n_samples) n = 2 * (n_samples - 1) - n;
-      const bool ok = i < SEG && n >= 0 && n < n_samples;
-      cur[j] = ok ? __ldg(y + n) : 0.f;
-      prv[j] = ok && n > 0 ? __ldg(y + n - 1) : 0.f;
-    }
-  };
-  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = (blockIdx.x + 1) * tiles_per_cta;
-  // pre-emphasised, reflect-padded segment of a tile: q[i] = p[reflect(i - 256)], p[n] = y[n] - 0.97 y[n-1]
-  auto stage_segment = [&]() {
-    if (vec_tile) {
-#pragma unroll
-      for (int j = 0; j < QPT; ++j) {
-        const int i4 = tid + j * (FE_WARPS * 32);
-        if (i4 < SEG / 4)
-          *reinterpret_cast<float4*>(s_seg + 4 * i4) =
-              make_float4(fmaf(-0.97f, prv[4 * j], cur[4 * j]), fmaf(-0.97f, cur[4 * j], cur[4 * j + 1]),
-                          fmaf(-0.97f, cur[4 * j + 1], cur[4 * j + 2]), fmaf(-0.97f, cur[4 * j + 2], cur[4 * j + 3]));
-      }
-      return;
-    }
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      const int i = tid + j * (FE_WARPS * 32);
-      if (i < SEG) s_seg[i] = fmaf(-0.97f, prv[j], cur[j]);
-    }
-  };
-  if (tile_begin * FPB < n_frames) {
-    fetch(tile_begin * FPB);
-    stage_segment();
-  }
-  __syncthreads();
-  // debug (AVHOT_FE_TRACE=<file>): thread 0 of CTA (0, 0) stamps clock64() at the phase boundaries of its sixth tile
-  int ev = 0;
-  auto TR = [&](int tile) { if (trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && tile == tile_begin + 5 && ev < 16) trace[ev++] = clock64(); };
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
-  const int t0 = tile * FPB;
-  if (t0 >= n_frames) break;
-  // the next tile's samples travel to registers during this tile's FFTs and are staged right after them (the segment
-  // buffer is free once the FFT phase is over), so a tile costs four block barriers, not five
-  const bool have_next = tile + 1 < tile_end && (tile + 1) * FPB < n_frames;
-  TR(tile);                            // 0: tile start
-  if (have_next) fetch((tile + 1) * FPB);
-  TR(tile);                            // 1: next tile's loads issued
-
-  float2* z = s_z[warp];
-  for (int f = warp; f < FPB; f += FE_WARPS) {
-    const int t = t0 + f;
-    if (t >= n_frames) break;            // warp-uniform
-    const float2* x2 = reinterpret_cast<const float2*>(s_seg + f * HOP);
-    const float2* w2 = reinterpret_cast<const float2*>(s_win);
-    float2 v[8];
-    // ---- pass 1: radix 8, Ns = 1 (no twiddles); input straight from the windowed samples
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float2 s = x2[lane + 32 * r], w = w2[lane + 32 * r];
-      v[r] = make_float2(s.x * w.x, s.y * w.y);
-    }
-    dft8(v);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; ++r) z[zpad(lane * 8 + r)] = v[r];
-    __syncwarp();
-    // ---- pass 2: radix 8, Ns = 8
-    {
-      const int k = lane & 7;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float2 a = z[zpad(lane + 32 * r)];
-        v[r] = r == 0 ? a : cmul(a, sm.tw2[r * 8 + k]);   // exp(-2 pi i r k / 64), bank-conflict-free layout
-      }
-      dft8(v);
-      __syncwarp();
-      const int j0 = (lane - k) * 8 + k;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) z[zpad(j0 + 8 * r)] = v[r];
-      __syncwarp();
-    }
-    // ---- pass 3: radix 4, Ns = 64, two butterflies per lane; results stay in registers:
-    //      Z[lane + 32 m] = v[m],  m = 2 r + jj
-    {
-      float2 u[2][4];
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = lane + 32 * jj;    // 0..63 = k
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float2 a = z[zpad(j + 64 * r)];
-          u[jj][r] = r == 0 ? a : cmul(a, sm.tw3[r * 64 + j]);   // exp(-2 pi i r j / 256)
-        }
-        dft4(u[jj][0], u[jj][1], u[jj][2], u[jj][3]);
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r) { v[2 * r] = u[0][r]; v[2 * r + 1] = u[1][r]; }
-    }
-    // ---- real-FFT split + power, two bins per butterfly: bin k = lane + 32 m (m < 4) and its mirror 256 - k come from
-    //      the same pair (Z_k, Z_{256-k}): with Zc = conj(Z_{256-k}), E = Z_k + Zc, T = w^k (Z_k - Zc) / i,
-    //      2 X_k = E + T and 2 X_{256-k} = conj(E - T).  Z_{256-k} is register 7 - m of lane 32 - lane (register 8 - m
-    //      of lane 0 itself for lane 0, whose m = 0 "mirror" is the unused Nyquist bin, written into the row's pad).
-    float* pw = s_pow[f];
-    const int src = (32 - lane) & 31;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const float2 a = v[7 - m], b = v[(8 - m) & 7];
-      const float mx_a = __shfl_sync(0xffffffffu, a.x, src), my_a = __shfl_sync(0xffffffffu, a.y, src);
-      const float2 zc = lane == 0 ? make_float2(b.x, -b.y) : make_float2(mx_a, -my_a);  // conj(Z[256-k])
-      const float2 zk = v[m];
-      const int k = lane + 32 * m;
-      // the factor 4 on |X|^2 lives in the mel weights (x 0.25, exact)
-      const float2 xe = cadd(zk, zc);
-      const float2 T = cmul(s_tw[k], mul_mi(csub(zk, zc)));
-      const float2 Xa = cadd(xe, T), Xb = csub(xe, T);
-      pw[k] = Xa.x * Xa.x + Xa.y * Xa.y;
-      pw[256 - k] = Xb.x * Xb.x + Xb.y * Xb.y;
-    }
-    if (lane == 0) pw[128] = 4.f * (v[4].x * v[4].x + v[4].y * v[4].y);   // Z_128 is its own mirror, w^128 = -i
-    // (bin 256 carries no filter weight - checked when the tables are built - and is not formed)
-    __syncwarp();
-  }
-  TR(tile);                            // 2: this thread's FFTs done
-  __syncthreads();                   // power spectra of the tile complete; the FFT scratch and the segment are free
-  TR(tile);                            // 3: every warp's FFTs done
-  if (have_next) stage_segment();
-  TR(tile);                            // 4: next segment staged
-  // ---- mel filterbank on the tensor cores + log: warp j = filters 8j .. 8j+7 of all 16 frames
-  {
-    const int g = lane >> 2, t4 = lane & 3;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int nk = sm.mel_nk[warp];
-    const float2* bt = sm.melb + sm.mel_off[warp] * 32 + lane;
-    const float* pa = &s_pow[g][8 * sm.mel_k0[warp] + t4];
-    for (int ks = 0; ks < nk; ++ks) {
-      const float x[4] = {pa[0], pa[8 * POW_LD], pa[4], pa[8 * POW_LD + 4]};
-      uint32_t ah[4], al[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        ah[e] = to_tf32(x[e]);
-        al[e] = to_tf32(x[e] - __uint_as_float(ah[e]));
-      }
-      const float2 b = bt[ks * 32];
-      mma_tf32_16x8x8(acc, ah, __float_as_uint(b.x), __float_as_uint(b.y));
-      mma_tf32_16x8x8(acc, al, __float_as_uint(b.x), __float_as_uint(b.y));
-      pa += 8;
-    }
-    float lm[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) lm[e] = 3.01029995663981195f * log2f(fmaxf(acc[e], 1e-10f));   // 10 log10(.)
-    *reinterpret_cast<float2*>(&s_out[g][8 * warp + 2 * t4]) = make_float2(lm[0], lm[1]);
-    *reinterpret_cast<float2*>(&s_out[g + 8][8 * warp + 2 * t4]) = make_float2(lm[2], lm[3]);
-  }
-  TR(tile);                            // 5: this warp's mel tile done
-  __syncthreads();                   // log-mel rows of the tile complete
-  TR(tile);                            // 6
-  // ---- DCT-II (orthonormal), first 40 coefficients, folded and error-compensated on the tensor cores:
-  //      warp = (parity p, tile nt): coefficients c = 2 (8 nt + n) + p over u[j] = lm[j] + (-1)^p lm[63 - j], j < 32
-  if (warp < DCT_TILES) {
-    const int p = warp & 1, nt = warp >> 1;
-    const int g = lane >> 2, t4 = lane & 3;
-    const float sgn = p ? -1.f : 1.f;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* r0 = &s_out[g][0];
-    const float* r1 = &s_out[g + 8][0];
-    const float4* bt = sm.dctb + (3 * p + nt) * 4 * 32 + lane;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int j = 8 * ks + t4;
-      const float x[4] = {fmaf(sgn, r0[63 - j], r0[j]), fmaf(sgn, r1[63 - j], r1[j]),
-                          fmaf(sgn, r0[59 - j], r0[j + 4]), fmaf(sgn, r1[59 - j], r1[j + 4])};
-      uint32_t ah[4], al[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        ah[e] = to_tf32(x[e]);
-        al[e] = to_tf32(x[e] - __uint_as_float(ah[e]));
-      }
-      const float4 b = bt[ks * 32];
-      mma_tf32_16x8x8(acc, ah, __float_as_uint(b.x), __float_as_uint(b.y));
-      mma_tf32_16x8x8(acc, al, __float_as_uint(b.x), __float_as_uint(b.y));
-      mma_tf32_16x8x8(acc, ah, __float_as_uint(b.z), __float_as_uint(b.w));
-    }
-    const int ca = 2 * (8 * nt + 2 * t4) + p, cb = ca + 2;
-    if (ca < N_MFCC) { s_out[g][N_MELS + ca] = acc[0]; s_out[g + 8][N_MELS + ca] = acc[2]; }
-    if (cb < N_MFCC) { s_out[g][N_MELS + cb] = acc[1]; s_out[g + 8][N_MELS + cb] = acc[3]; }
-  }
-  TR(tile);                            // 7: this warp's DCT tile done
-  __syncthreads();
-  TR(tile);                            // 8
-  // coalesced store of the CTA's output tile (rows are contiguous in feats)
-  const int rows = min(FPB, n_frames - t0);
-  if (feats) {
-    float4* dst = reinterpret_cast<float4*>(feats + ((size_t)clip * n_frames + t0) * N_FEATS);
-    for (int i = tid; i < rows * (N_FEATS / 4); i += blockDim.x)
-      dst[i] = *reinterpret_cast<const float4*>(&s_out[i / (N_FEATS / 4)][4 * (i % (N_FEATS / 4))]);
-  }
-  if (xs) {
-    // fused operand preparation for the tensor-core LSTM (lstm.cu): time-major rows (t, clip) of
-    // [hi(104) | lo(104) | hi(104) | 1, 1 | 0...] in fp16, hi = fp16(x), lo = fp16(x - hi)
-    // thread = (row, 8-feature chunk): 13 chunks per row convert 8 features and store them three times with 128-bit
-    // stores (hi at [8c], lo at [104 + 8c], hi at [208 + 8c]); a 14th thread per row writes the (1, 1, 0...) tail
-    for (int i = tid; i < rows * 14; i += blockDim.x) {
-      const int f = i / 14, c = i % 14;
-      __half* row = xs + ((size_t)(t0 + f) * Bp + clip) * ldx;
-      if (c < 13) {
-        const float4 x0 = *reinterpret_cast<const float4*>(&s_out[f][8 * c]);
-        const float4 x1 = *reinterpret_cast<const float4*>(&s_out[f][8 * c + 4]);
-        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
-          const float2 hf = __half22float2(h);
-          const __half2 l = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
-          hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-          lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-        }
-        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(row + 8 * c) = vh;
-        *reinterpret_cast<uint4*>(row + N_FEATS + 8 * c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(row + 2 * N_FEATS + 8 * c) = vh;
-      } else {
-        for (int k8 = 3 * N_FEATS; k8 < ldx; k8 += 8)
-          *reinterpret_cast<uint4*>(row + k8) = make_uint4(k8 == 3 * N_FEATS ? 0x3C003C00u : 0u, 0u, 0u, 0u);
-      }
-    }
-  }
-  TR(tile);                            // 9: this thread's stores issued
-  __syncthreads();   // s_seg / s_out are rewritten by the next tile
-  TR(tile);                            // 10: tile end
-  }
-}
-
-
 // =====================================================================================================================
 // frontend_tc_kernel: the front-end with the two dense contractions on the tcgen05 tensor cores.
 //
@@ -1032,8 +616,7 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
     AVHOT_CUDA(cudaMemset2DAsync(reinterpret_cast<__half*>(xs) + (size_t)B * ldx, (size_t)Bp * ldx * sizeof(__half), 0,
                                  (size_t)(Bp - B) * ldx * sizeof(__half), (size_t)n_frames, s));
   }
-  static const bool legacy = [] { const char* e = getenv("AVHOT_FE_LEGACY"); return e && atoi(e) != 0; }();
-  if (!legacy) {
+  {
     // tensor map of the operand (3-D, so a 128-frame box that runs past the clip's last frame is clipped):
     // (n_frames, Bp, ldx) fp16 as (col, clip, t)
     CUtensorMap tmX;
@@ -1054,20 +637,6 @@ static int frontend_launch(const float* wave, float* feats, void* xs, int Bp, in
     AVHOT_LAUNCH_CHECK();
     return AVHOT_OK;
   }
-  // many clips: one CTA per clip walks all its tiles (tables staged once per clip); few clips: one tile per CTA
-  const int n_tiles = ceil_div(n_frames, FPB);
-  const int tiles_per_cta = (long long)B * 1 >= 2LL * num_sms() ? n_tiles : 1;
-  dim3 grid(ceil_div(n_tiles, tiles_per_cta), B);
-  // > 48 KB of dynamic shared memory needs the opt-in (per device, cheap to repeat)
-  AVHOT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(FeSmem)));
-  {
-    ProfScope prof("frontend", s);
-    frontend_kernel<<<grid, FE_WARPS * 32, sizeof(FeSmem), s>>>(wave, feats, reinterpret_cast<__half*>(xs), Bp, ldx,
-                                                                n_samples, n_frames, tiles_per_cta, tab, nullptr);
-    AVHOT_LAUNCH_CHECK();
-  }
-  return AVHOT_OK;
 }
 
 extern "C" int avhot_frontend(const float* wave, float* feats, int B, int n_samples, avhot_stream_t stream) {

@@ -48,10 +48,10 @@ def logit_scale(model) -> float:
         lin, gain = model.fusion_head[2], None
     else:
         raise ValueError("NearTieResolver: hybrid / concat heads only")
-    w = lin.weight.detach().float()
+    w = lin.weight.detach().float().cpu().numpy().astype("float64")     # a scalar of the model, derived on the host
     if gain is not None:
-        w = w * gain.detach().float()
-    return float(w.pow(2).sum(dim=1).sqrt().max().item() * (w.shape[1] ** 0.5))
+        w = w * gain.detach().float().cpu().numpy().astype("float64")
+    return float((w ** 2).sum(axis=1).max() ** 0.5 * w.shape[1] ** 0.5)
 
 
 class NearTieResolver:
@@ -109,13 +109,13 @@ class NearTieResolver:
         for k, v in rows.items():
             if not v.is_contiguous():
                 rows[k] = v.contiguous()
-            if (rows[k][0].numel() * rows[k].element_size()) % 16 != 0:
-                raise ValueError(f"features['{k}']: rows must be a multiple of 16 bytes")
+            if (rows[k][0].numel() * rows[k].element_size()) % 4 != 0:
+                raise ValueError(f"features['{k}']: rows must be a multiple of 4 bytes")
         if mask is not None:
-            # (B, 2) fp32 rows are 8 bytes: widen to 16-byte rows for the gather
-            m4 = torch.zeros(B, 4, device=dev, dtype=torch.float32)
-            m4[:, :2] = torch.as_tensor(mask).to(device=dev, dtype=torch.float32)
-            rows["mask"] = m4
+            m = torch.as_tensor(mask)
+            if m.device != dev or m.dtype != torch.float32 or not m.is_contiguous():
+                m = m.to(device=dev, dtype=torch.float32).contiguous()
+            rows["mask"] = m
         self._ensure(dev, rows)
         self._params = (int(num_samples), int(seed))
         tag = self._next_tag
@@ -161,7 +161,7 @@ class NearTieResolver:
         has_mask = calls[0][5]
         if any(c[5] != has_mask for c in calls):
             raise RuntimeError("NearTieResolver: calls with and without a modality mask in one window")
-        mask = self._pool["mask"][:n, :2].contiguous() if has_mask else None
+        mask = self._pool["mask"][:n] if has_mask else None
         prev = model.precision
         model.set_precision("fp32")
         try:
