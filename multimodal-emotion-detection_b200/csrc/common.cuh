@@ -67,6 +67,14 @@ int gemm_f32(const float* a_f32, const uint8_t* a_u8, int lda, const float* w, i
 int gemm_tf32_tc(const float* a, int lda, const float* w, int ldw, const float* bias, float* c, int ldc, int M,
                  int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_tf32_tc");
 
+// gemm_u8.cu: C[M, 256] = act(A_u8[M, K] / 255 * W^T + bias) on tcgen05 with the pixels converted to fp16 in the kernel.
+// wq_f16 (256, K) / inv_scale_dev come from gemm_u8_pack_weights (scratch_dev: one uint32 of device scratch).
+int gemm_u8_pack_weights(const float* w, int N, int K, void* wq_f16, float* inv_scale_dev, uint32_t* scratch_dev,
+                         cudaStream_t s);
+bool gemm_u8_tc_supported(const uint8_t* a, int lda, int N, int K);
+int gemm_u8_tc(const uint8_t* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float* c,
+               int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_u8_tc");
+
 // lstm_tc.cu: W_hh (4H, H) fp32 -> fp16, rows regrouped per 32-unit chunk; and the tcgen05 recurrence of one layer.
 int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s);
 // h_seq_f16: (B, T, H) fp16 hidden sequence (input of the next layer's projection) or NULL

@@ -28,6 +28,8 @@ struct avhot_frame {
   float* proj_b;    // (out)
   float* arena;
   bool has_attention;
+  void* wq_f16;     // (H, frame_dim) fp16 = W s / 255 for the uint8 tensor-core GEMM (gemm_u8.cu), or NULL
+  float* wq_inv;    // 1 / s (device)
 };
 
 namespace avhot {
@@ -233,6 +235,9 @@ extern "C" int avhot_frame_create(const avhot_frame_desc* d, avhot_frame_t* out,
   const size_t sizes[8] = {(size_t)H * d->frame_dim, (size_t)H, (size_t)H, 1, (size_t)H, (size_t)H, (size_t)O * H, (size_t)O};
   size_t total = 0;
   for (size_t n : sizes) total += align256f(n * sizeof(float));
+  const bool u8_tc = (d->frame_dim % 128) == 0;           // uint8 frames straight onto the tensor cores (gemm_u8.cu)
+  const size_t wq_bytes = u8_tc ? align256f((size_t)H * d->frame_dim * 2) + 512 : 0;
+  total += wq_bytes;
   avhot_frame* h = new avhot_frame();
   h->frame_dim = d->frame_dim; h->hidden_dim = H; h->output_dim = O;
   h->arena = nullptr;
@@ -262,6 +267,14 @@ extern "C" int avhot_frame_create(const avhot_frame_desc* d, avhot_frame_t* out,
     }
   }
   if (rc == AVHOT_OK) rc = transpose(d->proj_weight, h->proj_wt, O, H, s);
+  h->wq_f16 = nullptr;
+  h->wq_inv = nullptr;
+  if (rc == AVHOT_OK && u8_tc) {
+    h->wq_f16 = p;
+    h->wq_inv = reinterpret_cast<float*>(p + align256f((size_t)H * d->frame_dim * 2));
+    rc = gemm_u8_pack_weights(d->mlp_weight, H, d->frame_dim, h->wq_f16, h->wq_inv,
+                              reinterpret_cast<uint32_t*>(h->wq_inv) + 64, s);
+  }
   if (rc != AVHOT_OK) {
     cudaFree(h->arena);
     delete h;
@@ -292,6 +305,9 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
   AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
                 "frame_hidden: precision %d not built", precision);
   AVHOT_REQUIRE((long long)B * F <= 0x7fffffff / 2, AVHOT_ERR_INVALID, "frame_hidden: B*F too large for one call");
+  if (precision == AVHOT_PREC_TC && frames_u8 && h->wq_f16 && gemm_u8_tc_supported(frames_u8, h->frame_dim, h->hidden_dim, h->frame_dim))
+    return gemm_u8_tc(frames_u8, h->frame_dim, h->wq_f16, h->mlp_b, h->wq_inv, hid, h->hidden_dim, B * F, h->hidden_dim,
+                      h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
   if (precision == AVHOT_PREC_TC && frames_u8 && (((size_t)B * F * h->frame_dim) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(frames_u8) & 15) == 0 && workspace &&
       workspace_bytes >= avhot_frame_workspace_bytes(h, B, F, precision)) {
