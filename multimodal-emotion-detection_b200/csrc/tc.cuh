@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // The same for waits that are expected to last (an epilogue warp waiting for a whole tile of producer work): sleep between
 // polls, so the waiting warps leave the issue slots to the working ones (the spinning form cost 14 % of all instructions
-// issued by frontend_tc_kernel, ncu r2g).
+// issued by frontend_tc_kernel, profiles/round2).
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 400) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();

@@ -6,7 +6,7 @@ fp32 path's only for a clip whose top-2 margin of the mean logits is smaller tha
 The scale of that error is a property of the model, not of the batch: the classifier sees a convex combination of
 LayerNorm outputs, so |logit_c - bias_c| <= S = max_c ||w_c * g||_2 sqrt(D) (w_c: classifier row, g: post_ln weight;
 S = 9.5 for the default init, where the largest |logit| of a batch is ~1.27).  Measured on 56 832 clips of the benchmark
-workload (tools/measure_near_ties.py, profiles/r2a_near_ties.json), in units of S: the error of the top-2 difference has
+workload (tools/measure_near_ties.py, profiles/round2/near_ties_margin_measurement.json), in units of S: the error of the top-2 difference has
 RMS 8.8e-6, 99.99 % quantile 5.9e-5, maximum 7.1e-5 (the per-pass rounding of the fusion GEMMs averages out over the T
 passes; what remains is the pass-invariant TF32 video Linear and the fp16 LSTM state) and a tail that falls a decade
 per 1.6e-5; the widest margin of a clip whose label actually flipped was 2.2e-5.  NearTieResolver takes every clip

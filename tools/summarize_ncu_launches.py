@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """ncu launch list (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv) of
 `python bench.py --no-e2e --no-cpu-baseline --no-extra --steps 2`  ->  the launches of one timed step of the main path
-(profiles/<tag>_step_launches.csv) and profiles/ncu_traffic.json (DRAM bytes per step per bench.py stage name).
-    python tools/summarize_ncu_launches.py gpurun_out/launches_r2.csv r2 [step_index]"""
+(profiles/<tag>/ncu_step_launches.csv) and profiles/ncu_traffic.json (DRAM bytes per step per bench.py stage name).
+    python tools/summarize_ncu_launches.py gpurun_out/launches_r2.csv round2 [step_index]"""
 import collections
 import csv
 import json
@@ -36,7 +36,7 @@ for i in ids[ids.index(begin):]:
     step.append(i)
     if "mc_reduce" in launches[i]["name"]:
         break
-out_csv = os.path.join(ROOT, "profiles", f"{tag}_step_launches.csv")
+out_csv = os.path.join(ROOT, "profiles", tag, "ncu_step_launches.csv")
 tot = sum(launches[i]["gpu__time_duration.sum"] for i in step)
 per_stage = collections.OrderedDict()
 with open(out_csv, "w", newline="") as f:
@@ -53,7 +53,7 @@ with open(out_csv, "w", newline="") as f:
             e["bytes"] += rd + wr
             e["launches"] += 1
     w.writerow(["", "TOTAL (serialised, cold cache, unthrottled clocks: compare shares)", "", "", f"{tot / 1e3:.1f}", "1.0", "", "", ""])
-traffic = {"batch": 18944, "precision": "tc", "source": f"profiles/{tag}_step_launches.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+traffic = {"batch": 18944, "precision": "tc", "source": f"profiles/{tag}/ncu_step_launches.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
            "one timed step of python bench.py --no-e2e --no-cpu-baseline --no-extra --steps 2)",
            "bytes_per_step": {k: v["bytes"] for k, v in per_stage.items()},
            "ncu_time_us_per_step": {k: v["time_us"] for k, v in per_stage.items()},
