@@ -511,14 +511,19 @@ def rooflines(prof, args, B, ms, peaks):
         vals = [tr["bytes_per_step"].get(n) for n in names if n in prof]
         return sum(vals) if vals and all(v is not None for v in vals) else None
 
+    tc = args.precision == "tc"
     groups = {   # stage -> (kernels, bound, algorithmic bytes per step, algorithmic FLOPs per step)
         "frontend": (["frontend"], "hbm", B * BYTES_FRONTEND, 0),
-        "lstm": (["lstm_split3", "lstm_input_gemm_tc", "lstm_recurrence_tc", "lstm_input_gemm", "lstm_recurrence",
-                  "lstm_fused_tc", "lstm_projection"], "tensor", B * BYTES_LSTM, B * FLOPS_LSTM),
+        "lstm": ((["lstm_split3", "lstm_input_gemm_tc", "lstm_recurrence_tc", "lstm_fused_tc"] if tc else
+                  ["lstm_input_gemm", "lstm_recurrence"]) + ["lstm_projection"], "tensor", B * BYTES_LSTM, B * FLOPS_LSTM),
         "video": (["frame_u8_to_f32", "frame_gemm"], "hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
-        "mc_tail": (["frame_tail", "fusion_clip", "fusion_tc", "fusion_pass", "hybrid_fusion", "mc_reduce"], "tensor",
-                    B * BYTES_MC_TAIL, B * args.passes * FLOPS_MC_PASS),
+        "mc_tail": (["frame_tail", "fusion_clip", "fusion_tc", "mc_reduce"] + ([] if tc else ["fusion_pass", "hybrid_fusion"]),
+                    "tensor", B * BYTES_MC_TAIL, B * args.passes * FLOPS_MC_PASS),
     }
+    if tc:   # the fp32 kernels that only the near-tie re-evaluation launches (its launches of the kernels it shares with the
+             # main path - front-end, video GEMM, tails - are a few percent of those stages and stay there)
+        groups["near_tie_reevaluation"] = (["lstm_input_gemm", "lstm_recurrence", "fusion_pass", "hybrid_fusion", "near_tie_flag",
+                                            "near_tie_gather", "near_tie_scatter"], "fp32", 0, 0)
     stage_rooflines = {}
     for name, (kernels, bound, nbytes, nflops) in groups.items():
         t = ms_of(kernels)
@@ -530,10 +535,12 @@ def rooflines(prof, args, B, ms, peaks):
                "dram_traffic_bytes_per_step": traffic_of(kernels)}
         if bound == "hbm":
             ent.update({"achieved": nbytes / sec / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / sec / 1e9 / hbm})
-        else:
+        elif bound == "tensor":
             ent.update({"achieved": nflops / sec / 1e12, "peak": tfs, "unit": "TFLOP/s",
                         "frac": nflops / sec / 1e12 / tfs})
-        if ent["dram_traffic_bytes_per_step"]:
+        else:
+            ent.update({"frac": None, "note": "fp32 CUDA-core re-evaluation of the near-tie clips (DESIGN.md section 2)"})
+        if ent["dram_traffic_bytes_per_step"] and nbytes:
             ent["traffic_over_algorithmic"] = ent["dram_traffic_bytes_per_step"] / nbytes
         stage_rooflines[name] = ent
     # the dominant kernel = the single kernel with the most device time per step; its roofline is its stage's bound with

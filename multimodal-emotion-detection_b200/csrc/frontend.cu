@@ -183,9 +183,9 @@ __device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2&
 //                = two more k-blocks).  The fp32 feature tensor (avhot_frontend) is written row by row.
 // mbarriers: a3_full (16 FFT warps -> MMA), a3_free / d3_full (MMA commit -> FFT warps / epilogue), x_full (4 epilogue
 // warps -> MMA), d4_full (MMA commit -> epilogue).  Parities follow the CTA's tile counter.
-// Precision: power bins and mel weights carry 11 significant bits each (fp16, round to nearest) - the same class as the
-// TF32 weights of the mma.sync version - so a log-mel value is within ~0.002 dB of the fp64 spec in the worst case and
-// ~0.0005 dB typically; the per-frame power-of-two scale keeps every bin within 84 dB of the frame's peak normal in fp16.
+// Precision: power bins and mel weights carry 11 significant bits each (fp16, round to nearest: 2^-11 relative), so a
+// log-mel value is within 0.0042 dB of the fp64 spec in the worst case (measured: 0.0035 dB at most, 0.0007 dB rms); the
+// per-frame power-of-two scale keeps every bin within 84 dB of the frame's peak normal in fp16.
 // =====================================================================================================================
 constexpr int FT_FFT_WARPS = 16, FT_EPI_WARP0 = 16, FT_THREADS = 20 * 32, FT_TILE = 128, FT_GROUP = 32;
 constexpr int FT_FFT_THREADS = FT_FFT_WARPS * 32;
