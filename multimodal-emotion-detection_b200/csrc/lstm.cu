@@ -26,6 +26,9 @@ struct avhot_lstm {
   void* w_hh_r16[4]; // fp16, rows regrouped per 32-unit chunk (lstm_tc.cu)
   void* w_ih_f16[4];  // fp16 input weights for the tensor-core path: layer 0 (4H, 3*in) = [W_hi | W_hi | W_lo],
                       // layers > 0 (4H, H)
+  void* w_ih_p16[4];  // layers > 0: fp16 W_ih / W_hh / fp32 bias in the fused layer kernel's row order (lstm_fused.cu)
+  void* w_hh_p16[4];
+  float* bias_p[4];
   float* proj_w;     // (out, H)
   float* proj_b;
   float* arena;
@@ -264,6 +267,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
   total += align256(2 * 4 * H * pad8(3 * d->input_dim + 2)) + (L - 1) * align256(2 * 4 * H * H);
+  total += (L - 1) * (2 * align256(2 * 4 * H * H) + align256(sizeof(float) * 4 * H));   // fused-layer packing
   avhot_lstm* h = new avhot_lstm();
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
@@ -302,6 +306,12 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
       h->w_ih_f16[l] = take(2 * 4 * H * ldo);
       pack_w_bias_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[l], h->bias[l], reinterpret_cast<__half*>(h->w_ih_f16[l]),
                                                4 * H, H, ldo);
+      h->w_ih_p16[l] = take(2 * 4 * H * H);
+      h->w_hh_p16[l] = take(2 * 4 * H * H);
+      h->bias_p[l] = take(sizeof(float) * 4 * H);
+      if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
+      if (rc == AVHOT_OK)
+        rc = lstm_fused_pack(d->weight_ih[l], H, d->weight_hh[l], h->bias[l], h->w_ih_p16[l], h->w_hh_p16[l], h->bias_p[l], s);
     }
     if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
   }
@@ -415,6 +425,11 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
           AVHOT_LAUNCH_CHECK();
         }
         rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
+      } else if (last && lstm_fused_tc_supported(in, B)) {
+        // the top layer of a stack: input projection and recurrence in one kernel, no xp round trip (lstm_fused.cu)
+        rc = lstm_layer_fused_tc(h->w_ih_p16[l], h->w_hh_p16[l], h->bias_p[l], h_seq, hp, hl_out, lengths, B, T, s);
+        if (rc != AVHOT_OK) return rc;
+        continue;
       } else {
         rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, h->bias_tc[l], xp, true, 4 * H, Mp, 4 * H, H, s, "lstm_input_gemm_tc");
       }

@@ -1,0 +1,370 @@
+// One LSTM layer as ONE kernel on the tcgen05 tensor cores: input projection and recurrence in the same MMA chain
+// (AVHOT_PREC_TC path of a3, src/encoders.py:54-61, :148-154; SURVEY.md section 7 "hard parts").
+//
+// lstm_tc.cu needs xp = x W_ih^T + b for all steps in HBM first (gemm_ws.cu): 12 GB written and read back per layer at
+// 18 944 clips, 26x the algorithmic traffic of the stage, and a second 3 ms kernel.  Here every step computes
+//     gates[256 clips, 1024] = [x_t | h_{t-1}] x [W_ih | W_hh]^T            (K = KX * 64 + 256, one accumulator chain)
+// per CTA pair (cta_group::2, M = 256 = 128 clips per CTA), in 8 chunks of 32 hidden units (N = 128 accumulator
+// columns, two TMEM buffers).  What made it fit (round 2 wrote it off: 128 KB of h ping-pong + 64 KB of x_t + the
+// weight ring > 227 KB of shared memory, TMEM full):
+//   * h lives in TENSOR MEMORY, not shared memory: the epilogue threads write h_t as packed fp16 with tcgen05.st into
+//     128 columns of their own lanes, and the recurrent half of the chain is tcgen05.mma with the A operand FROM TMEM
+//     ([a_tmem] form, K = 16 = 8 columns per instruction); two buffers (step parity) = 256 columns;
+//   * the cell state moves from TMEM to REGISTERS: thread (clip, q) owns 8 units of each of the 8 chunks = 64 fp32
+//     registers, statically indexed because the chunk loop is unrolled; the xp prefetch registers are gone;
+//   * shared memory then holds only the x_t tiles (a ring of NXS 16 KB k-block slots, filled by TMA from the time-major
+//     fp16 sequence the previous layer stored) and the weight ring (NWS stages of 4 k-blocks, this CTA's half of the
+//     gate rows, streamed from L2 every step as before).
+// The x half of chunk 0 of step t+1 does not depend on h_t, so the tensor pipe works through it while the epilogue
+// of step t's last chunk finishes: the step boundary costs no bubble.  TMEM: [0,256) accumulators, [256,512) h.
+//   warp 0      TMA producer: weight stages (W_ih chunk c, then W_hh chunk c), both CTAs, completing the leader's barriers
+//   warp 1      leader CTA: one elected lane issues the 32 MMAs of a chunk (16 SS on x_t, 16 TS on h_{t-1})
+//   warps 4-19  epilogue: thread = (clip = TMEM lane, q): tcgen05.ld 4 gates x 8 units, + bias, activations, c in
+//               registers, h_t -> tcgen05.st, arrive on h_ready[k-block] of the leader
+//   warp 2      TMA producer of the x_t k-blocks (runs ahead by the free slots of the ring); warp 3 idle
+// Gate columns of a chunk are permuted so that a thread's (4 gates x 4 units) are 16 consecutive TMEM columns:
+//   packed row c*128 + q*32 + hf*16 + g*4 + i  =  gate g, unit c*32 + q*8 + hf*4 + i     (pack_fused_w_kernel)
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace avhot {
+namespace tc {
+
+constexpr int FB = 128, FH = 256, FCH = 32, FNC = FH / FCH, FN = 4 * FCH, FHKB = FH / 64;
+constexpr int FTHREADS = 128 + 512;            // warpgroup 0: producers + MMA (setmaxnreg 56), warpgroups 1-4: epilogue (104): 128 x 56 + 512 x 104 <= 640 x 96, the launch allocation
+constexpr uint32_t FCOL_H = 256;                 // first TMEM column of the hidden state (2 x 128 columns)
+
+template <int NXS, int NWS> struct FusedSmem {
+  __half xA[NXS][FB * 64];          // x_t k-blocks, A operand: 128 rows x 128 B, 128-byte swizzle
+  __half wB[NWS][4][64 * 64];       // weight stages: 4 k-blocks of (this CTA's 64 gate rows x 64 k), B operand
+  uint64_t w_full[NWS], w_empty[NWS], acc_full[2], acc_empty[2], h_ready[FHKB], x_full[NXS], x_empty[NXS];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_f() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T, CTA pair: each CTA's 128 rows of A are 128 lanes x 8 columns (K = 16 fp16, two per
+// 32-bit column, row = lane) of its own tensor memory at the same address
+__device__ __forceinline__ void umma_f16_pair_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                       bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void stg256f(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// KX: 64-column k-blocks of the x operand (4 = a 256-wide hidden sequence).  The sigmoid gates' weights and biases are
+// packed halved (tc_gate_scale in lstm.cu): sigmoid(x) = 0.5 + 0.5 tanh(x / 2), one MUFU per activation.
+template <int KX, int NXS, int NWS>
+__global__ void __launch_bounds__(FTHREADS, 1)
+lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_constant__ CUtensorMap tmWh,
+                       const __grid_constant__ CUtensorMap tmX, const float* __restrict__ bias_p,
+                       float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T, int n_ct_arg) {
+  static_assert(KX == 4, "a weight stage holds the 4 k-blocks of one half (x or h) of a chunk");
+  using Smem = FusedSmem<NXS, NWS>;
+  const int ctile = min((int)blockIdx.x, n_ct_arg - 1);
+  const bool writer = (int)blockIdx.x < n_ct_arg;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  extern __shared__ unsigned char fused_smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(fused_smem_raw + ((1024u - (smem_u32(fused_smem_raw) & 1023u)) & 1023u));
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmWi);
+    tma_prefetch_desc(&tmWh);
+    for (int s = 0; s < NWS; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 16 * 2); }
+    for (int k = 0; k < FHKB; ++k) mbar_init(&sm.h_ready[k], 32 * 2);   // 16 epilogue warps x 2 chunks x 2 CTAs
+    for (int s = 0; s < NXS; ++s) { mbar_init(&sm.x_full[s], 1); mbar_init(&sm.x_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc_pair(&sm.tmem_base, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // both CTAs' barriers are initialised before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t W_STAGE_BYTES = 2u * 4u * 64u * 64u * (uint32_t)sizeof(__half);   // both CTAs' halves
+  constexpr uint32_t X_SLOT_BYTES = 2u * FB * 64u * (uint32_t)sizeof(__half);
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 0) {
+    // ---- weight producer (both CTAs): per (t, c) the x half (W_ih rows of chunk c), then the h half (W_hh; none at t = 0)
+    if (lane == 0) {
+      const uint32_t full0 = cluster_map_shared(&sm.w_full[0], 0);      // the leader's w_full[] barriers
+      uint32_t it = 0;
+      for (int t = 0; t < T; ++t)
+        for (int c = 0; c < FNC; ++c)
+          for (int half = 0; half < (t == 0 ? 1 : 2); ++half, ++it) {
+            const int s = it % NWS;
+            mbar_wait(&sm.w_empty[s], ((it / NWS) & 1) ^ 1);
+            if (leader) mbar_expect_tx(&sm.w_full[s], W_STAGE_BYTES);
+            const CUtensorMap* tm = half == 0 ? &tmWi : &tmWh;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+              tma_load_2d_pair(sm.wB[s][kb], tm, full0 + (uint32_t)s * 8u, kb * 64, c * FN + (int)crank * 64);
+          }
+    }
+  } else if (warp == 2) {
+    // ---- x producer (both CTAs): k-block kb of step t -> slot (t * KX + kb) % NXS, as far ahead as slots are free
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      const uint32_t xfull0 = cluster_map_shared(&sm.x_full[0], 0);
+      uint32_t xi = 0;
+      for (int t = 0; t < T; ++t)
+        for (int kb = 0; kb < KX; ++kb, ++xi) {
+          const int slot = xi % NXS;
+          mbar_wait(&sm.x_empty[slot], ((xi / NXS) & 1) ^ 1);
+          if (leader) mbar_expect_tx(&sm.x_full[slot], X_SLOT_BYTES);
+          tma_load_2d_pair(sm.xA[slot], &tmX, xfull0 + (uint32_t)slot * 8u, kb * 64, (t * n_ct_arg + ctile) * FB);
+        }
+    }
+  } else if (warp == 1) {
+    if (leader) {                               // the whole warp, converged; one elected lane issues
+      constexpr uint32_t idesc = umma_idesc(FMT_F16, 2 * FB, FN);
+      uint32_t it = 0, xi0 = 0;
+      for (int t = 0; t < T; ++t, xi0 += KX) {
+        const uint32_t hsrc = tmem + FCOL_H + (uint32_t)(t & 1) * 128u;     // h_{t-1}
+#pragma unroll 1
+        for (int c = 0; c < FNC; ++c) {
+          const int b = c & 1;
+          // buffer b is used FNC / 2 = 4 times per step: the parity of its use count at chunk c is (c >> 1) & 1
+          mbar_wait_cluster(&sm.acc_empty[b], (uint32_t)((c >> 1) & 1) ^ 1u);
+          const uint32_t acc = tmem + (uint32_t)(b * FN);
+          {                                     // x half: A = x_t (shared memory), B = W_ih rows of chunk c
+            const int s = it % NWS;
+            mbar_wait(&sm.w_full[s], (it / NWS) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < KX; ++kb) {
+              const uint32_t xi = xi0 + kb;
+              const int slot = xi % NXS;
+              if (c == 0) {
+                mbar_wait(&sm.x_full[slot], (xi / NXS) & 1);
+                tc_fence_after();
+              }
+              const uint64_t adesc = umma_desc_sw128(smem_u32(sm.xA[slot]));
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s][kb]));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair_elect(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              if (c == FNC - 1) umma_commit_pair_mc_elect(&sm.x_empty[slot], 3);   // last reader of x_t's k-block
+            }
+            umma_commit_pair_mc_elect(&sm.w_empty[s], 3);
+            ++it;
+          }
+          if (t > 0) {                          // h half: A = h_{t-1} (tensor memory), B = W_hh rows of chunk c
+            const int s = it % NWS;
+            mbar_wait(&sm.w_full[s], (it / NWS) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < FHKB; ++kb) {
+              if (c == 0) {
+                mbar_wait_cluster(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+                tc_fence_after();
+              }
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s][kb]));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair_ts_elect(acc, hsrc + (uint32_t)(kb * 32 + k * 8), bdesc + 2 * k, idesc, true);
+            }
+            umma_commit_pair_mc_elect(&sm.w_empty[s], 3);
+            ++it;
+          }
+          umma_commit_pair_mc_elect(&sm.acc_full[b], 3);
+        }
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ---- 16 epilogue warps = (TMEM lane quarter) x (quarter q of a chunk); thread (clip r, q) owns units
+    // 32 c + 8 q .. + 7 of every chunk c and keeps their cell state in registers for the whole sequence
+    const int q = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // clip row = TMEM lane
+    const int clip = ctile * FB + r;
+    const bool live = writer && clip < B;
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int last_t = (live && lengths ? min(max(__ldg(lengths + clip), 1), T) : T) - 1;
+    const uint32_t acc_empty_addr0 = cluster_map_shared(&sm.acc_empty[0], 0);
+    const uint32_t h_ready_addr0 = cluster_map_shared(&sm.h_ready[0], 0);
+    const float4* const bias4 = reinterpret_cast<const float4*>(bias_p) + q * 8;
+    float cs[FNC * 8];
+#pragma unroll
+    for (int i = 0; i < FNC * 8; ++i) cs[i] = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      const uint32_t hdst = tlane + FCOL_H + (uint32_t)((t + 1) & 1) * 128u + (uint32_t)(q * 4);
+      const bool emit = live && h_last && t == last_t;
+#pragma unroll
+      for (int c = 0; c < FNC; ++c) {
+        const int b = c & 1;
+        mbar_wait(&sm.acc_full[b], (uint32_t)((c >> 1) & 1));
+        tc_fence_after();
+        uint32_t a[2][16];
+        tmem_ld16(tlane + (uint32_t)(b * FN + q * 32), a[0]);
+        tmem_ld16(tlane + (uint32_t)(b * FN + q * 32 + 16), a[1]);
+        tmem_ld_wait();
+        // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the activation math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_addr0 + (uint32_t)b * 8u);
+        float hn[8];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float4 bg[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bg[g] = __ldg(bias4 + c * 32 + hf * 4 + g);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float bi = i == 0 ? bg[0].x : i == 1 ? bg[0].y : i == 2 ? bg[0].z : bg[0].w;
+            const float bf = i == 0 ? bg[1].x : i == 1 ? bg[1].y : i == 2 ? bg[1].z : bg[1].w;
+            const float bgg = i == 0 ? bg[2].x : i == 1 ? bg[2].y : i == 2 ? bg[2].z : bg[2].w;
+            const float bo = i == 0 ? bg[3].x : i == 1 ? bg[3].y : i == 2 ? bg[3].z : bg[3].w;
+            const float ig = fmaf(0.5f, tanh_mufu(__uint_as_float(a[hf][i]) + bi), 0.5f);
+            const float fg = fmaf(0.5f, tanh_mufu(__uint_as_float(a[hf][4 + i]) + bf), 0.5f);
+            const float gg = tanh_mufu(__uint_as_float(a[hf][8 + i]) + bgg);
+            const float og = fmaf(0.5f, tanh_mufu(__uint_as_float(a[hf][12 + i]) + bo), 0.5f);
+            const float cn = fmaf(fg, cs[c * 8 + hf * 4 + i], ig * gg);
+            cs[c * 8 + hf * 4 + i] = cn;
+            hn[hf * 4 + i] = og * tanh_mufu(cn);
+          }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2 v = __floats2half2_rn(hn[2 * j], hn[2 * j + 1]);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&v);
+        }
+        tmem_st4(hdst + (uint32_t)(c * 16), pk);             // units 32 c + 8 q .. + 7 = columns 16 c + 4 q .. + 3
+        if (emit) stg256f(h_last + (size_t)clip * FH + c * FCH + q * 8, hn);
+        tmem_st_wait_f();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(h_ready_addr0 + (uint32_t)(c >> 1) * 8u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // no CTA leaves while its peer can still signal its barriers
+  if (warp == 1) tmem_dealloc_pair(tmem, 512);
+}
+
+// w (4H, K) fp32 -> out (4H, K) fp16 in the packed row order of the kernel above, sigmoid gates halved;
+// bias (4H) fp32 (b_ih + b_hh) -> the same order and scaling
+__global__ void pack_fused_w_kernel(const float* __restrict__ w, __half* __restrict__ out, int K) {
+  const int p = blockIdx.x;                     // packed row
+  const int c = p >> 7, qq = (p >> 5) & 3, hf = (p >> 4) & 1, g = (p >> 2) & 3, i = p & 3;
+  const float* src = w + (size_t)(g * FH + c * FCH + qq * 8 + hf * 4 + i) * K;
+  const float sc = g == 2 ? 1.f : 0.5f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) out[(size_t)p * K + k] = __float2half_rn(sc * src[k]);
+}
+__global__ void pack_fused_bias_kernel(const float* __restrict__ bias, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= 4 * FH) return;
+  const int c = p >> 7, qq = (p >> 5) & 3, hf = (p >> 4) & 1, g = (p >> 2) & 3, i = p & 3;
+  out[p] = (g == 2 ? 1.f : 0.5f) * bias[g * FH + c * FCH + qq * 8 + hf * 4 + i];
+}
+
+}  // namespace tc
+
+int lstm_fused_pack(const float* w_ih, int K, const float* w_hh, const float* bias, void* w_ih_p16, void* w_hh_p16,
+                    float* bias_p, cudaStream_t s) {
+  tc::pack_fused_w_kernel<<<4 * tc::FH, 128, 0, s>>>(w_ih, reinterpret_cast<__half*>(w_ih_p16), K);
+  AVHOT_LAUNCH_CHECK();
+  tc::pack_fused_w_kernel<<<4 * tc::FH, 128, 0, s>>>(w_hh, reinterpret_cast<__half*>(w_hh_p16), tc::FH);
+  AVHOT_LAUNCH_CHECK();
+  tc::pack_fused_bias_kernel<<<4, 256, 0, s>>>(bias, bias_p);
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+namespace {
+constexpr int kNXS = 8, kNWS = 3;
+using FusedK4 = tc::FusedSmem<kNXS, kNWS>;
+bool fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_ct, int smem, cudaStream_t s) {
+  cfg = {};
+  cfg.gridDim = dim3((unsigned)(ceil_div(n_ct, 2) * 2));
+  cfg.blockDim = dim3(tc::FTHREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = s;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return true;
+}
+}  // namespace
+
+// can the fused kernel take this layer?  (x operand 256 wide, every CTA pair co-resident: one CTA per SM)
+bool lstm_fused_tc_supported(int in_dim, int B) {
+  static const int forced = [] { const char* e = getenv("AVHOT_LSTM_FUSED"); return e ? atoi(e) : -1; }();
+  if (forced == 0 || in_dim != tc::FH) return false;
+  const int n_ct = ceil_div(B, tc::FB);
+  if (n_ct < 2) return false;
+  auto kern = tc::lstm_fused_pair_kernel<4, kNXS, kNWS>;
+  const int smem = (int)sizeof(FusedK4) + 1024;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fused_cluster_cfg(cfg, attr, n_ct, smem, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  return n * 2 >= ceil_div(n_ct, 2) * 2;
+}
+
+// x_f16: (T, Bp, x_pitch) fp16 time-major sequence (Bp = B rounded up to 128), 256 features; h_last (B, 256) fp32 =
+// the layer's hidden state at step lengths[b] - 1
+int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_pitch,
+                        float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
+  using namespace tc;
+  const int n_ct = ceil_div(B, FB);
+  const int smem = (int)sizeof(FusedK4) + 1024;
+  AVHOT_REQUIRE(x_pitch >= FH && (x_pitch & 7) == 0, AVHOT_ERR_INVALID, "lstm_layer_fused_tc: bad x pitch %d", x_pitch);
+  CUtensorMap tmWi, tmWh, tmX;
+  int rc = make_tensor_map_2d(&tmWi, w_ih_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, FH, FH, 64, 64);
+  if (rc == AVHOT_OK) rc = make_tensor_map_2d(&tmWh, w_hh_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, FH, FH, 64, 64);
+  if (rc == AVHOT_OK)
+    rc = make_tensor_map_2d(&tmX, x_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)T * n_ct * FB, FH, (uint64_t)x_pitch,
+                            FB, 64);
+  if (rc != AVHOT_OK) return rc;
+  auto kern = lstm_fused_pair_kernel<4, kNXS, kNWS>;
+  AVHOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fused_cluster_cfg(cfg, attr, n_ct, smem, s);
+  ProfScope prof("lstm_layer_fused_tc", s);
+  AVHOT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmWi, tmWh, tmX, bias_p, h_last, lengths, B, T, n_ct));
+  AVHOT_LAUNCH_CHECK();
+  return AVHOT_OK;
+}
+
+}  // namespace avhot
