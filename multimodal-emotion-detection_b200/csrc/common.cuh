@@ -81,12 +81,15 @@ int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s);
 // xp: input projections incl. bias, time-major tile-transposed (gemm_ws.cu); h_seq_f16: (T, Bp, h_pitch) fp16 or NULL
 int lstm_recurrence_tc(const void* whh_packed_fp16, const void* xp, bool xp_f16, void* h_seq_f16, int h_pitch,
                        float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s);
-// lstm_fused.cu: one layer (x 256 wide), input projection + recurrence in one tcgen05 kernel (h in TMEM, c in registers)
-int lstm_fused_pack(const float* w_ih, int K, const float* w_hh, const float* bias, void* w_ih_p16, void* w_hh_p16,
-                    float* bias_p, cudaStream_t s);
-bool lstm_fused_tc_supported(int in_dim, int B);
-int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_pitch,
-                        float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s);
+// lstm_fused.cu: one LSTM layer, input projection + recurrence in one tcgen05 kernel (h in TMEM, c in registers).
+// Row order of its packed weights / bias: row p = c*128 + q*32 + hf*16 + g*4 + i holds gate g of unit c*32 + q*8 + hf*4 + i
+__host__ __device__ __forceinline__ int lstm_fused_src_row(int p, int H = 256) {
+  return ((p >> 2) & 3) * H + (p >> 7) * 32 + ((p >> 5) & 3) * 8 + ((p >> 4) & 1) * 4 + (p & 3);
+}
+bool lstm_fused_tc_supported(int x_cols, bool hseq, int B);
+int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_cols,
+                        int x_pitch, void* h_seq_f16, int h_pitch, float* h_last, const int32_t* lengths, int B, int T,
+                        cudaStream_t s);
 // gemm_ws.cu: weight-stationary tcgen05 GEMM, fp16 operands, fp32 output (LSTM input projections)
 int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, const float* bias, void* c, bool out_f16, int ldc, int M,
                 int N, int K, cudaStream_t s, const char* prof_name = "gemm_f16_ws");

@@ -173,9 +173,10 @@ __host__ __device__ __forceinline__ bool split3_slot(int c, int K, int& term, in
 // epilogue).  Rows of the sigmoid gates (i, f, o: every gate but g = rows [2H, 3H)) are stored halved - exact, a power of
 // two - so that the recurrent kernel's sigmoid(x) = 0.5 tanh(x / 2) + 0.5 needs no pre-scaling multiply (lstm_tc.cu).
 __device__ __forceinline__ float tc_gate_scale(int n, int N) { return (n / (N / 4)) == 2 ? 1.f : 0.5f; }
+// perm: output row p holds source row lstm_fused_src_row(p) (the fused layer kernel's gate-column order)
 __global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                     __half* __restrict__ out, int N, int K, int ldo) {
-  const int n = blockIdx.x;
+                                     __half* __restrict__ out, int N, int K, int ldo, bool perm) {
+  const int n = perm ? lstm_fused_src_row(blockIdx.x) : blockIdx.x;
   const float sc = tc_gate_scale(n, N);
   for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
     int term, feat;
@@ -185,22 +186,23 @@ __global__ void pack_w_split3_kernel(const float* __restrict__ w, const float* _
       const __half hi = __float2half_rn(v);
       o = term == 2 ? __float2half_rn(v - __half2float(hi)) : hi;
     }
-    out[(size_t)n * ldo + k] = o;
+    out[(size_t)blockIdx.x * ldo + k] = o;
   }
 }
 // weights of layers > 0: W (N, K) fp32 -> out (N, ldo) fp16 = [W | 0...]
-__global__ void scale_gate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < N) out[n] = tc_gate_scale(n, N) * b[n];
+__global__ void scale_gate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int N, bool perm) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int n = perm ? lstm_fused_src_row(p) : p;
+  out[p] = tc_gate_scale(n, N) * b[n];
 }
 __global__ void pack_w_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                   __half* __restrict__ out, int N, int K, int ldo) {
-  const int n = blockIdx.x;
+                                   __half* __restrict__ out, int N, int K, int ldo, bool perm) {
+  const int n = perm ? lstm_fused_src_row(blockIdx.x) : blockIdx.x;
   for (int k = threadIdx.x; k < ldo; k += blockDim.x) {
     float v = 0.f;
-    bool lo = false;
     if (k < K) v = tc_gate_scale(n, N) * w[(size_t)n * K + k];
-    out[(size_t)n * ldo + k] = __float2half_rn(v);
+    out[(size_t)blockIdx.x * ldo + k] = __float2half_rn(v);
   }
 }
 // activations: x (B, T, K) batch-major -> out (T, Bp, ldo) time-major, term 0 and 2 = hi, term 1 = lo (split3_slot); the
@@ -267,7 +269,9 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   AVHOT_REQUIRE(d->proj_weight && d->proj_bias, AVHOT_ERR_INVALID, "lstm_create: projection missing");
   total += align256(sizeof(float) * d->output_dim * H) + align256(sizeof(float) * d->output_dim);
   total += align256(2 * 4 * H * pad8(3 * d->input_dim + 2)) + (L - 1) * align256(2 * 4 * H * H);
-  total += (L - 1) * (2 * align256(2 * 4 * H * H) + align256(sizeof(float) * 4 * H));   // fused-layer packing
+  // the same in the fused layer kernel's row order: W_ih (layer 0: split), W_hh, bias
+  total += align256(2 * 4 * H * pad8(3 * d->input_dim + 2)) + (L - 1) * align256(2 * 4 * H * H) +
+           L * (align256(2 * 4 * H * H) + align256(sizeof(float) * 4 * H));
   avhot_lstm* h = new avhot_lstm();
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
@@ -295,24 +299,20 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     if (rc == AVHOT_OK) rc = lstm_pack_whh_fp16(d->weight_hh[l], h->w_hh_r16[l], s);
   }
   for (int l = 0; l < L && rc == AVHOT_OK; ++l) {   // after the bias sums above (same stream)
-    scale_gate_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, s>>>(h->bias[l], h->bias_tc[l], 4 * H);
-    if (l == 0) {
-      const int ldo = pad8(3 * d->input_dim + 2);
-      h->w_ih_f16[0] = take(2 * 4 * H * ldo);
-      pack_w_split3_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[0], h->bias[0], reinterpret_cast<__half*>(h->w_ih_f16[0]),
-                                                 4 * H, d->input_dim, ldo);
-    } else {
-      const int ldo = H;
-      h->w_ih_f16[l] = take(2 * 4 * H * ldo);
-      pack_w_bias_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[l], h->bias[l], reinterpret_cast<__half*>(h->w_ih_f16[l]),
-                                               4 * H, H, ldo);
-      h->w_ih_p16[l] = take(2 * 4 * H * H);
-      h->w_hh_p16[l] = take(2 * 4 * H * H);
-      h->bias_p[l] = take(sizeof(float) * 4 * H);
-      if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
-      if (rc == AVHOT_OK)
-        rc = lstm_fused_pack(d->weight_ih[l], H, d->weight_hh[l], h->bias[l], h->w_ih_p16[l], h->w_hh_p16[l], h->bias_p[l], s);
+    scale_gate_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, s>>>(h->bias[l], h->bias_tc[l], 4 * H, false);
+    const int ldo = l == 0 ? pad8(3 * d->input_dim + 2) : H;
+    h->w_ih_f16[l] = take(2 * 4 * H * ldo);
+    h->w_ih_p16[l] = take(2 * 4 * H * ldo);
+    h->w_hh_p16[l] = take(2 * 4 * H * H);
+    h->bias_p[l] = take(sizeof(float) * 4 * H);
+    for (int perm = 0; perm < 2; ++perm) {
+      __half* dst = reinterpret_cast<__half*>(perm ? h->w_ih_p16[l] : h->w_ih_f16[l]);
+      if (l == 0) pack_w_split3_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[0], h->bias[0], dst, 4 * H, d->input_dim, ldo, perm);
+      else pack_w_bias_kernel<<<4 * H, 128, 0, s>>>(d->weight_ih[l], h->bias[l], dst, 4 * H, H, ldo, perm);
     }
+    pack_w_bias_kernel<<<4 * H, 128, 0, s>>>(d->weight_hh[l], h->bias[l], reinterpret_cast<__half*>(h->w_hh_p16[l]), 4 * H,
+                                             H, H, true);
+    scale_gate_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, s>>>(h->bias[l], h->bias_p[l], 4 * H, true);
     if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
   }
   if (rc == AVHOT_OK) {
@@ -411,25 +411,27 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
       // layer 0: A = [hi | lo | hi] x W = [W_hi | W_hi | W_lo] (K = 3 in), an fp32-class product (dropping the
       // hi x W_lo term measured 5.4e-3 on the logits, outside the stated tolerance)
       constexpr int l0_terms = 3;
-      if (l == 0 && seq_split) {                      // operand already prepared by avhot_frontend_ex
-        const int ldx = pad8(3 * in + 2);
-        rc = gemm_f16_ws(seq_split, ldx, h->w_ih_f16[0], ldx, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
-      } else if (l == 0) {
-        const int ldx = pad8(3 * in + 2);
-        {
-          ProfScope prof("lstm_split3", s);
-          const size_t smem = sizeof(float) * SPL_CB * SPL_TB * in;
-          AVHOT_REQUIRE(smem <= 48 * 1024, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d too large", in);
-          split3_f16_tm_kernel<<<dim3((unsigned)(Bp / SPL_CB), (unsigned)ceil_div(T, SPL_TB)), 256, smem, s>>>(
-              x, x_split, B, (int)Bp, T, in, ldx);
-          AVHOT_LAUNCH_CHECK();
-        }
-        rc = gemm_f16_ws(x_split, ldx, h->w_ih_f16[0], ldx, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
-      } else if (last && lstm_fused_tc_supported(in, B)) {
-        // the top layer of a stack: input projection and recurrence in one kernel, no xp round trip (lstm_fused.cu)
-        rc = lstm_layer_fused_tc(h->w_ih_p16[l], h->w_hh_p16[l], h->bias_p[l], h_seq, hp, hl_out, lengths, B, T, s);
+      // one kernel per layer when it fits (lstm_fused.cu): input projection and recurrence in one MMA chain, no xp
+      const void* x_op = l > 0 ? (const void*)h_seq : seq_split ? seq_split : (const void*)x_split;
+      const int x_cols = l == 0 ? pad8(3 * in + 2) : H;
+      const bool fused = lstm_fused_tc_supported(x_cols, !last, B);
+      if (l == 0 && !seq_split) {                     // (operand not prepared by avhot_frontend_ex)
+        ProfScope prof("lstm_split3", s);
+        const size_t smem = sizeof(float) * SPL_CB * SPL_TB * in;
+        AVHOT_REQUIRE(smem <= 48 * 1024, AVHOT_ERR_UNSUPPORTED, "lstm_forward(tc): input_dim %d too large", in);
+        split3_f16_tm_kernel<<<dim3((unsigned)(Bp / SPL_CB), (unsigned)ceil_div(T, SPL_TB)), 256, smem, s>>>(
+            x, x_split, B, (int)Bp, T, in, x_cols);
+        AVHOT_LAUNCH_CHECK();
+      }
+      if (fused) {
+        // a middle layer reads and writes h_seq in place: step t's rows are stored after every MMA that reads them
+        rc = lstm_layer_fused_tc(h->w_ih_p16[l], h->w_hh_p16[l], h->bias_p[l], x_op, x_cols, x_cols,
+                                 last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);
         if (rc != AVHOT_OK) return rc;
         continue;
+      }
+      if (l == 0) {
+        rc = gemm_f16_ws(x_op, x_cols, h->w_ih_f16[0], x_cols, h->bias_tc[0], xp, xf16, 4 * H, Mp, 4 * H, l0_terms * in, s, "lstm_input_gemm_tc");
       } else {
         rc = gemm_f16_ws(h_seq, hp, h->w_ih_f16[l], hp, h->bias_tc[l], xp, true, 4 * H, Mp, 4 * H, H, s, "lstm_input_gemm_tc");
       }

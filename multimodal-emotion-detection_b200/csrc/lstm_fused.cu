@@ -13,15 +13,18 @@
 //   * the cell state moves from TMEM to REGISTERS: thread (clip, q) owns 8 units of each of the 8 chunks = 64 fp32
 //     registers, statically indexed because the chunk loop is unrolled; the xp prefetch registers are gone;
 //   * shared memory then holds only the x_t tiles (a ring of NXS 16 KB k-block slots, filled by TMA from the time-major
-//     fp16 sequence the previous layer stored) and the weight ring (NWS stages of 4 k-blocks, this CTA's half of the
-//     gate rows, streamed from L2 every step as before).
+//     fp16 operand: the front-end's [hi | lo | hi] split for layer 0, K = 320; the previous layer's hidden sequence
+//     above it, K = 256), the weight ring (NWS stages of G k-blocks, this CTA's half of the gate rows, streamed from
+//     L2 every step as before) and, below the top layer, two 16 KB staging tiles from which the layer's own fp16
+//     hidden sequence leaves through TMA stores (the next layer's x operand).
 // The x half of chunk 0 of step t+1 does not depend on h_t, so the tensor pipe works through it while the epilogue
 // of step t's last chunk finishes: the step boundary costs no bubble.  TMEM: [0,256) accumulators, [256,512) h.
 //   warp 0      TMA producer: weight stages (W_ih chunk c, then W_hh chunk c), both CTAs, completing the leader's barriers
-//   warp 1      leader CTA: one elected lane issues the 32 MMAs of a chunk (16 SS on x_t, 16 TS on h_{t-1})
+//   warp 1      leader CTA: one elected lane issues the MMAs of a chunk (4 KX SS on x_t, 16 TS on h_{t-1})
 //   warps 4-19  epilogue: thread = (clip = TMEM lane, q): tcgen05.ld 4 gates x 8 units, + bias, activations, c in
 //               registers, h_t -> tcgen05.st, arrive on h_ready[k-block] of the leader
-//   warp 2      TMA producer of the x_t k-blocks (runs ahead by the free slots of the ring); warp 3 idle
+//   warp 2      TMA producer of the x_t k-blocks (runs ahead by the free slots of the ring)
+//   warp 3      TMA stores of the layer's hidden sequence (HSEQ)
 // Gate columns of a chunk are permuted so that a thread's (4 gates x 4 units) are 16 consecutive TMEM columns:
 //   packed row c*128 + q*32 + hf*16 + g*4 + i  =  gate g, unit c*32 + q*8 + hf*4 + i     (pack_fused_w_kernel)
 #include <cuda_fp16.h>
@@ -37,10 +40,12 @@ constexpr int FB = 128, FH = 256, FCH = 32, FNC = FH / FCH, FN = 4 * FCH, FHKB =
 constexpr int FTHREADS = 128 + 512;            // warpgroup 0: producers + MMA (setmaxnreg 56), warpgroups 1-4: epilogue (104): 128 x 56 + 512 x 104 <= 640 x 96, the launch allocation
 constexpr uint32_t FCOL_H = 256;                 // first TMEM column of the hidden state (2 x 128 columns)
 
-template <int NXS, int NWS> struct FusedSmem {
+template <int NXS, int NWS, int G, int NHS> struct FusedSmem {
   __half xA[NXS][FB * 64];          // x_t k-blocks, A operand: 128 rows x 128 B, 128-byte swizzle
-  __half wB[NWS][4][64 * 64];       // weight stages: 4 k-blocks of (this CTA's 64 gate rows x 64 k), B operand
+  __half wB[NWS][G][64 * 64];       // weight stages: G k-blocks of (this CTA's 64 gate rows x 64 k), B operand
+  __half hS[NHS ? NHS : 1][NHS ? FB * 64 : 8];   // HSEQ: k-blocks of h_t on their way out (TMA store source)
   uint64_t w_full[NWS], w_empty[NWS], acc_full[2], acc_empty[2], h_ready[FHKB], x_full[NXS], x_empty[NXS];
+  uint64_t hs_done[2], hs_free[2];
   uint32_t tmem_base;
 };
 
@@ -72,15 +77,19 @@ __device__ __forceinline__ void stg256f(float* p, const float (&v)[8]) {
                : "memory");
 }
 
-// KX: 64-column k-blocks of the x operand (4 = a 256-wide hidden sequence).  The sigmoid gates' weights and biases are
-// packed halved (tc_gate_scale in lstm.cu): sigmoid(x) = 0.5 + 0.5 tanh(x / 2), one MUFU per activation.
-template <int KX, int NXS, int NWS>
+// KX: 64-column k-blocks of the x operand (5 = the [hi | lo | hi] split of 104 features, 4 = a 256-wide hidden
+// sequence).  G: k-blocks per weight stage (divides KX and 4).  HSEQ: the layer's fp16 hidden sequence is stored
+// (time-major (T, Bp, pitch), rows of padding clips included) and h_last is not.  The sigmoid gates' weights and
+// biases are packed halved (tc_gate_scale in lstm.cu): sigmoid(x) = 0.5 + 0.5 tanh(x / 2), one MUFU per activation.
+template <int KX, int NXS, int NWS, int G, bool HSEQ>
 __global__ void __launch_bounds__(FTHREADS, 1)
 lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_constant__ CUtensorMap tmWh,
-                       const __grid_constant__ CUtensorMap tmX, const float* __restrict__ bias_p,
-                       float* __restrict__ h_last, const int32_t* __restrict__ lengths, int B, int T, int n_ct_arg) {
-  static_assert(KX == 4, "a weight stage holds the 4 k-blocks of one half (x or h) of a chunk");
-  using Smem = FusedSmem<NXS, NWS>;
+                       const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                       const float* __restrict__ bias_p, float* __restrict__ h_last,
+                       const int32_t* __restrict__ lengths, int B, int T, int n_ct_arg) {
+  static_assert(KX % G == 0 && FHKB % G == 0, "a weight stage holds G k-blocks of one half (x or h) of a chunk");
+  static_assert(NXS > KX, "x ring: a whole step plus at least one slot to load ahead into");
+  using Smem = FusedSmem<NXS, NWS, G, HSEQ ? 2 : 0>;
   const int ctile = min((int)blockIdx.x, n_ct_arg - 1);
   const bool writer = (int)blockIdx.x < n_ct_arg;
   const uint32_t crank = cluster_ctarank();
@@ -96,6 +105,7 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
     for (int b = 0; b < 2; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 16 * 2); }
     for (int k = 0; k < FHKB; ++k) mbar_init(&sm.h_ready[k], 32 * 2);   // 16 epilogue warps x 2 chunks x 2 CTAs
     for (int s = 0; s < NXS; ++s) { mbar_init(&sm.x_full[s], 1); mbar_init(&sm.x_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.hs_done[b], 32); mbar_init(&sm.hs_free[b], 1); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_pair(&sm.tmem_base, 512); tmem_relinquish_pair(); }
@@ -104,99 +114,132 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
   cluster_sync_all();                          // both CTAs' barriers are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  constexpr uint32_t W_STAGE_BYTES = 2u * 4u * 64u * 64u * (uint32_t)sizeof(__half);   // both CTAs' halves
+  constexpr uint32_t W_STAGE_BYTES = 2u * G * 64u * 64u * (uint32_t)sizeof(__half);   // both CTAs' halves
   constexpr uint32_t X_SLOT_BYTES = 2u * FB * 64u * (uint32_t)sizeof(__half);
+  constexpr int XST = KX / G, HST = FHKB / G;  // weight stages of the x half / the h half of a chunk
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 0) {
-    // ---- weight producer (both CTAs): per (t, c) the x half (W_ih rows of chunk c), then the h half (W_hh; none at t = 0)
-    if (lane == 0) {
-      const uint32_t full0 = cluster_map_shared(&sm.w_full[0], 0);      // the leader's w_full[] barriers
-      uint32_t it = 0;
-      for (int t = 0; t < T; ++t)
-        for (int c = 0; c < FNC; ++c)
-          for (int half = 0; half < (t == 0 ? 1 : 2); ++half, ++it) {
-            const int s = it % NWS;
-            mbar_wait(&sm.w_empty[s], ((it / NWS) & 1) ^ 1);
-            if (leader) mbar_expect_tx(&sm.w_full[s], W_STAGE_BYTES);
-            const CUtensorMap* tm = half == 0 ? &tmWi : &tmWh;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ---- weight producer (both CTAs): per (t, c) the x half (W_ih rows of chunk c), then the h half (W_hh; none at t = 0)
+      if (lane == 0) {
+        const uint32_t full0 = cluster_map_shared(&sm.w_full[0], 0);      // the leader's w_full[] barriers
+        int s = 0;
+        uint32_t ph = 1;                        // parity to wait for on w_empty[s]
+        for (int t = 0; t < T; ++t)
+          for (int c = 0; c < FNC; ++c) {
+            const int nst = t == 0 ? XST : XST + HST;
+            for (int st = 0; st < nst; ++st) {
+              mbar_wait(&sm.w_empty[s], ph);
+              if (leader) mbar_expect_tx(&sm.w_full[s], W_STAGE_BYTES);
+              const CUtensorMap* tm = st < XST ? &tmWi : &tmWh;
+              const int kb0 = (st < XST ? st : st - XST) * G;
 #pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
-              tma_load_2d_pair(sm.wB[s][kb], tm, full0 + (uint32_t)s * 8u, kb * 64, c * FN + (int)crank * 64);
+              for (int j = 0; j < G; ++j)
+                tma_load_2d_pair(sm.wB[s][j], tm, full0 + (uint32_t)s * 8u, (kb0 + j) * 64, c * FN + (int)crank * 64);
+              if (++s == NWS) { s = 0; ph ^= 1u; }
+            }
           }
-    }
-  } else if (warp == 2) {
-    // ---- x producer (both CTAs): k-block kb of step t -> slot (t * KX + kb) % NXS, as far ahead as slots are free
-    if (lane == 0) {
-      tma_prefetch_desc(&tmX);
-      const uint32_t xfull0 = cluster_map_shared(&sm.x_full[0], 0);
-      uint32_t xi = 0;
-      for (int t = 0; t < T; ++t)
-        for (int kb = 0; kb < KX; ++kb, ++xi) {
-          const int slot = xi % NXS;
-          mbar_wait(&sm.x_empty[slot], ((xi / NXS) & 1) ^ 1);
-          if (leader) mbar_expect_tx(&sm.x_full[slot], X_SLOT_BYTES);
-          tma_load_2d_pair(sm.xA[slot], &tmX, xfull0 + (uint32_t)slot * 8u, kb * 64, (t * n_ct_arg + ctile) * FB);
-        }
-    }
-  } else if (warp == 1) {
-    if (leader) {                               // the whole warp, converged; one elected lane issues
-      constexpr uint32_t idesc = umma_idesc(FMT_F16, 2 * FB, FN);
-      uint32_t it = 0, xi0 = 0;
-      for (int t = 0; t < T; ++t, xi0 += KX) {
-        const uint32_t hsrc = tmem + FCOL_H + (uint32_t)(t & 1) * 128u;     // h_{t-1}
+      }
+    } else if (warp == 2) {
+      // ---- x producer (both CTAs): k-block kb of step t -> slot (t * KX + kb) % NXS, as far ahead as slots are free
+      if (lane == 0) {
+        tma_prefetch_desc(&tmX);
+        const uint32_t xfull0 = cluster_map_shared(&sm.x_full[0], 0);
+        int slot = 0;
+        uint32_t ph = 1;
+        for (int t = 0; t < T; ++t)
+          for (int kb = 0; kb < KX; ++kb) {
+            mbar_wait(&sm.x_empty[slot], ph);
+            if (leader) mbar_expect_tx(&sm.x_full[slot], X_SLOT_BYTES);
+            tma_load_2d_pair(sm.xA[slot], &tmX, xfull0 + (uint32_t)slot * 8u, kb * 64, (t * n_ct_arg + ctile) * FB);
+            if (++slot == NXS) { slot = 0; ph ^= 1u; }
+          }
+      }
+    } else if (warp == 1) {
+      if (leader) {                             // the whole warp, converged; one elected lane issues
+        constexpr uint32_t idesc = umma_idesc(FMT_F16, 2 * FB, FN);
+        int s = 0, xbase = 0;                   // weight stage; slot of x_t's k-block 0
+        uint32_t wph = 0, xph = 0;              // parities of w_full[s] / of x_full[xbase]
+        for (int t = 0; t < T; ++t) {
+          const uint32_t hsrc = tmem + FCOL_H + (uint32_t)(t & 1) * 128u;     // h_{t-1}
 #pragma unroll 1
-        for (int c = 0; c < FNC; ++c) {
-          const int b = c & 1;
-          // buffer b is used FNC / 2 = 4 times per step: the parity of its use count at chunk c is (c >> 1) & 1
-          mbar_wait_cluster(&sm.acc_empty[b], (uint32_t)((c >> 1) & 1) ^ 1u);
-          const uint32_t acc = tmem + (uint32_t)(b * FN);
-          {                                     // x half: A = x_t (shared memory), B = W_ih rows of chunk c
-            const int s = it % NWS;
-            mbar_wait(&sm.w_full[s], (it / NWS) & 1);
+          for (int c = 0; c < FNC; ++c) {
+            const int b = c & 1;
+            // buffer b is used FNC / 2 = 4 times per step: the parity of its use count at chunk c is (c >> 1) & 1
+            mbar_wait_cluster(&sm.acc_empty[b], (uint32_t)((c >> 1) & 1) ^ 1u);
             tc_fence_after();
+            const uint32_t acc = tmem + (uint32_t)(b * FN);
 #pragma unroll
-            for (int kb = 0; kb < KX; ++kb) {
-              const uint32_t xi = xi0 + kb;
-              const int slot = xi % NXS;
-              if (c == 0) {
-                mbar_wait(&sm.x_full[slot], (xi / NXS) & 1);
-                tc_fence_after();
+            for (int st = 0; st < XST; ++st) {  // x half: A = x_t (shared memory), B = W_ih rows of chunk c
+              mbar_wait(&sm.w_full[s], wph);
+              tc_fence_after();
+#pragma unroll
+              for (int j = 0; j < G; ++j) {
+                const int kb = st * G + j;
+                int slot = xbase + kb;
+                uint32_t ph = xph;
+                if (slot >= NXS) { slot -= NXS; ph ^= 1u; }
+                if (c == 0) {
+                  mbar_wait(&sm.x_full[slot], ph);
+                  tc_fence_after();
+                }
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sm.xA[slot]));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s][j]));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_pair_elect(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                if (c == FNC - 1) umma_commit_pair_mc_elect(&sm.x_empty[slot], 3);   // last reader of x_t's k-block
               }
-              const uint64_t adesc = umma_desc_sw128(smem_u32(sm.xA[slot]));
-              const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s][kb]));
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_pair_elect(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-              if (c == FNC - 1) umma_commit_pair_mc_elect(&sm.x_empty[slot], 3);   // last reader of x_t's k-block
+              umma_commit_pair_mc_elect(&sm.w_empty[s], 3);
+              if (++s == NWS) { s = 0; wph ^= 1u; }
             }
-            umma_commit_pair_mc_elect(&sm.w_empty[s], 3);
-            ++it;
-          }
-          if (t > 0) {                          // h half: A = h_{t-1} (tensor memory), B = W_hh rows of chunk c
-            const int s = it % NWS;
-            mbar_wait(&sm.w_full[s], (it / NWS) & 1);
-            tc_fence_after();
+            if (t > 0) {                        // h half: A = h_{t-1} (tensor memory), B = W_hh rows of chunk c
 #pragma unroll
-            for (int kb = 0; kb < FHKB; ++kb) {
-              if (c == 0) {
-                mbar_wait_cluster(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+              for (int st = 0; st < HST; ++st) {
+                mbar_wait(&sm.w_full[s], wph);
                 tc_fence_after();
-              }
-              const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s][kb]));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_pair_ts_elect(acc, hsrc + (uint32_t)(kb * 32 + k * 8), bdesc + 2 * k, idesc, true);
+                for (int j = 0; j < G; ++j) {
+                  const int kb = st * G + j;
+                  if (c == 0) {
+                    mbar_wait_cluster(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
+                    tc_fence_after();
+                  }
+                  const uint64_t bdesc = umma_desc_sw128(smem_u32(sm.wB[s][j]));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_pair_ts_elect(acc, hsrc + (uint32_t)(kb * 32 + k * 8), bdesc + 2 * k, idesc, true);
+                }
+                umma_commit_pair_mc_elect(&sm.w_empty[s], 3);
+                if (++s == NWS) { s = 0; wph ^= 1u; }
+              }
             }
-            umma_commit_pair_mc_elect(&sm.w_empty[s], 3);
-            ++it;
+            umma_commit_pair_mc_elect(&sm.acc_full[b], 3);
           }
-          umma_commit_pair_mc_elect(&sm.acc_full[b], 3);
+          xbase += KX;
+          if (xbase >= NXS) { xbase -= NXS; xph ^= 1u; }
         }
       }
+    } else if (HSEQ) {
+      // ---- store warp: k-block kb of h_t (128 clips x 64 units, swizzled like a TMA box) -> the time-major fp16 sequence
+      if (lane == 0) tma_prefetch_desc(&tmH);
+      for (int t = 0; t < T; ++t)
+        for (int kb = 0; kb < FHKB; ++kb) {
+          const int buf = kb & 1;
+          mbar_wait(&sm.hs_done[buf], (uint32_t)(kb >> 1) & 1);            // two uses of a buffer per step
+          if (lane == 0) {
+            if (writer) {
+              tma_store_2d(&tmH, sm.hS[buf], kb * 64, (t * n_ct_arg + ctile) * FB);
+              tma_store_commit();
+              tma_store_wait_read0();
+            }
+            mbar_arrive(&sm.hs_free[buf]);
+          }
+          __syncwarp();
+        }
+      if (lane == 0) tma_store_wait0();
     }
-  }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ---- 16 epilogue warps = (TMEM lane quarter) x (quarter q of a chunk); thread (clip r, q) owns units
@@ -211,13 +254,14 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
     const uint32_t acc_empty_addr0 = cluster_map_shared(&sm.acc_empty[0], 0);
     const uint32_t h_ready_addr0 = cluster_map_shared(&sm.h_ready[0], 0);
     const float4* const bias4 = reinterpret_cast<const float4*>(bias_p) + q * 8;
+    unsigned char* const hs_row = reinterpret_cast<unsigned char*>(&sm.hS[0][0]) + (size_t)r * 128;
     float cs[FNC * 8];
 #pragma unroll
     for (int i = 0; i < FNC * 8; ++i) cs[i] = 0.f;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const uint32_t hdst = tlane + FCOL_H + (uint32_t)((t + 1) & 1) * 128u + (uint32_t)(q * 4);
-      const bool emit = live && h_last && t == last_t;
+      const bool emit = !HSEQ && live && h_last && t == last_t;
 #pragma unroll
       for (int c = 0; c < FNC; ++c) {
         const int b = c & 1;
@@ -260,10 +304,25 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
         }
         tmem_st4(hdst + (uint32_t)(c * 16), pk);             // units 32 c + 8 q .. + 7 = columns 16 c + 4 q .. + 3
         if (emit) stg256f(h_last + (size_t)clip * FH + c * FCH + q * 8, hn);
+        if (HSEQ) {
+          // the same 16 bytes into the staging tile of k-block c / 2 (buffer (c / 2) & 1), XOR-swizzled by the row
+          const int buf = (c >> 1) & 1, use = c >> 2;          // second half of the step = second use of the buffer
+          if ((c & 1) == 0) {
+            if (use == 0) { if (t > 0) mbar_wait(&sm.hs_free[buf], 1u); }   // freed after use 1 of step t - 1
+            else mbar_wait(&sm.hs_free[buf], 0u);                           // freed after use 0 of this step
+          }
+          const int chunk16 = (c & 1) * 4 + q;                 // 16-byte chunk of the 128-byte row: units (c & 1) 32 + 8 q
+          *reinterpret_cast<uint4*>(hs_row + (size_t)buf * (FB * 128) + ((chunk16 ^ (r & 7)) << 4)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          fence_proxy_async_smem();
+        }
         tmem_st_wait_f();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(h_ready_addr0 + (uint32_t)(c >> 1) * 8u);
+        if (lane == 0) {
+          mbar_arrive_cluster(h_ready_addr0 + (uint32_t)(c >> 1) * 8u);
+          if (HSEQ) mbar_arrive(&sm.hs_done[(c >> 1) & 1]);
+        }
       }
     }
   }
@@ -273,39 +332,17 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
   if (warp == 1) tmem_dealloc_pair(tmem, 512);
 }
 
-// w (4H, K) fp32 -> out (4H, K) fp16 in the packed row order of the kernel above, sigmoid gates halved;
-// bias (4H) fp32 (b_ih + b_hh) -> the same order and scaling
-__global__ void pack_fused_w_kernel(const float* __restrict__ w, __half* __restrict__ out, int K) {
-  const int p = blockIdx.x;                     // packed row
-  const int c = p >> 7, qq = (p >> 5) & 3, hf = (p >> 4) & 1, g = (p >> 2) & 3, i = p & 3;
-  const float* src = w + (size_t)(g * FH + c * FCH + qq * 8 + hf * 4 + i) * K;
-  const float sc = g == 2 ? 1.f : 0.5f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) out[(size_t)p * K + k] = __float2half_rn(sc * src[k]);
-}
-__global__ void pack_fused_bias_kernel(const float* __restrict__ bias, float* __restrict__ out) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= 4 * FH) return;
-  const int c = p >> 7, qq = (p >> 5) & 3, hf = (p >> 4) & 1, g = (p >> 2) & 3, i = p & 3;
-  out[p] = (g == 2 ? 1.f : 0.5f) * bias[g * FH + c * FCH + qq * 8 + hf * 4 + i];
-}
-
 }  // namespace tc
 
-int lstm_fused_pack(const float* w_ih, int K, const float* w_hh, const float* bias, void* w_ih_p16, void* w_hh_p16,
-                    float* bias_p, cudaStream_t s) {
-  tc::pack_fused_w_kernel<<<4 * tc::FH, 128, 0, s>>>(w_ih, reinterpret_cast<__half*>(w_ih_p16), K);
-  AVHOT_LAUNCH_CHECK();
-  tc::pack_fused_w_kernel<<<4 * tc::FH, 128, 0, s>>>(w_hh, reinterpret_cast<__half*>(w_hh_p16), tc::FH);
-  AVHOT_LAUNCH_CHECK();
-  tc::pack_fused_bias_kernel<<<4, 256, 0, s>>>(bias, bias_p);
-  AVHOT_LAUNCH_CHECK();
-  return AVHOT_OK;
-}
-
 namespace {
-constexpr int kNXS = 8, kNWS = 3;
-using FusedK4 = tc::FusedSmem<kNXS, kNWS>;
-bool fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_ct, int smem, cudaStream_t s) {
+// KX = 5 with a hidden sequence out (layer 0 on the front-end's split operand), KX = 4 top layer, KX = 4 middle layer
+template <int KX, bool HSEQ> struct FusedCfg;
+template <> struct FusedCfg<5, true> { static constexpr int NXS = 7, NWS = 10, G = 1; };
+template <> struct FusedCfg<5, false> { static constexpr int NXS = 8, NWS = 12, G = 1; };
+template <> struct FusedCfg<4, false> { static constexpr int NXS = 8, NWS = 3, G = 4; };
+template <> struct FusedCfg<4, true> { static constexpr int NXS = 8, NWS = 4, G = 2; };
+
+void fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_ct, int smem, cudaStream_t s) {
   cfg = {};
   cfg.gridDim = dim3((unsigned)(ceil_div(n_ct, 2) * 2));
   cfg.blockDim = dim3(tc::FTHREADS);
@@ -317,18 +354,12 @@ bool fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return true;
 }
-}  // namespace
 
-// can the fused kernel take this layer?  (x operand 256 wide, every CTA pair co-resident: one CTA per SM)
-bool lstm_fused_tc_supported(int in_dim, int B) {
-  static const int forced = [] { const char* e = getenv("AVHOT_LSTM_FUSED"); return e ? atoi(e) : -1; }();
-  if (forced == 0 || in_dim != tc::FH) return false;
-  const int n_ct = ceil_div(B, tc::FB);
-  if (n_ct < 2) return false;
-  auto kern = tc::lstm_fused_pair_kernel<4, kNXS, kNWS>;
-  const int smem = (int)sizeof(FusedK4) + 1024;
+template <int KX, bool HSEQ> bool fused_fits(int n_ct) {
+  using C = FusedCfg<KX, HSEQ>;
+  auto kern = tc::lstm_fused_pair_kernel<KX, C::NXS, C::NWS, C::G, HSEQ>;
+  const int smem = (int)sizeof(tc::FusedSmem<C::NXS, C::NWS, C::G, HSEQ ? 2 : 0>) + 1024;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     cudaGetLastError();
     return false;
@@ -341,30 +372,67 @@ bool lstm_fused_tc_supported(int in_dim, int B) {
   return n * 2 >= ceil_div(n_ct, 2) * 2;
 }
 
-// x_f16: (T, Bp, x_pitch) fp16 time-major sequence (Bp = B rounded up to 128), 256 features; h_last (B, 256) fp32 =
-// the layer's hidden state at step lengths[b] - 1
-int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_pitch,
-                        float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
+template <int KX, bool HSEQ>
+int fused_launch(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_pitch,
+                 void* h_seq_f16, int h_pitch, float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
   using namespace tc;
+  using C = FusedCfg<KX, HSEQ>;
   const int n_ct = ceil_div(B, FB);
-  const int smem = (int)sizeof(FusedK4) + 1024;
-  AVHOT_REQUIRE(x_pitch >= FH && (x_pitch & 7) == 0, AVHOT_ERR_INVALID, "lstm_layer_fused_tc: bad x pitch %d", x_pitch);
-  CUtensorMap tmWi, tmWh, tmX;
-  int rc = make_tensor_map_2d(&tmWi, w_ih_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, FH, FH, 64, 64);
+  const int smem = (int)sizeof(FusedSmem<C::NXS, C::NWS, C::G, HSEQ ? 2 : 0>) + 1024;
+  CUtensorMap tmWi, tmWh, tmX, tmH;
+  int rc = make_tensor_map_2d(&tmWi, w_ih_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, KX * 64, KX * 64, 64, 64);
   if (rc == AVHOT_OK) rc = make_tensor_map_2d(&tmWh, w_hh_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, FH, FH, 64, 64);
   if (rc == AVHOT_OK)
-    rc = make_tensor_map_2d(&tmX, x_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)T * n_ct * FB, FH, (uint64_t)x_pitch,
-                            FB, 64);
+    rc = make_tensor_map_2d(&tmX, x_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)T * n_ct * FB, KX * 64,
+                            (uint64_t)x_pitch, FB, 64);
+  tmH = tmX;                                    // unused without an output sequence
+  if (rc == AVHOT_OK && HSEQ)
+    rc = make_tensor_map_2d(&tmH, h_seq_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)T * n_ct * FB, FH,
+                            (uint64_t)h_pitch, FB, 64);
   if (rc != AVHOT_OK) return rc;
-  auto kern = lstm_fused_pair_kernel<4, kNXS, kNWS>;
+  auto kern = lstm_fused_pair_kernel<KX, C::NXS, C::NWS, C::G, HSEQ>;
   AVHOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fused_cluster_cfg(cfg, attr, n_ct, smem, s);
   ProfScope prof("lstm_layer_fused_tc", s);
-  AVHOT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmWi, tmWh, tmX, bias_p, h_last, lengths, B, T, n_ct));
+  AVHOT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmWi, tmWh, tmX, tmH, bias_p, h_last, lengths, B, T, n_ct));
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
+}
+}  // namespace
+
+// can the fused kernel take this layer?  x operand of 5 (the split of <= 104 features) or 4 (a hidden sequence)
+// k-blocks, every CTA pair co-resident (one CTA per SM).  AVHOT_LSTM_FUSED=0 switches it off, =1 top layer only.
+bool lstm_fused_tc_supported(int x_cols, bool hseq, int B) {
+  static const int forced = [] { const char* e = getenv("AVHOT_LSTM_FUSED"); return e ? atoi(e) : -1; }();
+  if (forced == 0 || (forced == 1 && hseq)) return false;
+  const int n_ct = ceil_div(B, tc::FB);
+  if (n_ct < 2) return false;
+  if (x_cols == 320) return hseq ? fused_fits<5, true>(n_ct) : fused_fits<5, false>(n_ct);
+  if (x_cols == 256) return hseq ? fused_fits<4, true>(n_ct) : fused_fits<4, false>(n_ct);
+  return false;
+}
+
+// x_f16: (T, Bp, x_pitch) fp16 time-major operand (Bp = B rounded up to 128) of x_cols columns; weights / bias in the
+// packed row order (fused_src_row).  h_seq_f16 != NULL: the layer's hidden sequence (T, Bp, h_pitch) fp16 is stored;
+// else h_last (B, 256) fp32 = the hidden state at step lengths[b] - 1.
+int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_cols,
+                        int x_pitch, void* h_seq_f16, int h_pitch, float* h_last, const int32_t* lengths, int B, int T,
+                        cudaStream_t s) {
+  AVHOT_REQUIRE(x_pitch >= x_cols && (x_pitch & 7) == 0, AVHOT_ERR_INVALID, "lstm_layer_fused_tc: bad x pitch %d", x_pitch);
+  AVHOT_REQUIRE(!h_seq_f16 || (h_pitch >= tc::FH && (h_pitch & 7) == 0), AVHOT_ERR_INVALID,
+                "lstm_layer_fused_tc: bad h_seq pitch %d", h_pitch);
+  AVHOT_REQUIRE(h_seq_f16 || h_last, AVHOT_ERR_INVALID, "lstm_layer_fused_tc: no output");
+#define AVHOT_FUSED_CASE(KX_, HS_) \
+  return fused_launch<KX_, HS_>(w_ih_p16, w_hh_p16, bias_p, x_f16, x_pitch, h_seq_f16, h_pitch, h_last, lengths, B, T, s)
+  if (x_cols == 320 && h_seq_f16) AVHOT_FUSED_CASE(5, true);
+  if (x_cols == 320) AVHOT_FUSED_CASE(5, false);
+  if (x_cols == 256 && h_seq_f16) AVHOT_FUSED_CASE(4, true);
+  if (x_cols == 256) AVHOT_FUSED_CASE(4, false);
+#undef AVHOT_FUSED_CASE
+  set_error("lstm_layer_fused_tc: x operand of %d columns", x_cols);
+  return AVHOT_ERR_UNSUPPORTED;
 }
 
 }  // namespace avhot

@@ -8,8 +8,9 @@ import multimodal_emotion_detection_b200 as pkg
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+L = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 torch.manual_seed(0)
-enc = pkg.SequenceEncoder(104, 256, 128, 2, "lstm").to("cuda:0").eval()
+enc = pkg.SequenceEncoder(104, 256, 128, L, "lstm").to("cuda:0").eval()
 rng = np.random.default_rng(5)
 x = torch.from_numpy(rng.normal(size=(B, T, 104)).astype(np.float32)).to("cuda:0")
 lengths = torch.from_numpy(rng.integers(1, T + 1, size=B))
@@ -20,4 +21,4 @@ enc.precision = pkg._lib.PREC_FP32
 ref = enc(x, lengths)
 torch.cuda.synchronize()
 err = (out - ref).abs().max().item() / ref.abs().max().item()
-print("B", B, "T", T, "rel err tc vs fp32:", err)
+print("B", B, "T", T, "L", L, "rel err tc vs fp32:", err)
