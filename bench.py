@@ -514,7 +514,7 @@ def rooflines(prof, args, B, ms, peaks):
     tc = args.precision == "tc"
     groups = {   # stage -> (kernels, bound, algorithmic bytes per step, algorithmic FLOPs per step)
         "frontend": (["frontend"], "hbm", B * BYTES_FRONTEND, 0),
-        "lstm": ((["lstm_split3", "lstm_input_gemm_tc", "lstm_recurrence_tc", "lstm_fused_tc"] if tc else
+        "lstm": ((["lstm_split3", "lstm_layer_fused_tc", "lstm_input_gemm_tc", "lstm_recurrence_tc"] if tc else
                   ["lstm_input_gemm", "lstm_recurrence"]) + ["lstm_projection"], "tensor", B * BYTES_LSTM, B * FLOPS_LSTM),
         "video": (["frame_u8_to_f32", "frame_gemm"], "hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
         "mc_tail": (["frame_tail", "fusion_clip", "fusion_tc", "mc_reduce"] + ([] if tc else ["fusion_pass", "hybrid_fusion"]),
@@ -551,7 +551,7 @@ def rooflines(prof, args, B, ms, peaks):
         "frame_gemm": ("hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
         "lstm_recurrence_tc": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
         "lstm_input_gemm_tc": ("tensor", 0, B * (537_542_656 - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
-        "lstm_fused_tc": ("tensor", 0, B * 537_542_656),
+        "lstm_layer_fused_tc": ("tensor", 0, B * 537_542_656),
         "lstm_recurrence": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
         "lstm_input_gemm": ("tensor", 0, B * (537_542_656 - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
         "fusion_tc": ("tensor", 0, B * args.passes * 1_841_664),

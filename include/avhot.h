@@ -141,6 +141,13 @@ int avhot_lstm_split_pitch(avhot_lstm_t h);
 int avhot_lstm_forward_split(avhot_lstm_t h, const void* seq_split_f16, const int32_t* lengths, float* out,
                              int B, int T, void* workspace, size_t workspace_bytes, avhot_stream_t stream);
 
+/* The same for an operand written by avhot_frontend_ex (input_dim 104 = 64 log-mel + 40 MFCC): its MFCC columns are the
+ * front-end's DCT matrix times its log-mel columns, so layer 0 multiplies the log-mel k-blocks alone by
+ * W_ih[:, :64] + W_ih[:, 64:] D (folded once per handle, fp32-class): K = 192 instead of 320.  Same result as
+ * avhot_lstm_forward_split within fp32 rounding of the MFCC; AVHOT_LSTM_DCT_FOLD=0 routes it to that call. */
+int avhot_lstm_forward_frontend(avhot_lstm_t h, const void* seq_split_f16, const int32_t* lengths, float* out,
+                                int B, int T, void* workspace, size_t workspace_bytes, avhot_stream_t stream);
+
 /* ---- src/encoders.py:65-77, :137-155  SequenceEncoder(encoder_type='gru') ---------- */
 /* Same descriptor as the LSTM with nn.GRU's tensors: weight_ih_l{k} (3H, in_k), weight_hh_l{k} (3H, H), bias_ih /
  * bias_hh (3H), gate rows r, z, n.  fp32 path; lengths as in avhot_lstm_forward. */

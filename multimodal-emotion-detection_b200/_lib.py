@@ -140,6 +140,7 @@ PROTOTYPES = {
     "avhot_gru_forward": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "avhot_lstm_split_pitch": (_I, [_P]),
     "avhot_lstm_forward_split": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "avhot_lstm_forward_frontend": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "avhot_frame_create": (_I, [C.POINTER(FrameDesc), C.POINTER(_P), _P]),
     "avhot_frame_destroy": (None, [_P]),
     "avhot_frame_workspace_bytes": (_SZ, [_P, _I, _I, _I]),

@@ -15,6 +15,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 struct avhot_lstm {
@@ -29,6 +31,8 @@ struct avhot_lstm {
   void* w_ih_p16[4];  // layers > 0: fp16 W_ih / W_hh / fp32 bias in the fused layer kernel's row order (lstm_fused.cu)
   void* w_hh_p16[4];
   float* bias_p[4];
+  void* w_ih_fold_p16; // layer 0, (4H, 192) = [W'_hi | W'_hi | W'_lo], W' = W[:, :64] + W[:, 64:104] D: the MFCC columns of the
+                       // front-end's operand are D x its log-mel columns, so their weights fold into the log-mel ones
   float* proj_w;     // (out, H)
   float* proj_b;
   float* arena;
@@ -247,6 +251,35 @@ static inline int pad8(int k) { return (k + 7) & ~7; }   // fp16 row pitch: mult
 
 using namespace avhot;
 
+// The front-end's 40 MFCC are its 64 log-mel values times the DCT matrix D (frontend.cu; a3's input is
+// [log-mel | MFCC]), so on the operand avhot_frontend_ex writes, x W_ih^T = lm (W[:, :64] + W[:, 64:] D)^T: layer 0 needs
+// only the three log-mel k-blocks [lm_hi | lm_lo | lm_hi] (K = 192 instead of 320) against W' split the same way.
+// W' is formed in double on the host, once per handle (fp32-class like the 3-term product itself).
+static int lstm_build_dct_fold(avhot_lstm* h, const float* w_ih0_dev, cudaStream_t s) {
+  const int H = h->hidden_dim, N = 4 * H, NM = 64, NC = 40;
+  std::vector<float> w((size_t)N * (NM + NC)), dct((size_t)NC * NM);
+  int rc = avhot_frontend_tables_host(nullptr, dct.data(), nullptr);
+  if (rc != AVHOT_OK) return rc;
+  AVHOT_CUDA(cudaMemcpyAsync(w.data(), w_ih0_dev, sizeof(float) * w.size(), cudaMemcpyDeviceToHost, s));
+  AVHOT_CUDA(cudaStreamSynchronize(s));
+  std::vector<__half> out((size_t)N * 192);
+  for (int p = 0; p < N; ++p) {
+    const int n = lstm_fused_src_row(p, H);
+    const double sc = (n / H) == 2 ? 1.0 : 0.5;            // sigmoid gates halved (tc_gate_scale)
+    for (int j = 0; j < NM; ++j) {
+      double v = w[(size_t)n * (NM + NC) + j];
+      for (int c = 0; c < NC; ++c) v += (double)w[(size_t)n * (NM + NC) + NM + c] * (double)dct[(size_t)c * NM + j];
+      const float f = (float)(sc * v);
+      const __half hi = __float2half_rn(f);
+      out[(size_t)p * 192 + j] = out[(size_t)p * 192 + 64 + j] = hi;
+      out[(size_t)p * 192 + 128 + j] = __float2half_rn(f - __half2float(hi));
+    }
+  }
+  AVHOT_CUDA(cudaMemcpyAsync(h->w_ih_fold_p16, out.data(), sizeof(__half) * out.size(), cudaMemcpyHostToDevice, s));
+  AVHOT_CUDA(cudaStreamSynchronize(s));                    // `out` is pageable host memory
+  return AVHOT_OK;
+}
+
 extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, avhot_stream_t stream) {
   AVHOT_REQUIRE(d && out, AVHOT_ERR_INVALID, "lstm_create: null argument");
   AVHOT_REQUIRE(d->num_layers >= 1 && d->num_layers <= 4, AVHOT_ERR_INVALID,
@@ -275,6 +308,8 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   avhot_lstm* h = new avhot_lstm();
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
+  h->w_ih_fold_p16 = nullptr;
+  total += align256(2 * 4 * H * 192);
   cudaError_t e = cudaMalloc(&h->arena, total);
   if (e != cudaSuccess) {
     delete h;
@@ -315,6 +350,10 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     scale_gate_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, s>>>(h->bias[l], h->bias_p[l], 4 * H, true);
     if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
   }
+  if (rc == AVHOT_OK && d->input_dim == 104) {
+    h->w_ih_fold_p16 = take(2 * 4 * H * 192);
+    rc = lstm_build_dct_fold(h, d->weight_ih[0], s);
+  }
   if (rc == AVHOT_OK) {
     h->proj_w = take(sizeof(float) * d->output_dim * H);
     h->proj_b = take(sizeof(float) * d->output_dim);
@@ -341,13 +380,23 @@ extern "C" void avhot_lstm_destroy(avhot_lstm_t h) {
 }
 
 // workspace (fp32 path): xp (B*T*4H) + h_seq (B*T*H) + h_last (B*H)
-// workspace: xp (Bp*T*4H fp32) + h_seq (Bp*T*H fp32 / fp16) + h_last (B*H) [+ fp16 split of the input, TC path];
+// workspace: xp (Bp*T*4H fp32; none on the TC path when every layer runs fused) + h_seq (Bp*T*H fp32 / fp16) + h_last (B*H) [+ fp16 split of the input, TC path];
 // Bp = B rounded up to the 128-clip tile of the tensor-core kernels
+// does every layer of the stack run as the fused kernel (lstm_fused.cu) at this batch?  Then no xp buffer is needed.
+static bool lstm_all_fused(avhot_lstm_t h, int B) {
+  for (int l = 0; l < h->num_layers; ++l)
+    if (!lstm_fused_tc_supported(l == 0 ? pad8(3 * h->input_dim + 2) : h->hidden_dim, l + 1 < h->num_layers, B)) return false;
+  return true;
+}
+static size_t lstm_xp_bytes(avhot_lstm_t h, size_t Bp, int B, int T, int precision) {
+  if (precision == AVHOT_PREC_TC && lstm_all_fused(h, B)) return 0;
+  return align256(sizeof(float) * Bp * T * 4 * h->hidden_dim);
+}
 extern "C" size_t avhot_lstm_workspace_bytes(avhot_lstm_t h, int B, int T, int precision) {
   if (!h || B <= 0 || T <= 0) return 0;
   const size_t H = h->hidden_dim;
   const size_t Bp = ((size_t)B + 127) / 128 * 128;
-  size_t n = align256(sizeof(float) * Bp * T * 4 * H) + align256(sizeof(float) * Bp * T * H) +
+  size_t n = lstm_xp_bytes(h, Bp, B, T, precision) + align256(sizeof(float) * Bp * T * H) +
              align256(sizeof(float) * (size_t)B * H);
   if (precision == AVHOT_PREC_TC) n += align256(2 * Bp * T * (size_t)pad8(3 * h->input_dim + 2));   // fp16 split of the input
   return n;
@@ -357,7 +406,7 @@ extern "C" int avhot_lstm_split_pitch(avhot_lstm_t h) { return h ? pad8(3 * h->i
 
 static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_split, const int32_t* lengths, float* out,
                              int B, int T, int precision, void* workspace, size_t workspace_bytes,
-                             avhot_stream_t stream);
+                             avhot_stream_t stream, bool frontend_operand = false);
 
 extern "C" int avhot_lstm_forward(avhot_lstm_t h, const float* seq, const int32_t* lengths, float* out, int B,
                                   int T, int precision, void* workspace, size_t workspace_bytes,
@@ -373,8 +422,17 @@ extern "C" int avhot_lstm_forward_split(avhot_lstm_t h, const void* seq_split_f1
                            stream);
 }
 
+extern "C" int avhot_lstm_forward_frontend(avhot_lstm_t h, const void* seq_split_f16, const int32_t* lengths, float* out,
+                                           int B, int T, void* workspace, size_t workspace_bytes,
+                                           avhot_stream_t stream) {
+  AVHOT_REQUIRE(seq_split_f16, AVHOT_ERR_INVALID, "lstm_forward_frontend: operand is NULL");
+  return lstm_forward_impl(h, nullptr, seq_split_f16, lengths, out, B, T, AVHOT_PREC_TC, workspace, workspace_bytes,
+                           stream, true);
+}
+
 static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_split, const int32_t* lengths, float* out,
-                             int B, int T, int precision, void* workspace, size_t workspace_bytes, avhot_stream_t stream) {
+                             int B, int T, int precision, void* workspace, size_t workspace_bytes, avhot_stream_t stream,
+                             bool frontend_operand) {
   AVHOT_REQUIRE(h && (seq || seq_split) && out && B >= 0 && T >= 1, AVHOT_ERR_INVALID, "lstm_forward: bad arguments");
   AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
                 "lstm_forward: precision %d not built", precision);
@@ -387,7 +445,7 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
   cudaStream_t s = as_stream(stream);
   char* p = reinterpret_cast<char*>(workspace);
   const size_t Bp = ((size_t)B + 127) / 128 * 128;
-  float* xp = reinterpret_cast<float*>(p); p += align256(sizeof(float) * Bp * T * 4 * H);
+  float* xp = reinterpret_cast<float*>(p); p += lstm_xp_bytes(h, Bp, B, T, precision);   // unused when every layer is fused
   float* h_seq = reinterpret_cast<float*>(p); p += align256(sizeof(float) * Bp * T * H);
   float* h_last = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)B * H);
   __half* x_split = reinterpret_cast<__half*>(p);   // TC path only
@@ -415,6 +473,15 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
       const void* x_op = l > 0 ? (const void*)h_seq : seq_split ? seq_split : (const void*)x_split;
       const int x_cols = l == 0 ? pad8(3 * in + 2) : H;
       const bool fused = lstm_fused_tc_supported(x_cols, !last, B);
+      static const bool no_fold = [] { const char* e = getenv("AVHOT_LSTM_DCT_FOLD"); return e && atoi(e) == 0; }();
+      if (l == 0 && frontend_operand && seq_split && h->w_ih_fold_p16 && !no_fold &&
+          lstm_fused_tc_supported(192, !last, B)) {
+        // the operand's MFCC columns are the DCT of its log-mel columns: folded weights, the log-mel k-blocks only
+        rc = lstm_layer_fused_tc(h->w_ih_fold_p16, h->w_hh_p16[0], h->bias_p[0], seq_split, 192, x_cols,
+                                 last ? nullptr : (void*)h_seq, hp, hl_out, lengths, B, T, s);
+        if (rc != AVHOT_OK) return rc;
+        continue;
+      }
       if (l == 0 && !seq_split) {                     // (operand not prepared by avhot_frontend_ex)
         ProfScope prof("lstm_split3", s);
         const size_t smem = sizeof(float) * SPL_CB * SPL_TB * in;

@@ -40,7 +40,7 @@ constexpr int FB = 128, FH = 256, FCH = 32, FNC = FH / FCH, FN = 4 * FCH, FHKB =
 constexpr int FTHREADS = 128 + 512;            // warpgroup 0: producers + MMA (setmaxnreg 56), warpgroups 1-4: epilogue (104): 128 x 56 + 512 x 104 <= 640 x 96, the launch allocation
 constexpr uint32_t FCOL_H = 256;                 // first TMEM column of the hidden state (2 x 128 columns)
 
-template <int NXS, int NWS, int G, int NHS> struct FusedSmem {
+template <int NXS, int NWS, int G, int NHS> struct FusedSmem {   // G = k-blocks a weight stage can hold
   __half xA[NXS][FB * 64];          // x_t k-blocks, A operand: 128 rows x 128 B, 128-byte swizzle
   __half wB[NWS][G][64 * 64];       // weight stages: G k-blocks of (this CTA's 64 gate rows x 64 k), B operand
   __half hS[NHS ? NHS : 1][NHS ? FB * 64 : 8];   // HSEQ: k-blocks of h_t on their way out (TMA store source)
@@ -77,19 +77,20 @@ __device__ __forceinline__ void stg256f(float* p, const float (&v)[8]) {
                : "memory");
 }
 
-// KX: 64-column k-blocks of the x operand (5 = the [hi | lo | hi] split of 104 features, 4 = a 256-wide hidden
-// sequence).  G: k-blocks per weight stage (divides KX and 4).  HSEQ: the layer's fp16 hidden sequence is stored
+// KX: 64-column k-blocks of the x operand (5 = the [hi | lo | hi] split of 104 features, 3 = of the 64 log-mel features
+// alone with the MFCC's DCT folded into the weights, 4 = a 256-wide hidden sequence).  G: k-blocks per weight stage (divides KX and 4).  HSEQ: the layer's fp16 hidden sequence is stored
 // (time-major (T, Bp, pitch), rows of padding clips included) and h_last is not.  The sigmoid gates' weights and
 // biases are packed halved (tc_gate_scale in lstm.cu): sigmoid(x) = 0.5 + 0.5 tanh(x / 2), one MUFU per activation.
-template <int KX, int NXS, int NWS, int G, bool HSEQ>
+template <int KX, int NXS, int NWS, int GX, int GH, bool HSEQ>
 __global__ void __launch_bounds__(FTHREADS, 1)
 lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_constant__ CUtensorMap tmWh,
                        const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                        const float* __restrict__ bias_p, float* __restrict__ h_last,
                        const int32_t* __restrict__ lengths, int B, int T, int n_ct_arg) {
-  static_assert(KX % G == 0 && FHKB % G == 0, "a weight stage holds G k-blocks of one half (x or h) of a chunk");
+  static_assert(KX % GX == 0 && FHKB % GH == 0, "a weight stage holds GX / GH k-blocks of the x / h half of a chunk");
+  constexpr int G = GX > GH ? GX : GH;
   static_assert(NXS > KX, "x ring: a whole step plus at least one slot to load ahead into");
-  using Smem = FusedSmem<NXS, NWS, G, HSEQ ? 2 : 0>;
+  using Smem = FusedSmem<NXS, NWS, (GX > GH ? GX : GH), HSEQ ? 2 : 0>;
   const int ctile = min((int)blockIdx.x, n_ct_arg - 1);
   const bool writer = (int)blockIdx.x < n_ct_arg;
   const uint32_t crank = cluster_ctarank();
@@ -114,9 +115,9 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
   cluster_sync_all();                          // both CTAs' barriers are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  constexpr uint32_t W_STAGE_BYTES = 2u * G * 64u * 64u * (uint32_t)sizeof(__half);   // both CTAs' halves
+  constexpr uint32_t W_KB_BYTES = 2u * 64u * 64u * (uint32_t)sizeof(__half);   // one k-block, both CTAs' halves
   constexpr uint32_t X_SLOT_BYTES = 2u * FB * 64u * (uint32_t)sizeof(__half);
-  constexpr int XST = KX / G, HST = FHKB / G;  // weight stages of the x half / the h half of a chunk
+  constexpr int XST = KX / GX, HST = FHKB / GH;  // weight stages of the x half / the h half of a chunk
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -131,12 +132,14 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
             const int nst = t == 0 ? XST : XST + HST;
             for (int st = 0; st < nst; ++st) {
               mbar_wait(&sm.w_empty[s], ph);
-              if (leader) mbar_expect_tx(&sm.w_full[s], W_STAGE_BYTES);
-              const CUtensorMap* tm = st < XST ? &tmWi : &tmWh;
-              const int kb0 = (st < XST ? st : st - XST) * G;
+              const bool xh = st < XST;
+              if (leader) mbar_expect_tx(&sm.w_full[s], (xh ? GX : GH) * W_KB_BYTES);
+              const CUtensorMap* tm = xh ? &tmWi : &tmWh;
+              const int kb0 = xh ? st * GX : (st - XST) * GH;
 #pragma unroll
               for (int j = 0; j < G; ++j)
-                tma_load_2d_pair(sm.wB[s][j], tm, full0 + (uint32_t)s * 8u, (kb0 + j) * 64, c * FN + (int)crank * 64);
+                if (j < (xh ? GX : GH))
+                  tma_load_2d_pair(sm.wB[s][j], tm, full0 + (uint32_t)s * 8u, (kb0 + j) * 64, c * FN + (int)crank * 64);
               if (++s == NWS) { s = 0; ph ^= 1u; }
             }
           }
@@ -175,8 +178,8 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
               mbar_wait(&sm.w_full[s], wph);
               tc_fence_after();
 #pragma unroll
-              for (int j = 0; j < G; ++j) {
-                const int kb = st * G + j;
+              for (int j = 0; j < GX; ++j) {
+                const int kb = st * GX + j;
                 int slot = xbase + kb;
                 uint32_t ph = xph;
                 if (slot >= NXS) { slot -= NXS; ph ^= 1u; }
@@ -200,8 +203,8 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
                 mbar_wait(&sm.w_full[s], wph);
                 tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < G; ++j) {
-                  const int kb = st * G + j;
+                for (int j = 0; j < GH; ++j) {
+                  const int kb = st * GH + j;
                   if (c == 0) {
                     mbar_wait_cluster(&sm.h_ready[kb], (uint32_t)(t - 1) & 1);
                     tc_fence_after();
@@ -337,10 +340,22 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
 namespace {
 // KX = 5 with a hidden sequence out (layer 0 on the front-end's split operand), KX = 4 top layer, KX = 4 middle layer
 template <int KX, bool HSEQ> struct FusedCfg;
-template <> struct FusedCfg<5, true> { static constexpr int NXS = 7, NWS = 10, G = 1; };
-template <> struct FusedCfg<5, false> { static constexpr int NXS = 8, NWS = 12, G = 1; };
-template <> struct FusedCfg<4, false> { static constexpr int NXS = 8, NWS = 3, G = 4; };
-template <> struct FusedCfg<4, true> { static constexpr int NXS = 8, NWS = 4, G = 2; };
+template <> struct FusedCfg<5, true> { static constexpr int NXS = 7, NWS = 10, GX = 1, GH = 1; };
+template <> struct FusedCfg<5, false> { static constexpr int NXS = 8, NWS = 12, GX = 1, GH = 1; };
+// log-mel split only (DCT folded): whole halves of a chunk per stage (the MMA thread waits and commits twice per chunk;
+// per-k-block stages cost it ~45 cycles of tensor-pipe bubble each: 3.8 ms against 3.4 for this layer)
+template <> struct FusedCfg<3, true> { static constexpr int NXS = 6, NWS = 3, GX = 3, GH = 4; };
+template <> struct FusedCfg<3, false> { static constexpr int NXS = 6, NWS = 4, GX = 3, GH = 4; };
+template <> struct FusedCfg<4, false> { static constexpr int NXS = 8, NWS = 3, GX = 4, GH = 4; };
+template <> struct FusedCfg<4, true> { static constexpr int NXS = 8, NWS = 4, GX = 2, GH = 2; };
+template <int KX, bool HSEQ> struct FusedTypes {
+  using C = FusedCfg<KX, HSEQ>;
+  static constexpr int G = C::GX > C::GH ? C::GX : C::GH;
+  using Smem = tc::FusedSmem<C::NXS, C::NWS, G, HSEQ ? 2 : 0>;
+  static constexpr int smem_bytes = (int)sizeof(Smem) + 1024;
+  static_assert(smem_bytes <= 227 * 1024, "one CTA per SM");
+  static auto kernel() { return tc::lstm_fused_pair_kernel<KX, C::NXS, C::NWS, C::GX, C::GH, HSEQ>; }
+};
 
 void fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n_ct, int smem, cudaStream_t s) {
   cfg = {};
@@ -356,29 +371,31 @@ void fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n
   cfg.numAttrs = 1;
 }
 
+// co-resident CTA pairs of one variant on this device (one process drives one GPU: queried once)
 template <int KX, bool HSEQ> bool fused_fits(int n_ct) {
-  using C = FusedCfg<KX, HSEQ>;
-  auto kern = tc::lstm_fused_pair_kernel<KX, C::NXS, C::NWS, C::G, HSEQ>;
-  const int smem = (int)sizeof(tc::FusedSmem<C::NXS, C::NWS, C::G, HSEQ ? 2 : 0>) + 1024;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
-  fused_cluster_cfg(cfg, attr, n_ct, smem, nullptr);
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
-  return n * 2 >= ceil_div(n_ct, 2) * 2;
+  static const int max_clusters = [] {
+    auto kern = FusedTypes<KX, HSEQ>::kernel();
+    const int smem = FusedTypes<KX, HSEQ>::smem_bytes;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    fused_cluster_cfg(cfg, attr, 2 * 1024, smem, nullptr);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+  }();
+  return max_clusters >= ceil_div(n_ct, 2);
 }
 
 template <int KX, bool HSEQ>
 int fused_launch(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_pitch,
                  void* h_seq_f16, int h_pitch, float* h_last, const int32_t* lengths, int B, int T, cudaStream_t s) {
   using namespace tc;
-  using C = FusedCfg<KX, HSEQ>;
   const int n_ct = ceil_div(B, FB);
-  const int smem = (int)sizeof(FusedSmem<C::NXS, C::NWS, C::G, HSEQ ? 2 : 0>) + 1024;
+  const int smem = FusedTypes<KX, HSEQ>::smem_bytes;
   CUtensorMap tmWi, tmWh, tmX, tmH;
   int rc = make_tensor_map_2d(&tmWi, w_ih_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, KX * 64, KX * 64, 64, 64);
   if (rc == AVHOT_OK) rc = make_tensor_map_2d(&tmWh, w_hh_p16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4 * FH, FH, FH, 64, 64);
@@ -390,7 +407,7 @@ int fused_launch(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p
     rc = make_tensor_map_2d(&tmH, h_seq_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)T * n_ct * FB, FH,
                             (uint64_t)h_pitch, FB, 64);
   if (rc != AVHOT_OK) return rc;
-  auto kern = lstm_fused_pair_kernel<KX, C::NXS, C::NWS, C::G, HSEQ>;
+  auto kern = FusedTypes<KX, HSEQ>::kernel();
   AVHOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
@@ -402,13 +419,19 @@ int fused_launch(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p
 }
 }  // namespace
 
-// can the fused kernel take this layer?  x operand of 5 (the split of <= 104 features) or 4 (a hidden sequence)
-// k-blocks, every CTA pair co-resident (one CTA per SM).  AVHOT_LSTM_FUSED=0 switches it off, =1 top layer only.
+// Should this layer run as the fused kernel?  It can when the x operand has 5 (the split of <= 104 features), 3 (log-mel
+// split, DCT folded) or 4 (a hidden sequence) k-blocks and every CTA pair is co-resident (one CTA per SM).  It pays when
+// the batch is large: a fused step is a dependent chain of 8 x (4 KX + 16) MMAs whatever the batch (3.4 / 3.7 / 4.4 ms
+// per layer for KX = 3 / 4 / 5 at T = 301), while the two-kernel path spends 3.3 ms in the recurrence plus an input
+// GEMM that spreads over all SMs and shrinks with the batch (3 ms at 148 tiles).  Break-even tile counts below.
+// AVHOT_LSTM_FUSED = 0: never; 1: top layers only; 2: whenever it can (tests); unset: when it pays.
 bool lstm_fused_tc_supported(int x_cols, bool hseq, int B) {
   static const int forced = [] { const char* e = getenv("AVHOT_LSTM_FUSED"); return e ? atoi(e) : -1; }();
   if (forced == 0 || (forced == 1 && hseq)) return false;
   const int n_ct = ceil_div(B, tc::FB);
   if (n_ct < 2) return false;
+  if (forced != 2 && n_ct < (x_cols == 192 ? 2 : x_cols == 256 ? 24 : 48)) return false;
+  if (x_cols == 192) return hseq ? fused_fits<3, true>(n_ct) : fused_fits<3, false>(n_ct);
   if (x_cols == 320) return hseq ? fused_fits<5, true>(n_ct) : fused_fits<5, false>(n_ct);
   if (x_cols == 256) return hseq ? fused_fits<4, true>(n_ct) : fused_fits<4, false>(n_ct);
   return false;
@@ -426,6 +449,8 @@ int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float*
   AVHOT_REQUIRE(h_seq_f16 || h_last, AVHOT_ERR_INVALID, "lstm_layer_fused_tc: no output");
 #define AVHOT_FUSED_CASE(KX_, HS_) \
   return fused_launch<KX_, HS_>(w_ih_p16, w_hh_p16, bias_p, x_f16, x_pitch, h_seq_f16, h_pitch, h_last, lengths, B, T, s)
+  if (x_cols == 192 && h_seq_f16) AVHOT_FUSED_CASE(3, true);
+  if (x_cols == 192) AVHOT_FUSED_CASE(3, false);
   if (x_cols == 320 && h_seq_f16) AVHOT_FUSED_CASE(5, true);
   if (x_cols == 320) AVHOT_FUSED_CASE(5, false);
   if (x_cols == 256 && h_seq_f16) AVHOT_FUSED_CASE(4, true);

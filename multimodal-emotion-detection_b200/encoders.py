@@ -291,8 +291,9 @@ class SequenceEncoder(nn.Module):
             _lib.check(lib.avhot_frontend_ex(_lib.ptr(wave), None, _lib.ptr(xs), B, Bp, pitch, N, _lib.stream_ptr(dev)),
                        "logmel_mfcc (fused)")
             ws = _ws.get(lib.avhot_lstm_workspace_bytes(h, B, T, _lib.PREC_TC), dev)
-            _lib.check(lib.avhot_lstm_forward_split(h, _lib.ptr(xs), None, _lib.ptr(out), B, T, _lib.ptr(ws), ws.numel(),
-                                                    _lib.stream_ptr(dev)), "SequenceEncoder.forward (fused)")
+            # the operand is the front-end's: its MFCC columns are the DCT of its log-mel columns, which layer 0 exploits
+            _lib.check(lib.avhot_lstm_forward_frontend(h, _lib.ptr(xs), None, _lib.ptr(out), B, T, _lib.ptr(ws), ws.numel(),
+                                                       _lib.stream_ptr(dev)), "SequenceEncoder.forward (fused)")
         return out
 
 

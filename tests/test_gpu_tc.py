@@ -61,7 +61,6 @@ def test_lstm_tc_pair_kernel_equals_single_cta_kernel(pkg, dev, world, tmp_path)
     np.save(tmp_path / "len.npy", lengths)
     enc = make_model(pkg, dev, world).set_precision("tc").encoders["audio"]
     torch.save(enc.state_dict(), tmp_path / "enc.pt")
-    pair = enc(torch.from_numpy(x).to(dev), torch.from_numpy(lengths)).cpu().numpy()
     code = (
         "import sys, numpy as np, torch\n"
         "import multimodal_emotion_detection_b200 as pkg\n"
@@ -70,11 +69,92 @@ def test_lstm_tc_pair_kernel_equals_single_cta_kernel(pkg, dev, world, tmp_path)
         "enc.load_state_dict(torch.load(d + '/enc.pt'))\n"
         "enc = enc.to('cuda:0').eval(); enc.precision = pkg._lib.PREC_TC\n"
         "out = enc(torch.from_numpy(np.load(d + '/x.npy')).to('cuda:0'), torch.from_numpy(np.load(d + '/len.npy')))\n"
-        "np.save(d + '/single.npy', out.cpu().numpy())\n")
-    env = dict(os.environ, AVHOT_REC_PAIR="0", PYTHONPATH=os.pathsep.join(sys.path))
-    subprocess.run([sys.executable, "-c", code, str(tmp_path)], check=True, env=env, timeout=300)
-    single = np.load(tmp_path / "single.npy")
+        "np.save(d + '/' + sys.argv[2] + '.npy', out.cpu().numpy())\n")
+    # both runs with the fused layer kernel off (it would take this batch; lstm_fused.cu has its own test below)
+    for name, pair_env in (("pair", "1"), ("single", "0")):
+        env = dict(os.environ, AVHOT_LSTM_FUSED="0", AVHOT_REC_PAIR=pair_env, PYTHONPATH=os.pathsep.join(sys.path))
+        subprocess.run([sys.executable, "-c", code, str(tmp_path), name], check=True, env=env, timeout=300)
+    pair, single = np.load(tmp_path / "pair.npy"), np.load(tmp_path / "single.npy")
     assert (pair == single).all()
+
+
+def test_lstm_fused_layer_kernel(pkg, dev, world, tmp_path):
+    """lstm_fused.cu (input projection + recurrence of a layer in one kernel, h in tensor memory, c in registers) takes
+    over at large batches (where it pays); AVHOT_LSTM_FUSED=2 makes it run whenever a batch has two 128-clip tiles
+    (child process: the switch is read once).  Its roles - layer 0 on the split operand with the hidden sequence
+    stored, a middle layer in place, the top layer, a single layer - against the fp32 CUDA kernels at the stated
+    tolerance, ragged lengths, odd tile counts (the last pair's second CTA is a duplicate that writes nothing); and
+    against the two-kernel path (what the parent process runs at these sizes), which rounds xp to fp16 and so is not
+    bit-identical but sits inside the same tolerance.  One in-process run at a batch where the default takes it."""
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(23)
+    cases = ((1, 257, 9), (2, 300, 33), (3, 700, 17))
+    want, two_kernel = {}, {}
+    for layers, B, T in cases:
+        torch.manual_seed(100 + layers)
+        enc = pkg.SequenceEncoder(104, 256, 128, layers, "lstm").to(dev).eval()
+        x = rng.normal(size=(B, T, 104)).astype(np.float32) * 20.0      # dB-sized features: the split operand matters
+        lengths = rng.integers(1, T + 1, size=B)
+        np.save(tmp_path / f"x{layers}.npy", x)
+        np.save(tmp_path / f"len{layers}.npy", lengths)
+        torch.save(enc.state_dict(), tmp_path / f"enc{layers}.pt")
+        xd, ld = torch.from_numpy(x).to(dev), torch.from_numpy(lengths)
+        enc.precision = pkg._lib.PREC_TC
+        two_kernel[layers] = enc(xd, ld).cpu().numpy()
+        enc.precision = pkg._lib.PREC_FP32
+        want[layers] = enc(xd, ld).cpu().numpy()
+    code = (
+        "import sys, numpy as np, torch\n"
+        "import multimodal_emotion_detection_b200 as pkg\n"
+        "d = sys.argv[1]\n"
+        "for layers in (1, 2, 3):\n"
+        "    enc = pkg.SequenceEncoder(104, 256, 128, layers, 'lstm')\n"
+        "    enc.load_state_dict(torch.load(d + f'/enc{layers}.pt'))\n"
+        "    enc = enc.to('cuda:0').eval(); enc.precision = pkg._lib.PREC_TC\n"
+        "    out = enc(torch.from_numpy(np.load(d + f'/x{layers}.npy')).to('cuda:0'), torch.from_numpy(np.load(d + f'/len{layers}.npy')))\n"
+        "    np.save(d + f'/fused{layers}.npy', out.cpu().numpy())\n")
+    env = dict(os.environ, AVHOT_LSTM_FUSED="2", PYTHONPATH=os.pathsep.join(sys.path))
+    subprocess.run([sys.executable, "-c", code, str(tmp_path)], check=True, env=env, timeout=300)
+    for layers, B, T in cases:
+        fused = np.load(tmp_path / f"fused{layers}.npy")
+        e_f, e_u, e_fu = rel_err(fused, want[layers]), rel_err(two_kernel[layers], want[layers]), rel_err(fused, two_kernel[layers])
+        print(f"{layers} layer(s), B={B}, T={T}: fused {e_f:.3g}, two-kernel path {e_u:.3g}, fused vs two-kernel {e_fu:.3g}")
+        assert e_f <= TC_REL_LSTM and e_u <= TC_REL_LSTM
+        assert e_fu > 0, "the child process did not run the fused kernel (identical to the two-kernel result)"
+    # default selection: 50 tiles -> both layers fused in this process
+    torch.manual_seed(7)
+    enc = pkg.SequenceEncoder(104, 256, 128, 2, "lstm").to(dev).eval()
+    B, T = 50 * 128 - 5, 12
+    x = torch.from_numpy(rng.normal(size=(B, T, 104)).astype(np.float32) * 20.0).to(dev)
+    lengths = torch.from_numpy(rng.integers(1, T + 1, size=B))
+    enc.precision = pkg._lib.PREC_TC
+    got = enc(x, lengths).cpu().numpy()
+    enc.precision = pkg._lib.PREC_FP32
+    ref = enc(x, lengths).cpu().numpy()
+    print(f"default selection, B={B}: {rel_err(got, ref):.3g}")
+    assert rel_err(got, ref) <= TC_REL_LSTM
+
+
+def test_lstm_dct_fold_on_frontend_operand(pkg, dev, world):
+    """forward_from_waveform hands the LSTM the front-end's split operand, whose 40 MFCC columns are the DCT of its 64
+    log-mel columns; layer 0 then multiplies the log-mel k-blocks alone by W[:, :64] + W[:, 64:] D
+    (avhot_lstm_forward_frontend, K = 192 instead of 320).  Same embedding as the unfolded tensor-core path on the fp32
+    features and as the fp32 kernels, at the stated tolerance; small and large batches (fold + fused layer kernel)."""
+    torch.manual_seed(3)
+    enc = pkg.SequenceEncoder(104, 256, 128, 2, "lstm").to(dev).eval()
+    for B in (6, 300, 3000):
+        wave = pkg.synth.synth_audio(B, 1000, SEED, dev, n_samples=16000)
+        enc.precision = pkg._lib.PREC_TC
+        folded = enc.forward_from_waveform(wave).cpu().numpy()
+        feats = pkg.logmel_mfcc(wave)
+        unfolded = enc(feats).cpu().numpy()
+        enc.precision = pkg._lib.PREC_FP32
+        ref = enc(feats).cpu().numpy()
+        e1, e2 = rel_err(folded, ref), rel_err(unfolded, ref)
+        print(f"B={B}: folded {e1:.3g}, unfolded tc {e2:.3g} vs fp32 kernels")
+        assert e1 <= TC_REL_LSTM and e2 <= TC_REL_LSTM
 
 
 def test_full_path_tc(pkg, dev, world, golden):
