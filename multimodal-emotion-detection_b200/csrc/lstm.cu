@@ -22,7 +22,7 @@
 struct avhot_lstm {
   int input_dim, hidden_dim, num_layers, output_dim;
   float* w_ih[4];    // (4H, in_k) row-major copies
-  float* w_hh_t[4];  // [k][gate][j]  = W_hh[gate*H + j][k]
+  float* w_hh_t[4];  // [k][j][gate]  = W_hh[gate*H + j][k]
   float* bias[4];    // b_ih + b_hh
   float* bias_tc[4]; // the same with the i, f, o rows halved (tensor-core path: sigmoid(x) = 0.5 tanh(x / 2) + 0.5)
   void* w_hh_r16[4]; // fp16, rows regrouped per 32-unit chunk (lstm_tc.cu)
@@ -45,10 +45,19 @@ constexpr int LH = 256;  // hidden size this kernel is specialised for (one thre
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
 // W_hh is streamed through shared memory: chunks of WKC k-rows (WKC x 4 gates x 256 units = 32 KB, contiguous in the
-// k-major copy) travel global/L2 -> shared with cp.async into a ring of WNB buffers, two chunks ahead of the FMAs, one
+// k-major copy) travel global/L2 -> shared with cp.async into a ring of NB buffers, NB - 1 chunks ahead of the FMAs, one
 // block barrier per chunk.  (Reading W with per-thread __ldg left two warps per scheduler waiting on L2 round trips:
-// 111 k cycles per step measured at BT = 12 against 25 k of FMAs, whatever the unroll depth.)
-constexpr int WKC = 8, WNB = 3, WCHUNKS = LH / WKC;
+// 111 k cycles per step measured at BT = 12 against 25 k of FMAs, whatever the unroll depth.)  The ring is as deep as
+// shared memory allows (6 buffers up to 12 clips per CTA): with 3 buffers a chunk was requested two chunk periods
+// before its use and the period could not drop below half an L2 round trip (0.56 us per chunk at BT = 4, where the
+// FMAs take 0.14; 0.88 us at BT = 12 against 0.45).  Sharing one stream per cluster of four CTAs by TMA multicast,
+// with the hardware cluster barrier guarding buffer reuse, was measured slower (a cluster barrier round per 0.45 us
+// chunk: 1.29 us per chunk) - the kernel was never L2-bandwidth-bound.
+constexpr int WKC = 8, WCHUNKS = LH / WKC;
+constexpr int lstm_ring_depth(int BT) {
+  const int room = (227 * 1024 - 1024 - (int)sizeof(float) * 2 * LH * 2 * ((BT / 2 + 3) & ~3)) / ((int)sizeof(float) * WKC * 4 * LH);
+  return room > 6 ? 6 : room;
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
@@ -58,92 +67,104 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int BT>
-__global__ void __launch_bounds__(LH)
+// 512 threads: thread = (hidden unit j, half of the tile's clips).  With 256 threads (one per unit, all BT clips) an
+// SM held two warps per scheduler and ncu showed no eligible warp 39 % of the time at 61 % issue-slot use (FMA pipe
+// 44 %): four warps per scheduler hide each other's shared-memory and barrier latency.  The four gate weights of
+// (k, j) are one 128-bit shared load ([k][j][gate] copy of W_hh).
+__host__ __device__ constexpr int lstm_half_pad(int BT) { return (BT / 2 + 3) & ~3; }     // floats per half of an hs row (128-bit loads)
+template <int BT, int NB = lstm_ring_depth(BT)>
+__global__ void __launch_bounds__(2 * LH)
 lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
-                       const float* __restrict__ whh_t,   // [H][4][H]
+                       const float* __restrict__ whh_t,   // [H][H][4]: [k][j][gate] = W_hh[gate*H + j][k]
                        float* __restrict__ h_seq,         // (B, T, H) or NULL
                        float* __restrict__ h_last,        // (B, H) or NULL
                        const int32_t* __restrict__ lengths,  // (B) valid steps per clip, or NULL (= T)
                        int B, int T) {
-  constexpr int HP = BT + 4;  // padded row: conflict-free 128-bit stores of one unit's BT values
+  static_assert(BT % 2 == 0, "two halves");
+  constexpr int CH = BT / 2, CHP = lstm_half_pad(BT), HP = 2 * CHP;
   extern __shared__ __align__(16) unsigned char lstm_smem_raw[];
   float (*hs)[LH][HP] = reinterpret_cast<float (*)[LH][HP]>(lstm_smem_raw);   // [2][LH][HP]
-  float (*wb)[WKC][4][LH] = reinterpret_cast<float (*)[WKC][4][LH]>(lstm_smem_raw + sizeof(float) * 2 * LH * HP);  // [WNB]
-  const int j = threadIdx.x;
-  const int b0 = blockIdx.x * BT;
-  // chunk n of the endless stream (n = t * WCHUNKS + c) -> ring buffer n % WNB; every thread copies 8 x 16 bytes
+  float4 (*wb)[WKC][LH] = reinterpret_cast<float4 (*)[WKC][LH]>(lstm_smem_raw + sizeof(float) * 2 * LH * HP);  // [NB]
+  static_assert(NB >= 3, "ring: the chunk in use, one landing, one being requested");
+  const int j = threadIdx.x & (LH - 1), half = threadIdx.x >> 8;      // warps 0-7: clips [0, CH), warps 8-15: [CH, BT)
+  const int b0 = blockIdx.x * BT + half * CH;
+  // chunk n of the endless stream (n = t * WCHUNKS + c) -> ring buffer n % NB; every thread copies 4 x 16 bytes
   auto issue = [&](int n) {
     const float* src = whh_t + (size_t)(n % WCHUNKS) * (WKC * 4 * LH);
-    float* dst = &wb[n % WNB][0][0][0];
+    float* dst = reinterpret_cast<float*>(&wb[n % NB][0][0]);
 #pragma unroll
-    for (int i = 0; i < WKC * 4 * LH / 4 / LH; ++i) cp_async16(dst + 4 * (j + i * LH), src + 4 * (j + i * LH));
+    for (int i = 0; i < WKC * 4 * LH / 4 / (2 * LH); ++i)
+      cp_async16(dst + 4 * (threadIdx.x + i * 2 * LH), src + 4 * (threadIdx.x + i * 2 * LH));
     cp_async_commit();
   };
   const int n_total = T * WCHUNKS;
-  issue(0);
-  issue(1);
-  float c[BT];
 #pragma unroll
-  for (int b = 0; b < BT; ++b) {
+  for (int i = 0; i < NB - 1; ++i) {
+    if (i < n_total) issue(i); else cp_async_commit();
+  }
+  float c[CH];
+#pragma unroll
+  for (int b = 0; b < CH; ++b) {
     c[b] = 0.f;
-    hs[0][j][b] = 0.f;
+    hs[0][j][half * CHP + b] = 0.f;
   }
   __syncthreads();
   int n = 0;
   for (int t = 0; t < T; ++t) {
     const int cur = t & 1;
-    float acc[4][BT];
+    float acc[4][CH];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) {
-      const bool live = b0 + b < B;
-      const float* x = xp + ((size_t)(live ? b0 + b : b0) * T + t) * (4 * LH) + j;
+    for (int b = 0; b < CH; ++b) {
+      const float* x = xp + ((size_t)min(b0 + b, B - 1) * T + t) * (4 * LH) + j;
 #pragma unroll
       for (int g = 0; g < 4; ++g) acc[g][b] = __ldg(x + g * LH);
     }
 #pragma unroll 1
     for (int ch = 0; ch < WCHUNKS; ++ch, ++n) {
-      cp_async_wait<1>();                 // this thread's part of chunk n has landed (chunk n + 1 may be in flight)
+      cp_async_wait<NB - 2>();            // this thread's part of chunk n has landed (NB - 2 later ones may be in flight)
       __syncthreads();                    // ... and everybody's; everybody is also done with chunk n - 1's buffer
-      if (n + 2 < n_total) issue(n + 2); else cp_async_commit();   // (empty group: keeps the wait count uniform)
-      const float (*w)[4][LH] = wb[n % WNB];
+      if (n + NB - 1 < n_total) issue(n + NB - 1); else cp_async_commit();   // (empty group: keeps the wait count uniform)
+      const float4* w = wb[n % NB][0];
 #pragma unroll
       for (int kk = 0; kk < WKC; ++kk) {
         const int k = ch * WKC + kk;
-        float wg[4];
+        const float4 w4 = w[kk * LH + j];
+        const float wg[4] = {w4.x, w4.y, w4.z, w4.w};
+        float hv[CHP];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) wg[g] = w[kk][g][j];
-        float hv[BT];
-#pragma unroll
-        for (int b4 = 0; b4 < BT; b4 += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(&hs[cur][k][b4]);
-          hv[b4] = v.x; hv[b4 + 1] = v.y; hv[b4 + 2] = v.z; hv[b4 + 3] = v.w;
+        for (int b4 = 0; b4 < CHP; b4 += 4) {
+          if (CH - b4 >= 3) {
+            const float4 v = *reinterpret_cast<const float4*>(&hs[cur][k][half * CHP + b4]);
+            hv[b4] = v.x; hv[b4 + 1] = v.y; hv[b4 + 2] = v.z; hv[b4 + 3] = v.w;
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(&hs[cur][k][half * CHP + b4]);
+            hv[b4] = v.x; hv[b4 + 1] = v.y;
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int b = 0; b < BT; ++b) acc[g][b] = fmaf(wg[g], hv[b], acc[g][b]);
+          for (int b = 0; b < CH; ++b) acc[g][b] = fmaf(wg[g], hv[b], acc[g][b]);
       }
     }
-    float hn[BT];
+    float hn[CH];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) {
+    for (int b = 0; b < CH; ++b) {
       const float ig = sigmoid_acc(acc[0][b]), fg = sigmoid_acc(acc[1][b]);
       const float gg = tanhf(acc[2][b]), og = sigmoid_acc(acc[3][b]);
       c[b] = fmaf(fg, c[b], ig * gg);
       hn[b] = og * tanhf(c[b]);
     }
 #pragma unroll
-    for (int b4 = 0; b4 < BT; b4 += 4)
-      *reinterpret_cast<float4*>(&hs[cur ^ 1][j][b4]) = make_float4(hn[b4], hn[b4 + 1], hn[b4 + 2], hn[b4 + 3]);
+    for (int b = 0; b < CH; ++b) hs[cur ^ 1][j][half * CHP + b] = hn[b];
     if (h_seq) {
 #pragma unroll
-      for (int b = 0; b < BT; ++b)
+      for (int b = 0; b < CH; ++b)
         if (b0 + b < B) h_seq[((size_t)(b0 + b) * T + t) * LH + j] = hn[b];
     }
     if (h_last) {
 #pragma unroll
-      for (int b = 0; b < BT; ++b)
+      for (int b = 0; b < CH; ++b)
         if (b0 + b < B) {   // h_n = state after the clip's last valid step (packed sequences, src/encoders.py:139-147)
           const int last_t = (lengths ? min(max(__ldg(lengths + b0 + b), 1), T) : T) - 1;
           if (t == last_t) h_last[(size_t)(b0 + b) * LH + j] = hn[b];
@@ -152,6 +173,13 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
     // no barrier here: the next step's first chunk barrier orders these h writes before anybody reads them
   }
   cp_async_wait<0>();
+}
+
+// W_hh (4H, H) -> [k][j][gate] = W_hh[gate*H + j][k]
+__global__ void regroup_whh_kernel(const float* __restrict__ w_hh, float* __restrict__ dst) {
+  const int k = blockIdx.x, j = threadIdx.x;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) dst[((size_t)k * LH + j) * 4 + g] = w_hh[((size_t)g * LH + j) * LH + k];
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -329,7 +357,10 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
     h->w_hh_r16[l] = take(2 * 4 * H * H);
     if (cudaMemcpyAsync(h->w_ih[l], d->weight_ih[l], sizeof(float) * 4 * H * in, cudaMemcpyDeviceToDevice, s) !=
         cudaSuccess) rc = AVHOT_ERR_CUDA;
-    if (rc == AVHOT_OK) rc = transpose(d->weight_hh[l], h->w_hh_t[l], 4 * H, H, s);  // [k][gate*H + j]
+    if (rc == AVHOT_OK) {                                   // [k][j][gate], once per handle
+      regroup_whh_kernel<<<H, LH, 0, s>>>(d->weight_hh[l], h->w_hh_t[l]);
+      if (cudaGetLastError() != cudaSuccess) rc = AVHOT_ERR_CUDA;
+    }
     if (rc == AVHOT_OK) rc = add_vec(d->bias_ih[l], d->bias_hh[l], h->bias[l], 4 * H, s);
     if (rc == AVHOT_OK) rc = lstm_pack_whh_fp16(d->weight_hh[l], h->w_hh_r16[l], s);
   }
@@ -518,10 +549,10 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
     const int want = 4 * ceil_div(B, 4 * num_sms());
 #define AVHOT_REC_CASE(BT_)                                                                                        \
   case BT_: {                                                                                                       \
-    const size_t smem = sizeof(float) * (2 * LH * (BT_ + 4) + (size_t)WNB * WKC * 4 * LH);                         \
+    const size_t smem = sizeof(float) * (2 * LH * 2 * lstm_half_pad(BT_) + (size_t)lstm_ring_depth(BT_) * WKC * 4 * LH); \
     AVHOT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                     (int)smem));                                                                    \
-    lstm_recurrence_kernel<BT_><<<ceil_div(B, BT_), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T); \
+    lstm_recurrence_kernel<BT_><<<ceil_div(B, BT_), 2 * LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T); \
     break;                                                                                                          \
   }
     switch (want >= 32 ? 32 : want) {

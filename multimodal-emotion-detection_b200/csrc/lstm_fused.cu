@@ -66,11 +66,16 @@ __device__ __forceinline__ void umma_f16_pair_ts_elect(uint32_t d_tmem, uint32_t
       : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// tanh.approx.f32: one MUFU, max relative error 2^-11.  (ex2 + rcp activations, two MUFU and ~1e-7, were measured: the
+// audio path's share of the logit error stayed at 6e-6 rms / 4.8e-5 max of the logit scale - it is set by the fp16
+// hidden state and weights - and the kernel went from 7.3 to 9.0 ms per step.)
 __device__ __forceinline__ float tanh_mufu(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// sigmoid of a pre-activation that arrives halved (xh = x / 2)
+__device__ __forceinline__ float sigmoid_half(float xh) { return fmaf(0.5f, tanh_mufu(xh), 0.5f); }
 __device__ __forceinline__ void stg256f(float* p, const float (&v)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -290,10 +295,10 @@ lstm_fused_pair_kernel(const __grid_constant__ CUtensorMap tmWi, const __grid_co
             const float bf = i == 0 ? bg[1].x : i == 1 ? bg[1].y : i == 2 ? bg[1].z : bg[1].w;
             const float bgg = i == 0 ? bg[2].x : i == 1 ? bg[2].y : i == 2 ? bg[2].z : bg[2].w;
             const float bo = i == 0 ? bg[3].x : i == 1 ? bg[3].y : i == 2 ? bg[3].z : bg[3].w;
-            const float ig = fmaf(0.5f, tanh_mufu(__uint_as_float(a[hf][i]) + bi), 0.5f);
-            const float fg = fmaf(0.5f, tanh_mufu(__uint_as_float(a[hf][4 + i]) + bf), 0.5f);
+            const float ig = sigmoid_half(__uint_as_float(a[hf][i]) + bi);
+            const float fg = sigmoid_half(__uint_as_float(a[hf][4 + i]) + bf);
             const float gg = tanh_mufu(__uint_as_float(a[hf][8 + i]) + bgg);
-            const float og = fmaf(0.5f, tanh_mufu(__uint_as_float(a[hf][12 + i]) + bo), 0.5f);
+            const float og = sigmoid_half(__uint_as_float(a[hf][12 + i]) + bo);
             const float cn = fmaf(fg, cs[c * 8 + hf * 4 + i], ig * gg);
             cs[c * 8 + hf * 4 + i] = cn;
             hn[hf * 4 + i] = og * tanh_mufu(cn);
@@ -371,7 +376,7 @@ void fused_cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int n
   cfg.numAttrs = 1;
 }
 
-// co-resident CTA pairs of one variant on this device (one process drives one GPU: queried once)
+// can a CTA pair of this variant be resident on this device at all (one process drives one GPU: queried once)
 template <int KX, bool HSEQ> bool fused_fits(int n_ct) {
   static const int max_clusters = [] {
     auto kern = FusedTypes<KX, HSEQ>::kernel();
@@ -419,21 +424,19 @@ int fused_launch(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p
 }
 }  // namespace
 
-// Should this layer run as the fused kernel?  It can when the x operand has 5 (the split of <= 104 features), 3 (log-mel
-// split, DCT folded) or 4 (a hidden sequence) k-blocks and every CTA pair is co-resident (one CTA per SM).  It pays when
-// the batch is large: a fused step is a dependent chain of 8 x (4 KX + 16) MMAs whatever the batch (3.4 / 3.7 / 4.4 ms
-// per layer for KX = 3 / 4 / 5 at T = 301), while the two-kernel path spends 3.3 ms in the recurrence plus an input
-// GEMM that spreads over all SMs and shrinks with the batch (3 ms at 148 tiles).  Break-even tile counts below.
-// AVHOT_LSTM_FUSED = 0: never; 1: top layers only; 2: whenever it can (tests); unset: when it pays.
+// Does this layer run as the fused kernel?  Whenever the x operand has 5 (the split of <= 104 features), 3 (log-mel
+// split, DCT folded) or 4 (a hidden sequence) k-blocks - at EVERY batch size, so that a clip's embedding does not depend
+// on how the batch was sharded (the two-kernel path rounds xp to fp16: same tolerance, different bits).  A batch of
+// one tile runs as a pair whose second CTA duplicates the tile and writes nothing; more pairs than fit on the GPU run in
+// waves.  Small batches pay for it: a fused step is a dependent chain of 8 x (4 KX + 16) MMAs whatever the batch
+// (3.4 / 3.7 / 4.4 ms per layer for KX = 3 / 4 / 5 at T = 301), while the two-kernel path's input GEMM spreads over all
+// SMs (B = 512: 7.2 against 6.2 ms for the whole forward).  AVHOT_LSTM_FUSED=0: the two-kernel path everywhere.
 bool lstm_fused_tc_supported(int x_cols, bool hseq, int B) {
   static const int forced = [] { const char* e = getenv("AVHOT_LSTM_FUSED"); return e ? atoi(e) : -1; }();
-  if (forced == 0 || (forced == 1 && hseq)) return false;
-  const int n_ct = ceil_div(B, tc::FB);
-  if (n_ct < 2) return false;
-  if (forced != 2 && n_ct < (x_cols == 192 ? 2 : x_cols == 256 ? 24 : 48)) return false;
-  if (x_cols == 192) return hseq ? fused_fits<3, true>(n_ct) : fused_fits<3, false>(n_ct);
-  if (x_cols == 320) return hseq ? fused_fits<5, true>(n_ct) : fused_fits<5, false>(n_ct);
-  if (x_cols == 256) return hseq ? fused_fits<4, true>(n_ct) : fused_fits<4, false>(n_ct);
+  if (forced == 0 || B < 1) return false;
+  if (x_cols == 192) return hseq ? fused_fits<3, true>(1) : fused_fits<3, false>(1);
+  if (x_cols == 320) return hseq ? fused_fits<5, true>(1) : fused_fits<5, false>(1);
+  if (x_cols == 256) return hseq ? fused_fits<4, true>(1) : fused_fits<4, false>(1);
   return false;
 }
 
