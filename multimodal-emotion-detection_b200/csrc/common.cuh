@@ -75,6 +75,12 @@ bool gemm_u8_tc_supported(const uint8_t* a, int lda, int N, int K);
 int gemm_u8_tc(const uint8_t* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float* c,
                int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_u8_tc");
 
+// gemm_cvt.cu: the same Linear on fp32 frames, converted to fp16 inside the kernel, CTA pairs sharing the fp16 weights
+// (wq_f16 / inv_scale_dev of gemm_u8_pack_weights; scale_mul = 255 for frames that are pixels / 255)
+bool gemm_f32cvt_tc_supported(const float* a, int lda, int N, int K);
+int gemm_f32cvt_tc(const float* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float scale_mul,
+                   float* c, int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_f32cvt_tc");
+
 // lstm_tc.cu: W_hh (4H, H) fp32 -> fp16, rows regrouped per 32-unit chunk; and the tcgen05 recurrence of one layer.
 int lstm_pack_whh_fp16(const float* w_hh, void* out, cudaStream_t s);
 // h_seq_f16: (B, T, H) fp16 hidden sequence (input of the next layer's projection) or NULL

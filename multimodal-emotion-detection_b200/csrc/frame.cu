@@ -322,6 +322,12 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
     frames_f32 = reinterpret_cast<const float*>(workspace);
     frames_u8 = nullptr;
   }
+  // fp32 frames on the tensor-core path: converted to fp16 inside a CTA-pair GEMM that shares the fp16 weights
+  // (gemm_cvt.cu; wq_f16 is W s / 255, so the pixel scaling is undone by 255); TF32 on the fp32 operands otherwise
+  if (precision == AVHOT_PREC_TC && frames_f32 && h->wq_f16 &&
+      gemm_f32cvt_tc_supported(frames_f32, h->frame_dim, h->hidden_dim, h->frame_dim))
+    return gemm_f32cvt_tc(frames_f32, h->frame_dim, h->wq_f16, h->mlp_b, h->wq_inv, 255.f, hid, h->hidden_dim, B * F,
+                          h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
   if (precision == AVHOT_PREC_TC && frames_f32)
     return gemm_tf32_tc(frames_f32, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim, B * F,
                         h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
