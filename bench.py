@@ -516,13 +516,13 @@ def rooflines(prof, args, B, ms, peaks):
         "frontend": (["frontend"], "hbm", B * BYTES_FRONTEND, 0),
         "lstm": ((["lstm_split3", "lstm_layer_fused_tc", "lstm_input_gemm_tc", "lstm_recurrence_tc"] if tc else
                   ["lstm_input_gemm", "lstm_recurrence"]) + ["lstm_projection"], "tensor", B * BYTES_LSTM, B * FLOPS_LSTM),
-        "video": (["frame_u8_to_f32", "frame_gemm"], "hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
+        "video": (["frame_u8_to_f32", "frame_gemm"] + ([] if tc else ["frame_gemm_f32"]), "hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
         "mc_tail": (["frame_tail", "fusion_clip", "fusion_tc", "mc_reduce"] + ([] if tc else ["fusion_pass", "hybrid_fusion"]),
                     "tensor", B * BYTES_MC_TAIL, B * args.passes * FLOPS_MC_PASS),
     }
     if tc:   # the fp32 kernels that only the near-tie re-evaluation launches (its launches of the kernels it shares with the
              # main path - front-end, video GEMM, tails - are a few percent of those stages and stay there)
-        groups["near_tie_reevaluation"] = (["lstm_input_gemm", "lstm_recurrence", "fusion_pass", "hybrid_fusion", "near_tie_flag",
+        groups["near_tie_reevaluation"] = (["lstm_input_gemm", "lstm_recurrence", "frame_gemm_f32", "fusion_pass", "hybrid_fusion", "near_tie_flag",
                                             "near_tie_gather", "near_tie_scatter"], "fp32", 0, 0)
     stage_rooflines = {}
     for name, (kernels, bound, nbytes, nflops) in groups.items():
@@ -549,6 +549,7 @@ def rooflines(prof, args, B, ms, peaks):
     per_kernel = {
         "frontend": ("hbm", B * BYTES_FRONTEND, 0),
         "frame_gemm": ("hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
+        "frame_gemm_f32": ("hbm", B * BYTES_VIDEO, B * FLOPS_FRAME_GEMM),
         "lstm_recurrence_tc": ("tensor", 0, 2 * B * FLOPS_LSTM_RECURRENT_PER_LAYER),
         "lstm_input_gemm_tc": ("tensor", 0, B * (537_542_656 - 2 * FLOPS_LSTM_RECURRENT_PER_LAYER)),
         "lstm_layer_fused_tc": ("tensor", 0, B * 537_542_656),

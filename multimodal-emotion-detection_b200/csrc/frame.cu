@@ -332,7 +332,7 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
     return gemm_tf32_tc(frames_f32, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim, B * F,
                         h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
   return gemm_f32(frames_f32, frames_u8, h->frame_dim, h->mlp_w, h->frame_dim, h->mlp_b, hid, h->hidden_dim,
-                  B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
+                  B * F, h->hidden_dim, h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm_f32");
 }
 
 static int frame_tail_impl(avhot_frame_t h, const float* hid, const uint8_t* frame_valid, float* z, int B, int F, int T,

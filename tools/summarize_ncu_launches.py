@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, tag = sys.argv[1], sys.argv[2]
 which = int(sys.argv[3]) if len(sys.argv) > 3 else 4            # 0-based index of the main-path step to report (3 warm-up + 2 timed)
 STAGE = [("frontend_tc_kernel", "frontend"), ("lstm_fused_pair_kernel", "lstm_layer_fused_tc"), ("gemm_f16_ws_pair_kernel", "lstm_input_gemm_tc"), ("gemm_f16_ws_kernel", "lstm_input_gemm_tc"),
-         ("lstm_rec_tc_kernel", "lstm_recurrence_tc"), ("gemm_tf32_tc_kernel", "frame_gemm"), ("frame_tail_kernel", "frame_tail"),
+         ("lstm_rec_tc_kernel", "lstm_recurrence_tc"), ("gemm_tf32_tc_kernel", "frame_gemm"), ("gemm_cvt_f16_pair_kernel", "frame_gemm"), ("frame_tail_kernel", "frame_tail"),
          ("fusion_clip_kernel", "fusion_clip"), ("fusion_tc_kernel", "fusion_tc"), ("mc_reduce_kernel", "mc_reduce"),
          ("gemm_f32_kernel", "lstm_projection"), ("near_tie_flag_kernel", "near_tie_flag"), ("near_tie_begin_kernel", "near_tie_flag"),
          ("gather_flagged_kernel", "near_tie_gather")]
