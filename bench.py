@@ -761,7 +761,7 @@ def run_e2e(ctx, B, T, clip0_of, audio="i16", video="u8"):
     window's results are read back (the uploads of the next window's first sub-batches are already in flight)."""
     torch, dist, pkg, par, dev, world, args = ctx.torch, ctx.dist, ctx.pkg, ctx.par, ctx.dev, ctx.world, ctx.args
     model, res = ctx.model, ctx.resolver
-    C = min(args.e2e_chunk, B)
+    C = min(args.e2e_chunk if args.e2e_chunk > 0 else (6400 if video == "u8" else 2048), B)
     n_sub = (B + C - 1) // C
     host, slots = [], []
     for j in range(2):
@@ -842,7 +842,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=148 * 128,
                     help="clips per GPU per step (default: one 128-clip CTA of the recurrent kernel per SM)")
-    ap.add_argument("--e2e-chunk", type=int, default=2048, help="clips per host->device sub-batch in the e2e leg")
+    ap.add_argument("--e2e-chunk", type=int, default=0,
+                    help="clips per host->device sub-batch in the e2e legs (default: 6400 for the decoded-format leg - two "
+                         "34 ms uploads in flight cover the 34 ms near-tie flush and a sub-batch's compute stays well under "
+                         "its upload: 0.96 of the copy ceiling against 0.92 at 2048 - and 2048 for the fp32 leg, which is at "
+                         "0.99 either way and would pin 13 GB of host memory per rank otherwise)")
     ap.add_argument("--passes", type=int, default=32, help="MC-dropout passes T")
     ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU sample (~10 s of host work)")
     ap.add_argument("--check-clips", type=int, default=1024, help="clips of every timed step checked against the fp32 path")

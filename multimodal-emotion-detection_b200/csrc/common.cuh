@@ -141,6 +141,14 @@ __host__ __device__ __forceinline__ uint32_t philox_half(const Philox4& p, uint3
   return (i & 1u) ? (w >> 16) : (w & 0xFFFFu);
 }
 
+// philox_half(p, i) >= thr16 without extracting the half-word: the high half of a word compares as the word itself against
+// thr16 << 16, the low half as the word shifted up (one shift for the low halves, none for the high ones, instead of a
+// mask / shift per element on the integer pipe that bounds frame_tail_kernel)
+__device__ __forceinline__ bool philox_half_keep(const Philox4& p, uint32_t i, uint32_t thr16_hi) {   // thr16_hi = thr16 << 16
+  const uint32_t w = philox_word(p, i >> 1);
+  return ((i & 1u) ? w : (w << 16)) >= thr16_hi;
+}
+
 // floor(p * 2^32) clamped to uint32: an element is kept iff word >= threshold.
 static inline uint32_t drop_threshold(float p) {
   double v = (double)p * 4294967296.0;

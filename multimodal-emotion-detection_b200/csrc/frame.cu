@@ -64,7 +64,7 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
   const float4 aw1 = __ldg(reinterpret_cast<const float4*>(attn_w + c1));
   const float ab = __ldg(attn_b);
   const bool drop = ds.thr != 0u;
-  const uint32_t thr16 = ds.thr >> 16;
+  const uint32_t thr16_hi = ds.thr & 0xFFFF0000u;      // (thr >> 16) << 16
 
   for (int i = warp; i < FT_ROWS; i += FT_WARPS) {
     const long long row = row0 + i;
@@ -88,7 +88,7 @@ frame_tail_kernel(const float* __restrict__ hid,        // (B, F, H) post-ReLU, 
         if (drop) {
           const Philox4 r = philox4x32_10_rk((uint32_t)(f * 32 + lane), g, pass, AVHOT_SITE_FRAME_MLP, ds);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) x[q] = philox_half(r, (uint32_t)q) >= thr16 ? x[q] : 0.f;
+          for (int q = 0; q < 8; ++q) x[q] = philox_half_keep(r, (uint32_t)q, thr16_hi) ? x[q] : 0.f;
         }
         if (POOL != 0) {
           const bool ok = !valid || valid[(size_t)b * F + f];

@@ -128,6 +128,23 @@ def test_lstm_fused_layer_kernel(pkg, dev, world, tmp_path):
         assert e_fu > 0, "the fused kernel did not run (identical to the two-kernel result)"
 
 
+@pytest.mark.parametrize("B,T,layers", [(1, 1, 2), (1, 5, 1), (128, 2, 2), (129, 3, 2), (257, 1, 3), (5, 301, 2)])
+def test_lstm_fused_edge_shapes(pkg, dev, B, T, layers):
+    """The fused layer kernel at the edges: one clip, one step (no recurrent half at all), exactly one tile, one tile plus
+    one clip, full-length sequences; lengths None / all 1 / ragged - against the fp32 CUDA kernels."""
+    torch.manual_seed(B * 31 + T)
+    enc = pkg.SequenceEncoder(104, 256, 128, layers, "lstm").to(dev).eval()
+    rng = np.random.default_rng(B + 100 * T)
+    x = torch.from_numpy(rng.normal(size=(B, T, 104)).astype(np.float32) * 10.0).to(dev)
+    for lengths in (None, torch.ones(B, dtype=torch.int64), torch.from_numpy(rng.integers(1, T + 1, size=B))):
+        enc.precision = pkg._lib.PREC_TC
+        got = enc(x, lengths).cpu().numpy()
+        enc.precision = pkg._lib.PREC_FP32
+        ref = enc(x, lengths).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert rel_err(got, ref) <= TC_REL_LSTM, (B, T, layers, rel_err(got, ref))
+
+
 def test_lstm_dct_fold_on_frontend_operand(pkg, dev, world):
     """forward_from_waveform hands the LSTM the front-end's split operand, whose 40 MFCC columns are the DCT of its 64
     log-mel columns; layer 0 then multiplies the log-mel k-blocks alone by W[:, :64] + W[:, 64:] D
