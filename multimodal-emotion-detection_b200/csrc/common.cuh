@@ -96,6 +96,10 @@ bool lstm_fused_tc_supported(int x_cols, bool hseq, int B);
 int lstm_layer_fused_tc(const void* w_ih_p16, const void* w_hh_p16, const float* bias_p, const void* x_f16, int x_cols,
                         int x_pitch, void* h_seq_f16, int h_pitch, float* h_last, const int32_t* lengths, int B, int T,
                         cudaStream_t s);
+// lstm_cs.cu: fp32 recurrence of one layer with W_hh resident in the shared memory of an 8-CTA cluster (small batches);
+// false = the batch does not fit one wave of clusters, nothing launched.  Bit-identical to lstm_recurrence_kernel.
+bool lstm_recurrence_cs(const float* xp, const float* whh_t, float* h_seq, float* h_last, const int32_t* lengths, int B,
+                        int T, cudaStream_t s, int* rc);
 // gemm_ws.cu: weight-stationary tcgen05 GEMM, fp16 operands, fp32 output (LSTM input projections)
 int gemm_f16_ws(const void* a, int lda, const void* w, int ldw, const float* bias, void* c, bool out_f16, int ldc, int M,
                 int N, int K, cudaStream_t s, const char* prof_name = "gemm_f16_ws");

@@ -546,6 +546,14 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
     // least L2 traffic, but the 602 dependent steps want every SM busy: the smallest multiple of 4 that fits the batch
     // into one wave of CTAs (e.g. 2560 near-tie clips of a flush: 20 clips x 128 CTAs instead of 32 x 80, measured
     // 47 -> 25 ms for the two layers), 32 for large batches.
+    {   // small batches: W_hh resident in a cluster's shared memory instead of streamed every step (lstm_cs.cu)
+      int rc_cs = AVHOT_OK;
+      if (lstm_recurrence_cs(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T, s, &rc_cs)) {
+        if (rc_cs != AVHOT_OK) return rc_cs;
+        AVHOT_LAUNCH_CHECK();
+        continue;
+      }
+    }
     const int want = 4 * ceil_div(B, 4 * num_sms());
 #define AVHOT_REC_CASE(BT_)                                                                                        \
   case BT_: {                                                                                                       \

@@ -674,3 +674,39 @@ def test_split_reader_feeds_the_path(pkg, dev, world, tmp_path):
     ref = om.calibration_metrics(want.cpu(), torch.from_numpy(labels), 15)
     for k in ("ece", "mce", "nll", "accuracy"):
         assert abs(cal[k] - ref[k]) <= 1e-5, k
+
+
+def test_lstm_fp32_cluster_resident_kernel_equals_streaming_kernel(pkg, dev, tmp_path):
+    """Small fp32 batches run the recurrence with W_hh resident in the shared memory of an 8-CTA cluster (lstm_cs.cu: h
+    exchanged by st.async onto the receivers' mbarriers); larger ones stream W_hh per CTA (lstm.cu).  Same arithmetic in
+    the same order: bit-identical embeddings, so a clip's fp32 result does not depend on the batch size's kernel choice.
+    The streaming run happens in a child process (AVHOT_LSTM_CS=0 is read once)."""
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(77)
+    cases = ((1, 1, 7), (2, 8, 40), (2, 100, 13), (3, 300, 9), (2, 600, 5))       # (layers, B, T): 8 / 8 / 32 / 48 clips per cluster
+    got = {}
+    for i, (layers, B, T) in enumerate(cases):
+        torch.manual_seed(500 + i)
+        enc = pkg.SequenceEncoder(104, 256, 128, layers, "lstm").to(dev).eval()
+        x = rng.normal(size=(B, T, 104)).astype(np.float32)
+        lengths = rng.integers(1, T + 1, size=B)
+        np.save(tmp_path / f"x{i}.npy", x)
+        np.save(tmp_path / f"len{i}.npy", lengths)
+        torch.save(enc.state_dict(), tmp_path / f"enc{i}.pt")
+        got[i] = enc(torch.from_numpy(x).to(dev), torch.from_numpy(lengths)).cpu().numpy()
+    code = (
+        "import sys, numpy as np, torch\n"
+        "import multimodal_emotion_detection_b200 as pkg\n"
+        "d = sys.argv[1]\n"
+        "for i, layers in enumerate((1, 2, 2, 3, 2)):\n"
+        "    enc = pkg.SequenceEncoder(104, 256, 128, layers, 'lstm')\n"
+        "    enc.load_state_dict(torch.load(d + f'/enc{i}.pt'))\n"
+        "    enc = enc.to('cuda:0').eval()\n"
+        "    out = enc(torch.from_numpy(np.load(d + f'/x{i}.npy')).to('cuda:0'), torch.from_numpy(np.load(d + f'/len{i}.npy')))\n"
+        "    np.save(d + f'/stream{i}.npy', out.cpu().numpy())\n")
+    env = dict(os.environ, AVHOT_LSTM_CS="0", PYTHONPATH=os.pathsep.join(sys.path))
+    subprocess.run([sys.executable, "-c", code, str(tmp_path)], check=True, env=env, timeout=300)
+    for i in range(len(cases)):
+        assert (got[i] == np.load(tmp_path / f"stream{i}.npy")).all(), cases[i]
