@@ -22,7 +22,7 @@
 
 namespace avhot {
 
-constexpr int CSH = 256, CSU = 32, CSCL = 8, CSTHREADS = 256;   // hidden size, units per CTA, cluster size, threads
+constexpr int CSH = 256, CSU = 32, CSCL = 8;   // hidden size, units per CTA, cluster size
 
 __device__ __forceinline__ float cs_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 // remote (or own) shared-memory store whose bytes complete the mbarrier at `bar` in the SAME CTA as `addr`
@@ -42,15 +42,20 @@ __device__ __forceinline__ void st_async_f32x4(uint32_t addr, float a, float b, 
                : "memory");
 }
 
-// NB clips per cluster (multiple of 8); thread = (unit u = tid & 31, clip group tid >> 5 of CT = NB / 8 clips)
-template <int NB>
-__global__ void __launch_bounds__(CSTHREADS, 1)
+// NB clips per cluster in NW groups (warps); thread = (unit u = tid & 31, clip group tid >> 5 of CT = NB / NW clips).
+// Every warp reads the CTA's whole weight slice each step (4 shared-memory wavefronts per k), so large NB use few warps with
+// many clips per thread (48 clips: 4 warps x 12 clips = 28 wavefronts per k; 8 warps x 6 = 44; measured equal, 15.6 us per
+// step against 7 us of FMA issue - like the streaming kernel the FFMA stream runs at ~45 % of the pipe), small NB many
+// warps (the FMA chain of one clip is latency-bound).
+template <int NB, int NW>
+__global__ void __launch_bounds__(32 * NW, 1)
 lstm_rec_cs_kernel(const float* __restrict__ xp,      // (B, T, 4H)
                    const float* __restrict__ whh_t,   // [k][j][gate] = W_hh[gate*H + j][k]
                    float* __restrict__ h_seq,         // (B, T, H) or NULL
                    float* __restrict__ h_last,        // (B, H) or NULL
                    const int32_t* __restrict__ lengths, int B, int T) {
-  constexpr int CT = NB / 8;
+  constexpr int CT = NB / NW, CSTHREADS = 32 * NW;
+  static_assert(NB % NW == 0, "clip groups");
   extern __shared__ __align__(16) unsigned char cs_smem_raw[];
   float4 (*ws)[CSU] = reinterpret_cast<float4 (*)[CSU]>(cs_smem_raw);                                    // [256 k][32 u] x 4 gates
   float (*hs)[CSH][NB] = reinterpret_cast<float (*)[CSH][NB]>(cs_smem_raw + sizeof(float4) * CSH * CSU);   // [2][k][clip]
@@ -179,9 +184,9 @@ lstm_rec_cs_kernel(const float* __restrict__ xp,      // (B, T, 4H)
 namespace {
 template <int NB> int cs_smem_bytes() { return (int)(sizeof(float4) * CSH * CSU + sizeof(float) * 2 * CSH * NB) + 16; }
 
-template <int NB> bool cs_try_launch(const float* xp, const float* whh_t, float* h_seq, float* h_last, const int32_t* lengths,
-                                     int B, int T, cudaStream_t s, int* rc) {
-  auto kern = lstm_rec_cs_kernel<NB>;
+template <int NB, int NW> bool cs_try_launch(const float* xp, const float* whh_t, float* h_seq, float* h_last,
+                                             const int32_t* lengths, int B, int T, cudaStream_t s, int* rc) {
+  auto kern = lstm_rec_cs_kernel<NB, NW>;
   const int smem = cs_smem_bytes<NB>();
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     cudaGetLastError();
@@ -189,7 +194,7 @@ template <int NB> bool cs_try_launch(const float* xp, const float* whh_t, float*
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(CSCL * ceil_div(B, NB)));
-  cfg.blockDim = dim3(CSTHREADS);
+  cfg.blockDim = dim3(32 * NW);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -221,10 +226,10 @@ bool lstm_recurrence_cs(const float* xp, const float* whh_t, float* h_seq, float
                         int T, cudaStream_t s, int* rc) {
   static const bool off = [] { const char* e = getenv("AVHOT_LSTM_CS"); return e && atoi(e) == 0; }();
   if (off || B < 1) return false;
-  if (cs_try_launch<8>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
-  if (cs_try_launch<16>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
-  if (cs_try_launch<32>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
-  if (cs_try_launch<48>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
+  if (cs_try_launch<8, 8>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
+  if (cs_try_launch<16, 8>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
+  if (cs_try_launch<32, 8>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
+  if (cs_try_launch<48, 4>(xp, whh_t, h_seq, h_last, lengths, B, T, s, rc)) return true;
   return false;
 }
 
