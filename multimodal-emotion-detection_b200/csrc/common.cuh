@@ -78,6 +78,9 @@ int gemm_u8_tc(const uint8_t* a, int lda, const void* wq_f16, const float* bias,
 // gemm_cvt.cu: the same Linear on fp32 frames, converted to fp16 inside the kernel, CTA pairs sharing the fp16 weights
 // (wq_f16 / inv_scale_dev of gemm_u8_pack_weights; scale_mul = 255 for frames that are pixels / 255)
 bool gemm_f32cvt_tc_supported(const float* a, int lda, int N, int K);
+bool gemm_u8_pair_tc_supported(const uint8_t* a, int lda, int N, int K);
+int gemm_u8_pair_tc(const uint8_t* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float* c,
+                    int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_u8_pair_tc");
 int gemm_f32cvt_tc(const float* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float scale_mul,
                    float* c, int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name = "gemm_f32cvt_tc");
 

@@ -305,6 +305,10 @@ extern "C" int avhot_frame_hidden(avhot_frame_t h, const float* frames_f32, cons
   AVHOT_REQUIRE(precision == AVHOT_PREC_FP32 || precision == AVHOT_PREC_TC, AVHOT_ERR_UNSUPPORTED,
                 "frame_hidden: precision %d not built", precision);
   AVHOT_REQUIRE((long long)B * F <= 0x7fffffff / 2, AVHOT_ERR_INVALID, "frame_hidden: B*F too large for one call");
+  if (precision == AVHOT_PREC_TC && frames_u8 && h->wq_f16 &&
+      gemm_u8_pair_tc_supported(frames_u8, h->frame_dim, h->hidden_dim, h->frame_dim))
+    return gemm_u8_pair_tc(frames_u8, h->frame_dim, h->wq_f16, h->mlp_b, h->wq_inv, hid, h->hidden_dim, B * F, h->hidden_dim,
+                           h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");
   if (precision == AVHOT_PREC_TC && frames_u8 && h->wq_f16 && gemm_u8_tc_supported(frames_u8, h->frame_dim, h->hidden_dim, h->frame_dim))
     return gemm_u8_tc(frames_u8, h->frame_dim, h->wq_f16, h->mlp_b, h->wq_inv, hid, h->hidden_dim, B * F, h->hidden_dim,
                       h->frame_dim, ACT_RELU, as_stream(stream), "frame_gemm");

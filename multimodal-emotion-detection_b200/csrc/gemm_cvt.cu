@@ -1,5 +1,5 @@
-// FrameEncoder's Linear + ReLU on fp32 frames (AVHOT_PREC_TC path of a4, src/encoders.py:225-229) as an fp16 tensor-core
-// GEMM with the conversion inside the kernel, on CTA pairs:
+// FrameEncoder's Linear + ReLU on fp32 frames - and, with U8 = true, on uint8 pixels - (AVHOT_PREC_TC path of a4,
+// src/encoders.py:225-229) as an fp16 tensor-core GEMM with the conversion inside the kernel, on CTA pairs:
 //     C[M, 256] = relu( (fp16(A[M, K]) x Wq[256, K]^T) * c / s + bias ),   Wq = fp16(W s / 255) (gemm_u8.cu), c = 255
 // Why not kind::tf32 on the fp32 operands (gemm_tc.cu): that kernel streams the fp32 WEIGHTS next to the frames - per
 // 64-column k-block 64 KB of weights from L2 for 32 KB of frames from HBM, 45 B/clk per SM, the ingest limit of an SM -
@@ -7,6 +7,8 @@
 // fp16 (32 KB per k-block) and a CTA pair (cta_group::2, M = 256) shares them: each CTA loads 128 of the 256 weight
 // rows, 16 KB per k-block against its 32 KB of frames.  fp16 keeps 11 significant bits of a frame value (TF32: 10) and
 // runs at twice the TF32 rate.  Frame values must be fp16-representable in magnitude (|x| < 65504; pixels / 255 are).
+// uint8 pixels (c = 1; exact in fp16, PRMT + HSUB2 as in gemm_u8.cu, whose single-CTA kernel was bound by the same
+// weight stream: 32 KB of weights per 8 KB of pixels) take the same pair structure: a raw stage is then two k-blocks.
 //
 // Persistent pair (one CTA per SM, grid-stride over 256-row tiles), 12 warps per CTA:
 //   warp 0      TMA producer: fp32 boxes (128 rows x 32 floats, 128-byte swizzle), two per k-block, 3-stage ring; this CTA's
@@ -28,7 +30,8 @@ namespace tc {
 constexpr int VBM = 128, VBN = 256, VRAW = 3, VCV = 3, VWS = 4, VTHREADS = 384;
 
 struct GemmCvtSmem {
-  float raw[VRAW][2][VBM * 32];     // a k-block of fp32 frames as two TMA boxes (columns 0-31, 32-63)
+  float raw[VRAW][2][VBM * 32];     // fp32: a k-block as two TMA boxes (columns 0-31, 32-63); u8: raw[s][0] = one box of
+                                    // 128 rows x 128 pixels = two k-blocks
   __half cv[VCV][VBM * 64];         // converted A k-block (this CTA's 128 rows)
   __half w[VWS][(VBN / 2) * 64];    // this CTA's 128 weight rows of a k-block
   float bias[VBN];
@@ -37,6 +40,7 @@ struct GemmCvtSmem {
 };
 static_assert(sizeof(GemmCvtSmem) + 1024 <= 227 * 1024, "one CTA per SM");
 
+template <bool U8>
 __global__ void __launch_bounds__(VTHREADS, 1)
 gemm_cvt_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                          const float* __restrict__ bias, const float* __restrict__ inv_scale, float scale_mul,
@@ -72,12 +76,20 @@ gemm_cvt_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t ur = 0, uw = 0;
       for (int pt = pair; pt < n_ptiles; pt += n_pairs) {
         const int m0 = pt * 2 * VBM + (int)crank * VBM;
-        for (int kb = 0; kb < nkb; ++kb, ++ur, ++uw) {
-          const int s = ur % VRAW;
-          mbar_wait(&sm.raw_empty[s], ((ur / VRAW) & 1u) ^ 1u);
-          mbar_expect_tx(&sm.raw_full[s], (uint32_t)sizeof(sm.raw[0]));
-          tma_load_2d(sm.raw[s][0], &tmA, &sm.raw_full[s], kb * 64, m0);
-          tma_load_2d(sm.raw[s][1], &tmA, &sm.raw_full[s], kb * 64 + 32, m0);
+        for (int kb = 0; kb < nkb; ++kb, ++uw) {
+          if (!U8 || (kb & 1) == 0) {
+            const int s = ur % VRAW;
+            mbar_wait(&sm.raw_empty[s], ((ur / VRAW) & 1u) ^ 1u);
+            if (U8) {
+              mbar_expect_tx(&sm.raw_full[s], (uint32_t)sizeof(sm.raw[0][0]));
+              tma_load_2d(sm.raw[s][0], &tmA, &sm.raw_full[s], kb * 64, m0);        // 128 pixels = k-blocks kb, kb + 1
+            } else {
+              mbar_expect_tx(&sm.raw_full[s], (uint32_t)sizeof(sm.raw[0]));
+              tma_load_2d(sm.raw[s][0], &tmA, &sm.raw_full[s], kb * 64, m0);
+              tma_load_2d(sm.raw[s][1], &tmA, &sm.raw_full[s], kb * 64 + 32, m0);
+            }
+            ++ur;
+          }
           const int sw = uw % VWS;
           mbar_wait(&sm.w_empty[sw], ((uw / VWS) & 1u) ^ 1u);
           if (leader) mbar_expect_tx(&sm.w_full[sw], 2u * (uint32_t)sizeof(sm.w[0]));
@@ -111,34 +123,59 @@ gemm_cvt_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ---- converters: thread = row of this CTA's tile
     const int r = (warp - 8) * 32 + lane, sw7 = r & 7;
     const uint32_t cv_full0 = cluster_map_shared(&sm.cv_full[0], 0);
-    uint32_t ur = 0;
+    uint32_t ur = 0, uc = 0;
+    const uint32_t k1024 = 0x64006400u;               // half2(1024, 1024)
     for (int pt = pair; pt < n_ptiles; pt += n_pairs)
-      for (int kb = 0; kb < nkb; ++kb, ++ur) {
-        const int s = ur % VRAW, sc = ur % VCV;
-        mbar_wait(&sm.raw_full[s], (ur / VRAW) & 1u);
-        mbar_wait(&sm.cv_empty[sc], ((ur / VCV) & 1u) ^ 1u);
+      for (int kb = 0; kb < nkb; ++kb, ++uc) {
+        const int s = ur % VRAW, sc = uc % VCV;
+        if (!U8 || (kb & 1) == 0) mbar_wait(&sm.raw_full[s], (ur / VRAW) & 1u);
+        mbar_wait(&sm.cv_empty[sc], ((uc / VCV) & 1u) ^ 1u);
         unsigned char* crow = reinterpret_cast<unsigned char*>(sm.cv[sc]) + r * 128;
+        if (U8) {
+          const unsigned char* rrow = reinterpret_cast<const unsigned char*>(sm.raw[s][0]) + r * 128;
+          const int half = kb & 1;
 #pragma unroll
-        for (int bx = 0; bx < 2; ++bx) {
-          const unsigned char* rrow = reinterpret_cast<const unsigned char*>(sm.raw[s][bx]) + r * 128;
+          for (int c = 0; c < 4; ++c) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rrow + (((half * 4 + c) ^ sw7) << 4));   // 16 pixels
+            const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+            uint32_t h[8];
 #pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            const float4 f0 = *reinterpret_cast<const float4*>(rrow + ((c ^ sw7) << 4));
-            const float4 f1 = *reinterpret_cast<const float4*>(rrow + (((c + 1) ^ sw7) << 4));
-            const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
-            const __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
-            // floats bx*32 + 4c .. + 7 of the k-block = its 16-byte fp16 chunk bx*4 + c/2
-            *reinterpret_cast<uint4*>(crow + (((bx * 4 + (c >> 1)) ^ sw7) << 4)) =
-                make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                           *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+            for (int e = 0; e < 4; ++e) {
+              // bytes (k0, 0x64, k1, 0x64) = half2(1024 + k0, 1024 + k1); minus 1024 is exact
+              const uint32_t lo = __byte_perm(wv[e], 0x64646464u, 0x4140), hi = __byte_perm(wv[e], 0x64646464u, 0x4342);
+              const __half2 a = __hsub2(*reinterpret_cast<const __half2*>(&lo), *reinterpret_cast<const __half2*>(&k1024));
+              const __half2 bq = __hsub2(*reinterpret_cast<const __half2*>(&hi), *reinterpret_cast<const __half2*>(&k1024));
+              h[2 * e] = *reinterpret_cast<const uint32_t*>(&a);
+              h[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&bq);
+            }
+            *reinterpret_cast<uint4*>(crow + (((2 * c) ^ sw7) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(crow + (((2 * c + 1) ^ sw7) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+          }
+        } else {
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx) {
+            const unsigned char* rrow = reinterpret_cast<const unsigned char*>(sm.raw[s][bx]) + r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              const float4 f0 = *reinterpret_cast<const float4*>(rrow + ((c ^ sw7) << 4));
+              const float4 f1 = *reinterpret_cast<const float4*>(rrow + (((c + 1) ^ sw7) << 4));
+              const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
+              const __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
+              // floats bx*32 + 4c .. + 7 of the k-block = its 16-byte fp16 chunk bx*4 + c/2
+              *reinterpret_cast<uint4*>(crow + (((bx * 4 + (c >> 1)) ^ sw7) << 4)) =
+                  make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                             *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+            }
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
+        const bool raw_done = !U8 || (kb & 1) == 1 || kb == nkb - 1;
         if (lane == 0) {
           mbar_arrive_cluster(cv_full0 + (uint32_t)sc * 8u);
-          mbar_arrive(&sm.raw_empty[s]);
+          if (raw_done) mbar_arrive(&sm.raw_empty[s]);
         }
+        if (raw_done) ++ur;
       }
   } else if (warp >= 4) {
     // ---- epilogue: thread = output row of this CTA's half of the tile
@@ -187,25 +224,32 @@ gemm_cvt_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 }  // namespace tc
 
+bool gemm_u8_pair_tc_supported(const uint8_t* a, int lda, int N, int K) {
+  static const bool off = [] { const char* e = getenv("AVHOT_FRAME_U8_PAIR"); return e && atoi(e) == 0; }();
+  return !off && N == tc::VBN && K > 0 && (K % 128) == 0 && (lda % 16) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+}
+
 bool gemm_f32cvt_tc_supported(const float* a, int lda, int N, int K) {
   static const bool off = [] { const char* e = getenv("AVHOT_FRAME_CVT"); return e && atoi(e) == 0; }();
   return !off && N == tc::VBN && K > 0 && (K % 64) == 0 && (lda % 4) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
 }
 
-// wq_f16 / inv_scale_dev: gemm_u8_pack_weights (Wq = fp16(W s / 255)); scale_mul = 255 undoes the pixel scaling
-int gemm_f32cvt_tc(const float* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float scale_mul,
-                   float* c, int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name) {
+// wq_f16 / inv_scale_dev: gemm_u8_pack_weights (Wq = fp16(W s / 255)); scale_mul = 255 undoes the pixel scaling for fp32
+// frames; a_u8 != NULL: uint8 pixels (scale_mul = 1)
+static int gemm_cvt_launch(const float* a_f32, const uint8_t* a_u8, int lda, const void* wq_f16, const float* bias,
+                           const float* inv_scale_dev, float scale_mul, float* c, int ldc, int M, int N, int K, int act,
+                           cudaStream_t s, const char* prof_name) {
   using namespace tc;
-  AVHOT_REQUIRE(a && wq_f16 && inv_scale_dev && c && M >= 0, AVHOT_ERR_INVALID, "gemm_f32cvt_tc: bad arguments");
-  AVHOT_REQUIRE(gemm_f32cvt_tc_supported(a, lda, N, K), AVHOT_ERR_UNSUPPORTED, "gemm_f32cvt_tc: N must be 256, K a multiple of 64");
   if (M == 0) return AVHOT_OK;
   CUtensorMap tmA, tmW;
-  int rc = make_tensor_map_2d(&tmA, a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)lda, VBM, 32);
+  int rc = a_u8 ? make_tensor_map_2d(&tmA, a_u8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (uint64_t)M, (uint64_t)K, (uint64_t)lda, VBM, 128)
+                : make_tensor_map_2d(&tmA, a_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)lda, VBM, 32);
   if (rc != AVHOT_OK) return rc;
   rc = make_tensor_map_2d(&tmW, wq_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K, VBN / 2, 64);
   if (rc != AVHOT_OK) return rc;
   const int smem = (int)sizeof(GemmCvtSmem) + 1024;
-  AVHOT_CUDA(cudaFuncSetAttribute(gemm_cvt_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  auto kern = a_u8 ? gemm_cvt_f16_pair_kernel<true> : gemm_cvt_f16_pair_kernel<false>;
+  AVHOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_ptiles = ceil_div(M, 2 * VBM);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * min(n_ptiles, num_sms() / 2)));
@@ -220,9 +264,23 @@ int gemm_f32cvt_tc(const float* a, int lda, const void* wq_f16, const float* bia
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(prof_name, s);
-  AVHOT_CUDA(cudaLaunchKernelEx(&cfg, gemm_cvt_f16_pair_kernel, tmA, tmW, bias, inv_scale_dev, scale_mul, c, ldc, M, K, act));
+  AVHOT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, bias, inv_scale_dev, scale_mul, c, ldc, M, K, act));
   AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
+}
+
+int gemm_f32cvt_tc(const float* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float scale_mul,
+                   float* c, int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name) {
+  AVHOT_REQUIRE(a && wq_f16 && inv_scale_dev && c && M >= 0, AVHOT_ERR_INVALID, "gemm_f32cvt_tc: bad arguments");
+  AVHOT_REQUIRE(gemm_f32cvt_tc_supported(a, lda, N, K), AVHOT_ERR_UNSUPPORTED, "gemm_f32cvt_tc: N must be 256, K a multiple of 64");
+  return gemm_cvt_launch(a, nullptr, lda, wq_f16, bias, inv_scale_dev, scale_mul, c, ldc, M, N, K, act, s, prof_name);
+}
+
+int gemm_u8_pair_tc(const uint8_t* a, int lda, const void* wq_f16, const float* bias, const float* inv_scale_dev, float* c,
+                    int ldc, int M, int N, int K, int act, cudaStream_t s, const char* prof_name) {
+  AVHOT_REQUIRE(a && wq_f16 && inv_scale_dev && c && M >= 0, AVHOT_ERR_INVALID, "gemm_u8_pair_tc: bad arguments");
+  AVHOT_REQUIRE(gemm_u8_pair_tc_supported(a, lda, N, K), AVHOT_ERR_UNSUPPORTED, "gemm_u8_pair_tc: N must be 256, K a multiple of 128");
+  return gemm_cvt_launch(nullptr, a, lda, wq_f16, bias, inv_scale_dev, 1.f, c, ldc, M, N, K, act, s, prof_name);
 }
 
 }  // namespace avhot
