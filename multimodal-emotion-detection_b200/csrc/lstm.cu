@@ -44,18 +44,26 @@ constexpr int LH = 256;  // hidden size this kernel is specialised for (one thre
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
-// W_hh is streamed through shared memory: chunks of WKC k-rows (WKC x 4 gates x 256 units = 32 KB, contiguous in the
-// k-major copy) travel global/L2 -> shared with cp.async into a ring of NB buffers, NB - 1 chunks ahead of the FMAs, one
-// block barrier per chunk.  (Reading W with per-thread __ldg left two warps per scheduler waiting on L2 round trips:
-// 111 k cycles per step measured at BT = 12 against 25 k of FMAs, whatever the unroll depth.)  The ring is as deep as
-// shared memory allows (6 buffers up to 12 clips per CTA): with 3 buffers a chunk was requested two chunk periods
-// before its use and the period could not drop below half an L2 round trip (0.56 us per chunk at BT = 4, where the
-// FMAs take 0.14; 0.88 us at BT = 12 against 0.45).  Sharing one stream per cluster of four CTAs by TMA multicast,
-// with the hardware cluster barrier guarding buffer reuse, was measured slower (a cluster barrier round per 0.45 us
-// chunk: 1.29 us per chunk) - the kernel was never L2-bandwidth-bound.
-constexpr int WKC = 8, WCHUNKS = LH / WKC;
+// W_hh is streamed through shared memory: chunks of KC k-rows (KC x 256 units x 4 gates; 64 KB at KC = 16, contiguous in
+// the [k][j][gate] copy) travel global/L2 -> shared with cp.async into a ring of NB buffers, NB - 1 chunks ahead of the
+// FMAs, one block barrier per chunk.  (Reading W with per-thread __ldg left two warps per scheduler waiting on L2 round
+// trips: 111 k cycles per step measured at BT = 12 against 25 k of FMAs, whatever the unroll depth.)
+//
+// Thread = hidden unit j, all BT clips of the tile: per k-row one 128-bit load of the unit's four gate weights, BT / 4
+// broadcast loads of h_{t-1}[k], and 4 x BT / 2 FFMA2 (fma.rn.f32x2 over clip pairs: each half rounds exactly like fmaf).
+// The shape was settled with tools/micro/rec_loop.cu, which runs this loop in isolation: 512 threads with the clips split
+// in halves read 96 shared-memory wavefronts per row - as many cycles as the 96 of the FFMA2s - and reached 117 cycles
+// per row, 144 with a barrier every 8 rows, 191 in the real kernel; one thread per unit halves the wavefronts (56) and,
+// with the next row's operands fetched into a second register set BEFORE this row's FMAs (ptxas otherwise sinks each
+// load to within a few instructions of its use, and two warps per scheduler cannot cover that), reaches 107 cycles per
+// row, 112 with a barrier every 16 rows.  Measured in the kernel: 15.5 -> 13.5 ms for the two layers of a 1 565-clip
+// flush (166 cycles per row: the weight stream, the step's activations and xp loads are on top of the isolated loop).
+// Tried on top and dropped: a producer warp feeding the ring with TMA bulk copies, multicast to a cluster of two CTAs
+// (half the L2 traffic) and mbarrier hand-shakes instead of the block barrier - bit-identical, slower with or without
+// the multicast, so the kernel is not L2-bound at this rate either; fetching xp a step ahead - no change.
+constexpr int lstm_chunk_rows(int BT) { return BT <= 12 ? 16 : 8; }
 constexpr int lstm_ring_depth(int BT) {
-  const int room = (227 * 1024 - 1024 - (int)sizeof(float) * 2 * LH * 2 * ((BT / 2 + 3) & ~3)) / ((int)sizeof(float) * WKC * 4 * LH);
+  const int room = (227 * 1024 - 1024 - (int)sizeof(float) * 2 * LH * (BT + 4)) / ((int)sizeof(float) * lstm_chunk_rows(BT) * 4 * LH);
   return room > 6 ? 6 : room;
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -67,94 +75,87 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// 512 threads: thread = (hidden unit j, half of the tile's clips).  With 256 threads (one per unit, all BT clips) an
-// SM held two warps per scheduler and ncu showed no eligible warp 39 % of the time at 61 % issue-slot use (FMA pipe
-// 44 %): four warps per scheduler hide each other's shared-memory and barrier latency.  The four gate weights of
-// (k, j) are one 128-bit shared load ([k][j][gate] copy of W_hh).
-__host__ __device__ constexpr int lstm_half_pad(int BT) { return (BT / 2 + 3) & ~3; }     // floats per half of an hs row (128-bit loads)
-template <int BT, int NB = lstm_ring_depth(BT)>
-__global__ void __launch_bounds__(2 * LH)
+template <int BT, int KC = lstm_chunk_rows(BT), int NB = lstm_ring_depth(BT)>
+__global__ void __launch_bounds__(LH, 1)
 lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
                        const float* __restrict__ whh_t,   // [H][H][4]: [k][j][gate] = W_hh[gate*H + j][k]
                        float* __restrict__ h_seq,         // (B, T, H) or NULL
                        float* __restrict__ h_last,        // (B, H) or NULL
                        const int32_t* __restrict__ lengths,  // (B) valid steps per clip, or NULL (= T)
                        int B, int T) {
-  static_assert(BT % 2 == 0, "two halves");
-  constexpr int CH = BT / 2, CHP = lstm_half_pad(BT), HP = 2 * CHP;
+  static_assert(BT % 4 == 0 && NB >= 3, "clip quads; ring: the chunk in use, one landing, one being requested");
+  constexpr int HP = BT + 4;  // padded row: conflict-free 128-bit stores of one unit's BT values
+  constexpr int NCH = LH / KC;
   extern __shared__ __align__(16) unsigned char lstm_smem_raw[];
   float (*hs)[LH][HP] = reinterpret_cast<float (*)[LH][HP]>(lstm_smem_raw);   // [2][LH][HP]
-  float4 (*wb)[WKC][LH] = reinterpret_cast<float4 (*)[WKC][LH]>(lstm_smem_raw + sizeof(float) * 2 * LH * HP);  // [NB]
-  static_assert(NB >= 3, "ring: the chunk in use, one landing, one being requested");
-  const int j = threadIdx.x & (LH - 1), half = threadIdx.x >> 8;      // warps 0-7: clips [0, CH), warps 8-15: [CH, BT)
-  const int b0 = blockIdx.x * BT + half * CH;
-  // chunk n of the endless stream (n = t * WCHUNKS + c) -> ring buffer n % NB; every thread copies 4 x 16 bytes
+  float4 (*wb)[KC][LH] = reinterpret_cast<float4 (*)[KC][LH]>(lstm_smem_raw + sizeof(float) * 2 * LH * HP);  // [NB]
+  const int j = threadIdx.x;
+  const int b0 = blockIdx.x * BT;
+  // chunk n of the endless stream (n = t * NCH + c) -> ring buffer n % NB; every thread copies KC x 16 bytes
   auto issue = [&](int n) {
-    const float* src = whh_t + (size_t)(n % WCHUNKS) * (WKC * 4 * LH);
+    const float* src = whh_t + (size_t)(n % NCH) * (KC * 4 * LH);
     float* dst = reinterpret_cast<float*>(&wb[n % NB][0][0]);
 #pragma unroll
-    for (int i = 0; i < WKC * 4 * LH / 4 / (2 * LH); ++i)
-      cp_async16(dst + 4 * (threadIdx.x + i * 2 * LH), src + 4 * (threadIdx.x + i * 2 * LH));
+    for (int i = 0; i < KC; ++i) cp_async16(dst + 4 * (j + i * LH), src + 4 * (j + i * LH));
     cp_async_commit();
   };
-  const int n_total = T * WCHUNKS;
+  const int n_total = T * NCH;
 #pragma unroll
   for (int i = 0; i < NB - 1; ++i) {
     if (i < n_total) issue(i); else cp_async_commit();
   }
-  float c[CH];
+  float c[BT];
 #pragma unroll
-  for (int b = 0; b < CH; ++b) {
+  for (int b = 0; b < BT; ++b) {
     c[b] = 0.f;
-    hs[0][j][half * CHP + b] = 0.f;
+    hs[0][j][b] = 0.f;
   }
   __syncthreads();
   int n = 0;
   for (int t = 0; t < T; ++t) {
     const int cur = t & 1;
-    // Accumulators as fp32 pairs over clips: one FFMA2 (fma.rn.f32x2, sm_100) does acc[g][b], acc[g][b + 1] += w[g] * h[b],
-    // h[b + 1] - each half rounded exactly like fmaf, so results are unchanged - with half the instructions and 64-bit
-    // aligned register operands (the scalar FFMA stream ran at 45 % of the FMA pipe on register-bank conflicts).
-    static_assert(CH % 2 == 0, "clip pairs");
-    float2 acc[4][CH / 2];
+    float2 acc[4][BT / 2];
 #pragma unroll
-    for (int b = 0; b < CH; b += 2) {
+    for (int b = 0; b < BT; b += 2) {
       const float* x0 = xp + ((size_t)min(b0 + b, B - 1) * T + t) * (4 * LH) + j;
       const float* x1 = xp + ((size_t)min(b0 + b + 1, B - 1) * T + t) * (4 * LH) + j;
 #pragma unroll
       for (int g = 0; g < 4; ++g) acc[g][b / 2] = make_float2(__ldg(x0 + g * LH), __ldg(x1 + g * LH));
     }
 #pragma unroll 1
-    for (int ch = 0; ch < WCHUNKS; ++ch, ++n) {
+    for (int ch = 0; ch < NCH; ++ch, ++n) {
       cp_async_wait<NB - 2>();            // this thread's part of chunk n has landed (NB - 2 later ones may be in flight)
       __syncthreads();                    // ... and everybody's; everybody is also done with chunk n - 1's buffer
       if (n + NB - 1 < n_total) issue(n + NB - 1); else cp_async_commit();   // (empty group: keeps the wait count uniform)
       const float4* w = wb[n % NB][0];
+      const float (*hrow)[HP] = &hs[cur][ch * KC];
+      float4 wq[2], hq[2][BT / 4];
+      wq[0] = w[j];
 #pragma unroll
-      for (int kk = 0; kk < WKC; ++kk) {
-        const int k = ch * WKC + kk;
-        const float4 w4 = w[kk * LH + j];
+      for (int q = 0; q < BT / 4; ++q) hq[0][q] = *reinterpret_cast<const float4*>(&hrow[0][4 * q]);
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        if (kk + 1 < KC) {                // the next row's operands, before this row's FMAs
+          wq[(kk + 1) & 1] = w[(kk + 1) * LH + j];
+#pragma unroll
+          for (int q = 0; q < BT / 4; ++q) hq[(kk + 1) & 1][q] = *reinterpret_cast<const float4*>(&hrow[kk + 1][4 * q]);
+        }
+        const float4 w4 = wq[kk & 1];
         const float2 wg[4] = {make_float2(w4.x, w4.x), make_float2(w4.y, w4.y), make_float2(w4.z, w4.z), make_float2(w4.w, w4.w)};
-        float2 hv[CHP / 2];
 #pragma unroll
-        for (int b4 = 0; b4 < CHP; b4 += 4) {
-          if (CH - b4 >= 3) {
-            const float4 v = *reinterpret_cast<const float4*>(&hs[cur][k][half * CHP + b4]);
-            hv[b4 / 2] = make_float2(v.x, v.y); hv[b4 / 2 + 1] = make_float2(v.z, v.w);
-          } else {
-            const float2 v = *reinterpret_cast<const float2*>(&hs[cur][k][half * CHP + b4]);
-            hv[b4 / 2] = v;
+        for (int q = 0; q < BT / 4; ++q) {
+          const float4 h4 = hq[kk & 1][q];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            acc[g][2 * q] = __ffma2_rn(wg[g], make_float2(h4.x, h4.y), acc[g][2 * q]);
+            acc[g][2 * q + 1] = __ffma2_rn(wg[g], make_float2(h4.z, h4.w), acc[g][2 * q + 1]);
           }
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int b = 0; b < CH / 2; ++b) acc[g][b] = __ffma2_rn(wg[g], hv[b], acc[g][b]);
       }
     }
-    float hn[CH];
+    float hn[BT];
 #pragma unroll
-    for (int b = 0; b < CH; ++b) {
+    for (int b = 0; b < BT; ++b) {
       const float a0 = (b & 1) ? acc[0][b / 2].y : acc[0][b / 2].x, a1 = (b & 1) ? acc[1][b / 2].y : acc[1][b / 2].x;
       const float a2 = (b & 1) ? acc[2][b / 2].y : acc[2][b / 2].x, a3 = (b & 1) ? acc[3][b / 2].y : acc[3][b / 2].x;
       const float ig = sigmoid_acc(a0), fg = sigmoid_acc(a1);
@@ -163,15 +164,16 @@ lstm_recurrence_kernel(const float* __restrict__ xp,      // (B, T, 4H)
       hn[b] = og * tanhf(c[b]);
     }
 #pragma unroll
-    for (int b = 0; b < CH; ++b) hs[cur ^ 1][j][half * CHP + b] = hn[b];
+    for (int b4 = 0; b4 < BT; b4 += 4)
+      *reinterpret_cast<float4*>(&hs[cur ^ 1][j][b4]) = make_float4(hn[b4], hn[b4 + 1], hn[b4 + 2], hn[b4 + 3]);
     if (h_seq) {
 #pragma unroll
-      for (int b = 0; b < CH; ++b)
+      for (int b = 0; b < BT; ++b)
         if (b0 + b < B) h_seq[((size_t)(b0 + b) * T + t) * LH + j] = hn[b];
     }
     if (h_last) {
 #pragma unroll
-      for (int b = 0; b < CH; ++b)
+      for (int b = 0; b < BT; ++b)
         if (b0 + b < B) {   // h_n = state after the clip's last valid step (packed sequences, src/encoders.py:139-147)
           const int last_t = (lengths ? min(max(__ldg(lengths + b0 + b), 1), T) : T) - 1;
           if (t == last_t) h_last[(size_t)(b0 + b) * LH + j] = hn[b];
@@ -564,10 +566,10 @@ static int lstm_forward_impl(avhot_lstm_t h, const float* seq, const void* seq_s
     const int want = 4 * ceil_div(B, 4 * num_sms());
 #define AVHOT_REC_CASE(BT_)                                                                                        \
   case BT_: {                                                                                                       \
-    const size_t smem = sizeof(float) * (2 * LH * 2 * lstm_half_pad(BT_) + (size_t)lstm_ring_depth(BT_) * WKC * 4 * LH); \
+    const size_t smem = sizeof(float) * (2 * LH * (BT_ + 4) + (size_t)lstm_ring_depth(BT_) * lstm_chunk_rows(BT_) * 4 * LH); \
     AVHOT_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<BT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                     (int)smem));                                                                    \
-    lstm_recurrence_kernel<BT_><<<ceil_div(B, BT_), 2 * LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T); \
+    lstm_recurrence_kernel<BT_><<<ceil_div(B, BT_), LH, smem, s>>>(xp, h->w_hh_t[l], hs_out, hl_out, lengths, B, T); \
     break;                                                                                                          \
   }
     switch (want >= 32 ? 32 : want) {
