@@ -113,11 +113,9 @@ lstm_rec_cs_kernel(const float* __restrict__ xp,      // (B, T, 4H)
     // arm the barrier that will collect h_t (buffer cur ^ 1), then wait for all of h_{t-1} (buffer cur; zeros at t = 0)
     if (tid == 0 && t + 1 < T) tc::mbar_expect_tx(&hbar[cur ^ 1], H_BYTES);
     if (t > 0) tc::mbar_wait_cluster(&hbar[cur], (uint32_t)((t - 1) >> 1) & 1u);
-#pragma unroll 8
-    for (int k = 0; k < CSH; ++k) {
-      const float4 w4 = ws[k][u];
-      const float wg[4] = {w4.x, w4.y, w4.z, w4.w};
-      float hv[CT];
+    // the next row's operands are fetched into a second register set before this row's FMAs (ptxas otherwise leaves each
+    // shared load a few instructions in front of its use, which the few warps of a scheduler cannot cover)
+    auto load_h = [&](int k, float (&hv)[CT]) {
       if (CT % 4 == 0) {
 #pragma unroll
         for (int b4 = 0; b4 < CT; b4 += 4) {
@@ -134,10 +132,23 @@ lstm_rec_cs_kernel(const float* __restrict__ xp,      // (B, T, 4H)
 #pragma unroll
         for (int b = 0; b < CT; ++b) hv[b] = hs[cur][k][grp * CT + b];
       }
+    };
+    float4 wq[2];
+    float hq[2][CT];
+    wq[0] = ws[0][u];
+    load_h(0, hq[0]);
+#pragma unroll 8
+    for (int k = 0; k < CSH; ++k) {
+      if (k + 1 < CSH) {
+        wq[(k + 1) & 1] = ws[k + 1][u];
+        load_h(k + 1, hq[(k + 1) & 1]);
+      }
+      const float4 w4 = wq[k & 1];
+      const float wg[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int b = 0; b < CT; ++b) acc[g][b] = fmaf(wg[g], hv[b], acc[g][b]);
+        for (int b = 0; b < CT; ++b) acc[g][b] = fmaf(wg[g], hq[k & 1][b], acc[g][b]);
     }
     float hn[CT];
 #pragma unroll
