@@ -70,12 +70,22 @@ gemm_f32_kernel(const float* __restrict__ A, const uint8_t* __restrict__ A8, int
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) load_tiles((kt + 1) * GBK);
+    // fragments of row k + 1 are fetched into a second register set before the FMAs of row k (ptxas otherwise leaves the
+    // shared loads a few instructions in front of their first use: tools/micro/rec_loop.cu)
+    float4 fa[2][2], fb[2][2];
+    fa[0][0] = *reinterpret_cast<const float4*>(&As[buf][0][ty * 4]);
+    fa[0][1] = *reinterpret_cast<const float4*>(&As[buf][0][64 + ty * 4]);
+    fb[0][0] = *reinterpret_cast<const float4*>(&Ws[buf][0][tx * 4]);
+    fb[0][1] = *reinterpret_cast<const float4*>(&Ws[buf][0][64 + tx * 4]);
 #pragma unroll
     for (int k = 0; k < GBK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Ws[buf][k][64 + tx * 4]);
+      if (k + 1 < GBK) {
+        fa[(k + 1) & 1][0] = *reinterpret_cast<const float4*>(&As[buf][k + 1][ty * 4]);
+        fa[(k + 1) & 1][1] = *reinterpret_cast<const float4*>(&As[buf][k + 1][64 + ty * 4]);
+        fb[(k + 1) & 1][0] = *reinterpret_cast<const float4*>(&Ws[buf][k + 1][tx * 4]);
+        fb[(k + 1) & 1][1] = *reinterpret_cast<const float4*>(&Ws[buf][k + 1][64 + tx * 4]);
+      }
+      const float4 a0 = fa[k & 1][0], a1 = fa[k & 1][1], b0 = fb[k & 1][0], b1 = fb[k & 1][1];
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
