@@ -1052,7 +1052,8 @@ static int fusion_forward_impl(avhot_fusion_t h, const float* const* z_host_arra
         fusion_clip_kernel<<<ceil_div(B, FRT), FTHREADS, 0, s>>>(P, clipbuf);
         AVHOT_LAUNCH_CHECK();
       }
-      if (precision == AVHOT_PREC_TC && h->tc_w) {
+      // (the tensor-core kernel reads the per-clip vectors with 128-bit loads: an unaligned caller workspace takes the fp32 pass kernel)
+      if (precision == AVHOT_PREC_TC && h->tc_w && (reinterpret_cast<uintptr_t>(clipbuf) & 15) == 0) {
         FusTcParams Q;
         Q.z_v = P.z[1]; Q.rpc_v = P.rpc[1]; Q.dim_v = P.dim[1];
         Q.clipbuf = clipbuf; Q.mask = mask; Q.logits = logits;

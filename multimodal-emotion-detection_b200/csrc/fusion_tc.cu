@@ -300,11 +300,18 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
               uint32_t a[32];
               tmem_ld32(tl + (uint32_t)c, a);
               tmem_ld_wait();
+              // (the per-clip vectors are 16-byte aligned: 128-bit loads - as scalars they were 195 LDG sites, most of the
+              // kernel's long-scoreboard stalls with two warps per scheduler)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float q = __ldg(cbuf + 1 * UD + c + j);
-                sa = fmaf(q, __ldg(cbuf + 2 * UD + c + j), sa);
-                sv = fmaf(q, __uint_as_float(a[j]) + V[VEC_BK0 + c + j], sv);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(cbuf + 1 * UD + c + j));
+                const float4 k4 = __ldg(reinterpret_cast<const float4*>(cbuf + 2 * UD + c + j));
+                const float q[4] = {q4.x, q4.y, q4.z, q4.w}, kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  sa = fmaf(q[e], kk[e], sa);
+                  sv = fmaf(q[e], __uint_as_float(a[j + e]) + V[VEC_BK0 + c + j + e], sv);
+                }
               }
             }
             aa[hh] = sa; av[hh] = sv;
@@ -322,10 +329,15 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
               tmem_ld32(tl + 256u + (uint32_t)c, k);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float q = __uint_as_float(a[j]) + V[VEC_BQ1 + c + j];
-                sa = fmaf(q, __ldg(cbuf + 4 * UD + c + j), sa);
-                sv = fmaf(q, __uint_as_float(k[j]) + V[VEC_BK1 + c + j], sv);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 k4 = __ldg(reinterpret_cast<const float4*>(cbuf + 4 * UD + c + j));
+                const float ka[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float q = __uint_as_float(a[j + e]) + V[VEC_BQ1 + c + j + e];
+                  sa = fmaf(q, ka[e], sa);
+                  sv = fmaf(q, __uint_as_float(k[j + e]) + V[VEC_BK1 + c + j + e], sv);
+                }
               }
             }
             aa[hh] = sa; av[hh] = sv;
@@ -373,8 +385,13 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
             const int hh = (c >> 6) - hb;
             float ctx[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              ctx[j] = aa[hh] * __ldg(cbuf + vslot * UD + c + j) + av[hh] * (__uint_as_float(a[j]) + V[vb + c + j]);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 v4 = __ldg(reinterpret_cast<const float4*>(cbuf + vslot * UD + c + j));
+              const float va[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                ctx[j + e] = aa[hh] * va[e] + av[hh] * (__uint_as_float(a[j + e]) + V[vb + c + j + e]);
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) *a_chunk(&sm.C[0][0], r, c + j) = pack8(&ctx[j]);
           }
@@ -392,7 +409,10 @@ fusion_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FusTcParams P) {
           auto residual = [&](int c, float (&res)[32]) {
             if (layer == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) res[j] = __ldg(cbuf + c + j);                     // Z_a
+              for (int j = 0; j < 32; j += 4) {                                             // Z_a
+                const float4 z4 = __ldg(reinterpret_cast<const float4*>(cbuf + c + j));
+                res[j] = z4.x; res[j + 1] = z4.y; res[j + 2] = z4.z; res[j + 3] = z4.w;
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {                                             // Z_v = x^ * std + mean
