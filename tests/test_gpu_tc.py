@@ -254,6 +254,36 @@ def test_u8_ingest_tc(pkg, dev, world):
     assert float(got.min()) >= 0.0                           # ReLU
 
 
+def test_u8_pair_gemm_equals_single_cta_kernel(pkg, dev, world, tmp_path):
+    """uint8 frames: the CTA-pair converting GEMM (gemm_cvt.cu, M = 256, weights shared by the pair) and its single-CTA
+    predecessor (gemm_u8.cu, AVHOT_FRAME_U8_PAIR=0, child process: the switch is read once) run the same fp16 MMA chain
+    per row: bit-identical hidden activations, odd tile counts and partial tiles included."""
+    import os
+    import subprocess
+    import sys
+    m = make_model(pkg, dev, world).set_precision("tc")
+    enc = m.encoders["video"]
+    torch.save(enc.state_dict(), tmp_path / "venc.pt")
+    outs = {}
+    for B in (1, 21, 300):
+        frames = pkg.synth.synth_video(B, 3, SEED, dev, dtype=torch.uint8)
+        outs[B] = enc.hidden(frames).cpu().numpy()
+    code = (
+        "import sys, numpy as np, torch\n"
+        "import multimodal_emotion_detection_b200 as pkg\n"
+        "d = sys.argv[1]\n"
+        "enc = pkg.FrameEncoder(12544, 256, 128, 'attention', 0.1)\n"
+        "enc.load_state_dict(torch.load(d + '/venc.pt'))\n"
+        "enc = enc.to('cuda:0').eval(); enc.precision = pkg._lib.PREC_TC\n"
+        "for B in (1, 21, 300):\n"
+        "    frames = pkg.synth.synth_video(B, 3, 42, 'cuda:0', dtype=torch.uint8)\n"
+        "    np.save(d + f'/single{B}.npy', enc.hidden(frames).cpu().numpy())\n")
+    env = dict(os.environ, AVHOT_FRAME_U8_PAIR="0", PYTHONPATH=os.pathsep.join(sys.path))
+    subprocess.run([sys.executable, "-c", code, str(tmp_path)], check=True, env=env, timeout=300)
+    for B, got in outs.items():
+        assert (got == np.load(tmp_path / f"single{B}.npy")).all(), B
+
+
 def test_fp32_frames_cvt_pair_gemm(pkg, dev, world):
     """fp32 frames on the tensor-core path: gemm_cvt.cu converts them to fp16 inside a CTA-pair GEMM (M = 256 per pair,
     fp16 weights shared).  Odd numbers of 128-row tiles (the pair's second CTA has no rows), partial tiles, more tiles
