@@ -291,29 +291,30 @@ using namespace avhot;
 // The front-end's 40 MFCC are its 64 log-mel values times the DCT matrix D (frontend.cu; a3's input is
 // [log-mel | MFCC]), so on the operand avhot_frontend_ex writes, x W_ih^T = lm (W[:, :64] + W[:, 64:] D)^T: layer 0 needs
 // only the three log-mel k-blocks [lm_hi | lm_lo | lm_hi] (K = 192 instead of 320) against W' split the same way.
-// W' is formed in double on the host, once per handle (fp32-class like the 3-term product itself).
-static int lstm_build_dct_fold(avhot_lstm* h, const float* w_ih0_dev, cudaStream_t s) {
-  const int H = h->hidden_dim, N = 4 * H, NM = 64, NC = 40;
-  std::vector<float> w((size_t)N * (NM + NC)), dct((size_t)NC * NM);
-  int rc = avhot_frontend_tables_host(nullptr, dct.data(), nullptr);
+// W' is formed in double, once per handle (fp32-class like the 3-term product itself); output row p = packed row of the
+// fused layer kernel.
+__global__ void fold_dct_kernel(const float* __restrict__ w_ih0, const float* __restrict__ dct, __half* __restrict__ out, int H) {
+  constexpr int NM = 64, NC = 40;
+  const int p = blockIdx.x, j = threadIdx.x;               // packed row, log-mel column
+  const int n = lstm_fused_src_row(p, H);
+  const double sc = (n / H) == 2 ? 1.0 : 0.5;              // sigmoid gates halved (tc_gate_scale)
+  double v = w_ih0[(size_t)n * (NM + NC) + j];
+  for (int c = 0; c < NC; ++c) v += (double)w_ih0[(size_t)n * (NM + NC) + NM + c] * (double)dct[c * NM + j];
+  const float f = (float)(sc * v);
+  const __half hi = __float2half_rn(f);
+  out[(size_t)p * 192 + j] = hi;
+  out[(size_t)p * 192 + 64 + j] = hi;
+  out[(size_t)p * 192 + 128 + j] = __float2half_rn(f - __half2float(hi));
+}
+static int lstm_build_dct_fold(avhot_lstm* h, const float* w_ih0_dev, float* dct_scratch_dev, cudaStream_t s) {
+  std::vector<float> dct(40 * 64);
+  int rc = avhot_frontend_tables_host(nullptr, dct.data(), nullptr);   // the table the front-end kernel was built from
   if (rc != AVHOT_OK) return rc;
-  AVHOT_CUDA(cudaMemcpyAsync(w.data(), w_ih0_dev, sizeof(float) * w.size(), cudaMemcpyDeviceToHost, s));
-  AVHOT_CUDA(cudaStreamSynchronize(s));
-  std::vector<__half> out((size_t)N * 192);
-  for (int p = 0; p < N; ++p) {
-    const int n = lstm_fused_src_row(p, H);
-    const double sc = (n / H) == 2 ? 1.0 : 0.5;            // sigmoid gates halved (tc_gate_scale)
-    for (int j = 0; j < NM; ++j) {
-      double v = w[(size_t)n * (NM + NC) + j];
-      for (int c = 0; c < NC; ++c) v += (double)w[(size_t)n * (NM + NC) + NM + c] * (double)dct[(size_t)c * NM + j];
-      const float f = (float)(sc * v);
-      const __half hi = __float2half_rn(f);
-      out[(size_t)p * 192 + j] = out[(size_t)p * 192 + 64 + j] = hi;
-      out[(size_t)p * 192 + 128 + j] = __float2half_rn(f - __half2float(hi));
-    }
-  }
-  AVHOT_CUDA(cudaMemcpyAsync(h->w_ih_fold_p16, out.data(), sizeof(__half) * out.size(), cudaMemcpyHostToDevice, s));
-  AVHOT_CUDA(cudaStreamSynchronize(s));                    // `out` is pageable host memory
+  AVHOT_CUDA(cudaMemcpyAsync(dct_scratch_dev, dct.data(), sizeof(float) * dct.size(), cudaMemcpyHostToDevice, s));
+  AVHOT_CUDA(cudaStreamSynchronize(s));                    // `dct` is pageable host memory
+  fold_dct_kernel<<<4 * h->hidden_dim, 64, 0, s>>>(w_ih0_dev, dct_scratch_dev, reinterpret_cast<__half*>(h->w_ih_fold_p16),
+                                                   h->hidden_dim);
+  AVHOT_LAUNCH_CHECK();
   return AVHOT_OK;
 }
 
@@ -346,7 +347,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   h->input_dim = d->input_dim; h->hidden_dim = H; h->num_layers = L; h->output_dim = d->output_dim;
   h->arena = nullptr;
   h->w_ih_fold_p16 = nullptr;
-  total += align256(2 * 4 * H * 192);
+  total += align256(2 * 4 * H * 192) + align256(sizeof(float) * 40 * 64);
   cudaError_t e = cudaMalloc(&h->arena, total);
   if (e != cudaSuccess) {
     delete h;
@@ -392,7 +393,7 @@ extern "C" int avhot_lstm_create(const avhot_lstm_desc* d, avhot_lstm_t* out, av
   }
   if (rc == AVHOT_OK && d->input_dim == 104) {
     h->w_ih_fold_p16 = take(2 * 4 * H * 192);
-    rc = lstm_build_dct_fold(h, d->weight_ih[0], s);
+    rc = lstm_build_dct_fold(h, d->weight_ih[0], take(sizeof(float) * 40 * 64), s);
   }
   if (rc == AVHOT_OK) {
     h->proj_w = take(sizeof(float) * d->output_dim * H);
